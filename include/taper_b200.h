@@ -1,0 +1,249 @@
+/* taper_b200.h — C ABI of the B200-native backend for taper's tape-evaluation hot path.
+ *
+ * This is the drop-in boundary: what a Rust `extern "C"` block in taper would bind in place of its
+ * CPU kernels (see INTEGRATION.md for the shim).  Every entry point cites the reference
+ * interface it replaces as `path:line` relative to the reference root (vaibhawvipul/taper @ aea74b46).
+ *
+ * Conventions
+ *  - Every call returns 0 (TP_OK) on success; otherwise an error code, with a thread-local
+ *    message available from tp_last_error().  The reference panics on the same conditions
+ *    (assert!/unwrap, e.g. src/ops.rs:11-15, 201-208); the host shim turns non-zero into a panic.
+ *  - No C++ exceptions cross this boundary; no torch / CUDA types appear in signatures.
+ *  - tp_ctx  : 1 host thread : 1 device : 1 CUDA stream (: 1 NCCL rank).  Thread-affine — mirrors the
+ *              reference's `thread_local!` tape (src/tape.rs:6-9).  Different contexts are independent.
+ *  - tp_buf  : intrusively refcounted device buffer of 4-byte elements (fp32 unless stated) ==
+ *              the reference's `Arc<RwLock<Vec<f32>>>` (src/tensor.rs:236-244).  The callee never
+ *              frees caller buffers.  A NULL tp_buf* for an optional argument means "absent".
+ *  - All ops are asynchronous with respect to the host and ordered on the context's stream, except
+ *    tp_buf_download / tp_sync / tp_ctx_destroy which synchronise.
+ *  - `accumulate` arguments: 0 = first touch (dst  = value, the reference's lazily zero-allocated
+ *    grad followed by `+=`, e.g. src/ops.rs:126-128), 1 = dst += value.
+ *  - Matrices are dense row-major fp32, exactly as in the reference.
+ */
+#ifndef TAPER_B200_H
+#define TAPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TP_ABI_VERSION 1
+
+enum {
+    TP_OK = 0,
+    TP_ERR_INVALID = 1,     /* shape / argument check failed (reference: assert!/panic!) */
+    TP_ERR_CUDA = 2,        /* CUDA runtime / driver error                               */
+    TP_ERR_OOM = 3,
+    TP_ERR_COMM = 4,        /* NCCL / peer-memory error                                  */
+    TP_ERR_UNSUPPORTED = 5
+};
+
+typedef struct tp_ctx tp_ctx;
+typedef struct tp_buf tp_buf;
+typedef struct tp_graph tp_graph;
+
+/* ---------------------------------------------------------------------------------------------
+ * Runtime: context, stream, buffers  (replaces Vec<f32> allocation + mimalloc, src/main.rs:7-10)
+ * ------------------------------------------------------------------------------------------- */
+int         tp_abi_version(void);
+const char* tp_last_error(void);
+int  tp_device_count(int* count);
+int  tp_ctx_create(int device, tp_ctx** out);
+int  tp_ctx_destroy(tp_ctx* ctx);
+int  tp_sync(tp_ctx* ctx);
+void* tp_ctx_stream(tp_ctx* ctx);                  /* the cudaStream_t, for interop              */
+int  tp_ctx_device(tp_ctx* ctx);
+int  tp_ctx_sm_count(tp_ctx* ctx);
+/* bytes currently handed out / bytes held by the caching allocator */
+int  tp_ctx_mem_stats(tp_ctx* ctx, size_t* in_use, size_t* reserved);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int  tp_ctx_launch_count(tp_ctx* ctx, uint64_t* count);
+
+int  tp_buf_alloc(tp_ctx* ctx, size_t n, tp_buf** out);             /* n 4-byte elements       */
+int  tp_buf_wrap(tp_ctx* ctx, void* device_ptr, size_t n, tp_buf** out); /* external, not owned */
+int  tp_buf_slice(tp_buf* parent, size_t offset, size_t n, tp_buf** out); /* view; retains parent */
+int  tp_buf_retain(tp_buf* buf);
+int  tp_buf_release(tp_buf* buf);
+void*  tp_buf_ptr(const tp_buf* buf);
+size_t tp_buf_len(const tp_buf* buf);
+int  tp_buf_upload(tp_ctx* ctx, tp_buf* dst, const void* host, size_t n);    /* Tensor::new     src/tensor.rs:470-478 */
+int  tp_buf_upload_pinned(tp_ctx* ctx, tp_buf* dst, const void* pinned_host, size_t n); /* no staging copy */
+int  tp_buf_download(tp_ctx* ctx, const tp_buf* src, void* host, size_t n);  /* Tensor::data()  src/tensor.rs:493-496 */
+int  tp_buf_copy(tp_ctx* ctx, tp_buf* dst, const tp_buf* src, size_t n);     /* Vec::clone, e.g. reshape src/tensor.rs:814 */
+int  tp_buf_fill(tp_ctx* ctx, tp_buf* dst, float value, size_t n);           /* vec![v; n], e.g. backward seed src/tensor.rs:521 */
+int  tp_host_alloc_pinned(size_t bytes, void** out);
+int  tp_host_free_pinned(void* p);
+
+/* CUDA-graph capture of everything enqueued on the context's stream between begin and end. */
+int  tp_graph_begin(tp_ctx* ctx);
+int  tp_graph_end(tp_ctx* ctx, tp_graph** out);
+int  tp_graph_launch(tp_ctx* ctx, tp_graph* g);
+int  tp_graph_destroy(tp_graph* g);
+
+/* ---------------------------------------------------------------------------------------------
+ * The reference's existing operator boundary  (src/gemm.rs:8-19 cblas / :72-83 matrixmultiply;
+ * re-exported at src/lib.rs:13).  C[m,n] = alpha*op(A)*op(B) + beta*C, row-major,
+ * lda = k (N) | m (T), ldb = n (N) | k (T), ldc = n  (src/gemm.rs:21-29).  trans: 0 = N, 1 = T.
+ * ------------------------------------------------------------------------------------------- */
+int tp_sgemm_rowmajor(tp_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, float alpha,
+                      const tp_buf* a, const tp_buf* b, float beta, tp_buf* c);
+/* GEMM math mode for the tcgen05 path: 0 = exact fp32 (CUDA-core FFMA), 1 = 3xTF32 split
+ * (fp32-accurate on the tensor cores, default), 2 = 1xTF32 (throughput mode). */
+int tp_set_gemm_mode(tp_ctx* ctx, int mode);
+int tp_get_gemm_mode(tp_ctx* ctx, int* mode);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise family  (src/tensor.rs:14-234 `pub mod simd`; src/ops.rs:8-151, 312-496)
+ * ------------------------------------------------------------------------------------------- */
+int tp_add(tp_ctx*, const tp_buf* a, const tp_buf* b, tp_buf* out, size_t n);   /* src/ops.rs:8-30   */
+int tp_sub(tp_ctx*, const tp_buf* a, const tp_buf* b, tp_buf* out, size_t n);   /* src/ops.rs:377-396 */
+int tp_mul(tp_ctx*, const tp_buf* a, const tp_buf* b, tp_buf* out, size_t n);   /* src/ops.rs:54-71  */
+int tp_div(tp_ctx*, const tp_buf* a, const tp_buf* b, tp_buf* out, size_t n);   /* src/ops.rs:440-456 */
+/* dst (+)= scale*src : accumulate_grad (scale=1) / accumulate_grad_scaled  src/ops.rs:124-151 */
+int tp_accumulate(tp_ctx*, tp_buf* dst, const tp_buf* src, float scale, size_t n, int accumulate);
+/* gdst (+)= gout*other           Mul backward  src/ops.rs:79-115 */
+int tp_mul_bwd(tp_ctx*, const tp_buf* gout, const tp_buf* other, tp_buf* gdst, size_t n, int accumulate);
+/* ga (+)= gout/b ; gb (+)= -gout*a/(b*b)     Div backward  src/ops.rs:466-491 */
+int tp_div_bwd_a(tp_ctx*, const tp_buf* gout, const tp_buf* b, tp_buf* ga, size_t n, int accumulate);
+int tp_div_bwd_b(tp_ctx*, const tp_buf* gout, const tp_buf* a, const tp_buf* b, tp_buf* gb, size_t n, int accumulate);
+int tp_relu_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, size_t n);                 /* src/ops.rs:312-349 */
+/* gin (+)= x>0 ? gout : 0        src/ops.rs:358-370 */
+int tp_relu_bwd(tp_ctx*, const tp_buf* x, const tp_buf* gout, tp_buf* gin, size_t n, int accumulate);
+int tp_exp_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, size_t n);                  /* src/tensor.rs:1091-1101 */
+int tp_exp_bwd(tp_ctx*, const tp_buf* y, const tp_buf* gout, tp_buf* gin, size_t n, int accumulate); /* :1109-1127 */
+int tp_log_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, size_t n);                  /* src/tensor.rs:1136-1143 */
+int tp_log_bwd(tp_ctx*, const tp_buf* x, const tp_buf* gout, tp_buf* gin, size_t n, int accumulate); /* :1150-1163 */
+
+/* ---------------------------------------------------------------------------------------------
+ * Broadcast / reduction / layout ops on [rows, cols] matrices
+ * ------------------------------------------------------------------------------------------- */
+/* out[i,f] = a[i,f] + bias[f] (optionally ReLU)      add_broadcast  src/tensor.rs:636-663 */
+int tp_add_broadcast_fwd(tp_ctx*, const tp_buf* a, const tp_buf* bias, tp_buf* out, int rows, int cols, int relu);
+/* out[f] (+)= scale * sum_i g[i,f]                   add_broadcast bwd  src/tensor.rs:680-691;  sum(dim=0) :890-940 */
+int tp_colsum(tp_ctx*, const tp_buf* g, tp_buf* out, int rows, int cols, float scale, int accumulate);
+/* out[i] (+)= scale * sum_c g[i,c]                   sub_broadcast_rows bwd (scale=-1)  src/tensor.rs:748-761; sum(dim=1) */
+int tp_rowsum(tp_ctx*, const tp_buf* g, tp_buf* out, int rows, int cols, float scale, int accumulate);
+/* out[0] = sum x                                     sum(None)  src/tensor.rs:994-996 */
+int tp_sum_all(tp_ctx*, const tp_buf* x, tp_buf* out, size_t n);
+/* out[i,c] = a[i,c] - r[i]                           sub_broadcast_rows  src/tensor.rs:707-737 */
+int tp_sub_broadcast_rows_fwd(tp_ctx*, const tp_buf* a, const tp_buf* r, tp_buf* out, int rows, int cols);
+/* gin[i,c] (+)= g[i] (mode 0) | g[c] (mode 1) | g[0] (mode 2)     sum backward  src/tensor.rs:942-990, 1003-1010 */
+int tp_broadcast_bwd(tp_ctx*, const tp_buf* g, tp_buf* gin, int rows, int cols, int mode, int accumulate);
+/* row-wise (dim=1) / column-wise (dim=0) max with first-max-wins indices stored as f32  src/tensor.rs:1021-1069 */
+int tp_max_rows(tp_ctx*, const tp_buf* x, tp_buf* vals, tp_buf* idx, int rows, int cols);
+int tp_max_cols(tp_ctx*, const tp_buf* x, tp_buf* vals, tp_buf* idx, int rows, int cols);
+/* global max, LAST of equal maxima (Iterator::max_by)  src/tensor.rs:1072-1080 */
+int tp_max_all(tp_ctx*, const tp_buf* x, tp_buf* val, tp_buf* idx, size_t n);
+/* y[j,i] (+)= x[i,j]                                 transpose fwd/bwd  src/tensor.rs:544-591 */
+int tp_transpose2d(tp_ctx*, const tp_buf* x, tp_buf* y, int rows, int cols, int accumulate);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Linear  (src/nn.rs:54-60 = transpose src/tensor.rs:544 + matmul src/ops.rs:200 +
+ * add_broadcast src/tensor.rs:636; backward = the three closures of those ops)
+ *   fwd:  Y[B,out] = X[B,in] * W[out,in]^T + b[out]   (optionally ReLU; b may be NULL)
+ *   bwd:  dX[B,in] (+)= dY * W ;  dW[out,in] (+)= dY^T * X ;  db[out] (+)= colsum(dY)
+ *         any of dX/dW/db may be NULL (operand does not require grad).
+ *         relu_mask_y != NULL applies dY := dY * [Y>0] first (ReLU backward src/ops.rs:358-370 fused).
+ * ------------------------------------------------------------------------------------------- */
+int tp_linear_fwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp_buf* y,
+                  int batch, int in_features, int out_features, int relu);
+int tp_linear_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* dy, const tp_buf* relu_mask_y,
+                  tp_buf* dx, tp_buf* dw, tp_buf* db, int batch, int in_features, int out_features,
+                  int acc_dx, int acc_dw, int acc_db);
+
+/* ---------------------------------------------------------------------------------------------
+ * Softmax / cross-entropy / accuracy  (src/loss.rs:82-195, 271-290)
+ * ------------------------------------------------------------------------------------------- */
+int tp_log_softmax_fwd(tp_ctx*, const tp_buf* x, tp_buf* logp, int rows, int cols);   /* src/loss.rs:101-126 */
+int tp_softmax_fwd(tp_ctx*, const tp_buf* x, tp_buf* p, int rows, int cols);          /* src/loss.rs:82-98 (intent, A13) */
+/* fused: logp = log_softmax(logits); loss[0] = -(1/B) sum_i logp[i, (int)t_i]   src/loss.rs:152-165.
+ * A target outside [0, cols) sets the context's sticky device error flag (reference asserts, :161). */
+int tp_softmax_xent_fwd(tp_ctx*, const tp_buf* logits, const tp_buf* targets, tp_buf* logp, tp_buf* loss,
+                        int rows, int cols);
+/* glogits (+)= (exp(logp) - onehot(t)) * gloss[0]/B                               src/loss.rs:174-191 */
+int tp_softmax_xent_bwd(tp_ctx*, const tp_buf* logp, const tp_buf* targets, const tp_buf* gloss,
+                        tp_buf* glogits, int rows, int cols, int accumulate);
+/* correct[0] = #{ i : |argmax_c pred[i,c] - t_i| < 1e-6 } as f32                    src/loss.rs:271-290 */
+int tp_accuracy_count(tp_ctx*, const tp_buf* pred, const tp_buf* targets, tp_buf* correct, int rows, int cols);
+/* reads and clears the sticky device error flag (0 = none, 1 = target class out of bounds) */
+int tp_ctx_device_error(tp_ctx* ctx, int* flag);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution and pooling, NCHW fp32  (src/tensor.rs:1221-1285, 1391-1660, 1663-1780, 1972-2076)
+ * Weight buffer is the reference's [C_out,C_in,kh,kw] allocation REINTERPRETED as [K=C_in*kh*kw, C_out]
+ * (src/tensor.rs:1262): element (k, co) at flat k*C_out + co.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tp_conv_desc {
+    int n, c_in, h, w;          /* input  [N, C_in, H, W]          */
+    int c_out, kh, kw;          /* weight [C_out, C_in, kh, kw]    */
+    int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+} tp_conv_desc;
+int tp_conv2d_out_dims(const tp_conv_desc* d, int* h_out, int* w_out);     /* src/tensor.rs:1254-1255 */
+/* col[(n,oh,ow), ci*kh*kw + kr*kw + kc]                im2col  src/tensor.rs:1663-1780 */
+int tp_im2col(tp_ctx*, const tp_buf* x, tp_buf* col, const tp_conv_desc* d);
+/* gx (+)= col2im(gcol)  — adjoint of im2col (the link the reference drops at src/tensor.rs:1725) */
+int tp_col2im(tp_ctx*, const tp_buf* gcol, tp_buf* gx, const tp_conv_desc* d, int accumulate);
+/* y[N,C_out,Ho,Wo] = conv(x, w) + b, optional ReLU     conv2d / conv2d_relu  src/tensor.rs:1221-1285, 1379-1389 */
+int tp_conv2d_fwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp_buf* y,
+                  const tp_conv_desc* d, int relu);
+/* gy is the gradient w.r.t. the conv output (after undoing ReLU if fused: pass relu_mask_y).
+ *   db[co]   (+)= sum_{n,oh,ow} gy                       add_bias_4d backward  src/tensor.rs:2003-2027
+ *   dw[K,Co] (+)= col^T * gy_nhwc ;  dx (+)= col2im(gy_nhwc * w^T)   (full adjoint; NULL to skip —
+ *   the reference computes neither, Appendix A1) */
+int tp_conv2d_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* gy, const tp_buf* relu_mask_y,
+                  tp_buf* dx, tp_buf* dw, tp_buf* db, const tp_conv_desc* d,
+                  int acc_dx, int acc_dw, int acc_db);
+/* y = x + bias[c] per channel; gb[c] (+)= sum_{n,hw} g     add_bias_4d  src/tensor.rs:1972-2031 */
+int tp_add_bias_4d(tp_ctx*, const tp_buf* x, const tp_buf* bias, tp_buf* y, int n, int c, int hw, int relu);
+int tp_bias_grad_4d(tp_ctx*, const tp_buf* g, tp_buf* gb, int n, int c, int hw, int accumulate);
+/* y[N,C,H,W] = x[N,H,W,C]                               transpose_4d([0,3,1,2])  src/tensor.rs:2034-2076 */
+int tp_nhwc_to_nchw(tp_ctx*, const tp_buf* x, tp_buf* y, int n, int h, int w, int c);
+int tp_nchw_to_nhwc(tp_ctx*, const tp_buf* x, tp_buf* y, int n, int c, int h, int w);
+
+typedef struct tp_pool_desc {
+    int n, c, h, w, kh, kw, stride_h, stride_w, pad_h, pad_w;
+} tp_pool_desc;
+int tp_pool_out_dims(const tp_pool_desc* d, int* h_out, int* w_out);       /* src/tensor.rs:1406-1407 */
+/* max_pool2d: strict '>' scan kh then kw from -inf, first max wins; argmax = absolute flat input
+ * index as int32 (reference: usize)                          src/tensor.rs:1391-1464 */
+int tp_maxpool2d_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, tp_buf* argmax_i32, const tp_pool_desc* d);
+/* gin plane := 0 then gin[argmax] += gout   (overwrites, Appendix A6)   src/tensor.rs:1476-1516 */
+int tp_maxpool2d_bwd(tp_ctx*, const tp_buf* gout, const tp_buf* argmax_i32, tp_buf* gin, const tp_pool_desc* d);
+/* avg_pool2d: window sum over in-bounds taps / (kh*kw)       src/tensor.rs:1524-1590; bwd accumulates :1600-1655 */
+int tp_avgpool2d_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, const tp_pool_desc* d);
+int tp_avgpool2d_bwd(tp_ctx*, const tp_buf* gout, tp_buf* gin, const tp_pool_desc* d, int accumulate);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer steps  (src/optim.rs:21-33, 83-113, 148-168).  grad_scale multiplies g first
+ * (1/world for data-parallel averaging; 1 otherwise).
+ * ------------------------------------------------------------------------------------------- */
+int tp_sgd_step(tp_ctx*, tp_buf* p, const tp_buf* g, float lr, float grad_scale, size_t n);
+/* g' = g*grad_scale + wd*p; m = b1*m+(1-b1)*g'; v = b2*v+(1-b2)*g'*g'; p -= step_size*m/(sqrt(v)+eps)
+ * step_size = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (tp_adam_step_size). */
+int tp_adam_step(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size,
+                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, size_t n);
+/* fused AdamW: p *= (1 - lr*wd) first (src/optim.rs:154-161), then Adam with wd = 0 */
+int tp_adamw_step(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size,
+                  float beta1, float beta2, float eps, float decay_factor, float grad_scale, size_t n);
+int tp_scale(tp_ctx*, tp_buf* p, float s, size_t n);            /* AdamW decay of grad-less params */
+/* lr * sqrt(1 - b2^t) / (1 - b1^t) with f32::powi semantics   src/optim.rs:88-90 */
+float tp_adam_step_size(float lr, float beta1, float beta2, int t);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (no counterpart in the reference: it is single-process).
+ * One rank per context.  `unique_id` is the 128-byte ncclUniqueId produced by tp_comm_unique_id on
+ * rank 0 and distributed by the launcher (torch.distributed / MPI / files).
+ * ------------------------------------------------------------------------------------------- */
+int tp_comm_unique_id(void* out128);
+int tp_comm_init(tp_ctx* ctx, int rank, int world, const void* unique_id128);
+int tp_comm_destroy(tp_ctx* ctx);
+int tp_allreduce_sum(tp_ctx* ctx, tp_buf* buf, size_t n);       /* in place, fp32, on the ctx stream */
+int tp_broadcast(tp_ctx* ctx, tp_buf* buf, size_t n, int root);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAPER_B200_H */

@@ -1,0 +1,128 @@
+// Internal definitions shared by every translation unit of libtaper_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/taper_b200.h"
+
+namespace tp {
+
+void set_error(const char* fmt, ...);
+
+struct Allocator {
+    // Size-bucketed caching allocator.  Single stream per context, so a block freed by the host
+    // and re-used by a later launch is ordered after every earlier use; LIFO free lists make the
+    // address sequence of a repeated alloc/free pattern (one training step) deterministic, which
+    // is what lets a whole step be captured in a CUDA graph and replayed.
+    std::unordered_map<size_t, std::vector<void*>> free_lists;
+    std::vector<void*> all_blocks;
+    size_t in_use = 0, reserved = 0;
+    static size_t bucket(size_t bytes);
+    void* alloc(size_t bytes, size_t* cap);
+    void free(void* p, size_t cap);
+    void release_all();
+};
+
+}  // namespace tp
+
+struct tp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    tp::Allocator alloc;
+    uint64_t launches = 0;
+    int gemm_mode = 1;               // 0 exact fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
+    int* dev_error = nullptr;        // sticky device-side error flag
+    void* pinned = nullptr;          // staging ring for pageable uploads
+    size_t pinned_bytes = 0;
+    cudaEvent_t pinned_ev = nullptr;
+    bool capturing = false;
+    // scratch for split-K / two-stage reductions (grown on demand, never during capture)
+    float* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // communication
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    void* tc_state = nullptr;        // tensor-map cache of the tcgen05 GEMM path
+};
+
+struct tp_buf {
+    tp_ctx* ctx = nullptr;
+    float* ptr = nullptr;
+    size_t n = 0;
+    size_t cap = 0;                  // allocator bucket bytes (0 for views / external)
+    std::atomic<int> rc{1};
+    tp_buf* parent = nullptr;        // for slices
+    bool external = false;
+};
+
+#define TP_CHECK_ARG(cond, ...)                         \
+    do {                                                \
+        if (!(cond)) {                                  \
+            tp::set_error(__VA_ARGS__);                 \
+            return TP_ERR_INVALID;                      \
+        }                                               \
+    } while (0)
+
+#define TP_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            tp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                          __FILE__, __LINE__);                                          \
+            return TP_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+// call after every kernel launch
+#define TP_LAUNCH_OK(ctx)                                                               \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        cudaError_t _e = cudaPeekAtLastError();                                         \
+        if (_e != cudaSuccess) {                                                        \
+            cudaGetLastError();                                                         \
+            tp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                          __FILE__, __LINE__);                                          \
+            return TP_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define TP_NEED(buf, count, name)                                                        \
+    TP_CHECK_ARG((buf) != nullptr && (buf)->n >= (size_t)(count),                        \
+                 "%s: buffer '%s' is NULL or shorter than %zu elements", __func__, name, (size_t)(count))
+
+namespace tp {
+
+// Grid sizing for HBM-bound grid-stride kernels: a multiple of the SM count, capped by the work.
+inline int grid_for(const tp_ctx* ctx, size_t work_items, int threads, int ctas_per_sm = 8) {
+    size_t need = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)ctx->sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+int ensure_scratch(tp_ctx* ctx, size_t bytes);
+
+// internal GEMM entry points (device pointers), see gemm.cu
+struct Epilogue {
+    const float* bias = nullptr;     // per output column n
+    int relu = 0;                    // max(x, 0) after bias
+    const float* relu_mask = nullptr;// multiply by [mask[m,n] > 0] (same layout as C)
+    float* colsum = nullptr;         // unused by the SIMT path
+};
+int gemm_rowmajor(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a,
+                  const float* b, float beta, float* c, const Epilogue& ep);
+int gemm_simt(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a,
+              const float* b, float beta, float* c, const Epilogue& ep);
+// returns TP_ERR_UNSUPPORTED when the shape/alignment cannot go through TMA + tcgen05
+int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a,
+            const float* b, float beta, float* c, const Epilogue& ep, int mode);
+void gemm_tc_destroy(tp_ctx* ctx);
+
+}  // namespace tp

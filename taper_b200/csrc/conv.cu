@@ -1,0 +1,263 @@
+// conv2d via im2col + GEMM, NCHW fp32, with the reference's weight reinterpretation.
+// Reference: Tensor::conv2d (src/tensor.rs:1221-1285), im2col_optimized (:1663-1780),
+// transpose_4d (:2034-2076), add_bias_4d (:1972-2031).  The full adjoint (dW, dX) restores the two
+// tape links the reference drops (:1725, :2075) and is optional per call.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct ConvGeom {
+    int n, c, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, ho, wo, K;
+};
+
+// col[row=(n,oh,ow), k = ci*kh*kw + kr*kw + kc] = x[n,ci,oh*sh+kr*dh-ph, ow*sw+kc*dw-pw] or 0
+__global__ void __launch_bounds__(kThreads)
+im2col_kernel(const float* __restrict__ x, float* __restrict__ col, ConvGeom g, size_t total) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    const int khw = g.kh * g.kw;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+        int k = (int)(i % g.K);
+        size_t row = i / g.K;
+        int ow = (int)(row % g.wo);
+        size_t t = row / g.wo;
+        int oh = (int)(t % g.ho);
+        int nb = (int)(t / g.ho);
+        int ci = k / khw, r = k - ci * khw;
+        int kr = r / g.kw, kc = r - kr * g.kw;
+        int ih = oh * g.sh + kr * g.dh - g.ph;
+        int iw = ow * g.sw + kc * g.dw - g.pw;
+        float v = 0.0f;
+        if (ih >= 0 && ih < g.h && iw >= 0 && iw < g.w)
+            v = __ldg(x + (((size_t)nb * g.c + ci) * g.h + ih) * g.w + iw);
+        col[i] = v;
+    }
+}
+
+// gather-form adjoint of im2col (deterministic, no atomics):
+// gx[n,ci,ih,iw] (+)= sum_{kr,kc : oh,ow valid} gcol[(n,oh,ow), ci*kh*kw + kr*kw + kc]
+__global__ void __launch_bounds__(kThreads)
+col2im_kernel(const float* __restrict__ gcol, float* __restrict__ gx, ConvGeom g, size_t total, int accumulate) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    const int khw = g.kh * g.kw;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+        int iw = (int)(i % g.w);
+        size_t t = i / g.w;
+        int ih = (int)(t % g.h);
+        t /= g.h;
+        int ci = (int)(t % g.c);
+        int nb = (int)(t / g.c);
+        float acc = 0.0f;
+        for (int kr = 0; kr < g.kh; ++kr) {
+            int nh = ih + g.ph - kr * g.dh;
+            if (nh < 0 || nh % g.sh) continue;
+            int oh = nh / g.sh;
+            if (oh >= g.ho) continue;
+            for (int kc = 0; kc < g.kw; ++kc) {
+                int nw = iw + g.pw - kc * g.dw;
+                if (nw < 0 || nw % g.sw) continue;
+                int ow = nw / g.sw;
+                if (ow >= g.wo) continue;
+                size_t row = ((size_t)nb * g.ho + oh) * g.wo + ow;
+                acc += __ldg(gcol + row * g.K + ci * khw + kr * g.kw + kc);
+            }
+        }
+        gx[i] = accumulate ? gx[i] + acc : acc;
+    }
+}
+
+// y[n,c,hw] = x_nhwc[n,hw,c] + bias[c] (optional relu): 32x32 smem-tiled batched transpose with fused epilogue
+__global__ void __launch_bounds__(kThreads)
+nhwc_to_nchw_bias_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+                         int hw, int c, int relu) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;       // x viewed as [hw rows, c cols] per image
+    const size_t off = (size_t)blockIdx.z * hw * c;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        int r = r0 + ty + j, cc = c0 + tx;
+        if (r < hw && cc < c) tile[ty + j][tx] = __ldg(x + off + (size_t)r * c + cc);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        int ch = c0 + ty + j, sp = r0 + tx;
+        if (ch < c && sp < hw) {
+            float v = tile[tx][ty + j];
+            if (bias) v += __ldg(bias + ch);
+            if (relu) v = fmaxf(v, 0.0f);
+            y[off + (size_t)ch * hw + sp] = v;
+        }
+    }
+}
+
+// g_nhwc[n,hw,c] = gy[n,c,hw] * (mask ? [mask[n,c,hw] > 0] : 1)
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc_mask_kernel(const float* __restrict__ gy, const float* __restrict__ mask, float* __restrict__ out, int c, int hw) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int s0 = blockIdx.x * 32, ch0 = blockIdx.y * 32;       // gy viewed as [c rows, hw cols] per image
+    const size_t off = (size_t)blockIdx.z * hw * c;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        int ch = ch0 + ty + j, sp = s0 + tx;
+        if (ch < c && sp < hw) {
+            size_t idx = off + (size_t)ch * hw + sp;
+            float v = __ldg(gy + idx);
+            if (mask && !(__ldg(mask + idx) > 0.0f)) v = 0.0f;
+            tile[ty + j][tx] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        int sp = s0 + ty + j, ch = ch0 + tx;
+        if (sp < hw && ch < c) out[off + (size_t)sp * c + ch] = tile[tx][ty + j];
+    }
+}
+
+int make_geom(const tp_conv_desc* d, ConvGeom* g, const char* fn) {
+    TP_CHECK_ARG(d, "%s: NULL descriptor", fn);
+    TP_CHECK_ARG(d->n >= 0 && d->c_in > 0 && d->h > 0 && d->w > 0 && d->c_out > 0 && d->kh > 0 && d->kw > 0 &&
+                     d->stride_h > 0 && d->stride_w > 0 && d->pad_h >= 0 && d->pad_w >= 0 && d->dil_h > 0 && d->dil_w > 0,
+                 "%s: invalid convolution descriptor", fn);
+    int eh = d->h + 2 * d->pad_h - d->dil_h * (d->kh - 1) - 1;
+    int ew = d->w + 2 * d->pad_w - d->dil_w * (d->kw - 1) - 1;
+    TP_CHECK_ARG(eh >= 0 && ew >= 0, "%s: kernel larger than padded input", fn);
+    g->n = d->n; g->c = d->c_in; g->h = d->h; g->w = d->w; g->cout = d->c_out; g->kh = d->kh; g->kw = d->kw;
+    g->sh = d->stride_h; g->sw = d->stride_w; g->ph = d->pad_h; g->pw = d->pad_w; g->dh = d->dil_h; g->dw = d->dil_w;
+    g->ho = eh / d->stride_h + 1;
+    g->wo = ew / d->stride_w + 1;
+    g->K = d->c_in * d->kh * d->kw;
+    TP_CHECK_ARG(d->n <= 65535, "%s: batch %d exceeds grid.z limit", fn, d->n);
+    return TP_OK;
+}
+
+struct TmpBuf {           // RAII for workspace from the context's caching allocator
+    tp_buf* b = nullptr;
+    ~TmpBuf() { if (b) tp_buf_release(b); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int tp_conv2d_out_dims(const tp_conv_desc* d, int* h_out, int* w_out) {
+    ConvGeom g;
+    int rc = make_geom(d, &g, "tp_conv2d_out_dims");
+    if (rc) return rc;
+    if (h_out) *h_out = g.ho;
+    if (w_out) *w_out = g.wo;
+    return TP_OK;
+}
+
+int tp_im2col(tp_ctx* ctx, const tp_buf* x, tp_buf* col, const tp_conv_desc* d) {
+    TP_CHECK_ARG(ctx, "tp_im2col: NULL ctx");
+    ConvGeom g;
+    int rc = make_geom(d, &g, "tp_im2col");
+    if (rc) return rc;
+    size_t total = (size_t)g.n * g.ho * g.wo * g.K;
+    TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(col, total, "col");
+    if (!total) return TP_OK;
+    im2col_kernel<<<tp::grid_for(ctx, total, kThreads, 16), kThreads, 0, ctx->stream>>>(x->ptr, col->ptr, g, total);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_col2im(tp_ctx* ctx, const tp_buf* gcol, tp_buf* gx, const tp_conv_desc* d, int accumulate) {
+    TP_CHECK_ARG(ctx, "tp_col2im: NULL ctx");
+    ConvGeom g;
+    int rc = make_geom(d, &g, "tp_col2im");
+    if (rc) return rc;
+    size_t total = (size_t)g.n * g.c * g.h * g.w;
+    TP_NEED(gcol, (size_t)g.n * g.ho * g.wo * g.K, "gcol"); TP_NEED(gx, total, "gx");
+    if (!total) return TP_OK;
+    col2im_kernel<<<tp::grid_for(ctx, total, kThreads, 16), kThreads, 0, ctx->stream>>>(gcol->ptr, gx->ptr, g, total, accumulate);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp_buf* y, const tp_conv_desc* d, int relu) {
+    TP_CHECK_ARG(ctx, "tp_conv2d_fwd: NULL ctx");
+    ConvGeom g;
+    int rc = make_geom(d, &g, "tp_conv2d_fwd");
+    if (rc) return rc;
+    size_t M = (size_t)g.n * g.ho * g.wo;
+    TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(w, (size_t)g.K * g.cout, "w"); TP_NEED(y, M * g.cout, "y");
+    if (b) TP_NEED(b, g.cout, "b");
+    if (!M) return TP_OK;
+    TP_CHECK_ARG(M <= 0x7fffffff, "tp_conv2d_fwd: N*Ho*Wo = %zu exceeds int range", M);
+    TmpBuf col, out2d;
+    if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;
+    if ((rc = tp_buf_alloc(ctx, M * g.cout, &out2d.b))) return rc;
+    if ((rc = tp_im2col(ctx, x, col.b, d))) return rc;
+    tp::Epilogue ep;
+    // [M,K] x [K,Cout] -> NHWC rows  (src/tensor.rs:1262-1265); weight buffer reinterpreted as [K,Cout] (A2)
+    if ((rc = tp::gemm_rowmajor(ctx, 0, 0, (int)M, g.cout, g.K, 1.0f, col.b->ptr, w->ptr, 0.0f, out2d.b->ptr, ep))) return rc;
+    int hw = g.ho * g.wo;
+    nhwc_to_nchw_bias_kernel<<<dim3((g.cout + 31) / 32, (hw + 31) / 32, g.n), kThreads, 0, ctx->stream>>>(
+        out2d.b->ptr, b ? b->ptr : nullptr, y->ptr, hw, g.cout, relu);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_conv2d_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* gy, const tp_buf* relu_mask_y, tp_buf* dx,
+                  tp_buf* dw, tp_buf* db, const tp_conv_desc* d, int acc_dx, int acc_dw, int acc_db) {
+    TP_CHECK_ARG(ctx, "tp_conv2d_bwd: NULL ctx");
+    ConvGeom g;
+    int rc = make_geom(d, &g, "tp_conv2d_bwd");
+    if (rc) return rc;
+    size_t M = (size_t)g.n * g.ho * g.wo;
+    int hw = g.ho * g.wo;
+    TP_NEED(gy, M * g.cout, "gy");
+    if (relu_mask_y) TP_NEED(relu_mask_y, M * g.cout, "relu_mask_y");
+    if (!M) return TP_OK;
+    TP_CHECK_ARG(M <= 0x7fffffff, "tp_conv2d_bwd: N*Ho*Wo = %zu exceeds int range", M);
+
+    const tp_buf* gz = gy;                     // gradient w.r.t. the pre-activation conv output, NCHW
+    TmpBuf gmask;
+    if (relu_mask_y && db && !(dw || dx)) {
+        if ((rc = tp_buf_alloc(ctx, M * g.cout, &gmask.b))) return rc;
+        if ((rc = tp_relu_bwd(ctx, relu_mask_y, gy, gmask.b, M * g.cout, 0))) return rc;
+        gz = gmask.b;
+    }
+    TmpBuf g_nhwc;
+    if (dw || dx) {
+        if ((rc = tp_buf_alloc(ctx, M * g.cout, &g_nhwc.b))) return rc;
+        nchw_to_nhwc_mask_kernel<<<dim3((hw + 31) / 32, (g.cout + 31) / 32, g.n), kThreads, 0, ctx->stream>>>(
+            gy->ptr, relu_mask_y ? relu_mask_y->ptr : nullptr, g_nhwc.b->ptr, g.cout, hw);
+        TP_LAUNCH_OK(ctx);
+    }
+    if (db) {
+        TP_NEED(db, g.cout, "db");
+        if (g_nhwc.b) {
+            // column sums of the masked NHWC matrix [M, Cout]  ==  add_bias_4d backward (src/tensor.rs:2013-2025)
+            if ((rc = tp_colsum(ctx, g_nhwc.b, db, (int)M, g.cout, 1.0f, acc_db))) return rc;
+        } else {
+            if ((rc = tp_bias_grad_4d(ctx, gz, db, g.n, g.cout, hw, acc_db))) return rc;
+        }
+    }
+    tp::Epilogue ep;
+    if (dw) {
+        TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(dw, (size_t)g.K * g.cout, "dw");
+        TmpBuf col;
+        if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;
+        if ((rc = tp_im2col(ctx, x, col.b, d))) return rc;
+        // dW2[K,Cout] (+)= col^T[K,M] * g_nhwc[M,Cout]   (matmul backward wrt B, src/ops.rs:280-291)
+        if ((rc = tp::gemm_rowmajor(ctx, 1, 0, g.K, g.cout, (int)M, 1.0f, col.b->ptr, g_nhwc.b->ptr, acc_dw ? 1.0f : 0.0f, dw->ptr, ep)))
+            return rc;
+    }
+    if (dx) {
+        TP_NEED(w, (size_t)g.K * g.cout, "w"); TP_NEED(dx, (size_t)g.n * g.c * g.h * g.w, "dx");
+        TmpBuf gcol;
+        if ((rc = tp_buf_alloc(ctx, M * g.K, &gcol.b))) return rc;
+        // gcol[M,K] = g_nhwc[M,Cout] * W2^T[Cout,K]        (matmul backward wrt A, src/ops.rs:254-265)
+        if ((rc = tp::gemm_rowmajor(ctx, 0, 1, (int)M, g.K, g.cout, 1.0f, g_nhwc.b->ptr, w->ptr, 0.0f, gcol.b->ptr, ep))) return rc;
+        if ((rc = tp_col2im(ctx, gcol.b, dx, d, acc_dx))) return rc;
+    }
+    return TP_OK;
+}
+
+}  // extern "C"

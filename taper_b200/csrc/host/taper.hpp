@@ -1,0 +1,360 @@
+// taper.hpp — C++ host layer mirroring taper's Rust API one-to-one (Tensor / Tape / nn::Module /
+// loss / optim / train), sitting above the C ABI in include/taper_b200.h exactly as a Rust shim
+// would.  The reference's toolchain (cargo/rustc) is not available in the build image, so the host
+// side is C++; names, argument meaning and error behaviour (panic -> std::runtime_error) follow the
+// reference.  Citations are `path:line` in vaibhawvipul/taper @ aea74b46.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+#include "taper_b200.h"
+
+namespace taper {
+
+using Shape = std::vector<size_t>;
+using Pair = std::pair<size_t, size_t>;
+
+// ---- device context (one per host thread, like the reference's thread-local tape) -------------
+tp_ctx* ctx();
+void set_device(int device);            // must be called before the first tensor is created on this thread
+void synchronize();
+void check(int rc);                     // non-zero status -> throw (the reference panics)
+
+// Switches documented in DESIGN.md
+struct Config {
+    // the reference drops the tape links inside conv2d, so conv weights and
+    // conv inputs never receive gradients.  false (default) reproduces the reference bit-for-bit in
+    // structure; true computes the full adjoint (dW = col^T dY, dX = col2im(dY W^T)).
+    static bool& conv_full_adjoint();
+    // Sequential peephole: Linear followed by ReLU runs as one fused launch (bias+ReLU in the GEMM
+    // epilogue, ReLU mask folded into the backward).  Numerically identical to the unfused ops.
+    static bool& fuse_linear_relu();
+};
+
+struct TensorImpl;
+
+// ---- Tensor  (src/tensor.rs:236-244, 469-541) -----------------------------------------------------
+class Tensor {
+public:
+    Tensor() = default;
+    static Tensor create(const std::vector<float>& data, const Shape& shape);   // Tensor::new  :470-478
+    static Tensor from_host(const float* data, const Shape& shape);
+    static Tensor scalar(float v);                                              // :480-482
+    static Tensor zeros(const Shape& shape);
+    static Tensor randn(const Shape& shape, uint64_t seed);                     // src/ops.rs:301-309 (seeded here)
+    static Tensor adopt(tp_buf* buf, const Shape& shape);                       // takes ownership of buf
+
+    Tensor requires_grad() const;                 // `fn requires_grad(mut self) -> Self`  :484-487
+    bool needs_grad() const { return requires_grad_; }
+    void set_requires_grad(bool v) { requires_grad_ = v; }
+
+    const Shape& shape() const;                   // :489-491
+    size_t numel() const;
+    bool defined() const { return (bool)impl_; }
+    const std::vector<float>& data() const;       // :493-496 — lazily synchronised host mirror (syncs the stream)
+    float item() const;                           // data()[0]
+    void set_data(const std::vector<float>& v) const;   // data_mut() :499-501 — writes through to the device
+    std::optional<Tensor> grad() const;           // :512-518 (clone of the gradient, or None)
+    void set_grad(const std::vector<float>& g) const;   // `grad` is a pub field, src/tensor.rs:241
+    void zero_grad() const;                       // :531-533
+    void backward() const;                        // :520-529
+
+    tp_buf* buf() const;                          // device buffer (borrowed)
+    tp_buf* grad_buf() const;                     // device gradient buffer or NULL
+    std::shared_ptr<TensorImpl> impl() const { return impl_; }
+
+    // ops — each records a tape node exactly when the reference does
+    Tensor matmul(const Tensor& other) const;                     // src/ops.rs:200-298
+    Tensor relu() const;                                          // src/ops.rs:312-374
+    Tensor transpose() const;                                     // src/tensor.rs:544-591
+    Tensor add_broadcast(const Tensor& other) const;              // src/tensor.rs:636-704
+    Tensor sub_broadcast_rows(const Tensor& other) const;         // src/tensor.rs:707-770
+    Tensor reshape(const Shape& shape) const;                     // src/tensor.rs:803-840 (copies, A11)
+    Tensor flatten(size_t start_dim) const;                       // src/tensor.rs:842-858
+    Tensor view(const Shape& shape) const { return reshape(shape); }   // src/tensor.rs:1214
+    Tensor sum(std::optional<size_t> dim, bool keepdim) const;    // src/tensor.rs:890-1018
+    std::pair<Tensor, Tensor> max(std::optional<size_t> dim) const;   // src/tensor.rs:1021-1083
+    Tensor argmax(std::optional<size_t> dim) const;               // src/tensor.rs:1086-1088
+    Tensor exp() const;                                           // src/tensor.rs:1091-1133
+    Tensor log() const;                                           // src/tensor.rs:1136-1169
+    Tensor conv2d(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation) const;       // :1221-1285
+    Tensor conv2d_relu(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation) const;  // :1379-1389
+    Tensor max_pool2d(Pair kernel, std::optional<Pair> stride, Pair padding) const;   // :1391-1521
+    Tensor avg_pool2d(Pair kernel, std::optional<Pair> stride, Pair padding) const;   // :1524-1660
+
+    // fused Linear (+ReLU): one node standing for transpose+matmul+add_broadcast(+relu) of src/nn.rs:54-60
+    Tensor linear(const Tensor& weight, const Tensor* bias, bool relu) const;
+
+private:
+    Tensor conv2d_impl(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation, bool relu) const;
+    std::shared_ptr<TensorImpl> impl_;
+    bool requires_grad_ = false;
+    friend struct TensorImpl;
+};
+
+Tensor operator+(const Tensor& a, const Tensor& b);     // src/ops.rs:8-52
+Tensor operator-(const Tensor& a, const Tensor& b);     // src/ops.rs:377-420
+Tensor operator*(const Tensor& a, const Tensor& b);     // src/ops.rs:54-120
+Tensor operator/(const Tensor& a, const Tensor& b);     // src/ops.rs:440-496
+
+// ---- Tape  (src/tape.rs) ------------------------------------------------------------------------------
+class Tape {
+public:
+    static void ensure_active();                                                            // :34-40
+    static void reset();                                                                    // :43-49
+    static void push_binary_op(const Tensor& a, const Tensor& b, const Tensor& out, std::function<void()> fn);   // :51-76
+    static void push_unary_op(const Tensor& input, const Tensor& out, std::function<void()> fn);                 // :78-101
+    static size_t len();
+};
+void backward(size_t final_node_id);                                                        // src/tape.rs:106-127
+
+// ---- nn  (src/nn.rs, src/activation.rs) -------------------------------------------------------------------
+namespace nn {
+
+struct Module {
+    virtual ~Module() = default;
+    virtual Tensor forward(const Tensor& input) const = 0;          // src/nn.rs:10-12
+    virtual std::vector<Tensor> parameters() const { return {}; }
+    virtual const char* kind() const { return "module"; }
+};
+
+struct Linear : Module {                                             // src/nn.rs:28-78
+    Tensor weight;                   // [out, in]
+    std::optional<Tensor> bias;      // [out]
+    Linear(size_t in_features, size_t out_features, bool with_bias, uint64_t seed = 0);
+    Tensor forward(const Tensor& input) const override;
+    Tensor forward_fused_relu(const Tensor& input) const;
+    std::vector<Tensor> parameters() const override;
+    const char* kind() const override { return "linear"; }
+};
+
+struct ReLU : Module {                                               // src/activation.rs:7-21
+    Tensor forward(const Tensor& input) const override { return input.relu(); }
+    const char* kind() const override { return "relu"; }
+};
+
+struct Sequential : Module {                                         // src/nn.rs:130-162
+    std::vector<std::shared_ptr<Module>> layers;
+    Sequential() = default;
+    explicit Sequential(std::vector<std::shared_ptr<Module>> l) : layers(std::move(l)) {}
+    Tensor forward(const Tensor& input) const override;
+    std::vector<Tensor> parameters() const override;
+    const char* kind() const override { return "sequential"; }
+};
+
+struct Conv2d : Module {                                             // src/nn.rs:180-354 (groups == 1)
+    Tensor weight;                   // [C_out, C_in, kh, kw]
+    std::optional<Tensor> bias;
+    Pair stride, padding, dilation;
+    size_t groups;
+    Conv2d(size_t in_channels, size_t out_channels, Pair kernel_size, std::optional<Pair> stride,
+           std::optional<Pair> padding, std::optional<Pair> dilation, std::optional<size_t> groups, bool bias,
+           uint64_t seed = 0);
+    Tensor forward(const Tensor& input) const override;
+    std::vector<Tensor> parameters() const override;
+    const char* kind() const override { return "conv2d"; }
+};
+
+struct Conv2dReLU : Conv2d {                                         // src/nn.rs:433-490
+    using Conv2d::Conv2d;
+    Tensor forward(const Tensor& input) const override;
+    const char* kind() const override { return "conv2d_relu"; }
+};
+
+struct MaxPool2d : Module {                                          // src/nn.rs:508-549
+    Pair kernel_size;
+    std::optional<Pair> stride;
+    Pair padding;
+    MaxPool2d(Pair k, std::optional<Pair> s, std::optional<Pair> p) : kernel_size(k), stride(s), padding(p.value_or(Pair{0, 0})) {}
+    Tensor forward(const Tensor& input) const override { return input.max_pool2d(kernel_size, stride, padding); }
+    const char* kind() const override { return "maxpool2d"; }
+};
+
+struct AvgPool2d : Module {                                          // src/nn.rs:570-653
+    Pair kernel_size;
+    std::optional<Pair> stride;
+    Pair padding;
+    AvgPool2d(Pair k, std::optional<Pair> s, std::optional<Pair> p) : kernel_size(k), stride(s), padding(p.value_or(Pair{0, 0})) {}
+    Tensor forward(const Tensor& input) const override { return input.avg_pool2d(kernel_size, stride, padding); }
+    const char* kind() const override { return "avgpool2d"; }
+};
+
+struct AdaptiveAvgPool2d : Module {                                  // src/nn.rs:655-697
+    Pair output_size;
+    explicit AdaptiveAvgPool2d(Pair out) : output_size(out) {}
+    static AdaptiveAvgPool2d global() { return AdaptiveAvgPool2d({1, 1}); }
+    Tensor forward(const Tensor& input) const override;
+    const char* kind() const override { return "adaptive_avgpool2d"; }
+};
+
+struct Flatten : Module {                                            // src/nn.rs:730-756
+    size_t start_dim;
+    explicit Flatten(std::optional<size_t> sd = std::nullopt) : start_dim(sd.value_or(1)) {}
+    Tensor forward(const Tensor& input) const override { return input.flatten(start_dim); }
+    const char* kind() const override { return "flatten"; }
+};
+
+}  // namespace nn
+
+// ---- loss  (src/loss.rs) -----------------------------------------------------------------------------------
+namespace loss {
+Tensor softmax(const Tensor& x, int dim);                            // :82-98 (row-wise intent, A13)
+Tensor log_softmax(const Tensor& x, int dim);                        // :101-126 — composed op-for-op
+Tensor cross_entropy_loss(const Tensor& logits, const Tensor& targets);   // :136-195 — fused fwd, direct bwd
+float accuracy(const Tensor& predictions, const Tensor& targets);    // :271-290
+// device-side variant: correct count as a [1] tensor, no host sync (used by the captured train step)
+Tensor accuracy_count(const Tensor& predictions, const Tensor& targets);
+}  // namespace loss
+
+// ---- optim  (src/optim.rs) ----------------------------------------------------------------------------------
+namespace optim {
+
+// Flat parameter / gradient / moment arenas shared by the optimizers: params are re-homed into one
+// contiguous buffer so the step is one launch and the data-parallel exchange is one allreduce.
+struct Arena;
+
+struct Optimizer {                                                   // :3-6
+    virtual ~Optimizer() = default;
+    virtual void step() = 0;
+    virtual void zero_grad() = 0;
+};
+
+class SGD : public Optimizer {                                       // :8-40 (momentum ignored, :14-17)
+public:
+    SGD(std::vector<Tensor> params, float lr, std::optional<float> momentum = std::nullopt);
+    ~SGD() override;
+    void step() override;
+    void zero_grad() override;
+    void set_grad_scale(float s) { grad_scale_ = s; }
+    std::shared_ptr<Arena> arena() const { return arena_; }
+private:
+    std::vector<Tensor> params_;
+    float lr_;
+    float grad_scale_ = 1.0f;
+    std::shared_ptr<Arena> arena_;
+};
+
+class Adam : public Optimizer {                                      // :43-128
+public:
+    Adam(std::vector<Tensor> params, float lr, std::optional<std::pair<float, float>> betas = std::nullopt,
+         std::optional<float> eps = std::nullopt, std::optional<float> weight_decay = std::nullopt);
+    ~Adam() override;
+    void step() override;                                            // :83-113
+    void zero_grad() override;                                       // :115-119
+    float get_lr() const { return lr_; }                             // :121-123
+    void set_lr(float lr) { lr_ = lr; }                              // :125-127
+    void set_grad_scale(float s) { grad_scale_ = s; }                // 1/world for data-parallel averaging
+    std::shared_ptr<Arena> arena() const { return arena_; }
+    size_t t() const { return t_; }
+protected:
+    void step_impl(bool decoupled);
+    std::vector<Tensor> params_;
+    float lr_, beta1_, beta2_, eps_, weight_decay_;
+    float grad_scale_ = 1.0f;
+    size_t t_ = 0;
+    std::shared_ptr<Arena> arena_;
+    friend class AdamW;
+};
+
+class AdamW : public Optimizer {                                     // :131-181
+public:
+    AdamW(std::vector<Tensor> params, float lr, std::optional<std::pair<float, float>> betas = std::nullopt,
+          std::optional<float> eps = std::nullopt, std::optional<float> weight_decay = std::nullopt);
+    void step() override;                                            // :148-168
+    void zero_grad() override { adam_.zero_grad(); }
+    float get_lr() const { return adam_.get_lr(); }
+    void set_lr(float lr) { adam_.set_lr(lr); }
+    void set_grad_scale(float s) { adam_.set_grad_scale(s); }
+    std::shared_ptr<Arena> arena() const { return adam_.arena(); }
+private:
+    Adam adam_;
+};
+
+struct LRScheduler {                                                 // :184-187
+    virtual ~LRScheduler() = default;
+    virtual void step(std::optional<float> metrics) = 0;
+    virtual float get_lr() const = 0;
+};
+struct StepLR : LRScheduler {                                        // :190-219
+    float current_lr, gamma; size_t step_size, current_epoch = 0;
+    StepLR(float base_lr, size_t step_size_, float gamma_) : current_lr(base_lr), gamma(gamma_), step_size(step_size_) {}
+    void step(std::optional<float>) override;
+    float get_lr() const override { return current_lr; }
+};
+struct ExponentialLR : LRScheduler {                                 // :221-244
+    float current_lr, gamma;
+    ExponentialLR(float base_lr, float gamma_) : current_lr(base_lr), gamma(gamma_) {}
+    void step(std::optional<float>) override { current_lr *= gamma; }
+    float get_lr() const override { return current_lr; }
+};
+struct CosineAnnealingLR : LRScheduler {                             // :246-285
+    float base_lr, min_lr, current_lr; size_t t_max, current_epoch = 0;
+    CosineAnnealingLR(float base, size_t tmax, std::optional<float> minlr)
+        : base_lr(base), min_lr(minlr.value_or(0.0f)), current_lr(base), t_max(tmax) {}
+    void step(std::optional<float>) override;
+    float get_lr() const override { return current_lr; }
+};
+struct ReduceLROnPlateau : LRScheduler {                             // :287-352
+    float current_lr, factor, min_lr, best_metric; size_t patience, patience_counter = 0; std::string mode;
+    ReduceLROnPlateau(float initial_lr, float factor_, size_t patience_, std::optional<float> min_lr_, std::optional<std::string> mode_);
+    void step(std::optional<float> metrics) override;
+    float get_lr() const override { return current_lr; }
+};
+
+}  // namespace optim
+
+// ---- data-parallel group (no counterpart in the reference) -----------------------------------------------------
+namespace dist {
+void init(int rank, int world, const void* nccl_unique_id128);       // binds NCCL to this thread's context
+int rank();
+int world();
+void allreduce_sum(tp_buf* buf, size_t n);
+void broadcast(tp_buf* buf, size_t n, int root);
+}  // namespace dist
+
+// ---- train  (src/train.rs) -----------------------------------------------------------------------------------------
+namespace train {
+
+struct Metrics {                                                     // :10-71
+    std::vector<float> train_loss, train_acc, val_loss, val_acc, epoch_times;
+};
+
+struct StepResult { float loss; float correct; };
+
+class Trainer {                                                      // :73-293
+public:
+    std::shared_ptr<nn::Module> model;
+    std::shared_ptr<optim::Optimizer> optimizer;
+    std::shared_ptr<optim::LRScheduler> scheduler;
+    Metrics metrics;
+    Trainer(std::shared_ptr<nn::Module> m, std::shared_ptr<optim::Optimizer> o, std::shared_ptr<optim::LRScheduler> s = nullptr);
+    ~Trainer();
+    // The loop body of train_epoch (:106-138): reset tape, forward, CE, accuracy, backward,
+    // [allreduce], step, zero_grad; returns (loss, #correct).  `images` is host memory [batch, sample_dims...].
+    StepResult train_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);
+    // Asynchronous form: enqueue only (inputs may be pinned); results land in a device slot read by fetch().
+    void train_batch_async(const float* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned);
+    StepResult fetch();
+    // same body on inputs already resident on the device (bench `value` leg)
+    void train_batch_device(const Tensor& images, const Tensor& labels);
+    StepResult eval_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);   // :147-172 body
+    void save_checkpoint(const std::string& path) const;             // :264-292 text format
+    void load_checkpoint(const std::string& path) const;             // loader for the same format (the reference has none)
+    void set_use_graph(bool v) { use_graph_ = v; }
+    uint64_t graph_replays() const { return graph_replays_; }
+private:
+    struct Impl;
+    std::unique_ptr<Impl> p_;
+    bool use_graph_ = true;
+    uint64_t graph_replays_ = 0;
+};
+
+}  // namespace train
+
+}  // namespace taper

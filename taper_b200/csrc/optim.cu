@@ -1,0 +1,127 @@
+// Optimizer steps: HBM-bound streaming kernels (SGD 12 B/param, Adam/AdamW 28 B/param), 128-bit vectorised.
+// Reference: SGD::step (src/optim.rs:21-33), Adam::step (:83-113), AdamW::step (:148-168).
+// The operation order of every formula follows the reference expression-for-expression and the
+// kernels are compiled with -fmad=false so no multiply-add is contracted differently from the CPU code.
+#include "common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct AdamArgs {
+    float step_size, beta1, beta2, eps, weight_decay, grad_scale, decay_factor;
+    int decoupled;   // AdamW: p *= decay_factor first, wd = 0 inside
+};
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamArgs& a) {
+    if (a.decoupled) p *= a.decay_factor;                       // src/optim.rs:157-159
+    if (a.grad_scale != 1.0f) g *= a.grad_scale;                // data-parallel mean of the summed gradient
+    float gg = g + a.weight_decay * p;                          // src/optim.rs:98
+    m = a.beta1 * m + (1.0f - a.beta1) * gg;                    // :101
+    v = a.beta2 * v + (1.0f - a.beta2) * gg * gg;               // :104
+    p -= a.step_size * m / (sqrtf(v) + a.eps);                  // :107
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                 size_t n4, AdamArgs a) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p[i], gg = __ldg(g + i), mm = m[i], vv = v[i];
+        adam_elem(pp.x, gg.x, mm.x, vv.x, a);
+        adam_elem(pp.y, gg.y, mm.y, vv.y, a);
+        adam_elem(pp.z, gg.z, mm.z, vv.z, a);
+        adam_elem(pp.w, gg.w, mm.w, vv.w, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_scalar_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   size_t n, AdamArgs a) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_elem(pp, g[i], mm, vv, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float lr, float grad_scale) {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        float gg = g[i];
+        if (grad_scale != 1.0f) gg *= grad_scale;
+        p[i] -= lr * gg;                                        // src/optim.rs:29
+    }
+}
+
+int launch_adam(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, size_t n, const AdamArgs& a, const char* fn) {
+    TP_CHECK_ARG(ctx, "%s: NULL ctx", fn);
+    TP_NEED(p, n, "p"); TP_NEED(g, n, "g"); TP_NEED(m, n, "m"); TP_NEED(v, n, "v");
+    if (!n) return TP_OK;
+    bool vec = !(((uintptr_t)p->ptr | (uintptr_t)g->ptr | (uintptr_t)m->ptr | (uintptr_t)v->ptr) & 15);
+    size_t n4 = vec ? n / 4 : 0;
+    if (n4) {
+        adam_vec4_kernel<<<tp::grid_for(ctx, n4, kThreads), kThreads, 0, ctx->stream>>>(
+            (float4*)p->ptr, (const float4*)g->ptr, (float4*)m->ptr, (float4*)v->ptr, n4, a);
+        TP_LAUNCH_OK(ctx);
+    }
+    size_t done = n4 * 4;
+    if (done < n) {
+        adam_scalar_kernel<<<tp::grid_for(ctx, n - done, kThreads), kThreads, 0, ctx->stream>>>(
+            p->ptr + done, g->ptr + done, m->ptr + done, v->ptr + done, n - done, a);
+        TP_LAUNCH_OK(ctx);
+    }
+    return TP_OK;
+}
+
+// f32::powi == compiler-rt __powisf2: square-and-multiply in f32
+float powi_f32(float a, int b) {
+    const bool recip = b < 0;
+    float r = 1.0f;
+    unsigned int e = recip ? (unsigned int)(-(long long)b) : (unsigned int)b;
+    while (true) {
+        if (e & 1u) r *= a;
+        e >>= 1;
+        if (e == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0f / r : r;
+}
+
+}  // namespace
+
+extern "C" {
+
+float tp_adam_step_size(float lr, float beta1, float beta2, int t) {
+    volatile float bc1 = 1.0f - powi_f32(beta1, t);             // src/optim.rs:88
+    volatile float bc2 = 1.0f - powi_f32(beta2, t);             // :89
+    volatile float ratio = sqrtf(bc2) / bc1;
+    return lr * ratio;                                          // :90
+}
+
+int tp_sgd_step(tp_ctx* ctx, tp_buf* p, const tp_buf* g, float lr, float grad_scale, size_t n) {
+    TP_CHECK_ARG(ctx, "tp_sgd_step: NULL ctx");
+    TP_NEED(p, n, "p"); TP_NEED(g, n, "g");
+    if (!n) return TP_OK;
+    sgd_kernel<<<tp::grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(p->ptr, g->ptr, n, lr, grad_scale);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_adam_step(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size, float beta1, float beta2,
+                 float eps, float weight_decay, float grad_scale, size_t n) {
+    AdamArgs a{step_size, beta1, beta2, eps, weight_decay, grad_scale, 1.0f, 0};
+    return launch_adam(ctx, p, g, m, v, n, a, "tp_adam_step");
+}
+
+int tp_adamw_step(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size, float beta1, float beta2,
+                  float eps, float decay_factor, float grad_scale, size_t n) {
+    AdamArgs a{step_size, beta1, beta2, eps, 0.0f, grad_scale, decay_factor, 1};
+    return launch_adam(ctx, p, g, m, v, n, a, "tp_adamw_step");
+}
+
+}  // extern "C"
