@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every symbol that
+include/*.h declares; host-only entry points behave.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import taper_ref as R
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from taper_b200 import capi
+    syms = capi.declared_symbols()
+    assert len(syms) >= 80
+    for name in syms:
+        assert hasattr(capi.lib, name), f"{name} declared in include/ but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    missing = set(syms) - exported
+    assert not missing, f"not exported: {sorted(missing)}"
+
+
+def test_no_torch_or_cxx_types_in_abi():
+    from taper_b200 import capi
+    allowed = {"int", "float", "size_t", "uint64_t", "int64_t", "char", "void", "const", "*",
+               "tp_ctx", "tp_buf", "tp_graph", "tp_model", "tp_trainer", "tp_conv_desc", "tp_pool_desc"}
+    for name, (ret, params) in capi.declared_symbols().items():
+        for decl in [ret] + params:
+            toks = set(decl.replace("*", " * ").split())
+            assert toks <= allowed, f"{name}: non-plain type in signature: {decl!r}"
+
+
+def test_abi_version_and_error_string():
+    from taper_b200 import capi
+    assert capi.lib.tp_abi_version() == 1
+    # NULL out pointer -> TP_ERR_INVALID with a message, no crash (reference would panic)
+    rc = capi.lib.tp_ctx_create(0, None)
+    assert rc == 1
+    assert b"NULL" in capi.lib.tp_last_error()
+
+
+def test_adam_step_size_matches_oracle_powi():          # src/optim.rs:88-90
+    from taper_b200 import capi
+    for t in (1, 2, 3, 10, 100, 1000, 5000):
+        adam = R.Adam([], 1e-3)
+        adam.t = t
+        assert capi.lib.tp_adam_step_size(1e-3, 0.9, 0.999, t) == pytest.approx(float(adam.step_size()), rel=1e-6)
+        got = np.float32(capi.lib.tp_adam_step_size(1e-3, 0.9, 0.999, t))
+        assert got == adam.step_size(), (t, got, adam.step_size())
+
+
+def test_conv_and_pool_out_dims():                      # src/tensor.rs:1254-1255, 1406-1407
+    from taper_b200 import capi
+    d = capi.ConvDesc(4, 1, 28, 28, 32, 3, 3, 1, 1, 1, 1, 1, 1)
+    ho, wo = C.c_int(), C.c_int()
+    assert capi.lib.tp_conv2d_out_dims(C.byref(d), C.byref(ho), C.byref(wo)) == 0
+    assert (ho.value, wo.value) == (28, 28)
+    d = capi.ConvDesc(4, 3, 11, 9, 8, 3, 3, 2, 2, 0, 1, 1, 1)
+    assert capi.lib.tp_conv2d_out_dims(C.byref(d), C.byref(ho), C.byref(wo)) == 0
+    assert (ho.value, wo.value) == ((11 - 3) // 2 + 1, (9 + 2 - 3) // 2 + 1)
+    p = capi.PoolDesc(4, 32, 28, 28, 2, 2, 2, 2, 0, 0)
+    assert capi.lib.tp_pool_out_dims(C.byref(p), C.byref(ho), C.byref(wo)) == 0
+    assert (ho.value, wo.value) == (14, 14)
+    bad = capi.ConvDesc(4, 1, 2, 2, 32, 5, 5, 1, 1, 0, 0, 1, 1)
+    assert capi.lib.tp_conv2d_out_dims(C.byref(bad), C.byref(ho), C.byref(wo)) == 1
