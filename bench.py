@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py — MNIST samples/sec (fwd + bwd + optimizer step) of the tape-evaluation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2|cfg4|example_mlp|cnn2|cnn5] [--impl ours|reference]
+
+A "step" is one iteration of the reference's train_epoch loop body (src/train.rs:106-138): Tape::reset,
+forward, cross-entropy, accuracy, backward, [gradient allreduce], optimizer step, zero_grad — on one
+synthetic MNIST-shaped batch.  One JSON line is printed by rank 0:
+
+  value     whole-job samples/s with the dataset resident in HBM (188 MB > L2; every step gathers a fresh
+            batch on the device), timed with CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the reference-facing trainer call with HOST (pinned) inputs: per step an
+            H2D copy of the batch and a D2H read of {loss, #correct} are inside the timed region (wall clock)
+  roofline  the dominant kernel of the step, timed alone with CUDA events
+  cpu_baseline  the CPU restatement of the reference (oracle/, NumPy + OpenBLAS) on this box's host cores
+
+--impl reference times the oracle port instead (the reference is a Rust crate; no Rust toolchain exists
+in the image), same metric / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F32 = np.float32
+
+CONFIGS = {
+    # name: (layer spec key, oracle builder, batch/GPU, optimizer, lr, weight decay, sample shape, BASELINE.json config text)
+    "cfg2": ("MLP_784_128_10", ("mlp", [784, 128, 10]), 512, "adam", 1e-3, 0.0, (784,),
+             "configs[1]: MLP 784-128-10, batch 512, Adam, fp32, tape fwd/bwd on CUDA"),
+    "cfg1": ("MLP_784_128_10", ("mlp", [784, 128, 10]), 64, "sgd", 0.01, 0.0, (784,),
+             "configs[0]: MLP 784-128-10, batch 64, SGD"),
+    "example_mlp": ("MLP_EXAMPLE", ("mlp", [784, 128, 64, 10]), 256, "adam", 1e-3, 1e-4, (784,),
+                    "examples/train_mnist.rs: MLP 784-128-64-10, batch 256, Adam(1e-3, wd 1e-4)"),
+    "cfg4": ("MLP_784_1024_1024_10", ("mlp", [784, 1024, 1024, 10]), 1024, "adam", 1e-3, 0.0, (784,),
+             "configs[3]: MLP 784-1024-1024-10, batch 1024/GPU, cross-entropy, Adam"),
+    "cnn2": ("CNN2", ("cnn2", None), 256, "adam", 0.01, 1e-4, (1, 28, 28),
+             "configs[2](i): Conv3x3-ReLU-MaxPool x2 + Linear, batch 256, Adam"),
+    "cnn5": ("CNN5", ("cnn5", None), 256, "adam", 0.01, 1e-4, (1, 28, 28),
+             "configs[2](ii): examples/train_mnist_cnn.rs 5-conv CNN, batch 256, Adam"),
+}
+DATASET_N = 60000          # MNIST-sized: 60000 x 784 fp32 = 188 MB, larger than the 126 MB L2
+
+
+def synthetic(n, sample_shape, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n,) + tuple(sample_shape), dtype=F32)          # images U[0,1) (MNIST is u8/255, src/data/mnist.rs:225)
+    y = rng.integers(0, 10, n).astype(F32)                         # labels stored as f32 (src/data/mnist.rs:268)
+    return x, y
+
+
+def mlp_flops(sizes, batch):
+    """Algorithmic GEMM flops of one step: fwd + dW for every layer, dX for all but the first."""
+    f = 0
+    for i in range(len(sizes) - 1):
+        g = 2 * batch * sizes[i] * sizes[i + 1]
+        f += 2 * g + (g if i > 0 else 0)
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [s.strip() for s in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_oracle(kind, arg, seed):
+    from oracle import taper_ref as R
+    rng = np.random.default_rng(seed)
+    if kind == "mlp":
+        return R.build_mlp(arg, rng)
+    return R.build_cnn2(rng) if kind == "cnn2" else R.build_cnn5(rng)
+
+
+def time_oracle(cfg, steps, warmup, batch, budget_s=None):
+    """Times oracle train steps (the CPU restatement of the reference); returns (samples/s, steps run, threads)."""
+    from oracle import taper_ref as R
+    spec_key, (kind, arg), _, opt_kind, lr, wd, sample_shape, _ = cfg
+    model = build_oracle(kind, arg, 0)
+    params = model.parameters()
+    opt = {"sgd": lambda: R.SGD(params, lr), "adam": lambda: R.Adam(params, lr, None, None, wd),
+           "adamw": lambda: R.AdamW(params, lr, None, None, wd)}[opt_kind]()
+    x, y = synthetic(batch * 8, sample_shape, 1)
+    def one(i):
+        s = (i % 8) * batch
+        R.train_step(model, opt, R.Tensor.new(x[s:s + batch], (batch,) + tuple(sample_shape)), R.Tensor.new(y[s:s + batch], (batch,)))
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        one(i)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 5:
+            break
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    return done * batch / dt, done, threads, dt
+
+
+def run_reference(args, cfg_name, cfg):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = cfg[2]
+    sample_batch = batch if cfg_name in ("cfg1", "cfg2", "example_mlp", "cfg4") else 32     # CNN oracle steps are seconds long
+    t_probe = time.perf_counter()
+    v0, _, _, _ = time_oracle(cfg, 2, 1, sample_batch)
+    per_step = (time.perf_counter() - t_probe) / 3
+    steps = args.steps
+    max_steps = max(5, int(150.0 / max(per_step, 1e-6)))
+    sample = f"{steps} steps of batch {sample_batch}"
+    if steps > max_steps:                         # keep the whole run within a few minutes
+        steps = max_steps
+        sample = f"{steps} of the requested {args.steps} steps (150 s cap), batch {sample_batch}"
+    value, done, threads, dt = time_oracle(cfg, steps, args.warmup, sample_batch)
+    out = {
+        "impl": "reference", "metric": "MNIST samples/sec (fwd+bwd+step)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": dt / done * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg[7], "name": cfg_name, "batch_per_gpu": batch, "optimizer": cfg[3]},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": sample + "; NumPy/OpenBLAS restatement of the reference tape (oracle/taper_ref.py); "
+                                            "the Rust reference cannot be built here (no cargo/rustc)"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def measure_tf32_peak():
+    """cuBLAS TF32 8192^3 through torch (library GEMM, used only as the roofline denominator)."""
+    try:
+        import torch
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(8):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); a @ b; e.record(); torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def kernel_rooflines(cfg_name, cfg, peaks, tf32_peak):
+    """Times the step's main kernels alone (CUDA events on the launching stream, L2-cold operands rotated
+    through a pool larger than L2 where the working set allows) and returns roofline entries."""
+    import taper_b200
+    from taper_b200 import capi, host
+    import ctypes as C
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, _ = cfg
+    h = host.host_ctx()
+    lib = capi.lib
+
+    class HB:                                    # tp_buf helper on the host layer's context
+        def __init__(self, n):
+            self.h = C.c_void_p(); self.n = n
+            capi.check(lib.tp_buf_alloc(h, n, C.byref(self.h)))
+            capi.check(lib.tp_buf_fill(h, self.h, 0.5, n))
+        def __del__(self):
+            lib.tp_buf_release(self.h)
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn(0)
+        e0, e1 = host.Event(), host.Event()
+        host.sync()
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record(); e1.sync()
+        return e0.elapsed_ms(e1) / reps * 1e-3
+
+    out = []
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tc_peak = tf32_peak or peaks.get("bf16_tflops", 1590.0) / 2
+    tc_note = "measured cuBLAS TF32 8192^3 (this run)" if tf32_peak else "bf16 measured / 2 (TF32 nominal ratio)"
+    if kind == "mlp":
+        sizes = arg
+        fin, fout = sizes[0], sizes[1]
+        # rotate over enough operand copies that each launch reads L2-cold data (> 126 MB in total)
+        per = (batch * fin + fout * fin + batch * fout) * 4
+        copies = max(2, min(64, int(160e6 // per) + 1))
+        xs = [HB(batch * fin) for _ in range(copies)]
+        ws = [HB(fout * fin) for _ in range(copies)]
+        ys = [HB(batch * fout) for _ in range(copies)]
+        b = HB(fout)
+        def fwd(i):
+            j = i % copies
+            capi.check(lib.tp_linear_fwd(h, xs[j].h, ws[j].h, b.h, ys[j].h, batch, fin, fout, 1))
+        def bwd(i):
+            j = i % copies
+            capi.check(lib.tp_linear_bwd(h, xs[j].h, ws[j].h, ys[j].h, None, None, ws[(j + 1) % copies].h, None, batch, fin, fout, 0, 0, 0))
+        l0 = host.launches(); t = timeit(fwd, 200); n_l = (host.launches() - l0) / 203
+        fl = 2 * batch * fin * fout
+        out.append({"kernel": f"linear_fwd {batch}x{fin}x{fout} (bias+ReLU epilogue)", "bound": "tensor", "achieved": fl / t / 1e12,
+                    "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None,
+                    "launch_us": t * 1e6, "launches_per_call": n_l, "peak_source": tc_note})
+        l0 = host.launches(); t = timeit(bwd, 200); n_l = (host.launches() - l0) / 203
+        out.append({"kernel": f"linear_bwd dW {fout}x{fin} over batch {batch} (split-K)", "bound": "tensor", "achieved": fl / t / 1e12,
+                    "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None,
+                    "launch_us": t * 1e6, "launches_per_call": n_l, "peak_source": tc_note})
+        del xs, ws, ys
+    # fused Adam step over a flat arena larger than L2: 28 B/param (p, g, m, v read; p, m, v written)
+    n = 48 * 1024 * 1024
+    p, g, m, v, hy = HB(n), HB(n), HB(n), HB(n), HB(8)
+    capi.check(lib.tp_adam_hyper_init(h, hy.h, 1e-3, 0.9, 0.999, 1e-8, 0.0))
+    capi.check(lib.tp_adam_advance(h, hy.h))
+    def adam(i):
+        capi.check(lib.tp_adam_step_dev(h, p.h, g.h, m.h, v.h, hy.h, 1.0, 0, n))
+    t = timeit(adam, 20)
+    out.append({"kernel": f"adam_step {n} params (fused, flat arena)", "bound": "hbm", "achieved": 28 * n / t / 1e9, "peak": hbm,
+                "unit": "GB/s", "frac": 28 * n / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
+    # fused elementwise backward (ReLU backward: dY, X -> dX, 12 B/elem)
+    def relu_bwd(i):
+        capi.check(lib.tp_relu_bwd(h, p.h, g.h, m.h, n, 0))
+    t = timeit(relu_bwd, 20)
+    out.append({"kernel": f"relu_bwd {n} elements", "bound": "hbm", "achieved": 12 * n / t / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": 12 * n / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
+    return out
+
+
+def run_ours(args, cfg_name, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, workload = cfg
+
+    import taper_b200                      # raises if libtaper_b200.so is missing: there is no fallback
+    from taper_b200 import host
+    host.set_device(local)
+    host.config(conv_full_adjoint=1 if args.full_adjoint else 0, gemm_mode=args.gemm_mode)
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    model = host.Model(getattr(host, spec_key), seed=0)
+    tr = host.Trainer(model, opt_kind, lr=lr, weight_decay=wd)
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(host.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        tr.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        tr.broadcast_params(0)
+
+    # each rank owns a shard: its own resident dataset (weak scaling: batch/GPU fixed)
+    X, Y = synthetic(DATASET_N, sample_shape, 1 + rank)
+    perm = np.random.default_rng(100 + rank).permutation(DATASET_N).astype(np.uint32)
+    tr.load_dataset(X, Y, perm)
+
+    def barrier():
+        host.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    windows = []
+
+    # ---- value: dataset resident in HBM, CUDA events on the launching stream ---------------------------
+    last = (0.0, 0.0)
+    for _ in range(max(args.warmup, 3)):
+        tr.step_resident(batch)
+        last = tr.fetch()
+    barrier()
+    e0, e1 = host.Event(), host.Event()
+    l0 = host.launches()
+    w0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        if tr.pending() >= 6:
+            last = tr.fetch()
+        tr.step_resident(batch)
+    e1.record()
+    while tr.pending():
+        last = tr.fetch()
+    host.sync()
+    w1 = time.perf_counter()
+    gpu_launches = host.launches() - l0
+    ms = max_over_ranks(e0.elapsed_ms(e1))
+    barrier()
+    windows.append((w0, w1))
+    value = world * batch * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host (pinned) batches through the trainer call; H2D + D2H inside the timed region -----------
+    nbuf = 12
+    pins = [(host.PinnedArray((batch,) + tuple(sample_shape)), host.PinnedArray((batch,))) for _ in range(nbuf)]
+    for j, (px, py) in enumerate(pins):
+        s = (j * batch) % (DATASET_N - batch)
+        px.array[...] = X[s:s + batch]
+        py.array[...] = Y[s:s + batch]
+    for j in range(max(args.warmup, 3)):
+        tr.step_async(pins[j % nbuf][0].array, pins[j % nbuf][1].array, pinned=True)
+        tr.fetch()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        if tr.pending() >= 6:
+            last = tr.fetch()                       # D2H read of {loss, correct} of an earlier step
+        px, py = pins[i % nbuf]
+        tr.step_async(px.array, py.array, pinned=True)
+    while tr.pending():
+        last = tr.fetch()
+    host.sync()
+    t1 = time.perf_counter()
+    e2e_s = max_over_ranks(t1 - t0)
+    barrier()
+    windows.append((t0, t1))
+    e2e_value = world * batch * args.steps / e2e_s
+    clocks = sampler.stop(windows) if sampler else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_peak = measure_tf32_peak() if world == 1 else None
+    roofs = kernel_rooflines(cfg_name, cfg, peaks, tf32_peak) if world == 1 else []
+    # dominant kernel of the step = the one with the largest duration among the step's kernels
+    roofline = max([r for r in roofs if "adam_step" not in r["kernel"] and "relu_bwd" not in r["kernel"]] or roofs or [None],
+                   key=lambda r: r["launch_us"] if r else 0)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_batch = batch if kind == "mlp" else 32
+        v, done, threads, dt = time_oracle(cfg, 10 ** 9, 2, sample_batch, budget_s=12.0)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{done} oracle train steps of batch {sample_batch} in {dt:.1f} s (NumPy/OpenBLAS restatement of the reference tape)"}
+    flops = mlp_flops(arg, batch) if kind == "mlp" else None
+    out = {
+        "metric": "MNIST samples/sec (fwd+bwd+step)", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "name": cfg_name, "batch_per_gpu": batch, "global_batch": batch * world,
+                   "optimizer": opt_kind, "lr": lr, "weight_decay": wd, "parallelism": f"dp{world}",
+                   "gemm_mode": {0: "fp32 FFMA", 1: "3xTF32 tcgen05 (fp32-accurate)", 2: "1xTF32 tcgen05"}[args.gemm_mode],
+                   "conv_adjoint": "full" if args.full_adjoint else "strict_reference (SURVEY A1)",
+                   "l2_policy": f"inputs larger than L2: every step gathers a fresh batch from a {DATASET_N}x{int(np.prod(sample_shape))} "
+                                "fp32 resident dataset (188 MB); parameters/optimizer state are the step's own working set",
+                   "cuda_graph": True, "last_step": {"loss": last[0], "correct": last[1]}},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(batch * (np.prod(sample_shape) + 1) * 4),
+                "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / args.steps * 1e3, "timing": "host wall clock, sync on both sides"},
+        "gpu_launches": int(gpu_launches), "launches_per_step": gpu_launches / args.steps,
+        "clocks": clocks, "roofline": roofline, "kernels": roofs, "cpu_baseline": cpu,
+        "step_gemm_flops": flops,
+        "step_tensor_frac": (flops / (ms / args.steps * 1e-3) / 1e12 / (tf32_peak or 1e9)) if (flops and tf32_peak) else None,
+    }
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2])
+    ap.add_argument("--full-adjoint", action="store_true", help="CNN: compute conv dW/dX (the reference does not, SURVEY A1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.steps is None:
+        args.steps = (20000 if args.config in ("cfg1", "cfg2", "example_mlp") else 300) if args.impl == "ours" else 200
+    if args.impl == "reference":
+        run_reference(args, args.config, cfg)
+    else:
+        run_ours(args, args.config, cfg)
+
+
+if __name__ == "__main__":
+    main()

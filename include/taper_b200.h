@@ -44,6 +44,7 @@ enum {
 typedef struct tp_ctx tp_ctx;
 typedef struct tp_buf tp_buf;
 typedef struct tp_graph tp_graph;
+typedef struct tp_event tp_event;
 
 /* ---------------------------------------------------------------------------------------------
  * Runtime: context, stream, buffers  (replaces Vec<f32> allocation + mimalloc, src/main.rs:7-10)
@@ -74,8 +75,17 @@ int  tp_buf_upload_pinned(tp_ctx* ctx, tp_buf* dst, const void* pinned_host, siz
 int  tp_buf_download(tp_ctx* ctx, const tp_buf* src, void* host, size_t n);  /* Tensor::data()  src/tensor.rs:493-496 */
 int  tp_buf_copy(tp_ctx* ctx, tp_buf* dst, const tp_buf* src, size_t n);     /* Vec::clone, e.g. reshape src/tensor.rs:814 */
 int  tp_buf_fill(tp_ctx* ctx, tp_buf* dst, float value, size_t n);           /* vec![v; n], e.g. backward seed src/tensor.rs:521 */
+/* asynchronous device->pinned-host copy on the context's stream; pair with tp_event_record / tp_event_sync */
+int  tp_buf_download_async(tp_ctx* ctx, const tp_buf* src, void* pinned_host, size_t n);
 int  tp_host_alloc_pinned(size_t bytes, void** out);
 int  tp_host_free_pinned(void* p);
+
+/* Events on the context's stream (timing with CUDA events; host waits for one step's result only). */
+int  tp_event_create(tp_ctx* ctx, tp_event** out);
+int  tp_event_record(tp_ctx* ctx, tp_event* ev);
+int  tp_event_sync(tp_event* ev);
+int  tp_event_elapsed_ms(tp_event* start, tp_event* stop, float* ms);
+int  tp_event_destroy(tp_event* ev);
 
 /* CUDA-graph capture of everything enqueued on the context's stream between begin and end. */
 int  tp_graph_begin(tp_ctx* ctx);
@@ -229,8 +239,29 @@ int tp_adam_step(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, floa
 int tp_adamw_step(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size,
                   float beta1, float beta2, float eps, float decay_factor, float grad_scale, size_t n);
 int tp_scale(tp_ctx*, tp_buf* p, float s, size_t n);            /* AdamW decay of grad-less params */
+/* Device-resident Adam state so that a captured (CUDA-graph) step replays without the host patching
+ * arguments: hyper[8] = { t (int32 bits), lr, beta1, beta2, eps, weight_decay, step_size, decay }.
+ *   tp_adam_advance : t += 1; step_size = lr*sqrt(1-b2^t)/(1-b1^t); decay = 1 - lr*wd   (src/optim.rs:86-90, 157)
+ *   tp_adam_step_dev: Adam::step body (decoupled=0, src/optim.rs:93-110) or AdamW (decoupled=1, :154-164)
+ *   tp_decay_dev    : p *= decay for parameters without a gradient under AdamW (:154-161)            */
+int tp_adam_hyper_init(tp_ctx*, tp_buf* hyper, float lr, float beta1, float beta2, float eps, float weight_decay);
+int tp_adam_hyper_set_lr(tp_ctx*, tp_buf* hyper, float lr);     /* Adam::set_lr  src/optim.rs:125-127 */
+int tp_adam_advance(tp_ctx*, tp_buf* hyper);
+int tp_adam_step_dev(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, const tp_buf* hyper,
+                     float grad_scale, int decoupled, size_t n);
+int tp_decay_dev(tp_ctx*, tp_buf* p, const tp_buf* hyper, size_t n);
 /* lr * sqrt(1 - b2^t) / (1 - b1^t) with f32::powi semantics   src/optim.rs:88-90 */
 float tp_adam_step_size(float lr, float beta1, float beta2, int t);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident dataset: MNISTDataset::get_batch + DataLoader (src/data/mnist.rs:276-309, 326-385).
+ *   dst_x[r, :] = images[perm[(cursor + r) % n_perm], :],  dst_y[r] = labels[perm[...]]   for r < rows
+ *   perm is an int32 index buffer (the shuffled order); cursor is a 1-element int32 device counter that
+ *   tp_cursor_advance moves by `delta` modulo `modulo`, so a captured step walks the dataset by itself.
+ * ------------------------------------------------------------------------------------------- */
+int tp_gather_batch(tp_ctx*, const tp_buf* images, const tp_buf* labels, const tp_buf* perm_i32, const tp_buf* cursor_i32,
+                    tp_buf* dst_x, tp_buf* dst_y, int rows, int cols, int n_perm);
+int tp_cursor_advance(tp_ctx*, tp_buf* cursor_i32, int delta, int modulo);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (no counterpart in the reference: it is single-process).

@@ -1,0 +1,83 @@
+/* taper_b200_host.h — flat C entry points of the C++ host layer (taper::nn / optim / train in
+ * taper_b200/csrc/host/taper.hpp), for drivers that cannot include C++: the Python test-suite, bench.py
+ * and, later, a Rust shim that wants whole-module granularity instead of op granularity.
+ *
+ * The kernel-level boundary is include/taper_b200.h; everything here is composed from it.  Same
+ * conventions: every call returns 0 on success, tp_last_error() holds the message otherwise (the
+ * reference panics); one host thread : one context : one stream.  Citations are path:line in
+ * vaibhawvipul/taper @ aea74b46.
+ */
+#ifndef TAPER_B200_HOST_H
+#define TAPER_B200_HOST_H
+
+#include "taper_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tp_model tp_model;       /* nn::Sequential            src/nn.rs:130-162 */
+typedef struct tp_trainer tp_trainer;   /* train::Trainer            src/train.rs:73-293 */
+
+/* device of this thread's context (call before anything else on the thread); the context itself */
+int tp_host_set_device(int device);
+int tp_host_ctx(tp_ctx** out);
+/* switches (pass -1 to leave one unchanged):
+ *   conv_full_adjoint      0 = reproduce the reference's cut conv autograd chain (default), 1 = full adjoint
+ *   fuse_linear_relu       1 = Sequential runs Linear+ReLU as one fused launch (default)
+ *   reference_op_sequence  1 = Linear records transpose -> matmul -> add_broadcast exactly as src/nn.rs:54-60
+ *   gemm_mode              0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (default), 2 = 1xTF32 tcgen05 */
+int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op_sequence, int gemm_mode);
+
+/* Sequential from a comma-separated layer list (the constructors of src/nn.rs, src/activation.rs):
+ *   linear:IN:OUT[:nobias] | relu | conv:CIN:COUT:K:STRIDE:PAD | conv_relu:CIN:COUT:K:STRIDE:PAD |
+ *   maxpool:K:STRIDE | avgpool:K:STRIDE | gap (AdaptiveAvgPool2d::global) | flatten
+ * Weights are drawn from the reference's init distributions with a seeded generator. */
+int tp_model_create(const char* spec, uint64_t seed, tp_model** out);
+int tp_model_destroy(tp_model* m);
+int tp_model_num_params(tp_model* m, int* count);                    /* Module::parameters  src/nn.rs:17 */
+int tp_model_param_info(tp_model* m, int index, size_t* numel, int* ndim, size_t* dims4);
+int tp_model_set_param(tp_model* m, int index, const float* host, size_t n);
+int tp_model_get_param(tp_model* m, int index, float* host, size_t n);
+int tp_model_get_grad(tp_model* m, int index, float* host, size_t n, int* has_grad);   /* has_grad = 0 <=> None */
+int tp_model_zero_grad(tp_model* m);
+/* Module::forward on a host batch; out receives the logits (out_cap floats available) */
+int tp_model_forward(tp_model* m, const float* x, const size_t* shape, int ndim, float* out, size_t out_cap, size_t* out_n);
+/* Tape::reset; forward; cross_entropy_loss; accuracy; loss.backward()  — no optimizer (src/train.rs:108-121) */
+int tp_model_loss_backward(tp_model* m, const float* x, const size_t* shape, int ndim, const float* labels,
+                           float* loss, float* correct, size_t* tape_len);
+
+/* Trainer over a model; optimizer is "sgd" | "adam" | "adamw" (src/optim.rs).  The trainer shares the model's
+ * parameters (they are re-homed into one flat arena). */
+int tp_trainer_create(tp_model* m, const char* optimizer, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, tp_trainer** out);
+int tp_trainer_destroy(tp_trainer* t);
+int tp_trainer_set_lr(tp_trainer* t, float lr);                      /* Adam::set_lr  src/optim.rs:125-127 */
+int tp_trainer_set_use_graph(tp_trainer* t, int on);
+/* one train_epoch iteration (src/train.rs:106-138), synchronous, host inputs */
+int tp_trainer_step(tp_trainer* t, const float* images, const float* labels, size_t batch, const size_t* sample_shape,
+                    int ndim, float* loss, float* correct);
+/* the same, asynchronous: inputs are copied from (pinned) host memory on the stream; results are read with
+ * tp_trainer_fetch in FIFO order (at most 8 outstanding) */
+int tp_trainer_step_async(tp_trainer* t, const float* images, const float* labels, size_t batch,
+                          const size_t* sample_shape, int ndim, int pinned);
+/* device-resident dataset + on-device batch gather (MNISTDataset::get_batch, src/data/mnist.rs:276-309) */
+int tp_trainer_load_dataset(tp_trainer* t, const float* images, const float* labels, size_t n,
+                            const size_t* sample_shape, int ndim, const uint32_t* perm);
+int tp_trainer_step_resident(tp_trainer* t, size_t batch);
+int tp_trainer_fetch(tp_trainer* t, float* loss, float* correct);
+int tp_trainer_pending(tp_trainer* t, size_t* count);
+/* Trainer::evaluate body (src/train.rs:156-166) on one host batch */
+int tp_trainer_eval(tp_trainer* t, const float* images, const float* labels, size_t batch, const size_t* sample_shape,
+                    int ndim, float* loss, float* correct);
+int tp_trainer_save_checkpoint(tp_trainer* t, const char* path);     /* src/train.rs:264-292 */
+int tp_trainer_load_checkpoint(tp_trainer* t, const char* path);
+/* data-parallel replica: NCCL rank binding, parameter broadcast; gradients are allreduced inside every step */
+int tp_trainer_comm_init(tp_trainer* t, int rank, int world, const void* unique_id128);
+int tp_trainer_broadcast_params(tp_trainer* t, int root);
+int tp_trainer_graph_replays(tp_trainer* t, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAPER_B200_HOST_H */

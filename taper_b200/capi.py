@@ -34,9 +34,9 @@ class PoolDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n", "c", "h", "w", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w")]
 
 
-_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_model", "tp_trainer")
+_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer")
 _BASE = {
-    "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t, "uint64_t": C.c_uint64,
+    "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32,
     "int64_t": C.c_int64, "char": C.c_char, "void": None,
     "tp_conv_desc": ConvDesc, "tp_pool_desc": PoolDesc,
 }

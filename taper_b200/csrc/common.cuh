@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 #include "../../include/taper_b200.h"
 
@@ -17,14 +18,17 @@ void set_error(const char* fmt, ...);
 
 struct Allocator {
     // Size-bucketed caching allocator.  Single stream per context, so a block freed by the host
-    // and re-used by a later launch is ordered after every earlier use; LIFO free lists make the
-    // address sequence of a repeated alloc/free pattern (one training step) deterministic, which
-    // is what lets a whole step be captured in a CUDA graph and replayed.
+    // and re-used by a later launch is ordered after every earlier use (no events needed).
+    // A context has one main pool plus, while a CUDA graph is being captured, a private pool that
+    // the finished graph then owns: memory a captured step uses as scratch is never handed to
+    // anyone else while the graph can still be replayed.
     std::unordered_map<size_t, std::vector<void*>> free_lists;
-    std::vector<void*> all_blocks;
+    std::unordered_set<void*> all_blocks;
     size_t in_use = 0, reserved = 0;
+    size_t live_bufs = 0;            // tp_bufs currently allocated from this pool
+    bool orphaned = false;           // owner (graph) is gone; delete when live_bufs reaches 0
     static size_t bucket(size_t bytes);
-    void* alloc(size_t bytes, size_t* cap);
+    void* alloc(size_t bytes, size_t* cap, Allocator* steal_from = nullptr, bool relaxed_capture = false);
     void free(void* p, size_t cap);
     void release_all();
 };
@@ -36,6 +40,7 @@ struct tp_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     tp::Allocator alloc;
+    tp::Allocator* capture_pool = nullptr;   // non-null between tp_graph_begin and tp_graph_end
     uint64_t launches = 0;
     int gemm_mode = 1;               // 0 exact fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
     int* dev_error = nullptr;        // sticky device-side error flag
@@ -57,6 +62,7 @@ struct tp_buf {
     float* ptr = nullptr;
     size_t n = 0;
     size_t cap = 0;                  // allocator bucket bytes (0 for views / external)
+    tp::Allocator* pool = nullptr;   // pool the block came from
     std::atomic<int> rc{1};
     tp_buf* parent = nullptr;        // for slices
     bool external = false;

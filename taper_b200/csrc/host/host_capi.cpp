@@ -1,0 +1,300 @@
+// Flat C entry points of the host layer (include/taper_b200_host.h).  No exception crosses the boundary.
+#include "taper_internal.hpp"
+#include "../../../include/taper_b200_host.h"
+#include "../common.cuh"
+
+#include <cstring>
+#include <sstream>
+
+using namespace taper;
+
+struct tp_model {
+    std::shared_ptr<nn::Sequential> seq;
+    std::vector<Tensor> params;
+};
+
+struct tp_trainer {
+    std::shared_ptr<train::Trainer> tr;
+};
+
+namespace {
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return TP_OK;
+    } catch (const std::exception& e) {
+        std::string msg = e.what();          // copy first: set_error overwrites the thread-local a nested what() may alias
+        tp::set_error("%s", msg.c_str());
+        return TP_ERR_INVALID;
+    }
+}
+
+std::vector<std::string> split(const std::string& s, char sep) {
+    std::vector<std::string> out;
+    std::stringstream ss(s);
+    std::string item;
+    while (std::getline(ss, item, sep)) out.push_back(item);
+    return out;
+}
+
+size_t num(const std::vector<std::string>& f, size_t i, const std::string& layer) {
+    if (i >= f.size()) panic("layer '%s': missing field %zu", layer.c_str(), i);
+    return (size_t)std::stoul(f[i]);
+}
+
+Shape to_shape(const size_t* dims, int ndim) { return Shape(dims, dims + ndim); }
+
+}  // namespace
+
+extern "C" {
+
+int tp_host_set_device(int device) { return guarded([&] { set_device(device); }); }
+
+int tp_host_ctx(tp_ctx** out) {
+    return guarded([&] {
+        if (!out) panic("tp_host_ctx: NULL out pointer");
+        *out = ctx();
+    });
+}
+
+int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op_sequence, int gemm_mode) {
+    return guarded([&] {
+        if (conv_full_adjoint >= 0) Config::conv_full_adjoint() = conv_full_adjoint != 0;
+        if (fuse_linear_relu >= 0) Config::fuse_linear_relu() = fuse_linear_relu != 0;
+        if (reference_op_sequence >= 0) Config::reference_op_sequence() = reference_op_sequence != 0;
+        if (gemm_mode >= 0) check(tp_set_gemm_mode(ctx(), gemm_mode));
+    });
+}
+
+int tp_model_create(const char* spec, uint64_t seed, tp_model** out) {
+    return guarded([&] {
+        if (!spec || !out) panic("tp_model_create: NULL argument");
+        std::vector<std::shared_ptr<nn::Module>> layers;
+        uint64_t s = seed;
+        for (auto& item : split(spec, ',')) {
+            auto f = split(item, ':');
+            if (f.empty() || f[0].empty()) continue;
+            const std::string& k = f[0];
+            if (k == "linear") {
+                bool bias = !(f.size() > 3 && f[3] == "nobias");
+                layers.push_back(std::make_shared<nn::Linear>(num(f, 1, item), num(f, 2, item), bias, s++));
+            } else if (k == "relu") {
+                layers.push_back(std::make_shared<nn::ReLU>());
+            } else if (k == "conv" || k == "conv_relu") {
+                size_t cin = num(f, 1, item), cout = num(f, 2, item), ks = num(f, 3, item), st = num(f, 4, item), pd = num(f, 5, item);
+                if (k == "conv")
+                    layers.push_back(std::make_shared<nn::Conv2d>(cin, cout, Pair{ks, ks}, Pair{st, st}, Pair{pd, pd}, std::nullopt, std::nullopt, true, s++));
+                else
+                    layers.push_back(std::make_shared<nn::Conv2dReLU>(cin, cout, Pair{ks, ks}, Pair{st, st}, Pair{pd, pd}, std::nullopt, std::nullopt, true, s++));
+            } else if (k == "maxpool") {
+                size_t ks = num(f, 1, item), st = num(f, 2, item);
+                layers.push_back(std::make_shared<nn::MaxPool2d>(Pair{ks, ks}, Pair{st, st}, std::nullopt));
+            } else if (k == "avgpool") {
+                size_t ks = num(f, 1, item), st = num(f, 2, item);
+                layers.push_back(std::make_shared<nn::AvgPool2d>(Pair{ks, ks}, Pair{st, st}, std::nullopt));
+            } else if (k == "gap") {
+                layers.push_back(std::make_shared<nn::AdaptiveAvgPool2d>(nn::AdaptiveAvgPool2d::global()));
+            } else if (k == "flatten") {
+                layers.push_back(std::make_shared<nn::Flatten>(1));
+            } else {
+                panic("tp_model_create: unknown layer '%s'", item.c_str());
+            }
+        }
+        auto* m = new tp_model();
+        m->seq = std::make_shared<nn::Sequential>(std::move(layers));
+        m->params = m->seq->parameters();
+        *out = m;
+    });
+}
+
+int tp_model_destroy(tp_model* m) {
+    return guarded([&] { delete m; });
+}
+
+int tp_model_num_params(tp_model* m, int* count) {
+    return guarded([&] {
+        if (!m || !count) panic("tp_model_num_params: NULL argument");
+        *count = (int)m->params.size();
+    });
+}
+
+static Tensor& param_at(tp_model* m, int index) {
+    if (!m || index < 0 || (size_t)index >= m->params.size()) panic("parameter index %d out of range", index);
+    return m->params[index];
+}
+
+int tp_model_param_info(tp_model* m, int index, size_t* numel, int* ndim, size_t* dims4) {
+    return guarded([&] {
+        Tensor& p = param_at(m, index);
+        if (numel) *numel = p.numel();
+        if (ndim) *ndim = (int)p.shape().size();
+        if (dims4) for (size_t i = 0; i < p.shape().size() && i < 4; ++i) dims4[i] = p.shape()[i];
+    });
+}
+
+int tp_model_set_param(tp_model* m, int index, const float* host, size_t n) {
+    return guarded([&] {
+        Tensor& p = param_at(m, index);
+        if (!host || n != p.numel()) panic("tp_model_set_param: expected %zu floats", p.numel());
+        p.set_data(std::vector<float>(host, host + n));
+    });
+}
+
+int tp_model_get_param(tp_model* m, int index, float* host, size_t n) {
+    return guarded([&] {
+        Tensor& p = param_at(m, index);
+        if (!host || n != p.numel()) panic("tp_model_get_param: expected %zu floats", p.numel());
+        std::memcpy(host, p.data().data(), n * sizeof(float));
+    });
+}
+
+int tp_model_get_grad(tp_model* m, int index, float* host, size_t n, int* has_grad) {
+    return guarded([&] {
+        Tensor& p = param_at(m, index);
+        tp_buf* g = p.grad_buf();
+        if (has_grad) *has_grad = g ? 1 : 0;
+        if (g && host) {
+            if (n != p.numel()) panic("tp_model_get_grad: expected %zu floats", p.numel());
+            check(tp_buf_download(ctx(), g, host, n));
+        }
+    });
+}
+
+int tp_model_zero_grad(tp_model* m) {
+    return guarded([&] {
+        if (!m) panic("tp_model_zero_grad: NULL model");
+        for (auto& p : m->params) p.zero_grad();
+    });
+}
+
+int tp_model_forward(tp_model* m, const float* x, const size_t* shape, int ndim, float* out, size_t out_cap, size_t* out_n) {
+    return guarded([&] {
+        if (!m || !x || !shape || !out) panic("tp_model_forward: NULL argument");
+        Tensor in = Tensor::from_host(x, to_shape(shape, ndim));
+        Tensor y = m->seq->forward(in);
+        if (out_n) *out_n = y.numel();
+        if (y.numel() > out_cap) panic("tp_model_forward: output needs %zu floats, %zu available", y.numel(), out_cap);
+        std::memcpy(out, y.data().data(), y.numel() * sizeof(float));
+        Tape::reset();
+    });
+}
+
+int tp_model_loss_backward(tp_model* m, const float* x, const size_t* shape, int ndim, const float* labels, float* loss,
+                           float* correct, size_t* tape_len) {
+    return guarded([&] {
+        if (!m || !x || !shape || !labels) panic("tp_model_loss_backward: NULL argument");
+        Tape::reset();
+        Shape s = to_shape(shape, ndim);
+        Tensor in = Tensor::from_host(x, s);
+        Tensor t = Tensor::from_host(labels, {s[0]});
+        Tensor logits = m->seq->forward(in);
+        Tensor l = loss::cross_entropy_loss(logits, t);
+        Tensor c = loss::accuracy_count(logits, t);
+        if (tape_len) *tape_len = Tape::len();
+        l.backward();
+        if (loss) *loss = l.item();
+        if (correct) *correct = c.item();
+        Tape::reset();
+    });
+}
+
+int tp_trainer_create(tp_model* m, const char* optimizer, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      tp_trainer** out) {
+    return guarded([&] {
+        if (!m || !optimizer || !out) panic("tp_trainer_create: NULL argument");
+        std::shared_ptr<optim::Optimizer> opt;
+        std::string k = optimizer;
+        if (k == "sgd") opt = std::make_shared<optim::SGD>(m->params, lr);
+        else if (k == "adam") opt = std::make_shared<optim::Adam>(m->params, lr, std::make_pair(beta1, beta2), eps, weight_decay);
+        else if (k == "adamw") opt = std::make_shared<optim::AdamW>(m->params, lr, std::make_pair(beta1, beta2), eps, weight_decay);
+        else panic("tp_trainer_create: unknown optimizer '%s'", optimizer);
+        auto* t = new tp_trainer();
+        t->tr = std::make_shared<train::Trainer>(m->seq, opt, nullptr);
+        *out = t;
+    });
+}
+
+int tp_trainer_destroy(tp_trainer* t) {
+    return guarded([&] { delete t; });
+}
+
+#define TRAINER(t) do { if (!(t) || !(t)->tr) panic("%s: NULL trainer", __func__); } while (0)
+
+int tp_trainer_set_lr(tp_trainer* t, float lr) {
+    return guarded([&] { TRAINER(t); t->tr->optimizer->set_lr(lr); });
+}
+
+int tp_trainer_set_use_graph(tp_trainer* t, int on) {
+    return guarded([&] { TRAINER(t); t->tr->set_use_graph(on != 0); });
+}
+
+int tp_trainer_step(tp_trainer* t, const float* images, const float* labels, size_t batch, const size_t* sample_shape, int ndim,
+                    float* loss, float* correct) {
+    return guarded([&] {
+        TRAINER(t);
+        train::StepResult r = t->tr->train_batch(images, labels, batch, to_shape(sample_shape, ndim));
+        if (loss) *loss = r.loss;
+        if (correct) *correct = r.correct;
+    });
+}
+
+int tp_trainer_step_async(tp_trainer* t, const float* images, const float* labels, size_t batch, const size_t* sample_shape,
+                          int ndim, int pinned) {
+    return guarded([&] { TRAINER(t); t->tr->train_batch_async(images, labels, batch, to_shape(sample_shape, ndim), pinned != 0); });
+}
+
+int tp_trainer_load_dataset(tp_trainer* t, const float* images, const float* labels, size_t n, const size_t* sample_shape,
+                            int ndim, const uint32_t* perm) {
+    return guarded([&] { TRAINER(t); t->tr->load_dataset(images, labels, n, to_shape(sample_shape, ndim), perm); });
+}
+
+int tp_trainer_step_resident(tp_trainer* t, size_t batch) {
+    return guarded([&] { TRAINER(t); t->tr->train_batch_resident(batch); });
+}
+
+int tp_trainer_fetch(tp_trainer* t, float* loss, float* correct) {
+    return guarded([&] {
+        TRAINER(t);
+        train::StepResult r = t->tr->fetch();
+        if (loss) *loss = r.loss;
+        if (correct) *correct = r.correct;
+    });
+}
+
+int tp_trainer_pending(tp_trainer* t, size_t* count) {
+    return guarded([&] { TRAINER(t); if (count) *count = t->tr->pending(); });
+}
+
+int tp_trainer_eval(tp_trainer* t, const float* images, const float* labels, size_t batch, const size_t* sample_shape, int ndim,
+                    float* loss, float* correct) {
+    return guarded([&] {
+        TRAINER(t);
+        train::StepResult r = t->tr->eval_batch(images, labels, batch, to_shape(sample_shape, ndim));
+        if (loss) *loss = r.loss;
+        if (correct) *correct = r.correct;
+    });
+}
+
+int tp_trainer_save_checkpoint(tp_trainer* t, const char* path) {
+    return guarded([&] { TRAINER(t); t->tr->save_checkpoint(path); });
+}
+
+int tp_trainer_load_checkpoint(tp_trainer* t, const char* path) {
+    return guarded([&] { TRAINER(t); t->tr->load_checkpoint(path); });
+}
+
+int tp_trainer_comm_init(tp_trainer* t, int rank, int world, const void* unique_id128) {
+    return guarded([&] { TRAINER(t); t->tr->init_data_parallel(rank, world, unique_id128); });
+}
+
+int tp_trainer_broadcast_params(tp_trainer* t, int root) {
+    return guarded([&] { TRAINER(t); t->tr->broadcast_parameters(root); });
+}
+
+int tp_trainer_graph_replays(tp_trainer* t, uint64_t* count) {
+    return guarded([&] { TRAINER(t); if (count) *count = t->tr->graph_replays(); });
+}
+
+}  // extern "C"

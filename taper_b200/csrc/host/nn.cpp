@@ -1,0 +1,369 @@
+// Host layer, part 2: nn modules, losses, optimizers, LR schedulers, the data-parallel group.
+// Mirrors src/nn.rs, src/activation.rs, src/loss.rs and src/optim.rs of the reference.
+#include "taper_internal.hpp"
+
+#include <cmath>
+#include <random>
+
+namespace taper {
+
+// =====================================================================================================
+// nn  (src/nn.rs)
+// =====================================================================================================
+namespace nn {
+
+static std::vector<float> uniform_init(size_t n, float bound, uint64_t seed) {
+    // Uniform::new_inclusive(-bound, bound) drawn from thread_rng in the reference (src/nn.rs:36-41);
+    // seeded here so runs are reproducible.  Parity tests inject weights explicitly.
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<float> d(-bound, bound);
+    std::vector<float> v(n);
+    for (auto& x : v) x = d(rng);
+    return v;
+}
+
+Linear::Linear(size_t in_features, size_t out_features, bool with_bias, uint64_t seed) {
+    float scale = std::sqrt(2.0f / (float)in_features);                          // src/nn.rs:36
+    weight = Tensor::create(uniform_init(in_features * out_features, scale, seed), {out_features, in_features}).requires_grad();
+    if (with_bias) bias = Tensor::zeros({out_features}).requires_grad();         // src/nn.rs:46-47
+}
+
+Tensor Linear::forward(const Tensor& input) const {
+    if (Config::reference_op_sequence()) {
+        Tensor out = input.matmul(weight.transpose());                           // src/nn.rs:55
+        if (bias) out = out.add_broadcast(*bias);                                // src/nn.rs:56-58
+        return out;
+    }
+    return input.linear(weight, bias ? &*bias : nullptr, false);
+}
+
+Tensor Linear::forward_fused_relu(const Tensor& input) const {
+    return input.linear(weight, bias ? &*bias : nullptr, true);
+}
+
+std::vector<Tensor> Linear::parameters() const {
+    std::vector<Tensor> p{weight};
+    if (bias) p.push_back(*bias);
+    return p;
+}
+
+Tensor Sequential::forward(const Tensor& input) const {                         // src/nn.rs:149-151
+    Tensor x = input;
+    const bool fuse = Config::fuse_linear_relu() && !Config::reference_op_sequence();
+    for (size_t i = 0; i < layers.size(); ++i) {
+        if (fuse && i + 1 < layers.size()) {
+            // peephole: Linear followed by ReLU -> bias + ReLU in the GEMM epilogue, mask folded into backward
+            auto* lin = dynamic_cast<const Linear*>(layers[i].get());
+            auto* act = dynamic_cast<const ReLU*>(layers[i + 1].get());
+            if (lin && act) {
+                x = lin->forward_fused_relu(x);
+                ++i;
+                continue;
+            }
+        }
+        x = layers[i]->forward(x);
+    }
+    return x;
+}
+
+std::vector<Tensor> Sequential::parameters() const {                             // src/nn.rs:153-155
+    std::vector<Tensor> out;
+    for (auto& l : layers)
+        for (auto& p : l->parameters()) out.push_back(p);
+    return out;
+}
+
+Conv2d::Conv2d(size_t in_channels, size_t out_channels, Pair kernel_size, std::optional<Pair> stride_,
+               std::optional<Pair> padding_, std::optional<Pair> dilation_, std::optional<size_t> groups_, bool with_bias,
+               uint64_t seed)
+    : stride(stride_.value_or(Pair{1, 1})), padding(padding_.value_or(Pair{0, 0})),
+      dilation(dilation_.value_or(Pair{1, 1})), groups(groups_.value_or(1)) {
+    if (groups != 1) panic("Conv2d: groups > 1 is outside the hot path (the reference's grouped path records no gradients)");
+    size_t fan_in = in_channels * kernel_size.first * kernel_size.second / groups;
+    float bound = std::sqrt(2.0f / (float)fan_in) * std::sqrt(3.0f);             // src/nn.rs:219-221
+    weight = Tensor::create(uniform_init(out_channels * in_channels * kernel_size.first * kernel_size.second, bound, seed),
+                            {out_channels, in_channels, kernel_size.first, kernel_size.second}).requires_grad();
+    if (with_bias) bias = Tensor::zeros({out_channels}).requires_grad();
+}
+
+Tensor Conv2d::forward(const Tensor& input) const {                              // src/nn.rs:279-289
+    return input.conv2d(weight, bias ? &*bias : nullptr, stride, padding, dilation);
+}
+
+std::vector<Tensor> Conv2d::parameters() const {
+    std::vector<Tensor> p{weight};
+    if (bias) p.push_back(*bias);
+    return p;
+}
+
+Tensor Conv2dReLU::forward(const Tensor& input) const {                          // src/nn.rs:470-479
+    return input.conv2d_relu(weight, bias ? &*bias : nullptr, stride, padding, dilation);
+}
+
+Tensor AdaptiveAvgPool2d::forward(const Tensor& input) const {                   // src/nn.rs:670-686
+    if (input.shape().size() != 4) panic("AdaptiveAvgPool2d expects [N,C,H,W]");
+    size_t kh = input.shape()[2] / output_size.first, kw = input.shape()[3] / output_size.second;
+    return input.avg_pool2d({kh, kw}, Pair{kh, kw}, {0, 0});
+}
+
+}  // namespace nn
+
+// =====================================================================================================
+// loss  (src/loss.rs)
+// =====================================================================================================
+namespace loss {
+
+Tensor log_softmax(const Tensor& x, int dim) {                                   // src/loss.rs:101-126, op for op
+    int nd = (int)x.shape().size();
+    int d = dim < 0 ? nd + dim : dim;
+    if (d != nd - 1 || nd != 2) panic("Only last-dim log_softmax on [B,C] is supported");
+    Tensor max_vals = x.max((size_t)d).first;                                    // no tape node
+    Tensor shifted = x.sub_broadcast_rows(max_vals);
+    Tensor sum_exp = shifted.exp().sum((size_t)d, true);
+    Tensor log_sum = sum_exp.log();
+    return shifted.sub_broadcast_rows(log_sum);
+}
+
+Tensor softmax(const Tensor& x, int dim) {
+    // The reference body uses non-broadcasting `-` and `/` and panics for C > 1; this is the
+    // evident intent: a row-wise stable softmax (single fused kernel, no tape node).
+    int nd = (int)x.shape().size();
+    int d = dim < 0 ? nd + dim : dim;
+    if (d != nd - 1 || nd != 2) panic("Only last-dim softmax on [B,C] is supported");
+    Tensor out = Tensor::empty(x.shape());
+    check(tp_softmax_fwd(ctx(), x.buf(), out.buf(), (int)x.shape()[0], (int)x.shape()[1]));
+    return out;
+}
+
+Tensor cross_entropy_loss_into(const Tensor& logits, const Tensor& targets, const Tensor& out) {
+    const Shape& ts = targets.shape();
+    if (!(ts.size() == 1 || (ts.size() == 2 && ts[1] == 1))) panic("targets must be [B] or [B,1]");     // src/loss.rs:137-141
+    if (logits.shape().size() != 2 || logits.shape()[0] != ts[0]) panic("logits must be [B,C] with the targets' batch size");
+    int rows = (int)logits.shape()[0], cols = (int)logits.shape()[1];
+    Tensor logp = Tensor::empty(logits.shape());
+    // fused log_softmax + NLL mean (src/loss.rs:152-165); the six log_softmax nodes the reference records are
+    // dead in backward, so a single node carrying the direct gradient is recorded instead.
+    check(tp_softmax_xent_fwd(ctx(), logits.buf(), targets.buf(), logp.buf(), out.buf(), rows, cols));
+    Tensor o = out;
+    if (logits.needs_grad()) {
+        o.set_requires_grad(true);
+        Tensor lg = logits, t = targets;
+        Tape::push_unary_op(lg, o, [lg, t, logp, o, rows, cols]() {             // src/loss.rs:174-191
+            tp_buf* g = o.grad_buf();
+            if (!g) return;
+            int acc;
+            tp_buf* gl = lg.impl()->grad_for_write(&acc);
+            check(tp_softmax_xent_bwd(ctx(), logp.buf(), t.buf(), g, gl, rows, cols, acc));
+        });
+    }
+    return o;
+}
+
+Tensor cross_entropy_loss(const Tensor& logits, const Tensor& targets) {         // src/loss.rs:136-195
+    return cross_entropy_loss_into(logits, targets, Tensor::empty({1}));
+}
+
+void accuracy_count_into(const Tensor& predictions, const Tensor& targets, const Tensor& out) {
+    if (predictions.shape().size() != 2 || predictions.shape()[0] != targets.shape()[0]) panic("accuracy: batch size mismatch");
+    check(tp_accuracy_count(ctx(), predictions.buf(), targets.buf(), out.buf(), (int)predictions.shape()[0], (int)predictions.shape()[1]));
+}
+
+Tensor accuracy_count(const Tensor& predictions, const Tensor& targets) {
+    Tensor out = Tensor::empty({1});
+    accuracy_count_into(predictions, targets, out);
+    return out;
+}
+
+float accuracy(const Tensor& predictions, const Tensor& targets) {              // src/loss.rs:271-290
+    float correct = accuracy_count(predictions, targets).item();
+    return correct / (float)targets.shape()[0];
+}
+
+}  // namespace loss
+
+// =====================================================================================================
+// optim  (src/optim.rs)
+// =====================================================================================================
+namespace optim {
+
+// Flat arenas: parameters, gradients and Adam moments each live in ONE contiguous device buffer (every
+// parameter starts on a 16-byte boundary).  The optimizer step is then one fused launch and the
+// data-parallel exchange is one allreduce over the gradient arena.  Tensor handles keep working because
+// their buffers are re-pointed at slices of the arena.
+struct Arena {
+    std::vector<Tensor> params;
+    std::vector<size_t> off;
+    size_t total = 0;
+    tp_buf *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr, *hyper = nullptr;
+    std::vector<tp_buf*> ps, gs, ms, vs;          // per-parameter slices
+
+    Arena(std::vector<Tensor> prm, bool moments) : params(std::move(prm)) {
+        for (auto& t : params) {
+            off.push_back(total);
+            total += (t.numel() + 3) & ~(size_t)3;
+        }
+        tp_ctx* c = ctx();
+        size_t cap = total ? total : 4;
+        check(tp_buf_alloc(c, cap, &p));
+        check(tp_buf_alloc(c, cap, &g));
+        check(tp_buf_fill(c, p, 0.0f, cap));
+        check(tp_buf_fill(c, g, 0.0f, cap));
+        if (moments) {
+            check(tp_buf_alloc(c, cap, &m));
+            check(tp_buf_alloc(c, cap, &v));
+            check(tp_buf_fill(c, m, 0.0f, cap));                                 // src/optim.rs:62-71
+            check(tp_buf_fill(c, v, 0.0f, cap));
+            check(tp_buf_alloc(c, 8, &hyper));
+        }
+        for (size_t i = 0; i < params.size(); ++i) {
+            TensorImpl& im = *params[i].impl();
+            size_t n = im.n;
+            tp_buf *sp, *sg, *sm = nullptr, *sv = nullptr;
+            check(tp_buf_slice(p, off[i], n, &sp));
+            check(tp_buf_slice(g, off[i], n, &sg));
+            check(tp_buf_copy(c, sp, im.buf, n));
+            if (im.has_grad && im.grad) check(tp_buf_copy(c, sg, im.grad, n));
+            tp_buf_release(im.buf);
+            if (im.grad) tp_buf_release(im.grad);
+            im.buf = sp;  tp_buf_retain(sp);
+            im.grad = sg; tp_buf_retain(sg);
+            if (moments) {
+                check(tp_buf_slice(m, off[i], n, &sm));
+                check(tp_buf_slice(v, off[i], n, &sv));
+            }
+            ps.push_back(sp); gs.push_back(sg); ms.push_back(sm); vs.push_back(sv);
+        }
+    }
+    ~Arena() {
+        for (auto* b : ps) tp_buf_release(b);
+        for (auto* b : gs) tp_buf_release(b);
+        for (auto* b : ms) tp_buf_release(b);
+        for (auto* b : vs) tp_buf_release(b);
+        tp_buf_release(p); tp_buf_release(g); tp_buf_release(m); tp_buf_release(v); tp_buf_release(hyper);
+    }
+    bool all_have_grad() const {
+        for (auto& t : params) if (!t.impl()->has_grad) return false;
+        return true;
+    }
+    void bump_versions() { for (auto& t : params) t.impl()->version++; }
+};
+
+tp_buf* arena_grad_buf(const std::shared_ptr<Arena>& a) { return a->g; }
+size_t arena_total(const std::shared_ptr<Arena>& a) { return a->total; }
+tp_buf* arena_param_buf(const std::shared_ptr<Arena>& a) { return a->p; }
+
+// ---- SGD  (src/optim.rs:8-40) ----------------------------------------------------------------------
+SGD::SGD(std::vector<Tensor> params, float lr, std::optional<float> /*momentum: ignored, :14-17*/)
+    : params_(params), lr_(lr), arena_(std::make_shared<Arena>(std::move(params), false)) {}
+SGD::~SGD() = default;
+
+void SGD::step() {                                                               // :21-33
+    Arena& a = *arena_;
+    if (a.all_have_grad()) {
+        check(tp_sgd_step(ctx(), a.p, a.g, lr_, grad_scale_, a.total));
+    } else {
+        for (size_t i = 0; i < a.params.size(); ++i)
+            if (a.params[i].impl()->has_grad) check(tp_sgd_step(ctx(), a.ps[i], a.gs[i], lr_, grad_scale_, a.params[i].numel()));
+    }
+    a.bump_versions();
+}
+
+void SGD::zero_grad() { for (auto& p : params_) p.zero_grad(); }                 // :35-39
+
+// ---- Adam  (src/optim.rs:43-128) -----------------------------------------------------------------------
+Adam::Adam(std::vector<Tensor> params, float lr, std::optional<std::pair<float, float>> betas, std::optional<float> eps,
+           std::optional<float> weight_decay)
+    : params_(params), lr_(lr), beta1_(betas ? betas->first : 0.9f), beta2_(betas ? betas->second : 0.999f),
+      eps_(eps.value_or(1e-8f)), weight_decay_(weight_decay.value_or(0.0f)),
+      arena_(std::make_shared<Arena>(std::move(params), true)) {
+    check(tp_adam_hyper_init(ctx(), arena_->hyper, lr_, beta1_, beta2_, eps_, weight_decay_));
+}
+Adam::~Adam() = default;
+
+void Adam::set_lr(float lr) {                                                    // :125-127
+    lr_ = lr;
+    check(tp_adam_hyper_set_lr(ctx(), arena_->hyper, lr));
+}
+
+void Adam::step_impl(bool decoupled) {
+    Arena& a = *arena_;
+    tp_ctx* c = ctx();
+    t_ += 1;                                                                     // :86 (even if every grad is None)
+    check(tp_adam_advance(c, a.hyper));                                          // same increment, on the device
+    if (a.all_have_grad()) {
+        check(tp_adam_step_dev(c, a.p, a.g, a.m, a.v, a.hyper, grad_scale_, decoupled ? 1 : 0, a.total));
+    } else {
+        for (size_t i = 0; i < a.params.size(); ++i) {
+            size_t n = a.params[i].numel();
+            if (a.params[i].impl()->has_grad) check(tp_adam_step_dev(c, a.ps[i], a.gs[i], a.ms[i], a.vs[i], a.hyper, grad_scale_, decoupled ? 1 : 0, n));
+            else if (decoupled) check(tp_decay_dev(c, a.ps[i], a.hyper, n));     // AdamW decays grad-less params too (:154-161)
+        }
+    }
+    a.bump_versions();
+}
+
+void Adam::step() { step_impl(false); }                                          // :83-113
+void Adam::zero_grad() { for (auto& p : params_) p.zero_grad(); }                // :115-119
+
+// ---- AdamW  (src/optim.rs:131-181) ---------------------------------------------------------------------
+AdamW::AdamW(std::vector<Tensor> params, float lr, std::optional<std::pair<float, float>> betas, std::optional<float> eps,
+             std::optional<float> weight_decay)
+    : adam_(std::move(params), lr, betas, eps, weight_decay) {}
+
+void AdamW::step() { adam_.step_impl(true); }                                    // :148-168: p *= 1 - lr*wd, then Adam with wd = 0
+
+// ---- LR schedulers  (src/optim.rs:184-352), host scalars -------------------------------------------------
+void StepLR::step(std::optional<float>) {
+    current_epoch += 1;
+    if (current_epoch % step_size == 0) current_lr *= gamma;
+}
+
+void CosineAnnealingLR::step(std::optional<float>) {
+    current_epoch += 1;
+    float progress = (float)current_epoch / (float)t_max;
+    float cos_val = (1.0f + std::cos(progress * 3.14159265358979323846f)) / 2.0f;
+    current_lr = min_lr + (base_lr - min_lr) * cos_val;
+}
+
+ReduceLROnPlateau::ReduceLROnPlateau(float initial_lr, float factor_, size_t patience_, std::optional<float> min_lr_,
+                                     std::optional<std::string> mode_)
+    : current_lr(initial_lr), factor(factor_), min_lr(min_lr_.value_or(1e-6f)), patience(patience_), mode(mode_.value_or("min")) {
+    best_metric = mode == "min" ? INFINITY : -INFINITY;
+}
+
+void ReduceLROnPlateau::step(std::optional<float> metrics) {
+    if (!metrics) return;
+    bool improved = mode == "min" ? *metrics < best_metric : *metrics > best_metric;
+    if (improved) {
+        best_metric = *metrics;
+        patience_counter = 0;
+    } else {
+        patience_counter += 1;
+        if (patience_counter >= patience) {
+            current_lr = std::max(current_lr * factor, min_lr);
+            patience_counter = 0;
+        }
+    }
+}
+
+}  // namespace optim
+
+// =====================================================================================================
+// dist: data-parallel group (no counterpart in the reference)
+// =====================================================================================================
+namespace dist {
+namespace {
+thread_local int g_rank = 0, g_world = 1;
+}
+void init(int rank, int world, const void* nccl_unique_id128) {
+    check(tp_comm_init(ctx(), rank, world, nccl_unique_id128));
+    g_rank = rank;
+    g_world = world;
+}
+int rank() { return g_rank; }
+int world() { return g_world; }
+void allreduce_sum(tp_buf* buf, size_t n) { check(tp_allreduce_sum(ctx(), buf, n)); }
+void broadcast(tp_buf* buf, size_t n, int root) { check(tp_broadcast(ctx(), buf, n, root)); }
+}  // namespace dist
+
+}  // namespace taper

@@ -35,6 +35,9 @@ struct Config {
     // Sequential peephole: Linear followed by ReLU runs as one fused launch (bias+ReLU in the GEMM
     // epilogue, ReLU mask folded into the backward).  Numerically identical to the unfused ops.
     static bool& fuse_linear_relu();
+    // true: nn::Linear records the reference's literal op sequence transpose -> matmul -> add_broadcast
+    // (src/nn.rs:54-60, three tape nodes) instead of the single fused node.  Same numbers, more launches.
+    static bool& reference_op_sequence();
 };
 
 struct TensorImpl;
@@ -47,6 +50,7 @@ public:
     static Tensor from_host(const float* data, const Shape& shape);
     static Tensor scalar(float v);                                              // :480-482
     static Tensor zeros(const Shape& shape);
+    static Tensor empty(const Shape& shape);                                    // uninitialised device buffer
     static Tensor randn(const Shape& shape, uint64_t seed);                     // src/ops.rs:301-309 (seeded here)
     static Tensor adopt(tp_buf* buf, const Shape& shape);                       // takes ownership of buf
 
@@ -111,6 +115,9 @@ public:
     static void push_binary_op(const Tensor& a, const Tensor& b, const Tensor& out, std::function<void()> fn);   // :51-76
     static void push_unary_op(const Tensor& input, const Tensor& out, std::function<void()> fn);                 // :78-101
     static size_t len();
+    // moves the recorded closures out (a captured training step keeps them, and the tensors they
+    // own, alive for as long as its CUDA graph can be replayed)
+    static std::vector<std::function<void()>> take();
 };
 void backward(size_t final_node_id);                                                        // src/tape.rs:106-127
 
@@ -210,6 +217,9 @@ Tensor cross_entropy_loss(const Tensor& logits, const Tensor& targets);   // :13
 float accuracy(const Tensor& predictions, const Tensor& targets);    // :271-290
 // device-side variant: correct count as a [1] tensor, no host sync (used by the captured train step)
 Tensor accuracy_count(const Tensor& predictions, const Tensor& targets);
+// variants writing into a caller-provided [1] tensor (the trainer's result slot)
+Tensor cross_entropy_loss_into(const Tensor& logits, const Tensor& targets, const Tensor& out);
+void accuracy_count_into(const Tensor& predictions, const Tensor& targets, const Tensor& out);
 }  // namespace loss
 
 // ---- optim  (src/optim.rs) ----------------------------------------------------------------------------------
@@ -223,7 +233,15 @@ struct Optimizer {                                                   // :3-6
     virtual ~Optimizer() = default;
     virtual void step() = 0;
     virtual void zero_grad() = 0;
+    // data-parallel hooks (no counterpart in the reference): the flat gradient arena to allreduce and
+    // the 1/world factor the step kernel folds in
+    virtual std::shared_ptr<Arena> arena() const = 0;
+    virtual void set_grad_scale(float s) = 0;
+    virtual void set_lr(float) {}
 };
+tp_buf* arena_grad_buf(const std::shared_ptr<Arena>& a);
+tp_buf* arena_param_buf(const std::shared_ptr<Arena>& a);
+size_t arena_total(const std::shared_ptr<Arena>& a);
 
 class SGD : public Optimizer {                                       // :8-40 (momentum ignored, :14-17)
 public:
@@ -231,8 +249,8 @@ public:
     ~SGD() override;
     void step() override;
     void zero_grad() override;
-    void set_grad_scale(float s) { grad_scale_ = s; }
-    std::shared_ptr<Arena> arena() const { return arena_; }
+    void set_grad_scale(float s) override { grad_scale_ = s; }
+    std::shared_ptr<Arena> arena() const override { return arena_; }
 private:
     std::vector<Tensor> params_;
     float lr_;
@@ -248,9 +266,9 @@ public:
     void step() override;                                            // :83-113
     void zero_grad() override;                                       // :115-119
     float get_lr() const { return lr_; }                             // :121-123
-    void set_lr(float lr) { lr_ = lr; }                              // :125-127
-    void set_grad_scale(float s) { grad_scale_ = s; }                // 1/world for data-parallel averaging
-    std::shared_ptr<Arena> arena() const { return arena_; }
+    void set_lr(float lr) override;                                  // :125-127 (also updates the device-side state)
+    void set_grad_scale(float s) override { grad_scale_ = s; }       // 1/world for data-parallel averaging
+    std::shared_ptr<Arena> arena() const override { return arena_; }
     size_t t() const { return t_; }
 protected:
     void step_impl(bool decoupled);
@@ -269,9 +287,9 @@ public:
     void step() override;                                            // :148-168
     void zero_grad() override { adam_.zero_grad(); }
     float get_lr() const { return adam_.get_lr(); }
-    void set_lr(float lr) { adam_.set_lr(lr); }
-    void set_grad_scale(float s) { adam_.set_grad_scale(s); }
-    std::shared_ptr<Arena> arena() const { return adam_.arena(); }
+    void set_lr(float lr) override { adam_.set_lr(lr); }
+    void set_grad_scale(float s) override { adam_.set_grad_scale(s); }
+    std::shared_ptr<Arena> arena() const override { return adam_.arena(); }
 private:
     Adam adam_;
 };
@@ -318,11 +336,49 @@ void allreduce_sum(tp_buf* buf, size_t n);
 void broadcast(tp_buf* buf, size_t n, int root);
 }  // namespace dist
 
+// ---- data  (src/data/mnist.rs) ------------------------------------------------------------------------------------
+namespace data {
+
+struct MNISTDataset {                                                // :21-25
+    std::vector<float> images;       // [N, 784] in [0, 1]
+    std::vector<float> labels;       // [N]
+    bool train = true;
+    MNISTDataset() = default;
+    MNISTDataset(bool train, const std::string& data_dir = "./data/mnist");     // :29-58 (IDX files must exist; no download)
+    static MNISTDataset synthetic(size_t n, uint64_t seed);          // MNIST-shaped U[0,1) images, uniform labels
+    size_t len() const { return labels.size(); }                     // :312-314
+    void normalize(float mean, float std);                           // :317-322
+};
+
+class DataLoader {                                                   // :326-385
+public:
+    DataLoader(MNISTDataset dataset, size_t batch_size, bool shuffle, uint64_t seed = 0);
+    void reset();                                                    // :350-358 (reshuffles)
+    size_t num_batches() const { return (dataset_.len() + batch_size_ - 1) / batch_size_; }   // :360-362
+    // Iterator::next (:369-384): false at the end of the epoch.  The batch is gathered into host vectors
+    // (last batch partial, :377).
+    bool next(std::vector<float>& images, std::vector<float>& labels, size_t& batch);
+    const MNISTDataset& dataset() const { return dataset_; }
+    const std::vector<uint32_t>& indices() const { return indices_; }
+    size_t batch_size() const { return batch_size_; }
+private:
+    MNISTDataset dataset_;
+    size_t batch_size_;
+    bool shuffle_;
+    std::vector<uint32_t> indices_;
+    size_t current_ = 0;
+    uint64_t rng_state_;
+};
+
+}  // namespace data
+
 // ---- train  (src/train.rs) -----------------------------------------------------------------------------------------
 namespace train {
 
 struct Metrics {                                                     // :10-71
     std::vector<float> train_loss, train_acc, val_loss, val_acc, epoch_times;
+    void print_last() const;
+    void plot_summary() const;
 };
 
 struct StepResult { float loss; float correct; };
@@ -330,22 +386,38 @@ struct StepResult { float loss; float correct; };
 class Trainer {                                                      // :73-293
 public:
     std::shared_ptr<nn::Module> model;
-    std::shared_ptr<optim::Optimizer> optimizer;
+    std::shared_ptr<optim::Optimizer> optimizer;                     // the reference hard-wires Adam (:76)
     std::shared_ptr<optim::LRScheduler> scheduler;
     Metrics metrics;
     Trainer(std::shared_ptr<nn::Module> m, std::shared_ptr<optim::Optimizer> o, std::shared_ptr<optim::LRScheduler> s = nullptr);
     ~Trainer();
-    // The loop body of train_epoch (:106-138): reset tape, forward, CE, accuracy, backward,
-    // [allreduce], step, zero_grad; returns (loss, #correct).  `images` is host memory [batch, sample_dims...].
+
+    // One iteration of the train_epoch loop body (:106-138): Tape::reset, forward, cross-entropy, accuracy,
+    // backward, [gradient allreduce], optimizer.step, zero_grad.  After one eager iteration per batch
+    // shape the whole body is captured into a CUDA graph and replayed.
+    //   train_batch            host inputs (pageable), synchronous: returns (loss, #correct)
+    //   train_batch_async      host inputs (pinned => true async H2D), result via fetch() in FIFO order
+    //   load_dataset + train_batch_resident   inputs gathered on the device from a resident dataset
     StepResult train_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);
-    // Asynchronous form: enqueue only (inputs may be pinned); results land in a device slot read by fetch().
     void train_batch_async(const float* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned);
+    void load_dataset(const float* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm);
+    void train_batch_resident(size_t batch);
     StepResult fetch();
-    // same body on inputs already resident on the device (bench `value` leg)
-    void train_batch_device(const Tensor& images, const Tensor& labels);
-    StepResult eval_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);   // :147-172 body
+    size_t pending() const;
+    StepResult eval_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);   // :156-166 body
+
+    std::pair<float, float> train_epoch(data::DataLoader& loader);  // :98-144
+    std::pair<float, float> evaluate(data::DataLoader& loader);     // :147-172
+    void fit(data::DataLoader& train_loader, data::DataLoader& val_loader, size_t epochs, bool verbose);   // :175-261
+
     void save_checkpoint(const std::string& path) const;             // :264-292 text format
     void load_checkpoint(const std::string& path) const;             // loader for the same format (the reference has none)
+
+    // data-parallel: bind this thread's context to a NCCL rank; gradients are summed across ranks after
+    // backward and the optimizer folds 1/world.  broadcast_parameters makes every replica start equal.
+    void init_data_parallel(int rank, int world, const void* nccl_unique_id128);
+    void broadcast_parameters(int root);
+
     void set_use_graph(bool v) { use_graph_ = v; }
     uint64_t graph_replays() const { return graph_replays_; }
 private:

@@ -1,0 +1,481 @@
+// Host layer, part 3: the training loop (src/train.rs), the MNIST data path (src/data/mnist.rs) and
+// CUDA-graph capture of one whole training step.
+#include "taper_internal.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <map>
+#include <numeric>
+#include <sstream>
+
+namespace taper {
+
+// =====================================================================================================
+// data  (src/data/mnist.rs)
+// =====================================================================================================
+namespace data {
+
+namespace {
+uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+std::vector<unsigned char> read_file(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) panic("Failed to open %s", path.c_str());
+    return std::vector<unsigned char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+uint32_t be32(const unsigned char* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+}  // namespace
+
+MNISTDataset::MNISTDataset(bool train_, const std::string& dir) : train(train_) {
+    // IDX parser (src/data/mnist.rs:184-273).  The reference downloads missing files (:60-181); there is
+    // no network here, so missing files are an error.
+    auto img = read_file(dir + (train ? "/train_images" : "/test_images"));
+    auto lab = read_file(dir + (train ? "/train_labels" : "/test_labels"));
+    if (img.size() < 16 || be32(img.data()) != 0x00000803) panic("Invalid magic number for images");
+    size_t n = be32(img.data() + 4), rows = be32(img.data() + 8), cols = be32(img.data() + 12);
+    if (rows != 28 || cols != 28) panic("Unexpected image size: %zux%zu", rows, cols);
+    if (img.size() != 16 + n * 784) panic("Image file size mismatch");
+    if (lab.size() < 8 || be32(lab.data()) != 0x00000801) panic("Invalid magic number for labels");
+    if (be32(lab.data() + 4) != n || lab.size() != 8 + n) panic("Label file size mismatch");
+    images.resize(n * 784);
+    for (size_t i = 0; i < n * 784; ++i) images[i] = (float)img[16 + i] / 255.0f;          // :225
+    labels.resize(n);
+    for (size_t i = 0; i < n; ++i) labels[i] = (float)lab[8 + i];                           // :268
+}
+
+MNISTDataset MNISTDataset::synthetic(size_t n, uint64_t seed) {
+    MNISTDataset d;
+    d.images.resize(n * 784);
+    d.labels.resize(n);
+    uint64_t s = seed;
+    for (auto& v : d.images) v = (float)(splitmix64(s) >> 40) * (1.0f / 16777216.0f);
+    for (auto& v : d.labels) v = (float)(splitmix64(s) % 10);
+    return d;
+}
+
+void MNISTDataset::normalize(float mean, float std) {
+    for (auto& p : images) p = (p - mean) / std;
+}
+
+DataLoader::DataLoader(MNISTDataset dataset, size_t batch_size, bool shuffle, uint64_t seed)
+    : dataset_(std::move(dataset)), batch_size_(batch_size), shuffle_(shuffle), rng_state_(seed) {
+    indices_.resize(dataset_.len());
+    std::iota(indices_.begin(), indices_.end(), 0u);
+    if (shuffle_) reset();
+}
+
+void DataLoader::reset() {
+    current_ = 0;
+    if (shuffle_)                                                                           // Fisher-Yates (:353-357)
+        for (size_t i = indices_.size(); i > 1; --i) std::swap(indices_[i - 1], indices_[splitmix64(rng_state_) % i]);
+}
+
+bool DataLoader::next(std::vector<float>& images, std::vector<float>& labels, size_t& batch) {
+    if (current_ >= dataset_.len()) return false;
+    size_t end = std::min(current_ + batch_size_, dataset_.len());
+    batch = end - current_;
+    images.resize(batch * 784);
+    labels.resize(batch);
+    for (size_t i = 0; i < batch; ++i) {                                                    // get_batch (:276-309)
+        size_t idx = indices_[current_ + i];
+        std::memcpy(&images[i * 784], &dataset_.images[idx * 784], 784 * sizeof(float));
+        labels[i] = dataset_.labels[idx];
+    }
+    current_ = end;
+    return true;
+}
+
+}  // namespace data
+
+// =====================================================================================================
+// train  (src/train.rs)
+// =====================================================================================================
+namespace train {
+
+void Metrics::print_last() const {
+    if (train_loss.empty() || val_loss.empty()) return;
+    std::printf("Train Loss: %.4f | Train Acc: %.2f%% | Val Loss: %.4f | Val Acc: %.2f%%\n", train_loss.back(),
+                train_acc.back() * 100.0f, val_loss.back(), val_acc.back() * 100.0f);
+}
+
+void Metrics::plot_summary() const {
+    std::printf("\nTraining Summary:\n==================================================\n");
+    if (!train_acc.empty()) {
+        std::printf("Best Train Accuracy: %.2f%%\n", *std::max_element(train_acc.begin(), train_acc.end()) * 100.0f);
+        if (!val_acc.empty()) std::printf("Best Val Accuracy: %.2f%%\n", *std::max_element(val_acc.begin(), val_acc.end()) * 100.0f);
+        std::printf("Final Train Accuracy: %.2f%%\n", train_acc.back() * 100.0f);
+        if (!val_acc.empty()) std::printf("Final Val Accuracy: %.2f%%\n", val_acc.back() * 100.0f);
+        if (!epoch_times.empty()) {
+            float total = std::accumulate(epoch_times.begin(), epoch_times.end(), 0.0f);
+            std::printf("Total Training Time: %.2fs\nAverage Epoch Time: %.2fs\n", total, total / (float)epoch_times.size());
+        }
+    }
+    std::printf("==================================================\n");
+}
+
+namespace {
+constexpr size_t kRing = 8;          // result slots in flight (host may run this many steps ahead)
+
+struct Slot {                        // per batch-shape persistent state
+    Tensor x, y;                     // device inputs the step reads
+    int eager_runs = 0;
+    tp_graph* graph = nullptr;       // captured step (host-fed variant)
+    tp_graph* graph_resident = nullptr;      // captured gather + step (device-resident dataset)
+    std::vector<std::function<void()>> keep, keep_resident;    // tape closures (own the step's tensors)
+};
+}  // namespace
+
+struct Trainer::Impl {
+    std::map<std::vector<size_t>, Slot> slots;               // key: full input shape [B, sample...]
+    Tensor result;                                           // device {loss, correct}
+    Tensor loss_view, correct_view;
+    float* ring = nullptr;                                   // pinned kRing x 2 floats
+    tp_event* events[kRing] = {};
+    size_t head = 0, tail = 0;                               // FIFO of outstanding results
+    // resident dataset
+    tp_buf *ds_images = nullptr, *ds_labels = nullptr, *ds_perm = nullptr, *ds_cursor = nullptr;
+    size_t ds_n = 0;
+    Shape ds_sample;
+    int world = 1;
+
+    void enqueue_result() {
+        size_t i = head % kRing;
+        check(tp_buf_download_async(ctx(), result.buf(), ring + 2 * i, 2));
+        check(tp_event_record(ctx(), events[i]));
+        head++;
+    }
+
+    ~Impl() {
+        tp_sync(ctx());
+        for (auto& kv : slots) {
+            tp_graph_destroy(kv.second.graph);
+            tp_graph_destroy(kv.second.graph_resident);
+        }
+        slots.clear();
+        for (auto* e : events) tp_event_destroy(e);
+        if (ring) tp_host_free_pinned(ring);
+        tp_buf_release(ds_images); tp_buf_release(ds_labels); tp_buf_release(ds_perm); tp_buf_release(ds_cursor);
+    }
+};
+
+Trainer::Trainer(std::shared_ptr<nn::Module> m, std::shared_ptr<optim::Optimizer> o, std::shared_ptr<optim::LRScheduler> s)
+    : model(std::move(m)), optimizer(std::move(o)), scheduler(std::move(s)), p_(new Impl()) {
+    p_->result = Tensor::zeros({2});
+    tp_buf *l, *c;
+    check(tp_buf_slice(p_->result.buf(), 0, 1, &l));
+    check(tp_buf_slice(p_->result.buf(), 1, 1, &c));
+    p_->loss_view = Tensor::adopt(l, {1});
+    p_->correct_view = Tensor::adopt(c, {1});
+    void* ring = nullptr;
+    check(tp_host_alloc_pinned(kRing * 2 * sizeof(float), &ring));
+    p_->ring = (float*)ring;
+    for (auto& e : p_->events) check(tp_event_create(ctx(), &e));
+}
+
+Trainer::~Trainer() = default;
+
+void Trainer::init_data_parallel(int rank, int world, const void* uid) {
+    dist::init(rank, world, uid);
+    p_->world = world;
+    optimizer->set_grad_scale(1.0f / (float)world);
+}
+
+void Trainer::broadcast_parameters(int root) {
+    auto a = optimizer->arena();
+    dist::broadcast(optim::arena_param_buf(a), optim::arena_total(a), root);
+    for (auto& t : model->parameters()) t.impl()->version++;
+}
+
+namespace {
+
+// The loop body of Trainer::train_epoch (src/train.rs:106-138) on device-resident inputs.
+void step_body(Trainer& tr, const Tensor& x, const Tensor& y, const Tensor& loss_out, const Tensor& correct_out, int world) {
+    Tape::reset();                                                               // :108
+    Tensor logits = tr.model->forward(x);                                        // :111
+    // the loss tensor is a fresh handle on the result slot each step: its grad state must start as None
+    loss_out.impl()->has_grad = false;
+    loss_out.impl()->tape_node = 0;
+    Tensor loss = loss::cross_entropy_loss_into(logits, y, loss_out);            // :112
+    loss::accuracy_count_into(logits, y, correct_out);                           // :115
+    loss.backward();                                                             // :121
+    if (world > 1) {                                                             // sum of per-rank mean gradients
+        auto a = tr.optimizer->arena();
+        dist::allreduce_sum(optim::arena_grad_buf(a), optim::arena_total(a));
+    }
+    tr.optimizer->step();                                                        // :124
+    tr.optimizer->zero_grad();                                                   // :125
+}
+
+Shape full_shape(size_t batch, const Shape& sample) {
+    Shape s{batch};
+    s.insert(s.end(), sample.begin(), sample.end());
+    return s;
+}
+
+}  // namespace
+
+size_t Trainer::pending() const { return p_->head - p_->tail; }
+
+StepResult Trainer::fetch() {
+    if (p_->head == p_->tail) panic("Trainer::fetch: no step outstanding");
+    size_t i = p_->tail % kRing;
+    check(tp_event_sync(p_->events[i]));
+    StepResult r{p_->ring[2 * i], p_->ring[2 * i + 1]};
+    p_->tail++;
+    return r;
+}
+
+// enqueue: [optional gather] + step (eager for the first iteration of a shape, then captured, then replayed),
+// followed by the asynchronous read-back of {loss, correct} into the next ring slot.
+void Trainer::train_batch_async(const float* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned) {
+    Impl& p = *p_;
+    if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
+    Shape fs = full_shape(batch, sample_shape);
+    Slot& s = p.slots[fs];
+    if (!s.x.defined()) {
+        s.x = Tensor::empty(fs);
+        s.y = Tensor::empty({batch});
+    }
+    tp_ctx* c = ctx();
+    if (pinned) {
+        check(tp_buf_upload_pinned(c, s.x.buf(), images, s.x.numel()));
+        check(tp_buf_upload_pinned(c, s.y.buf(), labels, batch));
+    } else {
+        check(tp_buf_upload(c, s.x.buf(), images, s.x.numel()));
+        check(tp_buf_upload(c, s.y.buf(), labels, batch));
+    }
+    if (s.graph) {
+        check(tp_graph_launch(c, s.graph));
+        graph_replays_++;
+    } else if (use_graph_ && s.eager_runs >= 1) {
+        // second iteration of this shape: record it.  Every buffer the step allocates comes from a pool the
+        // graph owns, and the closures (which own the activations) are kept alive with the graph.
+        check(tp_graph_begin(c));
+        try {
+            step_body(*this, s.x, s.y, p.loss_view, p.correct_view, p.world);
+        } catch (...) {
+            tp_graph* g = nullptr;
+            tp_graph_end(c, &g);
+            tp_graph_destroy(g);
+            throw;
+        }
+        s.keep = Tape::take();
+        check(tp_graph_end(c, &s.graph));
+        check(tp_graph_launch(c, s.graph));
+        graph_replays_++;
+    } else {
+        step_body(*this, s.x, s.y, p.loss_view, p.correct_view, p.world);
+        s.eager_runs++;
+    }
+    p.enqueue_result();
+}
+
+StepResult Trainer::train_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape) {
+    train_batch_async(images, labels, batch, sample_shape, false);
+    return fetch();
+}
+
+void Trainer::load_dataset(const float* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm) {
+    Impl& p = *p_;
+    tp_ctx* c = ctx();
+    check(tp_sync(c));
+    for (auto& kv : p.slots) {                                  // graphs that reference the old dataset
+        tp_graph_destroy(kv.second.graph_resident);
+        kv.second.graph_resident = nullptr;
+        kv.second.keep_resident.clear();
+    }
+    tp_buf_release(p.ds_images); tp_buf_release(p.ds_labels); tp_buf_release(p.ds_perm); tp_buf_release(p.ds_cursor);
+    size_t cols = shape_numel(sample_shape);
+    check(tp_buf_alloc(c, n * cols, &p.ds_images));
+    check(tp_buf_alloc(c, n, &p.ds_labels));
+    check(tp_buf_alloc(c, n, &p.ds_perm));
+    check(tp_buf_alloc(c, 1, &p.ds_cursor));
+    check(tp_buf_upload(c, p.ds_images, images, n * cols));
+    check(tp_buf_upload(c, p.ds_labels, labels, n));
+    std::vector<uint32_t> ident;
+    if (!perm) {
+        ident.resize(n);
+        std::iota(ident.begin(), ident.end(), 0u);
+        perm = ident.data();
+    }
+    check(tp_buf_upload(c, p.ds_perm, perm, n));
+    check(tp_buf_fill(c, p.ds_cursor, 0.0f, 1));
+    p.ds_n = n;
+    p.ds_sample = sample_shape;
+}
+
+void Trainer::train_batch_resident(size_t batch) {
+    Impl& p = *p_;
+    if (!p.ds_images) panic("Trainer::train_batch_resident: load_dataset has not been called");
+    if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
+    Shape fs = full_shape(batch, p.ds_sample);
+    Slot& s = p.slots[fs];
+    if (!s.x.defined()) {
+        s.x = Tensor::empty(fs);
+        s.y = Tensor::empty({batch});
+    }
+    tp_ctx* c = ctx();
+    int cols = (int)shape_numel(p.ds_sample);
+    auto body = [&]() {
+        // MNISTDataset::get_batch on the device (src/data/mnist.rs:276-309), then the cursor moves on
+        check(tp_gather_batch(c, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, s.x.buf(), s.y.buf(), (int)batch, cols, (int)p.ds_n));
+        check(tp_cursor_advance(c, p.ds_cursor, (int)batch, (int)p.ds_n));
+        step_body(*this, s.x, s.y, p.loss_view, p.correct_view, p.world);
+    };
+    if (s.graph_resident) {
+        check(tp_graph_launch(c, s.graph_resident));
+        graph_replays_++;
+    } else if (use_graph_ && s.eager_runs >= 1) {
+        check(tp_graph_begin(c));
+        try {
+            body();
+        } catch (...) {
+            tp_graph* g = nullptr;
+            tp_graph_end(c, &g);
+            tp_graph_destroy(g);
+            throw;
+        }
+        s.keep_resident = Tape::take();
+        check(tp_graph_end(c, &s.graph_resident));
+        check(tp_graph_launch(c, s.graph_resident));
+        graph_replays_++;
+    } else {
+        body();
+        s.eager_runs++;
+    }
+    p.enqueue_result();
+}
+
+StepResult Trainer::eval_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape) {
+    // body of Trainer::evaluate (src/train.rs:156-166): forward + loss + accuracy.  The reference records tape
+    // nodes here too (no no-grad mode, A10); they are dropped right away.
+    Shape fs = full_shape(batch, sample_shape);
+    Tensor x = Tensor::from_host(images, fs), y = Tensor::from_host(labels, {batch});
+    Tensor logits = model->forward(x);
+    Tensor l = loss::cross_entropy_loss(logits, y);
+    Tensor cnt = loss::accuracy_count(logits, y);
+    StepResult r{l.item(), cnt.item()};
+    Tape::reset();
+    return r;
+}
+
+std::pair<float, float> Trainer::train_epoch(data::DataLoader& loader) {        // src/train.rs:98-144
+    float total_loss = 0.0f;
+    size_t total_correct = 0, total_samples = 0;
+    loader.reset();
+    size_t num_batches = loader.num_batches();
+    std::vector<float> images, labels;
+    size_t batch = 0, enq = 0;
+    std::deque<size_t> sizes;
+    auto drain_one = [&]() {
+        StepResult r = fetch();
+        total_correct += (size_t)r.correct;                                      // (acc * batch) as usize, :117
+        total_samples += sizes.front();
+        sizes.pop_front();
+        total_loss += r.loss;                                                    // :127
+    };
+    while (loader.next(images, labels, batch)) {
+        if (pending() >= kRing - 1) drain_one();
+        train_batch_async(images.data(), labels.data(), batch, {784}, false);
+        sizes.push_back(batch);
+        ++enq;
+    }
+    while (pending()) drain_one();
+    (void)enq;
+    return {total_loss / (float)num_batches, (float)total_correct / (float)total_samples};
+}
+
+std::pair<float, float> Trainer::evaluate(data::DataLoader& loader) {           // src/train.rs:147-172
+    float total_loss = 0.0f;
+    size_t total_correct = 0, total_samples = 0;
+    loader.reset();
+    size_t num_batches = loader.num_batches();
+    std::vector<float> images, labels;
+    size_t batch = 0;
+    while (loader.next(images, labels, batch)) {
+        StepResult r = eval_batch(images.data(), labels.data(), batch, {784});
+        total_correct += (size_t)r.correct;
+        total_samples += batch;
+        total_loss += r.loss;
+    }
+    return {total_loss / (float)num_batches, (float)total_correct / (float)total_samples};
+}
+
+void Trainer::fit(data::DataLoader& train_loader, data::DataLoader& val_loader, size_t epochs, bool verbose) {   // :175-261
+    std::printf("Starting training for %zu epochs\n============================================================\n", epochs);
+    for (size_t epoch = 0; epoch < epochs; ++epoch) {
+        auto t0 = std::chrono::steady_clock::now();
+        if (verbose) std::printf("\nEpoch %zu/%zu\n", epoch + 1, epochs);
+        auto [train_loss, train_acc] = train_epoch(train_loader);
+        auto [val_loss, val_acc] = evaluate(val_loader);
+        if (scheduler) {                                                         // :212-216
+            scheduler->step(val_loss);
+            optimizer->set_lr(scheduler->get_lr());
+        }
+        metrics.train_loss.push_back(train_loss);
+        metrics.train_acc.push_back(train_acc);
+        metrics.val_loss.push_back(val_loss);
+        metrics.val_acc.push_back(val_acc);
+        metrics.epoch_times.push_back(std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count());
+        if (verbose) {
+            std::printf("\nEpoch %zu - Train Loss: %.4f | Train Acc: %.2f%% | Val Loss: %.4f | Val Acc: %.2f%% | Time: %.2fs\n",
+                        epoch + 1, train_loss, train_acc * 100.0f, val_loss, val_acc * 100.0f, metrics.epoch_times.back());
+            if (scheduler) std::printf("   Learning Rate: %.6f\n", scheduler->get_lr());
+        }
+        if (val_acc > 0.99f) {                                                   // :246-249
+            std::printf("\nReached 99%% validation accuracy! Stopping early.\n");
+            break;
+        }
+    }
+    metrics.plot_summary();
+}
+
+void Trainer::save_checkpoint(const std::string& path) const {                  // src/train.rs:264-292
+    std::ofstream f(path);
+    if (!f) panic("save_checkpoint: cannot create %s", path.c_str());
+    auto params = model->parameters();
+    f << params.size() << "\n";
+    char buf[64];
+    for (auto& p : params) {
+        f << p.shape().size();
+        for (size_t d : p.shape()) f << " " << d;
+        f << "\n";
+        for (float v : p.data()) {
+            std::snprintf(buf, sizeof buf, "%.9g", v);                           // round-trips an f32 exactly
+            f << buf << "\n";
+        }
+    }
+}
+
+void Trainer::load_checkpoint(const std::string& path) const {
+    std::ifstream f(path);
+    if (!f) panic("load_checkpoint: cannot open %s", path.c_str());
+    auto params = model->parameters();
+    size_t count = 0;
+    f >> count;
+    if (count != params.size()) panic("load_checkpoint: file has %zu parameters, model has %zu", count, params.size());
+    for (auto& p : params) {
+        size_t nd = 0;
+        f >> nd;
+        Shape s(nd);
+        for (auto& d : s) f >> d;
+        if (s != p.shape()) panic("load_checkpoint: parameter shape mismatch");
+        std::vector<float> v(p.numel());
+        for (auto& x : v) f >> x;
+        if (!f) panic("load_checkpoint: truncated file");
+        p.set_data(v);
+    }
+}
+
+}  // namespace train
+
+}  // namespace taper

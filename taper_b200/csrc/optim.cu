@@ -58,6 +58,71 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float l
     }
 }
 
+// ---- device-resident optimizer state: lets a captured (CUDA-graph) step advance t and follow set_lr
+// without the host patching kernel arguments.  hyper = {t (int bits), lr, b1, b2, eps, wd, step_size, decay}
+enum { H_T = 0, H_LR, H_B1, H_B2, H_EPS, H_WD, H_SS, H_DECAY, H_COUNT };
+
+__device__ __forceinline__ float powi_dev(float a, int b) {     // f32::powi (compiler-rt __powisf2)
+    float r = 1.0f;
+    unsigned int e = (unsigned int)b;
+    while (true) {
+        if (e & 1u) r *= a;
+        e >>= 1;
+        if (e == 0) break;
+        a *= a;
+    }
+    return r;
+}
+
+__global__ void adam_advance_kernel(float* __restrict__ h) {
+    int t = __float_as_int(h[H_T]) + 1;                        // self.t += 1  (src/optim.rs:86)
+    h[H_T] = __int_as_float(t);
+    float bc1 = 1.0f - powi_dev(h[H_B1], t);                   // :88
+    float bc2 = 1.0f - powi_dev(h[H_B2], t);                   // :89
+    h[H_SS] = h[H_LR] * (sqrtf(bc2) / bc1);                    // :90
+    h[H_DECAY] = 1.0f - h[H_LR] * h[H_WD];                     // AdamW  :157
+}
+
+__global__ void set_scalar_kernel(float* __restrict__ dst, float v) { *dst = v; }
+
+__global__ void __launch_bounds__(kThreads)
+adam_dev_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                     size_t n4, const float* __restrict__ h, float grad_scale, int decoupled) {
+    AdamArgs a{h[H_SS], h[H_B1], h[H_B2], h[H_EPS], decoupled ? 0.0f : h[H_WD], grad_scale, h[H_DECAY],
+               (decoupled && h[H_WD] > 0.0f) ? 1 : 0};
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p[i], gg = __ldg(g + i), mm = m[i], vv = v[i];
+        adam_elem(pp.x, gg.x, mm.x, vv.x, a);
+        adam_elem(pp.y, gg.y, mm.y, vv.y, a);
+        adam_elem(pp.z, gg.z, mm.z, vv.z, a);
+        adam_elem(pp.w, gg.w, mm.w, vv.w, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_dev_scalar_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       size_t n, const float* __restrict__ h, float grad_scale, int decoupled) {
+    AdamArgs a{h[H_SS], h[H_B1], h[H_B2], h[H_EPS], decoupled ? 0.0f : h[H_WD], grad_scale, h[H_DECAY],
+               (decoupled && h[H_WD] > 0.0f) ? 1 : 0};
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_elem(pp, g[i], mm, vv, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+// p *= decay (hyper[H_DECAY]) — AdamW's decoupled decay of parameters that have no gradient this step
+__global__ void __launch_bounds__(kThreads)
+decay_dev_kernel(float* __restrict__ p, size_t n, const float* __restrict__ h) {
+    if (!(h[H_WD] > 0.0f)) return;
+    const float d = h[H_DECAY];
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) p[i] *= d;
+}
+
 int launch_adam(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, size_t n, const AdamArgs& a, const char* fn) {
     TP_CHECK_ARG(ctx, "%s: NULL ctx", fn);
     TP_NEED(p, n, "p"); TP_NEED(g, n, "g"); TP_NEED(m, n, "m"); TP_NEED(v, n, "v");
@@ -116,6 +181,59 @@ int tp_adam_step(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, 
                  float eps, float weight_decay, float grad_scale, size_t n) {
     AdamArgs a{step_size, beta1, beta2, eps, weight_decay, grad_scale, 1.0f, 0};
     return launch_adam(ctx, p, g, m, v, n, a, "tp_adam_step");
+}
+
+int tp_adam_hyper_init(tp_ctx* ctx, tp_buf* hyper, float lr, float beta1, float beta2, float eps, float weight_decay) {
+    TP_CHECK_ARG(ctx, "tp_adam_hyper_init: NULL ctx");
+    TP_NEED(hyper, H_COUNT, "hyper");
+    float h[H_COUNT] = {0.0f, lr, beta1, beta2, eps, weight_decay, 0.0f, 1.0f};
+    return tp_buf_upload(ctx, hyper, h, H_COUNT);
+}
+
+int tp_adam_hyper_set_lr(tp_ctx* ctx, tp_buf* hyper, float lr) {
+    TP_CHECK_ARG(ctx, "tp_adam_hyper_set_lr: NULL ctx");
+    TP_NEED(hyper, H_COUNT, "hyper");
+    set_scalar_kernel<<<1, 1, 0, ctx->stream>>>(hyper->ptr + H_LR, lr);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_adam_advance(tp_ctx* ctx, tp_buf* hyper) {
+    TP_CHECK_ARG(ctx, "tp_adam_advance: NULL ctx");
+    TP_NEED(hyper, H_COUNT, "hyper");
+    adam_advance_kernel<<<1, 1, 0, ctx->stream>>>(hyper->ptr);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_adam_step_dev(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, const tp_buf* hyper, float grad_scale,
+                     int decoupled, size_t n) {
+    TP_CHECK_ARG(ctx, "tp_adam_step_dev: NULL ctx");
+    TP_NEED(p, n, "p"); TP_NEED(g, n, "g"); TP_NEED(m, n, "m"); TP_NEED(v, n, "v"); TP_NEED(hyper, H_COUNT, "hyper");
+    if (!n) return TP_OK;
+    bool vec = !(((uintptr_t)p->ptr | (uintptr_t)g->ptr | (uintptr_t)m->ptr | (uintptr_t)v->ptr) & 15);
+    size_t n4 = vec ? n / 4 : 0;
+    if (n4) {
+        adam_dev_vec4_kernel<<<tp::grid_for(ctx, n4, kThreads), kThreads, 0, ctx->stream>>>(
+            (float4*)p->ptr, (const float4*)g->ptr, (float4*)m->ptr, (float4*)v->ptr, n4, hyper->ptr, grad_scale, decoupled);
+        TP_LAUNCH_OK(ctx);
+    }
+    size_t done = n4 * 4;
+    if (done < n) {
+        adam_dev_scalar_kernel<<<tp::grid_for(ctx, n - done, kThreads), kThreads, 0, ctx->stream>>>(
+            p->ptr + done, g->ptr + done, m->ptr + done, v->ptr + done, n - done, hyper->ptr, grad_scale, decoupled);
+        TP_LAUNCH_OK(ctx);
+    }
+    return TP_OK;
+}
+
+int tp_decay_dev(tp_ctx* ctx, tp_buf* p, const tp_buf* hyper, size_t n) {
+    TP_CHECK_ARG(ctx, "tp_decay_dev: NULL ctx");
+    TP_NEED(p, n, "p"); TP_NEED(hyper, H_COUNT, "hyper");
+    if (!n) return TP_OK;
+    decay_dev_kernel<<<tp::grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(p->ptr, n, hyper->ptr);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
 }
 
 int tp_adamw_step(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size, float beta1, float beta2,

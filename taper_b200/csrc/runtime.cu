@@ -25,7 +25,7 @@ size_t Allocator::bucket(size_t bytes) {
     return (bytes + (16u << 20) - 1) & ~(size_t)((16u << 20) - 1);           // 16 MiB
 }
 
-void* Allocator::alloc(size_t bytes, size_t* cap) {
+void* Allocator::alloc(size_t bytes, size_t* cap, Allocator* steal_from, bool relaxed_capture) {
     size_t b = bucket(bytes);
     *cap = b;
     auto it = free_lists.find(b);
@@ -35,24 +35,43 @@ void* Allocator::alloc(size_t bytes, size_t* cap) {
         in_use += b;
         return p;
     }
+    if (steal_from) {                 // graph-private pool: adopt a cached block of the main pool
+        auto st = steal_from->free_lists.find(b);
+        if (st != steal_from->free_lists.end() && !st->second.empty()) {
+            void* p = st->second.back();
+            st->second.pop_back();
+            steal_from->all_blocks.erase(p);
+            steal_from->reserved -= b;
+            all_blocks.insert(p);
+            reserved += b;
+            in_use += b;
+            return p;
+        }
+    }
+    // cudaMalloc is not allowed on a thread that is capturing unless the capture mode is relaxed
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    if (relaxed_capture) cudaThreadExchangeStreamCaptureMode(&mode);
     void* p = nullptr;
-    if (cudaMalloc(&p, b) != cudaSuccess) {
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e != cudaSuccess && !relaxed_capture) {
         cudaGetLastError();
         // give cached blocks back to the driver and retry once
         for (auto& kv : free_lists) {
             for (void* q : kv.second) {
                 cudaFree(q);
                 reserved -= kv.first;
-                for (auto& ab : all_blocks) if (ab == q) ab = nullptr;
+                all_blocks.erase(q);
             }
             kv.second.clear();
         }
-        if (cudaMalloc(&p, b) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
+        e = cudaMalloc(&p, b);
     }
-    all_blocks.push_back(p);
+    if (relaxed_capture) cudaThreadExchangeStreamCaptureMode(&mode);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    all_blocks.insert(p);
     reserved += b;
     in_use += b;
     return p;
@@ -64,7 +83,7 @@ void Allocator::free(void* p, size_t cap) {
 }
 
 void Allocator::release_all() {
-    for (void* p : all_blocks) if (p) cudaFree(p);
+    for (void* p : all_blocks) cudaFree(p);
     all_blocks.clear();
     free_lists.clear();
     in_use = reserved = 0;
@@ -90,11 +109,27 @@ int ensure_scratch(tp_ctx* ctx, size_t bytes) {
 
 }  // namespace tp
 
+struct tp_event {
+    cudaEvent_t ev = nullptr;
+};
+
 struct tp_graph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0;           // kernels recorded inside the graph
+    tp::Allocator* pool = nullptr;   // memory the captured work allocated; owned by the graph
+    int device = 0;
 };
+
+static void drop_pool(tp::Allocator* pool) {
+    if (!pool) return;
+    if (pool->live_bufs == 0) {
+        pool->release_all();
+        delete pool;
+    } else {
+        pool->orphaned = true;       // a tp_buf allocated during capture outlives the graph
+    }
+}
 
 extern "C" {
 
@@ -184,7 +219,9 @@ int tp_buf_alloc(tp_ctx* ctx, size_t n, tp_buf** out) {
     TP_CHECK_ARG(ctx && out, "tp_buf_alloc: NULL argument");
     cudaSetDevice(ctx->device);
     size_t cap = 0;
-    void* p = ctx->alloc.alloc(n * sizeof(float), &cap);
+    tp::Allocator* pool = ctx->capture_pool ? ctx->capture_pool : &ctx->alloc;
+    void* p = ctx->capture_pool ? pool->alloc(n * sizeof(float), &cap, &ctx->alloc, true)
+                                : pool->alloc(n * sizeof(float), &cap);
     if (!p) {
         tp::set_error("tp_buf_alloc: out of device memory allocating %zu bytes (reserved %zu)",
                       n * sizeof(float), ctx->alloc.reserved);
@@ -195,6 +232,8 @@ int tp_buf_alloc(tp_ctx* ctx, size_t n, tp_buf** out) {
     b->ptr = (float*)p;
     b->n = n;
     b->cap = cap;
+    b->pool = pool;
+    pool->live_bufs++;
     *out = b;
     return TP_OK;
 }
@@ -233,7 +272,15 @@ int tp_buf_release(tp_buf* buf) {
     if (!buf) return TP_OK;
     if (buf->rc.fetch_sub(1) == 1) {
         if (buf->parent) tp_buf_release(buf->parent);
-        else if (!buf->external) buf->ctx->alloc.free(buf->ptr, buf->cap);
+        else if (!buf->external) {
+            tp::Allocator* pool = buf->pool;
+            pool->free(buf->ptr, buf->cap);
+            pool->live_bufs--;
+            if (pool->orphaned && pool->live_bufs == 0) {
+                pool->release_all();
+                delete pool;
+            }
+        }
         delete buf;
     }
     return TP_OK;
@@ -285,6 +332,53 @@ int tp_buf_copy(tp_ctx* ctx, tp_buf* dst, const tp_buf* src, size_t n) {
     return TP_OK;
 }
 
+int tp_buf_download_async(tp_ctx* ctx, const tp_buf* src, void* pinned_host, size_t n) {
+    TP_CHECK_ARG(ctx && pinned_host, "tp_buf_download_async: NULL argument");
+    TP_NEED(src, n, "src");
+    TP_CUDA(cudaMemcpyAsync(pinned_host, src->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return TP_OK;
+}
+
+int tp_event_create(tp_ctx* ctx, tp_event** out) {
+    TP_CHECK_ARG(ctx && out, "tp_event_create: NULL argument");
+    cudaSetDevice(ctx->device);
+    tp_event* e = new tp_event();
+    cudaError_t rc = cudaEventCreate(&e->ev);
+    if (rc != cudaSuccess) {
+        delete e;
+        tp::set_error("cudaEventCreate failed: %s", cudaGetErrorString(rc));
+        return TP_ERR_CUDA;
+    }
+    *out = e;
+    return TP_OK;
+}
+
+int tp_event_record(tp_ctx* ctx, tp_event* ev) {
+    TP_CHECK_ARG(ctx && ev, "tp_event_record: NULL argument");
+    TP_CUDA(cudaEventRecord(ev->ev, ctx->stream));
+    return TP_OK;
+}
+
+int tp_event_sync(tp_event* ev) {
+    TP_CHECK_ARG(ev, "tp_event_sync: NULL event");
+    TP_CUDA(cudaEventSynchronize(ev->ev));
+    return TP_OK;
+}
+
+int tp_event_elapsed_ms(tp_event* start, tp_event* stop, float* ms) {
+    TP_CHECK_ARG(start && stop && ms, "tp_event_elapsed_ms: NULL argument");
+    TP_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    return TP_OK;
+}
+
+int tp_event_destroy(tp_event* ev) {
+    if (ev) {
+        cudaEventDestroy(ev->ev);
+        delete ev;
+    }
+    return TP_OK;
+}
+
 int tp_host_alloc_pinned(size_t bytes, void** out) {
     TP_CHECK_ARG(out, "tp_host_alloc_pinned: NULL out pointer");
     TP_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
@@ -298,8 +392,10 @@ int tp_host_free_pinned(void* p) {
 
 int tp_graph_begin(tp_ctx* ctx) {
     TP_CHECK_ARG(ctx && !ctx->capturing, "tp_graph_begin: NULL ctx or capture already active");
+    cudaSetDevice(ctx->device);
     TP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
+    ctx->capture_pool = new tp::Allocator();
     return TP_OK;
 }
 
@@ -307,9 +403,13 @@ int tp_graph_end(tp_ctx* ctx, tp_graph** out) {
     TP_CHECK_ARG(ctx && out && ctx->capturing, "tp_graph_end: no capture active");
     ctx->capturing = false;
     tp_graph* g = new tp_graph();
+    g->pool = ctx->capture_pool;
+    g->device = ctx->device;
+    ctx->capture_pool = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
     if (e != cudaSuccess || !g->graph) {
         cudaGetLastError();
+        drop_pool(g->pool);
         delete g;
         tp::set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
         return TP_ERR_CUDA;
@@ -318,6 +418,7 @@ int tp_graph_end(tp_ctx* ctx, tp_graph** out) {
     if (e != cudaSuccess) {
         cudaGetLastError();
         cudaGraphDestroy(g->graph);
+        drop_pool(g->pool);
         delete g;
         tp::set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
         return TP_ERR_CUDA;
@@ -343,8 +444,10 @@ int tp_graph_launch(tp_ctx* ctx, tp_graph* g) {
 
 int tp_graph_destroy(tp_graph* g) {
     if (!g) return TP_OK;
+    cudaSetDevice(g->device);
     if (g->exec) cudaGraphExecDestroy(g->exec);
     if (g->graph) cudaGraphDestroy(g->graph);
+    drop_pool(g->pool);               // the caller synchronises before destroying a graph in flight
     delete g;
     return TP_OK;
 }

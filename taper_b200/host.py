@@ -1,0 +1,251 @@
+"""Python handles over the flat C entry points of the C++ host layer (include/taper_b200_host.h).
+
+Used by tests/, bench.py and __graft_entry__.py.  All compute runs in libtaper_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .capi import check, lib
+
+F32 = np.float32
+
+# Canonical layer specs for BASELINE.json's configs
+MLP_784_128_10 = "linear:784:128,relu,linear:128:10"                       # cfg1 / cfg2
+MLP_EXAMPLE = "linear:784:128,relu,linear:128:64,relu,linear:64:10"         # examples/train_mnist.rs:28-51
+MLP_784_1024_1024_10 = "linear:784:1024,relu,linear:1024:1024,relu,linear:1024:10"   # cfg4
+CNN2 = ("conv_relu:1:32:3:1:1,maxpool:2:2,conv_relu:32:64:3:1:1,maxpool:2:2,flatten,linear:3136:10")   # cfg3(i)
+CNN5 = ("conv_relu:1:32:3:1:1,conv_relu:32:32:3:1:1,maxpool:2:2,conv_relu:32:64:3:1:1,conv_relu:64:64:3:1:1,maxpool:2:2,"
+        "conv_relu:64:128:3:1:1,gap,flatten,linear:128:128,relu,linear:128:64,relu,linear:64:10")      # examples/train_mnist_cnn.rs:35-100
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=F32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _shape(dims):
+    return (C.c_size_t * len(dims))(*[int(d) for d in dims])
+
+
+def set_device(device):
+    check(lib.tp_host_set_device(int(device)))
+
+
+def config(conv_full_adjoint=-1, fuse_linear_relu=-1, reference_op_sequence=-1, gemm_mode=-1):
+    check(lib.tp_host_config(int(conv_full_adjoint), int(fuse_linear_relu), int(reference_op_sequence), int(gemm_mode)))
+
+
+def host_ctx():
+    h = C.c_void_p()
+    check(lib.tp_host_ctx(C.byref(h)))
+    return h
+
+
+def launches() -> int:
+    c = C.c_uint64()
+    check(lib.tp_ctx_launch_count(host_ctx(), C.byref(c)))
+    return c.value
+
+
+def sync():
+    check(lib.tp_sync(host_ctx()))
+
+
+class Event:
+    def __init__(self):
+        self.h = C.c_void_p()
+        check(lib.tp_event_create(host_ctx(), C.byref(self.h)))
+
+    def record(self):
+        check(lib.tp_event_record(host_ctx(), self.h))
+
+    def sync(self):
+        check(lib.tp_event_sync(self.h))
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float()
+        check(lib.tp_event_elapsed_ms(self.h, stop.h, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib.tp_event_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """float32 numpy view over cudaMallocHost memory."""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape))
+        self.p = C.c_void_p()
+        check(lib.tp_host_alloc_pinned(max(n, 1) * 4, C.byref(self.p)))
+        self.array = np.ctypeslib.as_array(C.cast(self.p, C.POINTER(C.c_float)), shape=(n,)).reshape(shape)
+
+    def __del__(self):
+        try:
+            lib.tp_host_free_pinned(self.p)
+        except Exception:
+            pass
+
+
+class Model:
+    """nn::Sequential built from a layer spec (see taper_b200_host.h)."""
+
+    def __init__(self, spec: str, seed: int = 0):
+        self.h = C.c_void_p()
+        self.spec = spec
+        check(lib.tp_model_create(spec.encode(), int(seed), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_model_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def num_params(self) -> int:
+        n = C.c_int()
+        check(lib.tp_model_num_params(self.h, C.byref(n)))
+        return n.value
+
+    def param_shape(self, i):
+        numel, nd, dims = C.c_size_t(), C.c_int(), (C.c_size_t * 4)()
+        check(lib.tp_model_param_info(self.h, i, C.byref(numel), C.byref(nd), dims))
+        return tuple(dims[k] for k in range(nd.value))
+
+    def set_param(self, i, arr):
+        a = _f32(arr).reshape(-1)
+        check(lib.tp_model_set_param(self.h, i, _fp(a), a.size))
+
+    def get_param(self, i):
+        shape = self.param_shape(i)
+        out = np.empty(int(np.prod(shape)), F32)
+        check(lib.tp_model_get_param(self.h, i, _fp(out), out.size))
+        return out.reshape(shape)
+
+    def get_grad(self, i):
+        shape = self.param_shape(i)
+        out = np.empty(int(np.prod(shape)), F32)
+        has = C.c_int()
+        check(lib.tp_model_get_grad(self.h, i, _fp(out), out.size, C.byref(has)))
+        return out.reshape(shape) if has.value else None
+
+    def zero_grad(self):
+        check(lib.tp_model_zero_grad(self.h))
+
+    def load_from_oracle(self, oracle_model):
+        ps = oracle_model.parameters()
+        assert len(ps) == self.num_params()
+        for i, p in enumerate(ps):
+            self.set_param(i, p.data())
+
+    def forward(self, x, out_cap=None):
+        x = _f32(x)
+        cap = out_cap or max(x.shape[0] * 4096, 1 << 16)
+        out = np.empty(cap, F32)
+        n = C.c_size_t()
+        check(lib.tp_model_forward(self.h, _fp(x), _shape(x.shape), x.ndim, _fp(out), cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def loss_backward(self, x, labels):
+        x, labels = _f32(x), _f32(labels)
+        loss, correct, tl = C.c_float(), C.c_float(), C.c_size_t()
+        check(lib.tp_model_loss_backward(self.h, _fp(x), _shape(x.shape), x.ndim, _fp(labels), C.byref(loss), C.byref(correct), C.byref(tl)))
+        return loss.value, correct.value, tl.value
+
+
+class Trainer:
+    """train::Trainer: one train_epoch iteration per step() (src/train.rs:106-138)."""
+
+    def __init__(self, model: Model, optimizer="adam", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.model = model
+        self.h = C.c_void_p()
+        check(lib.tp_trainer_create(model.h, optimizer.encode(), lr, betas[0], betas[1], eps, weight_decay, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_trainer_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_lr(self, lr):
+        check(lib.tp_trainer_set_lr(self.h, lr))
+
+    def set_use_graph(self, on):
+        check(lib.tp_trainer_set_use_graph(self.h, int(bool(on))))
+
+    def step(self, images, labels):
+        images, labels = _f32(images), _f32(labels)
+        loss, correct = C.c_float(), C.c_float()
+        check(lib.tp_trainer_step(self.h, _fp(images), _fp(labels), images.shape[0], _shape(images.shape[1:]),
+                                  images.ndim - 1, C.byref(loss), C.byref(correct)))
+        return loss.value, correct.value
+
+    def step_async(self, images, labels, pinned=True):
+        """images/labels: C-contiguous float32 arrays that stay alive (and unmodified) until fetch()."""
+        check(lib.tp_trainer_step_async(self.h, _fp(images), _fp(labels), images.shape[0], _shape(images.shape[1:]),
+                                        images.ndim - 1, int(pinned)))
+
+    def load_dataset(self, images, labels, perm=None):
+        images, labels = _f32(images), _f32(labels)
+        p = None
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, dtype=np.uint32)
+            p = perm.ctypes.data_as(C.POINTER(C.c_uint32))
+        check(lib.tp_trainer_load_dataset(self.h, _fp(images), _fp(labels), images.shape[0], _shape(images.shape[1:]),
+                                          images.ndim - 1, p))
+
+    def step_resident(self, batch):
+        check(lib.tp_trainer_step_resident(self.h, int(batch)))
+
+    def fetch(self):
+        loss, correct = C.c_float(), C.c_float()
+        check(lib.tp_trainer_fetch(self.h, C.byref(loss), C.byref(correct)))
+        return loss.value, correct.value
+
+    def pending(self) -> int:
+        n = C.c_size_t()
+        check(lib.tp_trainer_pending(self.h, C.byref(n)))
+        return n.value
+
+    def eval(self, images, labels):
+        images, labels = _f32(images), _f32(labels)
+        loss, correct = C.c_float(), C.c_float()
+        check(lib.tp_trainer_eval(self.h, _fp(images), _fp(labels), images.shape[0], _shape(images.shape[1:]),
+                                  images.ndim - 1, C.byref(loss), C.byref(correct)))
+        return loss.value, correct.value
+
+    def save_checkpoint(self, path):
+        check(lib.tp_trainer_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        check(lib.tp_trainer_load_checkpoint(self.h, str(path).encode()))
+
+    def comm_init(self, rank, world, unique_id: bytes):
+        assert len(unique_id) == 128
+        check(lib.tp_trainer_comm_init(self.h, rank, world, unique_id))
+
+    def broadcast_params(self, root=0):
+        check(lib.tp_trainer_broadcast_params(self.h, root))
+
+    def graph_replays(self) -> int:
+        c = C.c_uint64()
+        check(lib.tp_trainer_graph_replays(self.h, C.byref(c)))
+        return c.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib.tp_comm_unique_id(buf))
+    return buf.raw

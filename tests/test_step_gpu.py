@@ -1,0 +1,260 @@
+"""Whole-step parity of the host layer (Tensor / Tape / nn / loss / optim / train, C++ over the C ABI)
+against the CPU oracle: forward record + reverse replay + optimizer step on identical seeded inputs,
+for BASELINE.json's configs (sizes the oracle finishes in seconds) and their ragged tails.
+Tolerance (north_star): max|x - ref| <= 1e-4 * max(||ref||_inf, 1e-6) per tensor; counts are exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import taper_ref as R
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def close(got, ref, tol=1e-4, what=""):
+    got = np.asarray(got, np.float64).reshape(-1)
+    ref = np.asarray(ref, np.float64).reshape(-1)
+    assert got.shape == ref.shape, what
+    scale = max(np.max(np.abs(ref)), 1e-6)
+    err = np.max(np.abs(got - ref))
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} > {tol} * {scale:.3e}"
+
+
+@pytest.fixture(autouse=True)
+def defaults():
+    from taper_b200 import host
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    R.Config.strict_reference_conv = True
+    R.Tape.reset()
+    yield
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    R.Config.strict_reference_conv = True
+
+
+def make_pair(builder, spec, seed=0):
+    from taper_b200 import host
+    rng = np.random.default_rng(seed)
+    ref = builder(rng)
+    for p in ref.parameters():                     # non-zero biases make the bias path observable
+        if len(p.shape) == 1:
+            p._data[:] = rng.standard_normal(p._data.size).astype(F32) * F32(0.05)
+    m = host.Model(spec, seed)
+    m.load_from_oracle(ref)
+    return ref, m
+
+
+def batches(rng, n_steps, batch, sample_shape, ragged=None):
+    for i in range(n_steps):
+        b = ragged if (ragged and i == n_steps - 1) else batch
+        x = rng.random((b,) + tuple(sample_shape)).astype(F32)
+        y = rng.integers(0, 10, b).astype(F32)
+        yield x, y
+
+
+def oracle_opt(kind, params, lr, wd):
+    if kind == "sgd":
+        return R.SGD(params, lr)
+    if kind == "adam":
+        return R.Adam(params, lr, None, None, wd)
+    return R.AdamW(params, lr, None, None, wd)
+
+
+def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=None, tol=1e-4, use_graph=True, seed=0):
+    from taper_b200 import host
+    ref, m = make_pair(builder, spec, seed)
+    tr = host.Trainer(m, kind, lr=lr, weight_decay=wd)
+    tr.set_use_graph(use_graph)
+    opt = oracle_opt(kind, ref.parameters(), lr, wd)
+    rng = np.random.default_rng(seed + 1)
+    for i, (x, y) in enumerate(batches(rng, steps, batch, sample_shape, ragged)):
+        loss_ref, acc_ref = R.train_step(ref, opt, R.Tensor.new(x, x.shape), R.Tensor.new(y, y.shape))
+        loss, correct = tr.step(x, y)
+        assert abs(loss - loss_ref) <= tol * max(abs(loss_ref), 1e-6), f"step {i}: loss {loss} vs {loss_ref}"
+        assert correct == round(acc_ref * x.shape[0]), f"step {i}: correct {correct} vs {acc_ref * x.shape[0]}"
+    for j, p in enumerate(ref.parameters()):
+        close(m.get_param(j), p.data(), tol, f"param {j} after {steps} steps")
+    return tr, m
+
+
+# ---- cfg1: MLP 784-128-10, batch 64, SGD (src/train.rs:390-394 model) --------------------------------------
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_cfg1_mlp_sgd_b64(gemm_mode):
+    from taper_b200 import host
+    host.config(gemm_mode=gemm_mode)
+    run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "sgd", 0.01, 0.0, 64, (784,), 12, ragged=32)
+
+
+# ---- cfg2: same MLP, batch 512, Adam ---------------------------------------------------------------------------
+@pytest.mark.parametrize("wd", [0.0, 1e-4])
+def test_cfg2_mlp_adam_b512(wd):
+    from taper_b200 import host
+    tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "adam", 1e-3, wd, 512, (784,), 8, ragged=96)
+    assert tr.graph_replays() >= 5             # steps 3.. of the B=512 shape ran as CUDA-graph replays
+
+
+def test_cfg2_eager_equals_graph_bitwise():
+    from taper_b200 import host
+    rng = np.random.default_rng(3)
+    data = list(batches(rng, 6, 512, (784,)))
+    outs = []
+    for use_graph in (False, True):
+        _, m = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 5)
+        tr = host.Trainer(m, "adam", lr=1e-3)
+        tr.set_use_graph(use_graph)
+        losses = [tr.step(x, y) for x, y in data]
+        outs.append((losses, [m.get_param(i) for i in range(m.num_params())]))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_example_mlp_adam_wd_b256():            # examples/train_mnist.rs:28-61: 784-128-64-10, Adam(1e-3, wd 1e-4), B=256
+    from taper_b200 import host
+    run_parity(lambda r: R.build_mlp([784, 128, 64, 10], r), host.MLP_EXAMPLE, "adam", 1e-3, 1e-4, 256, (784,), 6, ragged=96)
+
+
+def test_cfg4_mlp_wide_adam_b1024():
+    from taper_b200 import host
+    run_parity(lambda r: R.build_mlp([784, 1024, 1024, 10], r), host.MLP_784_1024_1024_10, "adam", 1e-3, 0.0, 1024, (784,), 3)
+
+
+def test_reference_op_sequence_records_reference_nodes_and_matches():
+    """Linear as transpose -> matmul -> add_broadcast (src/nn.rs:54-60) gives the same numbers as the fused node."""
+    from taper_b200 import host
+    rng = np.random.default_rng(11)
+    x = rng.random((64, 784)).astype(F32)
+    y = rng.integers(0, 10, 64).astype(F32)
+    res = {}
+    for ref_seq in (0, 1):
+        host.config(reference_op_sequence=ref_seq)
+        ref, m = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 2)
+        loss, correct, tape_len = m.loss_backward(x, y)
+        res[ref_seq] = (loss, correct, tape_len, [m.get_grad(i) for i in range(4)])
+    assert res[0][2] == 3                        # fused: Linear+ReLU, Linear, CE
+    assert res[1][2] == 8                        # 2 x (transpose, matmul, add_broadcast) + relu + CE (the reference adds 5 dead log_softmax nodes)
+    assert res[0][1] == res[1][1]
+    assert res[0][0] == pytest.approx(res[1][0], rel=1e-6)
+    R.Tape.reset()
+    logits = ref.forward(R.Tensor.new(x, x.shape))
+    l = R.cross_entropy_loss(logits, R.Tensor.new(y, y.shape))
+    l.backward()
+    for k in (0, 1):
+        assert res[k][0] == pytest.approx(float(l.data()[0]), rel=1e-5)
+        for g, p in zip(res[k][3], ref.parameters()):
+            close(g, p.grad(), 1e-4)
+
+
+# ---- cfg3: CNNs, strict_reference (A1) and full adjoint -----------------------------------------------------------
+@pytest.mark.parametrize("full", [0, 1])
+def test_cfg3_cnn2_adam(full):
+    from taper_b200 import host
+    host.config(conv_full_adjoint=full)
+    R.Config.strict_reference_conv = not full
+    run_parity(R.build_cnn2, host.CNN2, "adam", 0.01, 1e-4, 16, (1, 28, 28), 4, ragged=5, tol=2e-4)
+
+
+@pytest.mark.parametrize("full", [0, 1])
+def test_cfg3_cnn5_example_adam(full):           # examples/train_mnist_cnn.rs:35-137: Adam(0.01, wd 1e-4)
+    from taper_b200 import host
+    host.config(conv_full_adjoint=full)
+    R.Config.strict_reference_conv = not full
+    run_parity(R.build_cnn5, host.CNN5, "adam", 0.01, 1e-4, 8, (1, 28, 28), 3, tol=2e-4)
+
+
+def test_cnn5_strict_reference_trains_only_conv5_bias_and_linears():
+    from taper_b200 import host
+    ref, m = make_pair(R.build_cnn5, host.CNN5, 4)
+    rng = np.random.default_rng(0)
+    x = rng.random((4, 1, 28, 28)).astype(F32)
+    y = rng.integers(0, 10, 4).astype(F32)
+    m.loss_backward(x, y)
+    has = [m.get_grad(i) is not None for i in range(m.num_params())]
+    # params: conv1..5 (w, b) = indices 0..9, then three linears (w, b) = 10..15
+    assert has == [False] * 9 + [True] + [True] * 6
+
+
+def test_cfg5_cnn2_adamw_decays_gradless_params():                       # src/optim.rs:154-161 (A4)
+    from taper_b200 import host
+    run_parity(R.build_cnn2, host.CNN2, "adamw", 0.01, 1e-2, 8, (1, 28, 28), 3, tol=2e-4)
+
+
+def test_cnn_forward_only_matches_oracle():
+    from taper_b200 import host
+    ref, m = make_pair(R.build_cnn5, host.CNN5, 6)
+    x = np.random.default_rng(1).random((6, 1, 28, 28)).astype(F32)
+    close(m.forward(x), ref.forward(R.Tensor.new(x, x.shape)).data())
+
+
+# ---- device-resident dataset path == host-fed path -------------------------------------------------------------------
+def test_resident_dataset_gather_equals_host_batches():
+    from taper_b200 import host
+    rng = np.random.default_rng(9)
+    n, b = 1000, 128
+    X = rng.random((n, 784)).astype(F32)
+    Y = rng.integers(0, 10, n).astype(F32)
+    perm = rng.permutation(n).astype(np.uint32)
+    _, m1 = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 1)
+    _, m2 = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 1)
+    t1, t2 = host.Trainer(m1, "adam", lr=1e-3), host.Trainer(m2, "adam", lr=1e-3)
+    t2.load_dataset(X, Y, perm)
+    for s in range(12):                          # wraps around the dataset (cursor modulo n)
+        idx = perm[(s * b + np.arange(b)) % n]
+        r1 = t1.step(X[idx], Y[idx])
+        t2.step_resident(b)
+        r2 = t2.fetch()
+        assert r1 == r2, f"step {s}: {r1} vs {r2}"
+    for i in range(4):
+        np.testing.assert_array_equal(m1.get_param(i), m2.get_param(i))
+
+
+def test_async_pipeline_fifo_results():
+    from taper_b200 import host
+    rng = np.random.default_rng(2)
+    _, m1 = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 1)
+    _, m2 = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 1)
+    t1, t2 = host.Trainer(m1, "sgd", lr=0.01), host.Trainer(m2, "sgd", lr=0.01)
+    bufs = [(host.PinnedArray((64, 784)), host.PinnedArray((64,))) for _ in range(6)]
+    for px, py in bufs:
+        px.array[:] = rng.random((64, 784)).astype(F32)
+        py.array[:] = rng.integers(0, 10, 64).astype(F32)
+    sync = [t1.step(px.array, py.array) for px, py in bufs]
+    for px, py in bufs:
+        t2.step_async(px.array, py.array, pinned=True)
+    assert t2.pending() == 6
+    got = [t2.fetch() for _ in bufs]
+    assert got == sync
+    with pytest.raises(Exception):
+        t2.fetch()
+
+
+def test_eval_and_checkpoint_roundtrip(tmp_path):
+    from taper_b200 import host
+    ref, m = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 8)
+    tr = host.Trainer(m, "adam", lr=1e-3)
+    rng = np.random.default_rng(5)
+    x = rng.random((100, 784)).astype(F32)
+    y = rng.integers(0, 10, 100).astype(F32)
+    loss, correct = tr.eval(x, y)
+    logits = ref.forward(R.Tensor.new(x, x.shape))
+    assert loss == pytest.approx(float(R.cross_entropy_loss(logits, R.Tensor.new(y, y.shape)).data()[0]), rel=1e-5)
+    assert correct == round(float(R.accuracy(logits, R.Tensor.new(y, y.shape))) * 100)
+    path = tmp_path / "ckpt.txt"
+    tr.save_checkpoint(path)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "4" and lines[1] == "2 128 784"            # src/train.rs:272-281 text format
+    before = [m.get_param(i) for i in range(4)]
+    tr.step(x[:64], y[:64])
+    assert not np.array_equal(before[0], m.get_param(0))
+    tr.load_checkpoint(path)
+    for i in range(4):
+        np.testing.assert_array_equal(before[i], m.get_param(i))
+
+
+def test_shape_errors_are_reported_not_fatal():
+    from taper_b200 import host, TaperError
+    m = host.Model(host.MLP_784_128_10, 0)
+    with pytest.raises(TaperError, match="inner dimensions"):
+        m.forward(np.zeros((4, 100), F32))
+    with pytest.raises(TaperError, match="unknown layer"):
+        host.Model("linear:4:4,bogus", 0)
