@@ -51,6 +51,7 @@ struct tp_ctx {
     // scratch for split-K / two-stage reductions (grown on demand, never during capture)
     float* scratch = nullptr;
     size_t scratch_bytes = 0;
+    std::vector<float*> retired_scratch;
     // communication
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;

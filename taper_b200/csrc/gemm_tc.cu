@@ -1,8 +1,513 @@
-// placeholder until the tcgen05 path lands (next commit)
+// TF32 tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with the accumulator in TMEM, operands
+// staged in 128B-swizzled shared memory by TMA, mbarrier producer/consumer pipeline, warp-specialised
+// (warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = operand splitter + epilogue).
+//
+// Replaces matrixmultiply::sgemm / cblas_sgemm behind sgemm_rowmajor (src/gemm.rs:8-49, 72-119) for the
+// three call shapes of the reference: (N,N) forward, (N,T) dA, (T,N) dB (src/ops.rs:215-226, 254-265,
+// 280-291) plus the fused Linear (N,T).  No operand is ever transposed in memory: a transposed operand is
+// described to the tensor core as MN-major (instruction-descriptor bits 15/16), a plain one as K-major.
+//
+// Math modes
+//   1xTF32 (mode 2): operands are read as fp32 and used at TF32 precision (10-bit mantissa).
+//   3xTF32 (mode 1): x = hi + lo with hi = x truncated to TF32; D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with
+//                    fp32 accumulation: fp32-accurate products (~2^-21 relative) at one third of the MMA rate.
+//                    The split is done in shared memory by the (otherwise idle) epilogue warps, so HBM traffic
+//                    is unchanged.
+// Small problems are split along K so that the grid covers the 148 SMs; the partial tiles are folded in a
+// fixed order by the last-arriving CTA of each tile (deterministic, one launch).
 #include "common.cuh"
-namespace tp {
-int gemm_tc(tp_ctx*, int, int, int, int, int, float, const float*, const float*, float, float*, const Epilogue&, int) {
+
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;              // UMMA M (cta_group::1)
+constexpr int BK = 32;               // floats per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;            // tf32: 32 bytes per instruction
+constexpr int kThreads = 192;        // 6 warps
+constexpr int kMaxTiles = 8192;      // split-K tile counters
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    const long long t0 = clock64();
+    do {
+        // a pipeline bug must surface as a launch failure, never as a hung GPU
+        if (clock64() - t0 > 4000000000LL) __trap();
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (descriptor version 1 for sm_100):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
+//   [46,48) version = 1, [61,64) layout type.
+// K-major operand : layout type 2 (SWIZZLE_128B, 16-byte chunks XOR row % 8; TMA SWIZZLE_128B).  Rows of 128 B
+//                   (32 floats of K); 8 rows form a 1024 B atom -> SBO = 1024; LBO unused.
+// MN-major operand: 32-bit operands only exist in layout type 1 (SWIZZLE_128B_BASE32B: 32-byte chunks XOR row % 4;
+//                   TMA SWIZZLE_128B_ATOM_32B).  Rows of 128 B (32 floats of M/N) indexed by k; 4 k-rows form a 512 B
+//                   atom -> SBO = 512 (next 4 k), LBO = BK*128 = 4096 (next 32 elements of M/N = the next TMA box).
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    constexpr uint32_t lbo_bytes = MN_MAJOR ? BK * 128 : 16, sbo_bytes = MN_MAJOR ? 512 : 1024;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(MN_MAJOR ? 1 : 2) << 61;
+    return d;
+}
+
+struct EpiArgs {
+    const float* bias;
+    const float* relu_mask;
+    int relu;
+};
+
+struct GemmParams {
+    int m, n, k;
+    int kblocks_per_split, splits;
+    float alpha, beta;
+    float* c;
+    float* partial;      // [tile][split][BM][BN] when splits > 1
+    int* counters;       // one per output tile, zero between launches
+    EpiArgs ep;
+};
+
+template <int BN, bool SPLIT3>
+struct Smem {
+    static constexpr int kStages = SPLIT3 ? 3 : 6;
+    static constexpr int kABytes = BM * BK * 4;
+    static constexpr int kBBytes = BN * BK * 4;
+    static constexpr int kStageBytes = (kABytes + kBBytes) * (SPLIT3 ? 2 : 1);
+    static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float epilogue_elem(float acc, const GemmParams& p, size_t idx, int col) {
+    float v = p.alpha * acc;
+    if (p.beta != 0.0f) v += p.beta * p.c[idx];
+    if (p.ep.bias) v += __ldg(p.ep.bias + col);
+    if (p.ep.relu) v = fmaxf(v, 0.0f);
+    if (p.ep.relu_mask) v = __ldg(p.ep.relu_mask + idx) > 0.0f ? v : 0.0f;
+    return v;
+}
+
+// A_MN / B_MN: operand is MN-major in memory (trans_a = 1 / trans_b = 0 of sgemm_rowmajor).
+template <int BN, bool A_MN, bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+    using S = Smem<BN, SPLIT3>;
+    constexpr int kStages = S::kStages;
+    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B needs 1024 B alignment
+    uint64_t* full_bar = (uint64_t*)(smem + kStages * S::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* split_bar = empty_bar + kStages;        // SPLIT3: hi/lo tiles ready for the MMA warp
+    uint64_t* accum_bar = split_bar + kStages;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+    __shared__ int s_is_last;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int total_kb = (p.k + BK - 1) / BK;
+    const int kb0 = blockIdx.z * p.kblocks_per_split;
+    const int kb1 = min(total_kb, kb0 + p.kblocks_per_split);
+    const int nkb = kb1 - kb0;                        // >= 1 by construction
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+            mbar_init(split_bar + s, 128);            // every thread of the 4 splitter warps arrives
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                  // TMEM allocation is owned by the MMA warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto a_hi = [&](int s) { return smem + s * S::kStageBytes; };
+    auto b_hi = [&](int s) { return smem + s * S::kStageBytes + S::kABytes; };
+    auto a_lo = [&](int s) { return smem + s * S::kStageBytes + S::kABytes + S::kBBytes; };
+    auto b_lo = [&](int s) { return smem + s * S::kStageBytes + 2 * S::kABytes + S::kBBytes; };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
+                mbar_wait(empty_bar + s, ph ^ 1);
+                mbar_expect_tx(full_bar + s, S::kABytes + S::kBBytes);
+                const int k0 = (kb0 + i) * BK;
+                if (A_MN) {
+#pragma unroll
+                    for (int g = 0; g < BM / 32; ++g) tma_load_2d(a_hi(s) + g * (BK * 128), &map_a, full_bar + s, m0 + 32 * g, k0);
+                } else {
+                    tma_load_2d(a_hi(s), &map_a, full_bar + s, k0, m0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int g = 0; g < BN / 32; ++g) tma_load_2d(b_hi(s) + g * (BK * 128), &map_b, full_bar + s, n0 + 32 * g, k0);
+                } else {
+                    tma_load_2d(b_hi(s), &map_b, full_bar + s, k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            // instruction descriptor: c = F32 (bit 4), a/b = TF32 (2 << 7, 2 << 10), majors (15, 16), N >> 3 (17), M >> 4 (24)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t kStepA = A_MN ? 1024 : UMMA_K * 4;      // bytes per UMMA_K step inside a stage
+            constexpr uint32_t kStepB = B_MN ? 1024 : UMMA_K * 4;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
+                mbar_wait((SPLIT3 ? split_bar : full_bar) + s, ph);
+                tc_fence_after();
+                const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
+                if (SPLIT3) {
+                    const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk)          // small terms first
+                        tc_mma_tf32(tmem_base, make_desc<A_MN>(al + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB),
+                                    idesc, (i | kk) ? 1u : 0u);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                        tc_mma_tf32(tmem_base, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bl + kk * kStepB),
+                                    idesc, 1u);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                        tc_mma_tf32(tmem_base, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB),
+                                    idesc, 1u);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                        tc_mma_tf32(tmem_base, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB),
+                                    idesc, (i | kk) ? 1u : 0u);
+                }
+                tc_commit(empty_bar + s);             // frees the smem stage when these MMAs retire
+            }
+            tc_commit(accum_bar);                     // accumulator complete
+        }
+    } else {
+        // ===== warps 2-5: operand splitter (3xTF32) during the main loop, then epilogue =====
+        const int t = threadIdx.x - 64;               // 0..127
+        if (SPLIT3) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
+                mbar_wait(full_bar + s, ph);
+                // elementwise on identical offsets, so the swizzled layout is preserved:
+                //   hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi
+                float4* hi4 = (float4*)a_hi(s);       // A and B tiles are contiguous: [A_hi | B_hi | A_lo | B_lo]
+                float4* lo4 = (float4*)a_lo(s);
+                constexpr int kVec = (S::kABytes + S::kBBytes) / 16;
+#pragma unroll 4
+                for (int v = t; v < kVec; v += 128) {
+                    float4 x = hi4[v], h, l;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+                    hi4[v] = h;
+                    lo4[v] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(split_bar + s);
+            }
+        }
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int gm = m0 + row;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool vec_ok = (p.n % 4 == 0);
+        if (p.splits == 1) {
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                if (gm < p.m) {
+                    const size_t rowoff = (size_t)gm * p.n;
+                    if (vec_ok && n0 + c0 + 16 <= p.n) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 o;
+                            const int col = n0 + c0 + j;
+                            o.x = epilogue_elem(__uint_as_float(v[j + 0]), p, rowoff + col + 0, col + 0);
+                            o.y = epilogue_elem(__uint_as_float(v[j + 1]), p, rowoff + col + 1, col + 1);
+                            o.z = epilogue_elem(__uint_as_float(v[j + 2]), p, rowoff + col + 2, col + 2);
+                            o.w = epilogue_elem(__uint_as_float(v[j + 3]), p, rowoff + col + 3, col + 3);
+                            *(float4*)(p.c + rowoff + col) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = n0 + c0 + j;
+                            if (col < p.n) p.c[rowoff + col] = epilogue_elem(__uint_as_float(v[j]), p, rowoff + col, col);
+                        }
+                    }
+                }
+            }
+        } else {
+            // split-K: park the raw accumulator tile, the last CTA of this tile folds all splits in order
+            const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+            float* mine = p.partial + ((size_t)tile * p.splits + blockIdx.z) * (BM * BN) + (size_t)row * BN;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *(float4*)(mine + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                            __uint_as_float(v[j + 3]));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // the 4 epilogue warps only
+            if (t == 0) {
+                int prev = atomicAdd(p.counters + tile, 1);
+                s_is_last = (prev == p.splits - 1);
+                if (s_is_last) p.counters[tile] = 0;                     // ready for the next launch / graph replay
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_is_last) {
+                __threadfence();
+                if (gm < p.m) {
+                    const float* base = p.partial + (size_t)tile * p.splits * (BM * BN) + (size_t)row * BN;
+                    const size_t rowoff = (size_t)gm * p.n;
+                    for (int c0 = 0; c0 < BN; c0 += 4) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int z = 0; z < p.splits; ++z) {
+                            float4 x = __ldcg((const float4*)(base + (size_t)z * (BM * BN) + c0));
+                            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                        }
+                        const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = n0 + c0 + j;
+                            if (col < p.n) p.c[rowoff + col] = epilogue_elem(a[j], p, rowoff + col, col);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+    EncodeTiledFn encode = nullptr;
+    int* counters = nullptr;
+    bool attr_set[4][2][2][2] = {};
+};
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// stored matrix [rows, cols] row-major fp32; box = {32 floats, box_rows}; OOB elements read as zero
+bool make_map(EncodeTiledFn enc, CUtensorMap* map, const float* ptr, int rows, int cols, int box_rows, bool mn_major) {
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SPLIT3>
+int launch(tp_ctx* ctx, TcState* st, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, SPLIT3>;
+    constexpr int smem = Smem<BN, SPLIT3>::kTotal;
+    constexpr int bi = BN == 16 ? 0 : BN == 32 ? 1 : BN == 64 ? 2 : 3;
+    if (!st->attr_set[bi][A_MN][B_MN][SPLIT3]) {
+        TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        st->attr_set[bi][A_MN][B_MN][SPLIT3] = true;
+    }
+    kern<<<grid, kThreads, smem, ctx->stream>>>(ma, mb, p);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+template <int BN, bool SPLIT3>
+int dispatch_major(tp_ctx* ctx, TcState* st, int ta, int tb, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
+    const bool a_mn = ta != 0, b_mn = tb == 0;
+    if (!a_mn && !b_mn) return launch<BN, false, false, SPLIT3>(ctx, st, ma, mb, p, grid);
+    if (!a_mn && b_mn) {
+        if constexpr (BN >= 32) return launch<BN, false, true, SPLIT3>(ctx, st, ma, mb, p, grid);
+    }
+    if (a_mn && !b_mn) return launch<BN, true, false, SPLIT3>(ctx, st, ma, mb, p, grid);
+    if (a_mn && b_mn) {
+        if constexpr (BN >= 32) return launch<BN, true, true, SPLIT3>(ctx, st, ma, mb, p, grid);
+    }
     return TP_ERR_UNSUPPORTED;
 }
-void gemm_tc_destroy(tp_ctx*) {}
+
+}  // namespace
+
+namespace tp {
+
+int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, const float* b, float beta,
+            float* c, const Epilogue& ep, int mode) {
+    if (m <= 0 || n <= 0) return TP_OK;
+    if (k <= 0) return TP_ERR_UNSUPPORTED;
+    // TMA needs 16-byte aligned bases and row pitches: the contiguous dimension of each stored operand % 4 == 0
+    const int a_rows = ta ? k : m, a_cols = ta ? m : k;       // A stored [m,k] (N) or [k,m] (T)
+    const int b_rows = tb ? n : k, b_cols = tb ? k : n;       // B stored [k,n] (N) or [n,k] (T)
+    if ((a_cols & 3) || (b_cols & 3) || (((uintptr_t)a | (uintptr_t)b) & 15)) return TP_ERR_UNSUPPORTED;
+    if (k < 16 || (long)m * n * k < (1L << 16)) return TP_ERR_UNSUPPORTED;     // not worth a tensor-core tile
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TP_ERR_UNSUPPORTED;
+    cudaSetDevice(ctx->device);
+    TcState* st = (TcState*)ctx->tc_state;
+    if (!st) {
+        st = new TcState();
+        st->encode = enc;
+        if (ctx->capturing) { delete st; return TP_ERR_UNSUPPORTED; }
+        TP_CUDA(cudaMalloc(&st->counters, kMaxTiles * sizeof(int)));
+        TP_CUDA(cudaMemsetAsync(st->counters, 0, kMaxTiles * sizeof(int), ctx->stream));
+        ctx->tc_state = st;
+    }
+    const bool b_mn = tb == 0;
+    int bn = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : 128;
+    if (b_mn && bn < 32) bn = 32;
+    const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + bn - 1) / bn;
+    const long tiles = (long)tiles_m * tiles_n;
+    const int kblocks = (k + BK - 1) / BK;
+    int splits = 1;
+    if (tiles < ctx->sm_count && kblocks >= 4) {
+        splits = (int)(ctx->sm_count / tiles);
+        if (splits > kblocks / 2) splits = kblocks / 2;       // at least two k-blocks per CTA
+        if (splits > 64) splits = 64;
+        if (splits < 1) splits = 1;
+    }
+    int kps = (kblocks + splits - 1) / splits;
+    splits = (kblocks + kps - 1) / kps;
+    if (tiles > kMaxTiles || tiles_m > 65535 || splits > 65535) return TP_ERR_UNSUPPORTED;
+
+    CUtensorMap ma, mb;
+    if (!make_map(enc, &ma, a, a_rows, a_cols, ta ? 32 : BM, ta != 0)) return TP_ERR_UNSUPPORTED;
+    if (!make_map(enc, &mb, b, b_rows, b_cols, b_mn ? 32 : bn, b_mn)) return TP_ERR_UNSUPPORTED;
+
+    GemmParams p;
+    p.m = m; p.n = n; p.k = k;
+    p.kblocks_per_split = kps; p.splits = splits;
+    p.alpha = alpha; p.beta = beta;
+    p.c = c;
+    p.partial = nullptr;
+    p.counters = st->counters;
+    p.ep = EpiArgs{ep.bias, ep.relu_mask, ep.relu};
+    if (splits > 1) {
+        int rc = ensure_scratch(ctx, (size_t)tiles * splits * BM * bn * sizeof(float));
+        if (rc) return rc;
+        p.partial = ctx->scratch;
+    }
+    dim3 grid(tiles_n, tiles_m, splits);
+    const bool split3 = mode == 1;
+#define TP_BN(BNV)                                                                                          \
+    return split3 ? dispatch_major<BNV, true>(ctx, st, ta, tb, ma, mb, p, grid)                             \
+                  : dispatch_major<BNV, false>(ctx, st, ta, tb, ma, mb, p, grid)
+    switch (bn) {
+        case 16: TP_BN(16);
+        case 32: TP_BN(32);
+        case 64: TP_BN(64);
+        default: TP_BN(128);
+    }
+#undef TP_BN
+}
+
+void gemm_tc_destroy(tp_ctx* ctx) {
+    TcState* st = (TcState*)ctx->tc_state;
+    if (!st) return;
+    if (st->counters) cudaFree(st->counters);
+    delete st;
+    ctx->tc_state = nullptr;
+}
+
 }  // namespace tp

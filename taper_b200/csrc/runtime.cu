@@ -97,8 +97,8 @@ int ensure_scratch(tp_ctx* ctx, size_t bytes) {
     }
     size_t want = bytes < (8u << 20) ? (8u << 20) : bytes;
     float* p = nullptr;
-    TP_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    // The old block is kept until the context dies: a captured CUDA graph may still point at it.
+    if (ctx->scratch) ctx->retired_scratch.push_back(ctx->scratch);
     ctx->scratch = nullptr;
     ctx->scratch_bytes = 0;
     TP_CUDA(cudaMalloc(&p, want));
@@ -176,6 +176,7 @@ int tp_ctx_destroy(tp_ctx* ctx) {
     tp::gemm_tc_destroy(ctx);
     ctx->alloc.release_all();
     if (ctx->scratch) cudaFree(ctx->scratch);
+    for (float* q : ctx->retired_scratch) cudaFree(q);
     if (ctx->dev_error) cudaFree(ctx->dev_error);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
