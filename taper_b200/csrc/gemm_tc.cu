@@ -9,12 +9,14 @@
 //
 // Math modes
 //   1xTF32 (mode 2): operands are read as fp32 and used at TF32 precision (10-bit mantissa).
-//   3xTF32 (mode 1): x = hi + lo with hi = x truncated to TF32; D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with
-//                    fp32 accumulation: fp32-accurate products (~2^-21 relative) at one third of the MMA rate.
-//                    The split is done in shared memory by the (otherwise idle) epilogue warps, so HBM traffic
-//                    is unchanged.
-// Small problems are split along K so that the grid covers the 148 SMs; the partial tiles are folded in a
-// fixed order by the last-arriving CTA of each tile (deterministic, one launch).
+//   3xTF32 (mode 1): x = hi + lo with hi = x truncated to TF32 (what the tensor core does to an fp32 operand on its
+//                    own) and lo = x - hi; D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation: fp32-accurate
+//                    products (~2^-21 relative) at one third of the MMA rate.  The lo tiles are produced in shared
+//                    memory by four dedicated warps, so HBM traffic is unchanged.
+// Small problems are split along K over a thread-block cluster (2/4/8 CTAs along grid z): every CTA parks its
+// partial accumulator tile in its own shared memory and, after a cluster barrier, each CTA folds one slice of the
+// rows over all peers through distributed shared memory in a fixed order (deterministic, no global scratch, one
+// launch).  The epilogue always goes TMEM -> shared memory -> coalesced 128-bit global stores.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -24,8 +26,6 @@ namespace {
 constexpr int BM = 128;              // UMMA M (cta_group::1)
 constexpr int BK = 32;               // floats per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;            // tf32: 32 bytes per instruction
-constexpr int kThreads = 192;        // 6 warps
-constexpr int kMaxTiles = 8192;      // split-K tile counters
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +88,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local_smem_addr` in the shared memory of CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    // not volatile: the tiles are immutable between the two cluster barriers, so loads may be batched and reordered
+    asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // Shared-memory matrix descriptor (descriptor version 1 for sm_100):
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
 //   [46,48) version = 1, [61,64) layout type.
@@ -108,6 +125,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+// development aid: per-phase SM-clock timestamps of CTA (0,0,0), read back with tpdbg_gemm_times()
+__device__ long long g_dbg_t[16];
+#define DBG_T(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg_t[slot] = clock64(); } while (0)
+
 struct EpiArgs {
     const float* bias;
     const float* relu_mask;
@@ -116,21 +137,20 @@ struct EpiArgs {
 
 struct GemmParams {
     int m, n, k;
-    int kblocks_per_split, splits;
+    int splits;
     float alpha, beta;
     float* c;
-    float* partial;      // [tile][split][BM][BN] when splits > 1
-    int* counters;       // one per output tile, zero between launches
     EpiArgs ep;
 };
 
 template <int BN, bool SPLIT3>
 struct Smem {
-    static constexpr int kStages = SPLIT3 ? 3 : 6;
     static constexpr int kABytes = BM * BK * 4;
     static constexpr int kBBytes = BN * BK * 4;
     static constexpr int kStageBytes = (kABytes + kBBytes) * (SPLIT3 ? 2 : 1);
-    static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // as deep as ~200 KB allows (the TMA -> split -> MMA -> free round trip is ~2.5k cycles), at most 8
+    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ float epilogue_elem(float acc, const GemmParams& p, size_t idx, int col) {
@@ -143,27 +163,44 @@ __device__ __forceinline__ float epilogue_elem(float acc, const GemmParams& p, s
 }
 
 // A_MN / B_MN: operand is MN-major in memory (trans_a = 1 / trans_b = 0 of sgemm_rowmajor).
+//
+// Warp roles        1xTF32 (192 threads)                 3xTF32 (320 threads)
+//   warp 0          TMA producer                         TMA producer
+//   warp 1          MMA issuer, TMEM owner               MMA issuer, TMEM owner
+//   warps 2-5       epilogue                             hi/lo operand splitter
+//   warps 6-9       -                                    accumulator drain + epilogue
+//
+// 3xTF32 is the fp32-parity mode, so it also bounds the depth of the tensor core's own accumulation: the
+// hardware accumulator truncates, which biases long sums of same-signed products (MNIST pixels, post-ReLU
+// activations) by ~K/3 * 2^-24.  Every kChunk k-blocks the TMEM accumulator (double-buffered) is drained
+// into fp32 registers with round-to-nearest adds while the next chunk is already being multiplied.
 template <int BN, bool A_MN, bool B_MN, bool SPLIT3>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
     using S = Smem<BN, SPLIT3>;
     constexpr int kStages = S::kStages;
-    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B needs 1024 B alignment
+    constexpr int kChunk = 4;                         // k-blocks (128 elements of K) per tensor-core accumulation
+    constexpr uint32_t kTmemCols = SPLIT3 ? (2 * BN < 32 ? 32 : 2 * BN) : (BN < 32 ? 32 : BN);
+    constexpr int kPitch = BN + 4;                    // floats per staged accumulator row
+    constexpr int kEpiWarp0 = SPLIT3 ? 6 : 2;         // first of the four epilogue warps
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // swizzle atoms need 1024 B alignment; offsetting the array (instead of rounding a generic pointer) keeps every
+    // access below in the shared address space (LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = (uint64_t*)(smem + kStages * S::kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* split_bar = empty_bar + kStages;        // SPLIT3: hi/lo tiles ready for the MMA warp
-    uint64_t* accum_bar = split_bar + kStages;
-    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-    __shared__ int s_is_last;
+    uint64_t* split_bar = empty_bar + kStages;        // 3xTF32: hi/lo tiles ready for the MMA warp
+    uint64_t* acc_full = split_bar + kStages;         // [2] accumulator buffer complete (tcgen05.commit)
+    uint64_t* acc_empty = acc_full + 2;               // [2] accumulator buffer drained (3xTF32)
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int total_kb = (p.k + BK - 1) / BK;
-    const int kb0 = blockIdx.z * p.kblocks_per_split;
-    const int kb1 = min(total_kb, kb0 + p.kblocks_per_split);
-    const int nkb = kb1 - kb0;                        // >= 1 by construction
+    const int kb0 = (int)(((long long)blockIdx.z * total_kb) / p.splits);            // balanced: sizes differ by at most one
+    const int kb1 = (int)(((long long)(blockIdx.z + 1) * total_kb) / p.splits);
+    const int nkb = kb1 - kb0;                        // >= 1 because splits <= total_kb
+    if (threadIdx.x == 0) DBG_T(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -171,7 +208,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_init(empty_bar + s, 1);
             mbar_init(split_bar + s, 128);            // every thread of the 4 splitter warps arrives
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 4);              // one arrival per drain warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                  // TMEM allocation is owned by the MMA warp
@@ -182,11 +222,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG_T(1);
 
     auto a_hi = [&](int s) { return smem + s * S::kStageBytes; };
     auto b_hi = [&](int s) { return smem + s * S::kStageBytes + S::kABytes; };
     auto a_lo = [&](int s) { return smem + s * S::kStageBytes + S::kABytes + S::kBBytes; };
     auto b_lo = [&](int s) { return smem + s * S::kStageBytes + 2 * S::kABytes + S::kBBytes; };
+    float* stage = (float*)smem;                      // accumulator tile staging (the pipeline stages are free by then)
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -219,143 +261,200 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             constexpr uint32_t kStepA = A_MN ? 1024 : UMMA_K * 4;      // bytes per UMMA_K step inside a stage
             constexpr uint32_t kStepB = B_MN ? 1024 : UMMA_K * 4;
+            uint32_t tmem_d = tmem_base;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % kStages;
                 const uint32_t ph = (i / kStages) & 1;
+                uint32_t fresh = (i == 0) ? 1u : 0u;  // first MMA of an accumulation overwrites
+                if (SPLIT3 && i % kChunk == 0) {
+                    const int chunk = i / kChunk, b = chunk & 1;
+                    mbar_wait(acc_empty + b, ((chunk >> 1) & 1) ^ 1);      // buffer drained by the epilogue warps
+                    tc_fence_after();
+                    tmem_d = tmem_base + b * BN;
+                    fresh = 1u;
+                }
                 mbar_wait((SPLIT3 ? split_bar : full_bar) + s, ph);
                 tc_fence_after();
+                if (i == 0) DBG_T(2);
+                if (i == nkb - 1) DBG_T(3);
                 const uint32_t ah = smem_u32(a_hi(s)), bh = smem_u32(b_hi(s));
                 if (SPLIT3) {
                     const uint32_t al = smem_u32(a_lo(s)), bl = smem_u32(b_lo(s));
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk)          // small terms first
-                        tc_mma_tf32(tmem_base, make_desc<A_MN>(al + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB),
-                                    idesc, (i | kk) ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, make_desc<A_MN>(al + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB), idesc,
+                                    (fresh && kk == 0) ? 0u : 1u);
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk)
-                        tc_mma_tf32(tmem_base, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bl + kk * kStepB),
-                                    idesc, 1u);
+                        tc_mma_tf32(tmem_d, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bl + kk * kStepB), idesc, 1u);
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk)
-                        tc_mma_tf32(tmem_base, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB),
-                                    idesc, 1u);
+                        tc_mma_tf32(tmem_d, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB), idesc, 1u);
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < BK / UMMA_K; ++kk)
-                        tc_mma_tf32(tmem_base, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB),
-                                    idesc, (i | kk) ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, make_desc<A_MN>(ah + kk * kStepA), make_desc<B_MN>(bh + kk * kStepB), idesc,
+                                    (fresh && kk == 0) ? 0u : 1u);
                 }
                 tc_commit(empty_bar + s);             // frees the smem stage when these MMAs retire
+                if (SPLIT3 ? (i % kChunk == kChunk - 1 || i == nkb - 1) : (i == nkb - 1))
+                    tc_commit(acc_full + (SPLIT3 ? ((i / kChunk) & 1) : 0));      // accumulation complete
             }
-            tc_commit(accum_bar);                     // accumulator complete
+        }
+    } else if (SPLIT3 && warp < 6) {
+        // ===== warps 2-5 (3xTF32): split every landed stage into hi/lo tiles =====
+        const int t = threadIdx.x - 64;               // 0..127
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kStages;
+            const uint32_t ph = (i / kStages) & 1;
+            mbar_wait(full_bar + s, ph);
+            // The tensor core truncates its fp32 operands to TF32 by itself (measured: scripts/tf32_round_probe.py), so the
+            // landed tile already serves as `hi`; only lo = x - trunc(x) is written, elementwise at identical offsets so the
+            // swizzled layout is preserved.
+            const float4* hi4 = (const float4*)a_hi(s);       // A and B tiles are contiguous: [A_hi | B_hi | A_lo | B_lo]
+            float4* lo4 = (float4*)a_lo(s);
+            constexpr int kVec = (S::kABytes + S::kBBytes) / 16;
+#pragma unroll 8
+            for (int v = t; v < kVec; v += 128) {
+                const float4 x = hi4[v];
+                float4 l;
+                l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                lo4[v] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(split_bar + s);
         }
     } else {
-        // ===== warps 2-5: operand splitter (3xTF32) during the main loop, then epilogue =====
-        const int t = threadIdx.x - 64;               // 0..127
-        if (SPLIT3) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % kStages;
-                const uint32_t ph = (i / kStages) & 1;
-                mbar_wait(full_bar + s, ph);
-                // elementwise on identical offsets, so the swizzled layout is preserved:
-                //   hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi
-                float4* hi4 = (float4*)a_hi(s);       // A and B tiles are contiguous: [A_hi | B_hi | A_lo | B_lo]
-                float4* lo4 = (float4*)a_lo(s);
-                constexpr int kVec = (S::kABytes + S::kBBytes) / 16;
-#pragma unroll 4
-                for (int v = t; v < kVec; v += 128) {
-                    float4 x = hi4[v], h, l;
-                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-                    hi4[v] = h;
-                    lo4[v] = l;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(split_bar + s);
-            }
-        }
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        // ===== epilogue warps: accumulator -> fp32 registers -> this CTA's shared memory =====
+        // Row pitch BN + 4 floats keeps the per-row 128-bit stores of a quarter-warp on distinct banks.
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        const int gm = m0 + row;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool vec_ok = (p.n % 4 == 0);
-        if (p.splits == 1) {
+        if (SPLIT3) {
+            float acc[BN];
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                if (gm < p.m) {
-                    const size_t rowoff = (size_t)gm * p.n;
-                    if (vec_ok && n0 + c0 + 16 <= p.n) {
+            for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
+            const int nchunks = (nkb + kChunk - 1) / kChunk;
+            for (int c = 0; c < nchunks; ++c) {
+                const int b = c & 1;
+                mbar_wait(acc_full + b, (c >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 o;
-                            const int col = n0 + c0 + j;
-                            o.x = epilogue_elem(__uint_as_float(v[j + 0]), p, rowoff + col + 0, col + 0);
-                            o.y = epilogue_elem(__uint_as_float(v[j + 1]), p, rowoff + col + 1, col + 1);
-                            o.z = epilogue_elem(__uint_as_float(v[j + 2]), p, rowoff + col + 2, col + 2);
-                            o.w = epilogue_elem(__uint_as_float(v[j + 3]), p, rowoff + col + 3, col + 3);
-                            *(float4*)(p.c + rowoff + col) = o;
-                        }
-                    } else {
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + b * BN + c0, v);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int col = n0 + c0 + j;
-                            if (col < p.n) p.c[rowoff + col] = epilogue_elem(__uint_as_float(v[j]), p, rowoff + col, col);
-                        }
-                    }
+                    for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);      // round-to-nearest fp32
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + b);
             }
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 4)
+                *(float4*)(stage + row * kPitch + c0) = make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]);
         } else {
-            // split-K: park the raw accumulator tile, the last CTA of this tile folds all splits in order
-            const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-            float* mine = p.partial + ((size_t)tile * p.splits + blockIdx.z) * (BM * BN) + (size_t)row * BN;
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
-                    *(float4*)(mine + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                                            __uint_as_float(v[j + 3]));
+                    *(float4*)(stage + row * kPitch + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");             // the 4 epilogue warps only
-            if (t == 0) {
-                int prev = atomicAdd(p.counters + tile, 1);
-                s_is_last = (prev == p.splits - 1);
-                if (s_is_last) p.counters[tile] = 0;                     // ready for the next launch / graph replay
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_is_last) {
-                __threadfence();
-                if (gm < p.m) {
-                    const float* base = p.partial + (size_t)tile * p.splits * (BM * BN) + (size_t)row * BN;
-                    const size_t rowoff = (size_t)gm * p.n;
-                    for (int c0 = 0; c0 < BN; c0 += 4) {
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int z = 0; z < p.splits; ++z) {
-                            float4 x = __ldcg((const float4*)(base + (size_t)z * (BM * BN) + c0));
-                            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-                        }
-                        const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+            tc_fence_before();
+        }
+    }
+    // make the tiles visible (cluster-wide when K is split)
+    __syncwarp();
+    if (threadIdx.x == kEpiWarp0 * 32) DBG_T(4);
+    if (p.splits > 1) cluster_sync_all(); else __syncthreads();
+    if (threadIdx.x == kEpiWarp0 * 32) DBG_T(5);
+    {
+        // CTA z of the cluster owns rows [z*BM/S, (z+1)*BM/S) of the tile: fold the S partial tiles in split order
+        // through distributed shared memory, apply the epilogue, store coalesced.  Every warp of the CTA takes part.
+        constexpr int kT = SPLIT3 ? 320 : 192;
+        const int t = threadIdx.x;
+        const int S_ = p.splits;
+        const int rows_per = BM / S_;
+        const int r_begin = (int)blockIdx.z * rows_per;
+        constexpr int kVecPerRow = BN / 4;
+        const uint32_t stage_addr = smem_u32(smem);
+        const bool vec_ok = (p.n % 4 == 0);
+        const int total_vec = rows_per * kVecPerRow;
+        constexpr int kU = 4;                         // independent output vectors in flight per thread
+        for (int base = t; base < total_vec; base += kT * kU) {
+            float4 acc[kU];
+            uint32_t off[kU];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int col = n0 + c0 + j;
-                            if (col < p.n) p.c[rowoff + col] = epilogue_elem(a[j], p, rowoff + col, col);
-                        }
+            for (int u = 0; u < kU; ++u) {
+                const int idx = base + u * kT;
+                const int r = r_begin + idx / kVecPerRow, c4 = (idx % kVecPerRow) * 4;
+                off[u] = (uint32_t)(r * kPitch + c4) * 4;
+                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (S_ == 1) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (base + u * kT < total_vec) acc[u] = *(const float4*)(smem + off[u]);
+            } else {
+                // all loads of a group of two peers (x 4 vectors) are issued before the first add (DSMEM latency ~500 cycles);
+                // the adds run in split order 0, 1, 2, ... so the result does not depend on timing
+                for (int z0 = 0; z0 < S_; z0 += 2) {
+                    float4 x[2][kU];
+#pragma unroll
+                    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+                        for (int u = 0; u < kU; ++u)
+                            if (z0 + dz < S_ && base + u * kT < total_vec)
+                                x[dz][u] = ld_cluster_f4(map_to_cta(stage_addr + off[u], (uint32_t)(z0 + dz)));
+#pragma unroll
+                    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+                        for (int u = 0; u < kU; ++u)
+                            if (z0 + dz < S_ && base + u * kT < total_vec) {
+                                if (z0 + dz == 0) acc[u] = x[dz][u];
+                                else { acc[u].x += x[dz][u].x; acc[u].y += x[dz][u].y; acc[u].z += x[dz][u].z; acc[u].w += x[dz][u].w; }
+                            }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int idx = base + u * kT;
+                if (idx >= total_vec) continue;
+                const int r = r_begin + idx / kVecPerRow, c4 = (idx % kVecPerRow) * 4;
+                const int gm = m0 + r, col = n0 + c4;
+                if (gm < p.m && col < p.n) {
+                    const size_t rowoff = (size_t)gm * p.n;
+                    if (vec_ok && col + 4 <= p.n) {
+                        float4 o;
+                        o.x = epilogue_elem(acc[u].x, p, rowoff + col + 0, col + 0);
+                        o.y = epilogue_elem(acc[u].y, p, rowoff + col + 1, col + 1);
+                        o.z = epilogue_elem(acc[u].z, p, rowoff + col + 2, col + 2);
+                        o.w = epilogue_elem(acc[u].w, p, rowoff + col + 3, col + 3);
+                        *(float4*)(p.c + rowoff + col) = o;
+                    } else {
+                        const float a4[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < p.n) p.c[rowoff + col + j] = epilogue_elem(a4[j], p, rowoff + col + j, col + j);
                     }
                 }
             }
         }
-        tc_fence_before();
     }
+    // nobody leaves while a peer may still read its tile
+    __syncwarp();
+    if (threadIdx.x == kEpiWarp0 * 32) DBG_T(6);
+    if (p.splits > 1) cluster_sync_all();
     __syncthreads();
+    if (threadIdx.x == 0) DBG_T(7);
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -370,7 +469,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct TcState {
     EncodeTiledFn encode = nullptr;
-    int* counters = nullptr;
     bool attr_set[4][2][2][2] = {};
 };
 
@@ -410,7 +508,19 @@ int launch(tp_ctx* ctx, TcState* st, const CUtensorMap& ma, const CUtensorMap& m
         TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         st->attr_set[bi][A_MN][B_MN][SPLIT3] = true;
     }
-    kern<<<grid, kThreads, smem, ctx->stream>>>(ma, mb, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(SPLIT3 ? 320 : 192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;      // the K-splits of one output tile form a cluster
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = grid.z;
+    cfg.attrs = attr;
+    cfg.numAttrs = grid.z > 1 ? 1 : 0;
+    TP_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
     TP_LAUNCH_OK(ctx);
     return TP_OK;
 }
@@ -449,27 +559,27 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
     if (!st) {
         st = new TcState();
         st->encode = enc;
-        if (ctx->capturing) { delete st; return TP_ERR_UNSUPPORTED; }
-        TP_CUDA(cudaMalloc(&st->counters, kMaxTiles * sizeof(int)));
-        TP_CUDA(cudaMemsetAsync(st->counters, 0, kMaxTiles * sizeof(int), ctx->stream));
         ctx->tc_state = st;
     }
     const bool b_mn = tb == 0;
-    int bn = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : 128;
-    if (b_mn && bn < 32) bn = 32;
-    const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + bn - 1) / bn;
-    const long tiles = (long)tiles_m * tiles_n;
     const int kblocks = (k + BK - 1) / BK;
-    int splits = 1;
-    if (tiles < ctx->sm_count && kblocks >= 4) {
-        splits = (int)(ctx->sm_count / tiles);
-        if (splits > kblocks / 2) splits = kblocks / 2;       // at least two k-blocks per CTA
-        if (splits > 64) splits = 64;
-        if (splits < 1) splits = 1;
+    const int tiles_m = (m + BM - 1) / BM;
+    // Tile width and K-split: the widest tile that still puts ~100 CTAs on the 148 SMs, splitting K over a
+    // cluster of up to 8 CTAs (each with at least two k-blocks) when the output alone has too few tiles.
+    const int bn_min = b_mn ? 32 : 16;
+    int bn_max = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : 128;
+    if (bn_max < bn_min) bn_max = bn_min;
+    int bn = bn_max, splits = 1;
+    for (int cand = bn_max; cand >= bn_min; cand >>= 1) {
+        const long t = (long)tiles_m * ((n + cand - 1) / cand);
+        int sp = 1;
+        while (sp < 8 && t * sp * 2 <= ctx->sm_count && kblocks / (sp * 2) >= 2) sp *= 2;
+        bn = cand;
+        splits = sp;
+        if (t * sp >= 96) break;
     }
-    int kps = (kblocks + splits - 1) / splits;
-    splits = (kblocks + kps - 1) / kps;
-    if (tiles > kMaxTiles || tiles_m > 65535 || splits > 65535) return TP_ERR_UNSUPPORTED;
+    const int tiles_n = (n + bn - 1) / bn;
+    if (tiles_m > 65535) return TP_ERR_UNSUPPORTED;
 
     CUtensorMap ma, mb;
     if (!make_map(enc, &ma, a, a_rows, a_cols, ta ? 32 : BM, ta != 0)) return TP_ERR_UNSUPPORTED;
@@ -477,17 +587,10 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
 
     GemmParams p;
     p.m = m; p.n = n; p.k = k;
-    p.kblocks_per_split = kps; p.splits = splits;
+    p.splits = splits;
     p.alpha = alpha; p.beta = beta;
     p.c = c;
-    p.partial = nullptr;
-    p.counters = st->counters;
     p.ep = EpiArgs{ep.bias, ep.relu_mask, ep.relu};
-    if (splits > 1) {
-        int rc = ensure_scratch(ctx, (size_t)tiles * splits * BM * bn * sizeof(float));
-        if (rc) return rc;
-        p.partial = ctx->scratch;
-    }
     dim3 grid(tiles_n, tiles_m, splits);
     const bool split3 = mode == 1;
 #define TP_BN(BNV)                                                                                          \
@@ -502,10 +605,17 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
 #undef TP_BN
 }
 
+}  // namespace tp
+
+extern "C" int tpdbg_gemm_times(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_dbg_t, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
+
+namespace tp {
+
 void gemm_tc_destroy(tp_ctx* ctx) {
     TcState* st = (TcState*)ctx->tc_state;
     if (!st) return;
-    if (st->counters) cudaFree(st->counters);
     delete st;
     ctx->tc_state = nullptr;
 }

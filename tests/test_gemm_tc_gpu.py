@@ -94,3 +94,16 @@ def test_linear_epilogues_on_tensor_path(ctx, batch, fin, fout):
     assert rel_err(gx.download(), gz.astype(np.float64) @ w.astype(np.float64)) < 5e-6
     assert rel_err(gw.download(), gz.astype(np.float64).T @ x.astype(np.float64)) < 5e-6
     assert rel_err(gb.download(), gz.sum(axis=0, dtype=np.float64)) < 5e-6
+
+
+@pytest.mark.parametrize("m,n,k,ta,tb", [(512, 128, 784, 0, 1), (128, 784, 512, 1, 0), (288, 64, 12544, 1, 0), (2560, 1024, 8192, 0, 0)])
+def test_3xtf32_has_no_truncation_bias_on_nonnegative_data(ctx, m, n, k, ta, tb):
+    """MNIST pixels and post-ReLU activations are non-negative.  The tensor core's own accumulator truncates, which would
+    bias a long same-signed sum by ~K/3 * 2^-24; the 3xTF32 mode drains the accumulator every 128 elements of K."""
+    rng = np.random.default_rng(k)
+    A = rng.random((m, k)).astype(F32)
+    B = rng.random((k, n)).astype(F32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    got = run(ctx, 1, ta, tb, m, n, k, A, B).astype(np.float64)
+    assert rel_err(got, ref) < 5e-6
+    assert abs(np.mean(got - ref)) / np.max(np.abs(ref)) < 4e-6      # bounded by the 128-element chunk: ~128/3 * 2^-24
