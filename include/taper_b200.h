@@ -173,6 +173,10 @@ int tp_softmax_fwd(tp_ctx*, const tp_buf* x, tp_buf* p, int rows, int cols);    
  * A target outside [0, cols) sets the context's sticky device error flag (reference asserts, :161). */
 int tp_softmax_xent_fwd(tp_ctx*, const tp_buf* logits, const tp_buf* targets, tp_buf* logp, tp_buf* loss,
                         int rows, int cols);
+/* the same plus accuracy's correct count (src/loss.rs:271-290; correct may be NULL) in ONE launch: the head of a training
+ * step (src/train.rs:112-115).  Block partials are folded in block order by the last block to finish (deterministic). */
+int tp_softmax_xent_acc_fwd(tp_ctx*, const tp_buf* logits, const tp_buf* targets, tp_buf* logp, tp_buf* loss, tp_buf* correct,
+                            int rows, int cols);
 /* glogits (+)= (exp(logp) - onehot(t)) * gloss[0]/B                               src/loss.rs:174-191 */
 int tp_softmax_xent_bwd(tp_ctx*, const tp_buf* logp, const tp_buf* targets, const tp_buf* gloss,
                         tp_buf* glogits, int rows, int cols, int accumulate);

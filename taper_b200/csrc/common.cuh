@@ -14,6 +14,11 @@
 
 namespace tp {
 
+constexpr int kNumCounters = 1024;
+constexpr int kCounterXent = 0;      // fused softmax-xent fold
+constexpr int kCounterColsum = 16;   // [16, 528): one per 32-column block of tp_colsum
+constexpr int kCounterGemm = 528;    // [528, 1024): one per output tile of the split-K CUDA-core GEMM
+
 void set_error(const char* fmt, ...);
 
 struct Allocator {
@@ -44,6 +49,7 @@ struct tp_ctx {
     uint64_t launches = 0;
     int gemm_mode = 1;               // 0 exact fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
     int* dev_error = nullptr;        // sticky device-side error flag
+    int* dev_counters = nullptr;     // kNumCounters zero-initialised "last block done" tickets (each user resets its own)
     void* pinned = nullptr;          // staging ring for pageable uploads
     size_t pinned_bytes = 0;
     cudaEvent_t pinned_ev = nullptr;

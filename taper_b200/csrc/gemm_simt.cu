@@ -26,7 +26,7 @@ template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(int m, int n, int k, float alpha, const float* __restrict__ A, long ars, long acs,
                  const float* __restrict__ B, long brs, long bcs, float beta, float* __restrict__ C,
-                 EpiArgs ep, float* __restrict__ partial, int k_per_split) {
+                 EpiArgs ep, float* __restrict__ partial, int k_per_split, int* __restrict__ tickets) {
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int PAD = 4;
     __shared__ __align__(16) float As[BK][BM + PAD];
@@ -96,6 +96,39 @@ gemm_simt_kernel(int m, int n, int k, float alpha, const float* __restrict__ A, 
             }
         }
     }
+    if (partial && tickets) {
+        // split-K in one launch: the last CTA of this output tile folds the partial tiles in split order (deterministic)
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int* tk = tickets + blockIdx.y * gridDim.x + blockIdx.x;
+            int prev = atomicAdd(tk, 1);
+            s_last = (prev == (int)gridDim.z - 1);
+            if (s_last) *tk = 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const size_t mn = (size_t)m * n;
+#pragma unroll
+            for (int a = 0; a < TM; ++a) {
+                int gi = i0 + ty * TM + a;
+                if (gi >= m) continue;
+#pragma unroll
+                for (int b = 0; b < TN; ++b) {
+                    int gj = j0 + tx * TN + b;
+                    if (gj >= n) continue;
+                    size_t idx = (size_t)gi * n + gj;
+                    float sum = 0.0f;
+                    for (int z = 0; z < (int)gridDim.z; ++z) sum += __ldcg(partial + (size_t)z * mn + idx);
+                    float v = alpha * sum;
+                    if (beta != 0.0f) v += beta * C[idx];
+                    C[idx] = apply_epilogue(v, ep, idx, gj);
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -118,11 +151,11 @@ int launch(tp_ctx* ctx, int m, int n, int k, float alpha, const float* A, long a
     int gx = (n + BN - 1) / BN, gy = (m + BM - 1) / BM;
     long tiles = (long)gx * gy;
     int splits = 1;
-    if (tiles < ctx->sm_count && k >= 256) {
+    if (tiles < ctx->sm_count && k >= 64) {
         splits = (int)((2L * ctx->sm_count + tiles - 1) / tiles);
-        int max_splits = k / 128;
+        int max_splits = k / 32;                         // at least two BK steps per CTA
         if (splits > max_splits) splits = max_splits;
-        if (splits > 32) splits = 32;
+        if (splits > 64) splits = 64;
         if (splits < 1) splits = 1;
     }
     int kps = ((k + splits - 1) / splits + BK - 1) / BK * BK;
@@ -130,15 +163,17 @@ int launch(tp_ctx* ctx, int m, int n, int k, float alpha, const float* A, long a
     splits = (k + kps - 1) / kps;
     if (splits < 1) splits = 1;
     float* partial = nullptr;
+    int* tickets = nullptr;
     if (splits > 1) {
         int rc = tp::ensure_scratch(ctx, (size_t)splits * m * n * sizeof(float));
         if (rc) return rc;
         partial = ctx->scratch;
+        if (tiles <= tp::kNumCounters - tp::kCounterGemm) tickets = ctx->dev_counters + tp::kCounterGemm;
     }
     gemm_simt_kernel<BM, BN, BK, TM, TN><<<dim3(gx, gy, splits), NT, 0, ctx->stream>>>(
-        m, n, k, alpha, A, ars, acs, B, brs, bcs, beta, C, ep, partial, kps);
+        m, n, k, alpha, A, ars, acs, B, brs, bcs, beta, C, ep, partial, kps, tickets);
     TP_LAUNCH_OK(ctx);
-    if (splits > 1) {
+    if (splits > 1 && !tickets) {
         size_t mn = (size_t)m * n;
         splitk_fold_kernel<<<tp::grid_for(ctx, mn, 256), 256, 0, ctx->stream>>>(partial, C, mn, n, splits, alpha, beta, ep);
         TP_LAUNCH_OK(ctx);

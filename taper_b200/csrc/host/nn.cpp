@@ -136,6 +136,10 @@ Tensor softmax(const Tensor& x, int dim) {
 }
 
 Tensor cross_entropy_loss_into(const Tensor& logits, const Tensor& targets, const Tensor& out) {
+    return cross_entropy_with_accuracy_into(logits, targets, out, nullptr);
+}
+
+Tensor cross_entropy_with_accuracy_into(const Tensor& logits, const Tensor& targets, const Tensor& out, const Tensor* correct_out) {
     const Shape& ts = targets.shape();
     if (!(ts.size() == 1 || (ts.size() == 2 && ts[1] == 1))) panic("targets must be [B] or [B,1]");     // src/loss.rs:137-141
     if (logits.shape().size() != 2 || logits.shape()[0] != ts[0]) panic("logits must be [B,C] with the targets' batch size");
@@ -143,7 +147,11 @@ Tensor cross_entropy_loss_into(const Tensor& logits, const Tensor& targets, cons
     Tensor logp = Tensor::empty(logits.shape());
     // fused log_softmax + NLL mean (src/loss.rs:152-165); the six log_softmax nodes the reference records are
     // dead in backward, so a single node carrying the direct gradient is recorded instead.
-    check(tp_softmax_xent_fwd(ctx(), logits.buf(), targets.buf(), logp.buf(), out.buf(), rows, cols));
+    if (rows > 0)
+        check(tp_softmax_xent_acc_fwd(ctx(), logits.buf(), targets.buf(), logp.buf(), out.buf(), correct_out ? correct_out->buf() : nullptr,
+                                      rows, cols));
+    else
+        check(tp_softmax_xent_fwd(ctx(), logits.buf(), targets.buf(), logp.buf(), out.buf(), rows, cols));
     Tensor o = out;
     if (logits.needs_grad()) {
         o.set_requires_grad(true);

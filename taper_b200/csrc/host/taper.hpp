@@ -220,6 +220,8 @@ Tensor accuracy_count(const Tensor& predictions, const Tensor& targets);
 // variants writing into a caller-provided [1] tensor (the trainer's result slot)
 Tensor cross_entropy_loss_into(const Tensor& logits, const Tensor& targets, const Tensor& out);
 void accuracy_count_into(const Tensor& predictions, const Tensor& targets, const Tensor& out);
+// cross_entropy_loss + accuracy's correct count in one launch (the head of a training step, src/train.rs:112-115)
+Tensor cross_entropy_with_accuracy_into(const Tensor& logits, const Tensor& targets, const Tensor& out, const Tensor* correct_out);
 }  // namespace loss
 
 // ---- optim  (src/optim.rs) ----------------------------------------------------------------------------------

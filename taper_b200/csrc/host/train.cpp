@@ -204,9 +204,16 @@ void step_body(Trainer& tr, const Tensor& x, const Tensor& y, const Tensor& loss
     // the loss tensor is a fresh handle on the result slot each step: its grad state must start as None
     loss_out.impl()->has_grad = false;
     loss_out.impl()->tape_node = 0;
-    Tensor loss = loss::cross_entropy_loss_into(logits, y, loss_out);            // :112
-    loss::accuracy_count_into(logits, y, correct_out);                           // :115
-    loss.backward();                                                             // :121
+    Tensor loss = loss::cross_entropy_with_accuracy_into(logits, y, loss_out, &correct_out);      // :112-115, one launch
+    // loss.backward() (:121) = grad := ones, then the tape walk.  The result slot's gradient buffer holds 1.0 from its
+    // first allocation on and nothing ever writes it again, so the per-step fill is skipped.
+    TensorImpl& li = *loss.impl();
+    if (!li.grad) {
+        int acc;
+        check(tp_buf_fill(ctx(), li.grad_for_write(&acc), 1.0f, 1));
+    }
+    li.has_grad = true;
+    if (li.tape_node != 0) taper::backward(li.tape_node - 1);
     if (world > 1) {                                                             // sum of per-rank mean gradients
         auto a = tr.optimizer->arena();
         dist::allreduce_sum(optim::arena_grad_buf(a), optim::arena_total(a));

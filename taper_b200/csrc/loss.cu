@@ -71,6 +71,78 @@ softmax_rows_kernel(const float* __restrict__ x, const float* __restrict__ targe
     }
 }
 
+// Fused training-step head: log_softmax + NLL mean (src/loss.rs:152-165) + accuracy count (src/loss.rs:271-290) in ONE
+// launch.  One warp per row; per-block partial sums are parked, the last block to finish folds them in block order
+// (deterministic) and writes loss[0] = sum / rows and correct[0].
+__global__ void __launch_bounds__(kThreads)
+xent_acc_fused_kernel(const float* __restrict__ x, const float* __restrict__ targets, float* __restrict__ logp,
+                      float* __restrict__ partial, float* __restrict__ loss, float* __restrict__ correct, int* __restrict__ err,
+                      int* __restrict__ ticket, int rows, int cols) {
+    __shared__ float sm_nll[kWarpsPerBlock], sm_hit[kWarpsPerBlock];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.x * kWarpsPerBlock + wid;
+    float nll = 0.0f, hit = 0.0f;
+    if (row < rows) {
+        const float* xr = x + (size_t)row * cols;
+        float m = -INFINITY;
+        int bi = INT_MAX;
+        for (int c = lane; c < cols; c += 32) {           // row max + first-index argmax, strict '>' (src/tensor.rs:1062)
+            float v = __ldg(xr + c);
+            if (v > m) { m = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, m, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > m || (ov == m && oi < bi)) { m = ov; bi = oi; }
+        }
+        float s = 0.0f;
+        for (int c = lane; c < cols; c += 32) s += expf(__ldg(xr + c) - m);
+        s = warp_sum(s);
+        const float ls = logf(s);
+        float* o = logp + (size_t)row * cols;
+        for (int c = lane; c < cols; c += 32) o[c] = (__ldg(xr + c) - m) - ls;
+        if (lane == 0) {
+            const float t = __ldg(targets + row);
+            unsigned int cls = class_of(t);
+            if (cls >= (unsigned int)cols) { atomicExch(err, 1); cls = cols - 1; }
+            nll = -((__ldg(xr + cls) - m) - ls);
+            const float idx = (bi == INT_MAX) ? 0.0f : (float)bi;
+            if (fabsf(idx - t) < 1e-6f) hit = 1.0f;                              // src/loss.rs:284
+        }
+    }
+    if (lane == 0) { sm_nll[wid] = nll; sm_hit[wid] = hit; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.0f, h = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kWarpsPerBlock; ++j) { a += sm_nll[j]; h += sm_hit[j]; }      // rows ascending inside the block
+        partial[2 * blockIdx.x] = a;
+        partial[2 * blockIdx.x + 1] = h;
+        __threadfence();
+        int prev = atomicAdd(ticket, 1);
+        s_last = (prev == (int)gridDim.x - 1);
+        if (s_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float a = 0.0f, h = 0.0f;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) { a += __ldcg(partial + 2 * i); h += __ldcg(partial + 2 * i + 1); }
+        a = warp_sum(a); h = warp_sum(h);
+        if (lane == 0) { sm_nll[wid] = a; sm_hit[wid] = h; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float sa = 0.0f, sh = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kWarpsPerBlock; ++j) { sa += sm_nll[j]; sh += sm_hit[j]; }
+            loss[0] = sa / (float)rows;                                          // acc / b as f32 (src/loss.rs:164)
+            if (correct) correct[0] = sh;
+        }
+    }
+}
+
 // out[0] = (sum_j partial[j]) / divisor, j ascending (single thread block, fixed tree => deterministic)
 __global__ void __launch_bounds__(kThreads)
 fold_scalar_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, float divisor) {
@@ -176,6 +248,22 @@ int tp_softmax_fwd(tp_ctx* ctx, const tp_buf* x, tp_buf* p, int rows, int cols) 
 int tp_softmax_xent_fwd(tp_ctx* ctx, const tp_buf* logits, const tp_buf* targets, tp_buf* logp, tp_buf* loss, int rows, int cols) {
     TP_CHECK_ARG(targets && loss, "tp_softmax_xent_fwd: targets and loss are required");
     return softmax_common(ctx, logits, targets, logp, loss, rows, cols, 0, "tp_softmax_xent_fwd");
+}
+
+int tp_softmax_xent_acc_fwd(tp_ctx* ctx, const tp_buf* logits, const tp_buf* targets, tp_buf* logp, tp_buf* loss, tp_buf* correct,
+                            int rows, int cols) {
+    TP_CHECK_ARG(ctx && rows > 0 && cols > 0, "tp_softmax_xent_acc_fwd: bad dims %d x %d", rows, cols);
+    size_t total = (size_t)rows * cols;
+    TP_NEED(logits, total, "logits"); TP_NEED(targets, rows, "targets"); TP_NEED(logp, total, "logp"); TP_NEED(loss, 1, "loss");
+    if (correct) TP_NEED(correct, 1, "correct");
+    int blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int rc = tp::ensure_scratch(ctx, (size_t)blocks * 2 * sizeof(float));
+    if (rc) return rc;
+    xent_acc_fused_kernel<<<blocks, kThreads, 0, ctx->stream>>>(logits->ptr, targets->ptr, logp->ptr, ctx->scratch, loss->ptr,
+                                                               correct ? correct->ptr : nullptr, ctx->dev_error,
+                                                               ctx->dev_counters + tp::kCounterXent, rows, cols);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
 }
 
 int tp_softmax_xent_bwd(tp_ctx* ctx, const tp_buf* logp, const tp_buf* targets, const tp_buf* gloss, tp_buf* glogits,

@@ -79,6 +79,45 @@ colsum_stage1(const float* __restrict__ g, float* __restrict__ partial, int rows
     }
 }
 
+// single-launch column sums: every (column block, row split) CTA parks its partial row, takes a ticket, and the last
+// CTA of a column block folds the splits in order (deterministic) — no second kernel, no atomics on the data
+__global__ void __launch_bounds__(kThreads)
+colsum_fused_kernel(const float* __restrict__ g, float* __restrict__ partial, float* __restrict__ out, int* __restrict__ tickets,
+                    int rows, int cols, int rows_per_split, float scale, int accumulate) {
+    __shared__ float sm[8][33];
+    __shared__ int s_last;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_split;
+    const int r1 = min(rows, r0 + rows_per_split);
+    float acc = 0.0f;
+    if (col < cols)
+        for (int r = r0 + ty; r < r1; r += 8) acc += __ldg(g + (size_t)r * cols + col);
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += sm[j][tx];
+        if (col < cols) partial[(size_t)blockIdx.y * cols + col] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int prev = atomicAdd(tickets + blockIdx.x, 1);
+        s_last = (prev == (int)gridDim.y - 1);
+        if (s_last) tickets[blockIdx.x] = 0;          // ready for the next launch / graph replay
+    }
+    __syncthreads();
+    if (s_last && ty == 0 && col < cols) {
+        __threadfence();
+        float s = 0.0f;
+        for (int j = 0; j < (int)gridDim.y; ++j) s += __ldcg(partial + (size_t)j * cols + col);
+        s *= scale;
+        out[col] = accumulate ? out[col] + s : s;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 fold_partials(const float* __restrict__ partial, float* __restrict__ out, int n, int splits, float scale, int accumulate) {
     int i = blockIdx.x * kThreads + threadIdx.x;
@@ -300,8 +339,16 @@ int tp_colsum(tp_ctx* ctx, const tp_buf* g, tp_buf* out, int rows, int cols, flo
     int splits = pick_splits(ctx, bx, rows, 64);
     int rps = (rows + splits - 1) / splits;
     if (rps < 1) rps = 1;
+    splits = rows > 0 ? (rows + rps - 1) / rps : 1;
     int rc = tp::ensure_scratch(ctx, (size_t)splits * cols * sizeof(float));
     if (rc) return rc;
+    if (bx <= tp::kCounterGemm - tp::kCounterColsum) {
+        colsum_fused_kernel<<<dim3(bx, splits), kThreads, 0, ctx->stream>>>(g->ptr, ctx->scratch, out->ptr,
+                                                                           ctx->dev_counters + tp::kCounterColsum, rows, cols, rps,
+                                                                           scale, accumulate);
+        TP_LAUNCH_OK(ctx);
+        return TP_OK;
+    }
     colsum_stage1<<<dim3(bx, splits), kThreads, 0, ctx->stream>>>(g->ptr, ctx->scratch, rows, cols, rps);
     TP_LAUNCH_OK(ctx);
     fold_partials<<<(cols + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->scratch, out->ptr, cols, splits, scale, accumulate);

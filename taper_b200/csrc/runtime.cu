@@ -161,6 +161,8 @@ int tp_ctx_create(int device, tp_ctx** out) {
     TP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TP_CUDA(cudaMalloc(&ctx->dev_error, sizeof(int)));
     TP_CUDA(cudaMemsetAsync(ctx->dev_error, 0, sizeof(int), ctx->stream));
+    TP_CUDA(cudaMalloc(&ctx->dev_counters, tp::kNumCounters * sizeof(int)));
+    TP_CUDA(cudaMemsetAsync(ctx->dev_counters, 0, tp::kNumCounters * sizeof(int), ctx->stream));
     ctx->pinned_bytes = 8u << 20;
     TP_CUDA(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
     TP_CUDA(cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming));
@@ -178,6 +180,7 @@ int tp_ctx_destroy(tp_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (float* q : ctx->retired_scratch) cudaFree(q);
     if (ctx->dev_error) cudaFree(ctx->dev_error);
+    if (ctx->dev_counters) cudaFree(ctx->dev_counters);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
     cudaStreamDestroy(ctx->stream);

@@ -352,6 +352,15 @@ def test_softmax_xent_vs_oracle(ctx, rows, cols):
     ctx.call("softmax_xent_fwd", dZ, dT, LP, L, rows, cols)
     np.testing.assert_allclose(LP.download(), logp_ref, rtol=1e-5, atol=2e-6)
     close(L.download(), loss.data(), 1e-5)
+    # fused head of a training step: the same loss / logp plus accuracy's correct count, one launch
+    LP2, L2, Cn = ctx.alloc(rows * cols), ctx.alloc(1), ctx.alloc(1)
+    for _ in range(2):                          # twice: the "last block" ticket must reset itself
+        ctx.call("softmax_xent_acc_fwd", dZ, dT, LP2, L2, Cn, rows, cols)
+        exact(LP2.download(), LP.download())
+        close(L2.download(), loss.data(), 1e-5)
+        assert Cn.download()[0] == round(float(R.accuracy(R.Tensor.new(z, z.shape), Tt)) * rows)
+    ctx.call("softmax_xent_acc_fwd", dZ, dT, LP2, L2, None, rows, cols)
+    close(L2.download(), loss.data(), 1e-5)
     one = ctx.upload(np.ones(1, F32))
     G = ctx.alloc(rows * cols)
     ctx.call("softmax_xent_bwd", LP, dT, one, G, rows, cols, 0)
