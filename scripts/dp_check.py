@@ -1,0 +1,65 @@
+"""Run under torchrun (one rank per GPU): data-parallel invariance of the CUDA path.
+W ranks x (B/W) rows with the NCCL gradient allreduce must match one rank x B rows (only summation order differs)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch, torch.distributed as dist
+from taper_b200 import host
+from taper_b200.dp import shard_permutation
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+host.set_device(local)
+spec = host.MLP_784_128_10
+b, steps, n = 64, 6, 4096
+rng = np.random.default_rng(0)
+X = rng.random((n, 784)).astype(np.float32); Y = rng.integers(0, 10, n).astype(np.float32)
+perm = rng.permutation(n)
+
+model = host.Model(spec, seed=0)                  # same seed on every rank; broadcast anyway
+tr = host.Trainer(model, "adam", lr=1e-3)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    uid = torch.frombuffer(bytearray(host.nccl_unique_id()), dtype=torch.uint8).cuda()
+dist.broadcast(uid, 0)
+tr.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+tr.broadcast_params(0)
+tr.load_dataset(X, Y, shard_permutation(perm, rank, world, b))
+local_losses = []
+for s in range(steps):                            # eager, capture (with the allreduce inside the graph), replays
+    tr.step_resident(b)
+    local_losses.append(tr.fetch()[0])
+params = [model.get_param(i) for i in range(model.num_params())]
+
+# single-replica reference on the global batch, same process, no communicator
+ref_model = host.Model(spec, seed=0)
+ref_tr = host.Trainer(ref_model, "adam", lr=1e-3)
+ref_tr.load_dataset(X, Y, perm.astype(np.uint32))
+ref_losses = []
+for s in range(steps):
+    ref_tr.step_resident(b * world)
+    ref_losses.append(ref_tr.fetch()[0])
+t = torch.tensor(local_losses, dtype=torch.float64, device="cuda")
+dist.all_reduce(t)
+mean_losses = (t / world).cpu().numpy()
+ok = True
+for s in range(steps):
+    if abs(mean_losses[s] - ref_losses[s]) > 1e-4 * abs(ref_losses[s]):
+        ok = False; print(f"rank {rank}: step {s} loss {mean_losses[s]} vs {ref_losses[s]}")
+for i, p in enumerate(params):
+    r = ref_model.get_param(i)
+    err = np.max(np.abs(p - r)); scale = max(np.max(np.abs(r)), 1e-6)
+    if err > 1e-4 * scale + 0.03 * 1e-3:
+        ok = False; print(f"rank {rank}: param {i} err {err:.3e} scale {scale:.3e}")
+# replicas identical across ranks
+flat = torch.from_numpy(np.concatenate([p.reshape(-1) for p in params])).cuda()
+ref0 = flat.clone(); dist.broadcast(ref0, 0)
+if not torch.equal(flat, ref0):
+    ok = False; print(f"rank {rank}: replica diverged from rank 0")
+flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("DP_CHECK", "OK" if flag.item() == 1 else "FAILED", f"world={world} graph_replays={tr.graph_replays()}")
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)

@@ -82,10 +82,13 @@ def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=N
     opt = oracle_opt(kind, ref.parameters(), lr, wd)
     rng = np.random.default_rng(seed + 1)
     for i, (x, y) in enumerate(batches(rng, steps, batch, sample_shape, ragged)):
-        # rows whose two largest logits agree to within the 1e-4 parity tolerance may legitimately break the tie either way
+        # rows whose two largest logits agree to within the parity tolerance may legitimately break the tie either way
+        # (after the first Adam step the parameters themselves are only comparable to a few % of one update, see
+        # close_after_adam, so the margin is taken 20x wider there)
         lg = ref.forward(R.Tensor.new(x, x.shape)).numpy().astype(np.float64)
         top2 = np.sort(lg, axis=1)[:, -2:]
-        near_ties = int(np.sum(top2[:, 1] - top2[:, 0] <= 1e-4 * np.max(np.abs(lg))))
+        margin = (1e-4 if (kind == "sgd" or i == 0) else 2e-3) * np.max(np.abs(lg))
+        near_ties = int(np.sum(top2[:, 1] - top2[:, 0] <= margin))
         loss_ref, acc_ref = R.train_step(ref, opt, R.Tensor.new(x, x.shape), R.Tensor.new(y, y.shape))
         loss, correct = tr.step(x, y)
         assert abs(loss - loss_ref) <= tol * max(abs(loss_ref), 1e-6), f"step {i}: loss {loss} vs {loss_ref}"
