@@ -138,4 +138,10 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
             const float* b, float beta, float* c, const Epilogue& ep, int mode);
 void gemm_tc_destroy(tp_ctx* ctx);
 
+// Linear layers with out_features <= 16 (classifier heads), see linear_skinny.cu
+bool linear_skinny_ok(int batch, int in_f, int out_f);
+int linear_skinny_fwd(tp_ctx* ctx, const float* x, const float* w, const float* b, float* y, int batch, int in_f, int out_f, int relu);
+int linear_skinny_bwd(tp_ctx* ctx, const float* x, const float* w, const float* dy, const float* mask_y, float* dx, float* dw,
+                      float* db, int batch, int in_f, int out_f, int acc_dx, int acc_dw, int acc_db);
+
 }  // namespace tp

@@ -42,6 +42,8 @@ int tp_linear_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b
     TP_NEED(x, (size_t)batch * in_features, "x"); TP_NEED(w, (size_t)out_features * in_features, "w");
     TP_NEED(y, (size_t)batch * out_features, "y");
     if (b) TP_NEED(b, out_features, "b");
+    if (tp::linear_skinny_ok(batch, in_features, out_features))
+        return tp::linear_skinny_fwd(ctx, x->ptr, w->ptr, b ? b->ptr : nullptr, y->ptr, batch, in_features, out_features, relu);
     tp::Epilogue ep;
     ep.bias = b ? b->ptr : nullptr;
     ep.relu = relu;
@@ -55,6 +57,15 @@ int tp_linear_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* d
     size_t ny = (size_t)batch * out_features;
     TP_NEED(dy, ny, "dy");
     if (relu_mask_y) TP_NEED(relu_mask_y, ny, "relu_mask_y");
+    if (tp::linear_skinny_ok(batch, in_features, out_features)) {
+        const size_t nx = (size_t)batch * in_features, nw = (size_t)out_features * in_features;
+        if (dx) { TP_NEED(dx, nx, "dx"); TP_NEED(w, nw, "w"); }
+        if (dw) { TP_NEED(dw, nw, "dw"); TP_NEED(x, nx, "x"); }
+        if (db) TP_NEED(db, out_features, "db");
+        return tp::linear_skinny_bwd(ctx, x ? x->ptr : nullptr, w ? w->ptr : nullptr, dy->ptr, relu_mask_y ? relu_mask_y->ptr : nullptr,
+                                     dx ? dx->ptr : nullptr, dw ? dw->ptr : nullptr, db ? db->ptr : nullptr, batch, in_features,
+                                     out_features, acc_dx, acc_dw, acc_db);
+    }
     const tp_buf* g = dy;
     tp_buf* tmp = nullptr;
     int rc = TP_OK;

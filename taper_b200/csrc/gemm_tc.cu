@@ -21,6 +21,8 @@
 
 #include <cuda.h>
 
+extern "C" int tpdbg_max_clusters(int bn, int cluster);
+
 namespace {
 
 constexpr int BM = 128;              // UMMA M (cta_group::1)
@@ -470,6 +472,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TcState {
     EncodeTiledFn encode = nullptr;
     bool attr_set[4][2][2][2] = {};
+    int max_clusters[4] = {148, 74, 33, 15};      // co-resident clusters of 1/2/4/8 CTAs (queried at first use)
 };
 
 EncodeTiledFn get_encode() {
@@ -559,24 +562,36 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
     if (!st) {
         st = new TcState();
         st->encode = enc;
+        st->max_clusters[0] = ctx->sm_count;
+        for (int si = 1; si < 4; ++si) {
+            int q = tpdbg_max_clusters(128, 1 << si);
+            if (q > 0) st->max_clusters[si] = q;
+        }
         ctx->tc_state = st;
     }
     const bool b_mn = tb == 0;
     const int kblocks = (k + BK - 1) / BK;
     const int tiles_m = (m + BM - 1) / BM;
-    // Tile width and K-split: the widest tile that still puts ~100 CTAs on the 148 SMs, splitting K over a
-    // cluster of up to 8 CTAs (each with at least two k-blocks) when the output alone has too few tiles.
+    // Tile width BN and K-split S (cluster size) from a small cost model, in SM cycles per CTA:
+    //   waves * (fixed + k-blocks per CTA * t_kb(BN) + cluster fold), waves = ceil(tiles / co-resident clusters of S)
+    // t_kb is shared-memory bound in both modes (operand reads of the MMAs + the lo-tile pass in 3xTF32).  A cluster that
+    // does not fit in the first wave doubles the kernel, hence the measured residency limits (148 / 74 / 33 / 15).
     const int bn_min = b_mn ? 32 : 16;
     int bn_max = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : 128;
     if (bn_max < bn_min) bn_max = bn_min;
     int bn = bn_max, splits = 1;
+    long best = -1;
     for (int cand = bn_max; cand >= bn_min; cand >>= 1) {
         const long t = (long)tiles_m * ((n + cand - 1) / cand);
-        int sp = 1;
-        while (sp < 8 && t * sp * 2 <= ctx->sm_count && kblocks / (sp * 2) >= 2) sp *= 2;
-        bn = cand;
-        splits = sp;
-        if (t * sp >= 96) break;
+        const long tkb = mode == 1 ? 640 + 5 * cand : 256 + 2 * cand;
+        for (int si = 3; si >= 0; --si) {
+            const int sp = 1 << si;
+            if (sp > 1 && kblocks < 2 * sp) continue;               // at least two k-blocks per CTA
+            const long waves = (t + st->max_clusters[si] - 1) / st->max_clusters[si];
+            const long kbpc = (kblocks + sp - 1) / sp;
+            const long cost = waves * (3000 + kbpc * tkb + (sp > 1 ? 2500 : 0));
+            if (best < 0 || cost < best) { best = cost; bn = cand; splits = sp; }
+        }
     }
     const int tiles_n = (n + bn - 1) / bn;
     if (tiles_m > 65535) return TP_ERR_UNSUPPORTED;
@@ -606,6 +621,28 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
 }
 
 }  // namespace tp
+
+// development aid: how many clusters of `cluster` CTAs of the 3xTF32 K-major kernel can be resident at once
+extern "C" int tpdbg_max_clusters(int bn, int cluster) {
+    int n = -1;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cluster;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(320);
+    cfg.gridDim = dim3(1, 1, cluster);
+#define TP_Q(BNV)                                                                                           \
+    {                                                                                                       \
+        auto k = gemm_tf32_kernel<BNV, false, false, true>;                                                 \
+        cfg.dynamicSmemBytes = Smem<BNV, true>::kTotal;                                                     \
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNV, true>::kTotal);      \
+        if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); n = -1; }     \
+    }
+    if (bn == 16) TP_Q(16) else if (bn == 32) TP_Q(32) else if (bn == 64) TP_Q(64) else TP_Q(128)
+#undef TP_Q
+    return n;
+}
 
 extern "C" int tpdbg_gemm_times(long long* out16) {
     return cudaMemcpyFromSymbol(out16, g_dbg_t, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;

@@ -256,6 +256,8 @@ struct Arena {
     void bump_versions() { for (auto& t : params) t.impl()->version++; }
 };
 
+void Optimizer::mark_parameters_updated() const { arena()->bump_versions(); }
+
 tp_buf* arena_grad_buf(const std::shared_ptr<Arena>& a) { return a->g; }
 size_t arena_total(const std::shared_ptr<Arena>& a) { return a->total; }
 tp_buf* arena_param_buf(const std::shared_ptr<Arena>& a) { return a->p; }

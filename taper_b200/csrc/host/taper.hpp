@@ -240,6 +240,8 @@ struct Optimizer {                                                   // :3-6
     virtual std::shared_ptr<Arena> arena() const = 0;
     virtual void set_grad_scale(float s) = 0;
     virtual void set_lr(float) {}
+    // a replayed CUDA graph updated the parameters without the host-side step() running: invalidate host mirrors
+    void mark_parameters_updated() const;
 };
 tp_buf* arena_grad_buf(const std::shared_ptr<Arena>& a);
 tp_buf* arena_param_buf(const std::shared_ptr<Arena>& a);

@@ -262,6 +262,7 @@ void Trainer::train_batch_async(const float* images, const float* labels, size_t
     }
     if (s.graph) {
         check(tp_graph_launch(c, s.graph));
+        optimizer->mark_parameters_updated();
         graph_replays_++;
     } else if (use_graph_ && s.eager_runs >= 1) {
         // second iteration of this shape: record it.  Every buffer the step allocates comes from a pool the
@@ -340,6 +341,7 @@ void Trainer::train_batch_resident(size_t batch) {
     };
     if (s.graph_resident) {
         check(tp_graph_launch(c, s.graph_resident));
+        optimizer->mark_parameters_updated();
         graph_replays_++;
     } else if (use_graph_ && s.eager_runs >= 1) {
         check(tp_graph_begin(c));

@@ -1,0 +1,238 @@
+// Linear layers with a skinny output (out_features <= 16: the 10-logit classifier head of every MNIST model).
+// A 128-wide tensor-core tile is pointless there (N = 10), and the three backward products are ~1 MFLOP each, so
+// launch count and latency are what matter: forward is one launch, the whole backward (dX = dY*W, dW = dY^T*X,
+// db = colsum(dY), optional ReLU mask on dY) is ONE launch with two block roles, deterministic (fixed fold order).
+// Exact fp32 FMA arithmetic on the CUDA cores.  Reference: Linear::forward (src/nn.rs:54-60) and the backward closures
+// of matmul / transpose / add_broadcast (src/ops.rs:238-294, src/tensor.rs:575-586, 680-691).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxOut = 16;
+
+// ---- forward: one warp per row, W staged in shared memory ------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int batch, int in_f, int out_f, int relu) {
+    extern __shared__ float sw[];                              // [out_f][in_f]
+    for (int i = threadIdx.x; i < out_f * in_f; i += kThreads) sw[i] = __ldg(w + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * kThreads) >> 5;
+    for (int r = warp; r < batch; r += nwarps) {
+        const float* xr = x + (size_t)r * in_f;
+        float acc[kMaxOut];
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
+        for (int k = lane; k < in_f; k += 32) {
+            const float xv = __ldg(xr + k);
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o)
+                if (o < out_f) acc[o] = fmaf(xv, sw[o * in_f + k], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+            if (o < out_f) {
+                float v = acc[o];
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                acc[o] = v;
+            }
+        }
+        if (lane < out_f) {
+            float v = 0.0f;
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o) if (o == lane) v = acc[o];
+            if (bias) v += __ldg(bias + lane);
+            if (relu) v = fmaxf(v, 0.0f);
+            y[(size_t)r * out_f + lane] = v;
+        }
+    }
+}
+
+// ---- backward: blocks [0, dx_blocks) compute dX rows, the rest compute dW/db partials over row splits ------------
+struct BwdArgs {
+    const float* x;       // [B, in]
+    const float* w;       // [out, in]
+    const float* dy;      // [B, out]
+    const float* mask_y;  // optional [B, out]: dy := dy * [y > 0]
+    float* dx;            // optional [B, in]
+    float* dw;            // optional [out, in]
+    float* db;            // optional [out]
+    float* partial;       // [col_blocks][row_splits][out + 1... ] see below
+    int* tickets;         // one per column block
+    int batch, in_f, out_f;
+    int dx_blocks, col_blocks, row_splits, rows_per_split;
+    int acc_dx, acc_dw, acc_db;
+};
+
+__device__ __forceinline__ float masked(const BwdArgs& a, int r, int o) {
+    float g = __ldg(a.dy + (size_t)r * a.out_f + o);
+    if (a.mask_y && !(__ldg(a.mask_y + (size_t)r * a.out_f + o) > 0.0f)) g = 0.0f;
+    return g;
+}
+
+__global__ void __launch_bounds__(kThreads)
+skinny_bwd_kernel(BwdArgs a) {
+    extern __shared__ float smem[];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < a.dx_blocks) {
+        // dX[r, i] (+)= sum_o dY[r, o] * W[o, i]      (N,N; src/ops.rs:254-265 composed with transpose bwd)
+        float* sw = smem;                                      // [out][in]
+        for (int i = tid; i < a.out_f * a.in_f; i += kThreads) sw[i] = __ldg(a.w + i);
+        __syncthreads();
+        const int lane = tid & 31;
+        const int warp = (blockIdx.x * kThreads + tid) >> 5;
+        const int nwarps = (a.dx_blocks * kThreads) >> 5;
+        for (int r = warp; r < a.batch; r += nwarps) {
+            float g[kMaxOut];
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o) g[o] = o < a.out_f ? masked(a, r, o) : 0.0f;
+            float* dxr = a.dx + (size_t)r * a.in_f;
+            for (int i = lane; i < a.in_f; i += 32) {
+                float v = 0.0f;
+#pragma unroll
+                for (int o = 0; o < kMaxOut; ++o)
+                    if (o < a.out_f) v = fmaf(g[o], sw[o * a.in_f + i], v);
+                dxr[i] = a.acc_dx ? dxr[i] + v : v;
+            }
+        }
+        return;
+    }
+    // dW[o, i] (+)= sum_r dY[r, o] * X[r, i] ;  db[o] (+)= sum_r dY[r, o]      (T,N; src/ops.rs:280-291, src/tensor.rs:680-691)
+    const int b = blockIdx.x - a.dx_blocks;
+    const int cb = b % a.col_blocks, rs = b / a.col_blocks;
+    const int i = cb * kThreads + tid;                         // input column owned by this thread
+    const int r0 = rs * a.rows_per_split, r1 = min(a.batch, r0 + a.rows_per_split);
+    float* sdy = smem;                                         // [rows_per_split][out]
+    for (int e = tid; e < (r1 - r0) * a.out_f; e += kThreads) sdy[e] = masked(a, r0 + e / a.out_f, e % a.out_f);
+    __syncthreads();
+    float acc[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
+    if (i < a.in_f && a.dw) {
+        for (int r = r0; r < r1; ++r) {
+            const float xv = __ldg(a.x + (size_t)r * a.in_f + i);
+            const float* g = sdy + (r - r0) * a.out_f;
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o)
+                if (o < a.out_f) acc[o] = fmaf(g[o], xv, acc[o]);
+        }
+    }
+    // park the partials: layout [cb][rs][out][kThreads] (+ a [out] tail per (cb, rs) for db, written by column block 0)
+    const size_t per = (size_t)a.out_f * kThreads + kMaxOut;
+    float* mine = a.partial + ((size_t)cb * a.row_splits + rs) * per;
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o)
+        if (o < a.out_f) mine[o * kThreads + tid] = acc[o];
+    if (cb == 0 && a.db && tid < a.out_f) {
+        float s = 0.0f;
+        for (int r = r0; r < r1; ++r) s += sdy[(r - r0) * a.out_f + tid];      // rows ascending
+        mine[(size_t)a.out_f * kThreads + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        int prev = atomicAdd(a.tickets + cb, 1);
+        s_last = (prev == a.row_splits - 1);
+        if (s_last) a.tickets[cb] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* base = a.partial + (size_t)cb * a.row_splits * per;
+    if (i < a.in_f && a.dw) {
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+            if (o < a.out_f) {
+                float s = 0.0f;
+                for (int z = 0; z < a.row_splits; ++z) s += __ldcg(base + (size_t)z * per + o * kThreads + tid);      // split order
+                float* d = a.dw + (size_t)o * a.in_f + i;
+                *d = a.acc_dw ? *d + s : s;
+            }
+        }
+    }
+    if (cb == 0 && a.db && tid < a.out_f) {
+        float s = 0.0f;
+        for (int z = 0; z < a.row_splits; ++z) s += __ldcg(base + (size_t)z * per + (size_t)a.out_f * kThreads + tid);
+        a.db[tid] = a.acc_db ? a.db[tid] + s : s;
+    }
+}
+
+}  // namespace
+
+namespace tp {
+
+bool linear_skinny_ok(int batch, int in_f, int out_f) {
+    return out_f <= kMaxOut && (size_t)out_f * in_f * sizeof(float) <= 96 * 1024 && batch > 0;
+}
+
+int linear_skinny_fwd(tp_ctx* ctx, const float* x, const float* w, const float* b, float* y, int batch, int in_f, int out_f,
+                      int relu) {
+    cudaSetDevice(ctx->device);
+    size_t smem = (size_t)out_f * in_f * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        TP_CUDA(cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        TP_CUDA(cudaFuncSetAttribute(skinny_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    int blocks = (batch * 32 + kThreads - 1) / kThreads;
+    if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
+    skinny_fwd_kernel<<<blocks, kThreads, smem, ctx->stream>>>(x, w, b, y, batch, in_f, out_f, relu);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int linear_skinny_bwd(tp_ctx* ctx, const float* x, const float* w, const float* dy, const float* mask_y, float* dx, float* dw,
+                      float* db, int batch, int in_f, int out_f, int acc_dx, int acc_dw, int acc_db) {
+    cudaSetDevice(ctx->device);
+    static bool attr = false;
+    if (!attr) {
+        TP_CUDA(cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        TP_CUDA(cudaFuncSetAttribute(skinny_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
+    }
+    BwdArgs a;
+    a.x = x; a.w = w; a.dy = dy; a.mask_y = mask_y; a.dx = dx; a.dw = dw; a.db = db;
+    a.batch = batch; a.in_f = in_f; a.out_f = out_f;
+    a.acc_dx = acc_dx; a.acc_dw = acc_dw; a.acc_db = acc_db;
+    a.dx_blocks = 0;
+    if (dx) {
+        a.dx_blocks = (batch * 32 + kThreads - 1) / kThreads;
+        if (a.dx_blocks > ctx->sm_count) a.dx_blocks = ctx->sm_count;
+    }
+    a.col_blocks = 0; a.row_splits = 0; a.rows_per_split = 0;
+    a.partial = nullptr; a.tickets = nullptr;
+    if (dw || db) {
+        a.col_blocks = (in_f + kThreads - 1) / kThreads;
+        int splits = (ctx->sm_count + a.col_blocks - 1) / a.col_blocks;
+        int rps = (batch + splits - 1) / splits;
+        if (rps < 16) rps = 16;
+        if (rps > 1024) rps = 1024;                            // dY chunk of a split is staged in shared memory
+        a.rows_per_split = rps;
+        a.row_splits = (batch + rps - 1) / rps;
+        if (a.col_blocks > kCounterGemm - kCounterColsum) {
+            set_error("linear_skinny_bwd: in_features %d too large", in_f);
+            return TP_ERR_UNSUPPORTED;
+        }
+        size_t per = (size_t)out_f * kThreads + kMaxOut;
+        int rc = ensure_scratch(ctx, (size_t)a.col_blocks * a.row_splits * per * sizeof(float));
+        if (rc) return rc;
+        a.partial = ctx->scratch;
+        a.tickets = ctx->dev_counters + kCounterColsum;        // same stream, never concurrent with tp_colsum
+    }
+    int blocks = a.dx_blocks + a.col_blocks * a.row_splits;
+    if (blocks == 0) return TP_OK;
+    size_t smem_dx = dx ? (size_t)out_f * in_f * sizeof(float) : 0;
+    size_t smem_dw = (size_t)a.rows_per_split * out_f * sizeof(float);
+    size_t smem = smem_dx > smem_dw ? smem_dx : smem_dw;
+    skinny_bwd_kernel<<<blocks, kThreads, smem, ctx->stream>>>(a);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+}  // namespace tp
