@@ -87,6 +87,15 @@ int  tp_event_sync(tp_event* ev);
 int  tp_event_elapsed_ms(tp_event* start, tp_event* stop, float* ms);
 int  tp_event_destroy(tp_event* ev);
 
+/* Input prefetch: a second (copy) stream per context so the host->device copy of step i+1's batch overlaps
+ * step i's kernels.  tp_copy_* enqueue on the copy stream; events order the two streams:
+ *   copy stream : tp_copy_wait_event(done[i-N]) ; tp_copy_upload_pinned(x[i%N]) ; tp_copy_event_record(ready[i])
+ *   main stream : tp_stream_wait_event(ready[i]) ; <step i> ; tp_event_record(done[i])                         */
+int  tp_copy_upload_pinned(tp_ctx* ctx, tp_buf* dst, const void* pinned_host, size_t n);
+int  tp_copy_event_record(tp_ctx* ctx, tp_event* ev);
+int  tp_copy_wait_event(tp_ctx* ctx, tp_event* ev);
+int  tp_stream_wait_event(tp_ctx* ctx, tp_event* ev);
+
 /* CUDA-graph capture of everything enqueued on the context's stream between begin and end. */
 int  tp_graph_begin(tp_ctx* ctx);
 int  tp_graph_end(tp_ctx* ctx, tp_graph** out);
@@ -266,6 +275,47 @@ float tp_adam_step_size(float lr, float beta1, float beta2, int t);
 int tp_gather_batch(tp_ctx*, const tp_buf* images, const tp_buf* labels, const tp_buf* perm_i32, const tp_buf* cursor_i32,
                     tp_buf* dst_x, tp_buf* dst_y, int rows, int cols, int n_perm);
 int tp_cursor_advance(tp_ctx*, tp_buf* cursor_i32, int delta, int modulo);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device tape: one whole training step of a small MLP as ONE persistent cooperative kernel.
+ * Replaces the loop body of Trainer::train_epoch (src/train.rs:106-138: Tape::reset, model.forward
+ * [Linear src/nn.rs:54-60, ReLU src/ops.rs:312-374], cross_entropy_loss src/loss.rs:136-195, accuracy
+ * src/loss.rs:271-290, loss.backward src/tape.rs:106-127, optimizer.step src/optim.rs:21-33 / 83-113 /
+ * 148-168, zero_grad) for models that are a chain of Linear(+ReLU) layers ending in a classifier of at
+ * most 16 classes.  The job list is compiled once per (model, batch size); the kernel walks it phase by
+ * phase with a grid barrier between dependent phases.  Exact fp32 (FFMA), deterministic.
+ *   tp_step_supported : 1 if the fused step can run this description (feature widths multiples of 4,
+ *                       classes <= 16, batch <= 4096, < 1.5 GFLOP per step: larger models are faster
+ *                       on the tcgen05 GEMM path)
+ *   tp_step_run       : perm_i32 == NULL: x [batch,in] / labels [batch] are the batch (host-fed);
+ *                       otherwise x / labels are the resident dataset [n_perm,...] and rows
+ *                       perm[(cursor + r) % n_perm] are gathered in-kernel; cursor advances by batch.
+ *                       Writes result = {loss, #correct}; Adam state (hyper, see tp_adam_hyper_init)
+ *                       advances on the device exactly as tp_adam_advance + tp_adam_step_dev would.
+ * ------------------------------------------------------------------------------------------- */
+#define TP_STEP_MAX_LAYERS 8
+typedef struct tp_step tp_step;
+typedef struct tp_step_desc {
+    int n_layers;                            /* Linear layers; the last one is the classifier head */
+    int dims[TP_STEP_MAX_LAYERS + 1];        /* in, hidden..., classes                              */
+    int relu[TP_STEP_MAX_LAYERS];            /* ReLU after layer l (ignored for the last)           */
+    int batch;
+    int optimizer;                           /* 0 SGD, 1 Adam, 2 AdamW                              */
+    int64_t w_off[TP_STEP_MAX_LAYERS];       /* offset of W_l [out,in] in the flat arenas           */
+    int64_t b_off[TP_STEP_MAX_LAYERS];       /* offset of b_l [out], or -1 if the layer has no bias */
+    int64_t arena_len;                       /* elements in params / grads / m / v                  */
+} tp_step_desc;
+int tp_step_supported(const tp_step_desc* desc);
+int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v,
+                   tp_buf* hyper, tp_buf* result, tp_step** out);
+int tp_step_run(tp_ctx* ctx, tp_step* step, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32,
+                tp_buf* cursor_i32, int n_perm, float sgd_lr, float grad_scale);
+int tp_step_info(const tp_step* step, int* n_phases, int* n_jobs, int* grid);
+/* per-CTA SM-clock stamps of the last run: [grid][slots] = entry, setup done, then {work done, barrier passed}
+ * for each phase (evidence for profiles/: where the step's time goes) */
+int tp_step_set_profile(tp_step* step, int on);
+int tp_step_read_profile(tp_step* step, int64_t* out, size_t cap, int* slots);
+int tp_step_destroy(tp_step* step);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (no counterpart in the reference: it is single-process).

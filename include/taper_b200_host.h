@@ -54,6 +54,10 @@ int tp_trainer_create(tp_model* m, const char* optimizer, float lr, float beta1,
 int tp_trainer_destroy(tp_trainer* t);
 int tp_trainer_set_lr(tp_trainer* t, float lr);                      /* Adam::set_lr  src/optim.rs:125-127 */
 int tp_trainer_set_use_graph(tp_trainer* t, int on);
+/* fused device step (tp_step_* in taper_b200.h: the whole loop body as one persistent kernel); on by default, used
+ * whenever model, optimizer and batch qualify, otherwise the step runs through the tape + CUDA-graph path */
+int tp_trainer_set_use_fused(tp_trainer* t, int on);
+int tp_trainer_fused_steps(tp_trainer* t, uint64_t* count);
 /* one train_epoch iteration (src/train.rs:106-138), synchronous, host inputs */
 int tp_trainer_step(tp_trainer* t, const float* images, const float* labels, size_t batch, const size_t* sample_shape,
                     int ndim, float* loss, float* correct);

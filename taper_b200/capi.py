@@ -34,11 +34,18 @@ class PoolDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n", "c", "h", "w", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w")]
 
 
-_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer")
+class StepDesc(C.Structure):
+    """tp_step_desc (include/taper_b200.h): a chain of Linear(+ReLU) layers + classifier head + optimizer."""
+    MAX_LAYERS = 8
+    _fields_ = [("n_layers", C.c_int), ("dims", C.c_int * 9), ("relu", C.c_int * 8), ("batch", C.c_int), ("optimizer", C.c_int),
+                ("w_off", C.c_int64 * 8), ("b_off", C.c_int64 * 8), ("arena_len", C.c_int64)]
+
+
+_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step")
 _BASE = {
     "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32,
     "int64_t": C.c_int64, "char": C.c_char, "void": None,
-    "tp_conv_desc": ConvDesc, "tp_pool_desc": PoolDesc,
+    "tp_conv_desc": ConvDesc, "tp_pool_desc": PoolDesc, "tp_step_desc": StepDesc,
 }
 
 
@@ -201,5 +208,5 @@ class Ctx:
     def call(self, name, *args):
         """Invoke tp_<name>(ctx, *args) with Buf arguments unwrapped; raises on non-zero status."""
         fn = getattr(lib, "tp_" + name)
-        conv = [a.h if isinstance(a, Buf) else (C.byref(a) if isinstance(a, (ConvDesc, PoolDesc)) else a) for a in args]
+        conv = [a.h if isinstance(a, Buf) else (C.byref(a) if isinstance(a, (ConvDesc, PoolDesc, StepDesc)) else a) for a in args]
         return check(fn(self.h, *conv))

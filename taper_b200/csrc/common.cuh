@@ -44,6 +44,7 @@ struct tp_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // input prefetch: H2D copies that overlap the compute stream (created on first use)
     tp::Allocator alloc;
     tp::Allocator* capture_pool = nullptr;   // non-null between tp_graph_begin and tp_graph_end
     uint64_t launches = 0;

@@ -293,6 +293,14 @@ int tp_trainer_broadcast_params(tp_trainer* t, int root) {
     return guarded([&] { TRAINER(t); t->tr->broadcast_parameters(root); });
 }
 
+int tp_trainer_set_use_fused(tp_trainer* t, int on) {
+    return guarded([&] { TRAINER(t); t->tr->set_use_fused(on != 0); });
+}
+
+int tp_trainer_fused_steps(tp_trainer* t, uint64_t* count) {
+    return guarded([&] { TRAINER(t); if (count) *count = t->tr->fused_steps(); });
+}
+
 int tp_trainer_graph_replays(tp_trainer* t, uint64_t* count) {
     return guarded([&] { TRAINER(t); if (count) *count = t->tr->graph_replays(); });
 }

@@ -1,5 +1,6 @@
 // Host layer, part 2: nn modules, losses, optimizers, LR schedulers, the data-parallel group.
 // Mirrors src/nn.rs, src/activation.rs, src/loss.rs and src/optim.rs of the reference.
+#include <cstring>
 #include "taper_internal.hpp"
 
 #include <cmath>
@@ -261,6 +262,49 @@ void Optimizer::mark_parameters_updated() const { arena()->bump_versions(); }
 tp_buf* arena_grad_buf(const std::shared_ptr<Arena>& a) { return a->g; }
 size_t arena_total(const std::shared_ptr<Arena>& a) { return a->total; }
 tp_buf* arena_param_buf(const std::shared_ptr<Arena>& a) { return a->p; }
+
+bool describe_fused_step(const nn::Module& model, const Optimizer& opt, size_t batch, tp_step_desc* d, tp_buf* bufs[5]) {
+    auto* seq = dynamic_cast<const nn::Sequential*>(&model);
+    if (!seq || Config::reference_op_sequence()) return false;
+    std::shared_ptr<Arena> a = opt.arena();
+    if (!a) return false;
+    std::memset(d, 0, sizeof(*d));
+    auto offset_of = [&](const Tensor& t, int64_t* off) {
+        for (size_t i = 0; i < a->params.size(); ++i)
+            if (a->params[i].impl() == t.impl()) { *off = (int64_t)a->off[i]; return t.needs_grad(); }
+        return false;
+    };
+    size_t matched = 0;
+    int L = 0;
+    const auto& layers = seq->layers;
+    for (size_t i = 0; i < layers.size(); ++i) {
+        auto* lin = dynamic_cast<const nn::Linear*>(layers[i].get());
+        if (!lin || L >= TP_STEP_MAX_LAYERS) return false;
+        const Shape& ws = lin->weight.shape();
+        if (ws.size() != 2) return false;
+        if (L == 0) d->dims[0] = (int)ws[1];
+        else if ((size_t)d->dims[L] != ws[1]) return false;
+        d->dims[L + 1] = (int)ws[0];
+        if (!offset_of(lin->weight, &d->w_off[L])) return false;
+        matched++;
+        d->b_off[L] = -1;
+        if (lin->bias) {
+            if (!offset_of(*lin->bias, &d->b_off[L])) return false;
+            matched++;
+        }
+        bool relu = i + 1 < layers.size() && dynamic_cast<const nn::ReLU*>(layers[i + 1].get()) != nullptr;
+        d->relu[L] = relu ? 1 : 0;
+        if (relu) ++i;
+        ++L;
+    }
+    if (L == 0 || d->relu[L - 1] || matched != a->params.size()) return false;
+    d->n_layers = L;
+    d->batch = (int)batch;
+    d->optimizer = opt.kind();
+    d->arena_len = (int64_t)a->total;
+    bufs[0] = a->p; bufs[1] = a->g; bufs[2] = a->m; bufs[3] = a->v; bufs[4] = a->hyper;
+    return tp_step_supported(d) != 0;
+}
 
 // ---- SGD  (src/optim.rs:8-40) ----------------------------------------------------------------------
 SGD::SGD(std::vector<Tensor> params, float lr, std::optional<float> /*momentum: ignored, :14-17*/)

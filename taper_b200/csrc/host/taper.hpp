@@ -242,7 +242,15 @@ struct Optimizer {                                                   // :3-6
     virtual void set_lr(float) {}
     // a replayed CUDA graph updated the parameters without the host-side step() running: invalidate host mirrors
     void mark_parameters_updated() const;
+    // hooks of the fused device step (tp_step_*, the whole train_epoch loop body as one persistent kernel)
+    virtual int kind() const = 0;                 // tp_step_desc.optimizer: 0 SGD, 1 Adam, 2 AdamW
+    virtual float lr() const = 0;
+    virtual float grad_scale() const = 0;
+    virtual void note_device_step() = 0;          // the device ran one step(): host-side counters and mirrors follow
 };
+// Describe `model` + `opt` as a tp_step_desc if the model is a chain Linear[,ReLU]...Linear whose parameters are exactly
+// the optimizer's arena; false otherwise.  bufs receives {params, grads, m, v, hyper} (m, v, hyper NULL for SGD).
+bool describe_fused_step(const nn::Module& model, const Optimizer& opt, size_t batch, tp_step_desc* desc, tp_buf* bufs[5]);
 tp_buf* arena_grad_buf(const std::shared_ptr<Arena>& a);
 tp_buf* arena_param_buf(const std::shared_ptr<Arena>& a);
 size_t arena_total(const std::shared_ptr<Arena>& a);
@@ -255,6 +263,11 @@ public:
     void zero_grad() override;
     void set_grad_scale(float s) override { grad_scale_ = s; }
     std::shared_ptr<Arena> arena() const override { return arena_; }
+    void set_lr(float lr) override { lr_ = lr; }
+    int kind() const override { return 0; }
+    float lr() const override { return lr_; }
+    float grad_scale() const override { return grad_scale_; }
+    void note_device_step() override { mark_parameters_updated(); }
 private:
     std::vector<Tensor> params_;
     float lr_;
@@ -274,6 +287,10 @@ public:
     void set_grad_scale(float s) override { grad_scale_ = s; }       // 1/world for data-parallel averaging
     std::shared_ptr<Arena> arena() const override { return arena_; }
     size_t t() const { return t_; }
+    int kind() const override { return 1; }
+    float lr() const override { return lr_; }
+    float grad_scale() const override { return grad_scale_; }
+    void note_device_step() override { t_ += 1; mark_parameters_updated(); }
 protected:
     void step_impl(bool decoupled);
     std::vector<Tensor> params_;
@@ -294,6 +311,10 @@ public:
     void set_lr(float lr) override { adam_.set_lr(lr); }
     void set_grad_scale(float s) override { adam_.set_grad_scale(s); }
     std::shared_ptr<Arena> arena() const override { return adam_.arena(); }
+    int kind() const override { return 2; }
+    float lr() const override { return adam_.lr(); }
+    float grad_scale() const override { return adam_.grad_scale(); }
+    void note_device_step() override { adam_.note_device_step(); }
 private:
     Adam adam_;
 };
@@ -424,11 +445,17 @@ public:
 
     void set_use_graph(bool v) { use_graph_ = v; }
     uint64_t graph_replays() const { return graph_replays_; }
+    // fused device step (one persistent kernel per training step, tp_step_*): used whenever the model / optimizer /
+    // batch qualify (describe_fused_step + tp_step_supported); everything else takes the tape + CUDA-graph path
+    void set_use_fused(bool v) { use_fused_ = v; }
+    uint64_t fused_steps() const { return fused_steps_; }
 private:
     struct Impl;
     std::unique_ptr<Impl> p_;
     bool use_graph_ = true;
     uint64_t graph_replays_ = 0;
+    bool use_fused_ = true;
+    uint64_t fused_steps_ = 0;
 };
 
 }  // namespace train

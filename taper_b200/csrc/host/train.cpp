@@ -124,9 +124,16 @@ void Metrics::plot_summary() const {
 
 namespace {
 constexpr size_t kRing = 8;          // result slots in flight (host may run this many steps ahead)
+constexpr size_t kStage = 3;         // input staging buffers per batch shape (H2D of step i+1 overlaps step i)
 
 struct Slot {                        // per batch-shape persistent state
     Tensor x, y;                     // device inputs the step reads
+    // pinned-host inputs: copied on the context's copy stream into a rotating staging buffer
+    Tensor sx[kStage], sy[kStage];
+    tp_event* ready[kStage] = {};    // copy stream: staging buffer k holds the batch
+    tp_event* done[kStage] = {};     // main stream: the reader of staging buffer k has been enqueued and finished
+    bool done_valid[kStage] = {};
+    uint64_t staged = 0;
     int eager_runs = 0;
     tp_graph* graph = nullptr;       // captured step (host-fed variant)
     tp_graph* graph_resident = nullptr;      // captured gather + step (device-resident dataset)
@@ -146,6 +153,21 @@ struct Trainer::Impl {
     size_t ds_n = 0;
     Shape ds_sample;
     int world = 1;
+    // fused device step per batch size (NULL once a size is known not to qualify)
+    std::map<size_t, tp_step*> fused;
+
+    tp_step* fused_step(Trainer& tr, size_t batch, const Shape& sample_shape) {
+        if (world != 1 || sample_shape.size() != 1) return nullptr;
+        auto it = fused.find(batch);
+        if (it != fused.end()) return it->second;
+        tp_step* st = nullptr;
+        tp_step_desc d;
+        tp_buf* b[5] = {};
+        if (optim::describe_fused_step(*tr.model, *tr.optimizer, batch, &d, b) && (size_t)d.dims[0] == sample_shape[0])
+            check(tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), &st));
+        fused[batch] = st;
+        return st;
+    }
 
     void enqueue_result() {
         size_t i = head % kRing;
@@ -156,9 +178,14 @@ struct Trainer::Impl {
 
     ~Impl() {
         tp_sync(ctx());
+        for (auto& kv : fused) tp_step_destroy(kv.second);
         for (auto& kv : slots) {
             tp_graph_destroy(kv.second.graph);
             tp_graph_destroy(kv.second.graph_resident);
+            for (size_t k = 0; k < kStage; ++k) {
+                tp_event_destroy(kv.second.ready[k]);
+                tp_event_destroy(kv.second.done[k]);
+            }
         }
         slots.clear();
         for (auto* e : events) tp_event_destroy(e);
@@ -246,19 +273,55 @@ StepResult Trainer::fetch() {
 void Trainer::train_batch_async(const float* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned) {
     Impl& p = *p_;
     if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
-    Shape fs = full_shape(batch, sample_shape);
-    Slot& s = p.slots[fs];
+    Shape fs_shape = full_shape(batch, sample_shape);
+    Slot& s = p.slots[fs_shape];
     if (!s.x.defined()) {
-        s.x = Tensor::empty(fs);
+        s.x = Tensor::empty(fs_shape);
         s.y = Tensor::empty({batch});
     }
     tp_ctx* c = ctx();
+    tp_step* fs = use_fused_ ? p.fused_step(*this, batch, sample_shape) : nullptr;
+    tp_buf *xin = s.x.buf(), *yin = s.y.buf();
+    size_t k = 0;
     if (pinned) {
-        check(tp_buf_upload_pinned(c, s.x.buf(), images, s.x.numel()));
-        check(tp_buf_upload_pinned(c, s.y.buf(), labels, batch));
+        // H2D on the copy stream into staging buffer k while earlier steps still run on the main stream
+        k = s.staged % kStage;
+        if (!s.sx[k].defined()) {
+            s.sx[k] = Tensor::empty(fs_shape);
+            s.sy[k] = Tensor::empty({batch});
+            check(tp_event_create(c, &s.ready[k]));
+            check(tp_event_create(c, &s.done[k]));
+        }
+        if (s.done_valid[k]) check(tp_copy_wait_event(c, s.done[k]));
+        check(tp_copy_upload_pinned(c, s.sx[k].buf(), images, s.x.numel()));
+        check(tp_copy_upload_pinned(c, s.sy[k].buf(), labels, batch));
+        check(tp_copy_event_record(c, s.ready[k]));
+        check(tp_stream_wait_event(c, s.ready[k]));
+        if (fs) {
+            xin = s.sx[k].buf();
+            yin = s.sy[k].buf();
+        } else {                                           // a captured graph reads fixed buffers: device-to-device hop
+            check(tp_buf_copy(c, s.x.buf(), s.sx[k].buf(), s.x.numel()));
+            check(tp_buf_copy(c, s.y.buf(), s.sy[k].buf(), batch));
+            check(tp_event_record(c, s.done[k]));
+            s.done_valid[k] = true;
+        }
+        s.staged++;
     } else {
         check(tp_buf_upload(c, s.x.buf(), images, s.x.numel()));
         check(tp_buf_upload(c, s.y.buf(), labels, batch));
+    }
+    if (fs) {
+        // the whole loop body (src/train.rs:106-138) as one persistent kernel walking the compiled tape
+        check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, optimizer->lr(), optimizer->grad_scale()));
+        if (pinned) {
+            check(tp_event_record(c, s.done[k]));
+            s.done_valid[k] = true;
+        }
+        optimizer->note_device_step();
+        fused_steps_++;
+        p.enqueue_result();
+        return;
     }
     if (s.graph) {
         check(tp_graph_launch(c, s.graph));
@@ -325,6 +388,15 @@ void Trainer::train_batch_resident(size_t batch) {
     Impl& p = *p_;
     if (!p.ds_images) panic("Trainer::train_batch_resident: load_dataset has not been called");
     if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
+    if (tp_step* fst = use_fused_ ? p.fused_step(*this, batch, p.ds_sample) : nullptr) {
+        // batch rows are gathered out of the resident dataset inside the step kernel; the cursor advances there too
+        check(tp_step_run(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, optimizer->lr(),
+                          optimizer->grad_scale()));
+        optimizer->note_device_step();
+        fused_steps_++;
+        p.enqueue_result();
+        return;
+    }
     Shape fs = full_shape(batch, p.ds_sample);
     Slot& s = p.slots[fs];
     if (!s.x.defined()) {

@@ -174,6 +174,10 @@ int tp_ctx_destroy(tp_ctx* ctx) {
     if (!ctx) return TP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     tp_comm_destroy(ctx);
     tp::gemm_tc_destroy(ctx);
     ctx->alloc.release_all();
@@ -190,6 +194,7 @@ int tp_ctx_destroy(tp_ctx* ctx) {
 
 int tp_sync(tp_ctx* ctx) {
     TP_CHECK_ARG(ctx, "tp_sync: NULL ctx");
+    if (ctx->copy_stream) TP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     TP_CUDA(cudaStreamSynchronize(ctx->stream));
     return TP_OK;
 }
@@ -317,6 +322,46 @@ int tp_buf_upload_pinned(tp_ctx* ctx, tp_buf* dst, const void* pinned_host, size
     TP_CHECK_ARG(ctx && pinned_host, "tp_buf_upload_pinned: NULL argument");
     TP_NEED(dst, n, "dst");
     TP_CUDA(cudaMemcpyAsync(dst->ptr, pinned_host, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return TP_OK;
+}
+
+// ---- copy stream: host->device input prefetch that overlaps the compute stream --------------------------------------
+static int ensure_copy_stream(tp_ctx* ctx) {
+    if (ctx->copy_stream) return TP_OK;
+    cudaSetDevice(ctx->device);
+    TP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    return TP_OK;
+}
+
+int tp_copy_upload_pinned(tp_ctx* ctx, tp_buf* dst, const void* pinned_host, size_t n) {
+    TP_CHECK_ARG(ctx && pinned_host, "tp_copy_upload_pinned: NULL argument");
+    TP_NEED(dst, n, "dst");
+    int rc = ensure_copy_stream(ctx);
+    if (rc) return rc;
+    TP_CUDA(cudaMemcpyAsync(dst->ptr, pinned_host, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    return TP_OK;
+}
+
+int tp_copy_event_record(tp_ctx* ctx, tp_event* ev) {
+    TP_CHECK_ARG(ctx && ev, "tp_copy_event_record: NULL argument");
+    int rc = ensure_copy_stream(ctx);
+    if (rc) return rc;
+    TP_CUDA(cudaEventRecord(ev->ev, ctx->copy_stream));
+    return TP_OK;
+}
+
+int tp_copy_wait_event(tp_ctx* ctx, tp_event* ev) {
+    TP_CHECK_ARG(ctx && ev, "tp_copy_wait_event: NULL argument");
+    int rc = ensure_copy_stream(ctx);
+    if (rc) return rc;
+    TP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev->ev, 0));
+    return TP_OK;
+}
+
+int tp_stream_wait_event(tp_ctx* ctx, tp_event* ev) {
+    TP_CHECK_ARG(ctx && ev, "tp_stream_wait_event: NULL argument");
+    TP_CHECK_ARG(!ctx->capturing, "tp_stream_wait_event: not inside a graph capture");
+    TP_CUDA(cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
     return TP_OK;
 }
 

@@ -1,0 +1,904 @@
+// tape_step.cu — a whole MLP training step as ONE persistent kernel: the "device tape".
+//
+// The reference's step (src/train.rs:106-138: Tape::reset, forward, cross_entropy_loss, accuracy, backward,
+// optimizer.step, zero_grad) on the small MNIST MLPs is ~0.2 GFLOP: on a B200 every kernel of the eager / CUDA-graph
+// path is launch- and latency-bound (5-12 us each, 12 launches).  Here the host compiles the recorded tape of such a
+// model into a static job list and ONE cooperative kernel (one CTA per SM) walks it phase by phase with a grid barrier
+// between dependent phases:
+//     fwd GEMMs (gathering the batch rows straight out of the resident dataset)  ->  head (logits, log-softmax, NLL,
+//     accuracy, dlogits, dX of the head, ReLU mask)  ->  backward GEMMs (dW with the bias column-sum riding along, dX
+//     with the ReLU mask in the epilogue) + loss fold  ->  SGD / Adam / AdamW over the flat arena.
+// Arithmetic is exact fp32 FMA on the CUDA cores: at these sizes (512x128x784) the tensor-core path is bound by its own
+// TMA/TMEM/commit latency chain, not by math (measured: 12 us for the tcgen05 kernel alone).  Larger models keep the
+// tcgen05 GEMM path (gemm_tc.cu); tp_step_supported() draws the line.
+// Deterministic: split-K partials are folded in split order by the last CTA of a tile; no float atomics.
+#include "common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int BM = 64, BN = 64, BK = 16, LDS = BM + 4;        // smem tile row pitch (floats)
+constexpr int SUB = 4, SK = SUB * BK;                          // a pipeline stage = 4 sub-tiles = 64 k: one memory round trip
+constexpr int kMaxOut = 16;
+constexpr int kMaxJobs = 32, kMaxPhases = 20;
+constexpr int kMaxBatch = 4096;
+constexpr int kHeadRows = 8;                                   // one warp per row
+constexpr int kProfSlots = 2 + 2 * kMaxPhases;               // entry, setup done, then {work done, barrier passed} per phase
+constexpr long long kSpinLimit = 400000000LL;                  // ~0.2 s: a barrier that never completes must not hang the GPU
+
+enum { JOB_GEMM = 0, JOB_HEAD = 1, JOB_LOSS = 2, JOB_OPT = 3 };
+enum { H_T = 0, H_LR, H_B1, H_B2, H_EPS, H_WD, H_SS, H_DECAY, H_COUNT };       // same layout as optim.cu
+
+struct Job {
+    int kind, items;
+    // GEMM  C[M,N] = A[M,K] * B[K,N]   (A element (m,k): a_kc ? A[row(m)*lda + k] : A[row(k)*lda + m]; same for B with n)
+    const float* A; const float* B; float* C;
+    int lda, ldb, ldc;
+    int a_kc, b_kc;
+    int a_input, b_input;            // operand is the step's input batch X (rows go through the gather index)
+    int M, N, K, m_store;
+    int tiles_m, tiles_n, splits, kchunk;
+    const float* bias; int relu;
+    const float* mask; int ldmask;   // C *= [mask > 0]
+    float* partial;                  // [splits][tiles_m*BM][N]
+    float* colsum;                   // optional [M]: sum_k A(m,k)  (bias gradient rides on the dW GEMM)
+    float* cs_partial;               // [splits][tiles_m*BM]
+    int* tickets;                    // [tiles_m*tiles_n]
+    // HEAD  (A = activations [M=batch, K=in], B = W [N=out, in], bias)
+    float* dlog;                     // [batch, 16]  zero padded
+    float* dz;                       // optional [batch, in]
+    int dz_mask;                     // dz *= [A > 0]
+    float* nll; float* hit;          // [batch]
+    float inv_b;
+    // LOSS: nll, hit, M -> result {loss, correct}
+    float* result;
+    // OPT
+    float* p; float* g; float* m; float* v; int n4;
+};
+
+struct StepParams {
+    const Job* jobs;
+    int n_jobs, n_phases;
+    int phase_first[kMaxPhases + 1];
+    const float* x;                  // [batch, in] or the resident dataset [n_perm, in]
+    const float* labels;             // [batch] or [n_perm]
+    const int* perm;                 // NULL: x / labels are the batch itself
+    int* cursor;
+    int n_perm, batch;
+    unsigned int* bar;               // {count, generation}
+    int opt_kind;                    // 0 SGD, 1 Adam, 2 AdamW
+    float sgd_lr, grad_scale;
+    float* hyper;
+    int* err;
+    long long* prof;                 // optional [grid][kProfSlots] SM-clock stamps (tp_step_set_profile)
+};
+
+struct AdamArgs {
+    float step_size, beta1, beta2, eps, weight_decay, grad_scale, decay_factor;
+    int decoupled;
+};
+
+// identical to optim.cu's adam_elem (expression order follows src/optim.rs:93-110; -fmad=false)
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamArgs& a) {
+    if (a.decoupled) p *= a.decay_factor;
+    if (a.grad_scale != 1.0f) g *= a.grad_scale;
+    float gg = g + a.weight_decay * p;
+    m = a.beta1 * m + (1.0f - a.beta1) * gg;
+    v = a.beta2 * v + (1.0f - a.beta2) * gg * gg;
+    p -= a.step_size * m / (sqrtf(v) + a.eps);
+}
+
+__device__ __forceinline__ float powi_dev(float a, int b) {     // f32::powi, as optim.cu
+    float r = 1.0f;
+    unsigned int e = (unsigned int)b;
+    while (true) {
+        if (e & 1u) r *= a;
+        e >>= 1;
+        if (e == 0) break;
+        a *= a;
+    }
+    return r;
+}
+
+__device__ __forceinline__ unsigned int class_of(float t) {     // `t as usize` (src/loss.rs:160)
+    if (!(t > 0.0f)) return 0u;
+    if (t >= 4294967040.0f) return 0xffffffffu;
+    return (unsigned int)t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// ---- grid barrier (sense = generation counter; count is reset by the last arriver before it releases) ------------
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int prev = atomicAdd(&bar[0], 1u);
+        if (prev == gridDim.x - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(&bar[1], 1u);
+        } else {
+            unsigned int cur;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
+                if (cur == gen && clock64() - t0 > kSpinLimit) { atomicExch(err, 2); break; }
+            } while (cur == gen);
+        }
+        gen += 1u;
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---- GEMM tile loader: one float4 per thread per operand per BK step ------------------------------------------------
+template <bool KC>
+__device__ __forceinline__ float4 fetch(const float* __restrict__ P, int ld, const int* __restrict__ ridx, int mn0, int mn_lim,
+                                        int k0, int kend, int tid) {
+    float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (KC) {
+        const int mn = mn0 + (tid >> 2), gk = k0 + ((tid & 3) << 2);
+        if (mn < mn_lim && gk < kend) {
+            const int row = ridx ? ridx[mn] : mn;
+            z = ldcg4(P + (size_t)row * ld + gk);
+        }
+    } else {
+        const int gk = k0 + (tid >> 4), mn = mn0 + ((tid & 15) << 2);
+        if (gk < kend && mn < mn_lim) {
+            const int row = ridx ? ridx[gk] : gk;
+            z = ldcg4(P + (size_t)row * ld + mn);
+        }
+    }
+    return z;
+}
+
+template <bool KC>
+__device__ __forceinline__ void stash(float* __restrict__ S, float4 v, int tid) {          // S: [BK][LDS]
+    if (KC) {
+        const int mn = tid >> 2, kq = (tid & 3) << 2;
+        S[(kq + 0) * LDS + mn] = v.x;
+        S[(kq + 1) * LDS + mn] = v.y;
+        S[(kq + 2) * LDS + mn] = v.z;
+        S[(kq + 3) * LDS + mn] = v.w;
+    } else {
+        const int k = tid >> 4, mq = (tid & 15) << 2;
+        *reinterpret_cast<float4*>(S + k * LDS + mq) = v;
+    }
+}
+
+__device__ __forceinline__ void epilogue_store(const Job& j, int gm, int gn, float4 v) {
+    if (j.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(j.bias + gn));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (j.relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+    if (j.mask) {
+        const float4 k = ldcg4(j.mask + (size_t)gm * j.ldmask + gn);
+        v.x = k.x > 0.0f ? v.x : 0.0f; v.y = k.y > 0.0f ? v.y : 0.0f;
+        v.z = k.z > 0.0f ? v.z : 0.0f; v.w = k.w > 0.0f ? v.w : 0.0f;
+    }
+    *reinterpret_cast<float4*>(j.C + (size_t)gm * j.ldc + gn) = v;
+}
+
+template <bool AKC, bool BKC>
+__device__ void gemm_item(const Job& j, int item, const StepParams& P, const int* __restrict__ ridx, float* __restrict__ As,
+                          float* __restrict__ Bs, int* s_flag) {
+    const int tid = threadIdx.x;
+    const int tiles = j.tiles_m * j.tiles_n;
+    const int split = item / tiles, tile = item - split * tiles;
+    const int tm = tile / j.tiles_n, tn = tile - tm * j.tiles_n;
+    const int m0 = tm * BM, n0 = tn * BN;
+    const int kbeg = split * j.kchunk, kend = min(j.K, kbeg + j.kchunk);
+    const float* A = j.a_input ? P.x : j.A;
+    const float* B = j.b_input ? P.x : j.B;
+    const int* ra = j.a_input ? ridx : nullptr;
+    const int* rb = j.b_input ? ridx : nullptr;
+    const int tx = tid & 15, ty = tid >> 4;
+    const bool do_cs = (!AKC) && j.colsum && tn == 0 && tid < BM;
+
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+    float cs = 0.0f;
+
+    // Stage = SK (64) k-values per operand held in registers while the previous stage is multiplied out of shared
+    // memory: one global-memory round trip per 64 k instead of per 16 (the loop is latency-, not bandwidth-bound).
+    const int ns = (kend - kbeg + SK - 1) / SK;
+    float4 ra4[SUB], rb4[SUB];
+#pragma unroll
+    for (int u = 0; u < SUB; ++u) {
+        ra4[u] = fetch<AKC>(A, j.lda, ra, m0, j.M, kbeg + u * BK, kend, tid);
+        rb4[u] = fetch<BKC>(B, j.ldb, rb, n0, j.N, kbeg + u * BK, kend, tid);
+    }
+#pragma unroll
+    for (int u = 0; u < SUB; ++u) {
+        stash<AKC>(As + u * (BK * LDS), ra4[u], tid);
+        stash<BKC>(Bs + u * (BK * LDS), rb4[u], tid);
+    }
+    __syncthreads();
+    for (int st = 0; st < ns; ++st) {
+        const int cur = st & 1;
+        const int k0 = kbeg + st * SK;
+        if (st + 1 < ns) {
+#pragma unroll
+            for (int u = 0; u < SUB; ++u) {
+                ra4[u] = fetch<AKC>(A, j.lda, ra, m0, j.M, k0 + SK + u * BK, kend, tid);
+                rb4[u] = fetch<BKC>(B, j.ldb, rb, n0, j.N, k0 + SK + u * BK, kend, tid);
+            }
+        }
+        const float* as = As + cur * (SK * LDS);
+        const float* bs = Bs + cur * (SK * LDS);
+        const int klen = min(SK, kend - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < klen; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(as + kk * LDS + ty * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + kk * LDS + tx * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+        if (do_cs) {
+            for (int kk = 0; kk < klen; ++kk) cs += as[kk * LDS + tid];         // k ascending
+        }
+        if (st + 1 < ns) {
+#pragma unroll
+            for (int u = 0; u < SUB; ++u) {
+                stash<AKC>(As + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), ra4[u], tid);
+                stash<BKC>(Bs + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), rb4[u], tid);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int gn = n0 + tx * 4;
+    if (j.splits == 1) {
+        if (gn < j.N) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int gm = m0 + ty * 4 + a;
+                if (gm < j.m_store) epilogue_store(j, gm, gn, make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]));
+            }
+        }
+        if (do_cs && m0 + tid < j.m_store) j.colsum[m0 + tid] = cs;
+        return;
+    }
+    // split-K: park the partial tile; the last CTA to arrive folds all splits in split order
+    const int mpad = j.tiles_m * BM;
+    if (gn < j.N) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int gm = m0 + ty * 4 + a;
+            *reinterpret_cast<float4*>(j.partial + ((size_t)split * mpad + gm) * j.N + gn) =
+                make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        }
+    }
+    if (do_cs) j.cs_partial[(size_t)split * mpad + m0 + tid] = cs;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int prev = atomicAdd(j.tickets + tile, 1);
+        const int last = (prev == j.splits - 1);
+        if (last) j.tickets[tile] = 0;
+        *s_flag = last;
+    }
+    __syncthreads();
+    const int last = *s_flag;
+    __syncthreads();                                       // s_flag may be rewritten by the next item
+    if (!last) return;
+    __threadfence();
+    if (gn < j.N) {
+        // all loads of a batch are issued before the first add: the fold costs ceil(splits/4) round trips, not 4*splits
+        float4 s4[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s4[a] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int z0 = 0; z0 < j.splits; z0 += 4) {
+            float4 q[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    q[u][a] = (z0 + u < j.splits) ? ldcg4(j.partial + ((size_t)(z0 + u) * mpad + m0 + ty * 4 + a) * j.N + gn)
+                                                  : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)                        // split order
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { s4[a].x += q[u][a].x; s4[a].y += q[u][a].y; s4[a].z += q[u][a].z; s4[a].w += q[u][a].w; }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int gm = m0 + ty * 4 + a;
+            if (gm < j.m_store) epilogue_store(j, gm, gn, s4[a]);
+        }
+    }
+    if (do_cs && m0 + tid < j.m_store) {
+        float s = 0.0f;
+        for (int z0 = 0; z0 < j.splits; z0 += 8) {
+            float q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = (z0 + u < j.splits) ? __ldcg(j.cs_partial + (size_t)(z0 + u) * mpad + m0 + tid) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += q[u];
+        }
+        j.colsum[m0 + tid] = s;
+    }
+}
+
+// ---- classifier head: one warp per batch row ----------------------------------------------------------------------
+// logits = a.W^T + b (src/nn.rs:54-60), log_softmax + NLL (src/loss.rs:101-126, 152-165), accuracy hit (:271-290),
+// dlogits = (exp(logp) - onehot) * (1/B) (src/loss.rs:174-191 with g(loss) = 1), dA = dlogits.W (src/ops.rs:254-265),
+// optionally masked by the producing ReLU (src/ops.rs:358-370).
+__device__ void head_item(const Job& j, int item, const StepParams& P, const int* __restrict__ ridx) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r = item * kHeadRows + wid;
+    if (r >= j.M) return;
+    const int in_f = j.K, out_f = j.N, in4 = in_f >> 2;
+    const float* arow = (j.a_input ? P.x + (size_t)(ridx ? ridx[r] : r) * j.lda : j.A + (size_t)r * j.lda);
+    const float* W = j.B;
+    float acc[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
+    for (int c = lane; c < in4; c += 32) {
+        const float4 a = ldcg4(arow + 4 * c);
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+            if (o < out_f) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
+                acc[o] = fmaf(a.x, w.x, acc[o]);
+                acc[o] = fmaf(a.y, w.y, acc[o]);
+                acc[o] = fmaf(a.z, w.z, acc[o]);
+                acc[o] = fmaf(a.w, w.w, acc[o]);
+            }
+        }
+    }
+    float mx = -INFINITY;
+    int bi = 0;
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) {
+        if (o < out_f) {
+            float v = warp_sum(acc[o]);
+            if (j.bias) v += __ldg(j.bias + o);
+            acc[o] = v;
+            if (v > mx) { mx = v; bi = o; }                   // strict '>' from -inf, first max wins (src/tensor.rs:1062)
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o)
+        if (o < out_f) s += expf(acc[o] - mx);                // classes ascending (src/tensor.rs:890-1018 sum over dim 1)
+    const float ls = logf(s);
+    const float t = __ldg(P.labels + (P.perm ? ridx[r] : r));
+    unsigned int cls = class_of(t);
+    if (cls >= (unsigned int)out_f) { if (lane == 0) atomicExch(P.err, 1); cls = out_f - 1; }
+    float dl[kMaxOut];
+    float xc = 0.0f;
+    const float scale = 1.0f * j.inv_b;                       // g(loss)[0] / B with the seeded g = 1 (src/loss.rs:186)
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) {
+        dl[o] = 0.0f;
+        if (o < out_f) {
+            const float lp = (acc[o] - mx) - ls;
+            float p = expf(lp);
+            if ((unsigned int)o == cls) { p -= 1.0f; xc = acc[o]; }
+            dl[o] = p * scale;
+        }
+    }
+    if (lane == 0) {
+        j.nll[r] = -((xc - mx) - ls);
+        j.hit[r] = (fabsf((float)bi - t) < 1e-6f) ? 1.0f : 0.0f;       // src/loss.rs:284
+    }
+    if (lane < kMaxOut) {
+        float mine = 0.0f;
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) if (o == lane) mine = dl[o];
+        j.dlog[(size_t)r * kMaxOut + lane] = mine;
+    }
+    if (j.dz) {
+        for (int c = lane; c < in4; c += 32) {
+            float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o) {
+                if (o < out_f) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
+                    d.x = fmaf(dl[o], w.x, d.x); d.y = fmaf(dl[o], w.y, d.y);
+                    d.z = fmaf(dl[o], w.z, d.z); d.w = fmaf(dl[o], w.w, d.w);
+                }
+            }
+            if (j.dz_mask) {
+                const float4 a = ldcg4(arow + 4 * c);
+                d.x = a.x > 0.0f ? d.x : 0.0f; d.y = a.y > 0.0f ? d.y : 0.0f;
+                d.z = a.z > 0.0f ? d.z : 0.0f; d.w = a.w > 0.0f ? d.w : 0.0f;
+            }
+            *reinterpret_cast<float4*>(j.dz + (size_t)r * in_f + 4 * c) = d;
+        }
+    }
+}
+
+// ---- loss = sum(nll) / B, correct = sum(hit)  (fixed tree: deterministic) ----------------------------------------
+__device__ void loss_item(const Job& j, float* sm /* >= 16 floats */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float a = 0.0f, h = 0.0f;
+    for (int r = threadIdx.x; r < j.M; r += kThreads) { a += __ldcg(j.nll + r); h += __ldcg(j.hit + r); }
+    a = warp_sum(a); h = warp_sum(h);
+    if (lane == 0) { sm[wid] = a; sm[8 + wid] = h; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sa = 0.0f, sh = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) { sa += sm[w]; sh += sm[8 + w]; }
+        j.result[0] = sa / (float)j.M;                        // acc / b as f32 (src/loss.rs:164)
+        j.result[1] = sh;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void opt_item(const Job& j, int item, const StepParams& P, const AdamArgs& aa) {
+    const int i = item * kThreads + threadIdx.x;
+    if (i >= j.n4) return;
+    float4* p4 = reinterpret_cast<float4*>(j.p) + i;
+    float4 pp = *p4;
+    float4 gg = __ldcg(reinterpret_cast<const float4*>(j.g) + i);
+    if (P.opt_kind == 0) {                                    // SGD: p -= lr * g (src/optim.rs:29)
+        if (P.grad_scale != 1.0f) { gg.x *= P.grad_scale; gg.y *= P.grad_scale; gg.z *= P.grad_scale; gg.w *= P.grad_scale; }
+        pp.x -= P.sgd_lr * gg.x; pp.y -= P.sgd_lr * gg.y; pp.z -= P.sgd_lr * gg.z; pp.w -= P.sgd_lr * gg.w;
+        *p4 = pp;
+        return;
+    }
+    float4* m4 = reinterpret_cast<float4*>(j.m) + i;
+    float4* v4 = reinterpret_cast<float4*>(j.v) + i;
+    float4 mm = *m4, vv = *v4;
+    adam_elem(pp.x, gg.x, mm.x, vv.x, aa);
+    adam_elem(pp.y, gg.y, mm.y, vv.y, aa);
+    adam_elem(pp.z, gg.z, mm.z, vv.z, aa);
+    adam_elem(pp.w, gg.w, mm.w, vv.w, aa);
+    *p4 = pp; *m4 = mm; *v4 = vv;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tape_step_kernel(const StepParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* As = reinterpret_cast<float*>(smem_raw);            // [2][SK][LDS]
+    float* Bs = As + 2 * SK * LDS;                             // [2][SK][LDS]
+    float* red = Bs + 2 * SK * LDS;                            // [16]
+    int* s_flag = reinterpret_cast<int*>(red + 16);            // [4]
+    Job* sjobs = reinterpret_cast<Job*>(s_flag + 4);           // [n_jobs]
+    int* ridx = reinterpret_cast<int*>(sjobs + P.n_jobs);      // [batch] when gathering
+    const int tid = threadIdx.x;
+
+#define TP_PROF(slot) do { if (P.prof && tid == 0) P.prof[(size_t)blockIdx.x * kProfSlots + (slot)] = clock64(); } while (0)
+    TP_PROF(0);
+    {   // stage the job list
+        const int words = P.n_jobs * (int)(sizeof(Job) / 4);
+        const int* src = reinterpret_cast<const int*>(P.jobs);
+        int* dst = reinterpret_cast<int*>(sjobs);
+        for (int i = tid; i < words; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    const int* rix = nullptr;
+    if (P.perm) {                                              // MNISTDataset::get_batch as an index (src/data/mnist.rs:276-309)
+        const int start = __ldcg(P.cursor);
+        for (int r = tid; r < P.batch; r += kThreads) ridx[r] = __ldg(P.perm + (start + r) % P.n_perm);
+        rix = ridx;
+    }
+    AdamArgs aa{};
+    int t_new = 0;
+    if (P.opt_kind != 0) {                                     // Adam::step prologue (src/optim.rs:86-90), as adam_advance_kernel
+        const float* h = P.hyper;
+        t_new = __float_as_int(__ldcg(h + H_T)) + 1;
+        const float lr = __ldcg(h + H_LR), b1 = __ldcg(h + H_B1), b2 = __ldcg(h + H_B2), wd = __ldcg(h + H_WD);
+        const float bc1 = 1.0f - powi_dev(b1, t_new);
+        const float bc2 = 1.0f - powi_dev(b2, t_new);
+        aa.step_size = lr * (sqrtf(bc2) / bc1);
+        aa.beta1 = b1; aa.beta2 = b2; aa.eps = __ldcg(h + H_EPS);
+        aa.decay_factor = 1.0f - lr * wd;
+        const int decoupled = P.opt_kind == 2;
+        aa.weight_decay = decoupled ? 0.0f : wd;
+        aa.decoupled = (decoupled && wd > 0.0f) ? 1 : 0;
+        aa.grad_scale = P.grad_scale;
+    }
+    unsigned int gen = 0;
+    if (tid == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(P.bar + 1) : "memory");
+    __syncthreads();
+    TP_PROF(1);
+
+    for (int ph = 0; ph < P.n_phases; ++ph) {
+        const int j0 = P.phase_first[ph], j1 = P.phase_first[ph + 1];
+        int total = 0;
+        for (int q = j0; q < j1; ++q) total += sjobs[q].items;
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            int q = j0, local = item;
+            while (local >= sjobs[q].items) { local -= sjobs[q].items; ++q; }
+            const Job& j = sjobs[q];
+            switch (j.kind) {
+                case JOB_GEMM:
+                    if (j.a_kc && j.b_kc) gemm_item<true, true>(j, local, P, rix, As, Bs, s_flag);
+                    else if (j.a_kc) gemm_item<true, false>(j, local, P, rix, As, Bs, s_flag);
+                    else gemm_item<false, false>(j, local, P, rix, As, Bs, s_flag);
+                    break;
+                case JOB_HEAD: head_item(j, local, P, rix); break;
+                case JOB_LOSS: loss_item(j, red); break;
+                default: opt_item(j, local, P, aa); break;
+            }
+        }
+        TP_PROF(2 + 2 * ph);
+        if (ph + 1 < P.n_phases) grid_sync(P.bar, gen, P.err);
+        TP_PROF(3 + 2 * ph);
+    }
+#undef TP_PROF
+    if (blockIdx.x == 0 && tid == 0) {
+        // every CTA read the cursor and the optimizer state before the first barrier
+        if (P.perm) *P.cursor = (int)(((long long)*P.cursor + P.batch) % P.n_perm);
+        if (P.opt_kind != 0) {
+            P.hyper[H_T] = __int_as_float(t_new);
+            P.hyper[H_SS] = aa.step_size;
+            P.hyper[H_DECAY] = aa.decay_factor;
+        }
+    }
+}
+
+size_t smem_bytes(int n_jobs, int batch) {
+    return (size_t)(4 * SK * LDS + 16 + 4) * sizeof(float) + (size_t)n_jobs * sizeof(Job) + (size_t)batch * sizeof(int) + 16;
+}
+
+}  // namespace
+
+struct tp_step {
+    tp_ctx* ctx = nullptr;
+    tp_step_desc desc{};
+    StepParams params{};
+    std::vector<Job> jobs;
+    void* dev_block = nullptr;       // one allocation: job list, barrier, tickets, scratch
+    size_t dev_bytes = 0;
+    int grid = 0;
+    size_t smem = 0;
+    tp_buf *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr, *hyper = nullptr, *result = nullptr;
+    long long* prof = nullptr;
+};
+
+namespace {
+
+struct Carver {                      // bump allocator over one device block (two passes: size, then assign)
+    unsigned char* base = nullptr;
+    size_t off = 0;
+    template <typename T> T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+double step_flops(const tp_step_desc* d) {
+    double f = 0.0;
+    for (int l = 0; l < d->n_layers; ++l) f += 2.0 * d->batch * (double)d->dims[l] * d->dims[l + 1];
+    return 3.0 * f;
+}
+
+bool desc_ok(const tp_step_desc* d, const char** why) {
+    auto no = [&](const char* w) { if (why) *why = w; return false; };
+    if (!d) return no("NULL descriptor");
+    if (d->n_layers < 1 || d->n_layers > TP_STEP_MAX_LAYERS) return no("layer count");
+    if (d->batch < 1 || d->batch > kMaxBatch) return no("batch size");
+    if (d->optimizer < 0 || d->optimizer > 2) return no("optimizer kind");
+    const int L = d->n_layers;
+    if (d->dims[L] < 1 || d->dims[L] > kMaxOut) return no("classifier wider than 16");
+    for (int l = 0; l < L; ++l) {
+        if (d->dims[l] < 4 || d->dims[l] % 4) return no("feature width not a multiple of 4");
+        if (d->dims[l] > 4096) return no("feature width > 4096");
+        if (d->w_off[l] % 4 || (d->b_off[l] >= 0 && d->b_off[l] % 4)) return no("parameter slice not 16-byte aligned");
+    }
+    if (d->arena_len % 4) return no("arena length not a multiple of 4");
+    if (step_flops(d) > 1.5e9) return no("step too large: the tcgen05 GEMM path is faster");
+    return true;
+}
+
+// Build the job list.  Pass 1 (c.base == NULL) only sizes the device block.
+void build(tp_step* s, Carver& c, int sms) {
+    const tp_step_desc& d = s->desc;
+    const int L = d.n_layers, B = d.batch;
+    float* P = s->p->ptr;
+    float* G = s->g->ptr;
+    s->jobs.clear();
+    StepParams& sp = s->params;
+    int ph = 0;
+    auto begin_phase = [&]() { sp.phase_first[ph++] = (int)s->jobs.size(); };
+    auto pick_splits = [&](Job& j, int share) {
+        const int tiles = j.tiles_m * j.tiles_n;
+        int splits = share / tiles;
+        if (splits < 1) splits = 1;
+        int maxs = j.K / 32;
+        if (maxs < 1) maxs = 1;
+        if (splits > maxs) splits = maxs;
+        int kchunk = ((j.K + splits - 1) / splits + BK - 1) / BK * BK;
+        j.kchunk = kchunk;
+        j.splits = (j.K + kchunk - 1) / kchunk;
+        j.items = tiles * j.splits;
+        j.tickets = c.take<int>(tiles);
+        if (j.splits > 1) {
+            j.partial = c.take<float>((size_t)j.splits * j.tiles_m * BM * j.N);
+            if (j.colsum) j.cs_partial = c.take<float>((size_t)j.splits * j.tiles_m * BM);
+        }
+    };
+    auto gemm = [&](int M, int N, int K) {
+        Job j{};
+        j.kind = JOB_GEMM;
+        j.M = M; j.N = N; j.K = K; j.m_store = M;
+        j.tiles_m = (M + BM - 1) / BM; j.tiles_n = (N + BN - 1) / BN;
+        return j;
+    };
+    // activations act[l] = output of hidden layer l  [B, dims[l+1]];  dz[l] = gradient w.r.t. its pre-activation
+    std::vector<float*> act(L, nullptr), dz(L, nullptr);
+    for (int l = 0; l + 1 < L; ++l) {
+        act[l] = c.take<float>((size_t)B * d.dims[l + 1]);
+        dz[l] = c.take<float>((size_t)B * d.dims[l + 1]);
+    }
+    float* dlog = c.take<float>((size_t)B * kMaxOut);
+    float* nll = c.take<float>(B);
+    float* hit = c.take<float>(B);
+
+    // ---- forward: hidden layers (Linear::forward src/nn.rs:54-60 [+ ReLU src/ops.rs:312-349]) -----------------------
+    for (int l = 0; l + 1 < L; ++l) {
+        begin_phase();
+        Job j = gemm(B, d.dims[l + 1], d.dims[l]);
+        j.a_kc = 1; j.b_kc = 1;
+        if (l == 0) j.a_input = 1; else j.A = act[l - 1];
+        j.lda = d.dims[l];
+        j.B = P + d.w_off[l]; j.ldb = d.dims[l];
+        j.C = act[l]; j.ldc = d.dims[l + 1];
+        j.bias = d.b_off[l] >= 0 ? P + d.b_off[l] : nullptr;
+        j.relu = d.relu[l];
+        pick_splits(j, sms);
+        s->jobs.push_back(j);
+    }
+    // ---- head ----------------------------------------------------------------------------------------------------------
+    {
+        begin_phase();
+        Job j{};
+        j.kind = JOB_HEAD;
+        j.M = B; j.K = d.dims[L - 1]; j.N = d.dims[L];
+        if (L == 1) j.a_input = 1; else j.A = act[L - 2];
+        j.lda = d.dims[L - 1];
+        j.B = P + d.w_off[L - 1];
+        j.bias = d.b_off[L - 1] >= 0 ? P + d.b_off[L - 1] : nullptr;
+        j.dlog = dlog; j.nll = nll; j.hit = hit;
+        j.inv_b = 1.0f / (float)B;
+        if (L >= 2) { j.dz = dz[L - 2]; j.dz_mask = d.relu[L - 2]; }
+        j.items = (B + kHeadRows - 1) / kHeadRows;
+        s->jobs.push_back(j);
+    }
+    // ---- backward phases -------------------------------------------------------------------------------------------------
+    // layer l (from the head down): dW_l = dZ_l^T . A_{l-1} with db_l = colsum(dZ_l) riding along (src/ops.rs:280-291,
+    // src/tensor.rs:680-691) and, for hidden layers l > 0, dZ_{l-1} = (dZ_l . W_l) * [A_{l-1} > 0] (src/ops.rs:254-265,
+    // 358-370).  The head's dX comes out of the head job, so the head's dW shares a phase with layer L-2's jobs.
+    std::vector<Job> pending;
+    auto flush_phase = [&]() {
+        if (pending.empty()) return;
+        begin_phase();
+        int tiles_total = 0;
+        for (auto& j : pending) if (j.kind == JOB_GEMM) tiles_total += j.tiles_m * j.tiles_n;
+        for (auto& j : pending) {
+            if (j.kind == JOB_GEMM) {
+                int share = (int)((long long)sms * (j.tiles_m * j.tiles_n) / tiles_total);
+                pick_splits(j, share);
+            }
+            s->jobs.push_back(j);
+        }
+        pending.clear();
+    };
+    for (int l = L - 1; l >= 0; --l) {
+        const bool head = (l == L - 1);
+        const int out = d.dims[l + 1], in = d.dims[l];
+        {
+            Job j = gemm(head ? kMaxOut : out, in, B);
+            j.m_store = out;
+            j.a_kc = 0; j.b_kc = 0;
+            j.A = head ? dlog : dz[l]; j.lda = head ? kMaxOut : out;
+            if (l == 0) j.b_input = 1; else j.B = act[l - 1];
+            j.ldb = in;
+            j.C = G + d.w_off[l]; j.ldc = in;
+            j.colsum = d.b_off[l] >= 0 ? G + d.b_off[l] : nullptr;
+            pending.push_back(j);
+        }
+        if (l > 0 && !head) {
+            Job j = gemm(B, in, out);
+            j.a_kc = 1; j.b_kc = 0;
+            j.A = dz[l]; j.lda = out;
+            j.B = P + d.w_off[l]; j.ldb = in;
+            j.C = dz[l - 1]; j.ldc = in;
+            if (d.relu[l - 1]) { j.mask = act[l - 1]; j.ldmask = in; }
+            pending.push_back(j);
+        }
+        if (head) {
+            Job j{};
+            j.kind = JOB_LOSS;
+            j.items = 1;
+            j.M = B; j.nll = nll; j.hit = hit; j.result = s->result->ptr;
+            pending.push_back(j);
+            if (L >= 2) continue;                              // layer L-2's jobs only need the head job's outputs too
+        }
+        flush_phase();
+    }
+    flush_phase();
+    // ---- optimizer (src/optim.rs:21-33, 83-113, 148-168) over the flat arena ----------------------------------------------
+    {
+        begin_phase();
+        Job j{};
+        j.kind = JOB_OPT;
+        j.p = P; j.g = G;
+        j.m = s->m ? s->m->ptr : nullptr;
+        j.v = s->v ? s->v->ptr : nullptr;
+        j.n4 = (int)(d.arena_len / 4);
+        j.items = (j.n4 + kThreads - 1) / kThreads;
+        s->jobs.push_back(j);
+    }
+    sp.phase_first[ph] = (int)s->jobs.size();
+    sp.n_phases = ph;
+    sp.n_jobs = (int)s->jobs.size();
+    sp.bar = c.take<unsigned int>(4);
+    sp.jobs = c.take<Job>(s->jobs.size());
+}
+
+}  // namespace
+
+extern "C" {
+
+int tp_step_supported(const tp_step_desc* desc) {
+    const char* why = nullptr;
+    return desc_ok(desc, &why) ? 1 : 0;
+}
+
+int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v, tp_buf* hyper,
+                   tp_buf* result, tp_step** out) {
+    TP_CHECK_ARG(ctx && out, "tp_step_create: NULL argument");
+    const char* why = nullptr;
+    TP_CHECK_ARG(desc_ok(desc, &why), "tp_step_create: unsupported step (%s)", why ? why : "?");
+    TP_NEED(params, desc->arena_len, "params"); TP_NEED(grads, desc->arena_len, "grads"); TP_NEED(result, 2, "result");
+    if (desc->optimizer != 0) {
+        TP_NEED(m, desc->arena_len, "m"); TP_NEED(v, desc->arena_len, "v"); TP_NEED(hyper, H_COUNT, "hyper");
+    }
+    TP_CHECK_ARG(!(((uintptr_t)params->ptr | (uintptr_t)grads->ptr | (uintptr_t)(m ? m->ptr : nullptr) | (uintptr_t)(v ? v->ptr : nullptr)) & 15),
+                 "tp_step_create: arenas must be 16-byte aligned");
+    TP_CHECK_ARG(!ctx->capturing, "tp_step_create: not inside a graph capture");
+    cudaSetDevice(ctx->device);
+    const int L = desc->n_layers;
+    for (int l = 0; l < L; ++l) {
+        size_t wn = (size_t)desc->dims[l] * desc->dims[l + 1];
+        TP_CHECK_ARG((int64_t)(desc->w_off[l] + wn) <= desc->arena_len, "tp_step_create: weight %d outside the arena", l);
+        TP_CHECK_ARG(desc->b_off[l] < 0 || desc->b_off[l] + desc->dims[l + 1] <= desc->arena_len,
+                     "tp_step_create: bias %d outside the arena", l);
+    }
+    tp_step* s = new tp_step();
+    s->ctx = ctx;
+    s->desc = *desc;
+    s->p = params; s->g = grads; s->m = m; s->v = v; s->hyper = hyper; s->result = result;
+    for (tp_buf* b : {params, grads, m, v, hyper, result}) if (b) tp_buf_retain(b);
+    auto fail = [&](int rc) { tp_step_destroy(s); return rc; };
+    Carver sizing;
+    build(s, sizing, ctx->sm_count);
+    if ((int)s->jobs.size() > kMaxJobs || s->params.n_phases > kMaxPhases) {
+        tp::set_error("tp_step_create: model too deep for the fused step (%zu jobs)", s->jobs.size());
+        return fail(TP_ERR_UNSUPPORTED);
+    }
+    s->dev_bytes = sizing.off + 256;
+    if (cudaMalloc(&s->dev_block, s->dev_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        tp::set_error("tp_step_create: cudaMalloc(%zu) failed", s->dev_bytes);
+        return fail(TP_ERR_OOM);
+    }
+    if (cudaMemsetAsync(s->dev_block, 0, s->dev_bytes, ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);
+    Carver place;
+    place.base = (unsigned char*)s->dev_block;
+    build(s, place, ctx->sm_count);
+    if (cudaMemcpyAsync((void*)s->params.jobs, s->jobs.data(), s->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return fail(TP_ERR_CUDA);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);      // s->jobs is pageable host memory
+    s->params.batch = desc->batch;
+    s->params.opt_kind = desc->optimizer;
+    s->params.hyper = hyper ? hyper->ptr : nullptr;
+    s->params.err = ctx->dev_error;
+    s->smem = smem_bytes((int)s->jobs.size(), desc->batch);
+    if (cudaFuncSetAttribute(tape_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem) != cudaSuccess) {
+        cudaGetLastError();
+        tp::set_error("tp_step_create: %zu bytes of shared memory not available", s->smem);
+        return fail(TP_ERR_CUDA);
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tape_step_kernel, kThreads, s->smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        tp::set_error("tp_step_create: the step kernel does not fit on an SM");
+        return fail(TP_ERR_CUDA);
+    }
+    int max_items = 1;
+    for (int ph = 0; ph < s->params.n_phases; ++ph) {
+        int t = 0;
+        for (int q = s->params.phase_first[ph]; q < s->params.phase_first[ph + 1]; ++q) t += s->jobs[q].items;
+        if (t > max_items) max_items = t;
+    }
+    s->grid = ctx->sm_count < max_items ? ctx->sm_count : max_items;
+    *out = s;
+    return TP_OK;
+}
+
+int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32, tp_buf* cursor_i32,
+                int n_perm, float sgd_lr, float grad_scale) {
+    TP_CHECK_ARG(ctx && s && s->ctx == ctx, "tp_step_run: NULL or foreign step");
+    TP_CHECK_ARG(!ctx->capturing, "tp_step_run: a cooperative launch cannot be captured into a CUDA graph");
+    const int in = s->desc.dims[0];
+    StepParams p = s->params;
+    if (perm_i32) {
+        TP_CHECK_ARG(n_perm > 0, "tp_step_run: empty dataset");
+        TP_NEED(x, (size_t)n_perm * in, "images"); TP_NEED(labels, n_perm, "labels"); TP_NEED(perm_i32, n_perm, "perm");
+        TP_NEED(cursor_i32, 1, "cursor");
+        p.perm = (const int*)perm_i32->ptr; p.cursor = (int*)cursor_i32->ptr; p.n_perm = n_perm;
+    } else {
+        TP_NEED(x, (size_t)s->desc.batch * in, "x"); TP_NEED(labels, s->desc.batch, "labels");
+        p.perm = nullptr; p.cursor = nullptr; p.n_perm = 0;
+    }
+    TP_CHECK_ARG(!((uintptr_t)x->ptr & 15), "tp_step_run: input rows must be 16-byte aligned");
+    p.x = x->ptr; p.labels = labels->ptr;
+    p.sgd_lr = sgd_lr; p.grad_scale = grad_scale;
+    cudaSetDevice(ctx->device);
+    void* args[] = {(void*)&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)tape_step_kernel, dim3(s->grid), dim3(kThreads), args, s->smem, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        tp::set_error("tp_step_run: cooperative launch failed: %s", cudaGetErrorString(e));
+        return TP_ERR_CUDA;
+    }
+    ctx->launches++;
+    return TP_OK;
+}
+
+int tp_step_set_profile(tp_step* s, int on) {
+    TP_CHECK_ARG(s, "tp_step_set_profile: NULL step");
+    cudaSetDevice(s->ctx->device);
+    if (on && !s->prof) {
+        size_t bytes = (size_t)s->grid * kProfSlots * sizeof(long long);
+        TP_CUDA(cudaMalloc(&s->prof, bytes));
+        TP_CUDA(cudaMemsetAsync(s->prof, 0, bytes, s->ctx->stream));
+    }
+    s->params.prof = on ? s->prof : nullptr;
+    return TP_OK;
+}
+
+int tp_step_read_profile(tp_step* s, int64_t* out, size_t cap, int* slots) {
+    TP_CHECK_ARG(s && s->prof && out && cap >= (size_t)s->grid * kProfSlots, "tp_step_read_profile: profiling is off or the buffer is too small");
+    cudaSetDevice(s->ctx->device);
+    TP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    TP_CUDA(cudaMemcpy(out, s->prof, (size_t)s->grid * kProfSlots * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (slots) *slots = kProfSlots;
+    return TP_OK;
+}
+
+int tp_step_info(const tp_step* s, int* n_phases, int* n_jobs, int* grid) {
+    TP_CHECK_ARG(s, "tp_step_info: NULL step");
+    if (n_phases) *n_phases = s->params.n_phases;
+    if (n_jobs) *n_jobs = s->params.n_jobs;
+    if (grid) *grid = s->grid;
+    return TP_OK;
+}
+
+int tp_step_destroy(tp_step* s) {
+    if (!s) return TP_OK;
+    if (s->ctx) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+    }
+    if (s->dev_block) cudaFree(s->dev_block);
+    if (s->prof) cudaFree(s->prof);
+    for (tp_buf* b : {s->p, s->g, s->m, s->v, s->hyper, s->result}) if (b) tp_buf_release(b);
+    delete s;
+    return TP_OK;
+}
+
+}  // extern "C"

@@ -239,6 +239,14 @@ class Trainer:
     def broadcast_params(self, root=0):
         check(lib.tp_trainer_broadcast_params(self.h, root))
 
+    def set_use_fused(self, on):
+        check(lib.tp_trainer_set_use_fused(self.h, int(bool(on))))
+
+    def fused_steps(self) -> int:
+        c = C.c_uint64()
+        check(lib.tp_trainer_fused_steps(self.h, C.byref(c)))
+        return c.value
+
     def graph_replays(self) -> int:
         c = C.c_uint64()
         check(lib.tp_trainer_graph_replays(self.h, C.byref(c)))

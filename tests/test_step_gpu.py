@@ -83,11 +83,15 @@ def oracle_opt(kind, params, lr, wd, eps=None):
     return R.AdamW(params, lr, None, eps, wd)
 
 
-def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=None, tol=1e-4, use_graph=True, seed=0, eps=None):
+def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=None, tol=1e-4, use_graph=True, seed=0, eps=None,
+               fused=False):
+    """fused=False: tape + CUDA-graph path (one kernel per op); fused=True: the device tape (tp_step_*, one persistent
+    kernel per step) where the model qualifies."""
     from taper_b200 import host
     ref, m = make_pair(builder, spec, seed)
     tr = host.Trainer(m, kind, lr=lr, weight_decay=wd, eps=1e-8 if eps is None else eps)
     tr.set_use_graph(use_graph)
+    tr.set_use_fused(fused)
     opt = oracle_opt(kind, ref.parameters(), lr, wd, eps)
     rng = np.random.default_rng(seed + 1)
     for i, (x, y) in enumerate(batches(rng, steps, batch, sample_shape, ragged)):
@@ -119,12 +123,27 @@ def test_cfg1_mlp_sgd_b64(gemm_mode):
     run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "sgd", 0.01, 0.0, 64, (784,), 12, ragged=32)
 
 
+def test_cfg1_mlp_sgd_b64_fused():
+    from taper_b200 import host
+    tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "sgd", 0.01, 0.0, 64, (784,), 12, ragged=32,
+                       fused=True)
+    assert tr.fused_steps() == 12 and tr.graph_replays() == 0
+
+
 # ---- cfg2: same MLP, batch 512, Adam ---------------------------------------------------------------------------
 @pytest.mark.parametrize("wd", [0.0, 1e-4])
 def test_cfg2_mlp_adam_b512(wd):
     from taper_b200 import host
     tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "adam", 1e-3, wd, 512, (784,), 8, ragged=96)
     assert tr.graph_replays() >= 5             # steps 3.. of the B=512 shape ran as CUDA-graph replays
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-4])
+def test_cfg2_mlp_adam_b512_fused(wd):
+    from taper_b200 import host
+    tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "adam", 1e-3, wd, 512, (784,), 8, ragged=96,
+                       fused=True)
+    assert tr.fused_steps() == 8 and tr.graph_replays() == 0
 
 
 @pytest.mark.parametrize("kind,wd", [("adam", 0.0), ("adam", 1e-4), ("adamw", 1e-2)])
@@ -135,6 +154,15 @@ def test_cfg2_mlp_adam_large_eps_tight(kind, wd):
     tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, kind, 0.1, wd, 512, (784,), 10,
                        ragged=96, eps=0.1)
     assert tr.graph_replays() >= 7
+
+
+@pytest.mark.parametrize("kind,wd", [("adam", 0.0), ("adam", 1e-4), ("adamw", 1e-2), ("sgd", 0.0)])
+def test_cfg2_mlp_large_eps_tight_fused(kind, wd):
+    """The same free-running loop through the device tape: exact fp32 FMA products, so the plain 1e-4 bound with room."""
+    from taper_b200 import host
+    tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, kind, 0.1 if kind != "sgd" else 0.05, wd, 512,
+                       (784,), 10, ragged=96, eps=0.1, fused=True)
+    assert tr.fused_steps() == 10
 
 
 def test_cfg4_mlp_wide_adam_large_eps_tight():
@@ -155,6 +183,7 @@ def test_cfg2_eager_equals_graph_bitwise():
         _, m = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 5)
         tr = host.Trainer(m, "adam", lr=1e-3)
         tr.set_use_graph(use_graph)
+        tr.set_use_fused(False)
         losses = [tr.step(x, y) for x, y in data]
         outs.append((losses, [m.get_param(i) for i in range(m.num_params())]))
     assert outs[0][0] == outs[1][0]
@@ -162,9 +191,73 @@ def test_cfg2_eager_equals_graph_bitwise():
         np.testing.assert_array_equal(a, b)
 
 
-def test_example_mlp_adam_wd_b256():            # examples/train_mnist.rs:28-61: 784-128-64-10, Adam(1e-3, wd 1e-4), B=256
+@pytest.mark.parametrize("fused", [False, True])
+def test_example_mlp_adam_wd_b256(fused):       # examples/train_mnist.rs:28-61: 784-128-64-10, Adam(1e-3, wd 1e-4), B=256
     from taper_b200 import host
-    run_parity(lambda r: R.build_mlp([784, 128, 64, 10], r), host.MLP_EXAMPLE, "adam", 1e-3, 1e-4, 256, (784,), 6, ragged=96)
+    tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 64, 10], r), host.MLP_EXAMPLE, "adam", 1e-3, 1e-4, 256, (784,), 6, ragged=96,
+                       fused=fused)
+    assert tr.fused_steps() == (6 if fused else 0)
+
+
+@pytest.mark.parametrize("dims,spec,batch", [
+    ([784, 10], "linear:784:10", 200),                                                       # softmax regression: head only
+    ([784, 64, 32, 16, 10], "linear:784:64,relu,linear:64:32,relu,linear:32:16,relu,linear:16:10", 130),
+    ([100, 36, 12], "linear:100:36,relu,linear:36:12", 77),                                  # ragged tiles everywhere
+])
+def test_fused_step_other_chains_large_eps_tight(dims, spec, batch):
+    from taper_b200 import host
+    rng0 = np.random.default_rng(21)
+    in_f = dims[0]
+    ref, m = make_pair(lambda r: R.build_mlp(dims, r), spec, 4)
+    tr = host.Trainer(m, "adam", lr=0.05, weight_decay=1e-3, eps=0.1)
+    opt = R.Adam(ref.parameters(), 0.05, None, 0.1, 1e-3)
+    for i in range(6):
+        x = rng0.random((batch, in_f)).astype(F32)
+        y = rng0.integers(0, dims[-1], batch).astype(F32)
+        loss_ref, _ = R.train_step(ref, opt, R.Tensor.new(x, x.shape), R.Tensor.new(y, y.shape))
+        loss, _ = tr.step(x, y)
+        assert abs(loss - loss_ref) <= 1e-4 * abs(loss_ref), (i, loss, loss_ref)
+    assert tr.fused_steps() == 6
+    for j, p in enumerate(ref.parameters()):
+        close(m.get_param(j), p.data(), 1e-4, f"param {j}")
+
+
+def test_fused_step_falls_back_when_model_does_not_qualify():
+    """No ReLU-free classifier tail / too much work per step: the trainer silently keeps the tape + graph path."""
+    from taper_b200 import host
+    rng = np.random.default_rng(2)
+    m = host.Model("linear:784:128,relu,linear:128:10,relu", 0)             # ends in a ReLU: not a classifier chain
+    tr = host.Trainer(m, "adam", lr=1e-3)
+    x = rng.random((64, 784)).astype(F32); y = rng.integers(0, 10, 64).astype(F32)
+    for _ in range(3):
+        tr.step(x, y)
+    assert tr.fused_steps() == 0 and tr.graph_replays() >= 1
+    m2 = host.Model(host.MLP_784_1024_1024_10, 0)                            # 9.8 GFLOP per step: tcgen05 GEMM path
+    tr2 = host.Trainer(m2, "adam", lr=1e-3)
+    x = rng.random((1024, 784)).astype(F32); y = rng.integers(0, 10, 1024).astype(F32)
+    for _ in range(3):
+        tr2.step(x, y)
+    assert tr2.fused_steps() == 0
+
+
+def test_fused_step_matches_graph_path_closely():
+    """Device tape vs one-kernel-per-op path (exact-fp32 GEMM mode) on the same data: same algorithm, different summation
+    order only."""
+    from taper_b200 import host
+    host.config(gemm_mode=0)
+    rng = np.random.default_rng(3)
+    data = list(batches(rng, 6, 512, (784,)))
+    outs = []
+    for fused in (False, True):
+        _, m = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 5)
+        tr = host.Trainer(m, "adam", lr=0.05, eps=0.1)
+        tr.set_use_fused(fused)
+        losses = [tr.step(x, y) for x, y in data]
+        outs.append((losses, [m.get_param(i) for i in range(m.num_params())]))
+    for (la, ca), (lb, cb) in zip(outs[0][0], outs[1][0]):
+        assert abs(la - lb) <= 2e-6 * abs(la) and ca == cb
+    for a, b in zip(outs[0][1], outs[1][1]):
+        close(b, a, 1e-5)
 
 
 def test_cfg4_mlp_wide_adam_b1024():
@@ -317,7 +410,9 @@ def test_cnn_forward_only_matches_oracle():
 
 
 # ---- device-resident dataset path == host-fed path -------------------------------------------------------------------
-def test_resident_dataset_gather_equals_host_batches():
+@pytest.mark.parametrize("fused", [False, True])
+def test_resident_dataset_gather_equals_host_batches(fused):
+    """fused=True: rows are gathered inside the step kernel through perm + cursor; fused=False: tp_gather_batch."""
     from taper_b200 import host
     rng = np.random.default_rng(9)
     n, b = 1000, 128
@@ -327,6 +422,7 @@ def test_resident_dataset_gather_equals_host_batches():
     _, m1 = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 1)
     _, m2 = make_pair(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, 1)
     t1, t2 = host.Trainer(m1, "adam", lr=1e-3), host.Trainer(m2, "adam", lr=1e-3)
+    t1.set_use_fused(fused); t2.set_use_fused(fused)
     t2.load_dataset(X, Y, perm)
     for s in range(12):                          # wraps around the dataset (cursor modulo n)
         idx = perm[(s * b + np.arange(b)) % n]
@@ -336,6 +432,7 @@ def test_resident_dataset_gather_equals_host_batches():
         assert r1 == r2, f"step {s}: {r1} vs {r2}"
     for i in range(4):
         np.testing.assert_array_equal(m1.get_param(i), m2.get_param(i))
+    assert t2.fused_steps() == (12 if fused else 0)
 
 
 def test_async_pipeline_fifo_results():
