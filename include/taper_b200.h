@@ -290,6 +290,9 @@ int tp_cursor_advance(tp_ctx*, tp_buf* cursor_i32, int delta, int modulo);
  *   tp_step_run       : perm_i32 == NULL: x [batch,in] / labels [batch] are the batch (host-fed);
  *                       otherwise x / labels are the resident dataset [n_perm,...] and rows
  *                       perm[(cursor + r) % n_perm] are gathered in-kernel; cursor advances by batch.
+ *                       cursor_value >= 0 is the caller's mirror of *cursor (saves the kernel a dependent
+ *                       load), -1 reads the device word.  result_host (optional) is a pinned, device-
+ *                       mapped {loss, correct} slot the kernel also writes, so no separate D2H copy is needed.
  *                       Writes result = {loss, #correct}; Adam state (hyper, see tp_adam_hyper_init)
  *                       advances on the device exactly as tp_adam_advance + tp_adam_step_dev would.
  * ------------------------------------------------------------------------------------------- */
@@ -304,12 +307,14 @@ typedef struct tp_step_desc {
     int64_t w_off[TP_STEP_MAX_LAYERS];       /* offset of W_l [out,in] in the flat arenas           */
     int64_t b_off[TP_STEP_MAX_LAYERS];       /* offset of b_l [out], or -1 if the layer has no bias */
     int64_t arena_len;                       /* elements in params / grads / m / v                  */
+    int materialize_grads;                   /* 1: leave the folded gradients in the grads arena (needed by a gradient
+                                                exchange); 0: the optimizer phase sums the split-K partials itself     */
 } tp_step_desc;
 int tp_step_supported(const tp_step_desc* desc);
 int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v,
                    tp_buf* hyper, tp_buf* result, tp_step** out);
 int tp_step_run(tp_ctx* ctx, tp_step* step, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32,
-                tp_buf* cursor_i32, int n_perm, float sgd_lr, float grad_scale);
+                tp_buf* cursor_i32, int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host);
 int tp_step_info(const tp_step* step, int* n_phases, int* n_jobs, int* grid);
 /* per-CTA SM-clock stamps of the last run: [grid][slots] = entry, setup done, then {work done, barrier passed}
  * for each phase (evidence for profiles/: where the step's time goes) */

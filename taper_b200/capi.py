@@ -38,7 +38,7 @@ class StepDesc(C.Structure):
     """tp_step_desc (include/taper_b200.h): a chain of Linear(+ReLU) layers + classifier head + optimizer."""
     MAX_LAYERS = 8
     _fields_ = [("n_layers", C.c_int), ("dims", C.c_int * 9), ("relu", C.c_int * 8), ("batch", C.c_int), ("optimizer", C.c_int),
-                ("w_off", C.c_int64 * 8), ("b_off", C.c_int64 * 8), ("arena_len", C.c_int64)]
+                ("w_off", C.c_int64 * 8), ("b_off", C.c_int64 * 8), ("arena_len", C.c_int64), ("materialize_grads", C.c_int)]
 
 
 _OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step")

@@ -169,9 +169,13 @@ struct Trainer::Impl {
         return st;
     }
 
-    void enqueue_result() {
+    size_t ds_cursor_host = 0;                               // host mirror of the device cursor
+
+    float* next_result_slot() const { return ring + 2 * (head % kRing); }
+    // in_kernel: the step kernel already wrote {loss, correct} into next_result_slot() (mapped pinned memory)
+    void enqueue_result(bool in_kernel = false) {
         size_t i = head % kRing;
-        check(tp_buf_download_async(ctx(), result.buf(), ring + 2 * i, 2));
+        if (!in_kernel) check(tp_buf_download_async(ctx(), result.buf(), ring + 2 * i, 2));
         check(tp_event_record(ctx(), events[i]));
         head++;
     }
@@ -313,14 +317,14 @@ void Trainer::train_batch_async(const float* images, const float* labels, size_t
     }
     if (fs) {
         // the whole loop body (src/train.rs:106-138) as one persistent kernel walking the compiled tape
-        check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, optimizer->lr(), optimizer->grad_scale()));
+        check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, -1, optimizer->lr(), optimizer->grad_scale(), p.next_result_slot()));
         if (pinned) {
             check(tp_event_record(c, s.done[k]));
             s.done_valid[k] = true;
         }
         optimizer->note_device_step();
         fused_steps_++;
-        p.enqueue_result();
+        p.enqueue_result(true);
         return;
     }
     if (s.graph) {
@@ -381,6 +385,7 @@ void Trainer::load_dataset(const float* images, const float* labels, size_t n, c
     check(tp_buf_upload(c, p.ds_perm, perm, n));
     check(tp_buf_fill(c, p.ds_cursor, 0.0f, 1));
     p.ds_n = n;
+    p.ds_cursor_host = 0;
     p.ds_sample = sample_shape;
 }
 
@@ -390,13 +395,15 @@ void Trainer::train_batch_resident(size_t batch) {
     if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
     if (tp_step* fst = use_fused_ ? p.fused_step(*this, batch, p.ds_sample) : nullptr) {
         // batch rows are gathered out of the resident dataset inside the step kernel; the cursor advances there too
-        check(tp_step_run(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, optimizer->lr(),
-                          optimizer->grad_scale()));
+        check(tp_step_run(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, (int)p.ds_cursor_host,
+                          optimizer->lr(), optimizer->grad_scale(), p.next_result_slot()));
+        p.ds_cursor_host = (p.ds_cursor_host + batch) % p.ds_n;
         optimizer->note_device_step();
         fused_steps_++;
-        p.enqueue_result();
+        p.enqueue_result(true);
         return;
     }
+    p.ds_cursor_host = (p.ds_cursor_host + batch) % p.ds_n;
     Shape fs = full_shape(batch, p.ds_sample);
     Slot& s = p.slots[fs];
     if (!s.x.defined()) {

@@ -21,7 +21,7 @@ constexpr int kThreads = 256;
 constexpr int BM = 64, BN = 64, BK = 16, LDS = BM + 4;        // smem tile row pitch (floats)
 constexpr int SUB = 4, SK = SUB * BK;                          // a pipeline stage = 4 sub-tiles = 64 k: one memory round trip
 constexpr int kMaxOut = 16;
-constexpr int kMaxJobs = 32, kMaxPhases = 20;
+constexpr int kMaxJobs = 48, kMaxPhases = 20;
 constexpr int kMaxBatch = 4096;
 constexpr int kHeadRows = 8;                                   // one warp per row
 constexpr int kProfSlots = 2 + 2 * kMaxPhases;               // entry, setup done, then {work done, barrier passed} per phase
@@ -45,7 +45,13 @@ struct Job {
     float* colsum;                   // optional [M]: sum_k A(m,k)  (bias gradient rides on the dW GEMM)
     float* cs_partial;               // [splits][tiles_m*BM]
     int* tickets;                    // [tiles_m*tiles_n]
+    int defer_fold;                  // leave the split-K partials unfolded: the consumer (head / optimizer job) sums them
     // HEAD  (A = activations [M=batch, K=in], B = W [N=out, in], bias)
+    const float* a_part;             // activations still as split-K partials [a_splits][a_stride] (+ a_bias, a_relu); the head
+    int a_splits, a_relu;            //   folds them itself and materialises the rows into a_out
+    long long a_stride;
+    const float* a_bias;
+    float* a_out;
     float* dlog;                     // [batch, 16]  zero padded
     float* dz;                       // optional [batch, in]
     int dz_mask;                     // dz *= [A > 0]
@@ -53,8 +59,9 @@ struct Job {
     float inv_b;
     // LOSS: nll, hit, M -> result {loss, correct}
     float* result;
-    // OPT
+    // OPT (one job per parameter tensor): gradient = g, or the sum over g_splits partials at stride g_stride
     float* p; float* g; float* m; float* v; int n4;
+    const float* g_part; int g_splits; long long g_stride;
 };
 
 struct StepParams {
@@ -66,6 +73,8 @@ struct StepParams {
     const int* perm;                 // NULL: x / labels are the batch itself
     int* cursor;
     int n_perm, batch;
+    int cursor_value;                // host mirror of *cursor (>= 0), or -1: read the device word
+    float* result_host;              // optional mapped pinned {loss, correct} slot of this step (no separate D2H copy)
     unsigned int* bar;               // {count, generation}
     int opt_kind;                    // 0 SGD, 1 Adam, 2 AdamW
     float sgd_lr, grad_scale;
@@ -140,9 +149,10 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen, 
 }
 
 // ---- GEMM tile loader: one float4 per thread per operand per BK step ------------------------------------------------
-template <bool KC>
-__device__ __forceinline__ float4 fetch(const float* __restrict__ P, int ld, const int* __restrict__ ridx, int mn0, int mn_lim,
-                                        int k0, int kend, int tid) {
+// KC (operand stored K-contiguous or not) is a run-time, CTA-uniform flag: one copy of the multiply / epilogue / fold code
+// serves all three GEMM flavours (the kernel is instruction-fetch sensitive).
+__device__ __forceinline__ float4 fetch(const bool KC, const float* __restrict__ P, int ld, const int* __restrict__ ridx, int mn0,
+                                        int mn_lim, int k0, int kend, int tid) {
     float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (KC) {
         const int mn = mn0 + (tid >> 2), gk = k0 + ((tid & 3) << 2);
@@ -160,8 +170,7 @@ __device__ __forceinline__ float4 fetch(const float* __restrict__ P, int ld, con
     return z;
 }
 
-template <bool KC>
-__device__ __forceinline__ void stash(float* __restrict__ S, float4 v, int tid) {          // S: [BK][LDS]
+__device__ __forceinline__ void stash(const bool KC, float* __restrict__ S, float4 v, int tid) {          // S: [BK][LDS]
     if (KC) {
         const int mn = tid >> 2, kq = (tid & 3) << 2;
         S[(kq + 0) * LDS + mn] = v.x;
@@ -188,8 +197,7 @@ __device__ __forceinline__ void epilogue_store(const Job& j, int gm, int gn, flo
     *reinterpret_cast<float4*>(j.C + (size_t)gm * j.ldc + gn) = v;
 }
 
-template <bool AKC, bool BKC>
-__device__ void gemm_item(const Job& j, int item, const StepParams& P, const int* __restrict__ ridx, float* __restrict__ As,
+__device__ void gemm_item(const bool AKC, const bool BKC, const Job& j, int item, const StepParams& P, const int* __restrict__ ridx, float* __restrict__ As,
                           float* __restrict__ Bs, int* s_flag) {
     const int tid = threadIdx.x;
     const int tiles = j.tiles_m * j.tiles_n;
@@ -217,13 +225,13 @@ __device__ void gemm_item(const Job& j, int item, const StepParams& P, const int
     float4 ra4[SUB], rb4[SUB];
 #pragma unroll
     for (int u = 0; u < SUB; ++u) {
-        ra4[u] = fetch<AKC>(A, j.lda, ra, m0, j.M, kbeg + u * BK, kend, tid);
-        rb4[u] = fetch<BKC>(B, j.ldb, rb, n0, j.N, kbeg + u * BK, kend, tid);
+        ra4[u] = fetch(AKC, A, j.lda, ra, m0, j.M, kbeg + u * BK, kend, tid);
+        rb4[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, kbeg + u * BK, kend, tid);
     }
 #pragma unroll
     for (int u = 0; u < SUB; ++u) {
-        stash<AKC>(As + u * (BK * LDS), ra4[u], tid);
-        stash<BKC>(Bs + u * (BK * LDS), rb4[u], tid);
+        stash(AKC, As + u * (BK * LDS), ra4[u], tid);
+        stash(BKC, Bs + u * (BK * LDS), rb4[u], tid);
     }
     __syncthreads();
     for (int st = 0; st < ns; ++st) {
@@ -232,8 +240,8 @@ __device__ void gemm_item(const Job& j, int item, const StepParams& P, const int
         if (st + 1 < ns) {
 #pragma unroll
             for (int u = 0; u < SUB; ++u) {
-                ra4[u] = fetch<AKC>(A, j.lda, ra, m0, j.M, k0 + SK + u * BK, kend, tid);
-                rb4[u] = fetch<BKC>(B, j.ldb, rb, n0, j.N, k0 + SK + u * BK, kend, tid);
+                ra4[u] = fetch(AKC, A, j.lda, ra, m0, j.M, k0 + SK + u * BK, kend, tid);
+                rb4[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, k0 + SK + u * BK, kend, tid);
             }
         }
         const float* as = As + cur * (SK * LDS);
@@ -255,8 +263,8 @@ __device__ void gemm_item(const Job& j, int item, const StepParams& P, const int
         if (st + 1 < ns) {
 #pragma unroll
             for (int u = 0; u < SUB; ++u) {
-                stash<AKC>(As + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), ra4[u], tid);
-                stash<BKC>(Bs + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), rb4[u], tid);
+                stash(AKC, As + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), ra4[u], tid);
+                stash(BKC, Bs + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), rb4[u], tid);
             }
         }
         __syncthreads();
@@ -285,6 +293,7 @@ __device__ void gemm_item(const Job& j, int item, const StepParams& P, const int
         }
     }
     if (do_cs) j.cs_partial[(size_t)split * mpad + m0 + tid] = cs;
+    if (j.defer_fold) return;                              // folded by the consumer after the grid barrier
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -303,13 +312,16 @@ __device__ void gemm_item(const Job& j, int item, const StepParams& P, const int
         float4 s4[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) s4[a] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float* pbase = j.partial + (size_t)(m0 + ty * 4) * j.N + gn;
+        const size_t zstride = (size_t)mpad * j.N;
+#pragma unroll 1
         for (int z0 = 0; z0 < j.splits; z0 += 4) {
             float4 q[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
-                    q[u][a] = (z0 + u < j.splits) ? ldcg4(j.partial + ((size_t)(z0 + u) * mpad + m0 + ty * 4 + a) * j.N + gn)
+                    q[u][a] = (z0 + u < j.splits) ? ldcg4(pbase + (size_t)(z0 + u) * zstride + (size_t)a * j.N)
                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
             for (int u = 0; u < 4; ++u)                        // split order
@@ -346,19 +358,46 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
     const int in_f = j.K, out_f = j.N, in4 = in_f >> 2;
     const float* arow = (j.a_input ? P.x + (size_t)(ridx ? ridx[r] : r) * j.lda : j.A + (size_t)r * j.lda);
     const float* W = j.B;
+    const float* afin = j.a_part ? j.a_out + (size_t)r * in_f : arow;      // the materialised activation row
     float acc[kMaxOut];
 #pragma unroll
     for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
+    // rolled on purpose: the kernel is instruction-fetch sensitive (every CTA runs each path once, cold)
+#pragma unroll 1
     for (int c = lane; c < in4; c += 32) {
-        const float4 a = ldcg4(arow + 4 * c);
+        {
+            float4 a;
+            if (j.a_part) {
+                // the producing GEMM left its split-K partials unfolded: sum them here (split order), add bias, ReLU
+                a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float* base = j.a_part + (size_t)r * in_f + 4 * c;
+#pragma unroll 1
+                for (int z0 = 0; z0 < j.a_splits; z0 += 8) {
+                    float4 q[8];
 #pragma unroll
-        for (int o = 0; o < kMaxOut; ++o) {
-            if (o < out_f) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
-                acc[o] = fmaf(a.x, w.x, acc[o]);
-                acc[o] = fmaf(a.y, w.y, acc[o]);
-                acc[o] = fmaf(a.z, w.z, acc[o]);
-                acc[o] = fmaf(a.w, w.w, acc[o]);
+                    for (int t = 0; t < 8; ++t)
+                        q[t] = (z0 + t < j.a_splits) ? ldcg4(base + (size_t)(z0 + t) * j.a_stride) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) { a.x += q[t].x; a.y += q[t].y; a.z += q[t].z; a.w += q[t].w; }
+                }
+                if (j.a_bias) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(j.a_bias) + c);
+                    a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+                }
+                if (j.a_relu) { a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f); }
+                *reinterpret_cast<float4*>(j.a_out + (size_t)r * in_f + 4 * c) = a;
+            } else {
+                a = ldcg4(arow + 4 * c);
+            }
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o) {
+                if (o < out_f) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
+                    acc[o] = fmaf(a.x, w.x, acc[o]);
+                    acc[o] = fmaf(a.y, w.y, acc[o]);
+                    acc[o] = fmaf(a.z, w.z, acc[o]);
+                    acc[o] = fmaf(a.w, w.w, acc[o]);
+                }
             }
         }
     }
@@ -405,28 +444,31 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
         j.dlog[(size_t)r * kMaxOut + lane] = mine;
     }
     if (j.dz) {
+#pragma unroll 1
         for (int c = lane; c < in4; c += 32) {
-            float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            {
+                float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-            for (int o = 0; o < kMaxOut; ++o) {
-                if (o < out_f) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
-                    d.x = fmaf(dl[o], w.x, d.x); d.y = fmaf(dl[o], w.y, d.y);
-                    d.z = fmaf(dl[o], w.z, d.z); d.w = fmaf(dl[o], w.w, d.w);
+                for (int o = 0; o < kMaxOut; ++o) {
+                    if (o < out_f) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
+                        d.x = fmaf(dl[o], w.x, d.x); d.y = fmaf(dl[o], w.y, d.y);
+                        d.z = fmaf(dl[o], w.z, d.z); d.w = fmaf(dl[o], w.w, d.w);
+                    }
                 }
+                if (j.dz_mask) {
+                    const float4 a = ldcg4(afin + 4 * c);      // this lane wrote / read it above
+                    d.x = a.x > 0.0f ? d.x : 0.0f; d.y = a.y > 0.0f ? d.y : 0.0f;
+                    d.z = a.z > 0.0f ? d.z : 0.0f; d.w = a.w > 0.0f ? d.w : 0.0f;
+                }
+                *reinterpret_cast<float4*>(j.dz + (size_t)r * in_f + 4 * c) = d;
             }
-            if (j.dz_mask) {
-                const float4 a = ldcg4(arow + 4 * c);
-                d.x = a.x > 0.0f ? d.x : 0.0f; d.y = a.y > 0.0f ? d.y : 0.0f;
-                d.z = a.z > 0.0f ? d.z : 0.0f; d.w = a.w > 0.0f ? d.w : 0.0f;
-            }
-            *reinterpret_cast<float4*>(j.dz + (size_t)r * in_f + 4 * c) = d;
         }
     }
 }
 
 // ---- loss = sum(nll) / B, correct = sum(hit)  (fixed tree: deterministic) ----------------------------------------
-__device__ void loss_item(const Job& j, float* sm /* >= 16 floats */) {
+__device__ void loss_item(const Job& j, const StepParams& P, float* sm /* >= 16 floats */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float a = 0.0f, h = 0.0f;
     for (int r = threadIdx.x; r < j.M; r += kThreads) { a += __ldcg(j.nll + r); h += __ldcg(j.hit + r); }
@@ -437,8 +479,10 @@ __device__ void loss_item(const Job& j, float* sm /* >= 16 floats */) {
         float sa = 0.0f, sh = 0.0f;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) { sa += sm[w]; sh += sm[8 + w]; }
-        j.result[0] = sa / (float)j.M;                        // acc / b as f32 (src/loss.rs:164)
+        const float loss = sa / (float)j.M;                   // acc / b as f32 (src/loss.rs:164)
+        j.result[0] = loss;
         j.result[1] = sh;
+        if (P.result_host) { P.result_host[0] = loss; P.result_host[1] = sh; }
     }
     __syncthreads();
 }
@@ -448,7 +492,22 @@ __device__ __forceinline__ void opt_item(const Job& j, int item, const StepParam
     if (i >= j.n4) return;
     float4* p4 = reinterpret_cast<float4*>(j.p) + i;
     float4 pp = *p4;
-    float4 gg = __ldcg(reinterpret_cast<const float4*>(j.g) + i);
+    float4 gg;
+    if (j.g_part) {                                           // fold the producing GEMM's split-K partials (split order)
+        gg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float* base = j.g_part + 4 * (size_t)i;
+#pragma unroll 1
+        for (int z0 = 0; z0 < j.g_splits; z0 += 8) {
+            float4 q[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                q[t] = (z0 + t < j.g_splits) ? ldcg4(base + (size_t)(z0 + t) * j.g_stride) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { gg.x += q[t].x; gg.y += q[t].y; gg.z += q[t].z; gg.w += q[t].w; }
+        }
+    } else {
+        gg = __ldcg(reinterpret_cast<const float4*>(j.g) + i);
+    }
     if (P.opt_kind == 0) {                                    // SGD: p -= lr * g (src/optim.rs:29)
         if (P.grad_scale != 1.0f) { gg.x *= P.grad_scale; gg.y *= P.grad_scale; gg.z *= P.grad_scale; gg.w *= P.grad_scale; }
         pp.x -= P.sgd_lr * gg.x; pp.y -= P.sgd_lr * gg.y; pp.z -= P.sgd_lr * gg.z; pp.w -= P.sgd_lr * gg.w;
@@ -486,8 +545,13 @@ tape_step_kernel(const StepParams P) {
     }
     const int* rix = nullptr;
     if (P.perm) {                                              // MNISTDataset::get_batch as an index (src/data/mnist.rs:276-309)
-        const int start = __ldcg(P.cursor);
-        for (int r = tid; r < P.batch; r += kThreads) ridx[r] = __ldg(P.perm + (start + r) % P.n_perm);
+        const int start = P.cursor_value >= 0 ? P.cursor_value : __ldcg(P.cursor);
+#pragma unroll 1
+        for (int r = tid; r < P.batch; r += kThreads) {
+            int idx = start + r;
+            if (idx >= P.n_perm) idx %= P.n_perm;
+            ridx[r] = __ldg(P.perm + idx);
+        }
         rix = ridx;
     }
     AdamArgs aa{};
@@ -521,12 +585,10 @@ tape_step_kernel(const StepParams P) {
             const Job& j = sjobs[q];
             switch (j.kind) {
                 case JOB_GEMM:
-                    if (j.a_kc && j.b_kc) gemm_item<true, true>(j, local, P, rix, As, Bs, s_flag);
-                    else if (j.a_kc) gemm_item<true, false>(j, local, P, rix, As, Bs, s_flag);
-                    else gemm_item<false, false>(j, local, P, rix, As, Bs, s_flag);
+                    gemm_item(j.a_kc != 0, j.b_kc != 0, j, local, P, rix, As, Bs, s_flag);
                     break;
                 case JOB_HEAD: head_item(j, local, P, rix); break;
-                case JOB_LOSS: loss_item(j, red); break;
+                case JOB_LOSS: loss_item(j, P, red); break;
                 default: opt_item(j, local, P, aa); break;
             }
         }
@@ -537,7 +599,10 @@ tape_step_kernel(const StepParams P) {
 #undef TP_PROF
     if (blockIdx.x == 0 && tid == 0) {
         // every CTA read the cursor and the optimizer state before the first barrier
-        if (P.perm) *P.cursor = (int)(((long long)*P.cursor + P.batch) % P.n_perm);
+        if (P.perm) {
+            const int start = P.cursor_value >= 0 ? P.cursor_value : *P.cursor;
+            *P.cursor = (int)(((long long)start + P.batch) % P.n_perm);
+        }
         if (P.opt_kind != 0) {
             P.hyper[H_T] = __int_as_float(t_new);
             P.hyper[H_SS] = aa.step_size;
@@ -592,6 +657,7 @@ bool desc_ok(const tp_step_desc* d, const char** why) {
     if (d->optimizer < 0 || d->optimizer > 2) return no("optimizer kind");
     const int L = d->n_layers;
     if (d->dims[L] < 1 || d->dims[L] > kMaxOut) return no("classifier wider than 16");
+    if (d->dims[L - 1] > 1024) return no("classifier input wider than 1024");
     for (int l = 0; l < L; ++l) {
         if (d->dims[l] < 4 || d->dims[l] % 4) return no("feature width not a multiple of 4");
         if (d->dims[l] > 4096) return no("feature width > 4096");
@@ -658,6 +724,7 @@ void build(tp_step* s, Carver& c, int sms) {
         j.bias = d.b_off[l] >= 0 ? P + d.b_off[l] : nullptr;
         j.relu = d.relu[l];
         pick_splits(j, sms);
+        if (l == L - 2 && j.splits > 1) j.defer_fold = 1;      // the head job folds the partials while it reads its rows
         s->jobs.push_back(j);
     }
     // ---- head ----------------------------------------------------------------------------------------------------------
@@ -668,6 +735,11 @@ void build(tp_step* s, Carver& c, int sms) {
         j.M = B; j.K = d.dims[L - 1]; j.N = d.dims[L];
         if (L == 1) j.a_input = 1; else j.A = act[L - 2];
         j.lda = d.dims[L - 1];
+        if (L >= 2 && s->jobs.back().defer_fold) {
+            const Job& f = s->jobs.back();
+            j.a_part = f.partial; j.a_splits = f.splits; j.a_stride = (long long)f.tiles_m * BM * f.N;
+            j.a_bias = f.bias; j.a_relu = f.relu; j.a_out = act[L - 2];
+        }
         j.B = P + d.w_off[L - 1];
         j.bias = d.b_off[L - 1] >= 0 ? P + d.b_off[L - 1] : nullptr;
         j.dlog = dlog; j.nll = nll; j.hit = hit;
@@ -690,6 +762,9 @@ void build(tp_step* s, Carver& c, int sms) {
             if (j.kind == JOB_GEMM) {
                 int share = (int)((long long)sms * (j.tiles_m * j.tiles_n) / tiles_total);
                 pick_splits(j, share);
+                // parameter gradients: the optimizer job folds the partials itself unless something else (a gradient
+                // exchange) needs them materialised in the arena
+                if (!j.a_kc && j.splits > 1 && !d.materialize_grads) j.defer_fold = 1;
             }
             s->jobs.push_back(j);
         }
@@ -729,17 +804,32 @@ void build(tp_step* s, Carver& c, int sms) {
         flush_phase();
     }
     flush_phase();
-    // ---- optimizer (src/optim.rs:21-33, 83-113, 148-168) over the flat arena ----------------------------------------------
+    // ---- optimizer (src/optim.rs:21-33, 83-113, 148-168): one job per parameter tensor of the flat arena -----------------
     {
+        std::vector<Job> dws;                                  // the dW jobs, to find each tensor's gradient source
+        for (auto& q : s->jobs) if (q.kind == JOB_GEMM && !q.a_kc) dws.push_back(q);
         begin_phase();
-        Job j{};
-        j.kind = JOB_OPT;
-        j.p = P; j.g = G;
-        j.m = s->m ? s->m->ptr : nullptr;
-        j.v = s->v ? s->v->ptr : nullptr;
-        j.n4 = (int)(d.arena_len / 4);
-        j.items = (j.n4 + kThreads - 1) / kThreads;
-        s->jobs.push_back(j);
+        auto opt_job = [&](int64_t off, size_t n, const float* part, int splits, long long stride) {
+            Job j{};
+            j.kind = JOB_OPT;
+            j.p = P + off; j.g = G + off;
+            j.m = s->m ? s->m->ptr + off : nullptr;
+            j.v = s->v ? s->v->ptr + off : nullptr;
+            j.n4 = (int)((n + 3) / 4);
+            j.items = (j.n4 + kThreads - 1) / kThreads;
+            j.g_part = part; j.g_splits = splits; j.g_stride = stride;
+            s->jobs.push_back(j);
+        };
+        for (int l = 0; l < L; ++l) {
+            const Job* src = nullptr;
+            for (auto& q : dws) if (q.C == G + d.w_off[l]) src = &q;
+            const bool deferred = src && src->defer_fold;
+            const long long mpad = src ? (long long)src->tiles_m * BM : 0;
+            opt_job(d.w_off[l], (size_t)d.dims[l] * d.dims[l + 1], deferred ? src->partial : nullptr, deferred ? src->splits : 0,
+                    deferred ? mpad * src->N : 0);
+            if (d.b_off[l] >= 0)
+                opt_job(d.b_off[l], (size_t)d.dims[l + 1], deferred ? src->cs_partial : nullptr, deferred ? src->splits : 0, mpad);
+        }
     }
     sp.phase_first[ph] = (int)s->jobs.size();
     sp.n_phases = ph;
@@ -830,7 +920,7 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
 }
 
 int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32, tp_buf* cursor_i32,
-                int n_perm, float sgd_lr, float grad_scale) {
+                int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host) {
     TP_CHECK_ARG(ctx && s && s->ctx == ctx, "tp_step_run: NULL or foreign step");
     TP_CHECK_ARG(!ctx->capturing, "tp_step_run: a cooperative launch cannot be captured into a CUDA graph");
     const int in = s->desc.dims[0];
@@ -847,6 +937,9 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     TP_CHECK_ARG(!((uintptr_t)x->ptr & 15), "tp_step_run: input rows must be 16-byte aligned");
     p.x = x->ptr; p.labels = labels->ptr;
     p.sgd_lr = sgd_lr; p.grad_scale = grad_scale;
+    p.cursor_value = perm_i32 ? cursor_value : -1;
+    TP_CHECK_ARG(cursor_value < n_perm || !perm_i32, "tp_step_run: cursor_value %d outside the dataset", cursor_value);
+    p.result_host = result_host;
     cudaSetDevice(ctx->device);
     void* args[] = {(void*)&p};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)tape_step_kernel, dim3(s->grid), dim3(kThreads), args, s->smem, ctx->stream);
