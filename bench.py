@@ -300,6 +300,8 @@ def run_ours(args, cfg_name, cfg):
 
     model = host.Model(getattr(host, spec_key), seed=0)
     tr = host.Trainer(model, opt_kind, lr=lr, weight_decay=wd)
+    if args.no_fused or args.nccl_only:
+        tr.set_use_fused(False)
     if world > 1:
         import torch
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -308,6 +310,8 @@ def run_ours(args, cfg_name, cfg):
         dist.broadcast(uid, 0)
         tr.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
         tr.broadcast_params(0)
+        if not args.nccl_only:
+            tr.peer_exchange_init(dist)         # fused step: gradient exchange inside the step kernel over NVLink peer memory
 
     # each rank owns a shard: its own resident dataset (weak scaling: batch/GPU fixed)
     X, Y = synthetic(DATASET_N, sample_shape, 1 + rank)
@@ -439,6 +443,9 @@ def main():
     ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--full-adjoint", action="store_true", help="CNN: compute conv dW/dX (the reference does not, SURVEY A1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="N>1: keep the NCCL allreduce (tape + CUDA-graph path) instead of the "
+                                                             "in-kernel NVLink peer-memory exchange of the fused step")
+    ap.add_argument("--no-fused", action="store_true", help="run the tape + CUDA-graph path even where the fused device step qualifies")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.steps is None:

@@ -310,9 +310,22 @@ typedef struct tp_step_desc {
     int materialize_grads;                   /* 1: leave the folded gradients in the grads arena (needed by a gradient
                                                 exchange); 0: the optimizer phase sums the split-K partials itself     */
 } tp_step_desc;
+/* Data-parallel gradient exchange INSIDE the step kernel, over NVLink peer memory (one process per GPU on one node;
+ * no counterpart in the reference, which is single-process).  Every rank owns a window {flags, two gradient buffers}
+ * allocated with cudaMalloc and exported as a 64-byte cudaIpcMemHandle; the launcher distributes the handles
+ * (torch.distributed / MPI / files) and tp_xchg_connect maps the peers' windows.  A step created with an exchange
+ * writes its folded gradients into its own window, raises a flag in every peer's window and, in the optimizer phase,
+ * sums all windows in rank order (so replicas stay bit-identical) before SGD / Adam — allreduce and optimizer are one
+ * phase of one kernel.  Every rank must run the same sequence of steps. */
+typedef struct tp_xchg tp_xchg;
+int tp_xchg_create(tp_ctx* ctx, size_t arena_len, int rank, int world, tp_xchg** out);
+int tp_xchg_handle(tp_xchg* x, void* out64);
+int tp_xchg_connect(tp_xchg* x, const void* handles_world_x_64, int world);
+int tp_xchg_destroy(tp_xchg* x);
+
 int tp_step_supported(const tp_step_desc* desc);
 int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v,
-                   tp_buf* hyper, tp_buf* result, tp_step** out);
+                   tp_buf* hyper, tp_buf* result, tp_xchg* xchg, tp_step** out);
 int tp_step_run(tp_ctx* ctx, tp_step* step, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32,
                 tp_buf* cursor_i32, int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host);
 int tp_step_info(const tp_step* step, int* n_phases, int* n_jobs, int* grid);

@@ -79,6 +79,10 @@ int tp_trainer_load_checkpoint(tp_trainer* t, const char* path);
 /* data-parallel replica: NCCL rank binding, parameter broadcast; gradients are allreduced inside every step */
 int tp_trainer_comm_init(tp_trainer* t, int rank, int world, const void* unique_id128);
 int tp_trainer_broadcast_params(tp_trainer* t, int root);
+/* NVLink peer-memory gradient exchange for the fused device step (tp_xchg_* in taper_b200.h), after tp_trainer_comm_init:
+ * export this rank's 64-byte window handle, all-gather the handles in rank order with the launcher's transport, connect. */
+int tp_trainer_peer_handle(tp_trainer* t, void* out64);
+int tp_trainer_peer_connect(tp_trainer* t, const void* handles_world_x_64);
 int tp_trainer_graph_replays(tp_trainer* t, uint64_t* count);
 
 #ifdef __cplusplus

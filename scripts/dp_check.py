@@ -1,5 +1,7 @@
 """Run under torchrun (one rank per GPU): data-parallel invariance of the CUDA path.
-W ranks x (B/W) rows with the NCCL gradient allreduce must match one rank x B rows (only summation order differs)."""
+W ranks x (B/W) rows must match one rank x B rows (only summation order differs), for both gradient exchanges:
+    (default)  tape + CUDA-graph path with the NCCL allreduce captured in the graph
+    --peer     fused device step with the in-kernel NVLink peer-memory exchange (tp_xchg_*)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -25,12 +27,18 @@ if rank == 0:
 dist.broadcast(uid, 0)
 tr.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
 tr.broadcast_params(0)
+PEER = "--peer" in sys.argv
+if PEER:
+    tr.peer_exchange_init(dist)
+else:
+    tr.set_use_fused(False)
 tr.load_dataset(X, Y, shard_permutation(perm, rank, world, b))
 local_losses = []
 for s in range(steps):                            # eager, capture (with the allreduce inside the graph), replays
     tr.step_resident(b)
     local_losses.append(tr.fetch()[0])
 params = [model.get_param(i) for i in range(model.num_params())]
+assert tr.fused_steps() == (steps if PEER else 0), tr.fused_steps()
 
 # single-replica reference on the global batch, same process, no communicator
 ref_model = host.Model(spec, seed=0)

@@ -48,7 +48,7 @@ def build(ctx, dims, batch, opt, seed=0):
     result = ctx.zeros(2)
     step = C.c_void_p()
     assert lib.tp_step_supported(C.byref(d)) == 1, "step not supported"
-    check(lib.tp_step_create(ctx.h, C.byref(d), params.h, grads.h, m.h, v.h, hyper.h, result.h, C.byref(step)))
+    check(lib.tp_step_create(ctx.h, C.byref(d), params.h, grads.h, m.h, v.h, hyper.h, result.h, None, C.byref(step)))
     return d, step, (params, grads, m, v, hyper, result)
 
 

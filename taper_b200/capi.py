@@ -41,7 +41,7 @@ class StepDesc(C.Structure):
                 ("w_off", C.c_int64 * 8), ("b_off", C.c_int64 * 8), ("arena_len", C.c_int64), ("materialize_grads", C.c_int)]
 
 
-_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step")
+_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step", "tp_xchg")
 _BASE = {
     "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32,
     "int64_t": C.c_int64, "char": C.c_char, "void": None,

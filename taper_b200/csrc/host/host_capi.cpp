@@ -293,6 +293,14 @@ int tp_trainer_broadcast_params(tp_trainer* t, int root) {
     return guarded([&] { TRAINER(t); t->tr->broadcast_parameters(root); });
 }
 
+int tp_trainer_peer_handle(tp_trainer* t, void* out64) {
+    return guarded([&] { TRAINER(t); t->tr->peer_exchange_handle(out64); });
+}
+
+int tp_trainer_peer_connect(tp_trainer* t, const void* handles_world_x_64) {
+    return guarded([&] { TRAINER(t); t->tr->peer_exchange_connect(handles_world_x_64); });
+}
+
 int tp_trainer_set_use_fused(tp_trainer* t, int on) {
     return guarded([&] { TRAINER(t); t->tr->set_use_fused(on != 0); });
 }

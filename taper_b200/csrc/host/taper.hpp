@@ -442,6 +442,11 @@ public:
     // backward and the optimizer folds 1/world.  broadcast_parameters makes every replica start equal.
     void init_data_parallel(int rank, int world, const void* nccl_unique_id128);
     void broadcast_parameters(int root);
+    // NVLink peer-memory gradient exchange for the fused device step (tp_xchg_*): each rank exports the 64-byte IPC
+    // handle of its window, the launcher all-gathers them (rank order), connect maps the peers.  Without it a
+    // data-parallel trainer uses the tape + CUDA-graph path with the NCCL allreduce.
+    void peer_exchange_handle(void* out64);
+    void peer_exchange_connect(const void* handles_world_x_64);
 
     void set_use_graph(bool v) { use_graph_ = v; }
     uint64_t graph_replays() const { return graph_replays_; }

@@ -155,16 +155,20 @@ struct Trainer::Impl {
     int world = 1;
     // fused device step per batch size (NULL once a size is known not to qualify)
     std::map<size_t, tp_step*> fused;
+    tp_xchg* xchg = nullptr;                                 // NVLink peer-memory gradient exchange (world > 1)
+    bool xchg_connected = false;
 
     tp_step* fused_step(Trainer& tr, size_t batch, const Shape& sample_shape) {
-        if (world != 1 || sample_shape.size() != 1) return nullptr;
+        if ((world != 1 && !xchg_connected) || sample_shape.size() != 1) return nullptr;
         auto it = fused.find(batch);
         if (it != fused.end()) return it->second;
         tp_step* st = nullptr;
         tp_step_desc d;
         tp_buf* b[5] = {};
-        if (optim::describe_fused_step(*tr.model, *tr.optimizer, batch, &d, b) && (size_t)d.dims[0] == sample_shape[0])
-            check(tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), &st));
+        if (optim::describe_fused_step(*tr.model, *tr.optimizer, batch, &d, b) && (size_t)d.dims[0] == sample_shape[0]) {
+            d.materialize_grads = world > 1 ? 1 : 0;
+            check(tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), world > 1 ? xchg : nullptr, &st));
+        }
         fused[batch] = st;
         return st;
     }
@@ -183,6 +187,7 @@ struct Trainer::Impl {
     ~Impl() {
         tp_sync(ctx());
         for (auto& kv : fused) tp_step_destroy(kv.second);
+        tp_xchg_destroy(xchg);
         for (auto& kv : slots) {
             tp_graph_destroy(kv.second.graph);
             tp_graph_destroy(kv.second.graph_resident);
@@ -218,6 +223,22 @@ void Trainer::init_data_parallel(int rank, int world, const void* uid) {
     dist::init(rank, world, uid);
     p_->world = world;
     optimizer->set_grad_scale(1.0f / (float)world);
+}
+
+void Trainer::peer_exchange_handle(void* out64) {
+    Impl& p = *p_;
+    if (p.world < 2) panic("Trainer::peer_exchange_handle: call init_data_parallel first");
+    if (!p.xchg) check(tp_xchg_create(ctx(), optim::arena_total(optimizer->arena()), dist::rank(), p.world, &p.xchg));
+    check(tp_xchg_handle(p.xchg, out64));
+}
+
+void Trainer::peer_exchange_connect(const void* handles) {
+    Impl& p = *p_;
+    if (!p.xchg) panic("Trainer::peer_exchange_connect: no exchange window (peer_exchange_handle first)");
+    check(tp_xchg_connect(p.xchg, handles, p.world));
+    p.xchg_connected = true;
+    for (auto& kv : p.fused) tp_step_destroy(kv.second);    // steps compiled before the exchange existed
+    p.fused.clear();
 }
 
 void Trainer::broadcast_parameters(int root) {

@@ -14,6 +14,7 @@
 // Deterministic: split-K partials are folded in split order by the last CTA of a tile; no float atomics.
 #include "common.cuh"
 #include <cmath>
+#include <type_traits>
 
 namespace {
 
@@ -24,6 +25,9 @@ constexpr int kMaxOut = 16;
 constexpr int kMaxJobs = 48, kMaxPhases = 20;
 constexpr int kMaxBatch = 4096;
 constexpr int kHeadRows = 8;                                   // one warp per row
+constexpr int kMaxWorld = 8;
+constexpr int kFlagStride = 32;                                // one 128-byte line per flag
+constexpr long long kPeerSpinLimit = 40000000000LL;            // ~20 s: a peer that never arrives must not hang this GPU for ever
 constexpr int kProfSlots = 2 + 2 * kMaxPhases;               // entry, setup done, then {work done, barrier passed} per phase
 constexpr long long kSpinLimit = 400000000LL;                  // ~0.2 s: a barrier that never completes must not hang the GPU
 
@@ -62,6 +66,7 @@ struct Job {
     // OPT (one job per parameter tensor): gradient = g, or the sum over g_splits partials at stride g_stride
     float* p; float* g; float* m; float* v; int n4;
     const float* g_part; int g_splits; long long g_stride;
+    long long g_off;                 // offset of this tensor in the gradient arena (peer windows share the layout)
 };
 
 struct StepParams {
@@ -81,6 +86,13 @@ struct StepParams {
     float* hyper;
     int* err;
     long long* prof;                 // optional [grid][kProfSlots] SM-clock stamps (tp_step_set_profile)
+    // data-parallel gradient exchange over NVLink peer memory (world > 1): every rank leaves its folded gradients in its
+    // own window, raises a flag in every peer's window, and the optimizer phase sums all windows in rank order
+    int world, rank;
+    unsigned int xseq;               // this step's flag value (monotonic, identical on every rank)
+    unsigned int* my_flags;          // [world][kFlagStride] in the local window
+    unsigned int* peer_flags[kMaxWorld];
+    const float* peer_g[kMaxWorld];  // this step's gradient buffer of every rank (own one included)
 };
 
 struct AdamArgs {
@@ -505,6 +517,14 @@ __device__ __forceinline__ void opt_item(const Job& j, int item, const StepParam
 #pragma unroll
             for (int t = 0; t < 8; ++t) { gg.x += q[t].x; gg.y += q[t].y; gg.z += q[t].z; gg.w += q[t].w; }
         }
+    } else if (P.world > 1) {                                 // all-reduce fused into the optimizer: sum the ranks' windows
+        float4 q[kMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            q[r] = (r < P.world) ? ldcg4(P.peer_g[r] + j.g_off + 4 * (size_t)i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        gg = q[0];
+#pragma unroll
+        for (int r = 1; r < kMaxWorld; ++r) { gg.x += q[r].x; gg.y += q[r].y; gg.z += q[r].z; gg.w += q[r].w; }   // rank order
     } else {
         gg = __ldcg(reinterpret_cast<const float4*>(j.g) + i);
     }
@@ -537,45 +557,71 @@ tape_step_kernel(const StepParams P) {
 
 #define TP_PROF(slot) do { if (P.prof && tid == 0) P.prof[(size_t)blockIdx.x * kProfSlots + (slot)] = clock64(); } while (0)
     TP_PROF(0);
-    {   // stage the job list
+    // setup: the three independent fetches (job list, gather index, optimizer state) are issued by different warps /
+    // consumed late so that their latencies overlap
+    const int* rix = P.perm ? ridx : nullptr;
+    if (tid < kThreads / 2 || !P.perm) {                       // stage the job list
+        const int nthr = P.perm ? kThreads / 2 : kThreads;
         const int words = P.n_jobs * (int)(sizeof(Job) / 4);
         const int* src = reinterpret_cast<const int*>(P.jobs);
         int* dst = reinterpret_cast<int*>(sjobs);
-        for (int i = tid; i < words; i += kThreads) dst[i] = __ldg(src + i);
-    }
-    const int* rix = nullptr;
-    if (P.perm) {                                              // MNISTDataset::get_batch as an index (src/data/mnist.rs:276-309)
+#pragma unroll 4
+        for (int i = tid; i < words; i += nthr) dst[i] = __ldg(src + i);
+    } else {                                                   // MNISTDataset::get_batch as an index (src/data/mnist.rs:276-309)
         const int start = P.cursor_value >= 0 ? P.cursor_value : __ldcg(P.cursor);
-#pragma unroll 1
-        for (int r = tid; r < P.batch; r += kThreads) {
+#pragma unroll 4
+        for (int r = tid - kThreads / 2; r < P.batch; r += kThreads / 2) {
             int idx = start + r;
             if (idx >= P.n_perm) idx %= P.n_perm;
             ridx[r] = __ldg(P.perm + idx);
         }
-        rix = ridx;
     }
-    AdamArgs aa{};
-    int t_new = 0;
-    if (P.opt_kind != 0) {                                     // Adam::step prologue (src/optim.rs:86-90), as adam_advance_kernel
+    float h_t = 0.0f, h_lr = 0.0f, h_b1 = 0.0f, h_b2 = 0.0f, h_eps = 0.0f, h_wd = 0.0f;
+    if (P.opt_kind != 0) {                                     // loaded now (before CTA 0 advances it), used in the last phase
         const float* h = P.hyper;
-        t_new = __float_as_int(__ldcg(h + H_T)) + 1;
-        const float lr = __ldcg(h + H_LR), b1 = __ldcg(h + H_B1), b2 = __ldcg(h + H_B2), wd = __ldcg(h + H_WD);
-        const float bc1 = 1.0f - powi_dev(b1, t_new);
-        const float bc2 = 1.0f - powi_dev(b2, t_new);
-        aa.step_size = lr * (sqrtf(bc2) / bc1);
-        aa.beta1 = b1; aa.beta2 = b2; aa.eps = __ldcg(h + H_EPS);
-        aa.decay_factor = 1.0f - lr * wd;
-        const int decoupled = P.opt_kind == 2;
-        aa.weight_decay = decoupled ? 0.0f : wd;
-        aa.decoupled = (decoupled && wd > 0.0f) ? 1 : 0;
-        aa.grad_scale = P.grad_scale;
+        h_t = __ldcg(h + H_T); h_lr = __ldcg(h + H_LR); h_b1 = __ldcg(h + H_B1); h_b2 = __ldcg(h + H_B2);
+        h_eps = __ldcg(h + H_EPS); h_wd = __ldcg(h + H_WD);
     }
     unsigned int gen = 0;
     if (tid == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(P.bar + 1) : "memory");
     __syncthreads();
     TP_PROF(1);
 
+    AdamArgs aa{};
+    int t_new = 0;
     for (int ph = 0; ph < P.n_phases; ++ph) {
+        if (ph == P.n_phases - 1) {
+            if (P.opt_kind != 0) {                             // Adam::step prologue (src/optim.rs:86-90), as adam_advance_kernel
+                t_new = __float_as_int(h_t) + 1;
+                const float bc1 = 1.0f - powi_dev(h_b1, t_new);
+                const float bc2 = 1.0f - powi_dev(h_b2, t_new);
+                aa.step_size = h_lr * (sqrtf(bc2) / bc1);
+                aa.beta1 = h_b1; aa.beta2 = h_b2; aa.eps = h_eps;
+                aa.decay_factor = 1.0f - h_lr * h_wd;
+                const int decoupled = P.opt_kind == 2;
+                aa.weight_decay = decoupled ? 0.0f : h_wd;
+                aa.decoupled = (decoupled && h_wd > 0.0f) ? 1 : 0;
+                aa.grad_scale = P.grad_scale;
+            }
+            if (P.world > 1) {
+                // The grid barrier above ordered every local gradient write before this point.  CTA 0 publishes "rank
+                // `rank` finished step xseq" in every peer's window; every CTA then waits until all peers have published.
+                if (tid < P.world && tid != P.rank) {
+                    if (blockIdx.x == 0) {
+                        __threadfence_system();
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(P.peer_flags[tid] + P.rank * kFlagStride), "r"(P.xseq) : "memory");
+                    }
+                    const unsigned int* f = P.my_flags + tid * kFlagStride;
+                    unsigned int cur;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(f) : "memory");
+                        if ((int)(cur - P.xseq) < 0 && clock64() - t0 > kPeerSpinLimit) { atomicExch(P.err, 3); break; }
+                    } while ((int)(cur - P.xseq) < 0);
+                }
+                __syncthreads();
+            }
+        }
         const int j0 = P.phase_first[ph], j1 = P.phase_first[ph + 1];
         int total = 0;
         for (int q = j0; q < j1; ++q) total += sjobs[q].items;
@@ -617,8 +663,21 @@ size_t smem_bytes(int n_jobs, int batch) {
 
 }  // namespace
 
+struct tp_xchg {
+    tp_ctx* ctx = nullptr;
+    int rank = 0, world = 1;
+    size_t arena_len = 0;
+    unsigned char* window = nullptr;     // [flags: world x 128 B][G0: arena_len f32][G1: arena_len f32]
+    size_t bytes = 0, g_off[2] = {0, 0};
+    unsigned char* peers[kMaxWorld] = {};    // mapped base of every rank's window (own one included)
+    bool connected = false;
+    unsigned int seq = 0;                // steps run through this window (flag value of the next step is seq + 1)
+};
+
 struct tp_step {
     tp_ctx* ctx = nullptr;
+    tp_xchg* xchg = nullptr;
+    const Job* jobs_dev[2] = {nullptr, nullptr};     // job list per gradient-buffer parity (same list without an exchange)
     tp_step_desc desc{};
     StepParams params{};
     std::vector<Job> jobs;
@@ -669,11 +728,10 @@ bool desc_ok(const tp_step_desc* d, const char** why) {
 }
 
 // Build the job list.  Pass 1 (c.base == NULL) only sizes the device block.
-void build(tp_step* s, Carver& c, int sms) {
+void build(tp_step* s, Carver& c, int sms, float* G) {
     const tp_step_desc& d = s->desc;
     const int L = d.n_layers, B = d.batch;
     float* P = s->p->ptr;
-    float* G = s->g->ptr;
     s->jobs.clear();
     StepParams& sp = s->params;
     int ph = 0;
@@ -818,6 +876,7 @@ void build(tp_step* s, Carver& c, int sms) {
             j.n4 = (int)((n + 3) / 4);
             j.items = (j.n4 + kThreads - 1) / kThreads;
             j.g_part = part; j.g_splits = splits; j.g_stride = stride;
+            j.g_off = off;
             s->jobs.push_back(j);
         };
         for (int l = 0; l < L; ++l) {
@@ -835,7 +894,9 @@ void build(tp_step* s, Carver& c, int sms) {
     sp.n_phases = ph;
     sp.n_jobs = (int)s->jobs.size();
     sp.bar = c.take<unsigned int>(4);
-    sp.jobs = c.take<Job>(s->jobs.size());
+    s->jobs_dev[0] = c.take<Job>(s->jobs.size());
+    s->jobs_dev[1] = s->xchg ? c.take<Job>(s->jobs.size()) : s->jobs_dev[0];
+    sp.jobs = s->jobs_dev[0];
 }
 
 }  // namespace
@@ -848,8 +909,13 @@ int tp_step_supported(const tp_step_desc* desc) {
 }
 
 int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v, tp_buf* hyper,
-                   tp_buf* result, tp_step** out) {
+                   tp_buf* result, tp_xchg* xchg, tp_step** out) {
     TP_CHECK_ARG(ctx && out, "tp_step_create: NULL argument");
+    if (xchg) {
+        TP_CHECK_ARG(xchg->ctx == ctx && xchg->connected, "tp_step_create: the exchange window is not connected");
+        TP_CHECK_ARG(desc && desc->materialize_grads && (size_t)desc->arena_len == xchg->arena_len,
+                     "tp_step_create: an exchange needs materialize_grads = 1 and a window of the arena's length");
+    }
     const char* why = nullptr;
     TP_CHECK_ARG(desc_ok(desc, &why), "tp_step_create: unsupported step (%s)", why ? why : "?");
     TP_NEED(params, desc->arena_len, "params"); TP_NEED(grads, desc->arena_len, "grads"); TP_NEED(result, 2, "result");
@@ -871,10 +937,14 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     s->ctx = ctx;
     s->desc = *desc;
     s->p = params; s->g = grads; s->m = m; s->v = v; s->hyper = hyper; s->result = result;
+    s->xchg = xchg;
     for (tp_buf* b : {params, grads, m, v, hyper, result}) if (b) tp_buf_retain(b);
+    // with an exchange the gradients are written into the local window (double-buffered by step parity) instead of the arena
+    float* G0 = xchg ? reinterpret_cast<float*>(xchg->window + xchg->g_off[0]) : grads->ptr;
+    float* G1 = xchg ? reinterpret_cast<float*>(xchg->window + xchg->g_off[1]) : grads->ptr;
     auto fail = [&](int rc) { tp_step_destroy(s); return rc; };
     Carver sizing;
-    build(s, sizing, ctx->sm_count);
+    build(s, sizing, ctx->sm_count, G0);
     if ((int)s->jobs.size() > kMaxJobs || s->params.n_phases > kMaxPhases) {
         tp::set_error("tp_step_create: model too deep for the fused step (%zu jobs)", s->jobs.size());
         return fail(TP_ERR_UNSUPPORTED);
@@ -888,10 +958,22 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     if (cudaMemsetAsync(s->dev_block, 0, s->dev_bytes, ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);
     Carver place;
     place.base = (unsigned char*)s->dev_block;
-    build(s, place, ctx->sm_count);
-    if (cudaMemcpyAsync((void*)s->params.jobs, s->jobs.data(), s->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    build(s, place, ctx->sm_count, G0);
+    if (cudaMemcpyAsync((void*)s->jobs_dev[0], s->jobs.data(), s->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         return fail(TP_ERR_CUDA);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);      // s->jobs is pageable host memory
+    if (xchg) {                                            // the odd-step list: same jobs, gradients into the other buffer
+        std::vector<Job> odd = s->jobs;
+        const ptrdiff_t delta = G1 - G0;
+        auto moved = [&](auto*& ptr) {
+            using T = std::remove_reference_t<decltype(ptr)>;
+            if (ptr && (const float*)ptr >= G0 && (const float*)ptr < G0 + xchg->arena_len) ptr = (T)((float*)ptr + delta);
+        };
+        for (auto& j : odd) { moved(j.C); moved(j.colsum); moved(j.g); }
+        if (cudaMemcpyAsync((void*)s->jobs_dev[1], odd.data(), odd.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+            return fail(TP_ERR_CUDA);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);
+    }
     s->params.batch = desc->batch;
     s->params.opt_kind = desc->optimizer;
     s->params.hyper = hyper ? hyper->ptr : nullptr;
@@ -940,6 +1022,18 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     p.cursor_value = perm_i32 ? cursor_value : -1;
     TP_CHECK_ARG(cursor_value < n_perm || !perm_i32, "tp_step_run: cursor_value %d outside the dataset", cursor_value);
     p.result_host = result_host;
+    p.world = 1; p.rank = 0;
+    if (tp_xchg* x = s->xchg) {
+        x->seq += 1;
+        const int par = (int)(x->seq & 1u);
+        p.jobs = s->jobs_dev[par];
+        p.world = x->world; p.rank = x->rank; p.xseq = x->seq;
+        p.my_flags = reinterpret_cast<unsigned int*>(x->window);
+        for (int r = 0; r < x->world; ++r) {
+            p.peer_flags[r] = reinterpret_cast<unsigned int*>(x->peers[r]);
+            p.peer_g[r] = reinterpret_cast<const float*>(x->peers[r] + x->g_off[par]);
+        }
+    }
     cudaSetDevice(ctx->device);
     void* args[] = {(void*)&p};
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)tape_step_kernel, dim3(s->grid), dim3(kThreads), args, s->smem, ctx->stream);
@@ -949,6 +1043,69 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
         return TP_ERR_CUDA;
     }
     ctx->launches++;
+    return TP_OK;
+}
+
+int tp_xchg_create(tp_ctx* ctx, size_t arena_len, int rank, int world, tp_xchg** out) {
+    TP_CHECK_ARG(ctx && out && arena_len > 0 && arena_len % 4 == 0, "tp_xchg_create: bad arguments");
+    TP_CHECK_ARG(world >= 2 && world <= kMaxWorld && rank >= 0 && rank < world, "tp_xchg_create: world %d / rank %d (2..%d ranks)", world, rank, kMaxWorld);
+    cudaSetDevice(ctx->device);
+    tp_xchg* x = new tp_xchg();
+    x->ctx = ctx; x->rank = rank; x->world = world; x->arena_len = arena_len;
+    const size_t flags = (size_t)kMaxWorld * kFlagStride * sizeof(unsigned int);
+    const size_t gbytes = (arena_len * sizeof(float) + 255) & ~(size_t)255;
+    x->g_off[0] = flags; x->g_off[1] = flags + gbytes;
+    x->bytes = flags + 2 * gbytes;
+    if (cudaMalloc((void**)&x->window, x->bytes) != cudaSuccess) {       // plain cudaMalloc: cudaIpcGetMemHandle needs an allocation base
+        cudaGetLastError();
+        tp::set_error("tp_xchg_create: cudaMalloc(%zu) failed", x->bytes);
+        delete x;
+        return TP_ERR_OOM;
+    }
+    cudaMemset(x->window, 0, x->bytes);
+    x->peers[rank] = x->window;
+    *out = x;
+    return TP_OK;
+}
+
+int tp_xchg_handle(tp_xchg* x, void* out64) {
+    TP_CHECK_ARG(x && out64, "tp_xchg_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaSetDevice(x->ctx->device);
+    cudaIpcMemHandle_t h;
+    TP_CUDA(cudaIpcGetMemHandle(&h, x->window));
+    std::memcpy(out64, &h, 64);
+    return TP_OK;
+}
+
+int tp_xchg_connect(tp_xchg* x, const void* handles, int world) {
+    TP_CHECK_ARG(x && handles && world == x->world, "tp_xchg_connect: bad arguments");
+    cudaSetDevice(x->ctx->device);
+    for (int r = 0; r < world; ++r) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const unsigned char*)handles + 64 * (size_t)r, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            tp::set_error("tp_xchg_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+            return TP_ERR_COMM;
+        }
+        x->peers[r] = (unsigned char*)ptr;
+    }
+    x->connected = true;
+    return TP_OK;
+}
+
+int tp_xchg_destroy(tp_xchg* x) {
+    if (!x) return TP_OK;
+    cudaSetDevice(x->ctx->device);
+    cudaStreamSynchronize(x->ctx->stream);
+    for (int r = 0; r < x->world; ++r)
+        if (r != x->rank && x->peers[r]) cudaIpcCloseMemHandle(x->peers[r]);
+    if (x->window) cudaFree(x->window);
+    delete x;
     return TP_OK;
 }
 

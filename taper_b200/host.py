@@ -239,6 +239,20 @@ class Trainer:
     def broadcast_params(self, root=0):
         check(lib.tp_trainer_broadcast_params(self.h, root))
 
+    def peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib.tp_trainer_peer_handle(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles: bytes):
+        check(lib.tp_trainer_peer_connect(self.h, handles))
+
+    def peer_exchange_init(self, dist):
+        """All-gather the window handles over torch.distributed (plumbing only) and map the peers' windows."""
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, self.peer_handle())
+        self.peer_connect(b"".join(handles))
+
     def set_use_fused(self, on):
         check(lib.tp_trainer_set_use_fused(self.h, int(bool(on))))
 
