@@ -80,7 +80,8 @@ struct StepParams {
     int n_perm, batch;
     int cursor_value;                // host mirror of *cursor (>= 0), or -1: read the device word
     float* result_host;              // optional mapped pinned {loss, correct} slot of this step (no separate D2H copy)
-    unsigned int* bar;               // {count, generation}
+    unsigned int* bar;               // arrival counter of the grid barrier
+    unsigned int bar_base;           // its value when this launch starts (tracked by the host)
     int opt_kind;                    // 0 SGD, 1 Adam, 2 AdamW
     float sgd_lr, grad_scale;
     float* hyper;
@@ -136,26 +137,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// ---- grid barrier (sense = generation counter; count is reset by the last arriver before it releases) ------------
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen, int* err) {
+// ---- grid barrier: one monotonically increasing arrival counter.  The host passes the counter value at launch
+// (bar_base); barrier k of this launch completes when the counter reaches bar_base + (k + 1) * gridDim.x (wrap-safe
+// compare).  Arrival is a fire-and-forget release reduction, so a CTA pays one poll round trip, not an atomic's too.
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target, int* err) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        unsigned int prev = atomicAdd(&bar[0], 1u);
-        if (prev == gridDim.x - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(&bar[1], 1u);
-        } else {
-            unsigned int cur;
-            const long long t0 = clock64();
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
-                if (cur == gen && clock64() - t0 > kSpinLimit) { atomicExch(err, 2); break; }
-            } while (cur == gen);
-        }
-        gen += 1u;
-        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
+        unsigned int cur;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+            if ((int)(cur - target) < 0 && clock64() - t0 > kSpinLimit) { atomicExch(err, 2); break; }
+        } while ((int)(cur - target) < 0);
     }
     __syncthreads();
 }
@@ -259,7 +253,7 @@ __device__ void gemm_item(const bool AKC, const bool BKC, const Job& j, int item
         const float* as = As + cur * (SK * LDS);
         const float* bs = Bs + cur * (SK * LDS);
         const int klen = min(SK, kend - k0);
-#pragma unroll 4
+#pragma unroll 8
         for (int kk = 0; kk < klen; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(as + kk * LDS + ty * 4);
             const float4 b4 = *reinterpret_cast<const float4*>(bs + kk * LDS + tx * 4);
@@ -371,6 +365,12 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
     const float* arow = (j.a_input ? P.x + (size_t)(ridx ? ridx[r] : r) * j.lda : j.A + (size_t)r * j.lda);
     const float* W = j.B;
     const float* afin = j.a_part ? j.a_out + (size_t)r * in_f : arow;      // the materialised activation row
+    // issue everything that does not depend on the activations first: label, head bias (their latency hides behind the fold)
+    const float t = __ldg(P.labels + (P.perm ? ridx[r] : r));
+    float hb[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) hb[o] = (j.bias && o < out_f) ? __ldg(j.bias + o) : 0.0f;
+    float4 a_first = make_float4(0.0f, 0.0f, 0.0f, 0.0f);    // chunk `lane` of the row (the only one when in <= 128)
     float acc[kMaxOut];
 #pragma unroll
     for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
@@ -378,6 +378,10 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
 #pragma unroll 1
     for (int c = lane; c < in4; c += 32) {
         {
+            float4 wv[kMaxOut];                                // W column chunk: independent of the activations, issued first
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o)
+                if (o < out_f) wv[o] = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
             float4 a;
             if (j.a_part) {
                 // the producing GEMM left its split-K partials unfolded: sum them here (split order), add bias, ReLU
@@ -401,10 +405,11 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
             } else {
                 a = ldcg4(arow + 4 * c);
             }
+            if (c == lane) a_first = a;
 #pragma unroll
             for (int o = 0; o < kMaxOut; ++o) {
                 if (o < out_f) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in_f) + c);
+                    const float4 w = wv[o];
                     acc[o] = fmaf(a.x, w.x, acc[o]);
                     acc[o] = fmaf(a.y, w.y, acc[o]);
                     acc[o] = fmaf(a.z, w.z, acc[o]);
@@ -419,7 +424,7 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
     for (int o = 0; o < kMaxOut; ++o) {
         if (o < out_f) {
             float v = warp_sum(acc[o]);
-            if (j.bias) v += __ldg(j.bias + o);
+            if (j.bias) v += hb[o];
             acc[o] = v;
             if (v > mx) { mx = v; bi = o; }                   // strict '>' from -inf, first max wins (src/tensor.rs:1062)
         }
@@ -429,7 +434,6 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
     for (int o = 0; o < kMaxOut; ++o)
         if (o < out_f) s += expf(acc[o] - mx);                // classes ascending (src/tensor.rs:890-1018 sum over dim 1)
     const float ls = logf(s);
-    const float t = __ldg(P.labels + (P.perm ? ridx[r] : r));
     unsigned int cls = class_of(t);
     if (cls >= (unsigned int)out_f) { if (lane == 0) atomicExch(P.err, 1); cls = out_f - 1; }
     float dl[kMaxOut];
@@ -469,7 +473,7 @@ __device__ void head_item(const Job& j, int item, const StepParams& P, const int
                     }
                 }
                 if (j.dz_mask) {
-                    const float4 a = ldcg4(afin + 4 * c);      // this lane wrote / read it above
+                    const float4 a = (c == lane) ? a_first : ldcg4(afin + 4 * c);      // this lane wrote / read it above
                     d.x = a.x > 0.0f ? d.x : 0.0f; d.y = a.y > 0.0f ? d.y : 0.0f;
                     d.z = a.z > 0.0f ? d.z : 0.0f; d.w = a.w > 0.0f ? d.w : 0.0f;
                 }
@@ -549,8 +553,8 @@ tape_step_kernel(const StepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* As = reinterpret_cast<float*>(smem_raw);            // [2][SK][LDS]
     float* Bs = As + 2 * SK * LDS;                             // [2][SK][LDS]
-    float* red = Bs + 2 * SK * LDS;                            // [16]
-    int* s_flag = reinterpret_cast<int*>(red + 16);            // [4]
+    float* red = Bs + 2 * SK * LDS;                            // [16] reduction scratch + [16] optimizer state
+    int* s_flag = reinterpret_cast<int*>(red + 32);            // [4]
     Job* sjobs = reinterpret_cast<Job*>(s_flag + 4);           // [n_jobs]
     int* ridx = reinterpret_cast<int*>(sjobs + P.n_jobs);      // [batch] when gathering
     const int tid = threadIdx.x;
@@ -576,14 +580,11 @@ tape_step_kernel(const StepParams P) {
             ridx[r] = __ldg(P.perm + idx);
         }
     }
-    float h_t = 0.0f, h_lr = 0.0f, h_b1 = 0.0f, h_b2 = 0.0f, h_eps = 0.0f, h_wd = 0.0f;
-    if (P.opt_kind != 0) {                                     // loaded now (before CTA 0 advances it), used in the last phase
-        const float* h = P.hyper;
-        h_t = __ldcg(h + H_T); h_lr = __ldcg(h + H_LR); h_b1 = __ldcg(h + H_B1); h_b2 = __ldcg(h + H_B2);
-        h_eps = __ldcg(h + H_EPS); h_wd = __ldcg(h + H_WD);
+    // optimizer state: fetched now (before CTA 0 advances it at the end), parked in shared memory, used in the last phase
+    if (P.opt_kind != 0 && tid >= kThreads - H_COUNT) {
+        const int q = tid - (kThreads - H_COUNT);
+        red[16 + q] = __ldcg(P.hyper + q);
     }
-    unsigned int gen = 0;
-    if (tid == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(P.bar + 1) : "memory");
     __syncthreads();
     TP_PROF(1);
 
@@ -592,6 +593,8 @@ tape_step_kernel(const StepParams P) {
     for (int ph = 0; ph < P.n_phases; ++ph) {
         if (ph == P.n_phases - 1) {
             if (P.opt_kind != 0) {                             // Adam::step prologue (src/optim.rs:86-90), as adam_advance_kernel
+                const float h_t = red[16 + H_T], h_lr = red[16 + H_LR], h_b1 = red[16 + H_B1], h_b2 = red[16 + H_B2];
+                const float h_eps = red[16 + H_EPS], h_wd = red[16 + H_WD];
                 t_new = __float_as_int(h_t) + 1;
                 const float bc1 = 1.0f - powi_dev(h_b1, t_new);
                 const float bc2 = 1.0f - powi_dev(h_b2, t_new);
@@ -639,7 +642,7 @@ tape_step_kernel(const StepParams P) {
             }
         }
         TP_PROF(2 + 2 * ph);
-        if (ph + 1 < P.n_phases) grid_sync(P.bar, gen, P.err);
+        if (ph + 1 < P.n_phases) grid_sync(P.bar, P.bar_base + (unsigned int)(ph + 1) * gridDim.x, P.err);
         TP_PROF(3 + 2 * ph);
     }
 #undef TP_PROF
@@ -658,7 +661,7 @@ tape_step_kernel(const StepParams P) {
 }
 
 size_t smem_bytes(int n_jobs, int batch) {
-    return (size_t)(4 * SK * LDS + 16 + 4) * sizeof(float) + (size_t)n_jobs * sizeof(Job) + (size_t)batch * sizeof(int) + 16;
+    return (size_t)(4 * SK * LDS + 32 + 4) * sizeof(float) + (size_t)n_jobs * sizeof(Job) + (size_t)batch * sizeof(int) + 16;
 }
 
 }  // namespace
@@ -678,6 +681,7 @@ struct tp_step {
     tp_ctx* ctx = nullptr;
     tp_xchg* xchg = nullptr;
     const Job* jobs_dev[2] = {nullptr, nullptr};     // job list per gradient-buffer parity (same list without an exchange)
+    unsigned int bar_count = 0;                      // host mirror of the barrier's arrival counter
     tp_step_desc desc{};
     StepParams params{};
     std::vector<Job> jobs;
@@ -1023,6 +1027,8 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     TP_CHECK_ARG(cursor_value < n_perm || !perm_i32, "tp_step_run: cursor_value %d outside the dataset", cursor_value);
     p.result_host = result_host;
     p.world = 1; p.rank = 0;
+    p.bar_base = s->bar_count;
+    s->bar_count += (unsigned int)(s->params.n_phases - 1) * (unsigned int)s->grid;
     if (tp_xchg* x = s->xchg) {
         x->seq += 1;
         const int par = (int)(x->seq & 1u);
