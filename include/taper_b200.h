@@ -307,16 +307,18 @@ typedef struct tp_step_desc {
     int64_t w_off[TP_STEP_MAX_LAYERS];       /* offset of W_l [out,in] in the flat arenas           */
     int64_t b_off[TP_STEP_MAX_LAYERS];       /* offset of b_l [out], or -1 if the layer has no bias */
     int64_t arena_len;                       /* elements in params / grads / m / v                  */
-    int materialize_grads;                   /* 1: leave the folded gradients in the grads arena (needed by a gradient
-                                                exchange); 0: the optimizer phase sums the split-K partials itself     */
+    int materialize_grads;                   /* 1: leave the folded gradients in the grads arena (for inspection); 0: the
+                                                optimizer phase sums the split-K partials itself                       */
 } tp_step_desc;
 /* Data-parallel gradient exchange INSIDE the step kernel, over NVLink peer memory (one process per GPU on one node;
- * no counterpart in the reference, which is single-process).  Every rank owns a window {flags, two gradient buffers}
- * allocated with cudaMalloc and exported as a 64-byte cudaIpcMemHandle; the launcher distributes the handles
- * (torch.distributed / MPI / files) and tp_xchg_connect maps the peers' windows.  A step created with an exchange
- * writes its folded gradients into its own window, raises a flag in every peer's window and, in the optimizer phase,
- * sums all windows in rank order (so replicas stay bit-identical) before SGD / Adam — allreduce and optimizer are one
- * phase of one kernel.  Every rank must run the same sequence of steps. */
+ * no counterpart in the reference, which is single-process).  Every rank owns a window {per-slice flags, gradient slots
+ * [2 parities][world source ranks][arena_len]} allocated with cudaMalloc and exported as a 64-byte cudaIpcMemHandle; the
+ * launcher distributes the handles (torch.distributed / MPI / files) and tp_xchg_connect maps the peers' windows.
+ * In a step created with an exchange, the optimizer phase of the kernel becomes allreduce + optimizer in one: the CTA that
+ * owns a 256-float4 slice of the arena folds its local gradient slice, stores it into its slot of every peer's window,
+ * raises that slice's flag there (st.release.sys), waits for the peers' flags of the same slice (ld.acquire.sys) and sums the
+ * world's slices in rank order (replicas stay bit-identical) before SGD / Adam.  No grid-wide or host-side wait is involved.
+ * Every rank must run the same sequence of steps. */
 typedef struct tp_xchg tp_xchg;
 int tp_xchg_create(tp_ctx* ctx, size_t arena_len, int rank, int world, tp_xchg** out);
 int tp_xchg_handle(tp_xchg* x, void* out64);

@@ -17,7 +17,7 @@ from taper_b200 import capi                                       # noqa: E402
 from taper_b200.capi import check, lib                            # noqa: E402
 
 
-def build(ctx, dims, batch, opt, seed=0):
+def build(ctx, dims, batch, opt, seed=0, xchg_factory=None):
     rng = np.random.default_rng(seed)
     d = capi.StepDesc()
     L = len(dims) - 1
@@ -41,6 +41,8 @@ def build(ctx, dims, batch, opt, seed=0):
     d.batch = batch
     d.optimizer = {"sgd": 0, "adam": 1, "adamw": 2}[opt]
     d.arena_len = off
+    xchg = xchg_factory(off) if xchg_factory else None
+    d.materialize_grads = 0
     params = ctx.upload(np.concatenate(chunks))
     grads, m, v = ctx.zeros(off), ctx.zeros(off), ctx.zeros(off)
     hyper = ctx.alloc(8)
@@ -48,8 +50,8 @@ def build(ctx, dims, batch, opt, seed=0):
     result = ctx.zeros(2)
     step = C.c_void_p()
     assert lib.tp_step_supported(C.byref(d)) == 1, "step not supported"
-    check(lib.tp_step_create(ctx.h, C.byref(d), params.h, grads.h, m.h, v.h, hyper.h, result.h, None, C.byref(step)))
-    return d, step, (params, grads, m, v, hyper, result)
+    check(lib.tp_step_create(ctx.h, C.byref(d), params.h, grads.h, m.h, v.h, hyper.h, result.h, xchg, C.byref(step)))
+    return d, step, (params, grads, m, v, hyper, result, xchg)
 
 
 def main():
@@ -61,8 +63,27 @@ def main():
     ap.add_argument("--iters", type=int, default=2000)
     a = ap.parse_args()
     dims = [int(x) for x in a.dims.split(",")]
-    ctx = capi.Ctx(0)
-    d, step, keep = build(ctx, dims, a.batch, a.opt)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    xf = None
+    if world > 1:                                   # under torchrun: in-kernel NVLink peer-memory gradient exchange
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Ctx(local)
+    if world > 1:
+        def xf(arena_len):
+            x = C.c_void_p()
+            check(lib.tp_xchg_create(ctx.h, arena_len, rank, world, C.byref(x)))
+            buf = C.create_string_buffer(64)
+            check(lib.tp_xchg_handle(x, buf))
+            handles = [None] * world
+            dist.all_gather_object(handles, buf.raw)
+            check(lib.tp_xchg_connect(x, b"".join(handles), world))
+            return x
+    d, step, keep = build(ctx, dims, a.batch, a.opt, xchg_factory=xf)
     rng = np.random.default_rng(1)
     n = 60000 if a.resident else a.batch
     x = ctx.upload(rng.random((n, dims[0]), dtype=np.float32))
@@ -72,13 +93,15 @@ def main():
 
     def run():
         check(lib.tp_step_run(ctx.h, step, x.h, y.h, perm.h if perm else None, cursor.h if cursor else None, n if a.resident else 0,
-                              -1, 0.01, 1.0, None))
+                              -1, 0.01, 1.0 / world, None))
 
     nph, njobs, grid = C.c_int(), C.c_int(), C.c_int()
     check(lib.tp_step_info(step, C.byref(nph), C.byref(njobs), C.byref(grid)))
     for _ in range(20):
         run()
     ctx.sync()
+    if dist is not None:
+        dist.barrier()
     e0, e1 = C.c_void_p(), C.c_void_p()
     check(lib.tp_event_create(ctx.h, C.byref(e0))); check(lib.tp_event_create(ctx.h, C.byref(e1)))
     check(lib.tp_event_record(ctx.h, e0))
@@ -88,7 +111,15 @@ def main():
     ms = C.c_float()
     check(lib.tp_event_elapsed_ms(e0, e1, C.byref(ms)))
     us = ms.value * 1e3 / a.iters
-    print(f"dims {dims} batch {a.batch} {a.opt} resident={a.resident}: {nph.value} phases, {njobs.value} jobs, grid {grid.value}; "
+    if rank != 0:
+        check(lib.tp_step_set_profile(step, 1))
+        for _ in range(3):
+            run()
+        ctx.sync()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    print(f"world {world} dims {dims} batch {a.batch} {a.opt} resident={a.resident}: {nph.value} phases, {njobs.value} jobs, grid {grid.value}; "
           f"{us:.2f} us/step (CUDA events, {a.iters} back-to-back launches) = {a.batch / us:.2f} M samples/s")
 
     check(lib.tp_step_set_profile(step, 1))
@@ -109,6 +140,9 @@ def main():
               f"{np.mean(wait) / ghz / 1e3:6.2f} (min {np.min(wait) / ghz / 1e3:5.2f})")
         prev = t[:, 3 + 2 * ph]
     print(f"  total           {np.max(t[:, 1 + 2 * nph.value] - t[:, 0]) / ghz / 1e3:6.2f}")
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     check(lib.tp_step_destroy(step))
 
 

@@ -166,7 +166,7 @@ struct Trainer::Impl {
         tp_step_desc d;
         tp_buf* b[5] = {};
         if (optim::describe_fused_step(*tr.model, *tr.optimizer, batch, &d, b) && (size_t)d.dims[0] == sample_shape[0]) {
-            d.materialize_grads = world > 1 ? 1 : 0;
+            d.materialize_grads = 0;
             check(tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), world > 1 ? xchg : nullptr, &st));
         }
         fused[batch] = st;

@@ -26,7 +26,6 @@ constexpr int kMaxJobs = 48, kMaxPhases = 20;
 constexpr int kMaxBatch = 4096;
 constexpr int kHeadRows = 8;                                   // one warp per row
 constexpr int kMaxWorld = 8;
-constexpr int kFlagStride = 32;                                // one 128-byte line per flag
 constexpr long long kPeerSpinLimit = 40000000000LL;            // ~20 s: a peer that never arrives must not hang this GPU for ever
 constexpr int kProfSlots = 2 + 2 * kMaxPhases;               // entry, setup done, then {work done, barrier passed} per phase
 constexpr long long kSpinLimit = 400000000LL;                  // ~0.2 s: a barrier that never completes must not hang the GPU
@@ -87,13 +86,17 @@ struct StepParams {
     float* hyper;
     int* err;
     long long* prof;                 // optional [grid][kProfSlots] SM-clock stamps (tp_step_set_profile)
-    // data-parallel gradient exchange over NVLink peer memory (world > 1): every rank leaves its folded gradients in its
-    // own window, raises a flag in every peer's window, and the optimizer phase sums all windows in rank order
+    // data-parallel gradient exchange over NVLink peer memory (world > 1), fused into the optimizer phase: the CTA that owns
+    // a slice of the arena pushes its local gradient slice into every peer's window, raises a per-slice flag there, waits for
+    // the peers' flags on the same slice and sums the world's slices in rank order.  No grid-wide wait is involved.
     int world, rank;
     unsigned int xseq;               // this step's flag value (monotonic, identical on every rank)
-    unsigned int* my_flags;          // [world][kFlagStride] in the local window
-    unsigned int* peer_flags[kMaxWorld];
-    const float* peer_g[kMaxWorld];  // this step's gradient buffer of every rank (own one included)
+    int x_items;                     // flags per source rank
+    unsigned int* my_flags;          // [world][x_items] in the local window
+    const float* my_slots;           // [world][arena_len] in the local window: this step's gradient buffers, one per source rank
+    long long x_arena;               // arena_len
+    unsigned int* peer_flags[kMaxWorld];     // row `rank` of every peer's flag array
+    float* peer_slot[kMaxWorld];             // slot `rank` of every peer's window (this step's parity)
 };
 
 struct AdamArgs {
@@ -503,35 +506,67 @@ __device__ void loss_item(const Job& j, const StepParams& P, float* sm /* >= 16 
     __syncthreads();
 }
 
-__device__ __forceinline__ void opt_item(const Job& j, int item, const StepParams& P, const AdamArgs& aa) {
+__device__ __forceinline__ void opt_item(const Job& j, int item, int phase_item, const StepParams& P, const AdamArgs& aa) {
     const int i = item * kThreads + threadIdx.x;
-    if (i >= j.n4) return;
+    const bool live = i < j.n4;
+    float4 gg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (live) {
+        if (j.g_part) {                                       // fold the producing GEMM's split-K partials (split order)
+            const float* base = j.g_part + 4 * (size_t)i;
+#pragma unroll 1
+            for (int z0 = 0; z0 < j.g_splits; z0 += 8) {
+                float4 q[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    q[t] = (z0 + t < j.g_splits) ? ldcg4(base + (size_t)(z0 + t) * j.g_stride) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { gg.x += q[t].x; gg.y += q[t].y; gg.z += q[t].z; gg.w += q[t].w; }
+            }
+        } else {
+            gg = __ldcg(reinterpret_cast<const float4*>(j.g) + i);
+        }
+    }
+    if (P.world > 1) {
+        // all-reduce fused into the optimizer: push my slice to every peer, flag it, wait for theirs, sum in rank order
+        const size_t e = (size_t)j.g_off + 4 * (size_t)i;
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < kMaxWorld; ++r)
+                if (r < P.world && r != P.rank) *reinterpret_cast<float4*>(P.peer_slot[r] + e) = gg;
+        }
+        __syncthreads();
+        const int tid = threadIdx.x;
+        if (tid < P.world && tid != P.rank) {
+            // release at system scope: cumulative over the whole CTA's slot stores (ordered before it by the barrier above)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(P.peer_flags[tid] + phase_item), "r"(P.xseq) : "memory");
+            const unsigned int* f = P.my_flags + (size_t)tid * P.x_items + phase_item;
+            unsigned int cur;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(f) : "memory");
+                if ((int)(cur - P.xseq) < 0 && clock64() - t0 > kPeerSpinLimit) { atomicExch(P.err, 3); break; }
+            } while ((int)(cur - P.xseq) < 0);
+        }
+        __syncthreads();
+        if (live) {
+            float4 q[kMaxWorld];
+#pragma unroll
+            for (int r = 0; r < kMaxWorld; ++r)
+                q[r] = (r < P.world && r != P.rank) ? ldcg4(P.my_slots + (size_t)r * P.x_arena + e) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int r = 0; r < kMaxWorld; ++r) {             // rank order on every rank: replicas stay bit-identical
+                if (r < P.world) {
+                    const float4 v = (r == P.rank) ? gg : q[r];
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                }
+            }
+            gg = sum;
+        }
+    }
+    if (!live) return;
     float4* p4 = reinterpret_cast<float4*>(j.p) + i;
     float4 pp = *p4;
-    float4 gg;
-    if (j.g_part) {                                           // fold the producing GEMM's split-K partials (split order)
-        gg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        const float* base = j.g_part + 4 * (size_t)i;
-#pragma unroll 1
-        for (int z0 = 0; z0 < j.g_splits; z0 += 8) {
-            float4 q[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                q[t] = (z0 + t < j.g_splits) ? ldcg4(base + (size_t)(z0 + t) * j.g_stride) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) { gg.x += q[t].x; gg.y += q[t].y; gg.z += q[t].z; gg.w += q[t].w; }
-        }
-    } else if (P.world > 1) {                                 // all-reduce fused into the optimizer: sum the ranks' windows
-        float4 q[kMaxWorld];
-#pragma unroll
-        for (int r = 0; r < kMaxWorld; ++r)
-            q[r] = (r < P.world) ? ldcg4(P.peer_g[r] + j.g_off + 4 * (size_t)i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        gg = q[0];
-#pragma unroll
-        for (int r = 1; r < kMaxWorld; ++r) { gg.x += q[r].x; gg.y += q[r].y; gg.z += q[r].z; gg.w += q[r].w; }   // rank order
-    } else {
-        gg = __ldcg(reinterpret_cast<const float4*>(j.g) + i);
-    }
     if (P.opt_kind == 0) {                                    // SGD: p -= lr * g (src/optim.rs:29)
         if (P.grad_scale != 1.0f) { gg.x *= P.grad_scale; gg.y *= P.grad_scale; gg.z *= P.grad_scale; gg.w *= P.grad_scale; }
         pp.x -= P.sgd_lr * gg.x; pp.y -= P.sgd_lr * gg.y; pp.z -= P.sgd_lr * gg.z; pp.w -= P.sgd_lr * gg.w;
@@ -606,24 +641,6 @@ tape_step_kernel(const StepParams P) {
                 aa.decoupled = (decoupled && h_wd > 0.0f) ? 1 : 0;
                 aa.grad_scale = P.grad_scale;
             }
-            if (P.world > 1) {
-                // The grid barrier above ordered every local gradient write before this point.  CTA 0 publishes "rank
-                // `rank` finished step xseq" in every peer's window; every CTA then waits until all peers have published.
-                if (tid < P.world && tid != P.rank) {
-                    if (blockIdx.x == 0) {
-                        __threadfence_system();
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(P.peer_flags[tid] + P.rank * kFlagStride), "r"(P.xseq) : "memory");
-                    }
-                    const unsigned int* f = P.my_flags + tid * kFlagStride;
-                    unsigned int cur;
-                    const long long t0 = clock64();
-                    do {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(f) : "memory");
-                        if ((int)(cur - P.xseq) < 0 && clock64() - t0 > kPeerSpinLimit) { atomicExch(P.err, 3); break; }
-                    } while ((int)(cur - P.xseq) < 0);
-                }
-                __syncthreads();
-            }
         }
         const int j0 = P.phase_first[ph], j1 = P.phase_first[ph + 1];
         int total = 0;
@@ -638,7 +655,7 @@ tape_step_kernel(const StepParams P) {
                     break;
                 case JOB_HEAD: head_item(j, local, P, rix); break;
                 case JOB_LOSS: loss_item(j, P, red); break;
-                default: opt_item(j, local, P, aa); break;
+                default: opt_item(j, local, item, P, aa); break;
             }
         }
         TP_PROF(2 + 2 * ph);
@@ -670,8 +687,10 @@ struct tp_xchg {
     tp_ctx* ctx = nullptr;
     int rank = 0, world = 1;
     size_t arena_len = 0;
-    unsigned char* window = nullptr;     // [flags: world x 128 B][G0: arena_len f32][G1: arena_len f32]
-    size_t bytes = 0, g_off[2] = {0, 0};
+    int items = 0;                       // flags per source rank (>= optimizer-phase items of any step using this window)
+    // window: [flags: world x items u32][slots: 2 parities x world source ranks x arena_len f32]
+    unsigned char* window = nullptr;
+    size_t bytes = 0, slots_off = 0;
     unsigned char* peers[kMaxWorld] = {};    // mapped base of every rank's window (own one included)
     bool connected = false;
     unsigned int seq = 0;                // steps run through this window (flag value of the next step is seq + 1)
@@ -680,7 +699,7 @@ struct tp_xchg {
 struct tp_step {
     tp_ctx* ctx = nullptr;
     tp_xchg* xchg = nullptr;
-    const Job* jobs_dev[2] = {nullptr, nullptr};     // job list per gradient-buffer parity (same list without an exchange)
+    const Job* jobs_dev = nullptr;
     unsigned int bar_count = 0;                      // host mirror of the barrier's arrival counter
     tp_step_desc desc{};
     StepParams params{};
@@ -898,9 +917,8 @@ void build(tp_step* s, Carver& c, int sms, float* G) {
     sp.n_phases = ph;
     sp.n_jobs = (int)s->jobs.size();
     sp.bar = c.take<unsigned int>(4);
-    s->jobs_dev[0] = c.take<Job>(s->jobs.size());
-    s->jobs_dev[1] = s->xchg ? c.take<Job>(s->jobs.size()) : s->jobs_dev[0];
-    sp.jobs = s->jobs_dev[0];
+    s->jobs_dev = c.take<Job>(s->jobs.size());
+    sp.jobs = s->jobs_dev;
 }
 
 }  // namespace
@@ -917,8 +935,7 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     TP_CHECK_ARG(ctx && out, "tp_step_create: NULL argument");
     if (xchg) {
         TP_CHECK_ARG(xchg->ctx == ctx && xchg->connected, "tp_step_create: the exchange window is not connected");
-        TP_CHECK_ARG(desc && desc->materialize_grads && (size_t)desc->arena_len == xchg->arena_len,
-                     "tp_step_create: an exchange needs materialize_grads = 1 and a window of the arena's length");
+        TP_CHECK_ARG(desc && (size_t)desc->arena_len == xchg->arena_len, "tp_step_create: the exchange window was sized for another arena");
     }
     const char* why = nullptr;
     TP_CHECK_ARG(desc_ok(desc, &why), "tp_step_create: unsupported step (%s)", why ? why : "?");
@@ -943,9 +960,7 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     s->p = params; s->g = grads; s->m = m; s->v = v; s->hyper = hyper; s->result = result;
     s->xchg = xchg;
     for (tp_buf* b : {params, grads, m, v, hyper, result}) if (b) tp_buf_retain(b);
-    // with an exchange the gradients are written into the local window (double-buffered by step parity) instead of the arena
-    float* G0 = xchg ? reinterpret_cast<float*>(xchg->window + xchg->g_off[0]) : grads->ptr;
-    float* G1 = xchg ? reinterpret_cast<float*>(xchg->window + xchg->g_off[1]) : grads->ptr;
+    float* G0 = grads->ptr;
     auto fail = [&](int rc) { tp_step_destroy(s); return rc; };
     Carver sizing;
     build(s, sizing, ctx->sm_count, G0);
@@ -963,21 +978,9 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     Carver place;
     place.base = (unsigned char*)s->dev_block;
     build(s, place, ctx->sm_count, G0);
-    if (cudaMemcpyAsync((void*)s->jobs_dev[0], s->jobs.data(), s->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    if (cudaMemcpyAsync((void*)s->jobs_dev, s->jobs.data(), s->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         return fail(TP_ERR_CUDA);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);      // s->jobs is pageable host memory
-    if (xchg) {                                            // the odd-step list: same jobs, gradients into the other buffer
-        std::vector<Job> odd = s->jobs;
-        const ptrdiff_t delta = G1 - G0;
-        auto moved = [&](auto*& ptr) {
-            using T = std::remove_reference_t<decltype(ptr)>;
-            if (ptr && (const float*)ptr >= G0 && (const float*)ptr < G0 + xchg->arena_len) ptr = (T)((float*)ptr + delta);
-        };
-        for (auto& j : odd) { moved(j.C); moved(j.colsum); moved(j.g); }
-        if (cudaMemcpyAsync((void*)s->jobs_dev[1], odd.data(), odd.size() * sizeof(Job), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
-            return fail(TP_ERR_CUDA);
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(TP_ERR_CUDA);
-    }
     s->params.batch = desc->batch;
     s->params.opt_kind = desc->optimizer;
     s->params.hyper = hyper ? hyper->ptr : nullptr;
@@ -1001,6 +1004,14 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
         if (t > max_items) max_items = t;
     }
     s->grid = ctx->sm_count < max_items ? ctx->sm_count : max_items;
+    if (xchg) {
+        int opt_items = 0;
+        for (int q = s->params.phase_first[s->params.n_phases - 1]; q < s->params.phase_first[s->params.n_phases]; ++q) opt_items += s->jobs[q].items;
+        if (opt_items > xchg->items) {
+            tp::set_error("tp_step_create: %d optimizer slices but the exchange window has %d flags per rank", opt_items, xchg->items);
+            return fail(TP_ERR_INVALID);
+        }
+    }
     *out = s;
     return TP_OK;
 }
@@ -1031,13 +1042,14 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     s->bar_count += (unsigned int)(s->params.n_phases - 1) * (unsigned int)s->grid;
     if (tp_xchg* x = s->xchg) {
         x->seq += 1;
-        const int par = (int)(x->seq & 1u);
-        p.jobs = s->jobs_dev[par];
+        const size_t par = x->seq & 1u;
         p.world = x->world; p.rank = x->rank; p.xseq = x->seq;
+        p.x_items = x->items; p.x_arena = (long long)x->arena_len;
         p.my_flags = reinterpret_cast<unsigned int*>(x->window);
+        p.my_slots = reinterpret_cast<const float*>(x->window + x->slots_off) + par * x->world * x->arena_len;
         for (int r = 0; r < x->world; ++r) {
-            p.peer_flags[r] = reinterpret_cast<unsigned int*>(x->peers[r]);
-            p.peer_g[r] = reinterpret_cast<const float*>(x->peers[r] + x->g_off[par]);
+            p.peer_flags[r] = reinterpret_cast<unsigned int*>(x->peers[r]) + (size_t)x->rank * x->items;
+            p.peer_slot[r] = reinterpret_cast<float*>(x->peers[r] + x->slots_off) + (par * x->world + x->rank) * x->arena_len;
         }
     }
     cudaSetDevice(ctx->device);
@@ -1058,10 +1070,10 @@ int tp_xchg_create(tp_ctx* ctx, size_t arena_len, int rank, int world, tp_xchg**
     cudaSetDevice(ctx->device);
     tp_xchg* x = new tp_xchg();
     x->ctx = ctx; x->rank = rank; x->world = world; x->arena_len = arena_len;
-    const size_t flags = (size_t)kMaxWorld * kFlagStride * sizeof(unsigned int);
-    const size_t gbytes = (arena_len * sizeof(float) + 255) & ~(size_t)255;
-    x->g_off[0] = flags; x->g_off[1] = flags + gbytes;
-    x->bytes = flags + 2 * gbytes;
+    x->items = (int)(arena_len / 4 / kThreads) + 4 * TP_STEP_MAX_LAYERS + 8;      // one flag per 256-float4 optimizer slice
+    const size_t flags = ((size_t)world * x->items * sizeof(unsigned int) + 255) & ~(size_t)255;
+    x->slots_off = flags;
+    x->bytes = flags + 2 * (size_t)world * arena_len * sizeof(float);
     if (cudaMalloc((void**)&x->window, x->bytes) != cudaSuccess) {       // plain cudaMalloc: cudaIpcGetMemHandle needs an allocation base
         cudaGetLastError();
         tp::set_error("tp_xchg_create: cudaMalloc(%zu) failed", x->bytes);
