@@ -63,6 +63,63 @@ im2col_vec4_kernel(const float* __restrict__ x, float4* __restrict__ col, ConvGe
     }
 }
 
+// Direct convolution for a tiny contraction (K = Cin*kh*kw <= 32: the Cin = 1 first layer of both CNN configs).  A 128-wide
+// tensor-core tile would be > 70 % padding in K and the im2col + GEMM + transpose chain moves 60 MB to produce a 26 MB
+// activation.  One thread per output pixel keeps its K taps in registers and produces all Cout channels (weights and bias
+// broadcast from shared memory); stores are coalesced along ow for every channel; bias + ReLU fused.  Exact fp32, K order
+// (ci, kr, kc) ascending.  Replaces im2col + sgemm + transpose_4d + add_bias_4d (+ relu), src/tensor.rs:1221-1285, 1379-1389.
+constexpr int kDirectMaxK = 32;
+__global__ void __launch_bounds__(kThreads)
+conv_direct_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w2, const float* __restrict__ bias,
+                          float* __restrict__ y, ConvGeom g, int relu, unsigned int total_pix) {
+    extern __shared__ float sw[];                              // [K][Cout] then [Cout]
+    float* sb = sw + g.K * g.cout;
+    for (int i = threadIdx.x; i < g.K * g.cout; i += kThreads) sw[i] = __ldg(w2 + i);
+    for (int i = threadIdx.x; i < g.cout; i += kThreads) sb[i] = bias ? __ldg(bias + i) : 0.0f;
+    __syncthreads();
+    const unsigned int hw = (unsigned int)(g.ho * g.wo);
+    for (unsigned int pix = blockIdx.x * kThreads + threadIdx.x; pix < total_pix; pix += gridDim.x * kThreads) {
+        const unsigned int t = pix / (unsigned int)g.wo, ow = pix - t * (unsigned int)g.wo;
+        const unsigned int nb = t / (unsigned int)g.ho, oh = t - nb * (unsigned int)g.ho;
+        const float* xn = x + (size_t)nb * g.c * g.h * g.w;
+        const int ih0 = (int)oh * g.sh - g.ph, iw0 = (int)ow * g.sw - g.pw;
+        float tap[kDirectMaxK];
+        int ci = 0, kr = 0, kc = 0;
+#pragma unroll
+        for (int k = 0; k < kDirectMaxK; ++k) {
+            tap[k] = 0.0f;
+            if (k < g.K) {
+                const int ih = ih0 + kr * g.dh, iw = iw0 + kc * g.dw;
+                if (ih >= 0 && ih < g.h && iw >= 0 && iw < g.w) tap[k] = __ldg(xn + ((size_t)ci * g.h + ih) * g.w + iw);
+                if (++kc == g.kw) { kc = 0; if (++kr == g.kh) { kr = 0; ++ci; } }
+            }
+        }
+        float* yo = y + (size_t)nb * g.cout * hw + oh * (unsigned int)g.wo + ow;
+        for (int co0 = 0; co0 < g.cout; co0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kDirectMaxK; ++k) {
+                if (k < g.K) {
+                    const float* wr = sw + k * g.cout + co0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (co0 + j < g.cout) acc[j] = fmaf(tap[k], wr[j], acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (co0 + j < g.cout) {
+                    float v = acc[j] + sb[co0 + j];
+                    if (relu) v = fmaxf(v, 0.0f);
+                    yo[(size_t)(co0 + j) * hw] = v;
+                }
+            }
+        }
+    }
+}
+
 // gather-form adjoint of im2col (deterministic, no atomics):
 // gx[n,ci,ih,iw] (+)= sum_{kr,kc : oh,ow valid} gcol[(n,oh,ow), ci*kh*kw + kr*kw + kc]
 __global__ void __launch_bounds__(kThreads)
@@ -222,6 +279,13 @@ int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b
     if (b) TP_NEED(b, g.cout, "b");
     if (!M) return TP_OK;
     TP_CHECK_ARG(M <= 0x7fffffff, "tp_conv2d_fwd: N*Ho*Wo = %zu exceeds int range", M);
+    if (g.K <= kDirectMaxK && (size_t)(g.K + 1) * g.cout * sizeof(float) <= 40 * 1024) {
+        const size_t smem = (size_t)(g.K + 1) * g.cout * sizeof(float);
+        conv_direct_smallk_kernel<<<tp::grid_for(ctx, M, kThreads, 8), kThreads, smem, ctx->stream>>>(
+            x->ptr, w->ptr, b ? b->ptr : nullptr, y->ptr, g, relu, (unsigned int)M);
+        TP_LAUNCH_OK(ctx);
+        return TP_OK;
+    }
     TmpBuf col, out2d;
     if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;
     if ((rc = tp_buf_alloc(ctx, M * g.cout, &out2d.b))) return rc;

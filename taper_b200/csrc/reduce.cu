@@ -151,9 +151,18 @@ bias_grad4d_stage1(const float* __restrict__ g, float* __restrict__ partial, int
     const int ch = blockIdx.x;
     const int n0 = blockIdx.y * n_per_split, n1 = min(n, n0 + n_per_split);
     float acc = 0.0f;
-    for (int b = n0; b < n1; ++b) {
-        const float* p = g + ((size_t)b * c + ch) * hw;
-        for (int s = threadIdx.x; s < hw; s += kThreads) acc += __ldg(p + s);
+    if (hw >= kThreads) {
+        for (int b = n0; b < n1; ++b) {
+            const float* p = g + ((size_t)b * c + ch) * hw;
+            for (int s = threadIdx.x; s < hw; s += kThreads) acc += __ldg(p + s);
+        }
+    } else {
+        // small planes (7x7 after the last pool): flatten (image, pixel) so every thread has work
+        const int span = (n1 - n0) * hw;
+        for (int idx = threadIdx.x; idx < span; idx += kThreads) {
+            const int b = idx / hw, sidx = idx - b * hw;
+            acc += __ldg(g + ((size_t)(n0 + b) * c + ch) * hw + sidx);
+        }
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
