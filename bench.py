@@ -257,6 +257,24 @@ def kernel_rooflines(cfg_name, cfg, peaks, tf32_peak):
                     "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None,
                     "launch_us": t * 1e6, "launches_per_call": n_l, "peak_source": tc_note})
         del xs, ws, ys
+    else:
+        # CNN configs: the step's heaviest layer = the widest 3x3 conv (conv2 of either model): its im2col (HBM-bound,
+        # 4*(n_in + M*K) algorithmic bytes) and its [M,K]x[K,Cout] GEMM (tensor-bound, 2*M*K*Cout flops)
+        cin, hw_, cout = (32, 28, 32) if kind == "cnn5" else (32, 14, 64)
+        d = capi.ConvDesc(batch, cin, hw_, hw_, cout, 3, 3, 1, 1, 1, 1, 1, 1)
+        M, K = batch * hw_ * hw_, cin * 9
+        x, col, w, y = HB(batch * cin * hw_ * hw_), HB(M * K), HB(K * cout), HB(M * cout)
+        t = timeit(lambda i: capi.check(lib.tp_im2col(h, x.h, col.h, C.byref(d))), 30)
+        by = 4 * (batch * cin * hw_ * hw_ + M * K)
+        out.append({"kernel": f"im2col {batch}x{cin}x{hw_}x{hw_} 3x3 -> [{M},{K}]", "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm,
+                    "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
+        t = timeit(lambda i: capi.check(lib.tp_sgemm_rowmajor(h, 0, 0, M, cout, K, 1.0, col.h, w.h, 0.0, y.h)), 30)
+        fl = 2 * M * K * cout
+        out.append({"kernel": f"conv GEMM [{M},{K}]x[{K},{cout}] (tcgen05)", "bound": "tensor", "achieved": fl / t / 1e12, "peak": tc_peak,
+                    "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None, "launch_us": t * 1e6, "peak_source": tc_note,
+                    "note": f"N = {cout}: streams the {M * K * 4 / 1e6:.0f} MB im2col matrix once, so HBM ({M * K * 4 / t / 1e9:.0f} GB/s) bounds it, not the tensor pipe"})
+        del x, col, w, y
     # fused Adam step over a flat arena larger than L2: 28 B/param (p, g, m, v read; p, m, v written)
     n = 48 * 1024 * 1024
     p, g, m, v, hy = HB(n), HB(n), HB(n), HB(n), HB(8)
