@@ -471,7 +471,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct TcState {
     EncodeTiledFn encode = nullptr;
-    bool attr_set[4][2][2][2] = {};
+    bool attr_set[5][2][2][2] = {};
     int max_clusters[4] = {148, 74, 33, 15};      // co-resident clusters of 1/2/4/8 CTAs (queried at first use)
 };
 
@@ -506,7 +506,7 @@ template <int BN, bool A_MN, bool B_MN, bool SPLIT3>
 int launch(tp_ctx* ctx, TcState* st, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
     auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, SPLIT3>;
     constexpr int smem = Smem<BN, SPLIT3>::kTotal;
-    constexpr int bi = BN == 16 ? 0 : BN == 32 ? 1 : BN == 64 ? 2 : 3;
+    constexpr int bi = BN == 16 ? 0 : BN == 32 ? 1 : BN == 64 ? 2 : BN == 128 ? 3 : 4;
     if (!st->attr_set[bi][A_MN][B_MN][SPLIT3]) {
         TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         st->attr_set[bi][A_MN][B_MN][SPLIT3] = true;
@@ -577,7 +577,9 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
     // t_kb is shared-memory bound in both modes (operand reads of the MMAs + the lo-tile pass in 3xTF32).  A cluster that
     // does not fit in the first wave doubles the kernel, hence the measured residency limits (148 / 74 / 33 / 15).
     const int bn_min = b_mn ? 32 : 16;
-    int bn_max = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : 128;
+    // 128x256 tiles (1xTF32 only: the 3xTF32 stages would not fit) halve the B re-reads per MMA: with 128x128 SS-mode tiles the
+    // MMA operand fetch (128 B/clk) plus the TMA fill (128 B/clk) are twice the 128 B/clk shared-memory port; 128x256 needs 192.
+    int bn_max = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : (n >= 256 && mode == 2) ? 256 : 128;
     if (bn_max < bn_min) bn_max = bn_min;
     int bn = bn_max, splits = 1;
     long best = -1;
@@ -615,6 +617,7 @@ int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const
         case 16: TP_BN(16);
         case 32: TP_BN(32);
         case 64: TP_BN(64);
+        case 256: return dispatch_major<256, false>(ctx, st, ta, tb, ma, mb, p, grid);
         default: TP_BN(128);
     }
 #undef TP_BN
