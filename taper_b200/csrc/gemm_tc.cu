@@ -28,6 +28,7 @@ namespace {
 constexpr int BM = 128;              // UMMA M (cta_group::1)
 constexpr int BK = 32;               // floats per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;            // tf32: 32 bytes per instruction
+constexpr int kMaxConvK = 1536;      // implicit-GEMM conv: largest contraction (Cin*kh*kw) the per-k table behind the barriers holds
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,6 +128,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+// gather target for padding taps / k >= K of the implicit-GEMM convolution: every load is unconditional (no data-dependent
+// branch between the table lookup and the global load), padding simply reads this zero
+__device__ float g_zero_pad[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+
 // development aid: per-phase SM-clock timestamps of CTA (0,0,0), read back with tpdbg_gemm_times()
 __device__ long long g_dbg_t[16];
 #define DBG_T(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_dbg_t[slot] = clock64(); } while (0)
@@ -143,6 +148,9 @@ struct GemmParams {
     float alpha, beta;
     float* c;
     EpiArgs ep;
+    // implicit-GEMM convolution (IM2COL kernels): A(m, k) = x[n, ci, oh*sh + kr*dh - ph, ow*sw + kc*dw - pw] or 0
+    const float* x;
+    tp::ConvShape g;
 };
 
 template <int BN, bool SPLIT3>
@@ -176,9 +184,10 @@ __device__ __forceinline__ float epilogue_elem(float acc, const GemmParams& p, s
 // hardware accumulator truncates, which biases long sums of same-signed products (MNIST pixels, post-ReLU
 // activations) by ~K/3 * 2^-24.  Every kChunk k-blocks the TMEM accumulator (double-buffered) is drained
 // into fp32 registers with round-to-nearest adds while the next chunk is already being multiplied.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT3>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT3, bool IM2COL = false>
 __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+    static_assert(!IM2COL || (SPLIT3 && !A_MN), "the im2col gather is done by the 3xTF32 splitter warps into a K-major A tile");
     using S = Smem<BN, SPLIT3>;
     constexpr int kStages = S::kStages;
     constexpr int kChunk = 4;                         // k-blocks (128 elements of K) per tensor-core accumulation
@@ -195,6 +204,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* acc_full = split_bar + kStages;         // [2] accumulator buffer complete (tcgen05.commit)
     uint64_t* acc_empty = acc_full + 2;               // [2] accumulator buffer drained (3xTF32)
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    int* ktab = (int*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);      // IM2COL: per contraction index k: (input offset relative to the row's base) << 5 | tap
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -215,6 +225,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_init(acc_empty + b, 4);              // one arrival per drain warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (IM2COL) {
+        const int khw = p.g.kh * p.g.kw;
+        const int kpad = (p.k + BK - 1) / BK * BK;
+        for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+            const int ci = k / khw, r = k - ci * khw, kr = r / p.g.kw, kc = r - kr * p.g.kw;
+            // tap 31 is never valid (kh*kw <= 31): marks k >= K
+            ktab[k] = k < p.k ? ((((ci * p.g.h + kr * p.g.dh) * p.g.w + kc * p.g.dw) << 5) | r) : 31;
+        }
     }
     if (warp == 1) {                                  // TMEM allocation is owned by the MMA warp
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
@@ -239,9 +258,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int s = i % kStages;
                 const uint32_t ph = (i / kStages) & 1;
                 mbar_wait(empty_bar + s, ph ^ 1);
-                mbar_expect_tx(full_bar + s, S::kABytes + S::kBBytes);
+                mbar_expect_tx(full_bar + s, (IM2COL ? 0 : S::kABytes) + S::kBBytes);
                 const int k0 = (kb0 + i) * BK;
-                if (A_MN) {
+                if (IM2COL) {
+                    // A is gathered by warps 2-5
+                } else if (A_MN) {
 #pragma unroll
                     for (int g = 0; g < BM / 32; ++g) tma_load_2d(a_hi(s) + g * (BK * 128), &map_a, full_bar + s, m0 + 32 * g, k0);
                 } else {
@@ -306,9 +327,73 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (SPLIT3 && warp < 6) {
         // ===== warps 2-5 (3xTF32): split every landed stage into hi/lo tiles =====
         const int t = threadIdx.x - 64;               // 0..127
+        // IM2COL: this thread owns row t of the A tile = output pixel m0 + t; its 32 k-values per k-block are gathered from
+        // the NCHW input (lanes = consecutive ow: coalesced) and written as hi (the fp32 value) and lo = x - trunc_tf32(x)
+        // straight into the K-major SWIZZLE_128B layout the MMA descriptor expects (16-byte chunk j of row r at j ^ (r % 8)).
+        const float* xb = nullptr;
+        uint32_t tapmask = 0;
+        if (IM2COL) {
+            const int gm = m0 + t;
+            if (gm < p.m) {
+                const int ow = gm % p.g.wo, tq = gm / p.g.wo, oh = tq % p.g.ho, nb = tq / p.g.ho;
+                const int ih0 = oh * p.g.sh - p.g.ph, iw0 = ow * p.g.sw - p.g.pw;
+                xb = p.x + ((ptrdiff_t)nb * p.g.c * p.g.h + ih0) * p.g.w + iw0;
+                for (int kr = 0; kr < p.g.kh; ++kr)
+                    for (int kc = 0; kc < p.g.kw; ++kc) {
+                        const int ih = ih0 + kr * p.g.dh, iw = iw0 + kc * p.g.dw;
+                        if (ih >= 0 && ih < p.g.h && iw >= 0 && iw < p.g.w) tapmask |= 1u << (kr * p.g.kw + kc);
+                    }
+            }
+        }
         for (int i = 0; i < nkb; ++i) {
             const int s = i % kStages;
             const uint32_t ph = (i / kStages) & 1;
+            if (IM2COL) {
+                mbar_wait(empty_bar + s, ph ^ 1);     // the MMAs that read this stage last time have retired
+                const int k0 = (kb0 + i) * BK;
+                uint8_t* rhi = a_hi(s) + t * 128;
+                uint8_t* rlo = a_lo(s) + t * 128;
+                // all 32 gathers are issued before the first shared-memory store (the stores could alias the k tables as
+                // far as the compiler knows, which would serialise one global round trip per 16-byte chunk)
+                float v[BK];
+                const int4* kt4 = reinterpret_cast<const int4*>(ktab + k0);
+#pragma unroll
+                for (int c = 0; c < BK / 4; ++c) {
+                    const int4 kt = kt4[c];
+                    const int e4[4] = {kt.x, kt.y, kt.z, kt.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float* src = ((tapmask >> (e4[e] & 31)) & 1u) ? xb + (e4[e] >> 5) : g_zero_pad;
+                        v[4 * c + e] = __ldg(src);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < BK / 4; ++c) {
+                    float4 l;
+                    l.x = v[4 * c + 0] - __uint_as_float(__float_as_uint(v[4 * c + 0]) & 0xFFFFE000u);
+                    l.y = v[4 * c + 1] - __uint_as_float(__float_as_uint(v[4 * c + 1]) & 0xFFFFE000u);
+                    l.z = v[4 * c + 2] - __uint_as_float(__float_as_uint(v[4 * c + 2]) & 0xFFFFE000u);
+                    l.w = v[4 * c + 3] - __uint_as_float(__float_as_uint(v[4 * c + 3]) & 0xFFFFE000u);
+                    const int pc = (c ^ (t & 7)) * 16;
+                    *(float4*)(rhi + pc) = make_float4(v[4 * c + 0], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    *(float4*)(rlo + pc) = l;
+                }
+                mbar_wait(full_bar + s, ph);          // the weight tile has landed: split it
+                const float4* bh4 = (const float4*)b_hi(s);
+                float4* bl4 = (float4*)b_lo(s);
+                for (int v = t; v < S::kBBytes / 16; v += 128) {
+                    const float4 x = bh4[v];
+                    float4 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    bl4[v] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(split_bar + s);
+                continue;
+            }
             mbar_wait(full_bar + s, ph);
             // The tensor core truncates its fp32 operands to TF32 by itself (measured: scripts/tf32_round_probe.py), so the
             // landed tile already serves as `hi`; only lo = x - trunc(x) is written, elementwise at identical offsets so the
@@ -652,6 +737,51 @@ extern "C" int tpdbg_gemm_times(long long* out16) {
 }
 
 namespace tp {
+
+namespace {
+template <int BN>
+int launch_conv(tp_ctx* ctx, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
+    auto kern = gemm_tf32_kernel<BN, false, true, true, true>;
+    constexpr int smem = Smem<BN, true>::kTotal + kMaxConvK * 4 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    kern<<<grid, 320, smem, ctx->stream>>>(mb /*unused A map*/, mb, p);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+}  // namespace
+
+int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, float* out2d, const ConvShape& g) {
+    const long long M = (long long)g.n * g.ho * g.wo;
+    if (M <= 0 || M > 0x7fffffffLL || g.K < 16 || g.K > kMaxConvK) return TP_ERR_UNSUPPORTED;
+    if (g.kh * g.kw > 31 || g.cout < 32 || (g.cout & 3) || ((uintptr_t)w2 & 15)) return TP_ERR_UNSUPPORTED;
+    if ((long long)g.c * g.h * g.w >= (1LL << 26)) return TP_ERR_UNSUPPORTED;     // per-image offset must fit 26 bits of the k table
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TP_ERR_UNSUPPORTED;
+    cudaSetDevice(ctx->device);
+    const int bn = g.cout <= 32 ? 32 : g.cout <= 64 ? 64 : 128;
+    const int tiles_m = (int)((M + BM - 1) / BM), tiles_n = (g.cout + bn - 1) / bn;
+    if (tiles_m > 65535) return TP_ERR_UNSUPPORTED;
+    CUtensorMap mb;
+    if (!make_map(enc, &mb, w2, g.K, g.cout, 32, true)) return TP_ERR_UNSUPPORTED;     // weights [K, Cout]: MN-major B operand
+    GemmParams p{};
+    p.m = (int)M; p.n = g.cout; p.k = g.K;
+    p.splits = 1;
+    p.alpha = 1.0f; p.beta = 0.0f;
+    p.c = out2d;
+    p.ep = EpiArgs{nullptr, nullptr, 0};
+    p.x = x;
+    p.g = g;
+    dim3 grid(tiles_n, tiles_m, 1);
+    switch (bn) {
+        case 32: return launch_conv<32>(ctx, mb, p, grid);
+        case 64: return launch_conv<64>(ctx, mb, p, grid);
+        default: return launch_conv<128>(ctx, mb, p, grid);
+    }
+}
 
 void gemm_tc_destroy(tp_ctx* ctx) {
     TcState* st = (TcState*)ctx->tc_state;
