@@ -138,13 +138,14 @@ int gemm_simt(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, con
 int gemm_tc(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a,
             const float* b, float beta, float* c, const Epilogue& ep, int mode);
 void gemm_tc_destroy(tp_ctx* ctx);
-// Implicit-GEMM convolution forward on the tcgen05 path: out2d[M = n*ho*wo, cout] = im2col(x)[M, K] * w2[K, cout] without ever
-// materialising the im2col matrix (the A tiles are gathered from the NCHW input straight into swizzled shared memory).
+// Implicit-GEMM convolution forward on the tcgen05 path: y[n, cout, ho, wo] = (im2col(x)[M, K] * w2[K, cout]) + bias (+ ReLU)
+// without ever materialising the im2col matrix (the A tiles are gathered from the NCHW input straight into swizzled shared
+// memory) or the NHWC product (the epilogue writes NCHW).
 // Returns TP_ERR_UNSUPPORTED when the shape cannot go this way (caller falls back to im2col + GEMM).
 struct ConvShape {
     int n, c, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, ho, wo, K;
 };
-int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, float* out2d, const ConvShape& g);
+int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, const float* bias, int relu, float* y, const ConvShape& g);
 
 // Linear layers with out_features <= 16 (classifier heads), see linear_skinny.cu
 bool linear_skinny_ok(int batch, int in_f, int out_f);

@@ -286,23 +286,21 @@ int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b
         TP_LAUNCH_OK(ctx);
         return TP_OK;
     }
-    TmpBuf col, out2d;
-    if ((rc = tp_buf_alloc(ctx, M * g.cout, &out2d.b))) return rc;
-    // [M,K] x [K,Cout] -> NHWC rows  (src/tensor.rs:1262-1265); weight buffer reinterpreted as [K,Cout] (A2).
-    // 3xTF32 mode: implicit GEMM — the tensor-core kernel gathers its A tiles from x itself, the [M,K] im2col matrix
-    // (231 MB for the 32->32 layer at batch 256) never exists.  Other modes / shapes: materialised im2col + GEMM.
-    rc = TP_ERR_UNSUPPORTED;
+    // [M,K] x [K,Cout] -> NHWC rows -> NCHW + bias (src/tensor.rs:1262-1281); weight buffer reinterpreted as [K,Cout] (A2).
+    // 3xTF32 mode: implicit GEMM — the tensor-core kernel gathers its A tiles from x itself and its epilogue writes NCHW +
+    // bias (+ ReLU): neither the [M,K] im2col matrix (231 MB for the 32->32 layer at batch 256) nor the NHWC product ever
+    // exists.  Other modes / shapes: materialised im2col + GEMM + transpose.
     if (ctx->gemm_mode == 1) {
         tp::ConvShape cs{g.n, g.c, g.h, g.w, g.cout, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, g.ho, g.wo, g.K};
-        rc = tp::gemm_tc_conv_fwd(ctx, x->ptr, w->ptr, out2d.b->ptr, cs);
-        if (rc != TP_OK && rc != TP_ERR_UNSUPPORTED) return rc;
+        rc = tp::gemm_tc_conv_fwd(ctx, x->ptr, w->ptr, b ? b->ptr : nullptr, relu, y->ptr, cs);
+        if (rc != TP_ERR_UNSUPPORTED) return rc;
     }
-    if (rc == TP_ERR_UNSUPPORTED) {
-        if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;
-        if ((rc = tp_im2col(ctx, x, col.b, d))) return rc;
-        tp::Epilogue ep;
-        if ((rc = tp::gemm_rowmajor(ctx, 0, 0, (int)M, g.cout, g.K, 1.0f, col.b->ptr, w->ptr, 0.0f, out2d.b->ptr, ep))) return rc;
-    }
+    TmpBuf col, out2d;
+    if ((rc = tp_buf_alloc(ctx, M * g.cout, &out2d.b))) return rc;
+    if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;
+    if ((rc = tp_im2col(ctx, x, col.b, d))) return rc;
+    tp::Epilogue ep;
+    if ((rc = tp::gemm_rowmajor(ctx, 0, 0, (int)M, g.cout, g.K, 1.0f, col.b->ptr, w->ptr, 0.0f, out2d.b->ptr, ep))) return rc;
     int hw = g.ho * g.wo;
     nhwc_to_nchw_bias_kernel<<<dim3((g.cout + 31) / 32, (hw + 31) / 32, g.n), kThreads, 0, ctx->stream>>>(
         out2d.b->ptr, b ? b->ptr : nullptr, y->ptr, hw, g.cout, relu);

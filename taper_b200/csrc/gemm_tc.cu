@@ -345,18 +345,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
             }
         }
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % kStages;
-            const uint32_t ph = (i / kStages) & 1;
-            if (IM2COL) {
-                mbar_wait(empty_bar + s, ph ^ 1);     // the MMAs that read this stage last time have retired
-                const int k0 = (kb0 + i) * BK;
-                uint8_t* rhi = a_hi(s) + t * 128;
-                uint8_t* rlo = a_lo(s) + t * 128;
-                // all 32 gathers are issued before the first shared-memory store (the stores could alias the k tables as
-                // far as the compiler knows, which would serialise one global round trip per 16-byte chunk)
-                float v[BK];
-                const int4* kt4 = reinterpret_cast<const int4*>(ktab + k0);
+        if constexpr (IM2COL) {
+            // two k-blocks of gathers are in flight per thread: block i + 1 is issued before block i is written out
+            auto gather = [&](int i, float (&v)[BK]) {
+                const int4* kt4 = reinterpret_cast<const int4*>(ktab + (kb0 + i) * BK);
 #pragma unroll
                 for (int c = 0; c < BK / 4; ++c) {
                     const int4 kt = kt4[c];
@@ -367,6 +359,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         v[4 * c + e] = __ldg(src);
                     }
                 }
+            };
+            auto commit = [&](int i, const float (&v)[BK]) {
+                const int s = i % kStages;
+                const uint32_t ph = (i / kStages) & 1;
+                mbar_wait(empty_bar + s, ph ^ 1);     // the MMAs that read this stage last time have retired
+                uint8_t* rhi = a_hi(s) + t * 128;
+                uint8_t* rlo = a_lo(s) + t * 128;
 #pragma unroll
                 for (int c = 0; c < BK / 4; ++c) {
                     float4 l;
@@ -381,19 +380,32 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_wait(full_bar + s, ph);          // the weight tile has landed: split it
                 const float4* bh4 = (const float4*)b_hi(s);
                 float4* bl4 = (float4*)b_lo(s);
-                for (int v = t; v < S::kBBytes / 16; v += 128) {
-                    const float4 x = bh4[v];
+                for (int q = t; q < S::kBBytes / 16; q += 128) {
+                    const float4 x = bh4[q];
                     float4 l;
                     l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
                     l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
                     l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
                     l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                    bl4[v] = l;
+                    bl4[q] = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(split_bar + s);
-                continue;
+            };
+            float va[BK], vb[BK];
+            gather(0, va);
+            for (int i = 0; i < nkb; i += 2) {
+                if (i + 1 < nkb) gather(i + 1, vb);
+                commit(i, va);
+                if (i + 1 < nkb) {
+                    if (i + 2 < nkb) gather(i + 2, va);
+                    commit(i + 1, vb);
+                }
             }
+        } else
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kStages;
+            const uint32_t ph = (i / kStages) & 1;
             mbar_wait(full_bar + s, ph);
             // The tensor core truncates its fp32 operands to TF32 by itself (measured: scripts/tf32_round_probe.py), so the
             // landed tile already serves as `hi`; only lo = x - trunc(x) is written, elementwise at identical offsets so the
@@ -463,7 +475,34 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (threadIdx.x == kEpiWarp0 * 32) DBG_T(4);
     if (p.splits > 1) cluster_sync_all(); else __syncthreads();
     if (threadIdx.x == kEpiWarp0 * 32) DBG_T(5);
-    {
+    if constexpr (IM2COL) {
+        // convolution epilogue: the tile's rows are output pixels, its columns output channels; write y[n, co, oh, ow] (NCHW,
+        // what transpose_4d + add_bias_4d (+ relu) produce, src/tensor.rs:1275-1281, 1387-1388) straight from the staged
+        // accumulators: for a fixed channel consecutive rows are consecutive addresses, so the stores stay coalesced
+        constexpr int kT = 320;
+        const int hw = p.g.ho * p.g.wo;
+        // one float4 of four channels per thread-iteration: consecutive lanes = consecutive rows, so the shared-memory reads
+        // (row pitch BN + 4 floats) are conflict-free and each of the four channel stores is a coalesced run
+        for (int idx = threadIdx.x; idx < BM * (BN / 4); idx += kT) {
+            const int cq = idx / BM, r = idx - cq * BM;
+            const int gm = m0 + r, gc = n0 + 4 * cq;
+            if (gm < p.m && gc < p.n) {
+                const int nb = gm / hw, pix = gm - nb * hw;
+                const float4 a = *(const float4*)(stage + r * kPitch + 4 * cq);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                float* yo = p.c + ((size_t)nb * p.n + gc) * hw + pix;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (gc + e < p.n) {
+                        float v = av[e];
+                        if (p.ep.bias) v += __ldg(p.ep.bias + gc + e);
+                        if (p.ep.relu) v = fmaxf(v, 0.0f);
+                        yo[(size_t)e * hw] = v;
+                    }
+                }
+            }
+        }
+    } else {
         // CTA z of the cluster owns rows [z*BM/S, (z+1)*BM/S) of the tile: fold the S partial tiles in split order
         // through distributed shared memory, apply the epilogue, store coalesced.  Every warp of the CTA takes part.
         constexpr int kT = SPLIT3 ? 320 : 192;
@@ -754,7 +793,7 @@ int launch_conv(tp_ctx* ctx, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
 }
 }  // namespace
 
-int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, float* out2d, const ConvShape& g) {
+int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, const float* bias, int relu, float* y, const ConvShape& g) {
     const long long M = (long long)g.n * g.ho * g.wo;
     if (M <= 0 || M > 0x7fffffffLL || g.K < 16 || g.K > kMaxConvK) return TP_ERR_UNSUPPORTED;
     if (g.kh * g.kw > 31 || g.cout < 32 || (g.cout & 3) || ((uintptr_t)w2 & 15)) return TP_ERR_UNSUPPORTED;
@@ -771,8 +810,8 @@ int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, float* out2d,
     p.m = (int)M; p.n = g.cout; p.k = g.K;
     p.splits = 1;
     p.alpha = 1.0f; p.beta = 0.0f;
-    p.c = out2d;
-    p.ep = EpiArgs{nullptr, nullptr, 0};
+    p.c = y;
+    p.ep = EpiArgs{bias, nullptr, relu};
     p.x = x;
     p.g = g;
     dim3 grid(tiles_n, tiles_m, 1);
