@@ -264,17 +264,24 @@ def kernel_rooflines(cfg_name, cfg, peaks, tf32_peak):
         d = capi.ConvDesc(batch, cin, hw_, hw_, cout, 3, 3, 1, 1, 1, 1, 1, 1)
         M, K = batch * hw_ * hw_, cin * 9
         x, col, w, y = HB(batch * cin * hw_ * hw_), HB(M * K), HB(K * cout), HB(M * cout)
+        bvec = HB(cout)
+        t = timeit(lambda i: capi.check(lib.tp_conv2d_fwd(h, x.h, w.h, bvec.h, y.h, C.byref(d), 1)), 30)
+        fl = 2 * M * K * cout
+        out.append({"kernel": f"conv2d_relu fwd {batch}x{cin}x{hw_}x{hw_} -> {cout} ch, 3x3: implicit GEMM on tcgen05 (3xTF32), NCHW+bias+ReLU epilogue",
+                    "bound": "tensor", "achieved": fl / t / 1e12, "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak,
+                    "traffic": None, "launch_us": t * 1e6, "peak_source": tc_note,
+                    "note": f"{(M + 127) // 128} tiles x {K // 32} k-blocks, N = {cout}: bound by the gather warps and per-tile setup, not by the tensor pipe"})
         t = timeit(lambda i: capi.check(lib.tp_im2col(h, x.h, col.h, C.byref(d))), 30)
         by = 4 * (batch * cin * hw_ * hw_ + M * K)
-        out.append({"kernel": f"im2col {batch}x{cin}x{hw_}x{hw_} 3x3 -> [{M},{K}]", "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm,
-                    "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6,
+        out.append({"kernel": f"im2col {batch}x{cin}x{hw_}x{hw_} 3x3 -> [{M},{K}] (fallback / full-adjoint path)", "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm,
+                    "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6, "probe": True,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
         t = timeit(lambda i: capi.check(lib.tp_sgemm_rowmajor(h, 0, 0, M, cout, K, 1.0, col.h, w.h, 0.0, y.h)), 30)
         fl = 2 * M * K * cout
-        out.append({"kernel": f"conv GEMM [{M},{K}]x[{K},{cout}] (tcgen05)", "bound": "tensor", "achieved": fl / t / 1e12, "peak": tc_peak,
-                    "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None, "launch_us": t * 1e6, "peak_source": tc_note,
+        out.append({"kernel": f"conv GEMM [{M},{K}]x[{K},{cout}] on the materialised im2col matrix (fallback / full-adjoint path)", "bound": "tensor", "achieved": fl / t / 1e12, "peak": tc_peak,
+                    "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None, "launch_us": t * 1e6, "peak_source": tc_note, "probe": True,
                     "note": f"N = {cout}: streams the {M * K * 4 / 1e6:.0f} MB im2col matrix once, so HBM ({M * K * 4 / t / 1e9:.0f} GB/s) bounds it, not the tensor pipe"})
-        del x, col, w, y
+        del x, col, w, y, bvec
     # the operator boundary itself at a tensor-core-sized problem: tp_sgemm_rowmajor 8192^3 (BASELINE metric "GEMM %TC-peak")
     try:
         nn_ = 8192
