@@ -46,7 +46,10 @@ CONFIGS = {
              "configs[2](i): Conv3x3-ReLU-MaxPool x2 + Linear, batch 256, Adam"),
     "cnn5": ("CNN5", ("cnn5", None), 256, "adam", 0.01, 1e-4, (1, 28, 28),
              "configs[2](ii): examples/train_mnist_cnn.rs 5-conv CNN, batch 256, Adam"),
+    "cfg5": ("CNN5", ("cnn5", None), 1024, "adamw", 0.01, 1e-4, (1, 28, 28),
+             "configs[4]: 5-conv CNN, batch 1024/GPU, AdamW + StepLR(5 epochs, 0.8) stepped every 59-step epoch, synthetic 28x28x1"),
 }
+EPOCH_STEPS = 59           # 60000 / 1024: cfg5 steps its LR scheduler (src/optim.rs:190-219) once per epoch-equivalent
 DATASET_N = 60000          # MNIST-sized: 60000 x 784 fp32 = 188 MB, larger than the 126 MB L2
 
 
@@ -386,10 +389,14 @@ def run_ours(args, cfg_name, cfg):
     l0 = host.launches()
     w0 = time.perf_counter()
     e0.record()
+    sched_epoch = 0
     for i in range(args.steps):
         if tr.pending() >= 6:
             last = tr.fetch()
         tr.step_resident(batch)
+        if cfg_name == "cfg5" and i % EPOCH_STEPS == EPOCH_STEPS - 1:      # StepLR(step 5, gamma 0.8) + optimizer.set_lr (src/train.rs:212-216)
+            sched_epoch += 1
+            tr.set_lr(lr * 0.8 ** (sched_epoch // 5))
     e1.record()
     while tr.pending():
         last = tr.fetch()
@@ -528,6 +535,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.steps is None:
         args.steps = (20000 if args.config in ("cfg1", "cfg2", "example_mlp") else 300) if args.impl == "ours" else 200
+        if args.config == "cfg5" and args.impl == "reference":
+            args.steps = 10
     if args.impl == "reference":
         run_reference(args, args.config, cfg)
     else:
