@@ -292,7 +292,9 @@ int tp_cursor_advance(tp_ctx*, tp_buf* cursor_i32, int delta, int modulo);
  *                       perm[(cursor + r) % n_perm] are gathered in-kernel; cursor advances by batch.
  *                       cursor_value >= 0 is the caller's mirror of *cursor (saves the kernel a dependent
  *                       load), -1 reads the device word.  result_host (optional) is a pinned, device-
- *                       mapped {loss, correct} slot the kernel also writes, so no separate D2H copy is needed.
+ *                       mapped {loss, correct, seq} slot (3 words) the kernel also writes, so no separate D2H copy
+ *                       is needed; with result_seq != 0 the kernel stores it to word 2 after the other two
+ *                       (system-scope fence in between), so the host can poll the slot instead of a CUDA event.
  *                       Writes result = {loss, #correct}; Adam state (hyper, see tp_adam_hyper_init)
  *                       advances on the device exactly as tp_adam_advance + tp_adam_step_dev would.
  * ------------------------------------------------------------------------------------------- */
@@ -329,7 +331,8 @@ int tp_step_supported(const tp_step_desc* desc);
 int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v,
                    tp_buf* hyper, tp_buf* result, tp_xchg* xchg, tp_step** out);
 int tp_step_run(tp_ctx* ctx, tp_step* step, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32,
-                tp_buf* cursor_i32, int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host);
+                tp_buf* cursor_i32, int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host,
+                uint32_t result_seq);
 int tp_step_info(const tp_step* step, int* n_phases, int* n_jobs, int* grid);
 /* per-CTA SM-clock stamps of the last run: [grid][slots] = entry, setup done, then {work done, barrier passed}
  * for each phase (evidence for profiles/: where the step's time goes) */

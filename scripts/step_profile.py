@@ -93,7 +93,7 @@ def main():
 
     def run():
         check(lib.tp_step_run(ctx.h, step, x.h, y.h, perm.h if perm else None, cursor.h if cursor else None, n if a.resident else 0,
-                              -1, 0.01, 1.0 / world, None))
+                              -1, 0.01, 1.0 / world, None, 0))
 
     nph, njobs, grid = C.c_int(), C.c_int(), C.c_int()
     check(lib.tp_step_info(step, C.byref(nph), C.byref(njobs), C.byref(grid)))

@@ -2,6 +2,7 @@
 // CUDA-graph capture of one whole training step.
 #include "taper_internal.hpp"
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -145,8 +146,10 @@ struct Trainer::Impl {
     std::map<std::vector<size_t>, Slot> slots;               // key: full input shape [B, sample...]
     Tensor result;                                           // device {loss, correct}
     Tensor loss_view, correct_view;
-    float* ring = nullptr;                                   // pinned kRing x 2 floats
+    float* ring = nullptr;                                   // pinned kRing x 4 floats: {loss, correct, seq bits, pad}
     tp_event* events[kRing] = {};
+    uint32_t slot_seq[kRing] = {};                           // != 0: the step kernel publishes this value in the slot (host polls)
+    uint32_t next_seq = 1;
     size_t head = 0, tail = 0;                               // FIFO of outstanding results
     // resident dataset
     tp_buf *ds_images = nullptr, *ds_labels = nullptr, *ds_perm = nullptr, *ds_cursor = nullptr;
@@ -175,12 +178,22 @@ struct Trainer::Impl {
 
     size_t ds_cursor_host = 0;                               // host mirror of the device cursor
 
-    float* next_result_slot() const { return ring + 2 * (head % kRing); }
-    // in_kernel: the step kernel already wrote {loss, correct} into next_result_slot() (mapped pinned memory)
+    float* next_result_slot() const { return ring + 4 * (head % kRing); }
+    uint32_t next_result_seq() {                             // never 0
+        if (next_seq == 0) next_seq = 1;
+        return next_seq;
+    }
+    // in_kernel: the step kernel writes {loss, correct} and then the sequence word into next_result_slot() (mapped pinned
+    // memory): no D2H copy and no CUDA event on the stream — fetch() polls the slot
     void enqueue_result(bool in_kernel = false) {
         size_t i = head % kRing;
-        if (!in_kernel) check(tp_buf_download_async(ctx(), result.buf(), ring + 2 * i, 2));
-        check(tp_event_record(ctx(), events[i]));
+        if (in_kernel) {
+            slot_seq[i] = next_seq++;
+        } else {
+            slot_seq[i] = 0;
+            check(tp_buf_download_async(ctx(), result.buf(), ring + 4 * i, 2));
+            check(tp_event_record(ctx(), events[i]));
+        }
         head++;
     }
 
@@ -212,7 +225,8 @@ Trainer::Trainer(std::shared_ptr<nn::Module> m, std::shared_ptr<optim::Optimizer
     p_->loss_view = Tensor::adopt(l, {1});
     p_->correct_view = Tensor::adopt(c, {1});
     void* ring = nullptr;
-    check(tp_host_alloc_pinned(kRing * 2 * sizeof(float), &ring));
+    check(tp_host_alloc_pinned(kRing * 4 * sizeof(float), &ring));
+    std::memset(ring, 0, kRing * 4 * sizeof(float));
     p_->ring = (float*)ring;
     for (auto& e : p_->events) check(tp_event_create(ctx(), &e));
 }
@@ -287,8 +301,22 @@ size_t Trainer::pending() const { return p_->head - p_->tail; }
 StepResult Trainer::fetch() {
     if (p_->head == p_->tail) panic("Trainer::fetch: no step outstanding");
     size_t i = p_->tail % kRing;
-    check(tp_event_sync(p_->events[i]));
-    StepResult r{p_->ring[2 * i], p_->ring[2 * i + 1]};
+    if (p_->slot_seq[i]) {
+        // the step kernel publishes the slot itself: spin on the sequence word (bounded: a lost kernel must not hang the host)
+        volatile uint32_t* w = reinterpret_cast<volatile uint32_t*>(p_->ring + 4 * i + 2);
+        auto t0 = std::chrono::steady_clock::now();
+        uint64_t spins = 0;
+        while (*w != p_->slot_seq[i]) {
+            if ((++spins & 0xFFFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+                check(tp_sync(ctx()));
+                if (*w != p_->slot_seq[i]) panic("Trainer::fetch: the step kernel did not publish its result");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        check(tp_event_sync(p_->events[i]));
+    }
+    StepResult r{p_->ring[4 * i], p_->ring[4 * i + 1]};
     p_->tail++;
     return r;
 }
@@ -338,7 +366,8 @@ void Trainer::train_batch_async(const float* images, const float* labels, size_t
     }
     if (fs) {
         // the whole loop body (src/train.rs:106-138) as one persistent kernel walking the compiled tape
-        check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, -1, optimizer->lr(), optimizer->grad_scale(), p.next_result_slot()));
+        check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, -1, optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(),
+                          p.next_result_seq()));
         if (pinned) {
             check(tp_event_record(c, s.done[k]));
             s.done_valid[k] = true;
@@ -417,7 +446,7 @@ void Trainer::train_batch_resident(size_t batch) {
     if (tp_step* fst = use_fused_ ? p.fused_step(*this, batch, p.ds_sample) : nullptr) {
         // batch rows are gathered out of the resident dataset inside the step kernel; the cursor advances there too
         check(tp_step_run(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, (int)p.ds_cursor_host,
-                          optimizer->lr(), optimizer->grad_scale(), p.next_result_slot()));
+                          optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(), p.next_result_seq()));
         p.ds_cursor_host = (p.ds_cursor_host + batch) % p.ds_n;
         optimizer->note_device_step();
         fused_steps_++;

@@ -78,7 +78,8 @@ struct StepParams {
     int* cursor;
     int n_perm, batch;
     int cursor_value;                // host mirror of *cursor (>= 0), or -1: read the device word
-    float* result_host;              // optional mapped pinned {loss, correct} slot of this step (no separate D2H copy)
+    float* result_host;              // optional mapped pinned {loss, correct, seq} slot of this step (no separate D2H copy)
+    unsigned int result_seq;         // written (as bits) to result_host[2] after loss and correct: the host polls it
     unsigned int* bar;               // arrival counter of the grid barrier
     unsigned int bar_base;           // its value when this launch starts (tracked by the host)
     int opt_kind;                    // 0 SGD, 1 Adam, 2 AdamW
@@ -501,7 +502,13 @@ __device__ void loss_item(const Job& j, const StepParams& P, float* sm /* >= 16 
         const float loss = sa / (float)j.M;                   // acc / b as f32 (src/loss.rs:164)
         j.result[0] = loss;
         j.result[1] = sh;
-        if (P.result_host) { P.result_host[0] = loss; P.result_host[1] = sh; }
+        if (P.result_host) {
+            P.result_host[0] = loss; P.result_host[1] = sh;
+            if (P.result_seq) {                               // publish: the host spins on this word instead of a CUDA event
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(P.result_host + 2) = P.result_seq;
+            }
+        }
     }
     __syncthreads();
 }
@@ -1017,7 +1024,7 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
 }
 
 int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32, tp_buf* cursor_i32,
-                int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host) {
+                int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq) {
     TP_CHECK_ARG(ctx && s && s->ctx == ctx, "tp_step_run: NULL or foreign step");
     TP_CHECK_ARG(!ctx->capturing, "tp_step_run: a cooperative launch cannot be captured into a CUDA graph");
     const int in = s->desc.dims[0];
@@ -1037,6 +1044,7 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     p.cursor_value = perm_i32 ? cursor_value : -1;
     TP_CHECK_ARG(cursor_value < n_perm || !perm_i32, "tp_step_run: cursor_value %d outside the dataset", cursor_value);
     p.result_host = result_host;
+    p.result_seq = result_host ? result_seq : 0u;
     p.world = 1; p.rank = 0;
     p.bar_base = s->bar_count;
     s->bar_count += (unsigned int)(s->params.n_phases - 1) * (unsigned int)s->grid;
