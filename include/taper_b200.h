@@ -263,6 +263,11 @@ int tp_adam_advance(tp_ctx*, tp_buf* hyper);
 int tp_adam_step_dev(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, const tp_buf* hyper,
                      float grad_scale, int decoupled, size_t n);
 int tp_decay_dev(tp_ctx*, tp_buf* p, const tp_buf* hyper, size_t n);
+/* the same over up to any number of slices of the flat arenas in one launch per 32 slices: modes[i] = 1 Adam / AdamW step,
+ * 2 AdamW decay only (a parameter whose gradient is None still decays, src/optim.rs:154-161), 0 skip (Adam skips
+ * gradient-less parameters, :93).  Slices start at multiples of 4 elements and are padded to 4 with zeros. */
+int tp_adam_step_segments(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, const tp_buf* hyper, float grad_scale,
+                          int decoupled, const int64_t* offsets, const int64_t* lengths, const int* modes, int n_segments);
 /* lr * sqrt(1 - b2^t) / (1 - b1^t) with f32::powi semantics   src/optim.rs:88-90 */
 float tp_adam_step_size(float lr, float beta1, float beta2, int t);
 

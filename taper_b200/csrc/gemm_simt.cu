@@ -120,8 +120,14 @@ gemm_simt_kernel(int m, int n, int k, float alpha, const float* __restrict__ A, 
                     int gj = j0 + tx * TN + b;
                     if (gj >= n) continue;
                     size_t idx = (size_t)gi * n + gj;
-                    float sum = 0.0f;
-                    for (int z = 0; z < (int)gridDim.z; ++z) sum += __ldcg(partial + (size_t)z * mn + idx);
+                    float sum = 0.0f;                  // split order; 8 loads in flight per output instead of one round trip per split
+                    for (int z0 = 0; z0 < (int)gridDim.z; z0 += 8) {
+                        float q[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) q[u] = (z0 + u < (int)gridDim.z) ? __ldcg(partial + (size_t)(z0 + u) * mn + idx) : 0.0f;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) sum += q[u];
+                    }
                     float v = alpha * sum;
                     if (beta != 0.0f) v += beta * C[idx];
                     C[idx] = apply_epilogue(v, ep, idx, gj);
@@ -137,7 +143,13 @@ splitk_fold_kernel(const float* __restrict__ partial, float* __restrict__ C, siz
     const size_t stride = (size_t)gridDim.x * 256;
     for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < mn; idx += stride) {
         float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += partial[(size_t)z * mn + idx];
+        for (int z0 = 0; z0 < splits; z0 += 8) {
+            float q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = (z0 + u < splits) ? partial[(size_t)(z0 + u) * mn + idx] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += q[u];
+        }
         float v = alpha * s;
         if (beta != 0.0f) v += beta * C[idx];
         C[idx] = apply_epilogue(v, ep, idx, (int)(idx % n));

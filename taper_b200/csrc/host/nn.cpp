@@ -347,11 +347,16 @@ void Adam::step_impl(bool decoupled) {
     if (a.all_have_grad()) {
         check(tp_adam_step_dev(c, a.p, a.g, a.m, a.v, a.hyper, grad_scale_, decoupled ? 1 : 0, a.total));
     } else {
+        // some parameters have no gradient (None): Adam skips them, AdamW still decays them — one multi-tensor launch
+        std::vector<int64_t> offs, lens;
+        std::vector<int> modes;
         for (size_t i = 0; i < a.params.size(); ++i) {
-            size_t n = a.params[i].numel();
-            if (a.params[i].impl()->has_grad) check(tp_adam_step_dev(c, a.ps[i], a.gs[i], a.ms[i], a.vs[i], a.hyper, grad_scale_, decoupled ? 1 : 0, n));
-            else if (decoupled) check(tp_decay_dev(c, a.ps[i], a.hyper, n));     // AdamW decays grad-less params too (:154-161)
+            offs.push_back((int64_t)a.off[i]);
+            lens.push_back((int64_t)a.params[i].numel());
+            modes.push_back(a.params[i].impl()->has_grad ? 1 : (decoupled ? 2 : 0));
         }
+        check(tp_adam_step_segments(c, a.p, a.g, a.m, a.v, a.hyper, grad_scale_, decoupled ? 1 : 0, offs.data(), lens.data(), modes.data(),
+                                    (int)offs.size()));
     }
     a.bump_versions();
 }

@@ -148,8 +148,16 @@ skinny_bwd_kernel(BwdArgs a) {
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) {
             if (o < a.out_f) {
+                // split order; the loads of a batch are issued before the first add (one L2 round trip per 8 splits, not per split)
                 float s = 0.0f;
-                for (int z = 0; z < a.row_splits; ++z) s += __ldcg(base + (size_t)z * per + o * kThreads + tid);      // split order
+                for (int z0 = 0; z0 < a.row_splits; z0 += 8) {
+                    float q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        q[u] = (z0 + u < a.row_splits) ? __ldcg(base + (size_t)(z0 + u) * per + o * kThreads + tid) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s += q[u];
+                }
                 float* d = a.dw + (size_t)o * a.in_f + i;
                 *d = a.acc_dw ? *d + s : s;
             }
@@ -157,7 +165,14 @@ skinny_bwd_kernel(BwdArgs a) {
     }
     if (cb == 0 && a.db && tid < a.out_f) {
         float s = 0.0f;
-        for (int z = 0; z < a.row_splits; ++z) s += __ldcg(base + (size_t)z * per + (size_t)a.out_f * kThreads + tid);
+        for (int z0 = 0; z0 < a.row_splits; z0 += 8) {
+            float q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                q[u] = (z0 + u < a.row_splits) ? __ldcg(base + (size_t)(z0 + u) * per + (size_t)a.out_f * kThreads + tid) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += q[u];
+        }
         a.db[tid] = a.acc_db ? a.db[tid] + s : s;
     }
 }

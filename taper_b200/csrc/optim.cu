@@ -123,6 +123,49 @@ decay_dev_kernel(float* __restrict__ p, size_t n, const float* __restrict__ h) {
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) p[i] *= d;
 }
 
+// Multi-tensor form for arenas where some parameters have no gradient this step (the reference's conv weights):
+// one launch over up to kMaxSeg slices of the flat arena.  mode 1: Adam / AdamW step; mode 2: AdamW's decoupled decay only
+// (parameters without a gradient still decay, src/optim.rs:154-161).  blockIdx.y = slice.
+constexpr int kMaxSeg = 32;
+struct SegTable {
+    long long off[kMaxSeg];          // element offset of the slice in the arenas (multiple of 4)
+    int n4[kMaxSeg];                 // float4 count (slices are padded to 4 with zeros)
+    int mode[kMaxSeg];
+};
+
+__global__ void __launch_bounds__(kThreads)
+adam_dev_segments_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                         const __grid_constant__ SegTable t, const float* __restrict__ h, float grad_scale, int decoupled) {
+    const int sgm = blockIdx.y;
+    const int mode = t.mode[sgm];
+    const size_t n4 = (size_t)t.n4[sgm];
+    float4* p4 = reinterpret_cast<float4*>(p + t.off[sgm]);
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    if (mode == 2) {
+        if (!(h[H_WD] > 0.0f)) return;
+        const float d = h[H_DECAY];
+        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+            float4 pp = p4[i];
+            pp.x *= d; pp.y *= d; pp.z *= d; pp.w *= d;
+            p4[i] = pp;
+        }
+        return;
+    }
+    AdamArgs a{h[H_SS], h[H_B1], h[H_B2], h[H_EPS], decoupled ? 0.0f : h[H_WD], grad_scale, h[H_DECAY],
+               (decoupled && h[H_WD] > 0.0f) ? 1 : 0};
+    const float4* g4 = reinterpret_cast<const float4*>(g + t.off[sgm]);
+    float4* m4 = reinterpret_cast<float4*>(m + t.off[sgm]);
+    float4* v4 = reinterpret_cast<float4*>(v + t.off[sgm]);
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p4[i], gg = __ldg(g4 + i), mm = m4[i], vv = v4[i];
+        adam_elem(pp.x, gg.x, mm.x, vv.x, a);
+        adam_elem(pp.y, gg.y, mm.y, vv.y, a);
+        adam_elem(pp.z, gg.z, mm.z, vv.z, a);
+        adam_elem(pp.w, gg.w, mm.w, vv.w, a);
+        p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    }
+}
+
 int launch_adam(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, size_t n, const AdamArgs& a, const char* fn) {
     TP_CHECK_ARG(ctx, "%s: NULL ctx", fn);
     TP_NEED(p, n, "p"); TP_NEED(g, n, "g"); TP_NEED(m, n, "m"); TP_NEED(v, n, "v");
@@ -222,6 +265,35 @@ int tp_adam_step_dev(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf*
     if (done < n) {
         adam_dev_scalar_kernel<<<tp::grid_for(ctx, n - done, kThreads), kThreads, 0, ctx->stream>>>(
             p->ptr + done, g->ptr + done, m->ptr + done, v->ptr + done, n - done, hyper->ptr, grad_scale, decoupled);
+        TP_LAUNCH_OK(ctx);
+    }
+    return TP_OK;
+}
+
+int tp_adam_step_segments(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, const tp_buf* hyper, float grad_scale,
+                          int decoupled, const int64_t* offsets, const int64_t* lengths, const int* modes, int n_segments) {
+    TP_CHECK_ARG(ctx && offsets && lengths && modes && n_segments >= 0, "tp_adam_step_segments: bad arguments");
+    TP_NEED(hyper, H_COUNT, "hyper");
+    TP_CHECK_ARG(p && g && m && v, "tp_adam_step_segments: NULL arena");
+    TP_CHECK_ARG(!(((uintptr_t)p->ptr | (uintptr_t)g->ptr | (uintptr_t)m->ptr | (uintptr_t)v->ptr) & 15), "tp_adam_step_segments: arenas must be 16-byte aligned");
+    for (int s0 = 0; s0 < n_segments; s0 += kMaxSeg) {
+        SegTable t{};
+        int cnt = 0, max_n4 = 0;
+        for (int s = s0; s < n_segments && cnt < kMaxSeg; ++s) {
+            if (modes[s] == 0 || lengths[s] <= 0) continue;
+            const int64_t n_pad = (lengths[s] + 3) & ~(int64_t)3;
+            TP_CHECK_ARG(offsets[s] >= 0 && offsets[s] % 4 == 0 && (size_t)(offsets[s] + n_pad) <= p->n && (size_t)(offsets[s] + n_pad) <= g->n &&
+                             (size_t)(offsets[s] + n_pad) <= m->n && (size_t)(offsets[s] + n_pad) <= v->n,
+                         "tp_adam_step_segments: slice %d outside the arenas or not 16-byte aligned", s);
+            t.off[cnt] = offsets[s];
+            t.n4[cnt] = (int)(n_pad / 4);
+            t.mode[cnt] = modes[s];
+            if (t.n4[cnt] > max_n4) max_n4 = t.n4[cnt];
+            ++cnt;
+        }
+        if (!cnt) continue;
+        dim3 grid(tp::grid_for(ctx, max_n4, kThreads, 2), cnt);
+        adam_dev_segments_kernel<<<grid, kThreads, 0, ctx->stream>>>(p->ptr, g->ptr, m->ptr, v->ptr, t, hyper->ptr, grad_scale, decoupled);
         TP_LAUNCH_OK(ctx);
     }
     return TP_OK;

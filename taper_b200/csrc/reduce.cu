@@ -112,7 +112,13 @@ colsum_fused_kernel(const float* __restrict__ g, float* __restrict__ partial, fl
     if (s_last && ty == 0 && col < cols) {
         __threadfence();
         float s = 0.0f;
-        for (int j = 0; j < (int)gridDim.y; ++j) s += __ldcg(partial + (size_t)j * cols + col);
+        for (int j0 = 0; j0 < (int)gridDim.y; j0 += 8) {       // split order, 8 loads in flight
+            float q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = (j0 + u < (int)gridDim.y) ? __ldcg(partial + (size_t)(j0 + u) * cols + col) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += q[u];
+        }
         s *= scale;
         out[col] = accumulate ? out[col] + s : s;
     }
@@ -123,7 +129,13 @@ fold_partials(const float* __restrict__ partial, float* __restrict__ out, int n,
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     float s = 0.0f;
-    for (int j = 0; j < splits; ++j) s += partial[(size_t)j * n + i];
+    for (int j0 = 0; j0 < splits; j0 += 8) {                   // split order, 8 loads in flight
+        float q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = (j0 + u < splits) ? partial[(size_t)(j0 + u) * n + i] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += q[u];
+    }
     s *= scale;
     out[i] = accumulate ? out[i] + s : s;
 }
