@@ -18,11 +18,13 @@ __global__ void __launch_bounds__(kThreads)
 maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int* __restrict__ arg, PoolGeom g, size_t total) {
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
-        int ow = (int)(i % g.wo);
-        size_t t = i / g.wo;
-        int oh = (int)(t % g.ho);
-        size_t plane = t / g.ho;                       // n*C + c
-        size_t base = plane * g.h * g.w;
+        // total <= 2^31 (make_geom): 32-bit index arithmetic
+        const unsigned int iu = (unsigned int)i;
+        const unsigned int tq = iu / (unsigned int)g.wo;
+        int ow = (int)(iu - tq * (unsigned int)g.wo);
+        const unsigned int pl = tq / (unsigned int)g.ho;      // n*C + c
+        int oh = (int)(tq - pl * (unsigned int)g.ho);
+        size_t base = (size_t)pl * g.h * g.w;
         float best = -INFINITY;
         size_t bi = base;                              // "any valid default" (src/tensor.rs:1432)
         for (int kr = 0; kr < g.kh; ++kr) {
@@ -46,10 +48,12 @@ maxpool_bwd_gather_kernel(const float* __restrict__ gout, const int* __restrict_
                           PoolGeom g, size_t total) {
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
-        int iw = (int)(i % g.w);
-        size_t t = i / g.w;
-        int ih = (int)(t % g.h);
-        size_t plane = t / g.h;
+        // total <= 2^31 (make_geom): 32-bit index arithmetic
+        const unsigned int iu = (unsigned int)i;
+        const unsigned int tq = iu / (unsigned int)g.w;
+        int iw = (int)(iu - tq * (unsigned int)g.w);
+        const unsigned int plane = tq / (unsigned int)g.h;
+        int ih = (int)(tq - plane * (unsigned int)g.h);
         int oh_lo = (ih + g.ph - g.kh + 1 + g.sh - 1);
         oh_lo = oh_lo <= 0 ? 0 : oh_lo / g.sh;
         int oh_hi = min(g.ho - 1, (ih + g.ph) / g.sh);
@@ -116,10 +120,12 @@ avgpool_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, Pool
     const size_t stride = (size_t)gridDim.x * kThreads;
     const float pool = (float)(g.kh * g.kw);
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
-        int iw = (int)(i % g.w);
-        size_t t = i / g.w;
-        int ih = (int)(t % g.h);
-        size_t plane = t / g.h;
+        // total <= 2^31 (make_geom): 32-bit index arithmetic
+        const unsigned int iu = (unsigned int)i;
+        const unsigned int tq = iu / (unsigned int)g.w;
+        int iw = (int)(iu - tq * (unsigned int)g.w);
+        const unsigned int plane = tq / (unsigned int)g.h;
+        int ih = (int)(tq - plane * (unsigned int)g.h);
         int oh_lo = (ih + g.ph - g.kh + 1 + g.sh - 1);
         oh_lo = oh_lo <= 0 ? 0 : oh_lo / g.sh;
         int oh_hi = min(g.ho - 1, (ih + g.ph) / g.sh);
@@ -129,7 +135,7 @@ avgpool_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, Pool
         float acc = 0.0f;
         for (int oh = oh_lo; oh <= oh_hi; ++oh)
             for (int ow = ow_lo; ow <= ow_hi; ++ow)
-                acc += __ldg(gout + (plane * g.ho + oh) * g.wo + ow) / pool;     // g/pool_size per tap (src/tensor.rs:1628)
+                acc += __ldg(gout + ((size_t)plane * g.ho + oh) * g.wo + ow) / pool;     // g/pool_size per tap (src/tensor.rs:1628)
         gin[i] = accumulate ? gin[i] + acc : acc;
     }
 }
