@@ -356,7 +356,18 @@ def run_ours(args, cfg_name, cfg):
         tr.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
         tr.broadcast_params(0)
         if not args.nccl_only:
-            tr.peer_exchange_init(dist)         # fused step: gradient exchange inside the step kernel over NVLink peer memory
+            # fused step: gradient exchange inside the step kernel over NVLink peer memory.  Every rank must take the same
+            # path, so a rank that cannot map its peers (no P2P / IPC) sends everybody back to the NCCL-in-graph path.
+            ok = 1
+            try:
+                tr.peer_exchange_init(dist)
+            except Exception as e:
+                ok = 0
+                print(f"rank {rank}: peer exchange unavailable ({e}); falling back to the NCCL allreduce", file=sys.stderr)
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                tr.set_use_fused(False)
 
     # each rank owns a shard: its own resident dataset (weak scaling: batch/GPU fixed)
     X, Y = synthetic(DATASET_N, sample_shape, 1 + rank)

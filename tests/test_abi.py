@@ -65,3 +65,44 @@ def test_conv_and_pool_out_dims():                      # src/tensor.rs:1254-125
     assert (ho.value, wo.value) == (14, 14)
     bad = capi.ConvDesc(4, 1, 2, 2, 32, 5, 5, 1, 1, 0, 0, 1, 1)
     assert capi.lib.tp_conv2d_out_dims(C.byref(bad), C.byref(ho), C.byref(wo)) == 1
+
+
+def test_rust_ffi_block_covers_every_declared_symbol():
+    """rust/taper-b200-sys/src/lib.rs is generated from the headers (scripts/gen_rust_ffi.py): it must not drift."""
+    import os
+    import re
+    from taper_b200 import capi
+    path = os.path.join(capi.ROOT, "rust", "taper-b200-sys", "src", "lib.rs")
+    names = set(re.findall(r"pub fn (tp_\w+)\(", open(path).read()))
+    assert names == set(capi.declared_symbols()), sorted(names ^ set(capi.declared_symbols()))
+
+
+def test_step_supported_draws_the_line_without_a_gpu():
+    """tp_step_supported only inspects the description: chains of Linear(+ReLU) with widths % 4 == 0, <= 16 classes,
+    below 1.5 GFLOP per step (larger steps belong on the tcgen05 GEMM path)."""
+    import ctypes as C
+    from taper_b200 import capi
+
+    def desc(dims, batch, opt=1):
+        d = capi.StepDesc()
+        d.n_layers = len(dims) - 1
+        off = 0
+        for l in range(len(dims) - 1):
+            d.dims[l] = dims[l]
+            d.relu[l] = 1 if l < len(dims) - 2 else 0
+            d.w_off[l] = off; off += (dims[l] * dims[l + 1] + 3) // 4 * 4
+            d.b_off[l] = off; off += (dims[l + 1] + 3) // 4 * 4
+        d.dims[len(dims) - 1] = dims[-1]
+        d.batch, d.optimizer, d.arena_len = batch, opt, off
+        return d
+
+    ok = lambda d: capi.lib.tp_step_supported(C.byref(d))
+    assert ok(desc([784, 128, 10], 512)) == 1                 # configs[1]
+    assert ok(desc([784, 128, 10], 64, 0)) == 1               # configs[0]
+    assert ok(desc([784, 128, 64, 10], 256)) == 1             # the reference's example MLP
+    assert ok(desc([784, 10], 200)) == 1                      # softmax regression
+    assert ok(desc([784, 1024, 1024, 10], 1024)) == 0         # configs[3]: 9.8 GFLOP per step
+    assert ok(desc([784, 128, 32], 64)) == 0                  # 32 classes: not a skinny head
+    assert ok(desc([30, 10], 64)) == 0                        # width not a multiple of 4
+    assert ok(desc([784, 128, 10], 5000)) == 0                # batch beyond the gather index buffer
+    assert capi.lib.tp_step_supported(None) == 0
