@@ -153,13 +153,16 @@ struct GemmParams {
     tp::ConvShape g;
 };
 
-template <int BN, bool SPLIT3>
+template <int BN, bool SPLIT3, bool CONV = false, bool OCC2 = false>
 struct Smem {
     static constexpr int kABytes = BM * BK * 4;
     static constexpr int kBBytes = BN * BK * 4;
     static constexpr int kStageBytes = (kABytes + kBBytes) * (SPLIT3 ? 2 : 1);
-    // as deep as ~200 KB allows (the TMA -> split -> MMA -> free round trip is ~2.5k cycles), at most 8
-    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    // as deep as ~200 KB allows (the TMA -> split -> MMA -> free round trip is ~2.5k cycles), at most 8.
+    // Implicit-GEMM convolution: three stages only — the gather warps, not the MMAs, set the pace, and the shared memory
+    // not taken is L1: a tile's input footprint (25-50 KB) is re-read once per filter tap and should hit there, not in L2.
+    // OCC2: two stages so that two CTAs fit on an SM (one's setup / epilogue overlaps the other's main loop).
+    static constexpr int kStages = OCC2 ? 2 : CONV ? 3 : (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
     static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
 
@@ -184,11 +187,16 @@ __device__ __forceinline__ float epilogue_elem(float acc, const GemmParams& p, s
 // hardware accumulator truncates, which biases long sums of same-signed products (MNIST pixels, post-ReLU
 // activations) by ~K/3 * 2^-24.  Every kChunk k-blocks the TMEM accumulator (double-buffered) is drained
 // into fp32 registers with round-to-nearest adds while the next chunk is already being multiplied.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT3, bool IM2COL = false>
-__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
+// GATHER2 (implicit-GEMM convolution, BN <= 64): a second group of four gather warps (10-13) takes the upper half of every
+// k-block, doubling the global loads in flight — the kernel is bound by the gather, not by the tensor pipe.
+// OCC2 (implicit-GEMM convolution): two-stage pipeline and a register cap so that two CTAs share an SM — every tile is short
+// (9-18 k-blocks), so per-CTA setup and epilogue are a large share of its life and are hidden behind the other CTA's main loop.
+template <int BN, bool A_MN, bool B_MN, bool SPLIT3, bool IM2COL = false, bool GATHER2 = false, bool OCC2 = false>
+__global__ void __launch_bounds__(SPLIT3 ? (GATHER2 ? 448 : 320) : 192, OCC2 ? 2 : 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
     static_assert(!IM2COL || (SPLIT3 && !A_MN), "the im2col gather is done by the 3xTF32 splitter warps into a K-major A tile");
-    using S = Smem<BN, SPLIT3>;
+    static_assert(!GATHER2 || IM2COL, "the second gather group only exists in the implicit-GEMM convolution");
+    using S = Smem<BN, SPLIT3, IM2COL, OCC2>;
     constexpr int kStages = S::kStages;
     constexpr int kChunk = 4;                         // k-blocks (128 elements of K) per tensor-core accumulation
     constexpr uint32_t kTmemCols = SPLIT3 ? (2 * BN < 32 ? 32 : 2 * BN) : (BN < 32 ? 32 : BN);
@@ -218,7 +226,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, 1);
-            mbar_init(split_bar + s, 128);            // every thread of the 4 splitter warps arrives
+            mbar_init(split_bar + s, GATHER2 ? 256 : 128);      // every thread of the splitter / gather warps arrives
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(acc_full + b, 1);
@@ -324,9 +332,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tc_commit(acc_full + (SPLIT3 ? ((i / kChunk) & 1) : 0));      // accumulation complete
             }
         }
-    } else if (SPLIT3 && warp < 6) {
-        // ===== warps 2-5 (3xTF32): split every landed stage into hi/lo tiles =====
-        const int t = threadIdx.x - 64;               // 0..127
+    } else if (SPLIT3 && (warp < 6 || warp >= 10)) {
+        // ===== warps 2-5 (3xTF32): split every landed stage into hi/lo tiles; warps 10-13: second gather group (GATHER2) =====
+        const int half = warp >= 10 ? 1 : 0;          // which half of every k-block this gather group owns (GATHER2)
+        const int t = (threadIdx.x - 64) & 127;       // 0..127: row of the A tile
         // IM2COL: this thread owns row t of the A tile = output pixel m0 + t; its 32 k-values per k-block are gathered from
         // the NCHW input (lanes = consecutive ow: coalesced) and written as hi (the fp32 value) and lo = x - trunc_tf32(x)
         // straight into the K-major SWIZZLE_128B layout the MMA descriptor expects (16-byte chunk j of row r at j ^ (r % 8)).
@@ -347,10 +356,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if constexpr (IM2COL) {
             // two k-blocks of gathers are in flight per thread: block i + 1 is issued before block i is written out
+            constexpr int kC = GATHER2 ? BK / 8 : BK / 4;      // 16-byte chunks of a row per gather thread and k-block
+            const int c0 = GATHER2 ? half * kC : 0;
             auto gather = [&](int i, float (&v)[BK]) {
-                const int4* kt4 = reinterpret_cast<const int4*>(ktab + (kb0 + i) * BK);
+                const int4* kt4 = reinterpret_cast<const int4*>(ktab + (kb0 + i) * BK) + c0;
 #pragma unroll
-                for (int c = 0; c < BK / 4; ++c) {
+                for (int c = 0; c < kC; ++c) {
                     const int4 kt = kt4[c];
                     const int e4[4] = {kt.x, kt.y, kt.z, kt.w};
 #pragma unroll
@@ -367,20 +378,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 uint8_t* rhi = a_hi(s) + t * 128;
                 uint8_t* rlo = a_lo(s) + t * 128;
 #pragma unroll
-                for (int c = 0; c < BK / 4; ++c) {
+                for (int c = 0; c < kC; ++c) {
                     float4 l;
                     l.x = v[4 * c + 0] - __uint_as_float(__float_as_uint(v[4 * c + 0]) & 0xFFFFE000u);
                     l.y = v[4 * c + 1] - __uint_as_float(__float_as_uint(v[4 * c + 1]) & 0xFFFFE000u);
                     l.z = v[4 * c + 2] - __uint_as_float(__float_as_uint(v[4 * c + 2]) & 0xFFFFE000u);
                     l.w = v[4 * c + 3] - __uint_as_float(__float_as_uint(v[4 * c + 3]) & 0xFFFFE000u);
-                    const int pc = (c ^ (t & 7)) * 16;
+                    const int pc = ((c0 + c) ^ (t & 7)) * 16;
                     *(float4*)(rhi + pc) = make_float4(v[4 * c + 0], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                     *(float4*)(rlo + pc) = l;
                 }
-                mbar_wait(full_bar + s, ph);          // the weight tile has landed: split it
+                mbar_wait(full_bar + s, ph);          // the weight tile has landed: split it (each group takes half of it)
                 const float4* bh4 = (const float4*)b_hi(s);
                 float4* bl4 = (float4*)b_lo(s);
-                for (int q = t; q < S::kBBytes / 16; q += 128) {
+                for (int q = t + (GATHER2 ? half * 128 : 0); q < S::kBBytes / 16; q += (GATHER2 ? 256 : 128)) {
                     const float4 x = bh4[q];
                     float4 l;
                     l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
@@ -479,7 +490,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // convolution epilogue: the tile's rows are output pixels, its columns output channels; write y[n, co, oh, ow] (NCHW,
         // what transpose_4d + add_bias_4d (+ relu) produce, src/tensor.rs:1275-1281, 1387-1388) straight from the staged
         // accumulators: for a fixed channel consecutive rows are consecutive addresses, so the stores stay coalesced
-        constexpr int kT = 320;
+        constexpr int kT = GATHER2 ? 448 : 320;
         const int hw = p.g.ho * p.g.wo;
         // one float4 of four channels per thread-iteration: consecutive lanes = consecutive rows, so the shared-memory reads
         // (row pitch BN + 4 floats) are conflict-free and each of the four channel stores is a coalesced run
@@ -780,14 +791,16 @@ namespace tp {
 namespace {
 template <int BN>
 int launch_conv(tp_ctx* ctx, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
-    auto kern = gemm_tf32_kernel<BN, false, true, true, true>;
-    constexpr int smem = Smem<BN, true>::kTotal + kMaxConvK * 4 + 64;
+    constexpr bool kG2 = false;                       // second gather group (448 threads): superseded by two CTAs per SM below
+    constexpr bool kOcc2 = BN <= 64;                  // two co-resident CTAs: 2 x (2 stages + tables) of shared memory, <= 102 registers
+    auto kern = gemm_tf32_kernel<BN, false, true, true, true, kG2, kOcc2>;
+    constexpr int smem = Smem<BN, true, true, kOcc2>::kTotal + kMaxConvK * 4 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    kern<<<grid, 320, smem, ctx->stream>>>(mb /*unused A map*/, mb, p);
+    kern<<<grid, kG2 ? 448 : 320, smem, ctx->stream>>>(mb /*unused A map*/, mb, p);
     TP_LAUNCH_OK(ctx);
     return TP_OK;
 }
