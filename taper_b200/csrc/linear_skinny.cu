@@ -10,13 +10,35 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxOut = 16;
+constexpr int kColsPerBlock = 64, kRowGroups = kThreads / kColsPerBlock;      // dW role of the backward kernel
 
-// ---- forward: one warp per row, W staged in shared memory ------------------------------------------------
+// ---- forward: one warp per row.  W (out x in, <= 96 KB) is staged once per block in shared memory with 128-bit loads that
+// are all in flight together, then every warp streams its row of X (float4) against it; scalar path for in_features % 4 != 0
+// or unaligned operands --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ y, int batch, int in_f, int out_f, int relu) {
-    extern __shared__ float sw[];                              // [out_f][in_f]
-    for (int i = threadIdx.x; i < out_f * in_f; i += kThreads) sw[i] = __ldg(w + i);
+                  float* __restrict__ y, int batch, int in_f, int out_f, int relu, int vec) {
+    extern __shared__ __align__(16) float sw[];                // [out_f][in_f]
+    const int nw = out_f * in_f;
+    if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        float4* s4 = reinterpret_cast<float4*>(sw);
+        for (int i0 = threadIdx.x; i0 < nw / 4; i0 += kThreads * 8) {
+            float4 q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kThreads;
+                q[u] = i < nw / 4 ? __ldg(w4 + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kThreads;
+                if (i < nw / 4) s4[i] = q[u];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < nw; i += kThreads) sw[i] = __ldg(w + i);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -26,11 +48,29 @@ skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
         float acc[kMaxOut];
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
-        for (int k = lane; k < in_f; k += 32) {
-            const float xv = __ldg(xr + k);
+        if (vec) {
+            const int in4 = in_f >> 2;
+#pragma unroll 4
+            for (int c = lane; c < in4; c += 32) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xr) + c);
 #pragma unroll
-            for (int o = 0; o < kMaxOut; ++o)
-                if (o < out_f) acc[o] = fmaf(xv, sw[o * in_f + k], acc[o]);
+                for (int o = 0; o < kMaxOut; ++o) {
+                    if (o < out_f) {
+                        const float4 wv = *(reinterpret_cast<const float4*>(sw + (size_t)o * in_f) + c);
+                        acc[o] = fmaf(a.x, wv.x, acc[o]);
+                        acc[o] = fmaf(a.y, wv.y, acc[o]);
+                        acc[o] = fmaf(a.z, wv.z, acc[o]);
+                        acc[o] = fmaf(a.w, wv.w, acc[o]);
+                    }
+                }
+            }
+        } else {
+            for (int k = lane; k < in_f; k += 32) {
+                const float xv = __ldg(xr + k);
+#pragma unroll
+                for (int o = 0; o < kMaxOut; ++o)
+                    if (o < out_f) acc[o] = fmaf(xv, sw[o * in_f + k], acc[o]);
+            }
         }
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) {
@@ -76,13 +116,26 @@ __device__ __forceinline__ float masked(const BwdArgs& a, int r, int o) {
 
 __global__ void __launch_bounds__(kThreads)
 skinny_bwd_kernel(BwdArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     __shared__ int s_last;
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < a.dx_blocks) {
         // dX[r, i] (+)= sum_o dY[r, o] * W[o, i]      (N,N; src/ops.rs:254-265 composed with transpose bwd)
         float* sw = smem;                                      // [out][in]
-        for (int i = tid; i < a.out_f * a.in_f; i += kThreads) sw[i] = __ldg(a.w + i);
+        if (a.in_f % 4 == 0 && !((uintptr_t)a.w & 15)) {       // 128-bit staging loads, eight in flight per thread
+            const int n4 = a.out_f * a.in_f / 4;
+            const float4* w4 = reinterpret_cast<const float4*>(a.w);
+            float4* s4 = reinterpret_cast<float4*>(sw);
+            for (int i0 = tid; i0 < n4; i0 += kThreads * 8) {
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) q[u] = (i0 + u * kThreads < n4) ? __ldg(w4 + i0 + u * kThreads) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (i0 + u * kThreads < n4) s4[i0 + u * kThreads] = q[u];
+            }
+        } else {
+            for (int i = tid; i < a.out_f * a.in_f; i += kThreads) sw[i] = __ldg(a.w + i);
+        }
         __syncthreads();
         const int lane = tid & 31;
         const int warp = (blockIdx.x * kThreads + tid) >> 5;
@@ -103,35 +156,61 @@ skinny_bwd_kernel(BwdArgs a) {
         return;
     }
     // dW[o, i] (+)= sum_r dY[r, o] * X[r, i] ;  db[o] (+)= sum_r dY[r, o]      (T,N; src/ops.rs:280-291, src/tensor.rs:680-691)
+    // A block owns kColsPerBlock (64) input columns of one row split; its 256 threads are 64 columns x 4 row groups, each
+    // thread walking its rows 8 at a time (8 independent loads in flight), the row groups folded through shared memory.
     const int b = blockIdx.x - a.dx_blocks;
     const int cb = b % a.col_blocks, rs = b / a.col_blocks;
-    const int i = cb * kThreads + tid;                         // input column owned by this thread
+    const int cg = tid & (kColsPerBlock - 1), rg = tid / kColsPerBlock;
+    const int i = cb * kColsPerBlock + cg;                     // input column owned by this thread
     const int r0 = rs * a.rows_per_split, r1 = min(a.batch, r0 + a.rows_per_split);
     float* sdy = smem;                                         // [rows_per_split][out]
+    float* red = smem + (size_t)a.rows_per_split * a.out_f;    // [kRowGroups][kMaxOut][kColsPerBlock]
     for (int e = tid; e < (r1 - r0) * a.out_f; e += kThreads) sdy[e] = masked(a, r0 + e / a.out_f, e % a.out_f);
     __syncthreads();
     float acc[kMaxOut];
 #pragma unroll
     for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.0f;
     if (i < a.in_f && a.dw) {
-        for (int r = r0; r < r1; ++r) {
-            const float xv = __ldg(a.x + (size_t)r * a.in_f + i);
-            const float* g = sdy + (r - r0) * a.out_f;
+        for (int rb = r0 + rg; rb < r1; rb += kRowGroups * 8) {
+            float xv[8];
 #pragma unroll
-            for (int o = 0; o < kMaxOut; ++o)
-                if (o < a.out_f) acc[o] = fmaf(g[o], xv, acc[o]);
+            for (int u = 0; u < 8; ++u) {
+                const int r = rb + kRowGroups * u;
+                xv[u] = r < r1 ? __ldg(a.x + (size_t)r * a.in_f + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = rb + kRowGroups * u;
+                if (r < r1) {
+                    const float* g = sdy + (r - r0) * a.out_f;
+#pragma unroll
+                    for (int o = 0; o < kMaxOut; ++o)
+                        if (o < a.out_f) acc[o] = fmaf(g[o], xv[u], acc[o]);
+                }
+            }
         }
     }
-    // park the partials: layout [cb][rs][out][kThreads] (+ a [out] tail per (cb, rs) for db, written by column block 0)
-    const size_t per = (size_t)a.out_f * kThreads + kMaxOut;
-    float* mine = a.partial + ((size_t)cb * a.row_splits + rs) * per;
 #pragma unroll
-    for (int o = 0; o < kMaxOut; ++o)
-        if (o < a.out_f) mine[o * kThreads + tid] = acc[o];
+    for (int o = 0; o < kMaxOut; ++o) red[(rg * kMaxOut + o) * kColsPerBlock + cg] = acc[o];
+    __syncthreads();
+    // park the partials: layout [cb][rs][out][kColsPerBlock] (+ a [out] tail per (cb, rs) for db, written by column block 0)
+    const size_t per = (size_t)a.out_f * kColsPerBlock + kMaxOut;
+    float* mine = a.partial + ((size_t)cb * a.row_splits + rs) * per;
+    if (rg == 0) {
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+            if (o < a.out_f) {
+                float v = 0.0f;
+#pragma unroll
+                for (int q = 0; q < kRowGroups; ++q) v += red[(q * kMaxOut + o) * kColsPerBlock + cg];      // row-group order
+                mine[o * kColsPerBlock + cg] = v;
+            }
+        }
+    }
     if (cb == 0 && a.db && tid < a.out_f) {
         float s = 0.0f;
         for (int r = r0; r < r1; ++r) s += sdy[(r - r0) * a.out_f + tid];      // rows ascending
-        mine[(size_t)a.out_f * kThreads + tid] = s;
+        mine[(size_t)a.out_f * kColsPerBlock + tid] = s;
     }
     __threadfence();
     __syncthreads();
@@ -144,22 +223,28 @@ skinny_bwd_kernel(BwdArgs a) {
     if (!s_last) return;
     __threadfence();
     const float* base = a.partial + (size_t)cb * a.row_splits * per;
-    if (i < a.in_f && a.dw) {
+    if (rg == 0 && i < a.in_f && a.dw) {
+        // split order; the loads of four splits for every output row are in flight before the first add
+        float s[kMaxOut];
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) s[o] = 0.0f;
+        for (int z0 = 0; z0 < a.row_splits; z0 += 4) {
+            float q[4][kMaxOut];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int o = 0; o < kMaxOut; ++o)
+                    q[u][o] = (o < a.out_f && z0 + u < a.row_splits) ? __ldcg(base + (size_t)(z0 + u) * per + o * kColsPerBlock + cg) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int o = 0; o < kMaxOut; ++o) s[o] += q[u][o];
+        }
 #pragma unroll
         for (int o = 0; o < kMaxOut; ++o) {
             if (o < a.out_f) {
-                // split order; the loads of a batch are issued before the first add (one L2 round trip per 8 splits, not per split)
-                float s = 0.0f;
-                for (int z0 = 0; z0 < a.row_splits; z0 += 8) {
-                    float q[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        q[u] = (z0 + u < a.row_splits) ? __ldcg(base + (size_t)(z0 + u) * per + o * kThreads + tid) : 0.0f;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) s += q[u];
-                }
                 float* d = a.dw + (size_t)o * a.in_f + i;
-                *d = a.acc_dw ? *d + s : s;
+                *d = a.acc_dw ? *d + s[o] : s[o];
             }
         }
     }
@@ -169,7 +254,7 @@ skinny_bwd_kernel(BwdArgs a) {
             float q[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                q[u] = (z0 + u < a.row_splits) ? __ldcg(base + (size_t)(z0 + u) * per + (size_t)a.out_f * kThreads + tid) : 0.0f;
+                q[u] = (z0 + u < a.row_splits) ? __ldcg(base + (size_t)(z0 + u) * per + (size_t)a.out_f * kColsPerBlock + tid) : 0.0f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) s += q[u];
         }
@@ -188,7 +273,6 @@ bool linear_skinny_ok(int batch, int in_f, int out_f) {
 int linear_skinny_fwd(tp_ctx* ctx, const float* x, const float* w, const float* b, float* y, int batch, int in_f, int out_f,
                       int relu) {
     cudaSetDevice(ctx->device);
-    size_t smem = (size_t)out_f * in_f * sizeof(float);
     static bool attr = false;
     if (!attr) {
         TP_CUDA(cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -196,8 +280,10 @@ int linear_skinny_fwd(tp_ctx* ctx, const float* x, const float* w, const float* 
         attr = true;
     }
     int blocks = (batch * 32 + kThreads - 1) / kThreads;
-    if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
-    skinny_fwd_kernel<<<blocks, kThreads, smem, ctx->stream>>>(x, w, b, y, batch, in_f, out_f, relu);
+    if (blocks > ctx->sm_count) blocks = ctx->sm_count;       // every block stages W once: no more blocks than SMs
+    const int vec = (in_f % 4 == 0) && !(((uintptr_t)x | (uintptr_t)w) & 15);
+    const size_t smem = (size_t)out_f * in_f * sizeof(float);
+    skinny_fwd_kernel<<<blocks, kThreads, smem, ctx->stream>>>(x, w, b, y, batch, in_f, out_f, relu, vec);
     TP_LAUNCH_OK(ctx);
     return TP_OK;
 }
@@ -223,8 +309,12 @@ int linear_skinny_bwd(tp_ctx* ctx, const float* x, const float* w, const float* 
     a.col_blocks = 0; a.row_splits = 0; a.rows_per_split = 0;
     a.partial = nullptr; a.tickets = nullptr;
     if (dw || db) {
-        a.col_blocks = (in_f + kThreads - 1) / kThreads;
+        a.col_blocks = (in_f + kColsPerBlock - 1) / kColsPerBlock;
+        // few, long row splits: the last block of a column block folds all of them, so the fold (splits x out loads per
+        // thread) must stay short; 8 splits x col_blocks CTAs already cover the dW work in a few microseconds
         int splits = (ctx->sm_count + a.col_blocks - 1) / a.col_blocks;
+        if (splits > 8) splits = 8;
+        if (splits < 1) splits = 1;
         int rps = (batch + splits - 1) / splits;
         if (rps < 16) rps = 16;
         if (rps > 1024) rps = 1024;                            // dY chunk of a split is staged in shared memory
@@ -234,7 +324,7 @@ int linear_skinny_bwd(tp_ctx* ctx, const float* x, const float* w, const float* 
             set_error("linear_skinny_bwd: in_features %d too large", in_f);
             return TP_ERR_UNSUPPORTED;
         }
-        size_t per = (size_t)out_f * kThreads + kMaxOut;
+        size_t per = (size_t)out_f * kColsPerBlock + kMaxOut;
         int rc = ensure_scratch(ctx, (size_t)a.col_blocks * a.row_splits * per * sizeof(float));
         if (rc) return rc;
         a.partial = ctx->scratch;
@@ -243,7 +333,7 @@ int linear_skinny_bwd(tp_ctx* ctx, const float* x, const float* w, const float* 
     int blocks = a.dx_blocks + a.col_blocks * a.row_splits;
     if (blocks == 0) return TP_OK;
     size_t smem_dx = dx ? (size_t)out_f * in_f * sizeof(float) : 0;
-    size_t smem_dw = (size_t)a.rows_per_split * out_f * sizeof(float);
+    size_t smem_dw = ((size_t)a.rows_per_split * out_f + (size_t)kRowGroups * kMaxOut * kColsPerBlock) * sizeof(float);
     size_t smem = smem_dx > smem_dw ? smem_dx : smem_dw;
     skinny_bwd_kernel<<<blocks, kThreads, smem, ctx->stream>>>(a);
     TP_LAUNCH_OK(ctx);
