@@ -27,6 +27,7 @@ examples: $(LIB)
 	@mkdir -p build
 	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host examples/train_mnist.cpp -o build/train_mnist -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
 	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host examples/train_mnist_cnn.cpp -o build/train_mnist_cnn -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
+	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host examples/xor.cpp -o build/xor -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
 
 clean:
 	rm -rf build $(LIB)

@@ -240,6 +240,21 @@ int tp_avgpool2d_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, const tp_pool_desc* d)
 int tp_avgpool2d_bwd(tp_ctx*, const tp_buf* gout, tp_buf* gin, const tp_pool_desc* d, int accumulate);
 
 /* ---------------------------------------------------------------------------------------------
+ * the remaining elementwise / loss ops of the reference's XOR demo (src/main.rs) and MSE path
+ * ------------------------------------------------------------------------------------------- */
+int tp_sigmoid_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, size_t n);                            /* src/tensor.rs:594-610 */
+int tp_sigmoid_bwd(tp_ctx*, const tp_buf* y, const tp_buf* gout, tp_buf* gin, size_t n, int accumulate);   /* g*s*(1-s)  :617-629 */
+int tp_pow_fwd(tp_ctx*, const tp_buf* x, tp_buf* y, float exponent, size_t n);                /* powf; sqrt = pow(0.5)  :1172-1211 */
+int tp_pow_bwd(tp_ctx*, const tp_buf* x, const tp_buf* gout, tp_buf* gin, float exponent, size_t n, int accumulate);
+int tp_mean_fwd(tp_ctx*, const tp_buf* x, tp_buf* out1, size_t n);                            /* sum / len  :772-776 */
+int tp_mean_bwd(tp_ctx*, const tp_buf* gout1, tp_buf* gin, size_t n, int accumulate);         /* gin += g/len  :784-796 */
+/* bce_loss: -mean(y ln p + (1-y) ln(1-p)), p clamped to [1e-7, 1-1e-7]; gradients w.r.t. predictions and (optionally) targets
+ * scaled by the upstream scalar gloss[0]                                                     src/loss.rs:6-72 */
+int tp_bce_fwd(tp_ctx*, const tp_buf* pred, const tp_buf* target, tp_buf* loss1, size_t n);
+int tp_bce_bwd(tp_ctx*, const tp_buf* pred, const tp_buf* target, const tp_buf* gloss1, tp_buf* gpred, tp_buf* gtarget, size_t n,
+               int acc_pred, int acc_target);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer steps  (src/optim.rs:21-33, 83-113, 148-168).  grad_scale multiplies g first
  * (1/world for data-parallel averaging; 1 otherwise).
  * ------------------------------------------------------------------------------------------- */

@@ -30,7 +30,7 @@ int tp_host_ctx(tp_ctx** out);
 int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op_sequence, int gemm_mode);
 
 /* Sequential from a comma-separated layer list (the constructors of src/nn.rs, src/activation.rs):
- *   linear:IN:OUT[:nobias] | relu | conv:CIN:COUT:K:STRIDE:PAD | conv_relu:CIN:COUT:K:STRIDE:PAD |
+ *   linear:IN:OUT[:nobias] | relu | sigmoid | conv:CIN:COUT:K:STRIDE:PAD | conv_relu:CIN:COUT:K:STRIDE:PAD |
  *   maxpool:K:STRIDE | avgpool:K:STRIDE | gap (AdaptiveAvgPool2d::global) | flatten
  * Weights are drawn from the reference's init distributions with a seeded generator. */
 int tp_model_create(const char* spec, uint64_t seed, tp_model** out);
@@ -46,6 +46,11 @@ int tp_model_forward(tp_model* m, const float* x, const size_t* shape, int ndim,
 /* Tape::reset; forward; cross_entropy_loss; accuracy; loss.backward()  — no optimizer (src/train.rs:108-121) */
 int tp_model_loss_backward(tp_model* m, const float* x, const size_t* shape, int ndim, const float* labels,
                            float* loss, float* correct, size_t* tape_len);
+
+/* Tape::reset; forward; loss(out, targets); loss.backward() with loss_kind "bce" (src/loss.rs:6-72), "mse" (:75-80) or
+ * "ce_onehot" (:202-245); targets have the model output's shape.  Gradients are read with tp_model_get_grad. */
+int tp_model_regression_backward(tp_model* m, const float* x, const size_t* shape, int ndim, const float* targets,
+                                 size_t n_targets, const char* loss_kind, float* loss);
 
 /* Trainer over a model; optimizer is "sgd" | "adam" | "adamw" (src/optim.rs).  The trainer shares the model's
  * parameters (they are re-homed into one flat arena). */

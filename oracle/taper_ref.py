@@ -401,6 +401,66 @@ class Tensor:
     def argmax(self, dim=None):
         return self.max(dim)[1]
 
+    # ---- sigmoid / mean / pow / sqrt  (src/tensor.rs:594-634, 772-800, 1172-1211) ------------
+    def sigmoid(self):
+        x = self._data
+        with np.errstate(over="ignore"):
+            pos = F32(1.0) / (F32(1.0) + np.exp(-x))                  # x > 0 branch (:602-604)
+            ex = np.exp(x)
+            neg = ex / (F32(1.0) + ex)                                # else branch (:605-607)
+        res = np.where(x > 0, pos, neg).astype(F32)
+        out = Tensor(res, self.shape)
+        if self.requires_grad:
+            out.requires_grad = True
+            xt, o = self, out
+
+            def bw():
+                g = o._grad[0]
+                if g is not None:
+                    gin = xt._grad_slot()
+                    gin += g * res * (F32(1.0) - res)                 # :627
+            Tape.push_unary_op(self, out, bw)
+        return out
+
+    def mean(self):
+        n = self._data.size
+        acc = F32(0.0)
+        for v in self._data:                                          # iter().sum::<f32>() (:774)
+            acc = F32(acc + v)
+        out = Tensor.scalar(F32(acc / F32(n)))
+        if self.requires_grad:
+            out.requires_grad = True
+            xt, o = self, out
+
+            def bw():
+                g = o._grad[0]
+                if g is not None:
+                    gin = xt._grad_slot()
+                    gin += F32(g[0] / F32(n))                         # :786-795
+            Tape.push_unary_op(self, out, bw)
+        return out
+
+    def pow(self, exponent):
+        e = F32(exponent)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            res = np.power(self._data, e).astype(F32)                 # powf (:1177)
+        out = Tensor(res, self.shape)
+        if self.requires_grad:
+            out.requires_grad = True
+            xt, o = self, out
+
+            def bw():
+                g = o._grad[0]
+                if g is not None:
+                    gin = xt._grad_slot()
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        gin += g * e * np.power(xt._data, F32(e - F32(1.0))).astype(F32)      # :1199
+            Tape.push_unary_op(self, out, bw)
+        return out
+
+    def sqrt(self):                                                   # :1209-1211
+        return self.pow(0.5)
+
     # ---- exp / log  (src/tensor.rs:1091-1169) ---------------------------------------------------------
     def exp(self):
         res = np.exp(self._data)
@@ -689,6 +749,78 @@ def cross_entropy_loss(logits, targets):     # src/loss.rs:136-195
     return out
 
 
+def bce_loss(predictions, targets):          # src/loss.rs:6-72
+    eps = F32(1e-7)
+    p, t = predictions._data, targets._data
+    assert p.size == t.size, "bce_loss: predictions and targets must match in length"
+    n = p.size
+    pc = np.clip(p, eps, F32(1.0) - eps).astype(F32)
+    terms = (t * np.log(pc) + (F32(1.0) - t) * np.log(F32(1.0) - pc)).astype(F32)
+    acc = F32(0.0)
+    for v in terms:                              # acc -= ... sequentially (:18-22)
+        acc = F32(acc - v)
+    out = Tensor.scalar(F32(acc / F32(n)))
+    if predictions.requires_grad or targets.requires_grad:
+        out.requires_grad = True
+        pr, tg, o = predictions, targets, out
+
+        def bw():
+            g = o._grad[0]
+            if g is not None:
+                gs = F32(g[0])
+                pcl = np.clip(pr._data, eps, F32(1.0) - eps).astype(F32)
+                if pr.requires_grad:
+                    gp = pr._grad_slot()
+                    gp += (gs * (-(tg._data / pcl - (F32(1.0) - tg._data) / (F32(1.0) - pcl))) / F32(n)).astype(F32)   # :52
+                if tg.requires_grad:
+                    gy = tg._grad_slot()
+                    gy += (gs * (np.log(F32(1.0) - pcl) - np.log(pcl)) / F32(n)).astype(F32)                          # :66
+        Tape.push_binary_op(predictions, targets, out, bw)
+    return out
+
+
+def mse_loss(predictions, targets):          # src/loss.rs:75-80
+    diff = predictions - targets
+    squared = diff * diff
+    return squared.mean()
+
+
+def one_hot(indices, num_classes):           # src/loss.rs:248-268
+    assert len(indices.shape) == 1, "Indices must be 1D"
+    b = indices.shape[0]
+    cls = indices._data.astype(np.int64)
+    assert (cls >= 0).all() and (cls < num_classes).all(), "Index out of bounds"
+    oh = np.zeros((b, num_classes), F32)
+    oh[np.arange(b), cls] = F32(1.0)
+    return Tensor(oh.reshape(-1), (b, num_classes))
+
+
+def cross_entropy_loss_onehot(logits, targets):      # src/loss.rs:202-245
+    assert tuple(logits.shape) == tuple(targets.shape), "Logits and targets shapes must match"
+    assert len(logits.shape) == 2, "Must be 2D tensors"
+    b = logits.shape[0]
+    rg_l, rg_t = logits.requires_grad, targets.requires_grad
+    logits.requires_grad = targets.requires_grad = False      # the reference rebuilds a fresh scalar (:219-221): no tape link
+    try:
+        log_probs = log_softmax(logits, -1)
+        total = (targets * log_probs).sum(None, False)
+    finally:
+        logits.requires_grad, targets.requires_grad = rg_l, rg_t
+    out = Tensor.scalar(F32(-total._data[0] / F32(b)))
+    if logits.requires_grad:
+        out.requires_grad = True
+        lg, tg, o = logits, targets, out
+
+        def bw():
+            g = o._grad[0]
+            if g is not None:
+                probs = np.exp(log_probs._data)
+                grad = ((probs - tg._data) * F32(g[0]) / F32(b)).astype(F32)      # :233-236
+                accumulate_grad(lg, grad)
+        Tape.push_unary_op(logits, out, bw)
+    return out
+
+
 def accuracy(predictions, targets):          # src/loss.rs:271-290
     assert predictions.shape[0] == targets.shape[0]
     pred = predictions.argmax(1)._data
@@ -732,6 +864,11 @@ class Linear(Module):                 # src/nn.rs:28-78
 class ReLU(Module):                   # src/activation.rs:7-21
     def forward(self, x):
         return x.relu()
+
+
+class Sigmoid(Module):                # src/activation.rs:37-51
+    def forward(self, x):
+        return x.sigmoid()
 
 
 class Sequential(Module):             # src/nn.rs:130-162

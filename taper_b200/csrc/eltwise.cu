@@ -21,6 +21,44 @@ struct OpLog { __device__ float operator()(float a, float, float) const { return
 // div bwd wrt b: a = gout, b = a, c = b  ->  -gout*a/(b*b)
 struct OpDivBwdB { __device__ float operator()(float g, float a, float b) const { return -(g * a / (b * b)); } };
 struct OpFill { float v; __device__ float operator()(float, float, float) const { return v; } };
+// ---- sigmoid / pow / mean / binary cross-entropy (XOR demo, src/main.rs) -------------------------------
+// sigmoid, the reference's two-branch form (src/tensor.rs:601-608)
+struct OpSigmoid {
+    __device__ float operator()(float x, float, float) const {
+        if (x > 0.0f) { const float e = expf(-x); return 1.0f / (1.0f + e); }
+        const float e = expf(x);
+        return e / (1.0f + e);
+    }
+};
+struct OpSigmoidBwd { __device__ float operator()(float g, float s, float) const { return g * s * (1.0f - s); } };      // :627
+struct OpPow { float e; __device__ float operator()(float x, float, float) const { return powf(x, e); } };               // :1177
+struct OpPowBwd { float e; __device__ float operator()(float g, float x, float) const { return g * e * powf(x, e - 1.0f); } };   // :1199
+struct OpDivBy { float d; __device__ float operator()(float a, float, float) const { return a / d; } };
+// bce term -(y ln p + (1-y) ln(1-p)) with p clamped to [1e-7, 1-1e-7]  (src/loss.rs:7, 19-21)
+struct OpBceTerm {
+    __device__ float operator()(float p, float y, float) const {
+        const float pi = fminf(fmaxf(p, 1e-7f), 1.0f - 1e-7f);
+        return -(y * logf(pi) + (1.0f - y) * logf(1.0f - pi));
+    }
+};
+// g * (-(y/p - (1-y)/(1-p))) / n  with the upstream scalar g read from the device  (src/loss.rs:52)
+struct OpBceBwdP {
+    const float* g; float n;
+    __device__ float operator()(float p, float y, float) const {
+        const float pi = fminf(fmaxf(p, 1e-7f), 1.0f - 1e-7f);
+        return __ldg(g) * (-(y / pi - (1.0f - y) / (1.0f - pi))) / n;
+    }
+};
+// g * (ln(1-p) - ln p) / n  (src/loss.rs:66)
+struct OpBceBwdT {
+    const float* g; float n;
+    __device__ float operator()(float p, float, float) const {
+        const float pi = fminf(fmaxf(p, 1e-7f), 1.0f - 1e-7f);
+        return __ldg(g) * (logf(1.0f - pi) - logf(pi)) / n;
+    }
+};
+// gin (+)= g[0] / n for every element  (mean backward, src/tensor.rs:786-795)
+struct OpMeanBwd { const float* g; float n; __device__ float operator()(float, float, float) const { return __ldg(g) / n; } };
 
 template <int NIN, class Op>
 __global__ void __launch_bounds__(kThreads)
@@ -172,6 +210,72 @@ int tp_log_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* gout, tp_buf* gin, si
     TP_CHECK_ARG(ctx, "tp_log_bwd: NULL ctx");
     TP_NEED(x, n, "x"); TP_NEED(gout, n, "gout"); TP_NEED(gin, n, "gin");
     return launch_ew<2>(ctx, OpDiv(), gout->ptr, x->ptr, nullptr, gin->ptr, n, accumulate);
+}
+
+int tp_sigmoid_fwd(tp_ctx* ctx, const tp_buf* x, tp_buf* y, size_t n) {
+    TP_CHECK_ARG(ctx, "tp_sigmoid_fwd: NULL ctx");
+    TP_NEED(x, n, "x"); TP_NEED(y, n, "y");
+    return launch_ew<1>(ctx, OpSigmoid(), x->ptr, nullptr, nullptr, y->ptr, n, 0);
+}
+
+int tp_sigmoid_bwd(tp_ctx* ctx, const tp_buf* y, const tp_buf* gout, tp_buf* gin, size_t n, int accumulate) {
+    TP_CHECK_ARG(ctx, "tp_sigmoid_bwd: NULL ctx");
+    TP_NEED(y, n, "y"); TP_NEED(gout, n, "gout"); TP_NEED(gin, n, "gin");
+    return launch_ew<2>(ctx, OpSigmoidBwd(), gout->ptr, y->ptr, nullptr, gin->ptr, n, accumulate);
+}
+
+int tp_pow_fwd(tp_ctx* ctx, const tp_buf* x, tp_buf* y, float exponent, size_t n) {
+    TP_CHECK_ARG(ctx, "tp_pow_fwd: NULL ctx");
+    TP_NEED(x, n, "x"); TP_NEED(y, n, "y");
+    return launch_ew<1>(ctx, OpPow{exponent}, x->ptr, nullptr, nullptr, y->ptr, n, 0);
+}
+
+int tp_pow_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* gout, tp_buf* gin, float exponent, size_t n, int accumulate) {
+    TP_CHECK_ARG(ctx, "tp_pow_bwd: NULL ctx");
+    TP_NEED(x, n, "x"); TP_NEED(gout, n, "gout"); TP_NEED(gin, n, "gin");
+    return launch_ew<2>(ctx, OpPowBwd{exponent}, gout->ptr, x->ptr, nullptr, gin->ptr, n, accumulate);
+}
+
+int tp_mean_fwd(tp_ctx* ctx, const tp_buf* x, tp_buf* out, size_t n) {
+    TP_CHECK_ARG(ctx && n > 0, "tp_mean_fwd: empty input");
+    int rc = tp_sum_all(ctx, x, out, n);                       // sum: f32, then / len  (src/tensor.rs:773-775)
+    if (rc) return rc;
+    return launch_ew<1>(ctx, OpDivBy{(float)n}, out->ptr, nullptr, nullptr, out->ptr, 1, 0);
+}
+
+int tp_mean_bwd(tp_ctx* ctx, const tp_buf* gout, tp_buf* gin, size_t n, int accumulate) {
+    TP_CHECK_ARG(ctx, "tp_mean_bwd: NULL ctx");
+    TP_NEED(gout, 1, "gout"); TP_NEED(gin, n, "gin");
+    return launch_ew<0>(ctx, OpMeanBwd{gout->ptr, (float)n}, nullptr, nullptr, nullptr, gin->ptr, n, accumulate);
+}
+
+int tp_bce_fwd(tp_ctx* ctx, const tp_buf* pred, const tp_buf* target, tp_buf* loss, size_t n) {
+    TP_CHECK_ARG(ctx && n > 0, "tp_bce_fwd: empty input");
+    TP_NEED(pred, n, "pred"); TP_NEED(target, n, "target"); TP_NEED(loss, 1, "loss");
+    tp_buf* terms = nullptr;
+    int rc = tp_buf_alloc(ctx, n, &terms);
+    if (rc) return rc;
+    rc = launch_ew<2>(ctx, OpBceTerm(), pred->ptr, target->ptr, nullptr, terms->ptr, n, 0);
+    if (!rc) rc = tp_mean_fwd(ctx, terms, loss, n);            // acc / len  (src/loss.rs:23)
+    tp_buf_release(terms);
+    return rc;
+}
+
+int tp_bce_bwd(tp_ctx* ctx, const tp_buf* pred, const tp_buf* target, const tp_buf* gloss, tp_buf* gpred, tp_buf* gtarget, size_t n,
+               int acc_pred, int acc_target) {
+    TP_CHECK_ARG(ctx, "tp_bce_bwd: NULL ctx");
+    TP_NEED(pred, n, "pred"); TP_NEED(target, n, "target"); TP_NEED(gloss, 1, "gloss");
+    if (gpred) {
+        TP_NEED(gpred, n, "gpred");
+        int rc = launch_ew<2>(ctx, OpBceBwdP{gloss->ptr, (float)n}, pred->ptr, target->ptr, nullptr, gpred->ptr, n, acc_pred);
+        if (rc) return rc;
+    }
+    if (gtarget) {
+        TP_NEED(gtarget, n, "gtarget");
+        int rc = launch_ew<1>(ctx, OpBceBwdT{gloss->ptr, (float)n}, pred->ptr, nullptr, nullptr, gtarget->ptr, n, acc_target);
+        if (rc) return rc;
+    }
+    return TP_OK;
 }
 
 int tp_scale(tp_ctx* ctx, tp_buf* p, float s, size_t n) {

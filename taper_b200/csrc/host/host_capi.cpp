@@ -82,6 +82,8 @@ int tp_model_create(const char* spec, uint64_t seed, tp_model** out) {
                 layers.push_back(std::make_shared<nn::Linear>(num(f, 1, item), num(f, 2, item), bias, s++));
             } else if (k == "relu") {
                 layers.push_back(std::make_shared<nn::ReLU>());
+            } else if (k == "sigmoid") {
+                layers.push_back(std::make_shared<nn::Sigmoid>());
             } else if (k == "conv" || k == "conv_relu") {
                 size_t cin = num(f, 1, item), cout = num(f, 2, item), ks = num(f, 3, item), st = num(f, 4, item), pd = num(f, 5, item);
                 if (k == "conv")
@@ -196,6 +198,28 @@ int tp_model_loss_backward(tp_model* m, const float* x, const size_t* shape, int
         l.backward();
         if (loss) *loss = l.item();
         if (correct) *correct = c.item();
+        Tape::reset();
+    });
+}
+
+int tp_model_regression_backward(tp_model* m, const float* x, const size_t* shape, int ndim, const float* targets, size_t n_targets,
+                                 const char* loss_kind, float* loss) {
+    return guarded([&] {
+        if (!m || !x || !shape || !targets || !loss_kind) panic("tp_model_regression_backward: NULL argument");
+        Tape::reset();
+        Shape s = to_shape(shape, ndim);
+        Tensor in = Tensor::from_host(x, s);
+        Tensor out = m->seq->forward(in);
+        if (out.numel() != n_targets) panic("tp_model_regression_backward: %zu outputs but %zu targets", out.numel(), n_targets);
+        Tensor t = Tensor::from_host(targets, out.shape());
+        std::string k = loss_kind;
+        Tensor l;
+        if (k == "bce") l = loss::bce_loss(out, t);
+        else if (k == "mse") l = loss::mse_loss(out, t);
+        else if (k == "ce_onehot") l = loss::cross_entropy_loss_onehot(out, t);
+        else panic("tp_model_regression_backward: unknown loss '%s'", loss_kind);
+        l.backward();
+        if (loss) *loss = l.item();
         Tape::reset();
     });
 }

@@ -48,6 +48,24 @@ std::vector<Tensor> Linear::parameters() const {
     return p;
 }
 
+Dropout::Dropout(float p_, uint64_t seed) : p(p_), rng_state(seed ? seed : 0x9E3779B97F4A7C15ull) {
+    if (!(p >= 0.0f && p <= 1.0f)) panic("Dropout probability must be between 0 and 1");
+}
+
+Tensor Dropout::forward(const Tensor& input) const {                             // src/nn.rs:799-822
+    if (!training || p == 0.0f) return input;
+    if (p == 1.0f) return Tensor::zeros(input.shape());
+    // the reference draws the mask from thread_rng on the host (:808-816); a seeded xorshift keeps runs reproducible
+    std::vector<float> mask(input.numel());
+    const float scale = 1.0f / (1.0f - p);
+    for (auto& m : mask) {
+        rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
+        float u = (float)(rng_state >> 40) * (1.0f / 16777216.0f);
+        m = u > p ? scale : 0.0f;
+    }
+    return input * Tensor::create(mask, input.shape());
+}
+
 Tensor Sequential::forward(const Tensor& input) const {                         // src/nn.rs:149-151
     Tensor x = input;
     const bool fuse = Config::fuse_linear_relu() && !Config::reference_op_sequence();
@@ -133,6 +151,83 @@ Tensor softmax(const Tensor& x, int dim) {
     if (d != nd - 1 || nd != 2) panic("Only last-dim softmax on [B,C] is supported");
     Tensor out = Tensor::empty(x.shape());
     check(tp_softmax_fwd(ctx(), x.buf(), out.buf(), (int)x.shape()[0], (int)x.shape()[1]));
+    return out;
+}
+
+// ---- BCE / MSE / one-hot cross-entropy ---------------------------------------------------------------------
+Tensor bce_loss(const Tensor& predictions, const Tensor& targets) {             // src/loss.rs:6-72
+    if (predictions.numel() != targets.numel()) panic("bce_loss: predictions and targets must match in length");
+    size_t n = predictions.numel();
+    Tensor out = Tensor::empty({1});
+    check(tp_bce_fwd(ctx(), predictions.buf(), targets.buf(), out.buf(), n));
+    if (predictions.needs_grad() || targets.needs_grad()) {
+        out.set_requires_grad(true);
+        Tensor p = predictions, t = targets;
+        Tape::push_binary_op(p, t, out, [p, t, out, n]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            int ap = 0, at = 0;
+            tp_buf* gp = p.needs_grad() ? p.impl()->grad_for_write(&ap) : nullptr;
+            tp_buf* gt = t.needs_grad() ? t.impl()->grad_for_write(&at) : nullptr;
+            check(tp_bce_bwd(ctx(), p.buf(), t.buf(), g, gp, gt, n, ap, at));
+        });
+    }
+    return out;
+}
+
+Tensor mse_loss(const Tensor& predictions, const Tensor& targets) {             // src/loss.rs:75-80
+    Tensor diff = predictions - targets;
+    Tensor squared = diff * diff;
+    return squared.mean();
+}
+
+Tensor one_hot(const Tensor& indices, size_t num_classes) {                      // src/loss.rs:248-268 (host loop, as the reference)
+    if (indices.shape().size() != 1) panic("Indices must be 1D");
+    size_t b = indices.shape()[0];
+    const std::vector<float>& idx = indices.data();
+    std::vector<float> oh(b * num_classes, 0.0f);
+    for (size_t i = 0; i < b; ++i) {
+        size_t c = idx[i] > 0.0f ? (size_t)idx[i] : 0;
+        if (c >= num_classes) panic("Index %zu out of bounds for %zu classes", c, num_classes);
+        oh[i * num_classes + c] = 1.0f;
+    }
+    return Tensor::create(oh, {b, num_classes});
+}
+
+Tensor cross_entropy_loss_onehot(const Tensor& logits, const Tensor& targets) { // src/loss.rs:202-245
+    if (logits.shape() != targets.shape()) panic("Logits and targets shapes must match");
+    if (logits.shape().size() != 2) panic("Must be 2D tensors");
+    size_t batch = logits.shape()[0], total = logits.numel();
+    // forward: -sum(targets * log_softmax(logits)) / batch; the reference reads the sum back and builds a fresh scalar (:219),
+    // so the composed ops below it carry no gradient into the loss: the backward is the direct closure (:227-240)
+    Tensor logits_ng = logits;
+    logits_ng.set_requires_grad(false);
+    Tensor tg = targets;
+    tg.set_requires_grad(false);
+    Tensor logp = log_softmax(logits_ng, -1);
+    Tensor sum = (tg * logp).sum(std::nullopt, false);
+    Tensor out = Tensor::empty({1});
+    check(tp_accumulate(ctx(), out.buf(), sum.buf(), -1.0f / (float)batch, 1, 0));
+    if (logits.needs_grad()) {
+        out.set_requires_grad(true);
+        Tensor lg = logits;
+        Tape::push_unary_op(lg, out, [lg, tg, logp, out, batch, total]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            // (softmax - targets) * g / batch: softmax = exp(logp); two scaled accumulations with the device scalar g
+            Tensor probs = Tensor::empty(lg.shape());
+            check(tp_exp_fwd(ctx(), logp.buf(), probs.buf(), total));
+            Tensor diff = Tensor::empty(lg.shape());
+            check(tp_sub(ctx(), probs.buf(), tg.buf(), diff.buf(), total));
+            Tensor gb = Tensor::empty({1});                  // g / batch
+            check(tp_accumulate(ctx(), gb.buf(), g, 1.0f / (float)batch, 1, 0));
+            Tensor scaled = Tensor::empty(lg.shape());
+            check(tp_broadcast_bwd(ctx(), gb.buf(), scaled.buf(), 1, (int)total, 2, 0));      // every element = g / batch
+            int acc;
+            tp_buf* gin = lg.impl()->grad_for_write(&acc);
+            check(tp_mul_bwd(ctx(), diff.buf(), scaled.buf(), gin, total, acc));
+        });
+    }
     return out;
 }
 

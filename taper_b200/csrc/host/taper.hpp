@@ -85,6 +85,10 @@ public:
     Tensor sum(std::optional<size_t> dim, bool keepdim) const;    // src/tensor.rs:890-1018
     std::pair<Tensor, Tensor> max(std::optional<size_t> dim) const;   // src/tensor.rs:1021-1083
     Tensor argmax(std::optional<size_t> dim) const;               // src/tensor.rs:1086-1088
+    Tensor sigmoid() const;                                       // src/tensor.rs:594-634
+    Tensor mean() const;                                          // src/tensor.rs:772-800
+    Tensor pow(float exponent) const;                             // src/tensor.rs:1172-1206
+    Tensor sqrt() const { return pow(0.5f); }                     // src/tensor.rs:1209-1211
     Tensor exp() const;                                           // src/tensor.rs:1091-1133
     Tensor log() const;                                           // src/tensor.rs:1136-1169
     Tensor conv2d(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation) const;       // :1221-1285
@@ -144,6 +148,22 @@ struct Linear : Module {                                             // src/nn.r
 struct ReLU : Module {                                               // src/activation.rs:7-21
     Tensor forward(const Tensor& input) const override { return input.relu(); }
     const char* kind() const override { return "relu"; }
+};
+
+struct Sigmoid : Module {                                            // src/activation.rs:37-51
+    Tensor forward(const Tensor& input) const override { return input.sigmoid(); }
+    const char* kind() const override { return "sigmoid"; }
+};
+
+struct Dropout : Module {                                            // src/nn.rs:775-827 (mask from a seeded generator here)
+    float p;
+    bool training = true;
+    mutable uint64_t rng_state;
+    explicit Dropout(float p_, uint64_t seed = 0);
+    void eval() { training = false; }
+    void train() { training = true; }
+    Tensor forward(const Tensor& input) const override;
+    const char* kind() const override { return "dropout"; }
 };
 
 struct Sequential : Module {                                         // src/nn.rs:130-162
@@ -215,6 +235,10 @@ Tensor softmax(const Tensor& x, int dim);                            // :82-98 (
 Tensor log_softmax(const Tensor& x, int dim);                        // :101-126 — composed op-for-op
 Tensor cross_entropy_loss(const Tensor& logits, const Tensor& targets);   // :136-195 — fused fwd, direct bwd
 float accuracy(const Tensor& predictions, const Tensor& targets);    // :271-290
+Tensor bce_loss(const Tensor& predictions, const Tensor& targets);   // :6-72
+Tensor mse_loss(const Tensor& predictions, const Tensor& targets);   // :75-80  ((p - t) * (p - t)).mean(), composed as in the reference
+Tensor cross_entropy_loss_onehot(const Tensor& logits, const Tensor& targets);   // :202-245
+Tensor one_hot(const Tensor& indices, size_t num_classes);           // :248-268
 // device-side variant: correct count as a [1] tensor, no host sync (used by the captured train step)
 Tensor accuracy_count(const Tensor& predictions, const Tensor& targets);
 // variants writing into a caller-provided [1] tensor (the trainer's result slot)

@@ -509,6 +509,59 @@ Tensor Tensor::exp() const {
     return out;
 }
 
+// ---- sigmoid / mean / pow  (src/tensor.rs:594-634, 772-800, 1172-1211) ------------------------------------------
+Tensor Tensor::sigmoid() const {
+    Tensor out = Tensor::empty(shape());
+    check(tp_sigmoid_fwd(ctx(), buf(), out.buf(), numel()));
+    if (needs_grad()) {
+        out.set_requires_grad(true);
+        Tensor x = *this;
+        Tape::push_unary_op(x, out, [x, out]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            int acc;
+            tp_buf* gin = x.impl()->grad_for_write(&acc);
+            check(tp_sigmoid_bwd(ctx(), out.buf(), g, gin, x.numel(), acc));     // gin += g * s * (1 - s)
+        });
+    }
+    return out;
+}
+
+Tensor Tensor::mean() const {
+    if (numel() == 0) panic("mean of an empty tensor");
+    Tensor out = Tensor::empty({1});
+    check(tp_mean_fwd(ctx(), buf(), out.buf(), numel()));
+    if (needs_grad()) {
+        out.set_requires_grad(true);
+        Tensor x = *this;
+        Tape::push_unary_op(x, out, [x, out]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            int acc;
+            tp_buf* gin = x.impl()->grad_for_write(&acc);
+            check(tp_mean_bwd(ctx(), g, gin, x.numel(), acc));                   // gin += g[0] / n
+        });
+    }
+    return out;
+}
+
+Tensor Tensor::pow(float exponent) const {
+    Tensor out = Tensor::empty(shape());
+    check(tp_pow_fwd(ctx(), buf(), out.buf(), exponent, numel()));
+    if (needs_grad()) {
+        out.set_requires_grad(true);
+        Tensor x = *this;
+        Tape::push_unary_op(x, out, [x, out, exponent]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            int acc;
+            tp_buf* gin = x.impl()->grad_for_write(&acc);
+            check(tp_pow_bwd(ctx(), x.buf(), g, gin, exponent, x.numel(), acc)); // gin += g * n * x^(n-1)
+        });
+    }
+    return out;
+}
+
 Tensor Tensor::log() const {
     Tensor out = Tensor::empty(shape());
     check(tp_log_fwd(ctx(), buf(), out.buf(), numel()));

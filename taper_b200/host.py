@@ -156,6 +156,14 @@ class Model:
         check(lib.tp_model_forward(self.h, _fp(x), _shape(x.shape), x.ndim, _fp(out), cap, C.byref(n)))
         return out[: n.value].copy()
 
+    def regression_backward(self, x, targets, kind):
+        """forward; bce / mse / ce_onehot loss against `targets` (output-shaped); backward.  Returns the loss."""
+        x, targets = _f32(x), _f32(targets)
+        loss = C.c_float()
+        check(lib.tp_model_regression_backward(self.h, _fp(x), _shape(x.shape), x.ndim, _fp(targets), targets.size, kind.encode(),
+                                               C.byref(loss)))
+        return loss.value
+
     def loss_backward(self, x, labels):
         x, labels = _f32(x), _f32(labels)
         loss, correct, tl = C.c_float(), C.c_float(), C.c_size_t()

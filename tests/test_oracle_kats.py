@@ -348,3 +348,62 @@ def test_powi_matches_float32_square_and_multiply():    # src/optim.rs:88-89 `po
     assert float(R.powi_f32(0.9, 1)) == float(np.float32(0.9))
     assert float(R.powi_f32(0.999, 3)) == float(np.float32(np.float32(0.999) * np.float32(np.float32(0.999) * np.float32(0.999)))) or \
         math.isclose(float(R.powi_f32(0.999, 3)), 0.999 ** 3, rel_tol=1e-6)
+
+
+# ---- sigmoid / mean / pow / sqrt / BCE / MSE / one-hot cross-entropy -------------------------------
+def test_sqrt_pow_kats():                   # tests/smoke.rs:380-406
+    x = T.new([1.0, 4.0, 9.0], (3,)).requires_grad_()
+    y = x.sqrt()
+    np.testing.assert_allclose(y.data(), [1.0, 2.0, 3.0], atol=1e-6)
+    y.sum().backward()
+    np.testing.assert_allclose(x.grad(), [0.5, 0.25, 1.0 / 6.0], rtol=1e-6)        # d/dx sqrt(x) = 0.5 / sqrt(x)
+    np.testing.assert_allclose(T.new([2.0, 3.0], (2,)).pow(2.0).data(), [4.0, 9.0], rtol=1e-6)
+
+
+def test_one_hot_kat():                     # src/loss.rs:343-356
+    oh = R.one_hot(T.new([0, 2, 1], (3,)), 3)
+    assert oh.shape == (3, 3)
+    np.testing.assert_array_equal(oh.data(), [1, 0, 0, 0, 0, 1, 0, 1, 0])
+
+
+def test_bce_mse_sigmoid_against_torch():
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(5)
+    p = rng.uniform(0.02, 0.98, 12).astype(np.float32)
+    t = rng.integers(0, 2, 12).astype(np.float32)
+    P = T.new(p, (12,)).requires_grad_()
+    l = R.bce_loss(P, T.new(t, (12,)))
+    l.backward()
+    pt = torch.tensor(p, requires_grad=True)
+    lt = torch.nn.functional.binary_cross_entropy(pt, torch.tensor(t))
+    lt.backward()
+    assert abs(float(l.data()[0]) - lt.item()) < 1e-6
+    np.testing.assert_allclose(P.grad(), pt.grad.numpy(), rtol=2e-5)
+    R.Tape.reset()
+    a = rng.standard_normal(10).astype(np.float32)
+    b = rng.standard_normal(10).astype(np.float32)
+    A = T.new(a, (10,)).requires_grad_()
+    m = R.mse_loss(A, T.new(b, (10,)))
+    m.backward()
+    at = torch.tensor(a, requires_grad=True)
+    mt = torch.nn.functional.mse_loss(at, torch.tensor(b))
+    mt.backward()
+    assert abs(float(m.data()[0]) - mt.item()) < 1e-6
+    np.testing.assert_allclose(A.grad(), at.grad.numpy(), rtol=2e-5, atol=1e-7)
+    R.Tape.reset()
+    z = T.new(a, (10,)).requires_grad_()
+    s = z.sigmoid()
+    s.sum().backward()
+    zt = torch.tensor(a, requires_grad=True)
+    st = torch.sigmoid(zt)
+    st.sum().backward()
+    np.testing.assert_allclose(s.data(), st.detach().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(z.grad(), zt.grad.numpy(), rtol=2e-5)
+
+
+def test_ce_onehot_equals_index_ce():       # src/loss.rs:202-245 vs :136-195 on the KAT of tests/smoke.rs:450-458
+    lg = T.new([2, 1, 0, 0, 1, 2], (2, 3)).requires_grad_()
+    l = R.cross_entropy_loss_onehot(lg, R.one_hot(T.new([0, 2], (2,)), 3))
+    l.backward()
+    assert abs(float(l.data()[0]) - 0.407606) < 2e-6
+    np.testing.assert_allclose(lg.grad(), [-0.1673795, 0.1223642, 0.0450153, 0.0450153, 0.1223642, -0.1673795], atol=2e-6)
