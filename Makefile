@@ -10,7 +10,7 @@ CPP_SRCS  := $(wildcard $(CSRC)/host/*.cpp)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/host/%.cpp,$(OBJDIR)/host_%.o,$(CPP_SRCS))
 LIB       := taper_b200/libtaper_b200.so
 
-all: $(LIB)
+all: $(LIB) examples
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/taper_b200.h
 	@mkdir -p $(OBJDIR)
@@ -23,11 +23,12 @@ $(OBJDIR)/host_%.o: $(CSRC)/host/%.cpp $(wildcard $(CSRC)/host/*.hpp) include/ta
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl
 
-examples: $(LIB)
+EXAMPLES := build/train_mnist build/train_mnist_cnn build/xor
+examples: $(EXAMPLES)
+
+build/%: examples/%.cpp $(LIB) $(wildcard $(CSRC)/host/*.hpp) include/taper_b200.h
 	@mkdir -p build
-	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host examples/train_mnist.cpp -o build/train_mnist -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
-	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host examples/train_mnist_cnn.cpp -o build/train_mnist_cnn -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
-	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host examples/xor.cpp -o build/xor -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
+	g++ -O2 -std=c++17 -Iinclude -I$(CSRC)/host $< -o $@ -Ltaper_b200 -ltaper_b200 -Wl,-rpath,'$$ORIGIN/../taper_b200'
 
 clean:
 	rm -rf build $(LIB)
