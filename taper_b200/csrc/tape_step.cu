@@ -5,13 +5,17 @@
 // path is launch- and latency-bound (5-12 us each, 12 launches).  Here the host compiles the recorded tape of such a
 // model into a static job list and ONE cooperative kernel (one CTA per SM) walks it phase by phase with a grid barrier
 // between dependent phases:
-//     fwd GEMMs (gathering the batch rows straight out of the resident dataset)  ->  head (logits, log-softmax, NLL,
-//     accuracy, dlogits, dX of the head, ReLU mask)  ->  backward GEMMs (dW with the bias column-sum riding along, dX
-//     with the ReLU mask in the epilogue) + loss fold  ->  SGD / Adam / AdamW over the flat arena.
+//     fwd GEMMs (gathering the batch rows straight out of the resident dataset)  ->  head (fold of the fwd split-K partials,
+//     logits, log-softmax, NLL, accuracy, dlogits, dX of the head, ReLU mask)  ->  backward GEMMs (dW with the bias
+//     column-sum riding along, dX with the ReLU mask in the epilogue) + loss fold  ->  SGD / Adam / AdamW over the flat
+//     arena (fold of the dW split-K partials; with data parallelism also the gradient exchange over NVLink peer memory).
 // Arithmetic is exact fp32 FMA on the CUDA cores: at these sizes (512x128x784) the tensor-core path is bound by its own
 // TMA/TMEM/commit latency chain, not by math (measured: 12 us for the tcgen05 kernel alone).  Larger models keep the
 // tcgen05 GEMM path (gemm_tc.cu); tp_step_supported() draws the line.
-// Deterministic: split-K partials are folded in split order by the last CTA of a tile; no float atomics.
+// Deterministic: split-K partials are summed in split order by their consumer (head / optimizer job, or the last CTA of a
+// tile where the result must be materialised), peer gradient slices in rank order; no float atomics.
+// The step's {loss, #correct} are also published into a mapped pinned host slot followed by a sequence word, so the host
+// needs neither a D2H copy nor a CUDA event per step.
 #include "common.cuh"
 #include <cmath>
 #include <type_traits>
