@@ -140,6 +140,13 @@ def main():
               f"{np.mean(wait) / ghz / 1e3:6.2f} (min {np.min(wait) / ghz / 1e3:5.2f})")
         prev = t[:, 3 + 2 * ph]
     print(f"  total           {np.max(t[:, 1 + 2 * nph.value] - t[:, 0]) / ghz / 1e3:6.2f}")
+    for name, base in (("fwd GEMM item (K-major A)", 24), ("dW GEMM item (MN-major A)", 32)):
+        g = t[:, base:base + 5]
+        ok = (g[:, 0] > 0) & (g[:, 4] > g[:, 0])
+        if ok.any():
+            d = np.diff(g[ok], axis=1) / ghz / 1e3
+            print(f"  {name}: issue loads {d[:, 0].mean():.2f} | first stage lands + stash + sync {d[:, 1].mean():.2f} | multiply loop "
+                  f"{d[:, 2].mean():.2f} | store partials {d[:, 3].mean():.2f}  (mean us over {int(ok.sum())} CTAs)")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -72,7 +72,7 @@ constexpr int kDirectMaxK = 32;
 __global__ void __launch_bounds__(kThreads)
 conv_direct_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w2, const float* __restrict__ bias,
                           float* __restrict__ y, ConvGeom g, int relu, unsigned int total_pix) {
-    extern __shared__ float sw[];                              // [K][Cout] then [Cout]
+    extern __shared__ __align__(16) float sw[];                // [K][Cout] then [Cout]
     float* sb = sw + g.K * g.cout;
     for (int i = threadIdx.x; i < g.K * g.cout; i += kThreads) sw[i] = __ldg(w2 + i);
     for (int i = threadIdx.x; i < g.cout; i += kThreads) sb[i] = bias ? __ldg(bias + i) : 0.0f;
@@ -97,15 +97,33 @@ conv_direct_smallk_kernel(const float* __restrict__ x, const float* __restrict__
         float* yo = y + (size_t)nb * g.cout * hw + oh * (unsigned int)g.wo + ow;
         for (int co0 = 0; co0 < g.cout; co0 += 8) {
             float acc[8];
+            if ((g.cout & 7) == 0) {
+                // whole groups of 8 channels: packed FFMA2 (two IEEE FMAs per issue slot, same bits as fmaf), weights read
+                // as 8-byte pairs from shared memory
+                unsigned long long acc2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+                for (int k = 0; k < kDirectMaxK; ++k) {
+                    if (k < g.K) {
+                        const unsigned long long* wp = reinterpret_cast<const unsigned long long*>(sw + k * g.cout + co0);
+                        unsigned long long tt;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(tt) : "f"(tap[k]));
 #pragma unroll
-            for (int k = 0; k < kDirectMaxK; ++k) {
-                if (k < g.K) {
-                    const float* wr = sw + k * g.cout + co0;
+                        for (int j = 0; j < 4; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[j]) : "l"(tt), "l"(wp[j]));
+                    }
+                }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (co0 + j < g.cout) acc[j] = fmaf(tap[k], wr[j], acc[j]);
+                for (int j = 0; j < 4; ++j) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * j]), "=f"(acc[2 * j + 1]) : "l"(acc2[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kDirectMaxK; ++k) {
+                    if (k < g.K) {
+                        const float* wr = sw + k * g.cout + co0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (co0 + j < g.cout) acc[j] = fmaf(tap[k], wr[j], acc[j]);
+                    }
                 }
             }
 #pragma unroll

@@ -13,6 +13,16 @@ struct EpiArgs {
     int relu;
 };
 
+// Packed fp32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): two IEEE fused multiply-adds per issue slot, bit-identical to fmaf.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
 __device__ __forceinline__ float apply_epilogue(float v, const EpiArgs& ep, size_t idx, int col) {
     if (ep.bias) v += __ldg(ep.bias + col);
     if (ep.relu) v = fmaxf(v, 0.0f);
@@ -38,11 +48,17 @@ gemm_simt_kernel(int m, int n, int k, float alpha, const float* __restrict__ A, 
     const int kbeg = blockIdx.z * k_per_split;
     const int kend = min(k, kbeg + k_per_split);
 
+    constexpr bool kPacked = (TN % 2 == 0);                    // accumulate pairs along n with FFMA2
+    constexpr int TN2 = kPacked ? TN / 2 : 1;
     float acc[TM][TN];
+    f32x2 acc2[TM][TN2];
 #pragma unroll
-    for (int a = 0; a < TM; ++a)
+    for (int a = 0; a < TM; ++a) {
 #pragma unroll
         for (int b = 0; b < TN; ++b) acc[a][b] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < TN2; ++b) acc2[a][b] = 0ull;
+    }
 
     const bool a_k_contig = (acs == 1);
     const bool b_k_contig = (brs == 1);
@@ -70,14 +86,33 @@ gemm_simt_kernel(int m, int n, int k, float alpha, const float* __restrict__ A, 
             for (int a = 0; a < TM; ++a) av[a] = As[kk][ty * TM + a];
 #pragma unroll
             for (int b = 0; b < TN; ++b) bv[b] = Bs[kk][tx * TN + b];
+            if constexpr (kPacked) {
+                // pairs along n through FFMA2: half the issue slots of the scalar loop, same bits
+                f32x2 bp[TN2];
 #pragma unroll
-            for (int a = 0; a < TM; ++a)
+                for (int b = 0; b < TN2; ++b) bp[b] = pack2(bv[2 * b], bv[2 * b + 1]);
 #pragma unroll
-                for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                for (int a = 0; a < TM; ++a) {
+                    const f32x2 aa = pack2(av[a], av[a]);
+#pragma unroll
+                    for (int b = 0; b < TN2; ++b) fma2(acc2[a][b], aa, bp[b]);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < TM; ++a)
+#pragma unroll
+                    for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            }
         }
         __syncthreads();
     }
 
+    if constexpr (kPacked) {
+#pragma unroll
+        for (int a = 0; a < TM; ++a)
+#pragma unroll
+            for (int b = 0; b < TN2; ++b) unpack2(acc2[a][b], acc[a][2 * b], acc[a][2 * b + 1]);
+    }
 #pragma unroll
     for (int a = 0; a < TM; ++a) {
         int gi = i0 + ty * TM + a;

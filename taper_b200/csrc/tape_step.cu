@@ -145,6 +145,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+// Packed fp32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): two IEEE fused multiply-adds per issue slot, bit-identical to two
+// fmaf calls.  The multiply loops of this kernel are issue-bound, so this halves their instruction count.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
 // ---- grid barrier: one monotonically increasing arrival counter.  The host passes the counter value at launch
 // (bar_base); barrier k of this launch completes when the counter reaches bar_base + (k + 1) * gridDim.x (wrap-safe
 // compare).  Arrival is a fire-and-forget release reduction, so a CTA pays one poll round trip, not an atomic's too.
@@ -225,39 +236,46 @@ __device__ void gemm_item(const bool AKC, const bool BKC, const Job& j, int item
     const int* rb = j.b_input ? ridx : nullptr;
     const int tx = tid & 15, ty = tid >> 4;
     const bool do_cs = (!AKC) && j.colsum && tn == 0 && tid < BM;
+#define TP_GSTAMP(i) do { if (P.prof && tid == 0) P.prof[(size_t)blockIdx.x * kProfSlots + 24 + (AKC ? 0 : 8) + (i)] = clock64(); } while (0)
+    TP_GSTAMP(0);
 
-    float acc[4][4];
+    f32x2 acc2[4][2];                                          // 4 x 4 accumulators as packed pairs along n
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+    for (int a = 0; a < 4; ++a) { acc2[a][0] = 0ull; acc2[a][1] = 0ull; }
     float cs = 0.0f;
 
     // Stage = SK (64) k-values per operand held in registers while the previous stage is multiplied out of shared
     // memory: one global-memory round trip per 64 k instead of per 16 (the loop is latency-, not bandwidth-bound).
+    // The first TWO stages are requested before anything waits (the gathered rows come from HBM / cold TLB entries, ~2 us):
+    // later stages are requested right after the previous one has been written to shared memory.
     const int ns = (kend - kbeg + SK - 1) / SK;
-    float4 ra4[SUB], rb4[SUB];
+    float4 ra4[SUB], rb4[SUB];                                 // the stage that will be written to shared memory next
+    {
+        float4 r0a[SUB], r0b[SUB];
 #pragma unroll
-    for (int u = 0; u < SUB; ++u) {
-        ra4[u] = fetch(AKC, A, j.lda, ra, m0, j.M, kbeg + u * BK, kend, tid);
-        rb4[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, kbeg + u * BK, kend, tid);
-    }
+        for (int u = 0; u < SUB; ++u) {
+            r0a[u] = fetch(AKC, A, j.lda, ra, m0, j.M, kbeg + u * BK, kend, tid);
+            r0b[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, kbeg + u * BK, kend, tid);
+        }
+        if (ns > 1) {
 #pragma unroll
-    for (int u = 0; u < SUB; ++u) {
-        stash(AKC, As + u * (BK * LDS), ra4[u], tid);
-        stash(BKC, Bs + u * (BK * LDS), rb4[u], tid);
+            for (int u = 0; u < SUB; ++u) {
+                ra4[u] = fetch(AKC, A, j.lda, ra, m0, j.M, kbeg + SK + u * BK, kend, tid);
+                rb4[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, kbeg + SK + u * BK, kend, tid);
+            }
+        }
+        TP_GSTAMP(1);
+#pragma unroll
+        for (int u = 0; u < SUB; ++u) {
+            stash(AKC, As + u * (BK * LDS), r0a[u], tid);
+            stash(BKC, Bs + u * (BK * LDS), r0b[u], tid);
+        }
     }
     __syncthreads();
+    TP_GSTAMP(2);
     for (int st = 0; st < ns; ++st) {
         const int cur = st & 1;
         const int k0 = kbeg + st * SK;
-        if (st + 1 < ns) {
-#pragma unroll
-            for (int u = 0; u < SUB; ++u) {
-                ra4[u] = fetch(AKC, A, j.lda, ra, m0, j.M, k0 + SK + u * BK, kend, tid);
-                rb4[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, k0 + SK + u * BK, kend, tid);
-            }
-        }
         const float* as = As + cur * (SK * LDS);
         const float* bs = Bs + cur * (SK * LDS);
         const int klen = min(SK, kend - k0);
@@ -265,11 +283,14 @@ __device__ void gemm_item(const bool AKC, const bool BKC, const Job& j, int item
         for (int kk = 0; kk < klen; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(as + kk * LDS + ty * 4);
             const float4 b4 = *reinterpret_cast<const float4*>(bs + kk * LDS + tx * 4);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const f32x2 b01 = pack2(b4.x, b4.y), b23 = pack2(b4.z, b4.w);
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            for (int a = 0; a < 4; ++a) {
+                const f32x2 aa = pack2(av[a], av[a]);
+                fma2(acc2[a][0], aa, b01);
+                fma2(acc2[a][1], aa, b23);
+            }
         }
         if (do_cs) {
             for (int kk = 0; kk < klen; ++kk) cs += as[kk * LDS + tid];         // k ascending
@@ -280,10 +301,24 @@ __device__ void gemm_item(const bool AKC, const bool BKC, const Job& j, int item
                 stash(AKC, As + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), ra4[u], tid);
                 stash(BKC, Bs + (cur ^ 1) * (SK * LDS) + u * (BK * LDS), rb4[u], tid);
             }
+            if (st + 2 < ns) {
+#pragma unroll
+                for (int u = 0; u < SUB; ++u) {
+                    ra4[u] = fetch(AKC, A, j.lda, ra, m0, j.M, k0 + 2 * SK + u * BK, kend, tid);
+                    rb4[u] = fetch(BKC, B, j.ldb, rb, n0, j.N, k0 + 2 * SK + u * BK, kend, tid);
+                }
+            }
         }
         __syncthreads();
     }
 
+    TP_GSTAMP(3);
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        unpack2(acc2[a][0], acc[a][0], acc[a][1]);
+        unpack2(acc2[a][1], acc[a][2], acc[a][3]);
+    }
     const int gn = n0 + tx * 4;
     if (j.splits == 1) {
         if (gn < j.N) {
@@ -307,6 +342,7 @@ __device__ void gemm_item(const bool AKC, const bool BKC, const Job& j, int item
         }
     }
     if (do_cs) j.cs_partial[(size_t)split * mpad + m0 + tid] = cs;
+    TP_GSTAMP(4);
     if (j.defer_fold) return;                              // folded by the consumer after the grid barrier
     __threadfence();
     __syncthreads();
