@@ -1086,12 +1086,12 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     p.result_host = result_host;
     p.result_seq = result_host ? result_seq : 0u;
     p.world = 1; p.rank = 0;
+    // host mirrors (barrier counter, exchange sequence) only advance once the launch has been accepted
     p.bar_base = s->bar_count;
-    s->bar_count += (unsigned int)(s->params.n_phases - 1) * (unsigned int)s->grid;
     if (tp_xchg* x = s->xchg) {
-        x->seq += 1;
-        const size_t par = x->seq & 1u;
-        p.world = x->world; p.rank = x->rank; p.xseq = x->seq;
+        const unsigned int seq = x->seq + 1;
+        const size_t par = seq & 1u;
+        p.world = x->world; p.rank = x->rank; p.xseq = seq;
         p.x_items = x->items; p.x_arena = (long long)x->arena_len;
         p.my_flags = reinterpret_cast<unsigned int*>(x->window);
         p.my_slots = reinterpret_cast<const float*>(x->window + x->slots_off) + par * x->world * x->arena_len;
@@ -1108,6 +1108,8 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
         tp::set_error("tp_step_run: cooperative launch failed: %s", cudaGetErrorString(e));
         return TP_ERR_CUDA;
     }
+    s->bar_count += (unsigned int)(s->params.n_phases - 1) * (unsigned int)s->grid;
+    if (s->xchg) s->xchg->seq += 1;
     ctx->launches++;
     return TP_OK;
 }
