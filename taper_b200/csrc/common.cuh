@@ -63,6 +63,9 @@ struct tp_ctx {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
     void* tc_state = nullptr;        // tensor-map cache of the tcgen05 GEMM path
+    // per-context "function attribute already set" flags (cudaFuncSetAttribute is per device, contexts may sit on different ones)
+    bool attr_skinny = false;
+    bool attr_conv[3] = {false, false, false};
 };
 
 struct tp_buf {

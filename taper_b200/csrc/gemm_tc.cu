@@ -795,7 +795,7 @@ int launch_conv(tp_ctx* ctx, const CUtensorMap& mb, GemmParams& p, dim3 grid) {
     constexpr bool kOcc2 = BN <= 64;                  // two co-resident CTAs: 2 x (2 stages + tables) of shared memory, <= 102 registers
     auto kern = gemm_tf32_kernel<BN, false, true, true, true, kG2, kOcc2>;
     constexpr int smem = Smem<BN, true, true, kOcc2>::kTotal + kMaxConvK * 4 + 64;
-    static bool attr_set = false;
+    bool& attr_set = ctx->attr_conv[BN == 32 ? 0 : BN == 64 ? 1 : 2];
     if (!attr_set) {
         TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;

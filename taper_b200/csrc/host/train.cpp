@@ -170,7 +170,14 @@ struct Trainer::Impl {
         tp_buf* b[5] = {};
         if (optim::describe_fused_step(*tr.model, *tr.optimizer, batch, &d, b) && (size_t)d.dims[0] == sample_shape[0]) {
             d.materialize_grads = 0;
-            check(tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), world > 1 ? xchg : nullptr, &st));
+            // a step that qualifies on paper but cannot be built on this device (no cooperative launch, shared memory) simply
+            // stays on the tape + graph path; with an exchange every rank must agree, so there a failure is an error
+            int rc = tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), world > 1 ? xchg : nullptr, &st);
+            if (rc != TP_OK) {
+                if (world > 1) check(rc);
+                std::fprintf(stderr, "taper_b200: fused step unavailable (%s); using the tape + CUDA-graph path\n", tp_last_error());
+                st = nullptr;
+            }
         }
         fused[batch] = st;
         return st;

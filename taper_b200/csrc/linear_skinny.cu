@@ -273,11 +273,10 @@ bool linear_skinny_ok(int batch, int in_f, int out_f) {
 int linear_skinny_fwd(tp_ctx* ctx, const float* x, const float* w, const float* b, float* y, int batch, int in_f, int out_f,
                       int relu) {
     cudaSetDevice(ctx->device);
-    static bool attr = false;
-    if (!attr) {
+    if (!ctx->attr_skinny) {
         TP_CUDA(cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         TP_CUDA(cudaFuncSetAttribute(skinny_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+        ctx->attr_skinny = true;
     }
     int blocks = (batch * 32 + kThreads - 1) / kThreads;
     if (blocks > ctx->sm_count) blocks = ctx->sm_count;       // every block stages W once: no more blocks than SMs
@@ -291,11 +290,10 @@ int linear_skinny_fwd(tp_ctx* ctx, const float* x, const float* w, const float* 
 int linear_skinny_bwd(tp_ctx* ctx, const float* x, const float* w, const float* dy, const float* mask_y, float* dx, float* dw,
                       float* db, int batch, int in_f, int out_f, int acc_dx, int acc_dw, int acc_db) {
     cudaSetDevice(ctx->device);
-    static bool attr = false;
-    if (!attr) {
+    if (!ctx->attr_skinny) {
         TP_CUDA(cudaFuncSetAttribute(skinny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         TP_CUDA(cudaFuncSetAttribute(skinny_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+        ctx->attr_skinny = true;
     }
     BwdArgs a;
     a.x = x; a.w = w; a.dy = dy; a.mask_y = mask_y; a.dx = dx; a.dw = dw; a.db = db;
