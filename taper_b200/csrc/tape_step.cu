@@ -18,6 +18,7 @@
 // needs neither a D2H copy nor a CUDA event per step.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -642,10 +643,15 @@ tape_step_kernel(const StepParams P) {
     const int tid = threadIdx.x;
 
 #define TP_PROF(slot) do { if (P.prof && tid == 0) P.prof[(size_t)blockIdx.x * kProfSlots + (slot)] = clock64(); } while (0)
+    // Programmatic dependent launch: the next step's CTAs may be scheduled as soon as SMs free up (they stage their job list
+    // and gather index, which nothing in this step writes, and then wait for this grid to complete) — hides the ~3.5 us
+    // between two back-to-back launches.  No-ops when the kernel was launched without the PDL attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     TP_PROF(0);
     // setup: the three independent fetches (job list, gather index, optimizer state) are issued by different warps /
     // consumed late so that their latencies overlap
     const int* rix = P.perm ? ridx : nullptr;
+    if (P.perm && P.cursor_value < 0) asm volatile("griddepcontrol.wait;" ::: "memory");      // the device cursor is written by the previous step
     if (tid < kThreads / 2 || !P.perm) {                       // stage the job list
         const int nthr = P.perm ? kThreads / 2 : kThreads;
         const int words = P.n_jobs * (int)(sizeof(Job) / 4);
@@ -662,6 +668,8 @@ tape_step_kernel(const StepParams P) {
             ridx[r] = __ldg(P.perm + idx);
         }
     }
+    // everything below reads state the previous step (still draining under PDL) writes: parameters, moments, Adam state
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // optimizer state: fetched now (before CTA 0 advances it at the end), parked in shared memory, used in the last phase
     if (P.opt_kind != 0 && tid >= kThreads - H_COUNT) {
         const int q = tid - (kThreads - H_COUNT);
@@ -1102,7 +1110,27 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     }
     cudaSetDevice(ctx->device);
     void* args[] = {(void*)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)tape_step_kernel, dim3(s->grid), dim3(kThreads), args, s->smem, ctx->stream);
+    // Default: an ordinary launch with the programmatic-stream-serialization attribute (PDL): the grid is at most one CTA per SM,
+    // so once the previous step has drained every CTA is resident and the grid barrier is safe on a GPU this process has to
+    // itself (a spin limit turns a violation into a sticky device error, never a hang).  TAPER_STEP_COOP=1 asks the driver
+    // for a cooperative launch instead (co-residency guaranteed or the launch fails; no PDL overlap).
+    static const bool coop = [] { const char* v = getenv("TAPER_STEP_COOP"); return v && v[0] == '1'; }();
+    cudaError_t e;
+    if (coop) {
+        e = cudaLaunchCooperativeKernel((const void*)tape_step_kernel, dim3(s->grid), dim3(kThreads), args, s->smem, ctx->stream);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(s->grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = s->smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, tape_step_kernel, p);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         tp::set_error("tp_step_run: cooperative launch failed: %s", cudaGetErrorString(e));
