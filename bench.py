@@ -474,7 +474,7 @@ def run_ours(args, cfg_name, cfg):
         except Exception:
             pass
         fl = mlp_flops(arg, batch)
-        roofline = {"kernel": f"tape_step_kernel ({'-'.join(map(str, arg))}, batch {batch}, {opt_kind}): whole step, one cooperative launch",
+        roofline = {"kernel": f"tape_step_kernel ({'-'.join(map(str, arg))}, batch {batch}, {opt_kind}): whole step, one launch",
                     "bound": "hbm", "achieved": step_bytes / (step_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
                     "frac": step_bytes / (step_us * 1e-6) / 1e9 / hbm, "traffic": traffic, "launch_us": step_us,
                     "algorithmic_bytes": step_bytes,
@@ -511,7 +511,7 @@ def run_ours(args, cfg_name, cfg):
                    "conv_adjoint": "full" if args.full_adjoint else "strict_reference (SURVEY A1)",
                    "l2_policy": f"inputs larger than L2: every step gathers a fresh batch from a {DATASET_N}x{int(np.prod(sample_shape))} "
                                 "fp32 resident dataset (188 MB); parameters/optimizer state are the step's own working set",
-                   "step_path": ("device tape: one persistent cooperative kernel per step (exact fp32)"
+                   "step_path": ("device tape: one persistent kernel per step (grid barrier between phases, PDL between steps; exact fp32)"
                                  + ("; gradient exchange in-kernel over NVLink peer memory" if world > 1 else "")) if fused
                                 else ("tape + CUDA graph, one kernel per op" + ("; NCCL allreduce in the graph" if world > 1 else "")),
                    "cuda_graph": not fused, "last_step": {"loss": last[0], "correct": last[1]}},
