@@ -297,7 +297,7 @@ int tp_gather_batch(tp_ctx*, const tp_buf* images, const tp_buf* labels, const t
 int tp_cursor_advance(tp_ctx*, tp_buf* cursor_i32, int delta, int modulo);
 
 /* ---------------------------------------------------------------------------------------------
- * Device tape: one whole training step of a small MLP as ONE persistent cooperative kernel.
+ * Device tape: one whole training step of a small MLP as ONE persistent kernel (one CTA per SM, grid barrier between phases).
  * Replaces the loop body of Trainer::train_epoch (src/train.rs:106-138: Tape::reset, model.forward
  * [Linear src/nn.rs:54-60, ReLU src/ops.rs:312-374], cross_entropy_loss src/loss.rs:136-195, accuracy
  * src/loss.rs:271-290, loss.backward src/tape.rs:106-127, optimizer.step src/optim.rs:21-33 / 83-113 /

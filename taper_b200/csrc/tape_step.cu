@@ -3,8 +3,8 @@
 // The reference's step (src/train.rs:106-138: Tape::reset, forward, cross_entropy_loss, accuracy, backward,
 // optimizer.step, zero_grad) on the small MNIST MLPs is ~0.2 GFLOP: on a B200 every kernel of the eager / CUDA-graph
 // path is launch- and latency-bound (5-12 us each, 12 launches).  Here the host compiles the recorded tape of such a
-// model into a static job list and ONE cooperative kernel (one CTA per SM) walks it phase by phase with a grid barrier
-// between dependent phases:
+// model into a static job list and ONE persistent kernel (one CTA per SM) walks it phase by phase with a grid barrier
+// between dependent phases (consecutive steps are chained by programmatic dependent launch):
 //     fwd GEMMs (gathering the batch rows straight out of the resident dataset)  ->  head (fold of the fwd split-K partials,
 //     logits, log-softmax, NLL, accuracy, dlogits, dX of the head, ReLU mask)  ->  backward GEMMs (dW with the bias
 //     column-sum riding along, dX with the ReLU mask in the epilogue) + loss fold  ->  SGD / Adam / AdamW over the flat
