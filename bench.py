@@ -93,21 +93,35 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.lines:
-            if not any(a <= t <= b for a, b in windows):
-                continue
-            f = [s.strip() for s in line.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for nme, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+        def collect(keep):
+            sm, mx, reasons = [], [], set()
+            for t, line in self.lines:
+                if not keep(t):
+                    continue
+                f = [s.strip() for s in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except Exception:
+                    continue
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, reasons
+
+        sm, mx, reasons = collect(lambda t: any(a <= t <= b for a, b in windows))
+        note = None
+        if not sm and windows:
+            # a timed region shorter than the 50 ms sampling period: use the samples within 0.5 s of it instead
+            lo, hi = min(a for a, _ in windows) - 0.5, max(b for _, b in windows) + 0.5
+            sm, mx, reasons = collect(lambda t: lo <= t <= hi)
+            note = "timed regions shorter than the sampling period: samples within 0.5 s of them"
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def build_oracle(kind, arg, seed):
