@@ -1041,7 +1041,12 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     s->params.hyper = hyper ? hyper->ptr : nullptr;
     s->params.err = ctx->dev_error;
     s->smem = smem_bytes((int)s->jobs.size(), desc->batch);
-    if (cudaFuncSetAttribute(tape_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem) != cudaSuccess) {
+    // The limit is a property of the kernel, not of this step: steps of several batch sizes coexist (a ragged last batch
+    // compiles its own step), so it is raised to the device's opt-in maximum rather than set to this step's need — a smaller
+    // later step must not lower it under an earlier one.
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) != cudaSuccess || (size_t)optin < s->smem ||
+        cudaFuncSetAttribute(tape_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
         cudaGetLastError();
         tp::set_error("tp_step_create: %zu bytes of shared memory not available", s->smem);
         return fail(TP_ERR_CUDA);

@@ -67,9 +67,9 @@ def make_pair(builder, spec, seed=0):
     return ref, m
 
 
-def batches(rng, n_steps, batch, sample_shape, ragged=None):
+def batches(rng, n_steps, batch, sample_shape, ragged=None, ragged_at=None):
     for i in range(n_steps):
-        b = ragged if (ragged and i == n_steps - 1) else batch
+        b = ragged if (ragged and i == (n_steps - 1 if ragged_at is None else ragged_at)) else batch
         x = rng.random((b,) + tuple(sample_shape)).astype(F32)
         y = rng.integers(0, 10, b).astype(F32)
         yield x, y
@@ -84,7 +84,7 @@ def oracle_opt(kind, params, lr, wd, eps=None):
 
 
 def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=None, tol=1e-4, use_graph=True, seed=0, eps=None,
-               fused=False):
+               fused=False, ragged_at=None):
     """fused=False: tape + CUDA-graph path (one kernel per op); fused=True: the device tape (tp_step_*, one persistent
     kernel per step) where the model qualifies."""
     from taper_b200 import host
@@ -94,7 +94,7 @@ def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=N
     tr.set_use_fused(fused)
     opt = oracle_opt(kind, ref.parameters(), lr, wd, eps)
     rng = np.random.default_rng(seed + 1)
-    for i, (x, y) in enumerate(batches(rng, steps, batch, sample_shape, ragged)):
+    for i, (x, y) in enumerate(batches(rng, steps, batch, sample_shape, ragged, ragged_at)):
         # rows whose two largest logits agree to within the parity tolerance may legitimately break the tie either way
         # (after the first Adam step the parameters themselves are only comparable to a few % of one update, see
         # close_after_adam, so the margin is taken 20x wider there)
@@ -113,6 +113,17 @@ def run_parity(builder, spec, kind, lr, wd, batch, sample_shape, steps, ragged=N
         else:
             close_after_adam(m.get_param(j), p.data(), lr, steps, f"param {j} after {steps} steps")
     return tr, m
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_ragged_batch_in_the_middle_of_an_epoch_sequence(fused):
+    """The last batch of an epoch is ragged (60000 = 234 x 256 + 96) and the next epoch returns to the full size: the steps
+    compiled for the two batch sizes (device tapes / captured graphs) must coexist — a later, smaller one may not take
+    anything (shared-memory opt-in, scratch, result slots) away from an earlier, larger one."""
+    from taper_b200 import host
+    tr, _ = run_parity(lambda r: R.build_mlp([784, 128, 10], r), host.MLP_784_128_10, "sgd", 0.01, 0.0, 512, (784,), 8, ragged=96,
+                       ragged_at=3, fused=fused)
+    assert tr.fused_steps() == (8 if fused else 0)
 
 
 # ---- cfg1: MLP 784-128-10, batch 64, SGD (src/train.rs:390-394 model) --------------------------------------
