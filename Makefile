@@ -12,7 +12,7 @@ LIB       := taper_b200/libtaper_b200.so
 
 all: $(LIB) examples
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/taper_b200.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tc_ptx.cuh include/taper_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

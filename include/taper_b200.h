@@ -110,9 +110,14 @@ int  tp_graph_destroy(tp_graph* g);
 int tp_sgemm_rowmajor(tp_ctx* ctx, int trans_a, int trans_b, int m, int n, int k, float alpha,
                       const tp_buf* a, const tp_buf* b, float beta, tp_buf* c);
 /* GEMM math mode for the tcgen05 path: 0 = exact fp32 (CUDA-core FFMA), 1 = 3xTF32 split
- * (fp32-accurate on the tensor cores, default), 2 = 1xTF32 (throughput mode). */
+ * (fp32-accurate on the tensor cores, default), 2 = 1xTF32 (throughput mode), 3 = bf16x3 (operands split into
+ * bf16 hi + lo, three kind::f16 MMAs per product: ~1e-5 of |C|inf, half the tensor-pipe cost of 3xTF32; shapes TMA
+ * cannot describe run as mode 1). */
 int tp_set_gemm_mode(tp_ctx* ctx, int mode);
 int tp_get_gemm_mode(tp_ctx* ctx, int* mode);
+/* fp32 -> the pre-split operand format of mode 3: dst holds bf16 hi = rn(x) at [0, n) and lo = rn(x - hi) at
+ * [plane, plane + n) with plane = n rounded up to 8 (dst is a tp_buf of >= plane floats = 2 * plane bf16). */
+int tp_split_bf16(tp_ctx* ctx, const tp_buf* src, tp_buf* dst, size_t n);
 
 /* ---------------------------------------------------------------------------------------------
  * Elementwise family  (src/tensor.rs:14-234 `pub mod simd`; src/ops.rs:8-151, 312-496)
@@ -353,6 +358,22 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
 int tp_step_run(tp_ctx* ctx, tp_step* step, const tp_buf* x, const tp_buf* labels, const tp_buf* perm_i32,
                 tp_buf* cursor_i32, int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host,
                 uint32_t result_seq);
+/* Wide models (at least one hidden layer, feature widths multiples of 8, >= 1.5 GFLOP per step; TAPER_STEP_WIDE=0/1 forces the
+ * choice) run as a fixed plan of tcgen05 kernels chained with programmatic dependent launch instead of the persistent kernel:
+ * bf16x3 GEMMs on pre-split operands (tp_set_gemm_mode 3: ~1e-5 of |C|inf) with bias / ReLU / ReLU-mask / bias-gradient /
+ * operand-split epilogues, a fused classifier head and a fused optimizer step; data-parallel runs sum the gradient arena with
+ * the context's NCCL communicator (tp_comm_init).  Same entry points, same results contract.
+ *   tp_step_kind    : 0 unsupported, 1 persistent kernel, 2 wide plan: what tp_step_create would build
+ *   tp_step_run_u8  : as tp_step_run with x holding u8 pixels (MNIST's on-disk format; the plan divides by 255 on the
+ *                     device, src/data/mnist.rs:225): 4x fewer bytes over PCIe / HBM.  Wide plan only.
+ *   tp_step_refresh : tell the step that the parameter arena was written by somebody else (upload, broadcast, another step):
+ *                     the plan re-derives its bf16 operand planes on the next run */
+int tp_step_kind(const tp_step_desc* desc);
+int tp_step_run_u8(tp_ctx* ctx, tp_step* step, const tp_buf* x_u8, const tp_buf* labels, const tp_buf* perm_i32,
+                   tp_buf* cursor_i32, int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host,
+                   uint32_t result_seq);
+int tp_step_refresh(tp_step* step);
+int tp_step_is_wide(const tp_step* step);                            /* 1: this step is the wide plan */
 int tp_step_info(const tp_step* step, int* n_phases, int* n_jobs, int* grid);
 /* per-CTA SM-clock stamps of the last run: [grid][slots] = entry, setup done, then {work done, barrier passed}
  * for each phase (evidence for profiles/: where the step's time goes) */

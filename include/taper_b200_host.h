@@ -26,7 +26,7 @@ int tp_host_ctx(tp_ctx** out);
  *   conv_full_adjoint      0 = reproduce the reference's cut conv autograd chain (default), 1 = full adjoint
  *   fuse_linear_relu       1 = Sequential runs Linear+ReLU as one fused launch (default)
  *   reference_op_sequence  1 = Linear records transpose -> matmul -> add_broadcast exactly as src/nn.rs:54-60
- *   gemm_mode              0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (default), 2 = 1xTF32 tcgen05 */
+ *   gemm_mode              0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (default), 2 = 1xTF32 tcgen05, 3 = bf16x3 tcgen05 */
 int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op_sequence, int gemm_mode);
 
 /* Sequential from a comma-separated layer list (the constructors of src/nn.rs, src/activation.rs):
@@ -74,6 +74,15 @@ int tp_trainer_step_async(tp_trainer* t, const float* images, const float* label
 int tp_trainer_load_dataset(tp_trainer* t, const float* images, const float* labels, size_t n,
                             const size_t* sample_shape, int ndim, const uint32_t* perm);
 int tp_trainer_step_resident(tp_trainer* t, size_t batch);
+/* the same two entry points with u8 pixels (MNIST's on-disk format; the reference divides by 255 at load time,
+ * src/data/mnist.rs:225): the wide step plan (tp_step_run_u8) divides on the device, so a quarter of the bytes cross PCIe
+ * and sit in HBM; models without a wide plan widen a host-fed u8 batch on the host and refuse a u8 resident dataset */
+int tp_trainer_step_async_u8(tp_trainer* t, const void* images_u8, const float* labels, size_t batch,
+                             const size_t* sample_shape, int ndim, int pinned);
+int tp_trainer_load_dataset_u8(tp_trainer* t, const void* images_u8, const float* labels, size_t n,
+                               const size_t* sample_shape, int ndim, const uint32_t* perm);
+/* 2 if the last fused step ran the wide tcgen05 plan, 1 the persistent kernel, 0 none yet */
+int tp_trainer_fused_kind(tp_trainer* t, int* kind);
 int tp_trainer_fetch(tp_trainer* t, float* loss, float* correct);
 int tp_trainer_pending(tp_trainer* t, size_t* count);
 /* Trainer::evaluate body (src/train.rs:156-166) on one host batch */

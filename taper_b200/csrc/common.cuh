@@ -48,7 +48,7 @@ struct tp_ctx {
     tp::Allocator alloc;
     tp::Allocator* capture_pool = nullptr;   // non-null between tp_graph_begin and tp_graph_end
     uint64_t launches = 0;
-    int gemm_mode = 1;               // 0 exact fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05
+    int gemm_mode = 1;               // 0 exact fp32 SIMT, 1 3xTF32 tcgen05, 2 1xTF32 tcgen05, 3 bf16x3 tcgen05
     int* dev_error = nullptr;        // sticky device-side error flag
     int* dev_counters = nullptr;     // kNumCounters zero-initialised "last block done" tickets (each user resets its own)
     void* pinned = nullptr;          // staging ring for pageable uploads
@@ -63,6 +63,7 @@ struct tp_ctx {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
     void* tc_state = nullptr;        // tensor-map cache of the tcgen05 GEMM path
+    void* bx3_state = nullptr;       // cluster residency table of the bf16x3 GEMM path
     // per-context "function attribute already set" flags (cudaFuncSetAttribute is per device, contexts may sit on different ones)
     bool attr_skinny = false;
     bool attr_conv[3] = {false, false, false};
@@ -149,6 +150,43 @@ struct ConvShape {
     int n, c, h, w, cout, kh, kw, sh, sw, ph, pw, dh, dw, ho, wo, K;
 };
 int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, const float* bias, int relu, float* y, const ConvShape& g);
+
+
+// ---- bf16x3 tensor-core GEMM on pre-split operands (gemm_bx3.cu) -----------------------------------------------------
+// A "split" tensor holds an fp32 tensor of n elements as two bf16 planes: hi = rn_bf16(x) at [0, n) and
+// lo = rn_bf16(x - hi) `plane` elements further (plane >= n, multiple of 8).
+struct Bx3Epilogue {
+    const float* bias = nullptr;     // per output column
+    int relu = 0;
+    const float* relu_mask = nullptr;// fp32 [m,n]: out = mask > 0 ? out : 0
+    float* colsum_part = nullptr;    // [tiles_m * splits][n] partial column sums of the stored values
+    uint16_t* c_split = nullptr;     // bf16 planes of the output (operand of the next GEMM)
+    long long c_plane = 0;           // 0: m * n
+};
+struct Bx3Launch {                   // a prepared launch: tensor maps encoded once, replayed every step
+    CUtensorMap ma, mb;
+    int m, n, k, bn, splits, tiles_m, tiles_n;
+    bool a_mn, b_mn, drain;
+    float alpha, beta;
+    float* c;
+    uint16_t* c_split;
+    long long c_plane;
+    const float* bias;
+    const float* relu_mask;
+    int relu;
+    float* colsum_part;
+};
+int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const uint16_t* a_split, long long a_plane,
+                const uint16_t* b_split, long long b_plane, float beta, float* c, const Bx3Epilogue& ep, Bx3Launch* out);
+int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl);
+int split_bf16(tp_ctx* ctx, const float* src, uint16_t* dst, size_t n, long long plane, bool pdl);
+// fp32 operands: splits both into temporaries first.  TP_ERR_UNSUPPORTED when the shape cannot go through TMA.
+int gemm_bx3(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, const float* b, float beta,
+             float* c, const Epilogue& ep);
+void gemm_bx3_destroy(tp_ctx* ctx);
+// optimizer step over a flat arena that also rewrites the parameters' bf16 hi/lo planes (optim.cu); kind 0 SGD, 1 Adam, 2 AdamW
+int optimizer_step_split(tp_ctx* ctx, int kind, float* p, const float* g, float* m, float* v, const float* hyper, float sgd_lr,
+                         float grad_scale, size_t n, uint16_t* hi, uint16_t* lo, bool pdl);
 
 // Linear layers with out_features <= 16 (classifier heads), see linear_skinny.cu
 bool linear_skinny_ok(int batch, int in_f, int out_f);

@@ -5,8 +5,13 @@ namespace tp {
 
 int gemm_rowmajor(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, const float* b,
                   float beta, float* c, const Epilogue& ep) {
+    if (ctx->gemm_mode == 3) {
+        int rc = gemm_bx3(ctx, ta, tb, m, n, k, alpha, a, b, beta, c, ep);
+        if (rc != TP_ERR_UNSUPPORTED) return rc;
+    }
     if (ctx->gemm_mode != 0) {
-        int rc = gemm_tc(ctx, ta, tb, m, n, k, alpha, a, b, beta, c, ep, ctx->gemm_mode);
+        // bf16x3 shapes TMA cannot describe fall back to the fp32-accurate 3xTF32 kernel
+        int rc = gemm_tc(ctx, ta, tb, m, n, k, alpha, a, b, beta, c, ep, ctx->gemm_mode == 3 ? 1 : ctx->gemm_mode);
         if (rc != TP_ERR_UNSUPPORTED) return rc;
     }
     return gemm_simt(ctx, ta, tb, m, n, k, alpha, a, b, beta, c, ep);
@@ -17,7 +22,7 @@ int gemm_rowmajor(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha,
 extern "C" {
 
 int tp_set_gemm_mode(tp_ctx* ctx, int mode) {
-    TP_CHECK_ARG(ctx && mode >= 0 && mode <= 2, "tp_set_gemm_mode: mode must be 0 (fp32), 1 (3xTF32) or 2 (1xTF32)");
+    TP_CHECK_ARG(ctx && mode >= 0 && mode <= 3, "tp_set_gemm_mode: mode must be 0 (fp32), 1 (3xTF32), 2 (1xTF32) or 3 (bf16x3)");
     ctx->gemm_mode = mode;
     return TP_OK;
 }

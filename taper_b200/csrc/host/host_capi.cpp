@@ -274,6 +274,26 @@ int tp_trainer_load_dataset(tp_trainer* t, const float* images, const float* lab
     return guarded([&] { TRAINER(t); t->tr->load_dataset(images, labels, n, to_shape(sample_shape, ndim), perm); });
 }
 
+int tp_trainer_step_async_u8(tp_trainer* t, const void* images_u8, const float* labels, size_t batch, const size_t* sample_shape,
+                             int ndim, int pinned) {
+    return guarded([&] {
+        TRAINER(t);
+        t->tr->train_batch_async_u8(static_cast<const uint8_t*>(images_u8), labels, batch, to_shape(sample_shape, ndim), pinned != 0);
+    });
+}
+
+int tp_trainer_load_dataset_u8(tp_trainer* t, const void* images_u8, const float* labels, size_t n, const size_t* sample_shape,
+                               int ndim, const uint32_t* perm) {
+    return guarded([&] {
+        TRAINER(t);
+        t->tr->load_dataset_u8(static_cast<const uint8_t*>(images_u8), labels, n, to_shape(sample_shape, ndim), perm);
+    });
+}
+
+int tp_trainer_fused_kind(tp_trainer* t, int* kind) {
+    return guarded([&] { TRAINER(t); if (kind) *kind = t->tr->fused_kind(); });
+}
+
 int tp_trainer_step_resident(tp_trainer* t, size_t batch) {
     return guarded([&] { TRAINER(t); t->tr->train_batch_resident(batch); });
 }

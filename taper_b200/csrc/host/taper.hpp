@@ -450,6 +450,10 @@ public:
     StepResult train_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);
     void train_batch_async(const float* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned);
     void load_dataset(const float* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm);
+    // the same with u8 pixels, MNIST's on-disk format (src/data/mnist.rs:225 divides by 255 at load time; here the wide step
+    // plan does it on the device, so a quarter of the bytes cross PCIe / sit in HBM)
+    void train_batch_async_u8(const uint8_t* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned);
+    void load_dataset_u8(const uint8_t* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm);
     void train_batch_resident(size_t batch);
     StepResult fetch();
     size_t pending() const;
@@ -478,8 +482,11 @@ public:
     // batch qualify (describe_fused_step + tp_step_supported); everything else takes the tape + CUDA-graph path
     void set_use_fused(bool v) { use_fused_ = v; }
     uint64_t fused_steps() const { return fused_steps_; }
+    int fused_kind() const;                                          // 2 wide tcgen05 plan, 1 persistent kernel, 0 none run yet
 private:
     struct Impl;
+    void train_batch_async_impl(const void* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned, bool u8);
+    void load_dataset_impl(const void* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm, bool u8);
     std::unique_ptr<Impl> p_;
     bool use_graph_ = true;
     uint64_t graph_replays_ = 0;

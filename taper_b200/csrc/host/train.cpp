@@ -155,32 +155,58 @@ struct Trainer::Impl {
     tp_buf *ds_images = nullptr, *ds_labels = nullptr, *ds_perm = nullptr, *ds_cursor = nullptr;
     size_t ds_n = 0;
     Shape ds_sample;
+    bool ds_u8 = false;                                      // ds_images holds u8 pixels (MNIST on-disk format)
     int world = 1;
     // fused device step per batch size (NULL once a size is known not to qualify)
-    std::map<size_t, tp_step*> fused;
+    std::map<std::pair<size_t, size_t>, tp_step*> fused;
     tp_xchg* xchg = nullptr;                                 // NVLink peer-memory gradient exchange (world > 1)
     bool xchg_connected = false;
 
+    // fused device step per (batch, sample width): the persistent-kernel tape for small MLPs, the tcgen05 kernel plan for wide
+    // ones (tp_step_kind).  Data-parallel: the persistent kernel needs the connected peer window, the plan uses NCCL.
     tp_step* fused_step(Trainer& tr, size_t batch, const Shape& sample_shape) {
-        if ((world != 1 && !xchg_connected) || sample_shape.size() != 1) return nullptr;
-        auto it = fused.find(batch);
+        if (sample_shape.size() != 1) return nullptr;
+        const std::pair<size_t, size_t> key{batch, sample_shape[0]};
+        auto it = fused.find(key);
         if (it != fused.end()) return it->second;
         tp_step* st = nullptr;
         tp_step_desc d;
         tp_buf* b[5] = {};
         if (optim::describe_fused_step(*tr.model, *tr.optimizer, batch, &d, b) && (size_t)d.dims[0] == sample_shape[0]) {
+            const int kind = tp_step_kind(&d);
+            if (kind == 1 && world != 1 && !xchg_connected) return nullptr;      // not cached: the window may still be connected
             d.materialize_grads = 0;
             // a step that qualifies on paper but cannot be built on this device (no cooperative launch, shared memory) simply
             // stays on the tape + graph path; with an exchange every rank must agree, so there a failure is an error
-            int rc = tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), world > 1 ? xchg : nullptr, &st);
+            int rc = tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), (world > 1 && kind == 1) ? xchg : nullptr, &st);
             if (rc != TP_OK) {
                 if (world > 1) check(rc);
                 std::fprintf(stderr, "taper_b200: fused step unavailable (%s); using the tape + CUDA-graph path\n", tp_last_error());
                 st = nullptr;
             }
         }
-        fused[batch] = st;
+        fused[key] = st;
         return st;
+    }
+
+    // The wide plan keeps bf16 operand planes of the parameters, refreshed by its own optimizer kernel.  Anything else that
+    // writes the parameters (set_data, checkpoint load, broadcast, a step on another path) bumps their versions: the plan is
+    // told to re-derive the planes whenever the versions are not the ones it left behind.
+    std::vector<float> u8_scratch;
+    bool fused_is_wide(tp_step* st) const { return st && tp_step_is_wide(st) == 1; }
+    tp_step* last_fused = nullptr;
+    uint64_t fused_stamp = 0;
+    uint64_t param_stamp(Trainer& tr) const {
+        uint64_t s = 0;
+        for (auto& t : tr.model->parameters()) s += t.impl()->version;
+        return s;
+    }
+    void before_fused(Trainer& tr, tp_step* st) {
+        if (st != last_fused || param_stamp(tr) != fused_stamp) check(tp_step_refresh(st));
+    }
+    void after_fused(Trainer& tr, tp_step* st) {
+        last_fused = st;
+        fused_stamp = param_stamp(tr);
     }
 
     size_t ds_cursor_host = 0;                               // host mirror of the device cursor
@@ -260,6 +286,7 @@ void Trainer::peer_exchange_connect(const void* handles) {
     p.xchg_connected = true;
     for (auto& kv : p.fused) tp_step_destroy(kv.second);    // steps compiled before the exchange existed
     p.fused.clear();
+    p.last_fused = nullptr;
 }
 
 void Trainer::broadcast_parameters(int root) {
@@ -305,6 +332,8 @@ Shape full_shape(size_t batch, const Shape& sample) {
 
 size_t Trainer::pending() const { return p_->head - p_->tail; }
 
+int Trainer::fused_kind() const { return !p_->last_fused ? 0 : (p_->fused_is_wide(p_->last_fused) ? 2 : 1); }
+
 StepResult Trainer::fetch() {
     if (p_->head == p_->tail) panic("Trainer::fetch: no step outstanding");
     size_t i = p_->tail % kRing;
@@ -331,16 +360,38 @@ StepResult Trainer::fetch() {
 // enqueue: [optional gather] + step (eager for the first iteration of a shape, then captured, then replayed),
 // followed by the asynchronous read-back of {loss, correct} into the next ring slot.
 void Trainer::train_batch_async(const float* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned) {
+    train_batch_async_impl(images, labels, batch, sample_shape, pinned, false);
+}
+
+void Trainer::train_batch_async_u8(const uint8_t* images, const float* labels, size_t batch, const Shape& sample_shape, bool pinned) {
+    train_batch_async_impl(images, labels, batch, sample_shape, pinned, true);
+}
+
+void Trainer::train_batch_async_impl(const void* images_any, const float* labels, size_t batch, const Shape& sample_shape, bool pinned,
+                                     bool u8) {
     Impl& p = *p_;
     if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
     Shape fs_shape = full_shape(batch, sample_shape);
+    tp_ctx* c = ctx();
+    tp_step* fs = use_fused_ ? p.fused_step(*this, batch, sample_shape) : nullptr;
+    if (u8) {
+        // MNIST's on-disk pixel format (src/data/mnist.rs:225 converts to f32 at load time): the bytes cross PCIe as they are
+        // and the step divides by 255 on the device
+        if (!fs || !p.fused_is_wide(fs)) {
+            // no wide plan for this model: widen on the host side of the boundary into the f32 path
+            const uint8_t* src = static_cast<const uint8_t*>(images_any);
+            p.u8_scratch.resize(batch * shape_numel(sample_shape));
+            for (size_t i = 0; i < p.u8_scratch.size(); ++i) p.u8_scratch[i] = (float)src[i] / 255.0f;
+            train_batch_async_impl(p.u8_scratch.data(), labels, batch, sample_shape, false, false);
+            return;
+        }
+    }
+    const float* images = static_cast<const float*>(images_any);
     Slot& s = p.slots[fs_shape];
     if (!s.x.defined()) {
         s.x = Tensor::empty(fs_shape);
         s.y = Tensor::empty({batch});
     }
-    tp_ctx* c = ctx();
-    tp_step* fs = use_fused_ ? p.fused_step(*this, batch, sample_shape) : nullptr;
     tp_buf *xin = s.x.buf(), *yin = s.y.buf();
     size_t k = 0;
     if (pinned) {
@@ -353,7 +404,7 @@ void Trainer::train_batch_async(const float* images, const float* labels, size_t
             check(tp_event_create(c, &s.done[k]));
         }
         if (s.done_valid[k]) check(tp_copy_wait_event(c, s.done[k]));
-        check(tp_copy_upload_pinned(c, s.sx[k].buf(), images, s.x.numel()));
+        check(tp_copy_upload_pinned(c, s.sx[k].buf(), images, u8 ? (s.x.numel() + 3) / 4 : s.x.numel()));
         check(tp_copy_upload_pinned(c, s.sy[k].buf(), labels, batch));
         check(tp_copy_event_record(c, s.ready[k]));
         check(tp_stream_wait_event(c, s.ready[k]));
@@ -368,18 +419,25 @@ void Trainer::train_batch_async(const float* images, const float* labels, size_t
         }
         s.staged++;
     } else {
-        check(tp_buf_upload(c, s.x.buf(), images, s.x.numel()));
+        check(tp_buf_upload(c, s.x.buf(), images, u8 ? (s.x.numel() + 3) / 4 : s.x.numel()));
         check(tp_buf_upload(c, s.y.buf(), labels, batch));
     }
     if (fs) {
-        // the whole loop body (src/train.rs:106-138) as one persistent kernel walking the compiled tape
-        check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, -1, optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(),
-                          p.next_result_seq()));
+        // the whole loop body (src/train.rs:106-138) as one persistent kernel walking the compiled tape (or, wide models, as
+        // a plan of tcgen05 kernels)
+        p.before_fused(*this, fs);
+        if (u8)
+            check(tp_step_run_u8(c, fs, xin, yin, nullptr, nullptr, 0, -1, optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(),
+                                 p.next_result_seq()));
+        else
+            check(tp_step_run(c, fs, xin, yin, nullptr, nullptr, 0, -1, optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(),
+                              p.next_result_seq()));
         if (pinned) {
             check(tp_event_record(c, s.done[k]));
             s.done_valid[k] = true;
         }
         optimizer->note_device_step();
+        p.after_fused(*this, fs);
         fused_steps_++;
         p.enqueue_result(true);
         return;
@@ -417,6 +475,14 @@ StepResult Trainer::train_batch(const float* images, const float* labels, size_t
 }
 
 void Trainer::load_dataset(const float* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm) {
+    load_dataset_impl(images, labels, n, sample_shape, perm, false);
+}
+
+void Trainer::load_dataset_u8(const uint8_t* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm) {
+    load_dataset_impl(images, labels, n, sample_shape, perm, true);
+}
+
+void Trainer::load_dataset_impl(const void* images, const float* labels, size_t n, const Shape& sample_shape, const uint32_t* perm, bool u8) {
     Impl& p = *p_;
     tp_ctx* c = ctx();
     check(tp_sync(c));
@@ -427,11 +493,13 @@ void Trainer::load_dataset(const float* images, const float* labels, size_t n, c
     }
     tp_buf_release(p.ds_images); tp_buf_release(p.ds_labels); tp_buf_release(p.ds_perm); tp_buf_release(p.ds_cursor);
     size_t cols = shape_numel(sample_shape);
-    check(tp_buf_alloc(c, n * cols, &p.ds_images));
+    const size_t img_words = u8 ? (n * cols + 3) / 4 : n * cols;     // u8 pixels are stored as they are (4 per 32-bit word)
+    check(tp_buf_alloc(c, img_words, &p.ds_images));
     check(tp_buf_alloc(c, n, &p.ds_labels));
     check(tp_buf_alloc(c, n, &p.ds_perm));
     check(tp_buf_alloc(c, 1, &p.ds_cursor));
-    check(tp_buf_upload(c, p.ds_images, images, n * cols));
+    check(tp_buf_upload(c, p.ds_images, images, img_words));
+    p.ds_u8 = u8;
     check(tp_buf_upload(c, p.ds_labels, labels, n));
     std::vector<uint32_t> ident;
     if (!perm) {
@@ -450,12 +518,20 @@ void Trainer::train_batch_resident(size_t batch) {
     Impl& p = *p_;
     if (!p.ds_images) panic("Trainer::train_batch_resident: load_dataset has not been called");
     if (pending() >= kRing) panic("Trainer: %zu steps outstanding; call fetch()", kRing);
-    if (tp_step* fst = use_fused_ ? p.fused_step(*this, batch, p.ds_sample) : nullptr) {
+    tp_step* fst = use_fused_ ? p.fused_step(*this, batch, p.ds_sample) : nullptr;
+    if (p.ds_u8 && !(fst && p.fused_is_wide(fst))) panic("Trainer: a u8 resident dataset is read by the wide step plan only (load f32 pixels for this model)");
+    if (fst) {
         // batch rows are gathered out of the resident dataset inside the step kernel; the cursor advances there too
-        check(tp_step_run(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, (int)p.ds_cursor_host,
-                          optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(), p.next_result_seq()));
+        p.before_fused(*this, fst);
+        if (p.ds_u8)
+            check(tp_step_run_u8(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, (int)p.ds_cursor_host,
+                                 optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(), p.next_result_seq()));
+        else
+            check(tp_step_run(ctx(), fst, p.ds_images, p.ds_labels, p.ds_perm, p.ds_cursor, (int)p.ds_n, (int)p.ds_cursor_host,
+                              optimizer->lr(), optimizer->grad_scale(), p.next_result_slot(), p.next_result_seq()));
         p.ds_cursor_host = (p.ds_cursor_host + batch) % p.ds_n;
         optimizer->note_device_step();
+        p.after_fused(*this, fst);
         fused_steps_++;
         p.enqueue_result(true);
         return;

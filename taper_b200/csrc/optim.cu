@@ -4,6 +4,7 @@
 // kernels are compiled with -fmad=false so no multiply-add is contracted differently from the CPU code.
 #include "common.cuh"
 #include <cmath>
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -186,6 +187,94 @@ int launch_adam(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, s
     return TP_OK;
 }
 
+
+// ---- optimizer step that also refreshes the bf16 hi/lo planes of the parameters (operands of the bf16x3 GEMMs, gemm_bx3.cu):
+// the same arithmetic as adam_dev_vec4_kernel / sgd_kernel, plus 4 bytes per parameter of stores.
+__device__ __forceinline__ void split_store4_opt(uint16_t* hi, uint16_t* lo, const float (&v)[4]) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(v[j]);
+        l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+    }
+    uint2 ph, pl;
+    ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *(uint2*)hi = ph;
+    *(uint2*)lo = pl;
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_dev_split_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                      size_t n4, const float* __restrict__ h, float grad_scale, int decoupled, uint16_t* __restrict__ hi,
+                      uint16_t* __restrict__ lo) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    AdamArgs a{h[H_SS], h[H_B1], h[H_B2], h[H_EPS], decoupled ? 0.0f : h[H_WD], grad_scale, h[H_DECAY],
+               (decoupled && h[H_WD] > 0.0f) ? 1 : 0};
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p[i], gg = __ldg(g + i), mm = m[i], vv = v[i];
+        adam_elem(pp.x, gg.x, mm.x, vv.x, a);
+        adam_elem(pp.y, gg.y, mm.y, vv.y, a);
+        adam_elem(pp.z, gg.z, mm.z, vv.z, a);
+        adam_elem(pp.w, gg.w, mm.w, vv.w, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+        const float o[4] = {pp.x, pp.y, pp.z, pp.w};
+        split_store4_opt(hi + 4 * i, lo + 4 * i, o);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+sgd_split_kernel(float4* __restrict__ p, const float4* __restrict__ g, size_t n4, float lr, float grad_scale,
+                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p[i], gg = __ldg(g + i);
+        if (grad_scale != 1.0f) { gg.x *= grad_scale; gg.y *= grad_scale; gg.z *= grad_scale; gg.w *= grad_scale; }
+        pp.x -= lr * gg.x; pp.y -= lr * gg.y; pp.z -= lr * gg.z; pp.w -= lr * gg.w;      // src/optim.rs:29
+        p[i] = pp;
+        const float o[4] = {pp.x, pp.y, pp.z, pp.w};
+        split_store4_opt(hi + 4 * i, lo + 4 * i, o);
+    }
+}
+
+}  // namespace
+
+namespace tp {
+
+// optimizer kind: 0 SGD, 1 Adam, 2 AdamW.  n is a multiple of 4 (arena length); all pointers 16-byte aligned.
+int optimizer_step_split(tp_ctx* ctx, int kind, float* p, const float* g, float* m, float* v, const float* hyper, float sgd_lr,
+                         float grad_scale, size_t n, uint16_t* hi, uint16_t* lo, bool pdl) {
+    if (!n) return TP_OK;
+    const size_t n4 = n / 4;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_for(ctx, n4, kThreads));
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (kind == 0) {
+        TP_CUDA(cudaLaunchKernelEx(&cfg, sgd_split_kernel, (float4*)p, (const float4*)g, n4, sgd_lr, grad_scale, hi, lo));
+    } else {
+        TP_CUDA(cudaLaunchKernelEx(&cfg, adam_dev_split_kernel, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n4, hyper,
+                                   grad_scale, kind == 2 ? 1 : 0, hi, lo));
+    }
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+}  // namespace tp
+
+namespace {
+
 // f32::powi == compiler-rt __powisf2: square-and-multiply in f32
 float powi_f32(float a, int b) {
     const bool recip = b < 0;
@@ -276,10 +365,12 @@ int tp_adam_step_segments(tp_ctx* ctx, tp_buf* p, const tp_buf* g, tp_buf* m, tp
     TP_NEED(hyper, H_COUNT, "hyper");
     TP_CHECK_ARG(p && g && m && v, "tp_adam_step_segments: NULL arena");
     TP_CHECK_ARG(!(((uintptr_t)p->ptr | (uintptr_t)g->ptr | (uintptr_t)m->ptr | (uintptr_t)v->ptr) & 15), "tp_adam_step_segments: arenas must be 16-byte aligned");
-    for (int s0 = 0; s0 < n_segments; s0 += kMaxSeg) {
+    // `s` is the scan position: skipped slices (mode 0 / empty) do not count against a launch's table, so the next launch
+    // must resume where this one stopped, not kMaxSeg further (a slice would otherwise be stepped twice)
+    for (int s = 0; s < n_segments;) {
         SegTable t{};
         int cnt = 0, max_n4 = 0;
-        for (int s = s0; s < n_segments && cnt < kMaxSeg; ++s) {
+        for (; s < n_segments && cnt < kMaxSeg; ++s) {
             if (modes[s] == 0 || lengths[s] <= 0) continue;
             const int64_t n_pad = (lengths[s] + 3) & ~(int64_t)3;
             TP_CHECK_ARG(offsets[s] >= 0 && offsets[s] % 4 == 0 && (size_t)(offsets[s] + n_pad) <= p->n && (size_t)(offsets[s] + n_pad) <= g->n &&

@@ -180,6 +180,7 @@ int tp_ctx_destroy(tp_ctx* ctx) {
     }
     tp_comm_destroy(ctx);
     tp::gemm_tc_destroy(ctx);
+    tp::gemm_bx3_destroy(ctx);
     ctx->alloc.release_all();
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (float* q : ctx->retired_scratch) cudaFree(q);

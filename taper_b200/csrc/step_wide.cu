@@ -1,0 +1,694 @@
+// Wide device tape: the whole training step of a WIDE MLP (chain of Linear(+ReLU) ending in a classifier of <= 16 classes)
+// as a fixed plan of tensor-core kernels chained with programmatic dependent launch, behind the same tp_step_* ABI as the
+// persistent-kernel device tape (tape_step.cu), which keeps the small models (< 1.5 GFLOP per step).
+//
+// Replaces the loop body of Trainer::train_epoch (src/train.rs:106-138) for models like BASELINE configs[3]
+// (784-1024-1024-10, batch 1024): Linear::forward (src/nn.rs:54-60: transpose, matmul src/ops.rs:200-228, add_broadcast
+// src/tensor.rs:636-704), ReLU (src/ops.rs:312-374), cross_entropy_loss + accuracy (src/loss.rs:136-195, 271-290), the backward
+// closures (dY.W, dY^T.X src/ops.rs:254-291, bias column sums src/tensor.rs:680-691, ReLU mask src/ops.rs:358-370) and the
+// optimizer step (src/optim.rs:21-33, 83-113, 148-168).
+//
+// Plan for L layers (kernels per step = 2L + 3):
+//   input   gather the batch rows out of the resident dataset (or take the host-fed batch; fp32 or u8 pixels / 255,
+//           src/data/mnist.rs:225, 276-309) and write them as bf16 hi/lo planes (the GEMM operand format, gemm_bx3.cu)
+//   fwd l   act_l = relu(in_l . W_l^T + b_l)        bf16x3 tcgen05 GEMM; the epilogue also writes act_l's hi/lo planes
+//   head    logits = act . W_last^T + b (exact fp32), log-softmax, NLL, first-max accuracy, dlogits = (softmax - onehot) / B,
+//           dZ = (dlogits . W_last) * [act > 0] as hi/lo planes, and per-CTA partials of dW_last, db_last, colsum(dZ)
+//   bwd l   dZ_{l-1} = (dZ_l . W_l) * [act_{l-1} > 0]  (N,N; ReLU mask, hi/lo planes and column-sum partials in the epilogue)
+//           dW_l = dZ_l^T . in_l                       (T,N; straight into the gradient arena)
+//   fold    sums the partials in a fixed order into the gradient arena (dW_last, every db), publishes {loss, correct},
+//           advances Adam's t / step size and the dataset cursor
+//   [allreduce of the gradient arena when data-parallel]
+//   opt     SGD / Adam / AdamW over the flat arena; also rewrites the parameters' hi/lo planes for the next step
+// No kernel of the plan reads an fp32 operand through the tensor pipe and nothing is transposed or copied in memory.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <vector>
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kThreads = 256;
+constexpr int kMaxOut = 16;
+constexpr int kHeadRowsMax = 16;     // rows of the batch per head CTA and pass (staged in shared memory)
+enum { H_T = 0, H_LR, H_B1, H_B2, H_EPS, H_WD, H_SS, H_DECAY, H_COUNT };       // same layout as optim.cu
+
+__device__ __forceinline__ float powi_dev(float a, int b) {     // f32::powi, as optim.cu
+    float r = 1.0f;
+    unsigned int e = (unsigned int)b;
+    while (true) {
+        if (e & 1u) r *= a;
+        e >>= 1;
+        if (e == 0) break;
+        a *= a;
+    }
+    return r;
+}
+
+__device__ __forceinline__ unsigned int class_of(float t) {     // `t as usize` (src/loss.rs:160)
+    if (!(t > 0.0f)) return 0u;
+    if (t >= 4294967040.0f) return 0xffffffffu;
+    return (unsigned int)t;
+}
+
+__device__ __forceinline__ void split2(float v, uint16_t& hi, uint16_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+}
+
+__device__ __forceinline__ void split_store4(uint16_t* hi, uint16_t* lo, float a, float b, float c, float d) {
+    uint16_t h[4], l[4];
+    split2(a, h[0], l[0]); split2(b, h[1], l[1]); split2(c, h[2], l[2]); split2(d, h[3], l[3]);
+    *(uint2*)hi = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    *(uint2*)lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+// ---- input: batch rows -> bf16 hi/lo planes (+ labels) --------------------------------------------------------------
+struct InputArgs {
+    const void* x;                   // [rows or n_perm, cols] fp32 or u8
+    const float* labels;
+    const int* perm;                 // NULL: x / labels are the batch itself
+    const int* cursor;
+    int cursor_value;                // >= 0: host mirror of *cursor
+    int n_perm, rows, cols, is_u8;
+    uint16_t* hi;
+    uint16_t* lo;
+    float* y;                        // [rows]
+};
+
+__global__ void __launch_bounds__(kThreads)
+wide_input_kernel(InputArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * kThreads) >> 5;
+    const int start = a.perm ? (a.cursor_value >= 0 ? a.cursor_value : __ldg(a.cursor)) : 0;
+    for (int r = warp; r < a.rows; r += nwarps) {
+        const int src = a.perm ? __ldg(a.perm + (start + r) % a.n_perm) : r;
+        uint16_t* hi = a.hi + (size_t)r * a.cols;
+        uint16_t* lo = a.lo + (size_t)r * a.cols;
+        if (a.is_u8) {
+            // MNIST pixels as stored on disk: f32 = u8 / 255 (src/data/mnist.rs:225); 8 pixels per lane and load, four loads
+            // in flight per lane (a 784-pixel row is one round trip to HBM, not four)
+            const uint2* s = (const uint2*)((const unsigned char*)a.x + (size_t)src * a.cols);
+            const int n8 = a.cols / 8;
+            for (int c0 = 0; c0 < n8; c0 += 128) {
+                uint2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    v[u] = c < n8 ? __ldg(s + c) : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    if (c >= n8) continue;
+                    const uint32_t w[2] = {v[u].x, v[u].y};
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const float f0 = (float)(w[hlf] & 0xffu) / 255.0f, f1 = (float)((w[hlf] >> 8) & 0xffu) / 255.0f;
+                        const float f2 = (float)((w[hlf] >> 16) & 0xffu) / 255.0f, f3 = (float)(w[hlf] >> 24) / 255.0f;
+                        split_store4(hi + 8 * c + 4 * hlf, lo + 8 * c + 4 * hlf, f0, f1, f2, f3);
+                    }
+                }
+            }
+        } else {
+            const float4* s = (const float4*)((const float*)a.x + (size_t)src * a.cols);
+            const int n4 = a.cols / 4;
+            for (int c0 = 0; c0 < n4; c0 += 256) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    v[u] = c < n4 ? __ldg(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    if (c < n4) split_store4(hi + 4 * c, lo + 4 * c, v[u].x, v[u].y, v[u].z, v[u].w);
+                }
+            }
+        }
+        if (lane == 0) a.y[r] = __ldg(a.labels + src);
+    }
+}
+
+// ---- head -----------------------------------------------------------------------------------------------------------------
+struct HeadArgs {
+    const float* act;                // [B, K] fp32 input of the classifier
+    const float* w;                  // [C, K]
+    const float* bias;               // [C] or NULL
+    const float* y;                  // [B] labels
+    int B, K, C, relu_mask;          // relu_mask: dZ *= [act > 0]
+    int rows_per_cta;
+    float inv_b;
+    uint16_t* dz_hi;                 // [B, K] planes of dZ
+    uint16_t* dz_lo;
+    float* dw_part;                  // [grid][C*K]
+    float* db_part;                  // [grid][kMaxOut]
+    float* cs_part;                  // [grid][K]   column sums of dZ
+    float* lh_part;                  // [grid][2]   {sum of NLL, hits}
+    int* err;
+};
+
+// One CTA owns rows_per_cta rows of the batch.  Phase A (a warp per row): logits, log-softmax, loss / accuracy, dlogits.
+// Phase B (a thread per 4 columns): dZ rows, their column sums and this CTA's share of dW_last, with W_last's columns and the
+// accumulators in registers.  Everything a row needs is staged once in shared memory.
+__global__ void __launch_bounds__(kThreads)
+wide_head_kernel(HeadArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* w_s = sm;                                  // [C][K]
+    float* a_s = w_s + a.C * a.K;                     // [kHeadRowsMax][K]
+    float* dl_s = a_s + kHeadRowsMax * a.K;           // [kHeadRowsMax][kMaxOut]
+    float* red_s = dl_s + kHeadRowsMax * kMaxOut;     // [8][2]
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int K4 = a.K / 4;
+    pdl_launch_dependents();
+    // the classifier's parameters were written by the previous step's optimizer kernel, which completed before the kernel
+    // ahead of this one could start: safe to stage before the dependency wait
+    for (int i0 = t; i0 < a.C * K4; i0 += kThreads * 5) {               // five loads in flight per thread
+        float4 v[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) v[u] = i0 + u * kThreads < a.C * K4 ? __ldg((const float4*)a.w + i0 + u * kThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+            if (i0 + u * kThreads < a.C * K4) ((float4*)w_s)[i0 + u * kThreads] = v[u];
+    }
+    pdl_wait();
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r1 = min(a.B, r0 + a.rows_per_cta);
+    // phase-B registers: this thread's 4 columns of W_last and of the dW_last partial
+    float4 wreg[kMaxOut], dwacc[kMaxOut];
+    float4 csacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool colthread = t < K4;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kMaxOut; ++c) {
+        dwacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wreg[c] = (c < a.C && colthread) ? ((const float4*)(w_s + c * a.K))[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float nll_sum = 0.0f, hit_sum = 0.0f;             // lane 0 of each warp
+    float dbacc = 0.0f;                               // thread c < C: db_last[c]
+    for (int rb = r0; rb < r1; rb += kHeadRowsMax) {
+        const int nr = min(kHeadRowsMax, r1 - rb);
+        // ---- phase A ----
+        for (int rr = wid; rr < nr; rr += kThreads / 32) {
+            const int row = rb + rr;
+            const float4* xr = (const float4*)(a.act + (size_t)row * a.K);
+            float logit[kMaxOut];
+#pragma unroll
+            for (int c = 0; c < kMaxOut; ++c) logit[c] = 0.0f;
+            float4 xv[8];                                                      // K <= 1024: the whole row in one round trip
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = u * 32 + lane < K4 ? __ldg(xr + u * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = u * 32 + lane;
+                if (j < K4) {
+                    const float4 x = xv[u];
+                    ((float4*)(a_s + rr * a.K))[j] = x;
+#pragma unroll
+                    for (int c = 0; c < kMaxOut; ++c) {
+                        if (c < a.C) {
+                            const float4 w = ((const float4*)(w_s + c * a.K))[j];
+                            logit[c] = fmaf(x.x, w.x, logit[c]); logit[c] = fmaf(x.y, w.y, logit[c]);
+                            logit[c] = fmaf(x.z, w.z, logit[c]); logit[c] = fmaf(x.w, w.w, logit[c]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kMaxOut; ++c) {
+                if (c < a.C) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) logit[c] += __shfl_xor_sync(0xffffffffu, logit[c], o);
+                    if (a.bias) logit[c] += __ldg(a.bias + c);
+                }
+            }
+            // every lane holds all logits: log-softmax (src/loss.rs:101-126), NLL (:158-164), first-max accuracy (:271-290)
+            float m = -INFINITY;
+            int bi = 0;
+#pragma unroll
+            for (int c = 0; c < kMaxOut; ++c)
+                if (c < a.C && logit[c] > m) { m = logit[c]; bi = c; }
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kMaxOut; ++c)
+                if (c < a.C) s += expf(logit[c] - m);
+            const float ls = logf(s);
+            const float tgt = __ldg(a.y + row);
+            unsigned int cls = class_of(tgt);
+            if (cls >= (unsigned int)a.C) { if (lane == 0) atomicExch(a.err, 1); cls = a.C - 1; }
+            if (lane == 0) {
+                float lp_t = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kMaxOut; ++c)
+                    if (c == (int)cls) lp_t = (logit[c] - m) - ls;
+                nll_sum += -lp_t;
+                if (fabsf((float)bi - tgt) < 1e-6f) hit_sum += 1.0f;             // src/loss.rs:284
+            }
+            // dlogits = (exp(logp) - onehot) * (1 / B)  (src/loss.rs:174-191, upstream gradient 1)
+            if (lane < kMaxOut) {
+                float d = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kMaxOut; ++c)
+                    if (c == lane && c < a.C) d = (expf((logit[c] - m) - ls) - (c == (int)cls ? 1.0f : 0.0f)) * a.inv_b;
+                dl_s[rr * kMaxOut + lane] = d;
+            }
+        }
+        __syncthreads();
+        // ---- phase B ----
+        if (colthread) {
+            for (int rr = 0; rr < nr; ++rr) {
+                const float4 x = ((const float4*)(a_s + rr * a.K))[t];
+                float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < kMaxOut; ++c) {
+                    if (c < a.C) {
+                        const float d = dl_s[rr * kMaxOut + c];
+                        dz.x = fmaf(d, wreg[c].x, dz.x); dz.y = fmaf(d, wreg[c].y, dz.y);
+                        dz.z = fmaf(d, wreg[c].z, dz.z); dz.w = fmaf(d, wreg[c].w, dz.w);
+                        dwacc[c].x = fmaf(d, x.x, dwacc[c].x); dwacc[c].y = fmaf(d, x.y, dwacc[c].y);
+                        dwacc[c].z = fmaf(d, x.z, dwacc[c].z); dwacc[c].w = fmaf(d, x.w, dwacc[c].w);
+                    }
+                }
+                if (a.relu_mask) {                                             // src/ops.rs:358-370
+                    dz.x = x.x > 0.0f ? dz.x : 0.0f; dz.y = x.y > 0.0f ? dz.y : 0.0f;
+                    dz.z = x.z > 0.0f ? dz.z : 0.0f; dz.w = x.w > 0.0f ? dz.w : 0.0f;
+                }
+                csacc.x += dz.x; csacc.y += dz.y; csacc.z += dz.z; csacc.w += dz.w;
+                const size_t g = (size_t)(rb + rr) * a.K + 4 * t;
+                split_store4(a.dz_hi + g, a.dz_lo + g, dz.x, dz.y, dz.z, dz.w);
+            }
+        }
+        if (t < a.C)
+            for (int rr = 0; rr < nr; ++rr) dbacc += dl_s[rr * kMaxOut + t];
+        __syncthreads();
+    }
+    // ---- this CTA's partials ----
+    if (colthread) {
+#pragma unroll
+        for (int c = 0; c < kMaxOut; ++c)
+            if (c < a.C) ((float4*)(a.dw_part + (size_t)blockIdx.x * a.C * a.K + (size_t)c * a.K))[t] = dwacc[c];
+        ((float4*)(a.cs_part + (size_t)blockIdx.x * a.K))[t] = csacc;
+    }
+    if (t < kMaxOut) a.db_part[blockIdx.x * kMaxOut + t] = t < a.C ? dbacc : 0.0f;
+    if (lane == 0) { red_s[2 * wid] = nll_sum; red_s[2 * wid + 1] = hit_sum; }
+    __syncthreads();
+    if (t == 0) {
+        float n = 0.0f, h = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) { n += red_s[2 * w]; h += red_s[2 * w + 1]; }
+        a.lh_part[2 * blockIdx.x] = n;
+        a.lh_part[2 * blockIdx.x + 1] = h;
+    }
+}
+
+// ---- fold: partials -> gradient arena, results, optimizer counters -----------------------------------------------------
+constexpr int kMaxFold = 2 * TP_STEP_MAX_LAYERS + 4;
+constexpr int kFoldWarps = kThreads / 32;
+struct FoldEntry {
+    float* dst;                      // n outputs
+    const float* src;                // partial j of output i at src[j * stride + i]
+    int n, parts;
+    long long stride;
+    int first_block;                 // blocks [first_block, first_block + ceil(n / 32)) serve this entry
+};
+struct FoldArgs {
+    FoldEntry e[kMaxFold];
+    int n_entries;
+    const float* lh_part;            // [lh_parts][2]
+    int lh_parts;
+    int B;
+    float* result;                   // device {loss, correct}
+    float* result_host;              // optional mapped pinned {loss, correct, seq}
+    unsigned int result_seq;
+    float* hyper;                    // Adam state or NULL (SGD)
+    int* cursor;                     // dataset cursor or NULL
+    int cursor_delta, cursor_mod;
+};
+
+// A block folds 32 outputs (one per lane); warp w sums partials w, w + 8, w + 16, ... with eight loads in flight, the eight
+// warp sums are added in warp order.  The association order is fixed, so the result does not depend on timing.
+__global__ void __launch_bounds__(kThreads)
+wide_fold_kernel(const __grid_constant__ FoldArgs a) {
+    __shared__ float red[kFoldWarps][32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int ei = 0;
+#pragma unroll 1
+    for (int i = 1; i < a.n_entries; ++i)
+        if ((int)blockIdx.x >= a.e[i].first_block) ei = i;
+    const FoldEntry& e = a.e[ei];
+    const int i = ((int)blockIdx.x - e.first_block) * 32 + lane;
+    float s = 0.0f;
+    if (i < e.n) {
+        for (int j0 = wid; j0 < e.parts; j0 += kFoldWarps * 8) {
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * kFoldWarps;
+                x[u] = j < e.parts ? __ldg(e.src + (size_t)j * e.stride + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += x[u];
+        }
+    }
+    red[wid][lane] = s;
+    __syncthreads();
+    if (wid == 0 && i < e.n) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < kFoldWarps; ++w) t += red[w][lane];
+        e.dst[i] = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float n = 0.0f, h = 0.0f;
+        for (int j = 0; j < a.lh_parts; ++j) { n += __ldg(a.lh_part + 2 * j); h += __ldg(a.lh_part + 2 * j + 1); }     // rows ascending
+        const float loss = n / (float)a.B;                                       // src/loss.rs:164
+        a.result[0] = loss;
+        a.result[1] = h;
+        if (a.result_host) {
+            a.result_host[0] = loss;
+            a.result_host[1] = h;
+            if (a.result_seq) {
+                __threadfence_system();
+                ((volatile unsigned int*)a.result_host)[2] = a.result_seq;
+            }
+        }
+        if (a.hyper) {                                                           // Adam::step prologue (src/optim.rs:86-90, 157)
+            float* hy = a.hyper;
+            const int tt = __float_as_int(hy[H_T]) + 1;
+            hy[H_T] = __int_as_float(tt);
+            const float bc1 = 1.0f - powi_dev(hy[H_B1], tt);
+            const float bc2 = 1.0f - powi_dev(hy[H_B2], tt);
+            hy[H_SS] = hy[H_LR] * (sqrtf(bc2) / bc1);
+            hy[H_DECAY] = 1.0f - hy[H_LR] * hy[H_WD];
+        }
+        if (a.cursor) *a.cursor = (int)(((long long)*a.cursor + a.cursor_delta) % a.cursor_mod);
+    }
+}
+
+template <typename Kern, typename Arg>
+int launch_pdl(tp_ctx* ctx, Kern kern, dim3 grid, size_t smem, const Arg& arg, bool pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    TP_CUDA(cudaLaunchKernelEx(&cfg, kern, arg));
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+}  // namespace
+
+namespace tp {
+
+struct WidePlan {
+    tp_ctx* ctx = nullptr;
+    tp_step_desc d{};
+    float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *hyper = nullptr, *result = nullptr;
+    unsigned char* block = nullptr;  // one device allocation
+    size_t bytes = 0;
+    long long arena_plane = 0;
+    uint16_t* w_split = nullptr;     // planes of the whole parameter arena
+    uint16_t* x_split = nullptr;     // planes of the input batch
+    float* y = nullptr;
+    std::vector<float*> act;         // fp32 activations of the hidden layers
+    std::vector<uint16_t*> act_split, dz_split;
+    std::vector<float*> cs_part;     // column-sum partials of dz_split[l] (bias gradient of hidden layer l)
+    std::vector<int> cs_parts;
+    float *dw_part = nullptr, *db_part = nullptr, *lh_part = nullptr;
+    int head_grid = 0, head_rows = 0;
+    size_t head_smem = 0;
+    std::vector<Bx3Launch> fwd, dx, dw;   // dx[l] produces dz[l-1] (unused for l = 0)
+    FoldArgs fold{};
+    int fold_grid = 0;
+    bool pdl = true;
+    bool weights_fresh = false;
+};
+
+namespace {
+struct Carver {
+    unsigned char* base = nullptr;
+    size_t off = 0;
+    template <typename T> T* take(size_t count) {
+        off = (off + 1023) & ~(size_t)1023;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+double wide_flops(const tp_step_desc* d) {
+    double f = 0.0;
+    for (int l = 0; l < d->n_layers; ++l) f += 2.0 * d->batch * (double)d->dims[l] * d->dims[l + 1];
+    return 3.0 * f;
+}
+}  // namespace
+
+bool wide_supported(const tp_step_desc* d, const char** why) {
+    auto no = [&](const char* w) { if (why) *why = w; return false; };
+    if (!d) return no("NULL descriptor");
+    const int L = d->n_layers;
+    if (L < 2 || L > TP_STEP_MAX_LAYERS) return no("layer count (the wide plan needs at least one hidden layer)");
+    if (d->batch < 1 || d->batch > 65536) return no("batch size");
+    if (d->optimizer < 0 || d->optimizer > 2) return no("optimizer kind");
+    if (d->dims[L] < 1 || d->dims[L] > kMaxOut) return no("classifier wider than 16");
+    if (d->dims[L - 1] > 1024) return no("classifier input wider than 1024");
+    for (int l = 0; l < L; ++l) {
+        if (d->dims[l] < 8 || d->dims[l] % 8) return no("feature width not a multiple of 8");
+        if (d->w_off[l] % 4 || (d->b_off[l] >= 0 && d->b_off[l] % 4)) return no("parameter slice not 16-byte aligned");
+        if (l + 1 < L && d->w_off[l] % 8) return no("hidden weight slice not 16-byte aligned as bf16");
+    }
+    if (d->arena_len % 4) return no("arena length not a multiple of 4");
+    return true;
+}
+
+// which implementation tp_step_create picks: the plan for wide models, the persistent kernel for small ones
+bool wide_preferred(const tp_step_desc* d) {
+    static const int force = [] { const char* v = getenv("TAPER_STEP_WIDE"); return v && *v ? atoi(v) : -1; }();
+    if (!wide_supported(d, nullptr)) return false;
+    if (force == 0) return false;
+    if (force == 1) return true;
+    return wide_flops(d) > 1.5e9;
+}
+
+static int wide_build(WidePlan* w, Carver& c) {
+    const tp_step_desc& d = w->d;
+    const int L = d.n_layers, B = d.batch;
+    const int C = d.dims[L], KH = d.dims[L - 1];
+    w->arena_plane = (d.arena_len + 7) & ~(long long)7;
+    w->w_split = c.take<uint16_t>(2 * (size_t)w->arena_plane);
+    w->x_split = c.take<uint16_t>(2 * (size_t)B * d.dims[0]);
+    w->y = c.take<float>(B);
+    w->act.assign(L - 1, nullptr); w->act_split.assign(L - 1, nullptr); w->dz_split.assign(L - 1, nullptr);
+    w->cs_part.assign(L - 1, nullptr); w->cs_parts.assign(L - 1, 0);
+    for (int l = 0; l + 1 < L; ++l) {
+        const size_t n = (size_t)B * d.dims[l + 1];
+        w->act[l] = c.take<float>(n);
+        w->act_split[l] = c.take<uint16_t>(2 * n);
+        w->dz_split[l] = c.take<uint16_t>(2 * n);
+    }
+    // head: rows per CTA so that the grid covers the SMs once (at most kHeadRowsMax rows are staged per pass)
+    int rows = (B + w->ctx->sm_count - 1) / w->ctx->sm_count;
+    if (rows < 8) rows = B >= 8 * 32 ? 8 : (rows < 1 ? 1 : rows);
+    w->head_rows = rows;
+    w->head_grid = (B + rows - 1) / rows;
+    w->head_smem = ((size_t)C * KH + (size_t)kHeadRowsMax * KH + kHeadRowsMax * kMaxOut + 16) * sizeof(float);
+    w->dw_part = c.take<float>((size_t)w->head_grid * C * KH);
+    w->db_part = c.take<float>((size_t)w->head_grid * kMaxOut);
+    w->cs_part[L - 2] = c.take<float>((size_t)w->head_grid * KH);
+    w->cs_parts[L - 2] = w->head_grid;
+    w->lh_part = c.take<float>((size_t)w->head_grid * 2);
+    // column-sum partials of the dX GEMMs (sized for the worst tiling: 128-row tiles x 8 K-splits)
+    for (int l = 0; l + 2 < L; ++l) w->cs_part[l] = c.take<float>((size_t)((B + 127) / 128) * 8 * d.dims[l + 1]);
+    if (!c.base) return TP_OK;
+
+    tp_ctx* ctx = w->ctx;
+    w->fwd.assign(L - 1, Bx3Launch{}); w->dx.assign(L - 1, Bx3Launch{}); w->dw.assign(L - 1, Bx3Launch{});
+    for (int l = 0; l + 1 < L; ++l) {
+        const int in = d.dims[l], out = d.dims[l + 1];
+        const uint16_t* in_split = l == 0 ? w->x_split : w->act_split[l - 1];
+        const long long in_plane = (long long)B * in;
+        // act_l = relu(in . W_l^T + b_l)   (N,T)
+        Bx3Epilogue ef;
+        ef.bias = d.b_off[l] >= 0 ? w->P + d.b_off[l] : nullptr;
+        ef.relu = d.relu[l];
+        ef.c_split = w->act_split[l];
+        int rc = bx3_prepare(ctx, 0, 1, B, out, in, 1.0f, in_split, in_plane, w->w_split + d.w_off[l], w->arena_plane, 0.0f, w->act[l], ef,
+                             &w->fwd[l]);
+        if (rc) return rc;
+        // dW_l = dZ_l^T . in   (T,N) straight into the gradient arena
+        Bx3Epilogue ew;
+        rc = bx3_prepare(ctx, 1, 0, out, in, B, 1.0f, w->dz_split[l], (long long)B * out, in_split, in_plane, 0.0f, w->G + d.w_off[l], ew,
+                         &w->dw[l]);
+        if (rc) return rc;
+        if (l > 0) {
+            // dZ_{l-1} = (dZ_l . W_l) * [act_{l-1} > 0]   (N,N); planes + column sums (db_{l-1}) in the epilogue
+            Bx3Epilogue ex;
+            ex.relu_mask = d.relu[l - 1] ? w->act[l - 1] : nullptr;
+            ex.c_split = w->dz_split[l - 1];
+            ex.colsum_part = d.b_off[l - 1] >= 0 ? w->cs_part[l - 1] : nullptr;
+            rc = bx3_prepare(ctx, 0, 0, B, in, out, 1.0f, w->dz_split[l], (long long)B * out, w->w_split + d.w_off[l], w->arena_plane, 0.0f,
+                             nullptr, ex, &w->dx[l]);
+            if (rc) return rc;
+            w->cs_parts[l - 1] = w->dx[l].tiles_m * w->dx[l].splits;
+        }
+    }
+    // fold table
+    FoldArgs& f = w->fold;
+    f = FoldArgs{};
+    int nb = 0;
+    auto add = [&](float* dst, const float* src, int n, int parts, long long stride) {
+        FoldEntry& e = f.e[f.n_entries++];
+        e.dst = dst; e.src = src; e.n = n; e.parts = parts; e.stride = stride; e.first_block = nb;
+        nb += (n + 31) / 32;
+    };
+    add(w->G + d.w_off[L - 1], w->dw_part, C * KH, w->head_grid, (long long)C * KH);
+    if (d.b_off[L - 1] >= 0) add(w->G + d.b_off[L - 1], w->db_part, C, w->head_grid, kMaxOut);
+    for (int l = 0; l + 1 < L; ++l)
+        if (d.b_off[l] >= 0) add(w->G + d.b_off[l], w->cs_part[l], d.dims[l + 1], w->cs_parts[l], d.dims[l + 1]);
+    w->fold_grid = nb;
+    f.lh_part = w->lh_part; f.lh_parts = w->head_grid; f.B = B;
+    f.result = w->result;
+    f.hyper = d.optimizer != 0 ? w->hyper : nullptr;
+    return TP_OK;
+}
+
+int wide_create(tp_ctx* ctx, const tp_step_desc* desc, float* P, float* G, float* M, float* V, float* hyper, float* result,
+                WidePlan** out) {
+    const char* why = nullptr;
+    if (!wide_supported(desc, &why)) {
+        set_error("tp_step_create: unsupported wide step (%s)", why ? why : "?");
+        return TP_ERR_UNSUPPORTED;
+    }
+    cudaSetDevice(ctx->device);
+    WidePlan* w = new WidePlan();
+    w->ctx = ctx; w->d = *desc;
+    w->P = P; w->G = G; w->M = M; w->V = V; w->hyper = hyper; w->result = result;
+    { const char* v = getenv("TAPER_WIDE_PDL"); w->pdl = !(v && v[0] == '0'); }
+    Carver sizing;
+    wide_build(w, sizing);
+    w->bytes = sizing.off + 1024;
+    if (cudaMalloc(&w->block, w->bytes) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("tp_step_create: cudaMalloc(%zu) failed", w->bytes);
+        delete w;
+        return TP_ERR_OOM;
+    }
+    cudaMemsetAsync(w->block, 0, w->bytes, ctx->stream);
+    Carver place;
+    place.base = w->block;
+    int rc = wide_build(w, place);
+    if (!rc) {
+        int optin = 0;
+        if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) != cudaSuccess || (size_t)optin < w->head_smem ||
+            cudaFuncSetAttribute(wide_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("tp_step_create: %zu bytes of shared memory not available for the head kernel", w->head_smem);
+            rc = TP_ERR_CUDA;
+        }
+    }
+    if (rc) {
+        cudaFree(w->block);
+        delete w;
+        return rc;
+    }
+    *out = w;
+    return TP_OK;
+}
+
+void wide_destroy(WidePlan* w) {
+    if (!w) return;
+    cudaSetDevice(w->ctx->device);
+    cudaStreamSynchronize(w->ctx->stream);
+    if (w->block) cudaFree(w->block);
+    delete w;
+}
+
+// the parameters were changed by somebody else (host upload, broadcast, another step): re-split them
+int wide_refresh(WidePlan* w) {
+    w->weights_fresh = false;
+    return TP_OK;
+}
+
+void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid) {
+    const int L = w->d.n_layers;
+    if (n_phases) *n_phases = 2 * L + 3;
+    if (n_jobs) *n_jobs = 3 * (L - 1) + 4;
+    if (grid) *grid = w->ctx->sm_count;
+}
+
+int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const int* perm, int* cursor, int n_perm, int cursor_value,
+             float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq) {
+    tp_ctx* ctx = w->ctx;
+    const tp_step_desc& d = w->d;
+    const int L = d.n_layers, B = d.batch;
+    cudaSetDevice(ctx->device);
+    const bool pdl = w->pdl;
+    int rc = TP_OK;
+    if (!w->weights_fresh) {
+        rc = split_bf16(ctx, w->P, w->w_split, (size_t)d.arena_len, w->arena_plane, false);
+        if (rc) return rc;
+        w->weights_fresh = true;
+    }
+    InputArgs ia{};
+    ia.x = x; ia.labels = labels; ia.perm = perm; ia.cursor = cursor; ia.cursor_value = perm ? cursor_value : -1;
+    ia.n_perm = n_perm; ia.rows = B; ia.cols = d.dims[0]; ia.is_u8 = x_is_u8;
+    ia.hi = w->x_split; ia.lo = w->x_split + (size_t)B * d.dims[0]; ia.y = w->y;
+    rc = launch_pdl(ctx, wide_input_kernel, dim3(grid_for(ctx, (size_t)B * 32, kThreads, 2)), 0, ia, pdl);
+    if (rc) return rc;
+    for (int l = 0; l + 1 < L; ++l) {
+        rc = bx3_launch(ctx, w->fwd[l], pdl);
+        if (rc) return rc;
+    }
+    HeadArgs ha{};
+    ha.act = w->act[L - 2]; ha.w = w->P + d.w_off[L - 1]; ha.bias = d.b_off[L - 1] >= 0 ? w->P + d.b_off[L - 1] : nullptr;
+    ha.y = w->y; ha.B = B; ha.K = d.dims[L - 1]; ha.C = d.dims[L]; ha.relu_mask = d.relu[L - 2];
+    ha.rows_per_cta = w->head_rows; ha.inv_b = 1.0f / (float)B;
+    ha.dz_hi = w->dz_split[L - 2]; ha.dz_lo = w->dz_split[L - 2] + (size_t)B * d.dims[L - 1];
+    ha.dw_part = w->dw_part; ha.db_part = w->db_part; ha.cs_part = w->cs_part[L - 2]; ha.lh_part = w->lh_part;
+    ha.err = ctx->dev_error;
+    rc = launch_pdl(ctx, wide_head_kernel, dim3(w->head_grid), w->head_smem, ha, pdl);
+    if (rc) return rc;
+    for (int l = L - 2; l >= 0; --l) {
+        if (l > 0) {                                   // the chain's critical path first
+            rc = bx3_launch(ctx, w->dx[l], pdl);
+            if (rc) return rc;
+        }
+        rc = bx3_launch(ctx, w->dw[l], pdl);
+        if (rc) return rc;
+    }
+    FoldArgs fa = w->fold;
+    fa.result_host = result_host;
+    fa.result_seq = result_host ? result_seq : 0u;
+    fa.cursor = perm ? cursor : nullptr;
+    fa.cursor_delta = B; fa.cursor_mod = n_perm > 0 ? n_perm : 1;
+    rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold_grid), 0, fa, pdl);
+    if (rc) return rc;
+    if (ctx->world > 1 && ctx->nccl_comm) {
+        // sum of the per-rank mean gradients; the optimizer folds 1 / world (grad_scale)
+        tp_buf view;
+        view.ctx = ctx; view.ptr = w->G; view.n = (size_t)d.arena_len; view.external = true;
+        rc = tp_allreduce_sum(ctx, &view, (size_t)d.arena_len);
+        if (rc) return rc;
+    }
+    return optimizer_step_split(ctx, d.optimizer, w->P, w->G, w->M, w->V, w->hyper, sgd_lr, grad_scale, (size_t)d.arena_len, w->w_split,
+                                w->w_split + w->arena_plane, pdl);
+}
+
+}  // namespace tp

@@ -738,6 +738,18 @@ size_t smem_bytes(int n_jobs, int batch) {
 
 }  // namespace
 
+namespace tp {
+struct WidePlan;
+bool wide_supported(const tp_step_desc* d, const char** why);
+bool wide_preferred(const tp_step_desc* d);
+int wide_create(tp_ctx* ctx, const tp_step_desc* desc, float* P, float* G, float* M, float* V, float* hyper, float* result, WidePlan** out);
+void wide_destroy(WidePlan* w);
+int wide_refresh(WidePlan* w);
+void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid);
+int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const int* perm, int* cursor, int n_perm, int cursor_value,
+             float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq);
+}  // namespace tp
+
 struct tp_xchg {
     tp_ctx* ctx = nullptr;
     int rank = 0, world = 1;
@@ -765,6 +777,7 @@ struct tp_step {
     size_t smem = 0;
     tp_buf *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr, *hyper = nullptr, *result = nullptr;
     long long* prof = nullptr;
+    tp::WidePlan* wide = nullptr;    // non-NULL: this step is the multi-kernel tcgen05 plan (step_wide.cu), not the persistent kernel
 };
 
 namespace {
@@ -982,7 +995,14 @@ extern "C" {
 
 int tp_step_supported(const tp_step_desc* desc) {
     const char* why = nullptr;
-    return desc_ok(desc, &why) ? 1 : 0;
+    return (desc_ok(desc, &why) || tp::wide_supported(desc, &why)) ? 1 : 0;
+}
+
+int tp_step_kind(const tp_step_desc* desc) {
+    const char* why = nullptr;
+    if (tp::wide_preferred(desc)) return 2;
+    if (desc_ok(desc, &why)) return 1;
+    return tp::wide_supported(desc, &why) ? 2 : 0;
 }
 
 int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf* grads, tp_buf* m, tp_buf* v, tp_buf* hyper,
@@ -993,7 +1013,9 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
         TP_CHECK_ARG(desc && (size_t)desc->arena_len == xchg->arena_len, "tp_step_create: the exchange window was sized for another arena");
     }
     const char* why = nullptr;
-    TP_CHECK_ARG(desc_ok(desc, &why), "tp_step_create: unsupported step (%s)", why ? why : "?");
+    const int kind = tp_step_kind(desc);
+    if (kind == 0) desc_ok(desc, &why);
+    TP_CHECK_ARG(kind != 0, "tp_step_create: unsupported step (%s)", why ? why : "?");
     TP_NEED(params, desc->arena_len, "params"); TP_NEED(grads, desc->arena_len, "grads"); TP_NEED(result, 2, "result");
     if (desc->optimizer != 0) {
         TP_NEED(m, desc->arena_len, "m"); TP_NEED(v, desc->arena_len, "v"); TP_NEED(hyper, H_COUNT, "hyper");
@@ -1013,8 +1035,17 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     s->ctx = ctx;
     s->desc = *desc;
     s->p = params; s->g = grads; s->m = m; s->v = v; s->hyper = hyper; s->result = result;
-    s->xchg = xchg;
     for (tp_buf* b : {params, grads, m, v, hyper, result}) if (b) tp_buf_retain(b);
+    if (kind == 2) {
+        // wide model: a plan of tcgen05 kernels (step_wide.cu); a data-parallel run sums the gradient arena with the context's
+        // NCCL communicator between the plan's fold and optimizer kernels (the peer-memory window is not used)
+        int rc = tp::wide_create(ctx, desc, params->ptr, grads->ptr, m ? m->ptr : nullptr, v ? v->ptr : nullptr, hyper ? hyper->ptr : nullptr,
+                                 result->ptr, &s->wide);
+        if (rc != TP_OK) { tp_step_destroy(s); return rc; }
+        *out = s;
+        return TP_OK;
+    }
+    s->xchg = xchg;
     float* G0 = grads->ptr;
     auto fail = [&](int rc) { tp_step_destroy(s); return rc; };
     Carver sizing;
@@ -1081,6 +1112,19 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     TP_CHECK_ARG(ctx && s && s->ctx == ctx, "tp_step_run: NULL or foreign step");
     TP_CHECK_ARG(!ctx->capturing, "tp_step_run: a cooperative launch cannot be captured into a CUDA graph");
     const int in = s->desc.dims[0];
+    if (s->wide) {
+        if (perm_i32) {
+            TP_CHECK_ARG(n_perm > 0 && cursor_value < n_perm, "tp_step_run: empty dataset or cursor outside it");
+            TP_NEED(x, (size_t)n_perm * in, "images"); TP_NEED(labels, n_perm, "labels"); TP_NEED(perm_i32, n_perm, "perm");
+            TP_NEED(cursor_i32, 1, "cursor");
+        } else {
+            TP_NEED(x, (size_t)s->desc.batch * in, "x"); TP_NEED(labels, s->desc.batch, "labels");
+        }
+        TP_CHECK_ARG(!((uintptr_t)x->ptr & 15), "tp_step_run: input rows must be 16-byte aligned");
+        return tp::wide_run(s->wide, x->ptr, 0, labels->ptr, perm_i32 ? (const int*)perm_i32->ptr : nullptr,
+                            perm_i32 ? (int*)cursor_i32->ptr : nullptr, perm_i32 ? n_perm : 0, cursor_value, sgd_lr, grad_scale, result_host,
+                            result_seq);
+    }
     StepParams p = s->params;
     if (perm_i32) {
         TP_CHECK_ARG(n_perm > 0, "tp_step_run: empty dataset");
@@ -1145,6 +1189,31 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
     if (s->xchg) s->xchg->seq += 1;
     ctx->launches++;
     return TP_OK;
+}
+
+int tp_step_run_u8(tp_ctx* ctx, tp_step* s, const tp_buf* x_u8, const tp_buf* labels, const tp_buf* perm_i32, tp_buf* cursor_i32,
+                   int n_perm, int cursor_value, float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq) {
+    TP_CHECK_ARG(ctx && s && s->ctx == ctx, "tp_step_run_u8: NULL or foreign step");
+    if (!s->wide) {
+        tp::set_error("tp_step_run_u8: u8 pixels are read by the wide step plan only");
+        return TP_ERR_UNSUPPORTED;
+    }
+    const int in = s->desc.dims[0];
+    const size_t rows = perm_i32 ? (size_t)n_perm : (size_t)s->desc.batch;
+    TP_CHECK_ARG(!perm_i32 || (n_perm > 0 && cursor_value < n_perm), "tp_step_run_u8: empty dataset or cursor outside it");
+    TP_NEED(x_u8, (rows * in + 3) / 4, "x_u8"); TP_NEED(labels, rows, "labels");
+    if (perm_i32) { TP_NEED(perm_i32, n_perm, "perm"); TP_NEED(cursor_i32, 1, "cursor"); }
+    TP_CHECK_ARG(!((uintptr_t)x_u8->ptr & 15), "tp_step_run_u8: input rows must be 16-byte aligned");
+    return tp::wide_run(s->wide, x_u8->ptr, 1, labels->ptr, perm_i32 ? (const int*)perm_i32->ptr : nullptr,
+                        perm_i32 ? (int*)cursor_i32->ptr : nullptr, perm_i32 ? n_perm : 0, cursor_value, sgd_lr, grad_scale, result_host,
+                        result_seq);
+}
+
+int tp_step_is_wide(const tp_step* s) { return s && s->wide ? 1 : 0; }
+
+int tp_step_refresh(tp_step* s) {
+    TP_CHECK_ARG(s, "tp_step_refresh: NULL step");
+    return s->wide ? tp::wide_refresh(s->wide) : TP_OK;
 }
 
 int tp_xchg_create(tp_ctx* ctx, size_t arena_len, int rank, int world, tp_xchg** out) {
@@ -1212,6 +1281,7 @@ int tp_xchg_destroy(tp_xchg* x) {
 
 int tp_step_set_profile(tp_step* s, int on) {
     TP_CHECK_ARG(s, "tp_step_set_profile: NULL step");
+    if (s->wide) { tp::set_error("tp_step_set_profile: the wide plan is profiled per kernel (ncu)"); return TP_ERR_UNSUPPORTED; }
     cudaSetDevice(s->ctx->device);
     if (on && !s->prof) {
         size_t bytes = (size_t)s->grid * kProfSlots * sizeof(long long);
@@ -1233,6 +1303,7 @@ int tp_step_read_profile(tp_step* s, int64_t* out, size_t cap, int* slots) {
 
 int tp_step_info(const tp_step* s, int* n_phases, int* n_jobs, int* grid) {
     TP_CHECK_ARG(s, "tp_step_info: NULL step");
+    if (s->wide) { tp::wide_info(s->wide, n_phases, n_jobs, grid); return TP_OK; }
     if (n_phases) *n_phases = s->params.n_phases;
     if (n_jobs) *n_jobs = s->params.n_jobs;
     if (grid) *grid = s->grid;
@@ -1245,6 +1316,7 @@ int tp_step_destroy(tp_step* s) {
         cudaSetDevice(s->ctx->device);
         cudaStreamSynchronize(s->ctx->stream);
     }
+    if (s->wide) tp::wide_destroy(s->wide);
     if (s->dev_block) cudaFree(s->dev_block);
     if (s->prof) cudaFree(s->prof);
     for (tp_buf* b : {s->p, s->g, s->m, s->v, s->hyper, s->result}) if (b) tp_buf_release(b);

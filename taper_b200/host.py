@@ -214,6 +214,27 @@ class Trainer:
         check(lib.tp_trainer_load_dataset(self.h, _fp(images), _fp(labels), images.shape[0], _shape(images.shape[1:]),
                                           images.ndim - 1, p))
 
+    def step_async_u8(self, images_u8, labels, pinned=True):
+        """images_u8: C-contiguous uint8 [B, ...] (MNIST's on-disk pixels); labels float32 [B]; both stay alive until fetch()."""
+        assert images_u8.dtype == np.uint8 and images_u8.flags["C_CONTIGUOUS"]
+        check(lib.tp_trainer_step_async_u8(self.h, images_u8.ctypes.data_as(C.c_void_p), _fp(labels), images_u8.shape[0],
+                                           _shape(images_u8.shape[1:]), images_u8.ndim - 1, int(pinned)))
+
+    def load_dataset_u8(self, images_u8, labels, perm=None):
+        images_u8 = np.ascontiguousarray(images_u8, dtype=np.uint8)
+        labels = _f32(labels)
+        p = None
+        if perm is not None:
+            perm = np.ascontiguousarray(perm, dtype=np.uint32)
+            p = perm.ctypes.data_as(C.POINTER(C.c_uint32))
+        check(lib.tp_trainer_load_dataset_u8(self.h, images_u8.ctypes.data_as(C.c_void_p), _fp(labels), images_u8.shape[0],
+                                             _shape(images_u8.shape[1:]), images_u8.ndim - 1, p))
+
+    def fused_kind(self) -> int:
+        k = C.c_int()
+        check(lib.tp_trainer_fused_kind(self.h, C.byref(k)))
+        return k.value
+
     def step_resident(self, batch):
         check(lib.tp_trainer_step_resident(self.h, int(batch)))
 

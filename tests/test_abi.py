@@ -78,8 +78,9 @@ def test_rust_ffi_block_covers_every_declared_symbol():
 
 
 def test_step_supported_draws_the_line_without_a_gpu():
-    """tp_step_supported only inspects the description: chains of Linear(+ReLU) with widths % 4 == 0, <= 16 classes,
-    below 1.5 GFLOP per step (larger steps belong on the tcgen05 GEMM path)."""
+    """tp_step_supported / tp_step_kind only inspect the description: chains of Linear(+ReLU) with <= 16 classes; widths % 4 == 0
+    below 1.5 GFLOP per step run as the persistent kernel (kind 1), wider steps with a hidden layer and widths % 8 == 0 as the
+    plan of tcgen05 kernels (kind 2)."""
     import ctypes as C
     from taper_b200 import capi
 
@@ -101,8 +102,14 @@ def test_step_supported_draws_the_line_without_a_gpu():
     assert ok(desc([784, 128, 10], 64, 0)) == 1               # configs[0]
     assert ok(desc([784, 128, 64, 10], 256)) == 1             # the reference's example MLP
     assert ok(desc([784, 10], 200)) == 1                      # softmax regression
-    assert ok(desc([784, 1024, 1024, 10], 1024)) == 0         # configs[3]: 9.8 GFLOP per step
+    kind = lambda d: capi.lib.tp_step_kind(C.byref(d))
+    assert ok(desc([784, 1024, 1024, 10], 1024)) == 1         # configs[3]: 9.8 GFLOP per step: the wide plan
+    assert kind(desc([784, 1024, 1024, 10], 1024)) == 2
+    assert kind(desc([784, 128, 10], 512)) == 1 and kind(desc([784, 10], 200)) == 1
+    assert kind(desc([784, 1024, 2048, 10], 1024)) == 0       # classifier input wider than 1024: tape + graph path
+    assert kind(desc([780, 1024, 1024, 10], 1024)) == 0       # 780 % 8 != 0: TMA cannot describe the bf16 planes
     assert ok(desc([784, 128, 32], 64)) == 0                  # 32 classes: not a skinny head
     assert ok(desc([30, 10], 64)) == 0                        # width not a multiple of 4
-    assert ok(desc([784, 128, 10], 5000)) == 0                # batch beyond the gather index buffer
+    assert kind(desc([784, 128, 10], 5000)) == 2              # batch beyond the persistent kernel's gather index buffer: the plan
+    assert ok(desc([784, 128, 10], 100000)) == 0
     assert capi.lib.tp_step_supported(None) == 0

@@ -243,12 +243,17 @@ def test_fused_step_falls_back_when_model_does_not_qualify():
     for _ in range(3):
         tr.step(x, y)
     assert tr.fused_steps() == 0 and tr.graph_replays() >= 1
-    m2 = host.Model(host.MLP_784_1024_1024_10, 0)                            # 9.8 GFLOP per step: tcgen05 GEMM path
-    tr2 = host.Trainer(m2, "adam", lr=1e-3)
+    m2 = host.Model(host.MLP_784_1024_1024_10, 0)                            # 9.8 GFLOP per step: not the persistent kernel
+    tr2 = host.Trainer(m2, "adam", lr=1e-3)                                  # but the wide plan of tcgen05 kernels (step_wide.cu)
     x = rng.random((1024, 784)).astype(F32); y = rng.integers(0, 10, 1024).astype(F32)
     for _ in range(3):
         tr2.step(x, y)
-    assert tr2.fused_steps() == 0
+    assert tr2.fused_steps() == 3 and tr2.fused_kind() == 2
+    m3 = host.Model("linear:784:1024,relu,linear:1024:2048,relu,linear:2048:10", 0)      # classifier input wider than 1024: neither
+    tr3 = host.Trainer(m3, "adam", lr=1e-3)
+    for _ in range(3):
+        tr3.step(x, y)
+    assert tr3.fused_steps() == 0
 
 
 def test_fused_step_matches_graph_path_closely():
