@@ -75,5 +75,10 @@ if what in ("time", "both"):
             capi.check(lib.tp_graph_destroy(g))
             ms = C.c_float(); capi.check(lib.tp_event_elapsed_ms(e0, e1, C.byref(ms)))
             us = ms.value / r * 1e3
+            if mode == 3 and os.environ.get("DBG"):
+                t = (C.c_longlong * 16)()
+                ctx.sync(); lib.tpdbg_bx3_times(t)
+                names = ["entry", "setup", "pdl", "1st stage", "last stage", "acc full", "staged", "sync1", "stored", "end"]
+                print("    cycles: " + ", ".join(f"{nm}={t[i]-t[0]}" for i, nm in enumerate(names)))
             print(f"m={m} n={n} k={k} ta={ta} tb={tb} mode={mode}: {us:9.2f} us per call (mode 3 includes the two operand-split launches)  "
                   f"{2.0*m*n*k/us/1e6:9.2f} TFLOP/s", flush=True)

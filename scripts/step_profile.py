@@ -122,6 +122,31 @@ def main():
     print(f"world {world} dims {dims} batch {a.batch} {a.opt} resident={a.resident}: {nph.value} phases, {njobs.value} jobs, grid {grid.value}; "
           f"{us:.2f} us/step (CUDA events, {a.iters} back-to-back launches) = {a.batch / us:.2f} M samples/s")
 
+    if lib.tp_step_is_wide(step) == 1:
+        # the wide plan: one %globaltimer stamp per kernel (taken when its dependency wait is over) for the last two steps
+        check(lib.tp_step_set_profile(step, 1))
+        for _ in range(4):
+            run()
+        L = len(dims) - 1
+        names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head"]
+        for l in range(L - 2, -1, -1):
+            if l > 0:
+                names.append(f"dX{l}")
+            if l == L - 2:
+                names.append("dW_last")
+            names.append(f"dW{l}")
+        names += ["fold", "optimizer"]
+        buf = np.zeros(32, np.int64)
+        slots = C.c_int()
+        check(lib.tp_step_read_profile(step, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(slots)))
+        prev, last = buf[:16].astype(np.float64), buf[16:].astype(np.float64)
+        n = len(names)
+        print(f"per-kernel time in situ (us, %globaltimer at the end of each kernel's dependency wait; step-to-step {(last[0] - prev[0]) / 1e3:.2f} us)")
+        tl = list(prev[:n]) + [last[0]]
+        for i, nm in enumerate(names):
+            print(f"  {nm:10s} {(tl[i + 1] - tl[i]) / 1e3:7.2f}")
+        check(lib.tp_step_destroy(step))
+        return
     check(lib.tp_step_set_profile(step, 1))
     for _ in range(3):
         run()

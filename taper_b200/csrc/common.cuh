@@ -175,6 +175,7 @@ struct Bx3Launch {                   // a prepared launch: tensor maps encoded o
     const float* relu_mask;
     int relu;
     float* colsum_part;
+    unsigned long long* stamp;       // profiling: where the kernel stores %globaltimer after its dependency wait (NULL: off)
 };
 int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const uint16_t* a_split, long long a_plane,
                 const uint16_t* b_split, long long b_plane, float beta, float* c, const Bx3Epilogue& ep, Bx3Launch* out);
@@ -186,7 +187,7 @@ int gemm_bx3(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, cons
 void gemm_bx3_destroy(tp_ctx* ctx);
 // optimizer step over a flat arena that also rewrites the parameters' bf16 hi/lo planes (optim.cu); kind 0 SGD, 1 Adam, 2 AdamW
 int optimizer_step_split(tp_ctx* ctx, int kind, float* p, const float* g, float* m, float* v, const float* hyper, float sgd_lr,
-                         float grad_scale, size_t n, uint16_t* hi, uint16_t* lo, bool pdl);
+                         float grad_scale, size_t n, uint16_t* hi, uint16_t* lo, bool pdl, unsigned long long* stamp = nullptr);
 
 // Linear layers with out_features <= 16 (classifier heads), see linear_skinny.cu
 bool linear_skinny_ok(int batch, int in_f, int out_f);

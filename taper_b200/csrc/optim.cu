@@ -209,9 +209,14 @@ __device__ __forceinline__ void split_store4_opt(uint16_t* hi, uint16_t* lo, con
 __global__ void __launch_bounds__(kThreads)
 adam_dev_split_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                       size_t n4, const float* __restrict__ h, float grad_scale, int decoupled, uint16_t* __restrict__ hi,
-                      uint16_t* __restrict__ lo) {
+                      uint16_t* __restrict__ lo, unsigned long long* stamp) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (stamp && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        *stamp = gt;
+    }
     AdamArgs a{h[H_SS], h[H_B1], h[H_B2], h[H_EPS], decoupled ? 0.0f : h[H_WD], grad_scale, h[H_DECAY],
                (decoupled && h[H_WD] > 0.0f) ? 1 : 0};
     const size_t stride = (size_t)gridDim.x * kThreads;
@@ -229,9 +234,14 @@ adam_dev_split_kernel(float4* __restrict__ p, const float4* __restrict__ g, floa
 
 __global__ void __launch_bounds__(kThreads)
 sgd_split_kernel(float4* __restrict__ p, const float4* __restrict__ g, size_t n4, float lr, float grad_scale,
-                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, unsigned long long* stamp) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (stamp && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        *stamp = gt;
+    }
     const size_t stride = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
         float4 pp = p[i], gg = __ldg(g + i);
@@ -249,7 +259,7 @@ namespace tp {
 
 // optimizer kind: 0 SGD, 1 Adam, 2 AdamW.  n is a multiple of 4 (arena length); all pointers 16-byte aligned.
 int optimizer_step_split(tp_ctx* ctx, int kind, float* p, const float* g, float* m, float* v, const float* hyper, float sgd_lr,
-                         float grad_scale, size_t n, uint16_t* hi, uint16_t* lo, bool pdl) {
+                         float grad_scale, size_t n, uint16_t* hi, uint16_t* lo, bool pdl, unsigned long long* stamp) {
     if (!n) return TP_OK;
     const size_t n4 = n / 4;
     cudaLaunchConfig_t cfg = {};
@@ -262,10 +272,10 @@ int optimizer_step_split(tp_ctx* ctx, int kind, float* p, const float* g, float*
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     if (kind == 0) {
-        TP_CUDA(cudaLaunchKernelEx(&cfg, sgd_split_kernel, (float4*)p, (const float4*)g, n4, sgd_lr, grad_scale, hi, lo));
+        TP_CUDA(cudaLaunchKernelEx(&cfg, sgd_split_kernel, (float4*)p, (const float4*)g, n4, sgd_lr, grad_scale, hi, lo, stamp));
     } else {
         TP_CUDA(cudaLaunchKernelEx(&cfg, adam_dev_split_kernel, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n4, hyper,
-                                   grad_scale, kind == 2 ? 1 : 0, hi, lo));
+                                   grad_scale, kind == 2 ? 1 : 0, hi, lo, stamp));
     }
     TP_LAUNCH_OK(ctx);
     return TP_OK;

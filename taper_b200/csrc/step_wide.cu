@@ -8,15 +8,16 @@
 // closures (dY.W, dY^T.X src/ops.rs:254-291, bias column sums src/tensor.rs:680-691, ReLU mask src/ops.rs:358-370) and the
 // optimizer step (src/optim.rs:21-33, 83-113, 148-168).
 //
-// Plan for L layers (kernels per step = 2L + 3):
+// Plan for L layers (kernels per step = 2L + 4):
 //   input   gather the batch rows out of the resident dataset (or take the host-fed batch; fp32 or u8 pixels / 255,
 //           src/data/mnist.rs:225, 276-309) and write them as bf16 hi/lo planes (the GEMM operand format, gemm_bx3.cu)
 //   fwd l   act_l = relu(in_l . W_l^T + b_l)        bf16x3 tcgen05 GEMM; the epilogue also writes act_l's hi/lo planes
 //   head    logits = act . W_last^T + b (exact fp32), log-softmax, NLL, first-max accuracy, dlogits = (softmax - onehot) / B,
-//           dZ = (dlogits . W_last) * [act > 0] as hi/lo planes, and per-CTA partials of dW_last, db_last, colsum(dZ)
+//           dZ = (dlogits . W_last) * [act > 0] and dlogits as hi/lo planes, per-CTA partials of db_last and colsum(dZ)
+//   dW_last = dlogits^T . act                          (T,N, a 16-row A operand: the classifier's weight gradient)
 //   bwd l   dZ_{l-1} = (dZ_l . W_l) * [act_{l-1} > 0]  (N,N; ReLU mask, hi/lo planes and column-sum partials in the epilogue)
 //           dW_l = dZ_l^T . in_l                       (T,N; straight into the gradient arena)
-//   fold    sums the partials in a fixed order into the gradient arena (dW_last, every db), publishes {loss, correct},
+//   fold    sums the bias-gradient partials in a fixed order into the gradient arena, publishes {loss, correct},
 //           advances Adam's t / step size and the dataset cursor
 //   [allreduce of the gradient arena when data-parallel]
 //   opt     SGD / Adam / AdamW over the flat arena; also rewrites the parameters' hi/lo planes for the next step
@@ -68,6 +69,14 @@ __device__ __forceinline__ void split_store4(uint16_t* hi, uint16_t* lo, float a
     *(uint2*)lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
+__device__ __forceinline__ void stamp_now(unsigned long long* stamp) {
+    if (stamp && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        *stamp = gt;
+    }
+}
+
 // ---- input: batch rows -> bf16 hi/lo planes (+ labels) --------------------------------------------------------------
 struct InputArgs {
     const void* x;                   // [rows or n_perm, cols] fp32 or u8
@@ -79,12 +88,14 @@ struct InputArgs {
     uint16_t* hi;
     uint16_t* lo;
     float* y;                        // [rows]
+    unsigned long long* stamp;
 };
 
 __global__ void __launch_bounds__(kThreads)
 wide_input_kernel(InputArgs a) {
     pdl_launch_dependents();
     pdl_wait();
+    stamp_now(a.stamp);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kThreads) >> 5;
@@ -150,21 +161,24 @@ struct HeadArgs {
     float inv_b;
     uint16_t* dz_hi;                 // [B, K] planes of dZ
     uint16_t* dz_lo;
-    float* dw_part;                  // [grid][C*K]
+    uint16_t* dl_hi;                 // [B, 16] planes of dlogits (zero padded): A operand of the dW_last GEMM
+    uint16_t* dl_lo;
     float* db_part;                  // [grid][kMaxOut]
     float* cs_part;                  // [grid][K]   column sums of dZ
     float* lh_part;                  // [grid][2]   {sum of NLL, hits}
     int* err;
+    unsigned long long* stamp;
 };
 
 // One CTA owns rows_per_cta rows of the batch.  Phase A (a warp per row): logits, log-softmax, loss / accuracy, dlogits.
-// Phase B (a thread per 4 columns): dZ rows, their column sums and this CTA's share of dW_last, with W_last's columns and the
-// accumulators in registers.  Everything a row needs is staged once in shared memory.
+// Phase B (a thread per 4 columns): dZ rows and their column sums, with W_last's columns in registers.  Everything a row
+// needs is staged once in shared memory.  CT = compile-time class count (weights of classes >= C are zero padding).
+template <int CT>
 __global__ void __launch_bounds__(kThreads)
 wide_head_kernel(HeadArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float* w_s = sm;                                  // [C][K]
-    float* a_s = w_s + a.C * a.K;                     // [kHeadRowsMax][K]
+    float* w_s = sm;                                  // [CT][K]
+    float* a_s = w_s + CT * a.K;                      // [kHeadRowsMax][K]
     float* dl_s = a_s + kHeadRowsMax * a.K;           // [kHeadRowsMax][kMaxOut]
     float* red_s = dl_s + kHeadRowsMax * kMaxOut;     // [8][2]
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -172,27 +186,30 @@ wide_head_kernel(HeadArgs a) {
     pdl_launch_dependents();
     // the classifier's parameters were written by the previous step's optimizer kernel, which completed before the kernel
     // ahead of this one could start: safe to stage before the dependency wait
-    for (int i0 = t; i0 < a.C * K4; i0 += kThreads * 5) {               // five loads in flight per thread
+    for (int i0 = t; i0 < CT * K4; i0 += kThreads * 5) {                   // five loads in flight per thread
         float4 v[5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) v[u] = i0 + u * kThreads < a.C * K4 ? __ldg((const float4*)a.w + i0 + u * kThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < 5; ++u) {
+            const int i = i0 + u * kThreads;
+            v[u] = (i < CT * K4 && i < a.C * K4) ? __ldg((const float4*)a.w + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int u = 0; u < 5; ++u)
-            if (i0 + u * kThreads < a.C * K4) ((float4*)w_s)[i0 + u * kThreads] = v[u];
+            if (i0 + u * kThreads < CT * K4) ((float4*)w_s)[i0 + u * kThreads] = v[u];
     }
+    float bias_r[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) bias_r[c] = (a.bias && c < a.C) ? __ldg(a.bias + c) : 0.0f;
     pdl_wait();
+    stamp_now(a.stamp);
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int r1 = min(a.B, r0 + a.rows_per_cta);
-    // phase-B registers: this thread's 4 columns of W_last and of the dW_last partial
-    float4 wreg[kMaxOut], dwacc[kMaxOut];
+    float4 wreg[CT];
     float4 csacc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool colthread = t < K4;
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < kMaxOut; ++c) {
-        dwacc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        wreg[c] = (c < a.C && colthread) ? ((const float4*)(w_s + c * a.K))[t] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int c = 0; c < CT; ++c) wreg[c] = colthread ? ((const float4*)(w_s + c * a.K))[t] : make_float4(0.f, 0.f, 0.f, 0.f);
     float nll_sum = 0.0f, hit_sum = 0.0f;             // lane 0 of each warp
     float dbacc = 0.0f;                               // thread c < C: db_last[c]
     for (int rb = r0; rb < r1; rb += kHeadRowsMax) {
@@ -201,9 +218,10 @@ wide_head_kernel(HeadArgs a) {
         for (int rr = wid; rr < nr; rr += kThreads / 32) {
             const int row = rb + rr;
             const float4* xr = (const float4*)(a.act + (size_t)row * a.K);
-            float logit[kMaxOut];
+            const float tgt = __ldg(a.y + row);
+            float logit[CT];
 #pragma unroll
-            for (int c = 0; c < kMaxOut; ++c) logit[c] = 0.0f;
+            for (int c = 0; c < CT; ++c) logit[c] = 0.0f;
             float4 xv[8];                                                      // K <= 1024: the whole row in one round trip
 #pragma unroll
             for (int u = 0; u < 8; ++u) xv[u] = u * 32 + lane < K4 ? __ldg(xr + u * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -214,41 +232,36 @@ wide_head_kernel(HeadArgs a) {
                     const float4 x = xv[u];
                     ((float4*)(a_s + rr * a.K))[j] = x;
 #pragma unroll
-                    for (int c = 0; c < kMaxOut; ++c) {
-                        if (c < a.C) {
-                            const float4 w = ((const float4*)(w_s + c * a.K))[j];
-                            logit[c] = fmaf(x.x, w.x, logit[c]); logit[c] = fmaf(x.y, w.y, logit[c]);
-                            logit[c] = fmaf(x.z, w.z, logit[c]); logit[c] = fmaf(x.w, w.w, logit[c]);
-                        }
+                    for (int c = 0; c < CT; ++c) {
+                        const float4 w = ((const float4*)(w_s + c * a.K))[j];
+                        logit[c] = fmaf(x.x, w.x, logit[c]); logit[c] = fmaf(x.y, w.y, logit[c]);
+                        logit[c] = fmaf(x.z, w.z, logit[c]); logit[c] = fmaf(x.w, w.w, logit[c]);
                     }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < kMaxOut; ++c) {
-                if (c < a.C) {
+            for (int c = 0; c < CT; ++c) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) logit[c] += __shfl_xor_sync(0xffffffffu, logit[c], o);
-                    if (a.bias) logit[c] += __ldg(a.bias + c);
-                }
+                for (int o = 16; o > 0; o >>= 1) logit[c] += __shfl_xor_sync(0xffffffffu, logit[c], o);
+                logit[c] += bias_r[c];
             }
             // every lane holds all logits: log-softmax (src/loss.rs:101-126), NLL (:158-164), first-max accuracy (:271-290)
             float m = -INFINITY;
             int bi = 0;
 #pragma unroll
-            for (int c = 0; c < kMaxOut; ++c)
+            for (int c = 0; c < CT; ++c)
                 if (c < a.C && logit[c] > m) { m = logit[c]; bi = c; }
             float s = 0.0f;
 #pragma unroll
-            for (int c = 0; c < kMaxOut; ++c)
+            for (int c = 0; c < CT; ++c)
                 if (c < a.C) s += expf(logit[c] - m);
             const float ls = logf(s);
-            const float tgt = __ldg(a.y + row);
             unsigned int cls = class_of(tgt);
             if (cls >= (unsigned int)a.C) { if (lane == 0) atomicExch(a.err, 1); cls = a.C - 1; }
             if (lane == 0) {
                 float lp_t = 0.0f;
 #pragma unroll
-                for (int c = 0; c < kMaxOut; ++c)
+                for (int c = 0; c < CT; ++c)
                     if (c == (int)cls) lp_t = (logit[c] - m) - ls;
                 nll_sum += -lp_t;
                 if (fabsf((float)bi - tgt) < 1e-6f) hit_sum += 1.0f;             // src/loss.rs:284
@@ -257,9 +270,13 @@ wide_head_kernel(HeadArgs a) {
             if (lane < kMaxOut) {
                 float d = 0.0f;
 #pragma unroll
-                for (int c = 0; c < kMaxOut; ++c)
+                for (int c = 0; c < CT; ++c)
                     if (c == lane && c < a.C) d = (expf((logit[c] - m) - ls) - (c == (int)cls ? 1.0f : 0.0f)) * a.inv_b;
                 dl_s[rr * kMaxOut + lane] = d;
+                uint16_t h, l;
+                split2(d, h, l);
+                a.dl_hi[(size_t)row * kMaxOut + lane] = h;
+                a.dl_lo[(size_t)row * kMaxOut + lane] = l;
             }
         }
         __syncthreads();
@@ -267,16 +284,14 @@ wide_head_kernel(HeadArgs a) {
         if (colthread) {
             for (int rr = 0; rr < nr; ++rr) {
                 const float4 x = ((const float4*)(a_s + rr * a.K))[t];
+                const float4 d0 = ((const float4*)(dl_s + rr * kMaxOut))[0], d1 = ((const float4*)(dl_s + rr * kMaxOut))[1];
+                const float4 d2 = ((const float4*)(dl_s + rr * kMaxOut))[2], d3 = ((const float4*)(dl_s + rr * kMaxOut))[3];
+                const float dv[16] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
                 float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < kMaxOut; ++c) {
-                    if (c < a.C) {
-                        const float d = dl_s[rr * kMaxOut + c];
-                        dz.x = fmaf(d, wreg[c].x, dz.x); dz.y = fmaf(d, wreg[c].y, dz.y);
-                        dz.z = fmaf(d, wreg[c].z, dz.z); dz.w = fmaf(d, wreg[c].w, dz.w);
-                        dwacc[c].x = fmaf(d, x.x, dwacc[c].x); dwacc[c].y = fmaf(d, x.y, dwacc[c].y);
-                        dwacc[c].z = fmaf(d, x.z, dwacc[c].z); dwacc[c].w = fmaf(d, x.w, dwacc[c].w);
-                    }
+                for (int c = 0; c < CT; ++c) {
+                    dz.x = fmaf(dv[c], wreg[c].x, dz.x); dz.y = fmaf(dv[c], wreg[c].y, dz.y);
+                    dz.z = fmaf(dv[c], wreg[c].z, dz.z); dz.w = fmaf(dv[c], wreg[c].w, dz.w);
                 }
                 if (a.relu_mask) {                                             // src/ops.rs:358-370
                     dz.x = x.x > 0.0f ? dz.x : 0.0f; dz.y = x.y > 0.0f ? dz.y : 0.0f;
@@ -292,12 +307,7 @@ wide_head_kernel(HeadArgs a) {
         __syncthreads();
     }
     // ---- this CTA's partials ----
-    if (colthread) {
-#pragma unroll
-        for (int c = 0; c < kMaxOut; ++c)
-            if (c < a.C) ((float4*)(a.dw_part + (size_t)blockIdx.x * a.C * a.K + (size_t)c * a.K))[t] = dwacc[c];
-        ((float4*)(a.cs_part + (size_t)blockIdx.x * a.K))[t] = csacc;
-    }
+    if (colthread) ((float4*)(a.cs_part + (size_t)blockIdx.x * a.K))[t] = csacc;
     if (t < kMaxOut) a.db_part[blockIdx.x * kMaxOut + t] = t < a.C ? dbacc : 0.0f;
     if (lane == 0) { red_s[2 * wid] = nll_sum; red_s[2 * wid + 1] = hit_sum; }
     __syncthreads();
@@ -332,6 +342,7 @@ struct FoldArgs {
     float* hyper;                    // Adam state or NULL (SGD)
     int* cursor;                     // dataset cursor or NULL
     int cursor_delta, cursor_mod;
+    unsigned long long* stamp;
 };
 
 // A block folds 32 outputs (one per lane); warp w sums partials w, w + 8, w + 16, ... with eight loads in flight, the eight
@@ -341,6 +352,7 @@ wide_fold_kernel(const __grid_constant__ FoldArgs a) {
     __shared__ float red[kFoldWarps][32];
     pdl_launch_dependents();
     pdl_wait();
+    stamp_now(a.stamp);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int ei = 0;
 #pragma unroll 1
@@ -431,7 +443,9 @@ struct WidePlan {
     std::vector<uint16_t*> act_split, dz_split;
     std::vector<float*> cs_part;     // column-sum partials of dz_split[l] (bias gradient of hidden layer l)
     std::vector<int> cs_parts;
-    float *dw_part = nullptr, *db_part = nullptr, *lh_part = nullptr;
+    uint16_t* dl_split = nullptr;    // planes of dlogits [B, 16]
+    float *db_part = nullptr, *lh_part = nullptr;
+    Bx3Launch dw_last{};             // dW_last = dlogits^T . act   (T,N) on the tensor cores
     int head_grid = 0, head_rows = 0;
     size_t head_smem = 0;
     std::vector<Bx3Launch> fwd, dx, dw;   // dx[l] produces dz[l-1] (unused for l = 0)
@@ -439,6 +453,9 @@ struct WidePlan {
     int fold_grid = 0;
     bool pdl = true;
     bool weights_fresh = false;
+    unsigned long long* stamps = nullptr;    // [2][16] %globaltimer per kernel of the last two steps (tp_step_set_profile)
+    bool profile = false;
+    unsigned int runs = 0;
 };
 
 namespace {
@@ -508,8 +525,8 @@ static int wide_build(WidePlan* w, Carver& c) {
     if (rows < 8) rows = B >= 8 * 32 ? 8 : (rows < 1 ? 1 : rows);
     w->head_rows = rows;
     w->head_grid = (B + rows - 1) / rows;
-    w->head_smem = ((size_t)C * KH + (size_t)kHeadRowsMax * KH + kHeadRowsMax * kMaxOut + 16) * sizeof(float);
-    w->dw_part = c.take<float>((size_t)w->head_grid * C * KH);
+    w->head_smem = ((size_t)(C == 10 ? 10 : kMaxOut) * KH + (size_t)kHeadRowsMax * KH + kHeadRowsMax * kMaxOut + 16) * sizeof(float);
+    w->dl_split = c.take<uint16_t>(2 * (size_t)B * kMaxOut);
     w->db_part = c.take<float>((size_t)w->head_grid * kMaxOut);
     w->cs_part[L - 2] = c.take<float>((size_t)w->head_grid * KH);
     w->cs_parts[L - 2] = w->head_grid;
@@ -549,6 +566,15 @@ static int wide_build(WidePlan* w, Carver& c) {
             w->cs_parts[l - 1] = w->dx[l].tiles_m * w->dx[l].splits;
         }
     }
+    {
+        // dW_last[C, KH] = dlogits^T . act  (T,N): the A operand is declared 16 wide (zero padded planes); rows >= C are
+        // computed and not stored
+        Bx3Epilogue el;
+        int rc = bx3_prepare(ctx, 1, 0, kMaxOut, KH, B, 1.0f, w->dl_split, (long long)B * kMaxOut, w->act_split[L - 2], (long long)B * KH, 0.0f,
+                             w->G + d.w_off[L - 1], el, &w->dw_last);
+        if (rc) return rc;
+        w->dw_last.m = C;
+    }
     // fold table
     FoldArgs& f = w->fold;
     f = FoldArgs{};
@@ -558,7 +584,6 @@ static int wide_build(WidePlan* w, Carver& c) {
         e.dst = dst; e.src = src; e.n = n; e.parts = parts; e.stride = stride; e.first_block = nb;
         nb += (n + 31) / 32;
     };
-    add(w->G + d.w_off[L - 1], w->dw_part, C * KH, w->head_grid, (long long)C * KH);
     if (d.b_off[L - 1] >= 0) add(w->G + d.b_off[L - 1], w->db_part, C, w->head_grid, kMaxOut);
     for (int l = 0; l + 1 < L; ++l)
         if (d.b_off[l] >= 0) add(w->G + d.b_off[l], w->cs_part[l], d.dims[l + 1], w->cs_parts[l], d.dims[l + 1]);
@@ -597,7 +622,8 @@ int wide_create(tp_ctx* ctx, const tp_step_desc* desc, float* P, float* G, float
     if (!rc) {
         int optin = 0;
         if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) != cudaSuccess || (size_t)optin < w->head_smem ||
-            cudaFuncSetAttribute(wide_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
+            cudaFuncSetAttribute(wide_head_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
+            cudaFuncSetAttribute(wide_head_kernel<kMaxOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
             cudaGetLastError();
             set_error("tp_step_create: %zu bytes of shared memory not available for the head kernel", w->head_smem);
             rc = TP_ERR_CUDA;
@@ -612,10 +638,34 @@ int wide_create(tp_ctx* ctx, const tp_step_desc* desc, float* P, float* G, float
     return TP_OK;
 }
 
+int wide_set_profile(WidePlan* w, int on) {
+    cudaSetDevice(w->ctx->device);
+    if (on && !w->stamps) {
+        TP_CUDA(cudaMalloc(&w->stamps, 32 * sizeof(unsigned long long)));
+        TP_CUDA(cudaMemsetAsync(w->stamps, 0, 32 * sizeof(unsigned long long), w->ctx->stream));
+    }
+    w->profile = on != 0;
+    return TP_OK;
+}
+
+// out[0..15] = stamps of the step before last, out[16..31] = of the last one (slots: input, fwd..., head, bwd..., fold, optimizer)
+int wide_read_profile(WidePlan* w, long long* out, size_t cap, int* slots) {
+    if (!w->stamps || cap < 32) { set_error("tp_step_read_profile: profiling is off or the buffer is too small"); return TP_ERR_INVALID; }
+    cudaSetDevice(w->ctx->device);
+    TP_CUDA(cudaStreamSynchronize(w->ctx->stream));
+    unsigned long long h[32];
+    TP_CUDA(cudaMemcpy(h, w->stamps, sizeof h, cudaMemcpyDeviceToHost));
+    const int last = (w->runs + 1) & 1;                // parity of the last run
+    for (int i = 0; i < 16; ++i) { out[i] = (long long)h[(last ^ 1) * 16 + i]; out[16 + i] = (long long)h[last * 16 + i]; }
+    if (slots) *slots = 16;
+    return TP_OK;
+}
+
 void wide_destroy(WidePlan* w) {
     if (!w) return;
     cudaSetDevice(w->ctx->device);
     cudaStreamSynchronize(w->ctx->stream);
+    if (w->stamps) cudaFree(w->stamps);
     if (w->block) cudaFree(w->block);
     delete w;
 }
@@ -628,8 +678,8 @@ int wide_refresh(WidePlan* w) {
 
 void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid) {
     const int L = w->d.n_layers;
-    if (n_phases) *n_phases = 2 * L + 3;
-    if (n_jobs) *n_jobs = 3 * (L - 1) + 4;
+    if (n_phases) *n_phases = 2 * L + 4;
+    if (n_jobs) *n_jobs = 3 * (L - 1) + 5;
     if (grid) *grid = w->ctx->sm_count;
 }
 
@@ -646,34 +696,50 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         if (rc) return rc;
         w->weights_fresh = true;
     }
+    unsigned long long* st = w->profile ? w->stamps + (w->runs & 1) * 16 : nullptr;
+    int slot = 0;
+    auto next_stamp = [&]() { return st ? st + (slot < 15 ? slot++ : 15) : nullptr; };
     InputArgs ia{};
+    ia.stamp = next_stamp();
     ia.x = x; ia.labels = labels; ia.perm = perm; ia.cursor = cursor; ia.cursor_value = perm ? cursor_value : -1;
     ia.n_perm = n_perm; ia.rows = B; ia.cols = d.dims[0]; ia.is_u8 = x_is_u8;
     ia.hi = w->x_split; ia.lo = w->x_split + (size_t)B * d.dims[0]; ia.y = w->y;
     rc = launch_pdl(ctx, wide_input_kernel, dim3(grid_for(ctx, (size_t)B * 32, kThreads, 2)), 0, ia, pdl);
     if (rc) return rc;
     for (int l = 0; l + 1 < L; ++l) {
+        w->fwd[l].stamp = next_stamp();
         rc = bx3_launch(ctx, w->fwd[l], pdl);
         if (rc) return rc;
     }
     HeadArgs ha{};
+    ha.stamp = next_stamp();
     ha.act = w->act[L - 2]; ha.w = w->P + d.w_off[L - 1]; ha.bias = d.b_off[L - 1] >= 0 ? w->P + d.b_off[L - 1] : nullptr;
     ha.y = w->y; ha.B = B; ha.K = d.dims[L - 1]; ha.C = d.dims[L]; ha.relu_mask = d.relu[L - 2];
     ha.rows_per_cta = w->head_rows; ha.inv_b = 1.0f / (float)B;
     ha.dz_hi = w->dz_split[L - 2]; ha.dz_lo = w->dz_split[L - 2] + (size_t)B * d.dims[L - 1];
-    ha.dw_part = w->dw_part; ha.db_part = w->db_part; ha.cs_part = w->cs_part[L - 2]; ha.lh_part = w->lh_part;
+    ha.dl_hi = w->dl_split; ha.dl_lo = w->dl_split + (size_t)B * kMaxOut;
+    ha.db_part = w->db_part; ha.cs_part = w->cs_part[L - 2]; ha.lh_part = w->lh_part;
     ha.err = ctx->dev_error;
-    rc = launch_pdl(ctx, wide_head_kernel, dim3(w->head_grid), w->head_smem, ha, pdl);
+    rc = d.dims[L] == 10 ? launch_pdl(ctx, wide_head_kernel<10>, dim3(w->head_grid), w->head_smem, ha, pdl)
+                         : launch_pdl(ctx, wide_head_kernel<kMaxOut>, dim3(w->head_grid), w->head_smem, ha, pdl);
     if (rc) return rc;
     for (int l = L - 2; l >= 0; --l) {
         if (l > 0) {                                   // the chain's critical path first
+            w->dx[l].stamp = next_stamp();
             rc = bx3_launch(ctx, w->dx[l], pdl);
             if (rc) return rc;
         }
+        if (l == L - 2) {
+            w->dw_last.stamp = next_stamp();
+            rc = bx3_launch(ctx, w->dw_last, pdl);
+            if (rc) return rc;
+        }
+        w->dw[l].stamp = next_stamp();
         rc = bx3_launch(ctx, w->dw[l], pdl);
         if (rc) return rc;
     }
     FoldArgs fa = w->fold;
+    fa.stamp = next_stamp();
     fa.result_host = result_host;
     fa.result_seq = result_host ? result_seq : 0u;
     fa.cursor = perm ? cursor : nullptr;
@@ -687,8 +753,10 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         rc = tp_allreduce_sum(ctx, &view, (size_t)d.arena_len);
         if (rc) return rc;
     }
+    unsigned long long* opt_stamp = next_stamp();
+    w->runs++;
     return optimizer_step_split(ctx, d.optimizer, w->P, w->G, w->M, w->V, w->hyper, sgd_lr, grad_scale, (size_t)d.arena_len, w->w_split,
-                                w->w_split + w->arena_plane, pdl);
+                                w->w_split + w->arena_plane, pdl, opt_stamp);
 }
 
 }  // namespace tp

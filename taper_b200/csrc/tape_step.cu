@@ -746,6 +746,8 @@ int wide_create(tp_ctx* ctx, const tp_step_desc* desc, float* P, float* G, float
 void wide_destroy(WidePlan* w);
 int wide_refresh(WidePlan* w);
 void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid);
+int wide_set_profile(WidePlan* w, int on);
+int wide_read_profile(WidePlan* w, long long* out, size_t cap, int* slots);
 int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const int* perm, int* cursor, int n_perm, int cursor_value,
              float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq);
 }  // namespace tp
@@ -1281,7 +1283,7 @@ int tp_xchg_destroy(tp_xchg* x) {
 
 int tp_step_set_profile(tp_step* s, int on) {
     TP_CHECK_ARG(s, "tp_step_set_profile: NULL step");
-    if (s->wide) { tp::set_error("tp_step_set_profile: the wide plan is profiled per kernel (ncu)"); return TP_ERR_UNSUPPORTED; }
+    if (s->wide) return tp::wide_set_profile(s->wide, on);
     cudaSetDevice(s->ctx->device);
     if (on && !s->prof) {
         size_t bytes = (size_t)s->grid * kProfSlots * sizeof(long long);
@@ -1293,6 +1295,7 @@ int tp_step_set_profile(tp_step* s, int on) {
 }
 
 int tp_step_read_profile(tp_step* s, int64_t* out, size_t cap, int* slots) {
+    if (s && s->wide) return tp::wide_read_profile(s->wide, (long long*)out, cap, slots);
     TP_CHECK_ARG(s && s->prof && out && cap >= (size_t)s->grid * kProfSlots, "tp_step_read_profile: profiling is off or the buffer is too small");
     cudaSetDevice(s->ctx->device);
     TP_CUDA(cudaStreamSynchronize(s->ctx->stream));
