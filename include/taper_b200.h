@@ -198,6 +198,8 @@ int tp_softmax_xent_bwd(tp_ctx*, const tp_buf* logp, const tp_buf* targets, cons
 int tp_accuracy_count(tp_ctx*, const tp_buf* pred, const tp_buf* targets, tp_buf* correct, int rows, int cols);
 /* reads and clears the sticky device error flag (0 = none, 1 = target class out of bounds) */
 int tp_ctx_device_error(tp_ctx* ctx, int* flag);
+/* the same as an asynchronous copy on the context's stream into (pinned) host memory: ordered after the kernels enqueued so far */
+int tp_ctx_device_error_async(tp_ctx* ctx, int* host_flag);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution and pooling, NCHW fp32  (src/tensor.rs:1221-1285, 1391-1660, 1663-1780, 1972-2076)
@@ -264,6 +266,10 @@ int tp_bce_bwd(tp_ctx*, const tp_buf* pred, const tp_buf* target, const tp_buf* 
  * (1/world for data-parallel averaging; 1 otherwise).
  * ------------------------------------------------------------------------------------------- */
 int tp_sgd_step(tp_ctx*, tp_buf* p, const tp_buf* g, float lr, float grad_scale, size_t n);
+/* the same with lr read from lr1[0] on the device, so that a captured (CUDA-graph) step follows SGD::set_lr; tp_buf_set_scalar
+ * stores one float on the context's stream */
+int tp_sgd_step_dev(tp_ctx*, tp_buf* p, const tp_buf* g, const tp_buf* lr1, float grad_scale, size_t n);
+int tp_buf_set_scalar(tp_ctx*, tp_buf* buf, size_t index, float value);
 /* g' = g*grad_scale + wd*p; m = b1*m+(1-b1)*g'; v = b2*v+(1-b2)*g'*g'; p -= step_size*m/(sqrt(v)+eps)
  * step_size = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (tp_adam_step_size). */
 int tp_adam_step(tp_ctx*, tp_buf* p, const tp_buf* g, tp_buf* m, tp_buf* v, float step_size,
@@ -336,6 +342,8 @@ typedef struct tp_step_desc {
     int64_t arena_len;                       /* elements in params / grads / m / v                  */
     int materialize_grads;                   /* 1: leave the folded gradients in the grads arena (for inspection); 0: the
                                                 optimizer phase sums the split-K partials itself                       */
+    int data_parallel;                       /* wide plan: 1 = sum the gradient arena over the context's NCCL communicator
+                                                (tp_comm_init) between the fold and the optimizer kernels             */
 } tp_step_desc;
 /* Data-parallel gradient exchange INSIDE the step kernel, over NVLink peer memory (one process per GPU on one node;
  * no counterpart in the reference, which is single-process).  Every rank owns a window {per-slice flags, gradient slots

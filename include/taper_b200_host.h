@@ -18,6 +18,9 @@ extern "C" {
 
 typedef struct tp_model tp_model;       /* nn::Sequential            src/nn.rs:130-162 */
 typedef struct tp_trainer tp_trainer;   /* train::Trainer            src/train.rs:73-293 */
+typedef struct tp_dataset tp_dataset;   /* data::MNISTDataset        src/data/mnist.rs:21-25 */
+typedef struct tp_loader tp_loader;     /* data::DataLoader          src/data/mnist.rs:326-385 */
+typedef struct tp_scheduler tp_scheduler;   /* optim::LRScheduler    src/optim.rs:184-352 */
 
 /* device of this thread's context (call before anything else on the thread); the context itself */
 int tp_host_set_device(int device);
@@ -31,7 +34,7 @@ int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op
 
 /* Sequential from a comma-separated layer list (the constructors of src/nn.rs, src/activation.rs):
  *   linear:IN:OUT[:nobias] | relu | sigmoid | conv:CIN:COUT:K:STRIDE:PAD | conv_relu:CIN:COUT:K:STRIDE:PAD |
- *   maxpool:K:STRIDE | avgpool:K:STRIDE | gap (AdaptiveAvgPool2d::global) | flatten
+ *   maxpool:K:STRIDE | avgpool:K:STRIDE | gap (AdaptiveAvgPool2d::global) | flatten | dropout:PERCENT
  * Weights are drawn from the reference's init distributions with a seeded generator. */
 int tp_model_create(const char* spec, uint64_t seed, tp_model** out);
 int tp_model_destroy(tp_model* m);
@@ -98,6 +101,42 @@ int tp_trainer_broadcast_params(tp_trainer* t, int root);
 int tp_trainer_peer_handle(tp_trainer* t, void* out64);
 int tp_trainer_peer_connect(tp_trainer* t, const void* handles_world_x_64);
 int tp_trainer_graph_replays(tp_trainer* t, uint64_t* count);
+
+/* ---- the data path and the epoch-level trainer calls (src/data/mnist.rs, src/train.rs:98-261) ------------------------------
+ * tp_dataset_from_arrays : samples [n, cols] as f32 in [0,1] or (is_u8) as the raw u8 pixels, labels f32 [n]
+ * tp_dataset_load_mnist  : the IDX files `dir`/{train,test}_{images,labels} (src/data/mnist.rs:184-273; no download)
+ * tp_loader_create       : DataLoader::new(dataset, batch_size, shuffle) (:335-348); the loader shares the dataset.  Batches are
+ *                          gathered by worker threads into pinned host buffers ahead of the trainer (get_batch, :276-309).
+ * tp_loader_set_sample_shape : shape of one sample as the model wants it (default [cols]; a CNN takes [1,28,28]) */
+int tp_dataset_from_arrays(const void* images, int is_u8, const float* labels, size_t n, size_t cols, tp_dataset** out);
+int tp_dataset_load_mnist(const char* dir, int train, tp_dataset** out);
+int tp_dataset_len(tp_dataset* d, size_t* n);
+int tp_dataset_destroy(tp_dataset* d);
+int tp_loader_create(tp_dataset* d, size_t batch_size, int shuffle, uint64_t seed, tp_loader** out);
+int tp_loader_set_sample_shape(tp_loader* l, const size_t* sample_shape, int ndim);
+int tp_loader_num_batches(tp_loader* l, size_t* count);                                  /* :360-362 */
+int tp_loader_destroy(tp_loader* l);
+/* Trainer::train_epoch (src/train.rs:98-144): loader.reset(), then one step per batch; returns (sum of batch losses /
+ * num_batches, correct / samples).  max_batches > 0 stops the epoch early (benchmarks).  Raw u8 pixels cross PCIe when the
+ * dataset has them and the model's step is the wide plan; otherwise f32, as the reference's loader produces. */
+int tp_trainer_train_epoch(tp_trainer* t, tp_loader* l, size_t max_batches, float* loss, float* acc);
+int tp_trainer_evaluate(tp_trainer* t, tp_loader* l, float* loss, float* acc);          /* src/train.rs:147-172 */
+/* LR schedulers (src/optim.rs:190-352): kind "step" (p1 = gamma, n = step_size) | "exponential" (p1 = gamma) |
+ * "cosine" (p1 = min_lr, n = t_max) | "plateau" (p1 = factor, p2 = min_lr, n = patience, mode "min" | "max") */
+int tp_scheduler_create(const char* kind, float base_lr, float p1, float p2, size_t n, const char* mode, tp_scheduler** out);
+int tp_scheduler_step(tp_scheduler* s, int has_metric, float metric);
+int tp_scheduler_get_lr(tp_scheduler* s, float* lr);
+int tp_scheduler_destroy(tp_scheduler* s);
+int tp_trainer_set_scheduler(tp_trainer* t, tp_scheduler* s);                            /* Trainer::new(.., scheduler) :83-95 */
+/* Trainer::fit (src/train.rs:175-261): per epoch train_epoch, evaluate, scheduler.step(val_loss) + optimizer.set_lr, metrics;
+ * stops early above 99 % validation accuracy (:246-249) */
+int tp_trainer_fit(tp_trainer* t, tp_loader* train_loader, tp_loader* val_loader, size_t epochs, int verbose);
+/* Metrics (src/train.rs:10-71): which = 0 train_loss, 1 train_acc, 2 val_loss, 3 val_acc, 4 epoch_times */
+int tp_trainer_metrics(tp_trainer* t, int which, float* out, size_t cap, size_t* count);
+int tp_trainer_get_lr(tp_trainer* t, float* lr);
+/* sticky device-side error word of the trainer's context (0 = none): 1 label outside [0, classes), 2 grid barrier timeout,
+ * 3 peer exchange timeout.  fetch / train_epoch raise on a non-zero word; this reads it without raising. */
+int tp_trainer_device_error(tp_trainer* t, int* code);
 
 #ifdef __cplusplus
 }

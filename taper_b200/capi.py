@@ -38,10 +38,12 @@ class StepDesc(C.Structure):
     """tp_step_desc (include/taper_b200.h): a chain of Linear(+ReLU) layers + classifier head + optimizer."""
     MAX_LAYERS = 8
     _fields_ = [("n_layers", C.c_int), ("dims", C.c_int * 9), ("relu", C.c_int * 8), ("batch", C.c_int), ("optimizer", C.c_int),
-                ("w_off", C.c_int64 * 8), ("b_off", C.c_int64 * 8), ("arena_len", C.c_int64), ("materialize_grads", C.c_int)]
+                ("w_off", C.c_int64 * 8), ("b_off", C.c_int64 * 8), ("arena_len", C.c_int64), ("materialize_grads", C.c_int),
+                ("data_parallel", C.c_int)]
 
 
-_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step", "tp_xchg")
+_OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step", "tp_xchg", "tp_dataset", "tp_loader",
+           "tp_scheduler")
 _BASE = {
     "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32,
     "int64_t": C.c_int64, "char": C.c_char, "void": None,

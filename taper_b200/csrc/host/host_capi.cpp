@@ -17,6 +17,18 @@ struct tp_trainer {
     std::shared_ptr<train::Trainer> tr;
 };
 
+struct tp_dataset {
+    std::shared_ptr<data::MNISTDataset> ds;
+};
+
+struct tp_loader {
+    std::unique_ptr<data::DataLoader> ld;
+};
+
+struct tp_scheduler {
+    std::shared_ptr<optim::LRScheduler> sc;
+};
+
 namespace {
 
 template <class F>
@@ -100,6 +112,8 @@ int tp_model_create(const char* spec, uint64_t seed, tp_model** out) {
                 layers.push_back(std::make_shared<nn::AdaptiveAvgPool2d>(nn::AdaptiveAvgPool2d::global()));
             } else if (k == "flatten") {
                 layers.push_back(std::make_shared<nn::Flatten>(1));
+            } else if (k == "dropout") {                      // dropout:PERCENT (src/nn.rs:775-827)
+                layers.push_back(std::make_shared<nn::Dropout>((float)num(f, 1, item) / 100.0f, s++));
             } else {
                 panic("tp_model_create: unknown layer '%s'", item.c_str());
             }
@@ -355,6 +369,146 @@ int tp_trainer_fused_steps(tp_trainer* t, uint64_t* count) {
 
 int tp_trainer_graph_replays(tp_trainer* t, uint64_t* count) {
     return guarded([&] { TRAINER(t); if (count) *count = t->tr->graph_replays(); });
+}
+
+// ---- data path, epoch-level trainer calls, schedulers ----------------------------------------------------------------------
+int tp_dataset_from_arrays(const void* images, int is_u8, const float* labels, size_t n, size_t cols, tp_dataset** out) {
+    return guarded([&] {
+        if (!out) panic("tp_dataset_from_arrays: NULL out pointer");
+        auto* d = new tp_dataset();
+        d->ds = std::make_shared<data::MNISTDataset>(data::MNISTDataset::from_arrays(images, is_u8 != 0, labels, n, cols));
+        *out = d;
+    });
+}
+
+int tp_dataset_load_mnist(const char* dir, int train, tp_dataset** out) {
+    return guarded([&] {
+        if (!dir || !out) panic("tp_dataset_load_mnist: NULL argument");
+        auto* d = new tp_dataset();
+        d->ds = std::make_shared<data::MNISTDataset>(train != 0, std::string(dir));
+        *out = d;
+    });
+}
+
+int tp_dataset_len(tp_dataset* d, size_t* n) {
+    return guarded([&] { if (!d || !n) panic("tp_dataset_len: NULL argument"); *n = d->ds->len(); });
+}
+
+int tp_dataset_destroy(tp_dataset* d) {
+    return guarded([&] { delete d; });
+}
+
+int tp_loader_create(tp_dataset* d, size_t batch_size, int shuffle, uint64_t seed, tp_loader** out) {
+    return guarded([&] {
+        if (!d || !out) panic("tp_loader_create: NULL argument");
+        auto* l = new tp_loader();
+        l->ld.reset(new data::DataLoader(d->ds, batch_size, shuffle != 0, seed));
+        *out = l;
+    });
+}
+
+int tp_loader_set_sample_shape(tp_loader* l, const size_t* sample_shape, int ndim) {
+    return guarded([&] {
+        if (!l || !sample_shape || ndim < 1) panic("tp_loader_set_sample_shape: bad arguments");
+        Shape s = to_shape(sample_shape, ndim);
+        if (shape_numel(s) != l->ld->dataset().cols) panic("tp_loader_set_sample_shape: %zu elements per sample, the dataset has %zu", shape_numel(s), l->ld->dataset().cols);
+        l->ld->sample_shape = s;
+    });
+}
+
+int tp_loader_num_batches(tp_loader* l, size_t* count) {
+    return guarded([&] { if (!l || !count) panic("tp_loader_num_batches: NULL argument"); *count = l->ld->num_batches(); });
+}
+
+int tp_loader_destroy(tp_loader* l) {
+    return guarded([&] { delete l; });
+}
+
+int tp_trainer_train_epoch(tp_trainer* t, tp_loader* l, size_t max_batches, float* loss, float* acc) {
+    return guarded([&] {
+        TRAINER(t);
+        if (!l) panic("tp_trainer_train_epoch: NULL loader");
+        auto r = t->tr->train_epoch(*l->ld, max_batches);
+        if (loss) *loss = r.first;
+        if (acc) *acc = r.second;
+    });
+}
+
+int tp_trainer_evaluate(tp_trainer* t, tp_loader* l, float* loss, float* acc) {
+    return guarded([&] {
+        TRAINER(t);
+        if (!l) panic("tp_trainer_evaluate: NULL loader");
+        auto r = t->tr->evaluate(*l->ld);
+        if (loss) *loss = r.first;
+        if (acc) *acc = r.second;
+    });
+}
+
+int tp_scheduler_create(const char* kind, float base_lr, float p1, float p2, size_t n, const char* mode, tp_scheduler** out) {
+    return guarded([&] {
+        if (!kind || !out) panic("tp_scheduler_create: NULL argument");
+        std::string k = kind;
+        auto* s = new tp_scheduler();
+        if (k == "step") s->sc = std::make_shared<optim::StepLR>(base_lr, n, p1);
+        else if (k == "exponential") s->sc = std::make_shared<optim::ExponentialLR>(base_lr, p1);
+        else if (k == "cosine") s->sc = std::make_shared<optim::CosineAnnealingLR>(base_lr, n, p1);
+        else if (k == "plateau")
+            s->sc = std::make_shared<optim::ReduceLROnPlateau>(base_lr, p1, n, p2, mode ? std::optional<std::string>(mode) : std::nullopt);
+        else { delete s; panic("tp_scheduler_create: unknown scheduler '%s'", kind); }
+        *out = s;
+    });
+}
+
+int tp_scheduler_step(tp_scheduler* s, int has_metric, float metric) {
+    return guarded([&] {
+        if (!s) panic("tp_scheduler_step: NULL scheduler");
+        s->sc->step(has_metric ? std::optional<float>(metric) : std::nullopt);
+    });
+}
+
+int tp_scheduler_get_lr(tp_scheduler* s, float* lr) {
+    return guarded([&] { if (!s || !lr) panic("tp_scheduler_get_lr: NULL argument"); *lr = s->sc->get_lr(); });
+}
+
+int tp_scheduler_destroy(tp_scheduler* s) {
+    return guarded([&] { delete s; });
+}
+
+int tp_trainer_set_scheduler(tp_trainer* t, tp_scheduler* s) {
+    return guarded([&] { TRAINER(t); t->tr->scheduler = s ? s->sc : nullptr; });
+}
+
+int tp_trainer_fit(tp_trainer* t, tp_loader* train_loader, tp_loader* val_loader, size_t epochs, int verbose) {
+    return guarded([&] {
+        TRAINER(t);
+        if (!train_loader || !val_loader) panic("tp_trainer_fit: NULL loader");
+        t->tr->fit(*train_loader->ld, *val_loader->ld, epochs, verbose != 0);
+    });
+}
+
+int tp_trainer_metrics(tp_trainer* t, int which, float* out, size_t cap, size_t* count) {
+    return guarded([&] {
+        TRAINER(t);
+        const train::Metrics& m = t->tr->metrics;
+        const std::vector<float>* v = which == 0 ? &m.train_loss : which == 1 ? &m.train_acc : which == 2 ? &m.val_loss
+                                    : which == 3 ? &m.val_acc : which == 4 ? &m.epoch_times : nullptr;
+        if (!v) panic("tp_trainer_metrics: which must be 0..4");
+        if (count) *count = v->size();
+        if (out) for (size_t i = 0; i < v->size() && i < cap; ++i) out[i] = (*v)[i];
+    });
+}
+
+int tp_trainer_get_lr(tp_trainer* t, float* lr) {
+    return guarded([&] { TRAINER(t); if (lr) *lr = t->tr->optimizer->lr(); });
+}
+
+int tp_trainer_device_error(tp_trainer* t, int* code) {
+    return guarded([&] {
+        TRAINER(t);
+        int c = 0;
+        check(tp_ctx_device_error(ctx(), &c));
+        if (code) *code = c;
+    });
 }
 
 }  // extern "C"

@@ -403,16 +403,25 @@ bool describe_fused_step(const nn::Module& model, const Optimizer& opt, size_t b
 
 // ---- SGD  (src/optim.rs:8-40) ----------------------------------------------------------------------
 SGD::SGD(std::vector<Tensor> params, float lr, std::optional<float> /*momentum: ignored, :14-17*/)
-    : params_(params), lr_(lr), arena_(std::make_shared<Arena>(std::move(params), false)) {}
-SGD::~SGD() = default;
+    : params_(params), lr_(lr), arena_(std::make_shared<Arena>(std::move(params), false)) {
+    // the learning rate lives on the device (like Adam's hyper buffer): a captured step follows set_lr
+    check(tp_buf_alloc(ctx(), 4, &lr_dev_));
+    check(tp_buf_set_scalar(ctx(), lr_dev_, 0, lr_));
+}
+SGD::~SGD() { tp_buf_release(lr_dev_); }
+
+void SGD::set_lr(float lr) {
+    lr_ = lr;
+    check(tp_buf_set_scalar(ctx(), lr_dev_, 0, lr));
+}
 
 void SGD::step() {                                                               // :21-33
     Arena& a = *arena_;
     if (a.all_have_grad()) {
-        check(tp_sgd_step(ctx(), a.p, a.g, lr_, grad_scale_, a.total));
+        check(tp_sgd_step_dev(ctx(), a.p, a.g, lr_dev_, grad_scale_, a.total));
     } else {
         for (size_t i = 0; i < a.params.size(); ++i)
-            if (a.params[i].impl()->has_grad) check(tp_sgd_step(ctx(), a.ps[i], a.gs[i], lr_, grad_scale_, a.params[i].numel()));
+            if (a.params[i].impl()->has_grad) check(tp_sgd_step_dev(ctx(), a.ps[i], a.gs[i], lr_dev_, grad_scale_, a.params[i].numel()));
     }
     a.bump_versions();
 }

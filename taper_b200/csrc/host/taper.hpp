@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -133,6 +134,9 @@ struct Module {
     virtual Tensor forward(const Tensor& input) const = 0;          // src/nn.rs:10-12
     virtual std::vector<Tensor> parameters() const { return {}; }
     virtual const char* kind() const { return "module"; }
+    // false: forward() draws fresh host-side state every call (Dropout's mask), so a step containing it must not be
+    // captured into a CUDA graph and replayed
+    virtual bool capturable() const { return true; }
 };
 
 struct Linear : Module {                                             // src/nn.rs:28-78
@@ -164,6 +168,7 @@ struct Dropout : Module {                                            // src/nn.r
     void train() { training = true; }
     Tensor forward(const Tensor& input) const override;
     const char* kind() const override { return "dropout"; }
+    bool capturable() const override { return !training || p == 0.0f || p == 1.0f; }
 };
 
 struct Sequential : Module {                                         // src/nn.rs:130-162
@@ -173,6 +178,10 @@ struct Sequential : Module {                                         // src/nn.r
     Tensor forward(const Tensor& input) const override;
     std::vector<Tensor> parameters() const override;
     const char* kind() const override { return "sequential"; }
+    bool capturable() const override {
+        for (auto& l : layers) if (!l->capturable()) return false;
+        return true;
+    }
 };
 
 struct Conv2d : Module {                                             // src/nn.rs:180-354 (groups == 1)
@@ -287,7 +296,7 @@ public:
     void zero_grad() override;
     void set_grad_scale(float s) override { grad_scale_ = s; }
     std::shared_ptr<Arena> arena() const override { return arena_; }
-    void set_lr(float lr) override { lr_ = lr; }
+    void set_lr(float lr) override;               // also updates the device-side copy a captured step reads
     int kind() const override { return 0; }
     float lr() const override { return lr_; }
     float grad_scale() const override { return grad_scale_; }
@@ -297,6 +306,7 @@ private:
     float lr_;
     float grad_scale_ = 1.0f;
     std::shared_ptr<Arena> arena_;
+    tp_buf* lr_dev_ = nullptr;
 };
 
 class Adam : public Optimizer {                                      // :43-128
@@ -389,34 +399,58 @@ void broadcast(tp_buf* buf, size_t n, int root);
 namespace data {
 
 struct MNISTDataset {                                                // :21-25
-    std::vector<float> images;       // [N, 784] in [0, 1]
+    std::vector<float> images;       // [N, cols] in [0, 1]  (src/data/mnist.rs:225: u8 / 255); may be empty when only the raw
+                                     // pixels are kept (from_arrays with u8 input)
+    std::vector<uint8_t> images_u8;  // [N, cols] the pixels as stored on disk; dropped by normalize()
     std::vector<float> labels;       // [N]
+    size_t cols = 784;
     bool train = true;
     MNISTDataset() = default;
     MNISTDataset(bool train, const std::string& data_dir = "./data/mnist");     // :29-58 (IDX files must exist; no download)
     static MNISTDataset synthetic(size_t n, uint64_t seed);          // MNIST-shaped U[0,1) images, uniform labels
+    // caller-provided samples: f32 [n, cols] or u8 [n, cols] (is_u8), labels f32 [n]
+    static MNISTDataset from_arrays(const void* images, bool is_u8, const float* labels, size_t n, size_t cols);
     size_t len() const { return labels.size(); }                     // :312-314
     void normalize(float mean, float std);                           // :317-322
+    bool has_u8() const { return !images_u8.empty(); }
+    void ensure_f32();                                               // materialise `images` from the raw pixels if needed
 };
 
 class DataLoader {                                                   // :326-385
 public:
     DataLoader(MNISTDataset dataset, size_t batch_size, bool shuffle, uint64_t seed = 0);
+    DataLoader(std::shared_ptr<MNISTDataset> dataset, size_t batch_size, bool shuffle, uint64_t seed = 0);
+    ~DataLoader();
+    DataLoader(const DataLoader&) = delete;
+    DataLoader& operator=(const DataLoader&) = delete;
     void reset();                                                    // :350-358 (reshuffles)
-    size_t num_batches() const { return (dataset_.len() + batch_size_ - 1) / batch_size_; }   // :360-362
+    size_t num_batches() const { return (dataset_->len() + batch_size_ - 1) / batch_size_; }   // :360-362
     // Iterator::next (:369-384): false at the end of the epoch.  The batch is gathered into host vectors
     // (last batch partial, :377).
     bool next(std::vector<float>& images, std::vector<float>& labels, size_t& batch);
-    const MNISTDataset& dataset() const { return dataset_; }
+    const MNISTDataset& dataset() const { return *dataset_; }
     const std::vector<uint32_t>& indices() const { return indices_; }
     size_t batch_size() const { return batch_size_; }
+    // shape of one sample as the model wants it (default {cols}; a CNN takes {1, 28, 28}, examples/train_mnist_cnn.rs:162)
+    Shape sample_shape;
+
+    // The same iteration as a pipeline: worker threads gather the batches of the epoch (get_batch, :276-309, is a rayon
+    // row gather in the reference) into a ring of PINNED host buffers, in order, ahead of the consumer, so the trainer's
+    // H2D copies are asynchronous.  u8: deliver the raw pixels (the device divides by 255) instead of f32.
+    struct Batch { const void* images; const float* labels; size_t batch; int slot; bool u8; };
+    void start_prefetch(bool u8, size_t max_batches = 0);            // after reset(); max_batches 0 = the whole epoch
+    bool next_pinned(Batch& b);                                      // false at the end of the epoch
+    void release(int slot);                                          // the consumer is done with the slot's memory
+    void stop_prefetch();
 private:
-    MNISTDataset dataset_;
+    struct Pipe;
+    std::shared_ptr<MNISTDataset> dataset_;
     size_t batch_size_;
     bool shuffle_;
     std::vector<uint32_t> indices_;
     size_t current_ = 0;
     uint64_t rng_state_;
+    std::unique_ptr<Pipe> pipe_;
 };
 
 }  // namespace data
@@ -459,7 +493,7 @@ public:
     size_t pending() const;
     StepResult eval_batch(const float* images, const float* labels, size_t batch, const Shape& sample_shape);   // :156-166 body
 
-    std::pair<float, float> train_epoch(data::DataLoader& loader);  // :98-144
+    std::pair<float, float> train_epoch(data::DataLoader& loader, size_t max_batches = 0);  // :98-144 (max_batches 0 = all)
     std::pair<float, float> evaluate(data::DataLoader& loader);     // :147-172
     void fit(data::DataLoader& train_loader, data::DataLoader& val_loader, size_t epochs, bool verbose);   // :175-261
 

@@ -4,7 +4,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <thread>
 #include <cstring>
 #include <deque>
 #include <fstream>
@@ -42,13 +44,15 @@ MNISTDataset::MNISTDataset(bool train_, const std::string& dir) : train(train_) 
     auto img = read_file(dir + (train ? "/train_images" : "/test_images"));
     auto lab = read_file(dir + (train ? "/train_labels" : "/test_labels"));
     if (img.size() < 16 || be32(img.data()) != 0x00000803) panic("Invalid magic number for images");
-    size_t n = be32(img.data() + 4), rows = be32(img.data() + 8), cols = be32(img.data() + 12);
-    if (rows != 28 || cols != 28) panic("Unexpected image size: %zux%zu", rows, cols);
+    size_t n = be32(img.data() + 4), rows = be32(img.data() + 8), cols_ = be32(img.data() + 12);
+    if (rows != 28 || cols_ != 28) panic("Unexpected image size: %zux%zu", rows, cols_);
     if (img.size() != 16 + n * 784) panic("Image file size mismatch");
     if (lab.size() < 8 || be32(lab.data()) != 0x00000801) panic("Invalid magic number for labels");
     if (be32(lab.data() + 4) != n || lab.size() != 8 + n) panic("Label file size mismatch");
+    cols = 784;
     images.resize(n * 784);
     for (size_t i = 0; i < n * 784; ++i) images[i] = (float)img[16 + i] / 255.0f;          // :225
+    images_u8.assign(img.begin() + 16, img.end());                                          // the same pixels, undivided
     labels.resize(n);
     for (size_t i = 0; i < n; ++i) labels[i] = (float)lab[8 + i];                           // :268
 }
@@ -63,36 +67,197 @@ MNISTDataset MNISTDataset::synthetic(size_t n, uint64_t seed) {
     return d;
 }
 
-void MNISTDataset::normalize(float mean, float std) {
-    for (auto& p : images) p = (p - mean) / std;
+MNISTDataset MNISTDataset::from_arrays(const void* images_, bool is_u8, const float* labels_, size_t n, size_t cols_) {
+    if (!images_ || !labels_ || !cols_) panic("MNISTDataset::from_arrays: NULL or empty input");
+    MNISTDataset d;
+    d.cols = cols_;
+    if (is_u8) {
+        const uint8_t* p = static_cast<const uint8_t*>(images_);
+        d.images_u8.assign(p, p + n * cols_);
+    } else {
+        const float* p = static_cast<const float*>(images_);
+        d.images.assign(p, p + n * cols_);
+    }
+    d.labels.assign(labels_, labels_ + n);
+    return d;
 }
 
+void MNISTDataset::ensure_f32() {
+    if (!images.empty() || images_u8.empty()) return;
+    images.resize(images_u8.size());
+    for (size_t i = 0; i < images_u8.size(); ++i) images[i] = (float)images_u8[i] / 255.0f;      // :225
+}
+
+void MNISTDataset::normalize(float mean, float std) {
+    ensure_f32();
+    for (auto& p : images) p = (p - mean) / std;
+    images_u8.clear();
+    images_u8.shrink_to_fit();
+}
+
+// ---- pinned prefetch pipeline ---------------------------------------------------------------------------------------------------
+struct DataLoader::Pipe {
+    static constexpr int kSlots = 12;                // > the trainer's result ring (8) + its staging depth
+    struct Slot {
+        void* img = nullptr;
+        float* lab = nullptr;
+        size_t batch = 0;
+        long turn = 0;                               // batch index allowed to fill this slot next
+        long ready = -1;                             // batch index the slot holds
+    };
+    Slot slots[kSlots];
+    size_t img_bytes = 0;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;
+    bool u8 = false;
+    size_t n_batches = 0, next_consume = 0;
+    ~Pipe() {
+        for (auto& s : slots) {
+            if (s.img) tp_host_free_pinned(s.img);
+            if (s.lab) tp_host_free_pinned(s.lab);
+        }
+    }
+};
+
 DataLoader::DataLoader(MNISTDataset dataset, size_t batch_size, bool shuffle, uint64_t seed)
+    : DataLoader(std::make_shared<MNISTDataset>(std::move(dataset)), batch_size, shuffle, seed) {}
+
+DataLoader::DataLoader(std::shared_ptr<MNISTDataset> dataset, size_t batch_size, bool shuffle, uint64_t seed)
     : dataset_(std::move(dataset)), batch_size_(batch_size), shuffle_(shuffle), rng_state_(seed) {
-    indices_.resize(dataset_.len());
+    if (!dataset_ || !batch_size_) panic("DataLoader: NULL dataset or zero batch size");
+    sample_shape = {dataset_->cols};
+    indices_.resize(dataset_->len());
     std::iota(indices_.begin(), indices_.end(), 0u);
     if (shuffle_) reset();
 }
 
+DataLoader::~DataLoader() { stop_prefetch(); }
+
 void DataLoader::reset() {
+    stop_prefetch();
     current_ = 0;
     if (shuffle_)                                                                           // Fisher-Yates (:353-357)
         for (size_t i = indices_.size(); i > 1; --i) std::swap(indices_[i - 1], indices_[splitmix64(rng_state_) % i]);
 }
 
 bool DataLoader::next(std::vector<float>& images, std::vector<float>& labels, size_t& batch) {
-    if (current_ >= dataset_.len()) return false;
-    size_t end = std::min(current_ + batch_size_, dataset_.len());
+    if (current_ >= dataset_->len()) return false;
+    dataset_->ensure_f32();
+    const size_t cols = dataset_->cols;
+    size_t end = std::min(current_ + batch_size_, dataset_->len());
     batch = end - current_;
-    images.resize(batch * 784);
+    images.resize(batch * cols);
     labels.resize(batch);
     for (size_t i = 0; i < batch; ++i) {                                                    // get_batch (:276-309)
         size_t idx = indices_[current_ + i];
-        std::memcpy(&images[i * 784], &dataset_.images[idx * 784], 784 * sizeof(float));
-        labels[i] = dataset_.labels[idx];
+        std::memcpy(&images[i * cols], &dataset_->images[idx * cols], cols * sizeof(float));
+        labels[i] = dataset_->labels[idx];
     }
     current_ = end;
     return true;
+}
+
+void DataLoader::stop_prefetch() {
+    if (!pipe_) return;
+    {
+        std::lock_guard<std::mutex> g(pipe_->mu);
+        pipe_->stop = true;
+    }
+    pipe_->cv.notify_all();
+    for (auto& t : pipe_->workers) t.join();
+    pipe_->workers.clear();
+}
+
+void DataLoader::start_prefetch(bool u8, size_t max_batches) {
+    stop_prefetch();
+    if (u8 && !dataset_->has_u8()) panic("DataLoader: the dataset holds no u8 pixels");
+    if (!u8) dataset_->ensure_f32();
+    if (!pipe_) pipe_.reset(new Pipe());
+    Pipe& p = *pipe_;
+    const size_t cols = dataset_->cols;
+    const size_t need = batch_size_ * cols * (u8 ? 1 : sizeof(float));
+    if (p.img_bytes < need) {
+        for (auto& s : p.slots) {
+            if (s.img) tp_host_free_pinned(s.img);
+            if (s.lab) tp_host_free_pinned(s.lab);
+            s.img = nullptr; s.lab = nullptr;
+            void* q = nullptr;
+            check(tp_host_alloc_pinned((need + 63) & ~(size_t)63, &q));
+            s.img = q;
+            check(tp_host_alloc_pinned(((batch_size_ * sizeof(float)) + 63) & ~(size_t)63, &q));
+            s.lab = static_cast<float*>(q);
+        }
+        p.img_bytes = need;
+    }
+    p.stop = false;
+    p.u8 = u8;
+    size_t nb = num_batches();
+    if (max_batches && max_batches < nb) nb = max_batches;
+    p.n_batches = nb;
+    p.next_consume = 0;
+    for (int i = 0; i < Pipe::kSlots; ++i) { p.slots[i].turn = i; p.slots[i].ready = -1; }
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;
+    if ((size_t)T > nb) T = nb ? (int)nb : 1;
+    const MNISTDataset* ds = dataset_.get();
+    const uint32_t* idx = indices_.data();
+    const size_t n = dataset_->len(), bs = batch_size_;
+    for (int w = 0; w < T; ++w) {
+        p.workers.emplace_back([&p, ds, idx, n, bs, cols, u8, w, T]() {
+            for (size_t b = (size_t)w; b < p.n_batches; b += (size_t)T) {
+                Pipe::Slot& s = p.slots[b % Pipe::kSlots];
+                {
+                    std::unique_lock<std::mutex> lk(p.mu);
+                    p.cv.wait(lk, [&] { return p.stop || s.turn == (long)b; });
+                    if (p.stop) return;
+                }
+                const size_t first = b * bs, count = std::min(bs, n - first);
+                if (u8) {
+                    uint8_t* dst = static_cast<uint8_t*>(s.img);
+                    for (size_t i = 0; i < count; ++i) std::memcpy(dst + i * cols, &ds->images_u8[(size_t)idx[first + i] * cols], cols);
+                } else {
+                    float* dst = static_cast<float*>(s.img);
+                    for (size_t i = 0; i < count; ++i)
+                        std::memcpy(dst + i * cols, &ds->images[(size_t)idx[first + i] * cols], cols * sizeof(float));
+                }
+                for (size_t i = 0; i < count; ++i) s.lab[i] = ds->labels[idx[first + i]];
+                {
+                    std::lock_guard<std::mutex> g(p.mu);
+                    s.batch = count;
+                    s.ready = (long)b;
+                }
+                p.cv.notify_all();
+            }
+        });
+    }
+}
+
+bool DataLoader::next_pinned(Batch& out) {
+    if (!pipe_) panic("DataLoader::next_pinned: start_prefetch first");
+    Pipe& p = *pipe_;
+    const size_t b = p.next_consume;
+    if (b >= p.n_batches) return false;
+    Pipe::Slot& s = p.slots[b % Pipe::kSlots];
+    {
+        std::unique_lock<std::mutex> lk(p.mu);
+        p.cv.wait(lk, [&] { return s.ready == (long)b; });
+    }
+    out.images = s.img; out.labels = s.lab; out.batch = s.batch; out.slot = (int)(b % Pipe::kSlots); out.u8 = p.u8;
+    p.next_consume = b + 1;
+    current_ = std::min(dataset_->len(), (b + 1) * batch_size_);
+    return true;
+}
+
+void DataLoader::release(int slot) {
+    if (!pipe_ || slot < 0 || slot >= Pipe::kSlots) return;
+    Pipe& p = *pipe_;
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        p.slots[slot].turn = p.slots[slot].ready + Pipe::kSlots;
+    }
+    p.cv.notify_all();
 }
 
 }  // namespace data
@@ -176,6 +341,7 @@ struct Trainer::Impl {
             const int kind = tp_step_kind(&d);
             if (kind == 1 && world != 1 && !xchg_connected) return nullptr;      // not cached: the window may still be connected
             d.materialize_grads = 0;
+            d.data_parallel = world > 1 ? 1 : 0;
             // a step that qualifies on paper but cannot be built on this device (no cooperative launch, shared memory) simply
             // stays on the tape + graph path; with an exchange every rank must agree, so there a failure is an error
             int rc = tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), (world > 1 && kind == 1) ? xchg : nullptr, &st);
@@ -225,6 +391,7 @@ struct Trainer::Impl {
         } else {
             slot_seq[i] = 0;
             check(tp_buf_download_async(ctx(), result.buf(), ring + 4 * i, 2));
+            check(tp_ctx_device_error_async(ctx(), reinterpret_cast<int*>(ring + 4 * i + 3)));
             check(tp_event_record(ctx(), events[i]));
         }
         head++;
@@ -268,7 +435,18 @@ Trainer::~Trainer() = default;
 
 void Trainer::init_data_parallel(int rank, int world, const void* uid) {
     dist::init(rank, world, uid);
-    p_->world = world;
+    Impl& p = *p_;
+    // steps captured / compiled for the old world carry its gradient scale (a by-value kernel argument) and no exchange
+    check(tp_sync(ctx()));
+    for (auto& kv : p.slots) {
+        tp_graph_destroy(kv.second.graph); kv.second.graph = nullptr; kv.second.keep.clear();
+        tp_graph_destroy(kv.second.graph_resident); kv.second.graph_resident = nullptr; kv.second.keep_resident.clear();
+        kv.second.eager_runs = 0;
+    }
+    for (auto& kv : p.fused) tp_step_destroy(kv.second);
+    p.fused.clear();
+    p.last_fused = nullptr;
+    p.world = world;
     optimizer->set_grad_scale(1.0f / (float)world);
 }
 
@@ -353,7 +531,16 @@ StepResult Trainer::fetch() {
         check(tp_event_sync(p_->events[i]));
     }
     StepResult r{p_->ring[4 * i], p_->ring[4 * i + 1]};
+    int err;
+    std::memcpy(&err, p_->ring + 4 * i + 3, sizeof err);
     p_->tail++;
+    if (err != 0) {
+        // the reference panics on a label outside the class range (`logp[i * c + t]`, src/loss.rs:160-162); barrier / peer
+        // timeouts mean the step did not complete.  The flag is sticky: the context does not train on.
+        const char* why = err == 1 ? "a label is outside [0, classes)" : err == 2 ? "a grid barrier of the fused step timed out"
+                        : err == 3 ? "a peer never delivered its gradient slice (exchange timeout)" : "unknown device error";
+        panic("Trainer::fetch: device error %d: %s", err, why);
+    }
     return r;
 }
 
@@ -444,9 +631,9 @@ void Trainer::train_batch_async_impl(const void* images_any, const float* labels
     }
     if (s.graph) {
         check(tp_graph_launch(c, s.graph));
-        optimizer->mark_parameters_updated();
+        optimizer->note_device_step();                     // the replay advanced t / the parameters on the device
         graph_replays_++;
-    } else if (use_graph_ && s.eager_runs >= 1) {
+    } else if (use_graph_ && s.eager_runs >= 1 && model->capturable()) {
         // second iteration of this shape: record it.  Every buffer the step allocates comes from a pool the
         // graph owns, and the closures (which own the activations) are kept alive with the graph.
         check(tp_graph_begin(c));
@@ -553,9 +740,9 @@ void Trainer::train_batch_resident(size_t batch) {
     };
     if (s.graph_resident) {
         check(tp_graph_launch(c, s.graph_resident));
-        optimizer->mark_parameters_updated();
+        optimizer->note_device_step();
         graph_replays_++;
-    } else if (use_graph_ && s.eager_runs >= 1) {
+    } else if (use_graph_ && s.eager_runs >= 1 && model->capturable()) {
         check(tp_graph_begin(c));
         try {
             body();
@@ -589,29 +776,40 @@ StepResult Trainer::eval_batch(const float* images, const float* labels, size_t 
     return r;
 }
 
-std::pair<float, float> Trainer::train_epoch(data::DataLoader& loader) {        // src/train.rs:98-144
+std::pair<float, float> Trainer::train_epoch(data::DataLoader& loader, size_t max_batches) {        // src/train.rs:98-144
     float total_loss = 0.0f;
     size_t total_correct = 0, total_samples = 0;
     loader.reset();
     size_t num_batches = loader.num_batches();
-    std::vector<float> images, labels;
-    size_t batch = 0, enq = 0;
-    std::deque<size_t> sizes;
+    if (max_batches && max_batches < num_batches) num_batches = max_batches;
+    const Shape sample = loader.sample_shape;
+    // raw u8 pixels cross PCIe when the dataset still has them and this model's step is the wide plan (which divides by 255
+    // on the device); everything else is fed f32, as the reference's loader produces (src/data/mnist.rs:225)
+    bool u8 = false;
+    if (loader.dataset().has_u8() && use_fused_ && sample.size() == 1) {
+        tp_step* st = p_->fused_step(*this, std::min(loader.batch_size(), loader.dataset().len()), sample);
+        u8 = p_->fused_is_wide(st);
+    }
+    loader.start_prefetch(u8, max_batches);
+    std::deque<std::pair<size_t, int>> inflight;                                // {batch size, pinned slot}
     auto drain_one = [&]() {
         StepResult r = fetch();
         total_correct += (size_t)r.correct;                                      // (acc * batch) as usize, :117
-        total_samples += sizes.front();
-        sizes.pop_front();
+        total_samples += inflight.front().first;
+        loader.release(inflight.front().second);                                 // its H2D copy finished before its step ran
+        inflight.pop_front();
         total_loss += r.loss;                                                    // :127
     };
-    while (loader.next(images, labels, batch)) {
+    data::DataLoader::Batch b;
+    while (loader.next_pinned(b)) {
         if (pending() >= kRing - 1) drain_one();
-        train_batch_async(images.data(), labels.data(), batch, {784}, false);
-        sizes.push_back(batch);
-        ++enq;
+        if (b.u8) train_batch_async_u8(static_cast<const uint8_t*>(b.images), b.labels, b.batch, sample, true);
+        else train_batch_async(static_cast<const float*>(b.images), b.labels, b.batch, sample, true);
+        inflight.emplace_back(b.batch, b.slot);
     }
     while (pending()) drain_one();
-    (void)enq;
+    loader.stop_prefetch();
+    if (!total_samples) return {0.0f, 0.0f};
     return {total_loss / (float)num_batches, (float)total_correct / (float)total_samples};
 }
 
@@ -623,7 +821,7 @@ std::pair<float, float> Trainer::evaluate(data::DataLoader& loader) {           
     std::vector<float> images, labels;
     size_t batch = 0;
     while (loader.next(images, labels, batch)) {
-        StepResult r = eval_batch(images.data(), labels.data(), batch, {784});
+        StepResult r = eval_batch(images.data(), labels.data(), batch, loader.sample_shape);
         total_correct += (size_t)r.correct;
         total_samples += batch;
         total_loss += r.loss;

@@ -59,6 +59,18 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float l
     }
 }
 
+// SGD with the learning rate read from device memory: a captured (CUDA-graph) step follows SGD::set_lr without re-capture
+__global__ void __launch_bounds__(kThreads)
+sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, const float* __restrict__ lr1, float grad_scale) {
+    const float lr = *lr1;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        float gg = g[i];
+        if (grad_scale != 1.0f) gg *= grad_scale;
+        p[i] -= lr * gg;                                        // src/optim.rs:29
+    }
+}
+
 // ---- device-resident optimizer state: lets a captured (CUDA-graph) step advance t and follow set_lr
 // without the host patching kernel arguments.  hyper = {t (int bits), lr, b1, b2, eps, wd, step_size, decay}
 enum { H_T = 0, H_LR, H_B1, H_B2, H_EPS, H_WD, H_SS, H_DECAY, H_COUNT };
@@ -330,6 +342,23 @@ int tp_adam_hyper_init(tp_ctx* ctx, tp_buf* hyper, float lr, float beta1, float 
     TP_NEED(hyper, H_COUNT, "hyper");
     float h[H_COUNT] = {0.0f, lr, beta1, beta2, eps, weight_decay, 0.0f, 1.0f};
     return tp_buf_upload(ctx, hyper, h, H_COUNT);
+}
+
+int tp_sgd_step_dev(tp_ctx* ctx, tp_buf* p, const tp_buf* g, const tp_buf* lr1, float grad_scale, size_t n) {
+    TP_CHECK_ARG(ctx, "tp_sgd_step_dev: NULL ctx");
+    TP_NEED(p, n, "p"); TP_NEED(g, n, "g"); TP_NEED(lr1, 1, "lr");
+    if (!n) return TP_OK;
+    sgd_dev_kernel<<<tp::grid_for(ctx, n, kThreads), kThreads, 0, ctx->stream>>>(p->ptr, g->ptr, n, lr1->ptr, grad_scale);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+int tp_buf_set_scalar(tp_ctx* ctx, tp_buf* buf, size_t index, float value) {
+    TP_CHECK_ARG(ctx, "tp_buf_set_scalar: NULL ctx");
+    TP_NEED(buf, index + 1, "buf");
+    set_scalar_kernel<<<1, 1, 0, ctx->stream>>>(buf->ptr + index, value);
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
 }
 
 int tp_adam_hyper_set_lr(tp_ctx* ctx, tp_buf* hyper, float lr) {

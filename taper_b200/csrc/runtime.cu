@@ -217,6 +217,12 @@ int tp_ctx_launch_count(tp_ctx* ctx, uint64_t* count) {
     return TP_OK;
 }
 
+int tp_ctx_device_error_async(tp_ctx* ctx, int* host_flag) {
+    TP_CHECK_ARG(ctx && host_flag, "tp_ctx_device_error_async: NULL argument");
+    TP_CUDA(cudaMemcpyAsync(host_flag, ctx->dev_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return TP_OK;
+}
+
 int tp_ctx_device_error(tp_ctx* ctx, int* flag) {
     TP_CHECK_ARG(ctx && flag, "tp_ctx_device_error: NULL argument");
     TP_CUDA(cudaMemcpyAsync(flag, ctx->dev_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -302,6 +308,8 @@ size_t tp_buf_len(const tp_buf* buf) { return buf ? buf->n : 0; }
 int tp_buf_upload(tp_ctx* ctx, tp_buf* dst, const void* host, size_t n) {
     TP_CHECK_ARG(ctx && host, "tp_buf_upload: NULL argument");
     TP_NEED(dst, n, "dst");
+    // a captured copy out of the shared staging ring would replay whatever the ring holds at replay time
+    TP_CHECK_ARG(!ctx->capturing, "tp_buf_upload: host data cannot be uploaded while a CUDA graph is being captured");
     const char* src = (const char*)host;
     char* d = (char*)dst->ptr;
     size_t bytes = n * sizeof(float);

@@ -342,6 +342,7 @@ struct FoldArgs {
     float* hyper;                    // Adam state or NULL (SGD)
     int* cursor;                     // dataset cursor or NULL
     int cursor_delta, cursor_mod;
+    const int* err;                  // sticky device error word of the context
     unsigned long long* stamp;
 };
 
@@ -390,6 +391,7 @@ wide_fold_kernel(const __grid_constant__ FoldArgs a) {
         if (a.result_host) {
             a.result_host[0] = loss;
             a.result_host[1] = h;
+            a.result_host[3] = __int_as_float(__ldcg(a.err));                  // 1: a label outside [0, classes) (the reference panics)
             if (a.result_seq) {
                 __threadfence_system();
                 ((volatile unsigned int*)a.result_host)[2] = a.result_seq;
@@ -742,11 +744,12 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
     fa.stamp = next_stamp();
     fa.result_host = result_host;
     fa.result_seq = result_host ? result_seq : 0u;
+    fa.err = ctx->dev_error;
     fa.cursor = perm ? cursor : nullptr;
     fa.cursor_delta = B; fa.cursor_mod = n_perm > 0 ? n_perm : 1;
     rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold_grid), 0, fa, pdl);
     if (rc) return rc;
-    if (ctx->world > 1 && ctx->nccl_comm) {
+    if (d.data_parallel && ctx->world > 1 && ctx->nccl_comm) {
         // sum of the per-rank mean gradients; the optimizer folds 1 / world (grad_scale)
         tp_buf view;
         view.ctx = ctx; view.ptr = w->G; view.n = (size_t)d.arena_len; view.external = true;

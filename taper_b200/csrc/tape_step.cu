@@ -160,18 +160,20 @@ __device__ __forceinline__ void fma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f
 // ---- grid barrier: one monotonically increasing arrival counter.  The host passes the counter value at launch
 // (bar_base); barrier k of this launch completes when the counter reaches bar_base + (k + 1) * gridDim.x (wrap-safe
 // compare).  Arrival is a fire-and-forget release reduction, so a CTA pays one poll round trip, not an atomic's too.
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target, int* err) {
+__device__ __forceinline__ bool grid_sync(unsigned int* bar, unsigned int target, int* err, int* s_ok) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        *s_ok = 1;
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
         unsigned int cur;
         const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
-            if ((int)(cur - target) < 0 && clock64() - t0 > kSpinLimit) { atomicExch(err, 2); break; }
+            if ((int)(cur - target) < 0 && clock64() - t0 > kSpinLimit) { atomicExch(err, 2); *s_ok = 0; break; }
         } while ((int)(cur - target) < 0);
     }
     __syncthreads();
+    return *s_ok != 0;
 }
 
 // ---- GEMM tile loader: one float4 per thread per operand per BK step ------------------------------------------------
@@ -545,6 +547,7 @@ __device__ void loss_item(const Job& j, const StepParams& P, float* sm /* >= 16 
         j.result[1] = sh;
         if (P.result_host) {
             P.result_host[0] = loss; P.result_host[1] = sh;
+            P.result_host[3] = __int_as_float(__ldcg(P.err)); // 1: a label outside [0, classes) in this batch (the reference panics)
             if (P.result_seq) {                               // publish: the host spins on this word instead of a CUDA event
                 __threadfence_system();
                 *reinterpret_cast<volatile unsigned int*>(P.result_host + 2) = P.result_seq;
@@ -596,6 +599,7 @@ __device__ __forceinline__ void opt_item(const Job& j, int item, int phase_item,
             } while ((int)(cur - P.xseq) < 0);
         }
         __syncthreads();
+        if (__ldcg(P.err) >= 2) return;                      // a peer never arrived: its slot is stale, apply nothing
         if (live) {
             float4 q[kMaxWorld];
 #pragma unroll
@@ -675,8 +679,22 @@ tape_step_kernel(const StepParams P) {
         const int q = tid - (kThreads - H_COUNT);
         red[16 + q] = __ldcg(P.hyper + q);
     }
+    if (tid == 0) s_flag[3] = __ldcg(P.err);                  // sticky device error of an earlier step (same round trip)
     __syncthreads();
     TP_PROF(1);
+    // A barrier or peer-exchange timeout (codes 2, 3) leaves gradients incomplete: nothing may be applied from them, in this
+    // step or any later one.  The host sees the code in the result slot (fetch raises) or through tp_ctx_device_error.
+    if (s_flag[3] >= 2) {
+        if (blockIdx.x == 0 && tid == 0 && P.result_host) {
+            P.result_host[0] = 0.0f; P.result_host[1] = 0.0f;
+            P.result_host[3] = __int_as_float(s_flag[3]);
+            if (P.result_seq) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int*>(P.result_host + 2) = P.result_seq;
+            }
+        }
+        return;
+    }
 
     AdamArgs aa{};
     int t_new = 0;
@@ -714,7 +732,8 @@ tape_step_kernel(const StepParams P) {
             }
         }
         TP_PROF(2 + 2 * ph);
-        if (ph + 1 < P.n_phases) grid_sync(P.bar, P.bar_base + (unsigned int)(ph + 1) * gridDim.x, P.err);
+        if (ph + 1 < P.n_phases && !grid_sync(P.bar, P.bar_base + (unsigned int)(ph + 1) * gridDim.x, P.err, s_flag + 2))
+            return;                                          // incomplete barrier: this CTA applies nothing from partial data
         TP_PROF(3 + 2 * ph);
     }
 #undef TP_PROF

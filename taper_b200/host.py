@@ -282,6 +282,45 @@ class Trainer:
         dist.all_gather_object(handles, self.peer_handle())
         self.peer_connect(b"".join(handles))
 
+    def train_epoch(self, loader: Loader, max_batches=0):
+        """Trainer::train_epoch (src/train.rs:98-144): returns (mean batch loss, accuracy)."""
+        loss, acc = C.c_float(), C.c_float()
+        check(lib.tp_trainer_train_epoch(self.h, loader.h, int(max_batches), C.byref(loss), C.byref(acc)))
+        return loss.value, acc.value
+
+    def evaluate(self, loader: Loader):
+        loss, acc = C.c_float(), C.c_float()
+        check(lib.tp_trainer_evaluate(self.h, loader.h, C.byref(loss), C.byref(acc)))
+        return loss.value, acc.value
+
+    def set_scheduler(self, sched):
+        self._sched = sched
+        check(lib.tp_trainer_set_scheduler(self.h, sched.h if sched is not None else None))
+
+    def fit(self, train_loader: Loader, val_loader: Loader, epochs, verbose=False):
+        check(lib.tp_trainer_fit(self.h, train_loader.h, val_loader.h, int(epochs), int(bool(verbose))))
+
+    def metrics(self):
+        out = {}
+        for i, name in enumerate(("train_loss", "train_acc", "val_loss", "val_acc", "epoch_times")):
+            n = C.c_size_t()
+            check(lib.tp_trainer_metrics(self.h, i, None, 0, C.byref(n)))
+            buf = np.zeros(max(n.value, 1), F32)
+            check(lib.tp_trainer_metrics(self.h, i, _fp(buf), n.value, C.byref(n)))
+            out[name] = buf[: n.value].tolist()
+        return out
+
+    def get_lr(self) -> float:
+        lr = C.c_float()
+        check(lib.tp_trainer_get_lr(self.h, C.byref(lr)))
+        return lr.value
+
+    def device_error(self) -> int:
+        """Reads (and clears) the context's sticky device error word."""
+        c = C.c_int()
+        check(lib.tp_trainer_device_error(self.h, C.byref(c)))
+        return c.value
+
     def set_use_fused(self, on):
         check(lib.tp_trainer_set_use_fused(self.h, int(bool(on))))
 
@@ -294,6 +333,84 @@ class Trainer:
         c = C.c_uint64()
         check(lib.tp_trainer_graph_replays(self.h, C.byref(c)))
         return c.value
+
+
+class Dataset:
+    """data::MNISTDataset (src/data/mnist.rs:21-25) from arrays (f32 in [0,1] or the raw u8 pixels) or from the IDX files."""
+
+    def __init__(self, images=None, labels=None, mnist_dir=None, train=True):
+        self.h = C.c_void_p()
+        if mnist_dir is not None:
+            check(lib.tp_dataset_load_mnist(str(mnist_dir).encode(), int(train), C.byref(self.h)))
+            return
+        images = np.ascontiguousarray(images)
+        labels = _f32(labels)
+        is_u8 = images.dtype == np.uint8
+        if not is_u8:
+            images = _f32(images)
+        n = images.shape[0]
+        check(lib.tp_dataset_from_arrays(images.ctypes.data_as(C.c_void_p), int(is_u8), _fp(labels), n, images.size // max(n, 1), C.byref(self.h)))
+
+    def __len__(self):
+        n = C.c_size_t()
+        check(lib.tp_dataset_len(self.h, C.byref(n)))
+        return n.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_dataset_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Loader:
+    """data::DataLoader (src/data/mnist.rs:326-385) over a Dataset, with a pinned-memory prefetch pipeline."""
+
+    def __init__(self, dataset: Dataset, batch_size, shuffle=True, seed=0, sample_shape=None):
+        self.dataset = dataset
+        self.h = C.c_void_p()
+        check(lib.tp_loader_create(dataset.h, int(batch_size), int(bool(shuffle)), int(seed), C.byref(self.h)))
+        if sample_shape is not None:
+            check(lib.tp_loader_set_sample_shape(self.h, _shape(sample_shape), len(sample_shape)))
+
+    def num_batches(self) -> int:
+        n = C.c_size_t()
+        check(lib.tp_loader_num_batches(self.h, C.byref(n)))
+        return n.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_loader_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Scheduler:
+    """optim::{StepLR, ExponentialLR, CosineAnnealingLR, ReduceLROnPlateau} (src/optim.rs:190-352)."""
+
+    def __init__(self, kind, base_lr, p1=0.0, p2=0.0, n=0, mode=None):
+        self.h = C.c_void_p()
+        check(lib.tp_scheduler_create(kind.encode(), base_lr, p1, p2, int(n), mode.encode() if mode else None, C.byref(self.h)))
+
+    def step(self, metric=None):
+        check(lib.tp_scheduler_step(self.h, int(metric is not None), 0.0 if metric is None else float(metric)))
+
+    def get_lr(self) -> float:
+        lr = C.c_float()
+        check(lib.tp_scheduler_get_lr(self.h, C.byref(lr)))
+        return lr.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_scheduler_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 def nccl_unique_id() -> bytes:
