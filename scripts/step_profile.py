@@ -129,13 +129,8 @@ def main():
             run()
         L = len(dims) - 1
         names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head"]
-        for l in range(L - 2, -1, -1):
-            if l > 0:
-                names.append(f"dX{l}")
-            if l == L - 2:
-                names.append("dW_last")
-            names.append(f"dW{l}")
-        names += ["fold", "optimizer"]
+        names += [f"dX{l}" for l in range(L - 2, 0, -1)]
+        names += ["dW (all)", "fold", "optimizer"]
         buf = np.zeros(32, np.int64)
         slots = C.c_int()
         check(lib.tp_step_read_profile(step, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(slots)))

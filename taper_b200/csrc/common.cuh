@@ -176,10 +176,15 @@ struct Bx3Launch {                   // a prepared launch: tensor maps encoded o
     int relu;
     float* colsum_part;
     unsigned long long* stamp;       // profiling: where the kernel stores %globaltimer after its dependency wait (NULL: off)
+    bool a_early, b_early;           // under PDL: the operand was complete before the PREVIOUS kernel started (weights, older
+                                     // activations), so its first pipeline stages may be requested before the dependency wait
 };
 int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const uint16_t* a_split, long long a_plane,
-                const uint16_t* b_split, long long b_plane, float beta, float* c, const Bx3Epilogue& ep, Bx3Launch* out);
+                const uint16_t* b_split, long long b_plane, float beta, float* c, const Bx3Epilogue& ep, Bx3Launch* out,
+                int want_bn = 0, int want_splits = 0);                 // 0: tile width / K-split from the cost model
+int bx3_best_splits(tp_ctx* ctx, int bn, long tiles, int k);           // K-split for tiles that share one launch
 int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl);
+int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl);      // compatible problems share a launch
 int split_bf16(tp_ctx* ctx, const float* src, uint16_t* dst, size_t n, long long plane, bool pdl);
 // fp32 operands: splits both into temporaries first.  TP_ERR_UNSUPPORTED when the shape cannot go through TMA.
 int gemm_bx3(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, const float* b, float beta,

@@ -45,8 +45,20 @@ struct Bx3Params {
     const float* bias;
     const float* relu_mask;
     int relu;
-    float* colsum_part;              // [gridDim.y * splits][n] partial column sums of the stored values (NULL: none)
+    float* colsum_part;              // [tiles_m * splits][n] partial column sums of the stored values (NULL: none)
     unsigned long long* stamp;       // optional: CTA 0 stores %globaltimer here once its dependency wait is over
+    int tiles_n;                     // CTAs of the grid's x extent beyond this problem's tiles leave at once
+    int y0;                          // first grid row (blockIdx.y) of this problem in a grouped launch
+    int a_early, b_early;            // operand was complete before the previous kernel started: its first stages are
+                                     // requested BEFORE the programmatic dependency wait
+};
+
+// Up to three problems of the same tile shape / operand majors / K-split in ONE launch (grid rows are concatenated): the
+// independent weight-gradient GEMMs of a backward pass share a launch instead of paying one kernel slot each.
+constexpr int kMaxGroup = 3;
+struct Bx3Group {
+    Bx3Params p[kMaxGroup];
+    int count;
 };
 
 // K-major operand : rows of 128 B (64 bf16 of K), 8 rows = one 1024 B swizzle atom -> SBO 1024; LBO unused.
@@ -96,9 +108,20 @@ __device__ long long g_bx3_t[16];
 
 template <int BN, bool A_MN, bool B_MN, bool DRAIN>
 __global__ void __launch_bounds__(threads_of<DRAIN>(), 1)
-gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Bx3Params p) {
+gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
+                const __grid_constant__ Bx3Group grp) {
     static_assert(!DRAIN || BN <= 128, "the register drain holds BN accumulators per thread");
     constexpr int kThreads = threads_of<DRAIN>();
+    int gi = 0;
+    if (grp.count > 1 && (int)blockIdx.y >= grp.p[1].y0) gi = 1;
+    if (grp.count > 2 && (int)blockIdx.y >= grp.p[2].y0) gi = 2;
+    const Bx3Params& p = grp.p[gi];
+    if ((int)blockIdx.x >= p.tiles_n) return;         // (every CTA of a K-split cluster shares x and y: they leave together)
+    const CUtensorMap* pma = gi == 0 ? &map_a0 : gi == 1 ? &map_a1 : &map_a2;
+    const CUtensorMap* pmb = gi == 0 ? &map_b0 : gi == 1 ? &map_b1 : &map_b2;
+    const int by = (int)blockIdx.y - p.y0;
     using S = Smem<BN>;
     constexpr int kStages = S::kStages;
     constexpr int kChunk = 4;                         // k-blocks (256 elements of K) per tensor-core accumulation (DRAIN)
@@ -113,7 +136,7 @@ gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = by * BM, n0 = blockIdx.x * BN;
     const int total_kb = (p.k + BK - 1) / BK;
     const int kb0 = (int)(((long long)blockIdx.z * total_kb) / p.splits);
     const int kb1 = (int)(((long long)(blockIdx.z + 1) * total_kb) / p.splits);
@@ -121,8 +144,8 @@ gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (threadIdx.x == 0) BX3_T(0);
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&map_a);
-        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(pma);
+        tma_prefetch_desc(pmb);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, 1);
@@ -142,42 +165,65 @@ gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) BX3_T(1);
-    // programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may run before
-    // the previous kernel's memory is visible.  The next kernel's CTAs may be scheduled from here on.
+    auto a_st = [&](int s) { return smem + s * S::kStageBytes; };
+    auto b_st = [&](int s) { return smem + s * S::kStageBytes + S::kABytes; };
+    auto load_a = [&](int s, int k0) {
+        if (A_MN) {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g) tma_load_3d(a_st(s) + g * 16384, pma, full_bar + s, m0 + 64 * g, k0, 0);
+        } else {
+            tma_load_3d(a_st(s), pma, full_bar + s, k0, m0, 0);
+        }
+    };
+    auto load_b = [&](int s, int k0) {
+        if (B_MN) {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) tma_load_3d(b_st(s) + g * 16384, pmb, full_bar + s, n0 + 64 * g, k0, 0);
+        } else {
+            tma_load_3d(b_st(s), pmb, full_bar + s, k0, n0, 0);
+        }
+    };
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may touch memory
+    // the previous kernel writes before the wait.  An operand that was complete before the previous kernel even started
+    // (weights: written by the last step's optimizer; the forward activations in a backward GEMM) is requested for the
+    // first pipeline stages right away, so its tiles are in flight while the previous kernel drains.
     pdl_launch_dependents();
+    const int n_early = nkb < kStages ? nkb : kStages;
+    if (warp == 0 && lane == 0 && (p.a_early || p.b_early)) {
+        for (int i = 0; i < n_early; ++i) {
+            mbar_expect_tx(full_bar + i, S::kStageBytes);
+            const int k0 = (kb0 + i) * BK;
+            if (p.a_early) load_a(i, k0);
+            if (p.b_early) load_b(i, k0);
+        }
+    }
     pdl_wait();
     if (threadIdx.x == 0) BX3_T(2);
-    if (p.stamp && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (p.stamp && threadIdx.x == 0 && blockIdx.x == 0 && by == 0 && blockIdx.z == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         *p.stamp = gt;
     }
 
-    auto a_st = [&](int s) { return smem + s * S::kStageBytes; };
-    auto b_st = [&](int s) { return smem + s * S::kStageBytes + S::kABytes; };
     float* stage = (float*)smem;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            const bool early = p.a_early || p.b_early;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % kStages;
                 const uint32_t ph = (i / kStages) & 1;
+                const int k0 = (kb0 + i) * BK;
+                if (early && i < n_early) {            // the stage's transaction count is armed; only the late operand is missing
+                    if (!p.a_early) load_a(s, k0);
+                    if (!p.b_early) load_b(s, k0);
+                    continue;
+                }
                 mbar_wait(empty_bar + s, ph ^ 1);
                 mbar_expect_tx(full_bar + s, S::kStageBytes);
-                const int k0 = (kb0 + i) * BK;
-                if (A_MN) {
-#pragma unroll
-                    for (int g = 0; g < BM / 64; ++g) tma_load_3d(a_st(s) + g * 16384, &map_a, full_bar + s, m0 + 64 * g, k0, 0);
-                } else {
-                    tma_load_3d(a_st(s), &map_a, full_bar + s, k0, m0, 0);
-                }
-                if (B_MN) {
-#pragma unroll
-                    for (int g = 0; g < BN / 64; ++g) tma_load_3d(b_st(s) + g * 16384, &map_b, full_bar + s, n0 + 64 * g, k0, 0);
-                } else {
-                    tma_load_3d(b_st(s), &map_b, full_bar + s, k0, n0, 0);
-                }
+                load_a(s, k0);
+                load_b(s, k0);
             }
         }
     } else if (warp == 1) {
@@ -364,7 +410,7 @@ gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         else fold_store(std::integral_constant<int, 2>{});
         if (want_cs) {
             __syncthreads();
-            float* dst = p.colsum_part + ((size_t)blockIdx.y * S_ + blockIdx.z) * p.n;
+            float* dst = p.colsum_part + ((size_t)by * S_ + blockIdx.z) * p.n;
             for (int c = t; c < BN; c += kThreads) {
                 if (n0 + c >= p.n) continue;
                 float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
@@ -441,7 +487,7 @@ bool make_map(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, int rows
 }
 
 template <int BN, bool A_MN, bool B_MN, bool DRAIN>
-int launch_t(tp_ctx* ctx, const tp::Bx3Launch& L, bool pdl) {
+int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl) {
     auto kern = gemm_bx3_kernel<BN, A_MN, B_MN, DRAIN>;
     constexpr int smem = Smem<BN>::kTotal;
     static bool attr_set[16] = {};                    // per device
@@ -451,25 +497,40 @@ int launch_t(tp_ctx* ctx, const tp::Bx3Launch& L, bool pdl) {
     } else if (ctx->device >= 16) {
         TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    Bx3Params p;
-    p.m = L.m; p.n = L.n; p.k = L.k; p.splits = L.splits;
-    p.alpha = L.alpha; p.beta = L.beta;
-    p.c = L.c; p.c_split = L.c_split; p.c_plane = L.c_plane;
-    p.bias = L.bias; p.relu_mask = L.relu_mask; p.relu = L.relu;
-    p.colsum_part = L.colsum_part;
-    p.stamp = L.stamp;
+    Bx3Group g{};
+    g.count = count;
+    int rows = 0, max_tn = 0;
+    for (int i = 0; i < count; ++i) {
+        const tp::Bx3Launch& L = *Ls[i];
+        Bx3Params& p = g.p[i];
+        p.m = L.m; p.n = L.n; p.k = L.k; p.splits = L.splits;
+        p.alpha = L.alpha; p.beta = L.beta;
+        p.c = L.c; p.c_split = L.c_split; p.c_plane = L.c_plane;
+        p.bias = L.bias; p.relu_mask = L.relu_mask; p.relu = L.relu;
+        p.colsum_part = L.colsum_part;
+        p.stamp = L.stamp;
+        p.tiles_n = L.tiles_n;
+        p.y0 = rows;
+        p.a_early = L.a_early ? 1 : 0; p.b_early = L.b_early ? 1 : 0;
+        rows += L.tiles_m;
+        if (L.tiles_n > max_tn) max_tn = L.tiles_n;
+    }
+    if (rows > 65535) return TP_ERR_UNSUPPORTED;
+    const tp::Bx3Launch& L0 = *Ls[0];
+    const tp::Bx3Launch& L1 = *Ls[count > 1 ? 1 : 0];
+    const tp::Bx3Launch& L2 = *Ls[count > 2 ? 2 : 0];
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(L.tiles_n, L.tiles_m, L.splits);
+    cfg.gridDim = dim3(max_tn, rows, L0.splits);
     cfg.blockDim = dim3(threads_of<DRAIN>());
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (L.splits > 1) {
+    if (L0.splits > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = 1;
         attr[na].val.clusterDim.y = 1;
-        attr[na].val.clusterDim.z = L.splits;
+        attr[na].val.clusterDim.z = L0.splits;
         ++na;
     }
     if (pdl) {
@@ -479,17 +540,18 @@ int launch_t(tp_ctx* ctx, const tp::Bx3Launch& L, bool pdl) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    TP_CUDA(cudaLaunchKernelEx(&cfg, kern, L.ma, L.mb, p));
+    TP_CUDA(cudaLaunchKernelEx(&cfg, kern, L0.ma, L0.mb, L1.ma, L1.mb, L2.ma, L2.mb, g));
     TP_LAUNCH_OK(ctx);
     return TP_OK;
 }
 
 template <int BN, bool DRAIN>
-int launch_major(tp_ctx* ctx, const tp::Bx3Launch& L, bool pdl) {
-    if (!L.a_mn && !L.b_mn) return launch_t<BN, false, false, DRAIN>(ctx, L, pdl);
-    if (!L.a_mn && L.b_mn) return launch_t<BN, false, true, DRAIN>(ctx, L, pdl);
-    if (L.a_mn && !L.b_mn) return launch_t<BN, true, false, DRAIN>(ctx, L, pdl);
-    return launch_t<BN, true, true, DRAIN>(ctx, L, pdl);
+int launch_major(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl) {
+    const tp::Bx3Launch& L = *Ls[0];
+    if (!L.a_mn && !L.b_mn) return launch_t<BN, false, false, DRAIN>(ctx, Ls, count, pdl);
+    if (!L.a_mn && L.b_mn) return launch_t<BN, false, true, DRAIN>(ctx, Ls, count, pdl);
+    if (L.a_mn && !L.b_mn) return launch_t<BN, true, false, DRAIN>(ctx, Ls, count, pdl);
+    return launch_t<BN, true, true, DRAIN>(ctx, Ls, count, pdl);
 }
 
 template <int BN>
@@ -560,8 +622,38 @@ int split_bf16(tp_ctx* ctx, const float* src, uint16_t* dst, size_t n, long long
     return TP_OK;
 }
 
+namespace {
+// SM cycles of one CTA wave-by-wave: waves * (fixed + k-blocks per CTA * t_kb(BN) + fold(S, BN))
+long bx3_cost(const Bx3State* st, int bi, int si, long tiles, int kblocks) {
+    static const long tkb[3] = {1150, 1530, 3200};    // measured (B200, 1024^3): cycles per k-block incl. pipeline stalls
+    static const int cands[3] = {64, 128, 256};
+    const int sp = 1 << si;
+    const long kbpc = (kblocks + sp - 1) / sp;
+    const long waves = (tiles + st->max_clusters[bi][si] - 1) / st->max_clusters[bi][si];
+    return waves * (5000 + kbpc * tkb[bi] + (sp > 1 ? 1000 + 4 * cands[bi] + 500 * sp : 0));
+}
+}  // namespace
+
+// K-split for `tiles` output tiles of width bn that will share one launch (bx3_launch_group)
+int bx3_best_splits(tp_ctx* ctx, int bn, long tiles, int k) {
+    cudaSetDevice(ctx->device);
+    Bx3State* st = state_of(ctx);
+    const int bi = bn == 64 ? 0 : bn == 128 ? 1 : 2;
+    const int kblocks = (k + BK - 1) / BK;
+    int best_s = 1;
+    long best = -1;
+    for (int si = 3; si >= 0; --si) {
+        const int sp = 1 << si;
+        if (sp > 1 && kblocks < 2 * sp) continue;
+        const long c = bx3_cost(st, bi, si, tiles, kblocks);
+        if (best < 0 || c < best) { best = c; best_s = sp; }
+    }
+    return best_s;
+}
+
 int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const uint16_t* a_split, long long a_plane,
-                const uint16_t* b_split, long long b_plane, float beta, float* c, const Bx3Epilogue& ep, Bx3Launch* L) {
+                const uint16_t* b_split, long long b_plane, float beta, float* c, const Bx3Epilogue& ep, Bx3Launch* L,
+                int want_bn, int want_splits) {
     if (m <= 0 || n <= 0 || k <= 0) return TP_ERR_UNSUPPORTED;
     const int a_rows = ta ? k : m, a_cols = ta ? m : k;       // A stored [m,k] (N) or [k,m] (T)
     const int b_rows = tb ? n : k, b_cols = tb ? k : n;       // B stored [k,n] (N) or [n,k] (T)
@@ -580,9 +672,9 @@ int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, c
     // Tile width BN and K-split S (cluster size) from a cost model in SM cycles per CTA:
     //   waves * (fixed + k-blocks per CTA * t_kb(BN) + fold(S, BN)),  waves = ceil(tiles / co-resident clusters of S)
     // t_kb: 12 bf16 MMAs of 128 x BN x 16 per k-block (tensor-bound for BN = 256, shared-memory-port-bound below).
-    static const int force_bn = env_int("TAPER_BX3_BN", 0), force_s = env_int("TAPER_BX3_SPLITS", 0);
+    static const int env_bn = env_int("TAPER_BX3_BN", 0), env_s = env_int("TAPER_BX3_SPLITS", 0);
+    const int force_bn = want_bn ? want_bn : env_bn, force_s = want_splits ? want_splits : env_s;
     const int cands[3] = {64, 128, 256};
-    const long tkb[3] = {1150, 1530, 3200};           // measured (B200, 1024^3): cycles per k-block incl. pipeline stalls
     int bn = 128, splits = 1;
     long best = -1;
     for (int bi = 2; bi >= 0; --bi) {
@@ -595,8 +687,7 @@ int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, c
             if (sp > kblocks) continue;
             const long kbpc = (kblocks + sp - 1) / sp;
             if (cand == 256 && kbpc * BK > 2048) continue;       // no register drain for 256-wide tiles: bound the accumulation depth
-            const long waves = (t + st->max_clusters[bi][si] - 1) / st->max_clusters[bi][si];
-            const long cost = waves * (5000 + kbpc * tkb[bi] + (sp > 1 ? 1000 + 4 * cand + 500 * sp : 0));
+            const long cost = bx3_cost(st, bi, si, t, kblocks);
             if (best < 0 || cost < best) { best = cost; bn = cand; splits = sp; }
         }
     }
@@ -617,14 +708,37 @@ int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, c
     L->bias = ep.bias; L->relu_mask = ep.relu_mask; L->relu = ep.relu;
     L->colsum_part = ep.colsum_part;
     L->stamp = nullptr;
+    L->a_early = L->b_early = false;
     return TP_OK;
 }
 
-int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl) {
+static int launch_any(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl) {
     cudaSetDevice(ctx->device);
-    if (L.bn == 256) return launch_major<256, false>(ctx, L, pdl);
-    if (L.bn == 128) return L.drain ? launch_major<128, true>(ctx, L, pdl) : launch_major<128, false>(ctx, L, pdl);
-    return L.drain ? launch_major<64, true>(ctx, L, pdl) : launch_major<64, false>(ctx, L, pdl);
+    const Bx3Launch& L = *Ls[0];
+    if (L.bn == 256) return launch_major<256, false>(ctx, Ls, count, pdl);
+    if (L.bn == 128) return L.drain ? launch_major<128, true>(ctx, Ls, count, pdl) : launch_major<128, false>(ctx, Ls, count, pdl);
+    return L.drain ? launch_major<64, true>(ctx, Ls, count, pdl) : launch_major<64, false>(ctx, Ls, count, pdl);
+}
+
+int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl) {
+    const Bx3Launch* one[1] = {&L};
+    return launch_any(ctx, one, 1, pdl);
+}
+
+// problems that share tile width, operand majors, K-split and drain mode go out as ONE launch (up to three); the rest follow
+// one by one
+int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl) {
+    int i = 0;
+    while (i < count) {
+        int j = i + 1;
+        while (j < count && j - i < kMaxGroup && Ls[j]->bn == Ls[i]->bn && Ls[j]->a_mn == Ls[i]->a_mn && Ls[j]->b_mn == Ls[i]->b_mn &&
+               Ls[j]->splits == Ls[i]->splits && Ls[j]->drain == Ls[i]->drain && Ls[j]->k == Ls[i]->k)
+            ++j;
+        int rc = launch_any(ctx, Ls + i, j - i, pdl);
+        if (rc) return rc;
+        i = j;
+    }
+    return TP_OK;
 }
 
 // sgemm_rowmajor on fp32 operands in bf16x3 mode: split both operands into temporaries, then the pre-split kernel

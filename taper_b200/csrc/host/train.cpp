@@ -794,7 +794,10 @@ std::pair<float, float> Trainer::train_epoch(data::DataLoader& loader, size_t ma
     std::deque<std::pair<size_t, int>> inflight;                                // {batch size, pinned slot}
     auto drain_one = [&]() {
         StepResult r = fetch();
-        total_correct += (size_t)r.correct;                                      // (acc * batch) as usize, :117
+        // `(acc * batch_size as f32) as usize` with acc = correct / total in f32 (src/loss.rs:289, src/train.rs:117): the
+        // reference's round trip through the ratio truncates, so a count may come back one short — reproduced
+        const float bsz = (float)inflight.front().first;
+        total_correct += (size_t)((r.correct / bsz) * bsz);
         total_samples += inflight.front().first;
         loader.release(inflight.front().second);                                 // its H2D copy finished before its step ran
         inflight.pop_front();
@@ -822,7 +825,7 @@ std::pair<float, float> Trainer::evaluate(data::DataLoader& loader) {           
     size_t batch = 0;
     while (loader.next(images, labels, batch)) {
         StepResult r = eval_batch(images.data(), labels.data(), batch, loader.sample_shape);
-        total_correct += (size_t)r.correct;
+        total_correct += (size_t)((r.correct / (float)batch) * (float)batch);    // as in train_epoch (src/train.rs:160)
         total_samples += batch;
         total_loss += r.loss;
     }

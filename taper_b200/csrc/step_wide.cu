@@ -539,6 +539,12 @@ static int wide_build(WidePlan* w, Carver& c) {
 
     tp_ctx* ctx = w->ctx;
     w->fwd.assign(L - 1, Bx3Launch{}); w->dx.assign(L - 1, Bx3Launch{}); w->dw.assign(L - 1, Bx3Launch{});
+    // the weight-gradient GEMMs (every layer's dW and the classifier's) are independent and share launches: one tile
+    // width and one K-split for all of them, chosen for the total tile count
+    const int dw_bn = 128;
+    long dw_tiles = (KH + dw_bn - 1) / dw_bn;          // dW_last: one row of tiles
+    for (int l = 0; l + 1 < L; ++l) dw_tiles += (long)((d.dims[l + 1] + 127) / 128) * ((d.dims[l] + dw_bn - 1) / dw_bn);
+    const int dw_splits = bx3_best_splits(ctx, dw_bn, dw_tiles, B);
     for (int l = 0; l + 1 < L; ++l) {
         const int in = d.dims[l], out = d.dims[l + 1];
         const uint16_t* in_split = l == 0 ? w->x_split : w->act_split[l - 1];
@@ -551,11 +557,16 @@ static int wide_build(WidePlan* w, Carver& c) {
         int rc = bx3_prepare(ctx, 0, 1, B, out, in, 1.0f, in_split, in_plane, w->w_split + d.w_off[l], w->arena_plane, 0.0f, w->act[l], ef,
                              &w->fwd[l]);
         if (rc) return rc;
+        w->fwd[l].b_early = true;                      // W_l's planes: written by the previous step's optimizer kernel
         // dW_l = dZ_l^T . in   (T,N) straight into the gradient arena
         Bx3Epilogue ew;
         rc = bx3_prepare(ctx, 1, 0, out, in, B, 1.0f, w->dz_split[l], (long long)B * out, in_split, in_plane, 0.0f, w->G + d.w_off[l], ew,
-                         &w->dw[l]);
+                         &w->dw[l], dw_bn, dw_splits);
         if (rc) return rc;
+        // the weight-gradient GEMMs run after the whole dX chain (one grouped launch): the forward activations are old by
+        // then, and so is every dZ except the one the last dX kernel has just produced (dZ_0)
+        w->dw[l].b_early = true;
+        w->dw[l].a_early = l > 0;
         if (l > 0) {
             // dZ_{l-1} = (dZ_l . W_l) * [act_{l-1} > 0]   (N,N); planes + column sums (db_{l-1}) in the epilogue
             Bx3Epilogue ex;
@@ -565,6 +576,7 @@ static int wide_build(WidePlan* w, Carver& c) {
             rc = bx3_prepare(ctx, 0, 0, B, in, out, 1.0f, w->dz_split[l], (long long)B * out, w->w_split + d.w_off[l], w->arena_plane, 0.0f,
                              nullptr, ex, &w->dx[l]);
             if (rc) return rc;
+            w->dx[l].b_early = true;
             w->cs_parts[l - 1] = w->dx[l].tiles_m * w->dx[l].splits;
         }
     }
@@ -573,9 +585,11 @@ static int wide_build(WidePlan* w, Carver& c) {
         // computed and not stored
         Bx3Epilogue el;
         int rc = bx3_prepare(ctx, 1, 0, kMaxOut, KH, B, 1.0f, w->dl_split, (long long)B * kMaxOut, w->act_split[L - 2], (long long)B * KH, 0.0f,
-                             w->G + d.w_off[L - 1], el, &w->dw_last);
+                             w->G + d.w_off[L - 1], el, &w->dw_last, dw_bn, dw_splits);
         if (rc) return rc;
         w->dw_last.m = C;
+        w->dw_last.b_early = true;
+        w->dw_last.a_early = L > 2;                    // dlogits come from the head; a dX kernel sits in between unless L == 2
     }
     // fold table
     FoldArgs& f = w->fold;
@@ -725,19 +739,19 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
     rc = d.dims[L] == 10 ? launch_pdl(ctx, wide_head_kernel<10>, dim3(w->head_grid), w->head_smem, ha, pdl)
                          : launch_pdl(ctx, wide_head_kernel<kMaxOut>, dim3(w->head_grid), w->head_smem, ha, pdl);
     if (rc) return rc;
-    for (int l = L - 2; l >= 0; --l) {
-        if (l > 0) {                                   // the chain's critical path first
-            w->dx[l].stamp = next_stamp();
-            rc = bx3_launch(ctx, w->dx[l], pdl);
-            if (rc) return rc;
-        }
-        if (l == L - 2) {
-            w->dw_last.stamp = next_stamp();
-            rc = bx3_launch(ctx, w->dw_last, pdl);
-            if (rc) return rc;
-        }
-        w->dw[l].stamp = next_stamp();
-        rc = bx3_launch(ctx, w->dw[l], pdl);
+    for (int l = L - 2; l > 0; --l) {                  // the dX chain: dZ_{L-2} -> ... -> dZ_0
+        w->dx[l].stamp = next_stamp();
+        rc = bx3_launch(ctx, w->dx[l], pdl);
+        if (rc) return rc;
+    }
+    {
+        // every weight gradient: independent of each other, so compatible ones share a launch
+        const Bx3Launch* all[TP_STEP_MAX_LAYERS + 1];
+        int n = 0;
+        w->dw_last.stamp = next_stamp();
+        all[n++] = &w->dw_last;
+        for (int l = L - 2; l >= 0; --l) { w->dw[l].stamp = nullptr; all[n++] = &w->dw[l]; }
+        rc = bx3_launch_group(ctx, all, n, pdl);
         if (rc) return rc;
     }
     FoldArgs fa = w->fold;

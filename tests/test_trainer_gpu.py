@@ -28,7 +28,7 @@ def oracle_epoch(ref, opt, X, Y, order, batch):
         x, y = X[idx], Y[idx]
         loss, acc = R.train_step(ref, opt, R.Tensor.new(x, x.shape), R.Tensor.new(y, y.shape))
         tot_loss += loss
-        correct += int(acc * len(idx))                                            # (acc * batch) as usize, :117
+        correct += int(F32(acc) * F32(len(idx)))                                  # (acc * batch as f32) as usize, :117 (f32 round trip)
     return tot_loss / nb, correct / n
 
 
@@ -57,8 +57,10 @@ def test_train_epoch_and_evaluate_match_the_oracle_loop(dims, spec, n, batch, u8
         loss, acc = tr.train_epoch(loader)
         assert loss == pytest.approx(loss_ref, rel=1e-4), f"epoch {epoch}"
         assert abs(acc - acc_ref) <= 3.0 / n, f"epoch {epoch}"                    # near-tied rows may flip
+    # free-running SGD: the wide plan's bf16x3 products (~1e-5 of |g|inf per step) and ReLU units within summation noise of 0
+    # add up over the epochs' steps, as on the 3xTF32 tape path (test_cfg4_mlp_wide_adam_large_eps_tight): 3e-4 there
     for j, p in enumerate(ref.parameters()):
-        close(m.get_param(j), p.data(), 1e-4, f"param {j}")
+        close(m.get_param(j), p.data(), 3e-4 if dims is WIDE[0] else 1e-4, f"param {j}")
     # evaluate (src/train.rs:147-172): same sums without the optimizer
     R.Tape.reset()
     tot, correct = 0.0, 0
@@ -67,7 +69,7 @@ def test_train_epoch_and_evaluate_match_the_oracle_loop(dims, spec, n, batch, u8
         x, y = X[b * batch:(b + 1) * batch], Y[b * batch:(b + 1) * batch]
         lg = ref.forward(R.Tensor.new(x, x.shape))
         tot += float(R.cross_entropy_loss(lg, R.Tensor.new(y, y.shape)).data()[0])
-        correct += int(float(R.accuracy(lg, R.Tensor.new(y, y.shape))) * len(y))
+        correct += int(F32(R.accuracy(lg, R.Tensor.new(y, y.shape))) * F32(len(y)))
         R.Tape.reset()
     loss, acc = tr.evaluate(loader)
     assert loss == pytest.approx(tot / nb, rel=1e-4) and abs(acc - correct / n) <= 3.0 / n
