@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """bench.py — MNIST samples/sec (fwd + bwd + optimizer step) of the tape-evaluation hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2|cfg4|example_mlp|cnn2|cnn5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4|cfg5|cfg2|...] [--impl ours|reference]
 
-A "step" is one iteration of the reference's train_epoch loop body (src/train.rs:106-138): Tape::reset,
-forward, cross-entropy, accuracy, backward, [gradient allreduce], optimizer step, zero_grad — on one
-synthetic MNIST-shaped batch.  One JSON line is printed by rank 0:
+A "step" is one iteration of the reference's train_epoch loop body (src/train.rs:106-138): Tape::reset, forward,
+cross-entropy, accuracy, backward, [gradient allreduce], optimizer step, zero_grad — on one synthetic MNIST-shaped batch.
+The headline workload is BASELINE.json configs[3] (MLP 784-1024-1024-10, batch 1024 per GPU, Adam): the configuration the
+metric "samples/sec at 1/2/4/8 B200" is quoted on.  configs[4] (5-conv CNN, batch 1024/GPU, AdamW + StepLR) and configs[1]
+(MLP 784-128-10, batch 512, Adam) are measured in the same run and reported under "sub_records".
+One JSON line is printed by rank 0:
 
-  value     whole-job samples/s with the dataset resident in HBM (188 MB > L2; every step gathers a fresh
-            batch on the device), timed with CUDA events on the launching stream, max over ranks
-  e2e       the same metric through the reference-facing trainer call with HOST (pinned) inputs: per step an
-            H2D copy of the batch and a D2H read of {loss, #correct} are inside the timed region (wall clock)
-  roofline  the dominant kernel of the step, timed alone with CUDA events
+  value     whole-job samples/s with the dataset resident in HBM (60000 x 784 f32 = 188 MB > L2; every step gathers a fresh
+            batch on the device), CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the reference-facing call a user makes, Trainer::train_epoch over a DataLoader
+            (tp_trainer_train_epoch): per step the host-side batch gather (src/data/mnist.rs:276-309), the H2D copy of the
+            batch and the D2H read of {loss, #correct} are all inside the timed region (wall clock, max over ranks)
+  roofline  the dominant kernel of the step with its in-situ launch duration
   cpu_baseline  the CPU restatement of the reference (oracle/, NumPy + OpenBLAS) on this box's host cores
+  dp_check  (N > 1) replicas bit-identical, N ranks x B match 1 rank x N*B and the oracle's first step to 1e-4
 
---impl reference times the oracle port instead (the reference is a Rust crate; no Rust toolchain exists
-in the image), same metric / config.
+--impl reference times the oracle port instead (the reference is a Rust crate; no Rust toolchain exists in the image, see
+DESIGN.md), same metric / config, all host threads.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -49,19 +55,36 @@ CONFIGS = {
     "cfg5": ("CNN5", ("cnn5", None), 1024, "adamw", 0.01, 1e-4, (1, 28, 28),
              "configs[4]: 5-conv CNN, batch 1024/GPU, AdamW + StepLR(5 epochs, 0.8) stepped every 59-step epoch, synthetic 28x28x1"),
 }
-EPOCH_STEPS = 59           # 60000 / 1024: cfg5 steps its LR scheduler (src/optim.rs:190-219) once per epoch-equivalent
-DATASET_N = 60000          # MNIST-sized: 60000 x 784 fp32 = 188 MB, larger than the 126 MB L2
+PRIMARY = "cfg4"                    # BASELINE.json: the metric is quoted "at 1/2/4/8 B200" on configs[3]
+SUBS = ["cfg5", "cfg2"]             # configs[4] (the >= 6x scaling target) and configs[1] (round 1's headline)
+EPOCH_STEPS = 59                    # 60000 / 1024: cfg5 steps its LR scheduler (src/optim.rs:190-219) once per epoch-equivalent
+DATASET_N = 60000                   # MNIST-sized
 
 
-def synthetic(n, sample_shape, seed):
+def workload_config(name, world):
+    """The `config` object: identical in both arms (ours / reference) for the same workload."""
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, workload = CONFIGS[name]
+    return {"workload": workload, "name": name, "batch_per_gpu": batch, "global_batch": batch * world, "optimizer": opt_kind,
+            "lr": lr, "weight_decay": wd, "parallelism": f"dp{world}",
+            "dataset": f"synthetic MNIST-shaped, {DATASET_N} x {int(np.prod(sample_shape))} u8 pixels (f32 = u8 / 255, src/data/mnist.rs:225) + "
+                       "labels, per rank",
+            "l2_policy": f"inputs larger than L2: every step takes a fresh batch out of the {DATASET_N}-sample dataset (188 MB as f32); "
+                         "parameters and optimizer state are the step's own working set"}
+
+
+def synthetic_u8(n, sample_shape, seed):
     rng = np.random.default_rng(seed)
-    x = rng.random((n,) + tuple(sample_shape), dtype=F32)          # images U[0,1) (MNIST is u8/255, src/data/mnist.rs:225)
-    y = rng.integers(0, 10, n).astype(F32)                         # labels stored as f32 (src/data/mnist.rs:268)
-    return x, y
+    xu = rng.integers(0, 256, (n,) + tuple(sample_shape), dtype=np.uint8)      # MNIST pixels as on disk
+    y = rng.integers(0, 10, n).astype(F32)                                      # labels stored as f32 (src/data/mnist.rs:268)
+    return xu, y
+
+
+def to_f32(xu):
+    return (xu.astype(F32) / F32(255.0)).astype(F32)                            # src/data/mnist.rs:225
 
 
 def mlp_flops(sizes, batch):
-    """Algorithmic GEMM flops of one step: fwd + dW for every layer, dX for all but the first (SURVEY §8d)."""
+    """Algorithmic GEMM flops of one step: fwd + dW for every layer, dX for all but the first (SURVEY 8d)."""
     f = 0
     for i in range(len(sizes) - 1):
         g = 2 * batch * sizes[i] * sizes[i + 1]
@@ -112,8 +135,8 @@ class ClockSampler:
 
         sm, mx, reasons = collect(lambda t: any(a <= t <= b for a, b in windows))
         note = None
-        if not sm and windows:
-            # a timed region shorter than the 50 ms sampling period: use the samples within 0.5 s of it instead
+        if len(sm) < 3 and windows:
+            # timed regions shorter than the 50 ms sampling period: use the samples within 0.5 s of them instead
             lo, hi = min(a for a, _ in windows) - 0.5, max(b for _, b in windows) + 0.5
             sm, mx, reasons = collect(lambda t: lo <= t <= hi)
             note = "timed regions shorter than the sampling period: samples within 0.5 s of them"
@@ -124,6 +147,7 @@ class ClockSampler:
         return out
 
 
+# ---- the reference's CPU implementation of the path: the oracle port --------------------------------------------------------
 def build_oracle(kind, arg, seed):
     from oracle import taper_ref as R
     rng = np.random.default_rng(seed)
@@ -132,65 +156,399 @@ def build_oracle(kind, arg, seed):
     return R.build_cnn2(rng) if kind == "cnn2" else R.build_cnn5(rng)
 
 
-def time_oracle(cfg, steps, warmup, batch, budget_s=None):
-    """Times oracle train steps (the CPU restatement of the reference); returns (samples/s, steps run, threads)."""
+def blas_threads(n):
+    """Pins the BLAS pools behind NumPy to n threads (torchrun exports OMP_NUM_THREADS=1: undo that explicitly)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def time_oracle(name, steps, warmup, threads, budget_s=None):
+    """Times oracle train steps (the CPU restatement of the reference) at the config's own batch size with `threads` BLAS
+    threads; returns (samples/s, steps run, seconds)."""
     from oracle import taper_ref as R
-    spec_key, (kind, arg), _, opt_kind, lr, wd, sample_shape, _ = cfg
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, _ = CONFIGS[name]
     model = build_oracle(kind, arg, 0)
     params = model.parameters()
     opt = {"sgd": lambda: R.SGD(params, lr), "adam": lambda: R.Adam(params, lr, None, None, wd),
            "adamw": lambda: R.AdamW(params, lr, None, None, wd)}[opt_kind]()
-    x, y = synthetic(batch * 8, sample_shape, 1)
+    nb = 4
+    xu, y = synthetic_u8(batch * nb, sample_shape, 1)
+    x = to_f32(xu)
+
     def one(i):
-        s = (i % 8) * batch
+        s = (i % nb) * batch
         R.train_step(model, opt, R.Tensor.new(x[s:s + batch], (batch,) + tuple(sample_shape)), R.Tensor.new(y[s:s + batch], (batch,)))
-    for i in range(warmup):
-        one(i)
-    t0 = time.perf_counter()
-    done = 0
-    for i in range(steps):
-        one(i)
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 5:
-            break
-    dt = time.perf_counter() - t0
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    return done * batch / dt, done, threads, dt
+
+    with blas_threads(threads):
+        t_w = time.perf_counter()
+        for i in range(warmup):
+            one(i)
+            if budget_s is not None and time.perf_counter() - t_w > budget_s / 3:
+                break
+        t0 = time.perf_counter()
+        done = 0
+        for i in range(steps):
+            one(i)
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
+                break
+        dt = time.perf_counter() - t0
+    return done * batch / dt, done, dt
 
 
-def run_reference(args, cfg_name, cfg):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port, all host threads."""
+def run_reference(args, name):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port, all host threads, the config's own
+    batch size; a bounded sample (the whole run ends within a few minutes)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    batch = cfg[2]
-    sample_batch = batch if cfg_name in ("cfg1", "cfg2", "example_mlp", "cfg4") else 32     # CNN oracle steps are seconds long
-    t_probe = time.perf_counter()
-    v0, _, _, _ = time_oracle(cfg, 2, 1, sample_batch)
-    per_step = (time.perf_counter() - t_probe) / 3
-    steps = args.steps
-    max_steps = max(5, int(150.0 / max(per_step, 1e-6)))
-    sample = f"{steps} steps of batch {sample_batch}"
-    if steps > max_steps:                         # keep the whole run within a few minutes
-        steps = max_steps
-        sample = f"{steps} of the requested {args.steps} steps (150 s cap), batch {sample_batch}"
-    value, done, threads, dt = time_oracle(cfg, steps, args.warmup, sample_batch)
+    cores = os.cpu_count() or 1
+    budget = 90.0
+    value, done, dt = time_oracle(name, args.steps, args.warmup, cores, budget_s=budget)
+    sample = f"{done} oracle train steps at the config's batch size in {dt:.1f} s, {cores} BLAS threads"
+    if done < args.steps:
+        sample += f" (stopped at the {budget:.0f} s cap; {args.steps} requested)"
+    v1, d1, t1 = time_oracle(name, 3, 1, 1, budget_s=15.0)
     out = {
         "impl": "reference", "metric": "MNIST samples/sec (fwd+bwd+step)", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": dt / done * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg[7], "name": cfg_name, "batch_per_gpu": batch, "optimizer": cfg[3]},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+        "config": workload_config(name, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": sample + "; NumPy/OpenBLAS restatement of the reference tape (oracle/taper_ref.py); "
-                                            "the Rust reference cannot be built here (no cargo/rustc)"},
+                                            "the Rust reference cannot be built here (no cargo/rustc)",
+                         "single_thread": {"value": v1, "unit": "samples/s", "sample": f"{d1} steps in {t1:.1f} s, 1 BLAS thread "
+                                           "(the reference's default matrixmultiply build is single-threaded in GEMM)"}},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+# ---- our arm -----------------------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed is plumbing only: rendezvous, the NCCL id / IPC handle exchange, max-over-ranks of the timings."""
+
+    def __init__(self, world, local):
+        self.world, self.pg = world, None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.pg, self.torch = dist, torch
+
+    def barrier(self):
+        from taper_b200 import host
+        host.sync()
+        if self.pg:
+            self.pg.barrier()
+
+    def max(self, v):
+        if not self.pg:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MAX)
+        return float(t.item())
+
+    def mean(self, v):
+        if not self.pg:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.pg.all_reduce(t)
+        return float(t.item()) / self.world
+
+    def all_ok(self, ok):
+        if not self.pg:
+            return ok
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device="cuda")
+        self.pg.all_reduce(t, op=self.pg.ReduceOp.MIN)
+        return int(t.item()) == 1
+
+    def same_as_rank0(self, arr):
+        if not self.pg:
+            return True
+        t = self.torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        r0 = t.clone()
+        self.pg.broadcast(r0, 0)
+        return bool(self.torch.equal(t, r0))
+
+    def nccl_id(self, rank):
+        from taper_b200 import host
+        uid = self.torch.zeros(128, dtype=self.torch.uint8, device="cuda")
+        if rank == 0:
+            uid = self.torch.frombuffer(bytearray(host.nccl_unique_id()), dtype=self.torch.uint8).cuda()
+        self.pg.broadcast(uid, 0)
+        return bytes(uid.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.pg:
+            self.pg.barrier()
+            self.pg.destroy_process_group()
+
+
+def make_trainer(name, args, dist, rank, world, eps=1e-8, nccl_only=False, seed=0):
+    from taper_b200 import host
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, _ = CONFIGS[name]
+    model = host.Model(getattr(host, spec_key), seed=seed)
+    tr = host.Trainer(model, opt_kind, lr=lr, weight_decay=wd, eps=eps)
+    if args.no_fused:
+        tr.set_use_fused(False)
+    if world > 1:
+        tr.comm_init(rank, world, dist.nccl_id(rank))
+        tr.broadcast_params(0)
+        if not (args.nccl_only or nccl_only or args.no_fused):
+            # small models: gradient exchange inside the persistent step kernel over NVLink peer memory.  Every rank must take
+            # the same path, so a rank that cannot map its peers sends everybody back to the NCCL-in-graph path.  (The wide
+            # plan of configs[3] sums its gradient arena with NCCL between its fold and optimizer kernels.)
+            ok = True
+            try:
+                tr.peer_exchange_init(dist.pg)
+            except Exception as e:
+                ok = False
+                print(f"rank {rank}: peer exchange unavailable ({e}); falling back to the NCCL allreduce", file=sys.stderr)
+            if not dist.all_ok(ok):
+                tr.set_use_fused(False)
+    return model, tr
+
+
+def dp_check(name, args, dist, rank, world, with_oracle):
+    """Driver-visible data-parallel correctness: k steps with W ranks x B rows against (i) each other — replicas
+    must stay bit-identical, (ii) one rank x W*B rows on this GPU, (iii) the oracle's first step on the global batch.
+    Adam's eps is 0.1 here so that the update stays linear in the gradient and the plain 1e-4 bound applies (default-eps
+    trajectories amplify summation-order noise; tests/test_step_gpu.py::close_after_adam)."""
+    from taper_b200 import host
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, _ = CONFIGS[name]
+    k = 2
+    G = batch * world
+    xu, y = synthetic_u8(G * k, sample_shape, 4242)                    # the same global batches on every rank
+    x = to_f32(xu)
+    # (ii) single replica, global batch, no communicator yet on this context
+    ref_model = host.Model(getattr(host, spec_key), seed=0)
+    ref_tr = host.Trainer(ref_model, opt_kind, lr=lr, weight_decay=wd, eps=0.1)
+    if args.no_fused:
+        ref_tr.set_use_fused(False)
+    ref_losses = [ref_tr.step(x[s * G:(s + 1) * G], y[s * G:(s + 1) * G])[0] for s in range(k)]
+    ref_params = [ref_model.get_param(i) for i in range(ref_model.num_params())]
+    del ref_tr
+    model, tr = make_trainer(name, args, dist, rank, world, eps=0.1)
+    out = {"world": world, "steps": k, "ok": True, "adam_eps": 0.1}
+    losses = []
+    p_after1 = None
+    for s in range(k):
+        lo = s * G + rank * batch
+        losses.append(tr.step(x[lo:lo + batch], y[lo:lo + batch])[0])
+        if s == 0:
+            p_after1 = [model.get_param(i) for i in range(model.num_params())]
+    params = [model.get_param(i) for i in range(model.num_params())]
+    flat = np.concatenate([p.reshape(-1) for p in params])
+    identical = dist.all_ok(dist.same_as_rank0(flat))
+    out["replicas_bit_identical"] = identical
+    worst_loss, worst_param = 0.0, 0.0
+    for s in range(k):
+        worst_loss = max(worst_loss, abs(dist.mean(losses[s]) - ref_losses[s]) / abs(ref_losses[s]))
+    for p, r in zip(params, ref_params):
+        worst_param = max(worst_param, float(np.max(np.abs(p - r))) / max(float(np.max(np.abs(r))), 1e-6))
+    out["vs_one_rank_global_batch"] = {"loss_rel": worst_loss, "param_rel_inf": worst_param}
+    ok = identical and worst_loss <= 1e-4 and worst_param <= 1e-4
+    if with_oracle:
+        from oracle import taper_ref as R
+        o = build_oracle(kind, arg, 0)
+        init = host.Model(getattr(host, spec_key), seed=0)         # the CUDA model's own seeded init, injected into the oracle
+        for i, p in enumerate(o.parameters()):
+            p._data[:] = init.get_param(i).reshape(-1)
+        prm = o.parameters()
+        oopt = {"sgd": lambda: R.SGD(prm, lr), "adam": lambda: R.Adam(prm, lr, None, 0.1, wd),
+                "adamw": lambda: R.AdamW(prm, lr, None, 0.1, wd)}[opt_kind]()
+        with blas_threads(os.cpu_count() or 1):
+            l_or, _ = R.train_step(o, oopt, R.Tensor.new(x[:G], (G,) + tuple(sample_shape)), R.Tensor.new(y[:G], (G,)))
+        lo_rel = abs(dist.mean(losses[0]) - l_or) / abs(l_or)
+        po = max(float(np.max(np.abs(a.reshape(-1) - b.data()))) / max(float(np.max(np.abs(b.data()))), 1e-6) for a, b in zip(p_after1, prm))
+        out["vs_oracle_step1"] = {"loss_rel": lo_rel, "param_rel_inf": po}
+        ok = ok and lo_rel <= 1e-4 and po <= 1e-4
+    out["exchange"] = "NCCL allreduce of the gradient arena inside the step" if tr.fused_kind() != 1 else \
+        "in-kernel NVLink peer-memory exchange (tp_xchg_*)"
+    out["ok"] = bool(dist.all_ok(ok))
+    del tr
+    return out
+
+
+def measure(name, args, dist, rank, world, local, windows, primary):
+    """value + e2e of one workload.  Returns the record (rank 0 uses it) — every rank must call it."""
+    from taper_b200 import host
+    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, _ = CONFIGS[name]
+    cols = int(np.prod(sample_shape))
+    model, tr = make_trainer(name, args, dist, rank, world)
+    # each rank owns a shard: its own dataset (weak scaling: batch per GPU fixed)
+    Xu, Y = synthetic_u8(DATASET_N, sample_shape, 1 + rank)
+    X = to_f32(Xu)
+    perm = np.random.default_rng(100 + rank).permutation(DATASET_N).astype(np.uint32)
+    tr.load_dataset(X, Y, perm)                                        # f32 resident: 188 MB > L2
+    W = max(args.warmup, 3)
+    last = (0.0, 0.0)
+    for _ in range(W):
+        tr.step_resident(batch)
+        last = tr.fetch()
+    dist.barrier()
+    e0, e1 = host.Event(), host.Event()
+    l0 = host.launches()
+    w0 = time.perf_counter()
+    e0.record()
+    sched_epoch = 0
+    for i in range(args.steps):
+        if tr.pending() >= 6:
+            last = tr.fetch()
+        tr.step_resident(batch)
+        if name == "cfg5" and i % EPOCH_STEPS == EPOCH_STEPS - 1:     # StepLR(step 5, gamma 0.8) + optimizer.set_lr (src/train.rs:212-216)
+            sched_epoch += 1
+            tr.set_lr(lr * 0.8 ** (sched_epoch // 5))
+    e1.record()
+    while tr.pending():
+        last = tr.fetch()
+    host.sync()
+    w1 = time.perf_counter()
+    gpu_launches = host.launches() - l0
+    ms = dist.max(e0.elapsed_ms(e1))
+    dist.barrier()
+    windows.append((w0, w1))
+    value = world * batch * args.steps / (ms * 1e-3)
+    fused_kind = tr.fused_kind()
+
+    # ---- e2e: Trainer::train_epoch over a DataLoader (host gather into pinned memory, H2D, step, D2H of the results) ----------
+    wide = fused_kind == 2
+    ds = host.Dataset(Xu.reshape(DATASET_N, cols) if wide else X.reshape(DATASET_N, cols), Y)
+    loader = host.Loader(ds, batch, shuffle=False, sample_shape=sample_shape)      # shuffle off: K steps are a fraction of an epoch
+    tr.train_epoch(loader, max_batches=W)
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_loss, e2e_acc = tr.train_epoch(loader, max_batches=args.steps)
+    host.sync()
+    t1 = time.perf_counter()
+    e2e_s = dist.max(t1 - t0)
+    dist.barrier()
+    windows.append((t0, t1))
+    rec = {
+        "config": workload_config(name, world),
+        "value": value, "unit": "samples/s", "ms_per_step": ms / args.steps, "steps": args.steps, "warmup": W,
+        "e2e": {"value": world * batch * args.steps / e2e_s, "unit": "samples/s",
+                "h2d_bytes_per_step": int(batch * (cols * (1 if wide else 4) + 4)), "d2h_bytes_per_step": 16,
+                "ms_per_step": e2e_s / args.steps * 1e3, "input_dtype": "u8 pixels (divided by 255 on the device)" if wide else "f32",
+                "call": "tp_trainer_train_epoch(trainer, loader, max_batches = steps): loader worker threads gather each batch into pinned "
+                        "memory, H2D on the copy stream, results read back per step",
+                "timing": "host wall clock around the call, device synchronised on both sides, max over ranks",
+                "mean_loss": e2e_loss, "accuracy": e2e_acc},
+        "gpu_launches": int(gpu_launches), "launches_per_step": gpu_launches / args.steps,
+        "step_path": {2: "wide device tape: a plan of tcgen05 kernels chained with programmatic dependent launch (bf16x3 GEMMs on pre-split "
+                         "operands, fused head / epilogues / optimizer)" + ("; NCCL allreduce of the gradient arena" if world > 1 else ""),
+                      1: "device tape: one persistent kernel per step (grid barrier between phases; exact fp32 FFMA)"
+                         + ("; gradient exchange in-kernel over NVLink peer memory" if world > 1 else ""),
+                      0: "tape + CUDA graph, one kernel per op (3xTF32 tcgen05 GEMMs / implicit-GEMM convolutions)"
+                         + ("; NCCL allreduce in the graph" if world > 1 else "")}[fused_kind],
+        "gemm_math": {2: "bf16x3 on tcgen05 (kind::f16, 3 MMAs per product, ~1e-5 of |C|inf)", 1: "exact fp32 FFMA on the CUDA cores",
+                      0: {0: "fp32 FFMA", 1: "3xTF32 tcgen05 (fp32-accurate)", 2: "1xTF32 tcgen05", 3: "bf16x3 tcgen05"}[args.gemm_mode]}[fused_kind],
+        "conv_adjoint": ("full" if args.full_adjoint else "strict_reference (SURVEY A1)") if kind != "mlp" else None,
+        "last_step": {"loss": last[0], "correct": last[1]},
+    }
+    del tr
+    return rec
+
+
+def plan_profile(name, peaks, tf32_peak):
+    """In-situ duration of every kernel of the wide plan (one %globaltimer stamp per kernel, taken when its programmatic
+    dependency wait is over, i.e. launch gaps are charged to the kernel before) on the config's shapes, with the roofline
+    each kernel is bound by.  Drives the C ABI directly on a plan with random parameters."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import step_profile as SP
+    import taper_b200
+    from taper_b200 import capi
+    lib = capi.lib
+    spec_key, (kind, dims), batch, opt_kind, lr, wd, sample_shape, _ = CONFIGS[name]
+    ctx = taper_b200.Ctx(0)
+    d, step, keep = SP.build(ctx, dims, batch, opt_kind)
+    if lib.tp_step_is_wide(step) != 1:
+        capi.check(lib.tp_step_destroy(step))
+        return None, []
+    rng = np.random.default_rng(1)
+    n = DATASET_N
+    x = ctx.upload(rng.random((n, dims[0]), dtype=np.float32))
+    y = ctx.upload(rng.integers(0, dims[-1], n).astype(np.float32))
+    perm = ctx.upload(rng.permutation(n).astype(np.int32))
+    cursor = ctx.upload(np.zeros(1, np.int32))
+    run = lambda: capi.check(lib.tp_step_run(ctx.h, step, x.h, y.h, perm.h, cursor.h, n, -1, 0.01, 1.0, None, 0))
+    for _ in range(10):
+        run()
+    capi.check(lib.tp_step_set_profile(step, 1))
+    L = len(dims) - 1
+    names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head"] + [f"dX{l}" for l in range(L - 2, 0, -1)] + ["dW_all", "fold", "optimizer"]
+    acc = np.zeros(len(names))
+    reps = 20
+    for _ in range(reps):
+        for _ in range(3):
+            run()
+        buf = np.zeros(32, np.int64)
+        slots = C.c_int()
+        capi.check(lib.tp_step_read_profile(step, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(slots)))
+        prev, lastv = buf[:16].astype(np.float64), buf[16:].astype(np.float64)
+        tl = list(prev[:len(names)]) + [lastv[0]]
+        acc += np.diff(tl) / 1e3
+    us = acc / reps
+    capi.check(lib.tp_step_destroy(step))
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    B = batch
+    n_param = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(L))
+    out = []
+
+    def tensor_entry(label, flops, t_us, note):
+        ach = flops / (t_us * 1e-6) / 1e12
+        e = {"kernel": label, "bound": "tensor", "achieved": ach, "peak": tf32_peak or bf16 / 2, "unit": "TFLOP/s",
+             "frac": ach / (tf32_peak or bf16 / 2), "traffic": None, "launch_us": t_us,
+             "peak_source": "measured cuBLAS TF32 8192^3 (this run): the fp32 tensor-core peak north_star names" if tf32_peak
+             else "MEASURED_PEAKS.json bf16_tflops / 2",
+             "tensor_pipe_frac": 3 * ach / bf16,
+             "note": note + "; algorithmic flops 2*M*N*K; the kernel issues 3 bf16 MMAs per product, so its share of the measured bf16 "
+                            f"peak ({bf16:.0f} TFLOP/s, MEASURED_PEAKS.json) is tensor_pipe_frac; launch_us is the in-situ slot "
+                            "(launch gap to the next kernel included)"}
+        out.append(e)
+        return e
+
+    def hbm_entry(label, nbytes, t_us, note):
+        ach = nbytes / (t_us * 1e-6) / 1e9
+        out.append({"kernel": label, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "launch_us": t_us, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                    "note": note})
+
+    i = 0
+    hbm_entry("wide_input_kernel: gather + bf16 hi/lo planes", B * dims[0] * 8 + B * 8, us[i], "latency-bound at this size (3.2 MB)"); i += 1
+    gemms = []
+    for l in range(L - 1):
+        gemms.append(tensor_entry(f"gemm_bx3_kernel fwd{l} {B}x{dims[l + 1]}x{dims[l]} (bias+ReLU+planes epilogue)", 2.0 * B * dims[l] * dims[l + 1],
+                                  us[i], "N,T"))
+        i += 1
+    hbm_entry("wide_head_kernel: classifier + softmax-CE + dlogits + dZ planes", B * dims[L - 1] * 8 + B * 64, us[i], "latency-bound"); i += 1
+    for l in range(L - 2, 0, -1):
+        gemms.append(tensor_entry(f"gemm_bx3_kernel dX{l} {B}x{dims[l]}x{dims[l + 1]} (ReLU-mask + bias-gradient + planes epilogue)",
+                                  2.0 * B * dims[l] * dims[l + 1], us[i], "N,N"))
+        i += 1
+    fl = sum(2.0 * B * dims[l] * dims[l + 1] for l in range(L))
+    gemms.append(tensor_entry(f"gemm_bx3_kernel grouped dW (all {L} weight gradients in one launch)", fl, us[i], "T,N")); i += 1
+    hbm_entry("wide_fold_kernel: bias-gradient partials, results, Adam counters", 4 * 160 * sum(dims[1:]), us[i], "latency-bound"); i += 1
+    hbm_entry("adam_dev_split_kernel: fused optimizer + parameter planes", (28 + 4) * n_param, us[i],
+              "L2-resident state (52 MB < 126 MB L2): reported against HBM peak, so frac may exceed what DRAM alone allows"); i += 1
+    roof = max(gemms, key=lambda e: e["launch_us"])
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        t = tj.get(name, {})
+        if t.get("kernel") and t["kernel"] in roof["kernel"]:
+            roof = dict(roof, traffic=t.get("dram_bytes_per_launch"), traffic_source=t.get("source"))
+    except Exception:
+        pass
+    return roof, out
 
 
 def measure_tf32_peak():
@@ -215,21 +573,18 @@ def measure_tf32_peak():
         return None
 
 
-def kernel_rooflines(cfg_name, cfg, peaks, tf32_peak):
-    """Times the step's main kernels alone (CUDA events on the launching stream, L2-cold operands rotated
-    through a pool larger than L2 where the working set allows) and returns roofline entries."""
-    import taper_b200
+def probe_kernels(peaks, tf32_peak):
+    """Large-size evidence runs of single kernels through the C ABI (BASELINE metric: GEMM % TC-peak, elementwise % HBM)."""
     from taper_b200 import capi, host
-    import ctypes as C
-    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, _ = cfg
     h = host.host_ctx()
     lib = capi.lib
 
-    class HB:                                    # tp_buf helper on the host layer's context
+    class HB:
         def __init__(self, n):
             self.h = C.c_void_p(); self.n = n
             capi.check(lib.tp_buf_alloc(h, n, C.byref(self.h)))
             capi.check(lib.tp_buf_fill(h, self.h, 0.5, n))
+
         def __del__(self):
             lib.tp_buf_release(self.h)
 
@@ -247,65 +602,14 @@ def kernel_rooflines(cfg_name, cfg, peaks, tf32_peak):
     out = []
     hbm = peaks.get("hbm_gbs", 6650.0)
     tc_peak = tf32_peak or peaks.get("bf16_tflops", 1590.0) / 2
-    tc_note = "measured cuBLAS TF32 8192^3 (this run)" if tf32_peak else "bf16 measured / 2 (TF32 nominal ratio)"
-    if kind == "mlp":
-        sizes = arg
-        fin, fout = sizes[0], sizes[1]
-        # rotate over enough operand copies that each launch reads L2-cold data (> 126 MB in total)
-        per = (batch * fin + fout * fin + batch * fout) * 4
-        copies = max(2, min(64, int(160e6 // per) + 1))
-        xs = [HB(batch * fin) for _ in range(copies)]
-        ws = [HB(fout * fin) for _ in range(copies)]
-        ys = [HB(batch * fout) for _ in range(copies)]
-        b = HB(fout)
-        def fwd(i):
-            j = i % copies
-            capi.check(lib.tp_linear_fwd(h, xs[j].h, ws[j].h, b.h, ys[j].h, batch, fin, fout, 1))
-        def bwd(i):
-            j = i % copies
-            capi.check(lib.tp_linear_bwd(h, xs[j].h, ws[j].h, ys[j].h, None, None, ws[(j + 1) % copies].h, None, batch, fin, fout, 0, 0, 0))
-        l0 = host.launches(); t = timeit(fwd, 200); n_l = (host.launches() - l0) / 203
-        fl = 2 * batch * fin * fout
-        out.append({"kernel": f"linear_fwd {batch}x{fin}x{fout} (bias+ReLU epilogue)", "bound": "tensor", "achieved": fl / t / 1e12,
-                    "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None,
-                    "launch_us": t * 1e6, "launches_per_call": n_l, "peak_source": tc_note})
-        l0 = host.launches(); t = timeit(bwd, 200); n_l = (host.launches() - l0) / 203
-        out.append({"kernel": f"linear_bwd dW {fout}x{fin} over batch {batch} (split-K)", "bound": "tensor", "achieved": fl / t / 1e12,
-                    "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None,
-                    "launch_us": t * 1e6, "launches_per_call": n_l, "peak_source": tc_note})
-        del xs, ws, ys
-    else:
-        # CNN configs: the step's heaviest layer = the widest 3x3 conv (conv2 of either model): its im2col (HBM-bound,
-        # 4*(n_in + M*K) algorithmic bytes) and its [M,K]x[K,Cout] GEMM (tensor-bound, 2*M*K*Cout flops)
-        cin, hw_, cout = (32, 28, 32) if kind == "cnn5" else (32, 14, 64)
-        d = capi.ConvDesc(batch, cin, hw_, hw_, cout, 3, 3, 1, 1, 1, 1, 1, 1)
-        M, K = batch * hw_ * hw_, cin * 9
-        x, col, w, y = HB(batch * cin * hw_ * hw_), HB(M * K), HB(K * cout), HB(M * cout)
-        bvec = HB(cout)
-        t = timeit(lambda i: capi.check(lib.tp_conv2d_fwd(h, x.h, w.h, bvec.h, y.h, C.byref(d), 1)), 30)
-        fl = 2 * M * K * cout
-        out.append({"kernel": f"conv2d_relu fwd {batch}x{cin}x{hw_}x{hw_} -> {cout} ch, 3x3: implicit GEMM on tcgen05 (3xTF32), NCHW+bias+ReLU epilogue",
-                    "bound": "tensor", "achieved": fl / t / 1e12, "peak": tc_peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak,
-                    "traffic": None, "launch_us": t * 1e6, "peak_source": tc_note,
-                    "note": f"{(M + 127) // 128} tiles x {K // 32} k-blocks, N = {cout}: bound by the gather warps and per-tile setup, not by the tensor pipe"})
-        t = timeit(lambda i: capi.check(lib.tp_im2col(h, x.h, col.h, C.byref(d))), 30)
-        by = 4 * (batch * cin * hw_ * hw_ + M * K)
-        out.append({"kernel": f"im2col {batch}x{cin}x{hw_}x{hw_} 3x3 -> [{M},{K}] (fallback / full-adjoint path)", "bound": "hbm", "achieved": by / t / 1e9, "peak": hbm,
-                    "unit": "GB/s", "frac": by / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6, "probe": True,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
-        t = timeit(lambda i: capi.check(lib.tp_sgemm_rowmajor(h, 0, 0, M, cout, K, 1.0, col.h, w.h, 0.0, y.h)), 30)
-        fl = 2 * M * K * cout
-        out.append({"kernel": f"conv GEMM [{M},{K}]x[{K},{cout}] on the materialised im2col matrix (fallback / full-adjoint path)", "bound": "tensor", "achieved": fl / t / 1e12, "peak": tc_peak,
-                    "unit": "TFLOP/s", "frac": fl / t / 1e12 / tc_peak, "traffic": None, "launch_us": t * 1e6, "peak_source": tc_note, "probe": True,
-                    "note": f"N = {cout}: streams the {M * K * 4 / 1e6:.0f} MB im2col matrix once, so HBM ({M * K * 4 / t / 1e9:.0f} GB/s) bounds it, not the tensor pipe"})
-        del x, col, w, y, bvec
-    # the operator boundary itself at a tensor-core-sized problem: tp_sgemm_rowmajor 8192^3 (BASELINE metric "GEMM %TC-peak")
+    tc_note = "measured cuBLAS TF32 8192^3 (this run)" if tf32_peak else "bf16 measured / 2"
     try:
         nn_ = 8192
         ga, gb, gc = HB(nn_ * nn_), HB(nn_ * nn_), HB(nn_ * nn_)
         mode0 = C.c_int()
         capi.check(lib.tp_get_gemm_mode(h, C.byref(mode0)))
-        for mode, label in ((2, "1xTF32, 128x256 tiles"), (1, "3xTF32 = fp32-accurate, algorithmic flops")):
+        for mode, label in ((2, "1xTF32, 128x256 tiles"), (1, "3xTF32 = fp32-accurate, algorithmic flops"),
+                            (3, "bf16x3 incl. the two operand-split launches, algorithmic flops")):
             capi.check(lib.tp_set_gemm_mode(h, mode))
             t = timeit(lambda i: capi.check(lib.tp_sgemm_rowmajor(h, 0, 1, nn_, nn_, nn_, 1.0, ga.h, gb.h, 0.0, gc.h)), 5)
             fl = 2.0 * nn_ ** 3
@@ -314,156 +618,53 @@ def kernel_rooflines(cfg_name, cfg, peaks, tf32_peak):
                         "peak_source": tc_note, "probe": True})
         capi.check(lib.tp_set_gemm_mode(h, mode0.value))
         del ga, gb, gc
-    except Exception as e:                       # never let the evidence probe take the bench line down
+    except Exception as e:                       # never let an evidence probe take the bench line down
         out.append({"kernel": "tp_sgemm_rowmajor 8192^3", "error": str(e)})
-    # fused Adam step over a flat arena larger than L2: 28 B/param (p, g, m, v read; p, m, v written)
     n = 48 * 1024 * 1024
     p, g, m, v, hy = HB(n), HB(n), HB(n), HB(n), HB(8)
     capi.check(lib.tp_adam_hyper_init(h, hy.h, 1e-3, 0.9, 0.999, 1e-8, 0.0))
     capi.check(lib.tp_adam_advance(h, hy.h))
-    def adam(i):
-        capi.check(lib.tp_adam_step_dev(h, p.h, g.h, m.h, v.h, hy.h, 1.0, 0, n))
-    t = timeit(adam, 20)
+    t = timeit(lambda i: capi.check(lib.tp_adam_step_dev(h, p.h, g.h, m.h, v.h, hy.h, 1.0, 0, n)), 20)
     out.append({"kernel": f"adam_step {n} params (fused, flat arena)", "bound": "hbm", "achieved": 28 * n / t / 1e9, "peak": hbm,
                 "unit": "GB/s", "frac": 28 * n / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6, "probe": True,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
-    # fused elementwise backward (ReLU backward: dY, X -> dX, 12 B/elem)
-    def relu_bwd(i):
-        capi.check(lib.tp_relu_bwd(h, p.h, g.h, m.h, n, 0))
-    t = timeit(relu_bwd, 20)
+    t = timeit(lambda i: capi.check(lib.tp_relu_bwd(h, p.h, g.h, m.h, n, 0)), 20)
     out.append({"kernel": f"relu_bwd {n} elements", "bound": "hbm", "achieved": 12 * n / t / 1e9, "peak": hbm, "unit": "GB/s",
                 "frac": 12 * n / t / 1e9 / hbm, "traffic": None, "launch_us": t * 1e6, "probe": True,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"})
     return out
 
 
-def run_ours(args, cfg_name, cfg):
+def run_ours(args, name):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    spec_key, (kind, arg), batch, opt_kind, lr, wd, sample_shape, workload = cfg
 
     import taper_b200                      # raises if libtaper_b200.so is missing: there is no fallback
     from taper_b200 import host
     host.set_device(local)
     host.config(conv_full_adjoint=1 if args.full_adjoint else 0, gemm_mode=args.gemm_mode)
-
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    model = host.Model(getattr(host, spec_key), seed=0)
-    tr = host.Trainer(model, opt_kind, lr=lr, weight_decay=wd)
-    if args.no_fused or args.nccl_only:
-        tr.set_use_fused(False)
-    if world > 1:
-        import torch
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(host.nccl_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        tr.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        tr.broadcast_params(0)
-        if not args.nccl_only:
-            # fused step: gradient exchange inside the step kernel over NVLink peer memory.  Every rank must take the same
-            # path, so a rank that cannot map its peers (no P2P / IPC) sends everybody back to the NCCL-in-graph path.
-            ok = 1
-            try:
-                tr.peer_exchange_init(dist)
-            except Exception as e:
-                ok = 0
-                print(f"rank {rank}: peer exchange unavailable ({e}); falling back to the NCCL allreduce", file=sys.stderr)
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                tr.set_use_fused(False)
-
-    # each rank owns a shard: its own resident dataset (weak scaling: batch/GPU fixed)
-    X, Y = synthetic(DATASET_N, sample_shape, 1 + rank)
-    perm = np.random.default_rng(100 + rank).permutation(DATASET_N).astype(np.uint32)
-    tr.load_dataset(X, Y, perm)
-
-    def barrier():
-        host.sync()
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        import torch
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    dist = Dist(world, local)
     sampler = ClockSampler(local) if rank == 0 else None
     windows = []
 
-    # ---- value: dataset resident in HBM, CUDA events on the launching stream ---------------------------
-    last = (0.0, 0.0)
-    for _ in range(max(args.warmup, 3)):
-        tr.step_resident(batch)
-        last = tr.fetch()
-    barrier()
-    e0, e1 = host.Event(), host.Event()
-    l0 = host.launches()
-    w0 = time.perf_counter()
-    e0.record()
-    sched_epoch = 0
-    for i in range(args.steps):
-        if tr.pending() >= 6:
-            last = tr.fetch()
-        tr.step_resident(batch)
-        if cfg_name == "cfg5" and i % EPOCH_STEPS == EPOCH_STEPS - 1:      # StepLR(step 5, gamma 0.8) + optimizer.set_lr (src/train.rs:212-216)
-            sched_epoch += 1
-            tr.set_lr(lr * 0.8 ** (sched_epoch // 5))
-    e1.record()
-    while tr.pending():
-        last = tr.fetch()
-    host.sync()
-    w1 = time.perf_counter()
-    gpu_launches = host.launches() - l0
-    ms = max_over_ranks(e0.elapsed_ms(e1))
-    barrier()
-    windows.append((w0, w1))
-    value = world * batch * args.steps / (ms * 1e-3)
-
-    # ---- e2e: host (pinned) batches through the trainer call; H2D + D2H inside the timed region -----------
-    nbuf = 12
-    pins = [(host.PinnedArray((batch,) + tuple(sample_shape)), host.PinnedArray((batch,))) for _ in range(nbuf)]
-    for j, (px, py) in enumerate(pins):
-        s = (j * batch) % (DATASET_N - batch)
-        px.array[...] = X[s:s + batch]
-        py.array[...] = Y[s:s + batch]
-    for j in range(max(args.warmup, 3)):
-        tr.step_async(pins[j % nbuf][0].array, pins[j % nbuf][1].array, pinned=True)
-        tr.fetch()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        if tr.pending() >= 6:
-            last = tr.fetch()                       # D2H read of {loss, correct} of an earlier step
-        px, py = pins[i % nbuf]
-        tr.step_async(px.array, py.array, pinned=True)
-    while tr.pending():
-        last = tr.fetch()
-    host.sync()
-    t1 = time.perf_counter()
-    e2e_s = max_over_ranks(t1 - t0)
-    barrier()
-    windows.append((t0, t1))
-    e2e_value = world * batch * args.steps / e2e_s
+    check = None
+    if world > 1 and not args.no_dp_check:
+        check = dp_check(name, args, dist, rank, world, with_oracle=True)
+    rec = measure(name, args, dist, rank, world, local, windows, True)
+    subs = []
+    if not args.no_subs and name == PRIMARY:
+        for sub in SUBS:
+            sw = []
+            r = measure(sub, args, dist, rank, world, local, sw, False)
+            if world > 1 and not args.no_dp_check:
+                r["dp_check"] = dp_check(sub, args, dist, rank, world, with_oracle=False)
+            subs.append(r)
     clocks = sampler.stop(windows) if sampler else None
-
     if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
+        dist.close()
         return
 
     peaks = {}
@@ -471,76 +672,50 @@ def run_ours(args, cfg_name, cfg):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tf32_peak = measure_tf32_peak() if world == 1 else None
-    fused = tr.fused_steps() > 0
-    roofs = kernel_rooflines(cfg_name, cfg, peaks, tf32_peak) if world == 1 else []
-    if fused:
-        # The step IS one kernel (tape_step_kernel): its launch duration is the step time measured above with CUDA events.
-        # Algorithmic HBM bytes per launch: the gathered batch rows and labels, every parameter read once,
-        # optimizer state read + written (Adam/AdamW: p, m, v; SGD: p); gradients and activations never need to leave the chip.
-        n_param = sum(arg[i] * arg[i + 1] + arg[i + 1] for i in range(len(arg) - 1))
-        step_bytes = 4 * batch * (arg[0] + 1) + (24 if opt_kind != "sgd" else 8) * n_param
-        step_us = ms / args.steps * 1e3
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(cfg_name, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        fl = mlp_flops(arg, batch)
-        roofline = {"kernel": f"tape_step_kernel ({'-'.join(map(str, arg))}, batch {batch}, {opt_kind}): whole step, one launch",
-                    "bound": "hbm", "achieved": step_bytes / (step_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
-                    "frac": step_bytes / (step_us * 1e-6) / 1e9 / hbm, "traffic": traffic, "launch_us": step_us,
-                    "algorithmic_bytes": step_bytes,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
-                    "note": "latency-bound by construction: 4 dependent phases (fwd GEMM, head, bwd GEMMs, optimizer) of ~1-2 memory "
-                            "round trips each plus 3 grid barriers; at peak HBM rate the step's bytes take < 1 us "
-                            "(per-phase SM-clock breakdown: profiles/)"}
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        roofs = [roofline,
-                 {"kernel": roofline["kernel"], "bound": "tensor", "achieved": fl / (step_us * 1e-6) / 1e12, "peak": tf32_peak,
-                  "unit": "TFLOP/s", "frac": (fl / (step_us * 1e-6) / 1e12 / tf32_peak) if tf32_peak else None, "traffic": traffic,
-                  "launch_us": step_us, "peak_source": "measured cuBLAS TF32 8192^3 (this run)",
-                  "note": f"exact-fp32 FFMA on the CUDA cores (nominal {fp32_peak:.1f} TFLOP/s); the tcgen05 kernels of the tape + graph path "
-                          "follow for comparison"}] + roofs
-    else:
-        # dominant kernel of the step = the one with the largest duration among the step's kernels
-        # ("probe" entries are large-size evidence runs of single kernels, not kernels of this step)
-        roofline = max([r for r in roofs if not r.get("probe") and "error" not in r] or roofs or [None],
-                       key=lambda r: r["launch_us"] if r else 0)
+    kind, arg = CONFIGS[name][1]
+    roofline, kernels = None, []
+    tf32_peak = None
+    if world == 1:
+        tf32_peak = measure_tf32_peak()
+        if kind == "mlp" and not args.no_fused:
+            try:
+                roofline, kernels = plan_profile(name, peaks, tf32_peak)
+            except Exception as e:
+                kernels = [{"kernel": "plan_profile", "error": str(e)}]
+        if not args.no_probes:
+            kernels = kernels + probe_kernels(peaks, tf32_peak)
+        if roofline is None:
+            cands = [k for k in kernels if "error" not in k]
+            roofline = max(cands, key=lambda k: k["launch_us"]) if cands else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sample_batch = batch if kind == "mlp" else 32
-        v, done, threads, dt = time_oracle(cfg, 10 ** 9, 2, sample_batch, budget_s=12.0)
-        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"{done} oracle train steps of batch {sample_batch} in {dt:.1f} s (NumPy/OpenBLAS restatement of the reference tape)"}
-    flops = mlp_flops(arg, batch) if kind == "mlp" else None
+        cores = os.cpu_count() or 1
+        v, done, dt = time_oracle(name, 10 ** 9, 1, cores, budget_s=12.0)
+        v1, d1, t1 = time_oracle(name, 3, 1, 1, budget_s=8.0)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{done} oracle train steps at the config's batch size in {dt:.1f} s, {cores} BLAS threads "
+                         "(NumPy/OpenBLAS restatement of the reference tape, oracle/taper_ref.py)",
+               "single_thread": {"value": v1, "unit": "samples/s", "sample": f"{d1} steps in {t1:.1f} s, 1 BLAS thread"}}
+    flops = mlp_flops(arg, CONFIGS[name][2]) if kind == "mlp" else None
     out = {
-        "metric": "MNIST samples/sec (fwd+bwd+step)", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "metric": "MNIST samples/sec (fwd+bwd+step)", "value": rec["value"], "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": rec["warmup"], "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "name": cfg_name, "batch_per_gpu": batch, "global_batch": batch * world,
-                   "optimizer": opt_kind, "lr": lr, "weight_decay": wd, "parallelism": f"dp{world}",
-                   "gemm_mode": {0: "fp32 FFMA", 1: "3xTF32 tcgen05 (fp32-accurate)", 2: "1xTF32 tcgen05"}[args.gemm_mode],
-                   "conv_adjoint": "full" if args.full_adjoint else "strict_reference (SURVEY A1)",
-                   "l2_policy": f"inputs larger than L2: every step gathers a fresh batch from a {DATASET_N}x{int(np.prod(sample_shape))} "
-                                "fp32 resident dataset (188 MB); parameters/optimizer state are the step's own working set",
-                   "step_path": ("device tape: one persistent kernel per step (grid barrier between phases, PDL between steps; exact fp32)"
-                                 + ("; gradient exchange in-kernel over NVLink peer memory" if world > 1 else "")) if fused
-                                else ("tape + CUDA graph, one kernel per op" + ("; NCCL allreduce in the graph" if world > 1 else "")),
-                   "cuda_graph": not fused, "last_step": {"loss": last[0], "correct": last[1]}},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(batch * (np.prod(sample_shape) + 1) * 4),
-                "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / args.steps * 1e3,
-                "timing": "host wall clock, sync on both sides; pinned host batches, H2D on a copy stream overlapping the previous step"},
-        "gpu_launches": int(gpu_launches), "launches_per_step": gpu_launches / args.steps,
-        "clocks": clocks, "roofline": roofline, "kernels": roofs, "cpu_baseline": cpu,
+        "config": rec["config"],
+        "e2e": rec["e2e"],
+        "gpu_launches": rec["gpu_launches"], "launches_per_step": rec["launches_per_step"],
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "impl_details": {k: rec[k] for k in ("step_path", "gemm_math", "conv_adjoint", "last_step")},
+        "dp_check": check,
+        "sub_records": [{k: r[k] for k in ("config", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "launches_per_step", "step_path",
+                                            "gemm_math", "conv_adjoint", "last_step") if k in r} | ({"dp_check": r["dp_check"]} if "dp_check" in r else {})
+                        for r in subs],
+        "kernels": kernels,
         "step_gemm_flops": flops,
-        "step_tensor_frac": (flops / (ms / args.steps * 1e-3) / 1e12 / (tf32_peak or 1e9)) if (flops and tf32_peak) else None,
+        "step_tensor_frac": (flops / (rec["ms_per_step"] * 1e-3) / 1e12 / tf32_peak) if (flops and tf32_peak) else None,
     }
     print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    dist.close()
 
 
 def main():
@@ -549,23 +724,24 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
-    ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2])
+    ap.add_argument("--config", default=PRIMARY, choices=sorted(CONFIGS))
+    ap.add_argument("--gemm-mode", type=int, default=1, choices=[0, 1, 2, 3],
+                    help="GEMM math of the tape + graph path (the wide plan always runs bf16x3, the persistent kernel exact fp32)")
     ap.add_argument("--full-adjoint", action="store_true", help="CNN: compute conv dW/dX (the reference does not, SURVEY A1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nccl-only", action="store_true", help="N>1: keep the NCCL allreduce (tape + CUDA-graph path) instead of the "
-                                                             "in-kernel NVLink peer-memory exchange of the fused step")
-    ap.add_argument("--no-fused", action="store_true", help="run the tape + CUDA-graph path even where the fused device step qualifies")
+    ap.add_argument("--no-subs", action="store_true", help="skip the sub-records (configs[4], configs[1])")
+    ap.add_argument("--no-probes", action="store_true", help="skip the large single-kernel evidence probes")
+    ap.add_argument("--no-dp-check", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="N>1, small models: keep the NCCL allreduce (tape + CUDA-graph path) instead "
+                                                             "of the in-kernel NVLink peer-memory exchange of the persistent step")
+    ap.add_argument("--no-fused", action="store_true", help="run the tape + CUDA-graph path even where a fused device step qualifies")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
     if args.steps is None:
-        args.steps = (20000 if args.config in ("cfg1", "cfg2", "example_mlp") else 300) if args.impl == "ours" else 200
-        if args.config == "cfg5" and args.impl == "reference":
-            args.steps = 10
+        args.steps = 300 if args.impl == "ours" else 20
     if args.impl == "reference":
-        run_reference(args, args.config, cfg)
+        run_reference(args, args.config)
     else:
-        run_ours(args, args.config, cfg)
+        run_ours(args, args.config)
 
 
 if __name__ == "__main__":

@@ -74,7 +74,11 @@ int tp_comm_unique_id(void* out128) {
 
 int tp_comm_init(tp_ctx* ctx, int rank, int world, const void* unique_id128) {
     TP_CHECK_ARG(ctx && unique_id128 && world >= 1 && rank >= 0 && rank < world, "tp_comm_init: bad arguments");
-    TP_CHECK_ARG(!ctx->nccl_comm, "tp_comm_init: communicator already initialised");
+    if (ctx->nccl_comm) {
+        // one communicator per context: a second trainer on the same thread joins the one that exists
+        TP_CHECK_ARG(ctx->rank == rank && ctx->world == world, "tp_comm_init: communicator already initialised as rank %d of %d", ctx->rank, ctx->world);
+        return TP_OK;
+    }
     int rc = need_api();
     if (rc) return rc;
     cudaSetDevice(ctx->device);

@@ -96,6 +96,7 @@ void MNISTDataset::normalize(float mean, float std) {
 }
 
 // ---- pinned prefetch pipeline ---------------------------------------------------------------------------------------------------
+// Worker threads live as long as the loader (parked between epochs): starting an epoch costs a notify, not a thread spawn.
 struct DataLoader::Pipe {
     static constexpr int kSlots = 12;                // > the trainer's result ring (8) + its staging depth
     struct Slot {
@@ -110,10 +111,63 @@ struct DataLoader::Pipe {
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv;
-    bool stop = false;
+    bool quit = false;
+    uint64_t gen = 0;                                // epoch generation the workers should be running
+    uint64_t aborted = 0;                            // generations <= this one are cancelled
+    int finished = 0;                                // workers done with generation `gen`
+    // epoch parameters (written under mu before gen is bumped)
     bool u8 = false;
-    size_t n_batches = 0, next_consume = 0;
+    size_t n_batches = 0, next_consume = 0, bs = 0, cols = 0, n = 0;
+    const uint32_t* idx = nullptr;
+    const MNISTDataset* ds = nullptr;
+
+    void worker(int w, int T) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || gen != seen; });
+                if (quit) return;
+                seen = gen;
+            }
+            for (size_t b = (size_t)w; b < n_batches; b += (size_t)T) {
+                Slot& s = slots[b % kSlots];
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return quit || aborted >= seen || s.turn == (long)b; });
+                    if (quit || aborted >= seen) break;
+                }
+                const size_t first = b * bs, count = std::min(bs, n - first);
+                if (u8) {
+                    uint8_t* dst = static_cast<uint8_t*>(s.img);
+                    for (size_t i = 0; i < count; ++i) std::memcpy(dst + i * cols, &ds->images_u8[(size_t)idx[first + i] * cols], cols);
+                } else {
+                    float* dst = static_cast<float*>(s.img);
+                    for (size_t i = 0; i < count; ++i)
+                        std::memcpy(dst + i * cols, &ds->images[(size_t)idx[first + i] * cols], cols * sizeof(float));
+                }
+                for (size_t i = 0; i < count; ++i) s.lab[i] = ds->labels[idx[first + i]];
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    s.batch = count;
+                    s.ready = (long)b;
+                }
+                cv.notify_all();
+            }
+            {
+                std::lock_guard<std::mutex> g(mu);
+                finished++;
+            }
+            cv.notify_all();
+        }
+    }
     ~Pipe() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        for (auto& t : workers) t.join();
         for (auto& s : slots) {
             if (s.img) tp_host_free_pinned(s.img);
             if (s.lab) tp_host_free_pinned(s.lab);
@@ -160,14 +214,12 @@ bool DataLoader::next(std::vector<float>& images, std::vector<float>& labels, si
 }
 
 void DataLoader::stop_prefetch() {
-    if (!pipe_) return;
-    {
-        std::lock_guard<std::mutex> g(pipe_->mu);
-        pipe_->stop = true;
-    }
-    pipe_->cv.notify_all();
-    for (auto& t : pipe_->workers) t.join();
-    pipe_->workers.clear();
+    if (!pipe_ || pipe_->gen == 0) return;
+    Pipe& p = *pipe_;
+    std::unique_lock<std::mutex> lk(p.mu);
+    p.aborted = p.gen;                               // cancel whatever is left of the current epoch
+    p.cv.notify_all();
+    p.cv.wait(lk, [&] { return p.finished == (int)p.workers.size(); });
 }
 
 void DataLoader::start_prefetch(bool u8, size_t max_batches) {
@@ -191,47 +243,26 @@ void DataLoader::start_prefetch(bool u8, size_t max_batches) {
         }
         p.img_bytes = need;
     }
-    p.stop = false;
-    p.u8 = u8;
+    if (p.workers.empty()) {
+        unsigned hw = std::thread::hardware_concurrency();
+        const int T = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;
+        for (int w = 0; w < T; ++w) p.workers.emplace_back([&p, w, T]() { p.worker(w, T); });
+    }
     size_t nb = num_batches();
     if (max_batches && max_batches < nb) nb = max_batches;
-    p.n_batches = nb;
-    p.next_consume = 0;
-    for (int i = 0; i < Pipe::kSlots; ++i) { p.slots[i].turn = i; p.slots[i].ready = -1; }
-    unsigned hw = std::thread::hardware_concurrency();
-    int T = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;
-    if ((size_t)T > nb) T = nb ? (int)nb : 1;
-    const MNISTDataset* ds = dataset_.get();
-    const uint32_t* idx = indices_.data();
-    const size_t n = dataset_->len(), bs = batch_size_;
-    for (int w = 0; w < T; ++w) {
-        p.workers.emplace_back([&p, ds, idx, n, bs, cols, u8, w, T]() {
-            for (size_t b = (size_t)w; b < p.n_batches; b += (size_t)T) {
-                Pipe::Slot& s = p.slots[b % Pipe::kSlots];
-                {
-                    std::unique_lock<std::mutex> lk(p.mu);
-                    p.cv.wait(lk, [&] { return p.stop || s.turn == (long)b; });
-                    if (p.stop) return;
-                }
-                const size_t first = b * bs, count = std::min(bs, n - first);
-                if (u8) {
-                    uint8_t* dst = static_cast<uint8_t*>(s.img);
-                    for (size_t i = 0; i < count; ++i) std::memcpy(dst + i * cols, &ds->images_u8[(size_t)idx[first + i] * cols], cols);
-                } else {
-                    float* dst = static_cast<float*>(s.img);
-                    for (size_t i = 0; i < count; ++i)
-                        std::memcpy(dst + i * cols, &ds->images[(size_t)idx[first + i] * cols], cols * sizeof(float));
-                }
-                for (size_t i = 0; i < count; ++i) s.lab[i] = ds->labels[idx[first + i]];
-                {
-                    std::lock_guard<std::mutex> g(p.mu);
-                    s.batch = count;
-                    s.ready = (long)b;
-                }
-                p.cv.notify_all();
-            }
-        });
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        p.u8 = u8;
+        p.n_batches = nb;
+        p.next_consume = 0;
+        p.bs = batch_size_; p.cols = cols; p.n = dataset_->len();
+        p.idx = indices_.data();
+        p.ds = dataset_.get();
+        for (int i = 0; i < Pipe::kSlots; ++i) { p.slots[i].turn = i; p.slots[i].ready = -1; }
+        p.finished = 0;
+        p.gen++;
     }
+    p.cv.notify_all();
 }
 
 bool DataLoader::next_pinned(Batch& out) {

@@ -19,7 +19,11 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["steps"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "configs[1]" in d["config"]["workload"]
+    assert "configs[3]" in d["config"]["workload"]            # the configuration the metric is quoted on
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("cfg4", 1)    # the reference arm prints the very config object our arm prints
+    assert d["cpu_baseline"]["single_thread"]["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
