@@ -113,7 +113,7 @@ def main():
     us = ms.value * 1e3 / a.iters
     if rank != 0:
         check(lib.tp_step_set_profile(step, 1))
-        for _ in range(3):
+        for _ in range(4 if lib.tp_step_is_wide(step) == 1 else 3):      # every rank must run the same number of steps
             run()
         ctx.sync()
         dist.barrier()
@@ -130,7 +130,7 @@ def main():
         L = len(dims) - 1
         names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head"]
         names += [f"dX{l}" for l in range(L - 2, 0, -1)]
-        names += ["dW (all)", "fold", "optimizer"]
+        names += ["dW (all)", "fold", "optimizer" if world == 1 else "exchange+optimizer"]
         buf = np.zeros(32, np.int64)
         slots = C.c_int()
         check(lib.tp_step_read_profile(step, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(slots)))

@@ -375,7 +375,9 @@ struct Trainer::Impl {
             d.data_parallel = world > 1 ? 1 : 0;
             // a step that qualifies on paper but cannot be built on this device (no cooperative launch, shared memory) simply
             // stays on the tape + graph path; with an exchange every rank must agree, so there a failure is an error
-            int rc = tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), (world > 1 && kind == 1) ? xchg : nullptr, &st);
+            // data-parallel: the persistent kernel needs the connected window; the plan uses it when there is one (two-phase
+            // peer-memory exchange fused with the optimizer) and the NCCL communicator otherwise
+            int rc = tp_step_create(ctx(), &d, b[0], b[1], b[2], b[3], b[4], result.buf(), (world > 1 && xchg_connected) ? xchg : nullptr, &st);
             if (rc != TP_OK) {
                 if (world > 1) check(rc);
                 std::fprintf(stderr, "taper_b200: fused step unavailable (%s); using the tape + CUDA-graph path\n", tp_last_error());

@@ -410,6 +410,185 @@ wide_fold_kernel(const __grid_constant__ FoldArgs a) {
     }
 }
 
+// ---- data-parallel: two-phase gradient exchange over NVLink peer memory + optimizer, one kernel -------------------------
+// Every rank owns a window (tp_xchg_*): flags + slot rows, mapped into every peer.  The arena is cut into `world` slices and
+// every slice into gridDim.x chunks; CTA c serves chunk c of every slice and only ever waits for CTA c of the other ranks
+// (no grid-wide wait, no co-residency assumption):
+//   A  push my gradient chunk of slice j into rank j's window (row = my rank), then raise flag1[me][c] there   (reduce-scatter)
+//   B  wait for flag1[q][c] of every q, sum the world's contributions to MY slice in rank order, push the reduced chunk
+//      into every rank's result row, raise flag2[me][c] there                                                  (all-gather)
+//   C  wait for flag2[q][c] of every q, apply SGD / Adam / AdamW to chunk c of every slice and rewrite the bf16 planes
+// Per rank 2 * (world-1)/world * arena bytes cross NVLink (one-shot pushing of whole arenas would be (world-1) * arena);
+// each slice is summed by exactly one rank in rank order, so replicas stay bit-identical.  Double-buffered by step parity.
+constexpr int kMaxWorld = 8;
+constexpr long long kPeerSpinLimit = 40000000000LL;            // ~20 s: a peer that never arrives must not hang this GPU for ever
+struct XchgArgs {
+    float* P; const float* G; float* M; float* V; const float* hyper;
+    uint16_t* hi; uint16_t* lo;
+    long long arena4, slice4, chunk4;    // float4 counts: arena, per slice, per (slice, chunk)
+    long long row;                       // floats between the rows of a slot array
+    int opt_kind;
+    float sgd_lr, grad_scale;
+    int world, rank, items;
+    unsigned int seq;
+    const unsigned int* my_flags;        // [world][items]: flag1 at [q][c], flag2 at [q][gridDim.x + c]
+    float* my_slots;                     // this parity: [world][row]; row q = {recv from q: slice4*4 floats, result slice q: slice4*4}
+    unsigned int* peer_flags[kMaxWorld];
+    float* peer_slots[kMaxWorld];
+    int* err;
+    unsigned long long* stamp;
+};
+
+struct AdamArgsW {
+    float step_size, beta1, beta2, eps, weight_decay, grad_scale, decay_factor;
+    int decoupled;
+};
+// identical to optim.cu's adam_elem (expression order follows src/optim.rs:93-110; -fmad=false)
+__device__ __forceinline__ void adam_elem_w(float& p, float g, float& m, float& v, const AdamArgsW& a) {
+    if (a.decoupled) p *= a.decay_factor;
+    if (a.grad_scale != 1.0f) g *= a.grad_scale;
+    float gg = g + a.weight_decay * p;
+    m = a.beta1 * m + (1.0f - a.beta1) * gg;
+    v = a.beta2 * v + (1.0f - a.beta2) * gg * gg;
+    p -= a.step_size * m / (sqrtf(v) + a.eps);
+}
+
+__device__ __forceinline__ bool wait_flags(const XchgArgs& a, int flag_index) {
+    const int t = threadIdx.x;
+    if (t < a.world && t != a.rank) {
+        const unsigned int* f = a.my_flags + (size_t)t * a.items + flag_index;
+        unsigned int cur;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(f) : "memory");
+            if ((int)(cur - a.seq) < 0 && clock64() - t0 > kPeerSpinLimit) { atomicExch(a.err, 3); break; }
+        } while ((int)(cur - a.seq) < 0);
+    }
+    __syncthreads();
+    return __ldcg(a.err) < 2;
+}
+
+__device__ __forceinline__ void raise_flags(const XchgArgs& a, int flag_index) {
+    __syncthreads();                     // the CTA's data stores are ordered before the release below
+    const int t = threadIdx.x;
+    if (t < a.world && t != a.rank)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.peer_flags[t] + (size_t)a.rank * a.items + flag_index), "r"(a.seq) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    stamp_now(a.stamp);
+    const int t = threadIdx.x, c = blockIdx.x, C_ = gridDim.x;
+    const long long c0 = (long long)c * a.chunk4;
+    const float4* G4 = reinterpret_cast<const float4*>(a.G);
+    auto chunk_len = [&](int q) {        // float4 of chunk c that exist in slice q
+        const long long s_len = min(a.slice4, a.arena4 - (long long)q * a.slice4);
+        long long n = min(a.chunk4, s_len - c0);
+        return n > 0 ? n : 0;
+    };
+    // ---- A: my contributions to the other ranks' slices ----
+    for (int j = 0; j < a.world; ++j) {
+        if (j == a.rank) continue;
+        const long long n = chunk_len(j);
+        const float4* src = G4 + (long long)j * a.slice4 + c0;
+        float4* dst = reinterpret_cast<float4*>(a.peer_slots[j] + (long long)a.rank * a.row) + c0;
+        for (long long i0 = t; i0 < n; i0 += kThreads * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i0 + u * kThreads < n) v[u] = __ldcg(src + i0 + u * kThreads);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i0 + u * kThreads < n) dst[i0 + u * kThreads] = v[u];
+        }
+    }
+    raise_flags(a, c);
+    // ---- B: reduce my slice in rank order, hand the result to everybody ----
+    if (!wait_flags(a, c)) return;       // a peer never arrived: its slot is stale, apply nothing
+    {
+        const long long n = chunk_len(a.rank);
+        const long long res_off = a.slice4;                    // result area of a row starts after its recv area
+        for (long long i0 = t; i0 < n; i0 += kThreads * 2) {                 // two output vectors x world loads in flight per thread
+            float4 q[2][kMaxWorld];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long i = i0 + u * kThreads;
+#pragma unroll
+                for (int r = 0; r < kMaxWorld; ++r)
+                    if (r < a.world && i < n)
+                        q[u][r] = (r == a.rank) ? __ldcg(G4 + (long long)a.rank * a.slice4 + c0 + i)
+                                                : __ldcg(reinterpret_cast<const float4*>(a.my_slots + (long long)r * a.row) + c0 + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long i = i0 + u * kThreads;
+                if (i >= n) continue;
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < kMaxWorld; ++r)                                // rank order on every rank: one rank sums a slice
+                    if (r < a.world) { sum.x += q[u][r].x; sum.y += q[u][r].y; sum.z += q[u][r].z; sum.w += q[u][r].w; }
+#pragma unroll
+                for (int r = 0; r < kMaxWorld; ++r)
+                    if (r < a.world) {
+                        float* base = (r == a.rank) ? a.my_slots : a.peer_slots[r];
+                        reinterpret_cast<float4*>(base + (long long)a.rank * a.row)[res_off + c0 + i] = sum;
+                    }
+            }
+        }
+    }
+    raise_flags(a, C_ + c);
+    // ---- C: optimizer on chunk c of every slice ----
+    if (!wait_flags(a, C_ + c)) return;
+    AdamArgsW aa{};
+    if (a.opt_kind != 0) {
+        const float* h = a.hyper;
+        const int decoupled = a.opt_kind == 2;
+        aa.step_size = h[H_SS]; aa.beta1 = h[H_B1]; aa.beta2 = h[H_B2]; aa.eps = h[H_EPS];
+        aa.weight_decay = decoupled ? 0.0f : h[H_WD];
+        aa.grad_scale = a.grad_scale;
+        aa.decay_factor = h[H_DECAY];
+        aa.decoupled = (decoupled && h[H_WD] > 0.0f) ? 1 : 0;
+    }
+    float4* P4 = reinterpret_cast<float4*>(a.P);
+    float4* M4 = reinterpret_cast<float4*>(a.M);
+    float4* V4 = reinterpret_cast<float4*>(a.V);
+    for (int q = 0; q < a.world; ++q) {
+        const long long n = chunk_len(q);
+        const float4* res = reinterpret_cast<const float4*>(a.my_slots + (long long)q * a.row) + a.slice4 + c0;
+        const long long e0 = (long long)q * a.slice4 + c0;
+        for (long long i0 = t; i0 < n; i0 += kThreads * 4) {                 // four vectors (gradient, p, m, v) in flight per thread
+            float4 gg[4], pp[4], mm[4], vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long i = i0 + u * kThreads;
+                if (i < n) {
+                    gg[u] = __ldcg(res + i);
+                    pp[u] = P4[e0 + i];
+                    if (a.opt_kind != 0) { mm[u] = M4[e0 + i]; vv[u] = V4[e0 + i]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long i = i0 + u * kThreads;
+                if (i >= n) continue;
+                if (a.opt_kind == 0) {
+                    if (a.grad_scale != 1.0f) { gg[u].x *= a.grad_scale; gg[u].y *= a.grad_scale; gg[u].z *= a.grad_scale; gg[u].w *= a.grad_scale; }
+                    pp[u].x -= a.sgd_lr * gg[u].x; pp[u].y -= a.sgd_lr * gg[u].y;                                      // src/optim.rs:29
+                    pp[u].z -= a.sgd_lr * gg[u].z; pp[u].w -= a.sgd_lr * gg[u].w;
+                } else {
+                    adam_elem_w(pp[u].x, gg[u].x, mm[u].x, vv[u].x, aa);
+                    adam_elem_w(pp[u].y, gg[u].y, mm[u].y, vv[u].y, aa);
+                    adam_elem_w(pp[u].z, gg[u].z, mm[u].z, vv[u].z, aa);
+                    adam_elem_w(pp[u].w, gg[u].w, mm[u].w, vv[u].w, aa);
+                    M4[e0 + i] = mm[u]; V4[e0 + i] = vv[u];
+                }
+                P4[e0 + i] = pp[u];
+                split_store4(a.hi + 4 * (e0 + i), a.lo + 4 * (e0 + i), pp[u].x, pp[u].y, pp[u].z, pp[u].w);
+            }
+        }
+    }
+}
+
 template <typename Kern, typename Arg>
 int launch_pdl(tp_ctx* ctx, Kern kern, dim3 grid, size_t smem, const Arg& arg, bool pdl) {
     cudaLaunchConfig_t cfg = {};
@@ -430,6 +609,15 @@ int launch_pdl(tp_ctx* ctx, Kern kern, dim3 grid, size_t smem, const Arg& arg, b
 }  // namespace
 
 namespace tp {
+
+// what the plan needs to know about a connected tp_xchg window (filled by tape_step.cu, where the type lives)
+struct WideXchg {
+    int rank = 0, world = 1, items = 0;
+    size_t arena_len = 0, row = 0, slots_off = 0;
+    unsigned char* window = nullptr;
+    unsigned char* peers[8] = {};
+    unsigned int seq = 0;            // flag value of this run
+};
 
 struct WidePlan {
     tp_ctx* ctx = nullptr;
@@ -700,7 +888,7 @@ void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid) {
 }
 
 int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const int* perm, int* cursor, int n_perm, int cursor_value,
-             float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq) {
+             float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq, const WideXchg* xc) {
     tp_ctx* ctx = w->ctx;
     const tp_step_desc& d = w->d;
     const int L = d.n_layers, B = d.batch;
@@ -763,6 +951,31 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
     fa.cursor_delta = B; fa.cursor_mod = n_perm > 0 ? n_perm : 1;
     rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold_grid), 0, fa, pdl);
     if (rc) return rc;
+    if (xc) {
+        // allreduce + optimizer as one kernel over NVLink peer memory (reduce-scatter, all-gather, update)
+        const size_t par = xc->seq & 1u;
+        XchgArgs xa{};
+        xa.P = w->P; xa.G = w->G; xa.M = w->M; xa.V = w->V; xa.hyper = w->hyper;
+        xa.hi = w->w_split; xa.lo = w->w_split + w->arena_plane;
+        xa.arena4 = d.arena_len / 4;
+        xa.slice4 = (xa.arena4 + xc->world - 1) / xc->world;
+        int grid = 4 * ctx->sm_count < xc->items / 2 ? 4 * ctx->sm_count : xc->items / 2;      // latency-bound: four CTAs per SM
+        if ((long long)grid > xa.slice4) grid = (int)xa.slice4;
+        xa.chunk4 = (xa.slice4 + grid - 1) / grid;
+        xa.row = (long long)xc->row;
+        xa.opt_kind = d.optimizer; xa.sgd_lr = sgd_lr; xa.grad_scale = grad_scale;
+        xa.world = xc->world; xa.rank = xc->rank; xa.items = xc->items; xa.seq = xc->seq;
+        xa.my_flags = reinterpret_cast<const unsigned int*>(xc->window);
+        xa.my_slots = reinterpret_cast<float*>(xc->window + xc->slots_off) + par * xc->world * xc->row;
+        for (int r = 0; r < xc->world; ++r) {
+            xa.peer_flags[r] = reinterpret_cast<unsigned int*>(xc->peers[r]);
+            xa.peer_slots[r] = reinterpret_cast<float*>(xc->peers[r] + xc->slots_off) + par * xc->world * xc->row;
+        }
+        xa.err = ctx->dev_error;
+        xa.stamp = next_stamp();
+        w->runs++;
+        return launch_pdl(ctx, wide_xchg_opt_kernel, dim3(grid), 0, xa, pdl);
+    }
     if (d.data_parallel && ctx->world > 1 && ctx->nccl_comm) {
         // sum of the per-rank mean gradients; the optimizer folds 1 / world (grad_scale)
         tp_buf view;

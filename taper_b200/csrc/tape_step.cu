@@ -767,14 +767,22 @@ int wide_refresh(WidePlan* w);
 void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid);
 int wide_set_profile(WidePlan* w, int on);
 int wide_read_profile(WidePlan* w, long long* out, size_t cap, int* slots);
+struct WideXchg {
+    int rank = 0, world = 1, items = 0;
+    size_t arena_len = 0, row = 0, slots_off = 0;
+    unsigned char* window = nullptr;
+    unsigned char* peers[8] = {};
+    unsigned int seq = 0;
+};
 int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const int* perm, int* cursor, int n_perm, int cursor_value,
-             float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq);
+             float sgd_lr, float grad_scale, float* result_host, unsigned int result_seq, const WideXchg* xc);
 }  // namespace tp
 
 struct tp_xchg {
     tp_ctx* ctx = nullptr;
     int rank = 0, world = 1;
     size_t arena_len = 0;
+    size_t row = 0;                      // floats per slot row: arena_len + 16 (the wide plan packs {recv, result} = 2 slices per row)
     int items = 0;                       // flags per source rank (>= optimizer-phase items of any step using this window)
     // window: [flags: world x items u32][slots: 2 parities x world source ranks x arena_len f32]
     unsigned char* window = nullptr;
@@ -800,6 +808,20 @@ struct tp_step {
     long long* prof = nullptr;
     tp::WidePlan* wide = nullptr;    // non-NULL: this step is the multi-kernel tcgen05 plan (step_wide.cu), not the persistent kernel
 };
+
+namespace {
+// the window as the wide plan sees it; seq is the flag value of the run about to be launched
+bool wide_xchg_of(const tp_step* s, tp::WideXchg* xc) {
+    const tp_xchg* x = s->xchg;
+    if (!x) return false;
+    xc->rank = x->rank; xc->world = x->world; xc->items = x->items;
+    xc->arena_len = x->arena_len; xc->row = x->row; xc->slots_off = x->slots_off;
+    xc->window = x->window;
+    for (int r = 0; r < x->world && r < 8; ++r) xc->peers[r] = x->peers[r];
+    xc->seq = x->seq + 1;
+    return true;
+}
+}  // namespace
 
 namespace {
 
@@ -1058,11 +1080,12 @@ int tp_step_create(tp_ctx* ctx, const tp_step_desc* desc, tp_buf* params, tp_buf
     s->p = params; s->g = grads; s->m = m; s->v = v; s->hyper = hyper; s->result = result;
     for (tp_buf* b : {params, grads, m, v, hyper, result}) if (b) tp_buf_retain(b);
     if (kind == 2) {
-        // wide model: a plan of tcgen05 kernels (step_wide.cu); a data-parallel run sums the gradient arena with the context's
-        // NCCL communicator between the plan's fold and optimizer kernels (the peer-memory window is not used)
+        // wide model: a plan of tcgen05 kernels (step_wide.cu); a data-parallel run exchanges gradients through the peer-memory
+        // window if one is given (two-phase, fused with the optimizer), else sums the arena with the context's NCCL communicator
         int rc = tp::wide_create(ctx, desc, params->ptr, grads->ptr, m ? m->ptr : nullptr, v ? v->ptr : nullptr, hyper ? hyper->ptr : nullptr,
                                  result->ptr, &s->wide);
         if (rc != TP_OK) { tp_step_destroy(s); return rc; }
+        s->xchg = xchg;                  // connected window: exchange + optimizer as one peer-memory kernel; NULL: NCCL
         *out = s;
         return TP_OK;
     }
@@ -1142,9 +1165,13 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
             TP_NEED(x, (size_t)s->desc.batch * in, "x"); TP_NEED(labels, s->desc.batch, "labels");
         }
         TP_CHECK_ARG(!((uintptr_t)x->ptr & 15), "tp_step_run: input rows must be 16-byte aligned");
-        return tp::wide_run(s->wide, x->ptr, 0, labels->ptr, perm_i32 ? (const int*)perm_i32->ptr : nullptr,
-                            perm_i32 ? (int*)cursor_i32->ptr : nullptr, perm_i32 ? n_perm : 0, cursor_value, sgd_lr, grad_scale, result_host,
-                            result_seq);
+        tp::WideXchg xc;
+        const bool have_x = wide_xchg_of(s, &xc);
+        int rc = tp::wide_run(s->wide, x->ptr, 0, labels->ptr, perm_i32 ? (const int*)perm_i32->ptr : nullptr,
+                              perm_i32 ? (int*)cursor_i32->ptr : nullptr, perm_i32 ? n_perm : 0, cursor_value, sgd_lr, grad_scale, result_host,
+                              result_seq, have_x ? &xc : nullptr);
+        if (rc == TP_OK && have_x) s->xchg->seq += 1;
+        return rc;
     }
     StepParams p = s->params;
     if (perm_i32) {
@@ -1170,12 +1197,12 @@ int tp_step_run(tp_ctx* ctx, tp_step* s, const tp_buf* x, const tp_buf* labels, 
         const unsigned int seq = x->seq + 1;
         const size_t par = seq & 1u;
         p.world = x->world; p.rank = x->rank; p.xseq = seq;
-        p.x_items = x->items; p.x_arena = (long long)x->arena_len;
+        p.x_items = x->items; p.x_arena = (long long)x->row;
         p.my_flags = reinterpret_cast<unsigned int*>(x->window);
-        p.my_slots = reinterpret_cast<const float*>(x->window + x->slots_off) + par * x->world * x->arena_len;
+        p.my_slots = reinterpret_cast<const float*>(x->window + x->slots_off) + par * x->world * x->row;
         for (int r = 0; r < x->world; ++r) {
             p.peer_flags[r] = reinterpret_cast<unsigned int*>(x->peers[r]) + (size_t)x->rank * x->items;
-            p.peer_slot[r] = reinterpret_cast<float*>(x->peers[r] + x->slots_off) + (par * x->world + x->rank) * x->arena_len;
+            p.peer_slot[r] = reinterpret_cast<float*>(x->peers[r] + x->slots_off) + (par * x->world + x->rank) * x->row;
         }
     }
     cudaSetDevice(ctx->device);
@@ -1225,9 +1252,13 @@ int tp_step_run_u8(tp_ctx* ctx, tp_step* s, const tp_buf* x_u8, const tp_buf* la
     TP_NEED(x_u8, (rows * in + 3) / 4, "x_u8"); TP_NEED(labels, rows, "labels");
     if (perm_i32) { TP_NEED(perm_i32, n_perm, "perm"); TP_NEED(cursor_i32, 1, "cursor"); }
     TP_CHECK_ARG(!((uintptr_t)x_u8->ptr & 15), "tp_step_run_u8: input rows must be 16-byte aligned");
-    return tp::wide_run(s->wide, x_u8->ptr, 1, labels->ptr, perm_i32 ? (const int*)perm_i32->ptr : nullptr,
-                        perm_i32 ? (int*)cursor_i32->ptr : nullptr, perm_i32 ? n_perm : 0, cursor_value, sgd_lr, grad_scale, result_host,
-                        result_seq);
+    tp::WideXchg xc;
+    const bool have_x = wide_xchg_of(s, &xc);
+    int rc = tp::wide_run(s->wide, x_u8->ptr, 1, labels->ptr, perm_i32 ? (const int*)perm_i32->ptr : nullptr,
+                          perm_i32 ? (int*)cursor_i32->ptr : nullptr, perm_i32 ? n_perm : 0, cursor_value, sgd_lr, grad_scale, result_host,
+                          result_seq, have_x ? &xc : nullptr);
+    if (rc == TP_OK && have_x) s->xchg->seq += 1;
+    return rc;
 }
 
 int tp_step_is_wide(const tp_step* s) { return s && s->wide ? 1 : 0; }
@@ -1243,10 +1274,11 @@ int tp_xchg_create(tp_ctx* ctx, size_t arena_len, int rank, int world, tp_xchg**
     cudaSetDevice(ctx->device);
     tp_xchg* x = new tp_xchg();
     x->ctx = ctx; x->rank = rank; x->world = world; x->arena_len = arena_len;
+    x->row = arena_len + 16;
     x->items = (int)(arena_len / 4 / kThreads) + 4 * TP_STEP_MAX_LAYERS + 8;      // one flag per 256-float4 optimizer slice
     const size_t flags = ((size_t)world * x->items * sizeof(unsigned int) + 255) & ~(size_t)255;
     x->slots_off = flags;
-    x->bytes = flags + 2 * (size_t)world * arena_len * sizeof(float);
+    x->bytes = flags + 2 * (size_t)world * x->row * sizeof(float);
     if (cudaMalloc((void**)&x->window, x->bytes) != cudaSuccess) {       // plain cudaMalloc: cudaIpcGetMemHandle needs an allocation base
         cudaGetLastError();
         tp::set_error("tp_xchg_create: cudaMalloc(%zu) failed", x->bytes);

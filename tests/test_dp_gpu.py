@@ -18,15 +18,17 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("mode", ["nccl", "peer"])
+@pytest.mark.parametrize("mode", ["nccl", "peer", "wide_nccl", "wide_peer"])
 @pytest.mark.parametrize("world", [2])
 def test_dp_invariance(world, mode):
-    """nccl: allreduce captured in the step's CUDA graph; peer: in-kernel NVLink peer-memory exchange of the fused step."""
+    """nccl: allreduce captured in the step's CUDA graph; peer: in-kernel NVLink peer-memory exchange of the persistent step;
+    wide_*: the tcgen05 kernel plan with the NCCL allreduce / the two-phase peer-memory exchange fused with the optimizer."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    extra = ["--peer"] if mode == "peer" else []
+    extra = {"nccl": [], "peer": ["--peer"], "wide_nccl": ["--wide"], "wide_peer": ["--wide", "--peer"]}[mode]
+    port = {"nccl": "29517", "peer": "29518", "wide_nccl": "29519", "wide_peer": "29520"}[mode]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517" if mode == "nccl" else "29518",
+                        "--master-addr", "127.0.0.1", "--master-port", port,
                         os.path.join(ROOT, "scripts", "dp_check.py")] + extra,
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "DP_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
