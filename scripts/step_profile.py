@@ -140,6 +140,9 @@ def main():
         tl = list(prev[:n]) + [last[0]]
         for i, nm in enumerate(names):
             print(f"  {nm:10s} {(tl[i + 1] - tl[i]) / 1e3:7.2f}")
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         check(lib.tp_step_destroy(step))
         return
     check(lib.tp_step_set_profile(step, 1))

@@ -959,7 +959,10 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         xa.hi = w->w_split; xa.lo = w->w_split + w->arena_plane;
         xa.arena4 = d.arena_len / 4;
         xa.slice4 = (xa.arena4 + xc->world - 1) / xc->world;
-        int grid = 4 * ctx->sm_count < xc->items / 2 ? 4 * ctx->sm_count : xc->items / 2;      // latency-bound: four CTAs per SM
+        // one wave: every CTA spins on its peers' flags, so all of them must be resident at once (two per SM by registers);
+        // a second wave would only start after the first has been through both exchange phases
+        static const int per_sm = [] { const char* v = getenv("TAPER_XCHG_CTAS_PER_SM"); return v && *v ? atoi(v) : 2; }();
+        int grid = per_sm * ctx->sm_count < xc->items / 2 ? per_sm * ctx->sm_count : xc->items / 2;
         if ((long long)grid > xa.slice4) grid = (int)xa.slice4;
         xa.chunk4 = (xa.slice4 + grid - 1) / grid;
         xa.row = (long long)xc->row;
