@@ -12,7 +12,7 @@ import argparse, csv, io, re, subprocess, sys
 def short(name):
     name = name.replace("<unnamed>::", "").replace("void ", "")
     m = re.match(r"([\w:]+(<[^(]*>)?)", name)
-    return (m.group(1) if m else name)[:70]
+    return (m.group(1) if m else name)[:90]
 
 
 def launches_table(path, first):
@@ -34,20 +34,25 @@ def rep_table(rep, maxk):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
-    want = [("gpu__time_duration.sum", "dur"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
+    want = [("gpu__time_duration.sum", "dur"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+            ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "dyn smem"),
             ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
             ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
-            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe % (active)"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe % (elapsed)"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %")]
     cols = [(hdr.index(k), lab, units[hdr.index(k)]) for k, lab in want if k in hdr]
     ki = hdr.index("Kernel Name")
     out = ["| kernel | " + " | ".join(f"{lab} ({u})" if u else lab for _, lab, u in cols) + " |", "|---|" + "---|" * len(cols)]
     seen = {}
+    gi = hdr.index("launch__grid_size") if "launch__grid_size" in hdr else None
     for r in rows[2:]:
         n = short(r[ki])
-        seen[n] = seen.get(n, 0) + 1
-        if seen[n] > 1 or len(seen) > maxk:
+        key = (n, r[gi] if gi is not None else "")            # one row per (kernel, grid): the same kernel at another shape is listed too
+        seen[key] = seen.get(key, 0) + 1
+        if seen[key] > 1 or len(seen) > maxk:
             continue
         vals = []
         for i, _, _ in cols:

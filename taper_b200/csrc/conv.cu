@@ -287,6 +287,11 @@ int tp_col2im(tp_ctx* ctx, const tp_buf* gcol, tp_buf* gx, const tp_conv_desc* d
     return TP_OK;
 }
 
+// which kernel the last tp_conv2d_fwd of this thread ran: 1 direct small-K (CUDA cores), 2 implicit GEMM on tcgen05,
+// 3 materialised im2col + GEMM (tests assert that the BASELINE shapes really take the tensor-core path)
+static thread_local int g_last_conv_path = 0;
+int tpdbg_last_conv_path(void) { return g_last_conv_path; }
+
 int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp_buf* y, const tp_conv_desc* d, int relu) {
     TP_CHECK_ARG(ctx, "tp_conv2d_fwd: NULL ctx");
     ConvGeom g;
@@ -302,6 +307,7 @@ int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b
         conv_direct_smallk_kernel<<<tp::grid_for(ctx, M, kThreads, 8), kThreads, smem, ctx->stream>>>(
             x->ptr, w->ptr, b ? b->ptr : nullptr, y->ptr, g, relu, (unsigned int)M);
         TP_LAUNCH_OK(ctx);
+        g_last_conv_path = 1;
         return TP_OK;
     }
     // [M,K] x [K,Cout] -> NHWC rows -> NCHW + bias (src/tensor.rs:1262-1281); weight buffer reinterpreted as [K,Cout] (A2).
@@ -311,8 +317,9 @@ int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b
     if (ctx->gemm_mode == 1) {
         tp::ConvShape cs{g.n, g.c, g.h, g.w, g.cout, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, g.ho, g.wo, g.K};
         rc = tp::gemm_tc_conv_fwd(ctx, x->ptr, w->ptr, b ? b->ptr : nullptr, relu, y->ptr, cs);
-        if (rc != TP_ERR_UNSUPPORTED) return rc;
+        if (rc != TP_ERR_UNSUPPORTED) { g_last_conv_path = 2; return rc; }
     }
+    g_last_conv_path = 3;
     TmpBuf col, out2d;
     if ((rc = tp_buf_alloc(ctx, M * g.cout, &out2d.b))) return rc;
     if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;

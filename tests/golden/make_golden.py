@@ -67,11 +67,27 @@ def conv_pool(seed):
             "grad_b": Bv.grad().copy(), "grad_w_is_none": np.array([W.grad() is None])}
 
 
+def conv_igemm(seed):
+    """A 3x3 convolution wide enough (C_in = C_out = 32, K = 288) to take the implicit-GEMM tensor-core kernel, with bias and
+    ReLU, followed by the 2x2 max-pool: forward values (the A2 weight layout is what a wrong kernel gets wrong first)."""
+    rng = np.random.default_rng(seed)
+    R.Tape.reset()
+    R.Config.strict_reference_conv = True
+    x = rng.standard_normal((2, 32, 8, 8)).astype(F32)
+    w = (rng.standard_normal((32, 32, 3, 3)) * 0.08).astype(F32)
+    b = (rng.standard_normal(32) * 0.1).astype(F32)
+    X = R.Tensor.new(x, x.shape)
+    y = X.conv2d_relu(R.Tensor.new(w, w.shape), R.Tensor.new(b, b.shape), (1, 1), (1, 1), (1, 1))
+    mp = y.max_pool2d((2, 2), (2, 2))
+    return {"x": x, "w": w, "b": b, "conv_relu": y.data().copy(), "maxpool": mp.data().copy()}
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "mlp_sgd.npz"), **mlp_steps([20, 12, 5], 8, "sgd", 4, 11, ragged=5))
     np.savez_compressed(os.path.join(HERE, "mlp_adam.npz"), **mlp_steps([24, 16, 8, 6], 16, "adam", 5, 12, ragged=7))
     np.savez_compressed(os.path.join(HERE, "mlp_adamw.npz"), **mlp_steps([784, 128, 10], 32, "adamw", 3, 13))
     np.savez_compressed(os.path.join(HERE, "conv_pool.npz"), **conv_pool(14))
+    np.savez_compressed(os.path.join(HERE, "conv_igemm.npz"), **conv_igemm(15))
     print("golden fixtures written to", HERE)
 
 

@@ -132,6 +132,14 @@ def test_oracle_reproduces_golden_conv_pool():
     assert W.grad() is None and bool(fx["grad_w_is_none"][0])
 
 
+def test_oracle_reproduces_golden_conv_igemm():
+    fx = np.load(os.path.join(HERE, "conv_igemm.npz"))
+    X = T.new(fx["x"], fx["x"].shape)
+    y = X.conv2d_relu(T.new(fx["w"], fx["w"].shape), T.new(fx["b"], fx["b"].shape), (1, 1), (1, 1), (1, 1))
+    close(y.data(), fx["conv_relu"], 1e-6)
+    close(y.max_pool2d((2, 2), (2, 2)).data(), fx["maxpool"], 1e-6)
+
+
 # ---- GPU: the CUDA path vs the same fixtures, through the C ABI ----------------------------------------------------------
 def _spec(dims):
     parts = []
@@ -181,3 +189,21 @@ def test_cuda_reproduces_golden_conv_pool():
     m2.set_param(0, fx["w"])
     m2.set_param(1, fx["b"])
     close(m2.forward(fx["x"]), fx["conv_relu"], 1e-4, "conv_relu")
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_conv_on_the_tcgen05_path():
+    """C_out = 32, K = 288: this fixture goes through the implicit-GEMM tensor-core kernel (asserted), unlike conv_pool.npz whose
+    C_out = 4 layer takes the direct kernel."""
+    from taper_b200 import host, capi
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    fx = np.load(os.path.join(HERE, "conv_igemm.npz"))
+    m = host.Model("conv_relu:32:32:3:1:1", 0)
+    m.set_param(0, fx["w"])
+    m.set_param(1, fx["b"])
+    close(m.forward(fx["x"]), fx["conv_relu"], 1e-4, "conv_relu 32 -> 32")
+    assert capi.lib.tpdbg_last_conv_path() == 2
+    m2 = host.Model("conv_relu:32:32:3:1:1,maxpool:2:2", 0)
+    m2.set_param(0, fx["w"])
+    m2.set_param(1, fx["b"])
+    close(m2.forward(fx["x"]), fx["maxpool"], 1e-4, "conv_relu -> maxpool")
