@@ -498,6 +498,11 @@ def plan_profile(name, peaks, tf32_peak):
     capi.check(lib.tp_step_set_profile(step, 1))
     L = len(dims) - 1
     names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head"] + [f"dX{l}" for l in range(L - 2, 0, -1)] + ["dW_all", "fold", "optimizer"]
+    nph = C.c_int()
+    capi.check(lib.tp_step_info(step, C.byref(nph), None, None))
+    folded = nph.value == len(names) - 1                   # the fold rode along on extra CTAs of the grouped dW launch
+    if folded:
+        names.remove("fold")
     acc = np.zeros(len(names))
     reps = 20
     for _ in range(reps):
@@ -549,8 +554,10 @@ def plan_profile(name, peaks, tf32_peak):
                                   2.0 * B * dims[l] * dims[l + 1], us[i], "N,N"))
         i += 1
     fl = sum(2.0 * B * dims[l] * dims[l + 1] for l in range(L))
-    gemms.append(tensor_entry(f"gemm_bx3_kernel grouped dW (all {L} weight gradients in one launch)", fl, us[i], "T,N")); i += 1
-    hbm_entry("wide_fold_kernel: bias-gradient partials, results, Adam counters", 4 * 160 * sum(dims[1:]), us[i], "latency-bound"); i += 1
+    gemms.append(tensor_entry(f"gemm_bx3_kernel grouped dW (all {L} weight gradients in one launch" + (", bias-gradient fold on spare CTAs)" if folded else ")"),
+                              fl, us[i], "T,N")); i += 1
+    if not folded:
+        hbm_entry("wide_fold_kernel: bias-gradient partials, results, Adam counters", 4 * 160 * sum(dims[1:]), us[i], "latency-bound"); i += 1
     hbm_entry("adam_dev_split_kernel: fused optimizer + parameter planes", (28 + 4) * n_param, us[i],
               "L2-resident state (52 MB < 126 MB L2): reported against HBM peak, so frac may exceed what DRAM alone allows"); i += 1
     roof = max(gemms, key=lambda e: e["launch_us"])

@@ -21,6 +21,8 @@ typedef struct tp_trainer tp_trainer;   /* train::Trainer            src/train.r
 typedef struct tp_dataset tp_dataset;   /* data::MNISTDataset        src/data/mnist.rs:21-25 */
 typedef struct tp_loader tp_loader;     /* data::DataLoader          src/data/mnist.rs:326-385 */
 typedef struct tp_scheduler tp_scheduler;   /* optim::LRScheduler    src/optim.rs:184-352 */
+typedef struct tp_tensor tp_tensor;     /* Tensor (a shared handle: clone = Tensor::clone)   src/tensor.rs:236-244 */
+typedef struct tp_optimizer tp_optimizer;   /* optim::{SGD, Adam, AdamW}                     src/optim.rs:8-181 */
 
 /* device of this thread's context (call before anything else on the thread); the context itself */
 int tp_host_set_device(int device);
@@ -137,6 +139,48 @@ int tp_trainer_get_lr(tp_trainer* t, float* lr);
 /* sticky device-side error word of the trainer's context (0 = none): 1 label outside [0, classes), 2 grid barrier timeout,
  * 3 peer exchange timeout.  fetch / train_epoch raise on a non-zero word; this reads it without raising. */
 int tp_trainer_device_error(tp_trainer* t, int* code);
+
+/* ---- Tensor / Tape / Module / loss / optimizer at the granularity of the reference's own API ----------------------------
+ * What a Rust (or any FFI) shim binds so that examples/train_mnist.rs-style code runs unmodified: every call records the
+ * same tape node the reference records (src/tape.rs:51-101); tensors live on the device, tp_tensor_data reads them back.
+ *   tp_tensor_new        Tensor::new(data, shape) [.requires_grad()]                 src/tensor.rs:470-487
+ *   tp_tensor_unary      op = relu | exp | log | sigmoid | mean | transpose | pow | sqrt   (arg = exponent for pow)
+ *   tp_tensor_binary     op = add | sub | mul | div | matmul | add_broadcast | sub_broadcast_rows
+ *   tp_tensor_sum/argmax dim < 0: over all elements                                  src/tensor.rs:890-1088
+ *   tp_module_forward    Module::forward on a device tensor (src/nn.rs:10-12); tp_model_parameter = parameters()[i]
+ *   tp_loss              kind = cross_entropy | cross_entropy_onehot | bce | mse     src/loss.rs:6-245
+ *   tp_optimizer_*       SGD / Adam / AdamW over tensor handles                      src/optim.rs:8-181 */
+int tp_tensor_new(const float* data, const size_t* shape, int ndim, int requires_grad, tp_tensor** out);
+int tp_tensor_clone(tp_tensor* t, tp_tensor** out);
+int tp_tensor_free(tp_tensor* t);
+int tp_tensor_ndim(tp_tensor* t, int* ndim);
+int tp_tensor_shape(tp_tensor* t, size_t* dims, int cap);
+int tp_tensor_numel(tp_tensor* t, size_t* n);
+int tp_tensor_data(tp_tensor* t, float* out, size_t n);                                  /* Tensor::data      :493-496 */
+int tp_tensor_set_data(tp_tensor* t, const float* data, size_t n);                       /* data_mut          :499-501 */
+int tp_tensor_grad(tp_tensor* t, float* out, size_t n, int* has_grad);                   /* Tensor::grad      :512-518 */
+int tp_tensor_requires_grad(tp_tensor* t, int* flag);
+int tp_tensor_zero_grad(tp_tensor* t);                                                   /* :531-533 */
+int tp_tensor_backward(tp_tensor* t);                                                    /* :520-529 */
+int tp_tensor_unary(const char* op, tp_tensor* x, float arg, tp_tensor** out);
+int tp_tensor_binary(const char* op, tp_tensor* a, tp_tensor* b, tp_tensor** out);
+int tp_tensor_reshape(tp_tensor* x, const size_t* shape, int ndim, tp_tensor** out);     /* :803-840 */
+int tp_tensor_flatten(tp_tensor* x, size_t start_dim, tp_tensor** out);                  /* :842-858 */
+int tp_tensor_sum(tp_tensor* x, int dim, int keepdim, tp_tensor** out);
+int tp_tensor_argmax(tp_tensor* x, int dim, tp_tensor** out);
+int tp_tape_reset(void);                                                                 /* Tape::reset       src/tape.rs:43-49 */
+int tp_tape_len(size_t* nodes);
+int tp_module_forward(tp_model* m, tp_tensor* x, tp_tensor** out);
+int tp_model_parameter(tp_model* m, int index, tp_tensor** out);
+int tp_loss(const char* kind, tp_tensor* predictions, tp_tensor* targets, tp_tensor** out);
+int tp_accuracy(tp_tensor* predictions, tp_tensor* targets, float* acc);                 /* src/loss.rs:271-290 */
+int tp_optimizer_create(const char* kind, tp_tensor* const* params, int n_params, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, tp_optimizer** out);
+int tp_optimizer_step(tp_optimizer* o);
+int tp_optimizer_zero_grad(tp_optimizer* o);
+int tp_optimizer_set_lr(tp_optimizer* o, float lr);
+int tp_optimizer_get_lr(tp_optimizer* o, float* lr);
+int tp_optimizer_destroy(tp_optimizer* o);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,10 @@ def main():
         names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head"]
         names += [f"dX{l}" for l in range(L - 2, 0, -1)]
         names += ["dW (all)", "fold", "optimizer" if world == 1 else "exchange+optimizer"]
+        check(lib.tp_step_info(step, C.byref(nph), C.byref(njobs), C.byref(grid)))
+        if nph.value == len(names) - 1:               # the fold rode along on extra CTAs of the dW launch
+            names.remove("fold")
+            names[names.index("dW (all)")] = "dW (all) + fold"
         buf = np.zeros(32, np.int64)
         slots = C.c_int()
         check(lib.tp_step_read_profile(step, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(slots)))

@@ -43,7 +43,7 @@ class StepDesc(C.Structure):
 
 
 _OPAQUE = ("tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_step", "tp_xchg", "tp_dataset", "tp_loader",
-           "tp_scheduler")
+           "tp_scheduler", "tp_tensor", "tp_optimizer")
 _BASE = {
     "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32,
     "int64_t": C.c_int64, "char": C.c_char, "void": None,

@@ -184,7 +184,9 @@ int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, c
                 int want_bn = 0, int want_splits = 0);                 // 0: tile width / K-split from the cost model
 int bx3_best_splits(tp_ctx* ctx, int bn, long tiles, int k);           // K-split for tiles that share one launch
 int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl);
-int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl);      // compatible problems share a launch
+// compatible problems share a launch; `tail` (a tpfold::FoldStep, wide_fold.cuh) rides along on extra CTAs of the LAST launch
+// when that launch leaves SMs free (*tail_done says whether it did)
+int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const void* tail = nullptr, bool* tail_done = nullptr);
 int split_bf16(tp_ctx* ctx, const float* src, uint16_t* dst, size_t n, long long plane, bool pdl);
 // fp32 operands: splits both into temporaries first.  TP_ERR_UNSUPPORTED when the shape cannot go through TMA.
 int gemm_bx3(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, const float* b, float beta,

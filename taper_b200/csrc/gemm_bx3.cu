@@ -18,6 +18,7 @@
 // OUTPUT (operand of the next GEMM) and partial column sums (bias gradients), all stored with 128-bit accesses.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "wide_fold.cuh"
 
 #include <cuda_bf16.h>
 #include <cstdlib>
@@ -59,6 +60,10 @@ constexpr int kMaxGroup = 3;
 struct Bx3Group {
     Bx3Params p[kMaxGroup];
     int count;
+    // grid rows >= tail_y0 are not GEMM tiles: their first CTA runs the plan's fold / bookkeeping (wide_fold.cuh) on SMs
+    // the GEMM tiles leave free, the others leave at once
+    int tail_y0, tail_workers;
+    tpfold::FoldStep tail;
 };
 
 // K-major operand : rows of 128 B (64 bf16 of K), 8 rows = one 1024 B swizzle atom -> SBO 1024; LBO unused.
@@ -114,6 +119,14 @@ gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const __grid_constant__ Bx3Group grp) {
     static_assert(!DRAIN || BN <= 128, "the register drain holds BN accumulators per thread");
     constexpr int kThreads = threads_of<DRAIN>();
+    if (grp.tail_workers > 0 && (int)blockIdx.y >= grp.tail_y0) {
+        if (blockIdx.x != 0 || blockIdx.z != 0) return;
+        extern __shared__ __align__(1024) uint8_t tail_smem[];
+        pdl_launch_dependents();
+        pdl_wait();
+        tpfold::fold_worker<kThreads>(grp.tail, (int)blockIdx.y - grp.tail_y0, grp.tail_workers, reinterpret_cast<float*>(tail_smem));
+        return;
+    }
     int gi = 0;
     if (grp.count > 1 && (int)blockIdx.y >= grp.p[1].y0) gi = 1;
     if (grp.count > 2 && (int)blockIdx.y >= grp.p[2].y0) gi = 2;
@@ -487,7 +500,7 @@ bool make_map(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, int rows
 }
 
 template <int BN, bool A_MN, bool B_MN, bool DRAIN>
-int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl) {
+int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail, int tail_workers) {
     auto kern = gemm_bx3_kernel<BN, A_MN, B_MN, DRAIN>;
     constexpr int smem = Smem<BN>::kTotal;
     static bool attr_set[16] = {};                    // per device
@@ -514,6 +527,13 @@ int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl) {
         p.a_early = L.a_early ? 1 : 0; p.b_early = L.b_early ? 1 : 0;
         rows += L.tiles_m;
         if (L.tiles_n > max_tn) max_tn = L.tiles_n;
+    }
+    g.tail_y0 = rows;
+    g.tail_workers = 0;
+    if (tail && tail_workers > 0) {
+        g.tail_workers = tail_workers;
+        g.tail = *tail;
+        rows += tail_workers;
     }
     if (rows > 65535) return TP_ERR_UNSUPPORTED;
     const tp::Bx3Launch& L0 = *Ls[0];
@@ -546,12 +566,12 @@ int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl) {
 }
 
 template <int BN, bool DRAIN>
-int launch_major(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl) {
+int launch_major(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail, int tw) {
     const tp::Bx3Launch& L = *Ls[0];
-    if (!L.a_mn && !L.b_mn) return launch_t<BN, false, false, DRAIN>(ctx, Ls, count, pdl);
-    if (!L.a_mn && L.b_mn) return launch_t<BN, false, true, DRAIN>(ctx, Ls, count, pdl);
-    if (L.a_mn && !L.b_mn) return launch_t<BN, true, false, DRAIN>(ctx, Ls, count, pdl);
-    return launch_t<BN, true, true, DRAIN>(ctx, Ls, count, pdl);
+    if (!L.a_mn && !L.b_mn) return launch_t<BN, false, false, DRAIN>(ctx, Ls, count, pdl, tail, tw);
+    if (!L.a_mn && L.b_mn) return launch_t<BN, false, true, DRAIN>(ctx, Ls, count, pdl, tail, tw);
+    if (L.a_mn && !L.b_mn) return launch_t<BN, true, false, DRAIN>(ctx, Ls, count, pdl, tail, tw);
+    return launch_t<BN, true, true, DRAIN>(ctx, Ls, count, pdl, tail, tw);
 }
 
 template <int BN>
@@ -712,12 +732,12 @@ int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, c
     return TP_OK;
 }
 
-static int launch_any(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl) {
+static int launch_any(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail = nullptr, int tw = 0) {
     cudaSetDevice(ctx->device);
     const Bx3Launch& L = *Ls[0];
-    if (L.bn == 256) return launch_major<256, false>(ctx, Ls, count, pdl);
-    if (L.bn == 128) return L.drain ? launch_major<128, true>(ctx, Ls, count, pdl) : launch_major<128, false>(ctx, Ls, count, pdl);
-    return L.drain ? launch_major<64, true>(ctx, Ls, count, pdl) : launch_major<64, false>(ctx, Ls, count, pdl);
+    if (L.bn == 256) return launch_major<256, false>(ctx, Ls, count, pdl, tail, tw);
+    if (L.bn == 128) return L.drain ? launch_major<128, true>(ctx, Ls, count, pdl, tail, tw) : launch_major<128, false>(ctx, Ls, count, pdl, tail, tw);
+    return L.drain ? launch_major<64, true>(ctx, Ls, count, pdl, tail, tw) : launch_major<64, false>(ctx, Ls, count, pdl, tail, tw);
 }
 
 int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl) {
@@ -726,16 +746,26 @@ int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl) {
 }
 
 // problems that share tile width, operand majors, K-split and drain mode go out as ONE launch (up to three); the rest follow
-// one by one
-int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl) {
+// one by one.  The tail (fold + bookkeeping of the wide plan) joins the last launch when that launch's tiles leave at least
+// four SMs free in its first wave and it is not a K-split (cluster) launch; otherwise the caller launches it by itself.
+int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const void* tail, bool* tail_done) {
+    if (tail_done) *tail_done = false;
     int i = 0;
     while (i < count) {
         int j = i + 1;
         while (j < count && j - i < kMaxGroup && Ls[j]->bn == Ls[i]->bn && Ls[j]->a_mn == Ls[i]->a_mn && Ls[j]->b_mn == Ls[i]->b_mn &&
                Ls[j]->splits == Ls[i]->splits && Ls[j]->drain == Ls[i]->drain && Ls[j]->k == Ls[i]->k)
             ++j;
-        int rc = launch_any(ctx, Ls + i, j - i, pdl);
+        int tw = 0;
+        if (tail && j == count && Ls[i]->splits == 1 && !Ls[i]->drain) {
+            long ctas = 0;
+            for (int q = i; q < j; ++q) ctas += (long)Ls[q]->tiles_m * Ls[q]->tiles_n;
+            const long free_sms = (long)ctx->sm_count - ctas % ctx->sm_count;
+            if (ctas % ctx->sm_count != 0 && free_sms >= 4) tw = (int)(free_sms < 16 ? free_sms : 16);
+        }
+        int rc = launch_any(ctx, Ls + i, j - i, pdl, tw ? static_cast<const tpfold::FoldStep*>(tail) : nullptr, tw);
         if (rc) return rc;
+        if (tw && tail_done) *tail_done = true;
         i = j;
     }
     return TP_OK;

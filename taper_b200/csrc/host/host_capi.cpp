@@ -29,6 +29,14 @@ struct tp_scheduler {
     std::shared_ptr<optim::LRScheduler> sc;
 };
 
+struct tp_tensor {
+    Tensor t;
+};
+
+struct tp_optimizer {
+    std::shared_ptr<optim::Optimizer> opt;
+};
+
 namespace {
 
 template <class F>
@@ -500,6 +508,229 @@ int tp_trainer_metrics(tp_trainer* t, int which, float* out, size_t cap, size_t*
 
 int tp_trainer_get_lr(tp_trainer* t, float* lr) {
     return guarded([&] { TRAINER(t); if (lr) *lr = t->tr->optimizer->lr(); });
+}
+
+// ---- Tensor / Tape / Module / loss / optimizer handles -----------------------------------------------------------------------
+#define TENSOR(x) do { if (!(x) || !(x)->t.defined()) panic("%s: NULL tensor", __func__); } while (0)
+
+static tp_tensor* wrap(const Tensor& t) {
+    auto* h = new tp_tensor();
+    h->t = t;
+    return h;
+}
+
+int tp_tensor_new(const float* data, const size_t* shape, int ndim, int requires_grad, tp_tensor** out) {
+    return guarded([&] {
+        if (!data || !shape || ndim < 1 || !out) panic("tp_tensor_new: bad arguments");
+        Tensor t = Tensor::from_host(data, to_shape(shape, ndim));
+        *out = wrap(requires_grad ? t.requires_grad() : t);
+    });
+}
+
+int tp_tensor_clone(tp_tensor* t, tp_tensor** out) {
+    return guarded([&] { TENSOR(t); if (!out) panic("tp_tensor_clone: NULL out pointer"); *out = wrap(t->t); });
+}
+
+int tp_tensor_free(tp_tensor* t) {
+    return guarded([&] { delete t; });
+}
+
+int tp_tensor_ndim(tp_tensor* t, int* ndim) {
+    return guarded([&] { TENSOR(t); if (ndim) *ndim = (int)t->t.shape().size(); });
+}
+
+int tp_tensor_shape(tp_tensor* t, size_t* dims, int cap) {
+    return guarded([&] {
+        TENSOR(t);
+        const Shape& s = t->t.shape();
+        if (!dims || cap < (int)s.size()) panic("tp_tensor_shape: buffer for %zu dimensions needed", s.size());
+        for (size_t i = 0; i < s.size(); ++i) dims[i] = s[i];
+    });
+}
+
+int tp_tensor_numel(tp_tensor* t, size_t* n) {
+    return guarded([&] { TENSOR(t); if (n) *n = t->t.numel(); });
+}
+
+int tp_tensor_data(tp_tensor* t, float* out, size_t n) {
+    return guarded([&] {
+        TENSOR(t);
+        if (!out || n != t->t.numel()) panic("tp_tensor_data: expected a buffer of %zu floats", t->t.numel());
+        const std::vector<float>& d = t->t.data();
+        std::memcpy(out, d.data(), n * sizeof(float));
+    });
+}
+
+int tp_tensor_set_data(tp_tensor* t, const float* data, size_t n) {
+    return guarded([&] {
+        TENSOR(t);
+        if (!data || n != t->t.numel()) panic("tp_tensor_set_data: expected %zu floats", t->t.numel());
+        t->t.set_data(std::vector<float>(data, data + n));
+    });
+}
+
+int tp_tensor_grad(tp_tensor* t, float* out, size_t n, int* has_grad) {
+    return guarded([&] {
+        TENSOR(t);
+        auto g = t->t.grad();
+        if (has_grad) *has_grad = g ? 1 : 0;
+        if (g && out) {
+            if (n != t->t.numel()) panic("tp_tensor_grad: expected a buffer of %zu floats", t->t.numel());
+            std::memcpy(out, g->data().data(), n * sizeof(float));
+        }
+    });
+}
+
+int tp_tensor_requires_grad(tp_tensor* t, int* flag) {
+    return guarded([&] { TENSOR(t); if (flag) *flag = t->t.needs_grad() ? 1 : 0; });
+}
+
+int tp_tensor_zero_grad(tp_tensor* t) {
+    return guarded([&] { TENSOR(t); t->t.zero_grad(); });
+}
+
+int tp_tensor_backward(tp_tensor* t) {
+    return guarded([&] { TENSOR(t); t->t.backward(); });
+}
+
+int tp_tensor_unary(const char* op, tp_tensor* x, float arg, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(x);
+        if (!op || !out) panic("tp_tensor_unary: NULL argument");
+        std::string k = op;
+        const Tensor& t = x->t;
+        if (k == "relu") *out = wrap(t.relu());
+        else if (k == "exp") *out = wrap(t.exp());
+        else if (k == "log") *out = wrap(t.log());
+        else if (k == "sigmoid") *out = wrap(t.sigmoid());
+        else if (k == "mean") *out = wrap(t.mean());
+        else if (k == "transpose") *out = wrap(t.transpose());
+        else if (k == "pow") *out = wrap(t.pow(arg));
+        else if (k == "sqrt") *out = wrap(t.sqrt());
+        else panic("tp_tensor_unary: unknown op '%s'", op);
+    });
+}
+
+int tp_tensor_binary(const char* op, tp_tensor* a, tp_tensor* b, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(a); TENSOR(b);
+        if (!op || !out) panic("tp_tensor_binary: NULL argument");
+        std::string k = op;
+        if (k == "add") *out = wrap(a->t + b->t);
+        else if (k == "sub") *out = wrap(a->t - b->t);
+        else if (k == "mul") *out = wrap(a->t * b->t);
+        else if (k == "div") *out = wrap(a->t / b->t);
+        else if (k == "matmul") *out = wrap(a->t.matmul(b->t));
+        else if (k == "add_broadcast") *out = wrap(a->t.add_broadcast(b->t));
+        else if (k == "sub_broadcast_rows") *out = wrap(a->t.sub_broadcast_rows(b->t));
+        else panic("tp_tensor_binary: unknown op '%s'", op);
+    });
+}
+
+int tp_tensor_reshape(tp_tensor* x, const size_t* shape, int ndim, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(x);
+        if (!shape || ndim < 1 || !out) panic("tp_tensor_reshape: bad arguments");
+        *out = wrap(x->t.reshape(to_shape(shape, ndim)));
+    });
+}
+
+int tp_tensor_flatten(tp_tensor* x, size_t start_dim, tp_tensor** out) {
+    return guarded([&] { TENSOR(x); if (!out) panic("tp_tensor_flatten: NULL out pointer"); *out = wrap(x->t.flatten(start_dim)); });
+}
+
+int tp_tensor_sum(tp_tensor* x, int dim, int keepdim, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(x);
+        if (!out) panic("tp_tensor_sum: NULL out pointer");
+        *out = wrap(x->t.sum(dim < 0 ? std::nullopt : std::optional<size_t>((size_t)dim), keepdim != 0));
+    });
+}
+
+int tp_tensor_argmax(tp_tensor* x, int dim, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(x);
+        if (!out) panic("tp_tensor_argmax: NULL out pointer");
+        *out = wrap(x->t.argmax(dim < 0 ? std::nullopt : std::optional<size_t>((size_t)dim)));
+    });
+}
+
+int tp_tape_reset(void) {
+    return guarded([&] { Tape::reset(); });
+}
+
+int tp_tape_len(size_t* nodes) {
+    return guarded([&] { if (nodes) *nodes = Tape::len(); });
+}
+
+int tp_module_forward(tp_model* m, tp_tensor* x, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(x);
+        if (!m || !out) panic("tp_module_forward: NULL argument");
+        *out = wrap(m->seq->forward(x->t));
+    });
+}
+
+int tp_model_parameter(tp_model* m, int index, tp_tensor** out) {
+    return guarded([&] {
+        if (!m || !out) panic("tp_model_parameter: NULL argument");
+        *out = wrap(param_at(m, index));
+    });
+}
+
+int tp_loss(const char* kind, tp_tensor* predictions, tp_tensor* targets, tp_tensor** out) {
+    return guarded([&] {
+        TENSOR(predictions); TENSOR(targets);
+        if (!kind || !out) panic("tp_loss: NULL argument");
+        std::string k = kind;
+        if (k == "cross_entropy") *out = wrap(loss::cross_entropy_loss(predictions->t, targets->t));
+        else if (k == "cross_entropy_onehot") *out = wrap(loss::cross_entropy_loss_onehot(predictions->t, targets->t));
+        else if (k == "bce") *out = wrap(loss::bce_loss(predictions->t, targets->t));
+        else if (k == "mse") *out = wrap(loss::mse_loss(predictions->t, targets->t));
+        else panic("tp_loss: unknown loss '%s'", kind);
+    });
+}
+
+int tp_accuracy(tp_tensor* predictions, tp_tensor* targets, float* acc) {
+    return guarded([&] { TENSOR(predictions); TENSOR(targets); if (acc) *acc = loss::accuracy(predictions->t, targets->t); });
+}
+
+int tp_optimizer_create(const char* kind, tp_tensor* const* params, int n_params, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, tp_optimizer** out) {
+    return guarded([&] {
+        if (!kind || !params || n_params < 1 || !out) panic("tp_optimizer_create: bad arguments");
+        std::vector<Tensor> ps;
+        for (int i = 0; i < n_params; ++i) { TENSOR(params[i]); ps.push_back(params[i]->t); }
+        std::string k = kind;
+        auto* o = new tp_optimizer();
+        if (k == "sgd") o->opt = std::make_shared<optim::SGD>(ps, lr);
+        else if (k == "adam") o->opt = std::make_shared<optim::Adam>(ps, lr, std::make_pair(beta1, beta2), eps, weight_decay);
+        else if (k == "adamw") o->opt = std::make_shared<optim::AdamW>(ps, lr, std::make_pair(beta1, beta2), eps, weight_decay);
+        else { delete o; panic("tp_optimizer_create: unknown optimizer '%s'", kind); }
+        *out = o;
+    });
+}
+
+#define OPTIMIZER(o) do { if (!(o) || !(o)->opt) panic("%s: NULL optimizer", __func__); } while (0)
+
+int tp_optimizer_step(tp_optimizer* o) {
+    return guarded([&] { OPTIMIZER(o); o->opt->step(); });
+}
+
+int tp_optimizer_zero_grad(tp_optimizer* o) {
+    return guarded([&] { OPTIMIZER(o); o->opt->zero_grad(); });
+}
+
+int tp_optimizer_set_lr(tp_optimizer* o, float lr) {
+    return guarded([&] { OPTIMIZER(o); o->opt->set_lr(lr); });
+}
+
+int tp_optimizer_get_lr(tp_optimizer* o, float* lr) {
+    return guarded([&] { OPTIMIZER(o); if (lr) *lr = o->opt->lr(); });
+}
+
+int tp_optimizer_destroy(tp_optimizer* o) {
+    return guarded([&] { delete o; });
 }
 
 int tp_trainer_device_error(tp_trainer* t, int* code) {

@@ -24,6 +24,7 @@
 // No kernel of the plan reads an fp32 operand through the tensor pipe and nothing is transposed or copied in memory.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "wide_fold.cuh"
 
 #include <cuda_bf16.h>
 #include <cstdlib>
@@ -32,23 +33,11 @@
 namespace {
 
 using namespace tcptx;
+using namespace tpfold;
 
 constexpr int kThreads = 256;
 constexpr int kMaxOut = 16;
 constexpr int kHeadRowsMax = 16;     // rows of the batch per head CTA and pass (staged in shared memory)
-enum { H_T = 0, H_LR, H_B1, H_B2, H_EPS, H_WD, H_SS, H_DECAY, H_COUNT };       // same layout as optim.cu
-
-__device__ __forceinline__ float powi_dev(float a, int b) {     // f32::powi, as optim.cu
-    float r = 1.0f;
-    unsigned int e = (unsigned int)b;
-    while (true) {
-        if (e & 1u) r *= a;
-        e >>= 1;
-        if (e == 0) break;
-        a *= a;
-    }
-    return r;
-}
 
 __device__ __forceinline__ unsigned int class_of(float t) {     // `t as usize` (src/loss.rs:160)
     if (!(t > 0.0f)) return 0u;
@@ -320,94 +309,16 @@ wide_head_kernel(HeadArgs a) {
     }
 }
 
-// ---- fold: partials -> gradient arena, results, optimizer counters -----------------------------------------------------
-constexpr int kMaxFold = 2 * TP_STEP_MAX_LAYERS + 4;
-constexpr int kFoldWarps = kThreads / 32;
-struct FoldEntry {
-    float* dst;                      // n outputs
-    const float* src;                // partial j of output i at src[j * stride + i]
-    int n, parts;
-    long long stride;
-    int first_block;                 // blocks [first_block, first_block + ceil(n / 32)) serve this entry
-};
-struct FoldArgs {
-    FoldEntry e[kMaxFold];
-    int n_entries;
-    const float* lh_part;            // [lh_parts][2]
-    int lh_parts;
-    int B;
-    float* result;                   // device {loss, correct}
-    float* result_host;              // optional mapped pinned {loss, correct, seq}
-    unsigned int result_seq;
-    float* hyper;                    // Adam state or NULL (SGD)
-    int* cursor;                     // dataset cursor or NULL
-    int cursor_delta, cursor_mod;
-    const int* err;                  // sticky device error word of the context
-    unsigned long long* stamp;
-};
-
-// A block folds 32 outputs (one per lane); warp w sums partials w, w + 8, w + 16, ... with eight loads in flight, the eight
-// warp sums are added in warp order.  The association order is fixed, so the result does not depend on timing.
+// ---- fold: partials -> gradient arena, results, optimizer counters (wide_fold.cuh) ------------------------------------
+// Runs on a few extra CTAs of the grouped weight-gradient launch (gemm_bx3.cu); this stand-alone kernel serves plans whose
+// weight-gradient GEMMs cannot take it along.
 __global__ void __launch_bounds__(kThreads)
-wide_fold_kernel(const __grid_constant__ FoldArgs a) {
-    __shared__ float red[kFoldWarps][32];
+wide_fold_kernel(const FoldStep st) {
+    __shared__ float red[kThreads];
     pdl_launch_dependents();
     pdl_wait();
-    stamp_now(a.stamp);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int ei = 0;
-#pragma unroll 1
-    for (int i = 1; i < a.n_entries; ++i)
-        if ((int)blockIdx.x >= a.e[i].first_block) ei = i;
-    const FoldEntry& e = a.e[ei];
-    const int i = ((int)blockIdx.x - e.first_block) * 32 + lane;
-    float s = 0.0f;
-    if (i < e.n) {
-        for (int j0 = wid; j0 < e.parts; j0 += kFoldWarps * 8) {
-            float x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = j0 + u * kFoldWarps;
-                x[u] = j < e.parts ? __ldg(e.src + (size_t)j * e.stride + i) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += x[u];
-        }
-    }
-    red[wid][lane] = s;
-    __syncthreads();
-    if (wid == 0 && i < e.n) {
-        float t = red[0][lane];
-#pragma unroll
-        for (int w = 1; w < kFoldWarps; ++w) t += red[w][lane];
-        e.dst[i] = t;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        float n = 0.0f, h = 0.0f;
-        for (int j = 0; j < a.lh_parts; ++j) { n += __ldg(a.lh_part + 2 * j); h += __ldg(a.lh_part + 2 * j + 1); }     // rows ascending
-        const float loss = n / (float)a.B;                                       // src/loss.rs:164
-        a.result[0] = loss;
-        a.result[1] = h;
-        if (a.result_host) {
-            a.result_host[0] = loss;
-            a.result_host[1] = h;
-            a.result_host[3] = __int_as_float(__ldcg(a.err));                  // 1: a label outside [0, classes) (the reference panics)
-            if (a.result_seq) {
-                __threadfence_system();
-                ((volatile unsigned int*)a.result_host)[2] = a.result_seq;
-            }
-        }
-        if (a.hyper) {                                                           // Adam::step prologue (src/optim.rs:86-90, 157)
-            float* hy = a.hyper;
-            const int tt = __float_as_int(hy[H_T]) + 1;
-            hy[H_T] = __int_as_float(tt);
-            const float bc1 = 1.0f - powi_dev(hy[H_B1], tt);
-            const float bc2 = 1.0f - powi_dev(hy[H_B2], tt);
-            hy[H_SS] = hy[H_LR] * (sqrtf(bc2) / bc1);
-            hy[H_DECAY] = 1.0f - hy[H_LR] * hy[H_WD];
-        }
-        if (a.cursor) *a.cursor = (int)(((long long)*a.cursor + a.cursor_delta) % a.cursor_mod);
-    }
+    stamp_now(st.stamp);
+    fold_worker<kThreads>(st, (int)blockIdx.x, (int)gridDim.x, red);
 }
 
 // ---- data-parallel: two-phase gradient exchange over NVLink peer memory + optimizer, one kernel -------------------------
@@ -639,13 +550,15 @@ struct WidePlan {
     int head_grid = 0, head_rows = 0;
     size_t head_smem = 0;
     std::vector<Bx3Launch> fwd, dx, dw;   // dx[l] produces dz[l-1] (unused for l = 0)
-    FoldArgs fold{};
-    int fold_grid = 0;
+    FoldTable fold{};                // host copy; the device copy lives in the plan's block
+    FoldTable* fold_dev = nullptr;
+    bool fold_in_group = true;       // the grouped dW launch runs the fold on extra CTAs
     bool pdl = true;
     bool weights_fresh = false;
     unsigned long long* stamps = nullptr;    // [2][16] %globaltimer per kernel of the last two steps (tp_step_set_profile)
     bool profile = false;
     unsigned int runs = 0;
+    int kernels_per_step = 0;        // launches of the last run (the fold rides on the dW launch when it can)
 };
 
 namespace {
@@ -723,6 +636,7 @@ static int wide_build(WidePlan* w, Carver& c) {
     w->lh_part = c.take<float>((size_t)w->head_grid * 2);
     // column-sum partials of the dX GEMMs (sized for the worst tiling: 128-row tiles x 8 K-splits)
     for (int l = 0; l + 2 < L; ++l) w->cs_part[l] = c.take<float>((size_t)((B + 127) / 128) * 8 * d.dims[l + 1]);
+    w->fold_dev = c.take<FoldTable>(1);
     if (!c.base) return TP_OK;
 
     tp_ctx* ctx = w->ctx;
@@ -779,9 +693,9 @@ static int wide_build(WidePlan* w, Carver& c) {
         w->dw_last.b_early = true;
         w->dw_last.a_early = L > 2;                    // dlogits come from the head; a dX kernel sits in between unless L == 2
     }
-    // fold table
-    FoldArgs& f = w->fold;
-    f = FoldArgs{};
+    // fold table (device copy in the plan's block)
+    FoldTable& f = w->fold;
+    f = FoldTable{};
     int nb = 0;
     auto add = [&](float* dst, const float* src, int n, int parts, long long stride) {
         FoldEntry& e = f.e[f.n_entries++];
@@ -791,10 +705,18 @@ static int wide_build(WidePlan* w, Carver& c) {
     if (d.b_off[L - 1] >= 0) add(w->G + d.b_off[L - 1], w->db_part, C, w->head_grid, kMaxOut);
     for (int l = 0; l + 1 < L; ++l)
         if (d.b_off[l] >= 0) add(w->G + d.b_off[l], w->cs_part[l], d.dims[l + 1], w->cs_parts[l], d.dims[l + 1]);
-    w->fold_grid = nb;
+    f.n_blocks = nb;
     f.lh_part = w->lh_part; f.lh_parts = w->head_grid; f.B = B;
     f.result = w->result;
+    f.err = ctx->dev_error;
     f.hyper = d.optimizer != 0 ? w->hyper : nullptr;
+    if (cudaMemcpyAsync(w->fold_dev, &f, sizeof f, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("tp_step_create: uploading the fold table failed");
+        return TP_ERR_CUDA;
+    }
+    { const char* v = getenv("TAPER_WIDE_FOLD_IN_GROUP"); w->fold_in_group = !(v && v[0] == '0'); }
     return TP_OK;
 }
 
@@ -882,7 +804,7 @@ int wide_refresh(WidePlan* w) {
 
 void wide_info(const WidePlan* w, int* n_phases, int* n_jobs, int* grid) {
     const int L = w->d.n_layers;
-    if (n_phases) *n_phases = 2 * L + 4;
+    if (n_phases) *n_phases = w->kernels_per_step ? w->kernels_per_step : 2 * L + 1;
     if (n_jobs) *n_jobs = 3 * (L - 1) + 5;
     if (grid) *grid = w->ctx->sm_count;
 }
@@ -900,6 +822,7 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         if (rc) return rc;
         w->weights_fresh = true;
     }
+    const uint64_t launches0 = ctx->launches;
     unsigned long long* st = w->profile ? w->stamps + (w->runs & 1) * 16 : nullptr;
     int slot = 0;
     auto next_stamp = [&]() { return st ? st + (slot < 15 ? slot++ : 15) : nullptr; };
@@ -932,25 +855,29 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         rc = bx3_launch(ctx, w->dx[l], pdl);
         if (rc) return rc;
     }
+    FoldStep fs{};
+    fs.table = w->fold_dev;
+    fs.result_host = result_host;
+    fs.result_seq = result_host ? result_seq : 0u;
+    fs.cursor = perm ? cursor : nullptr;
+    fs.cursor_delta = B; fs.cursor_mod = n_perm > 0 ? n_perm : 1;
     {
-        // every weight gradient: independent of each other, so compatible ones share a launch
+        // every weight gradient: independent of each other, so compatible ones share a launch — and a few extra CTAs of that
+        // launch fold the bias-gradient partials and publish the step's results (everything they read is complete by then)
         const Bx3Launch* all[TP_STEP_MAX_LAYERS + 1];
         int n = 0;
         w->dw_last.stamp = next_stamp();
         all[n++] = &w->dw_last;
         for (int l = L - 2; l >= 0; --l) { w->dw[l].stamp = nullptr; all[n++] = &w->dw[l]; }
-        rc = bx3_launch_group(ctx, all, n, pdl);
+        bool folded = false;
+        rc = bx3_launch_group(ctx, all, n, pdl, w->fold_in_group ? &fs : nullptr, &folded);
         if (rc) return rc;
+        if (!folded) {
+            fs.stamp = next_stamp();
+            rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold.n_blocks < 2 * ctx->sm_count ? w->fold.n_blocks : 2 * ctx->sm_count), 0, fs, pdl);
+            if (rc) return rc;
+        }
     }
-    FoldArgs fa = w->fold;
-    fa.stamp = next_stamp();
-    fa.result_host = result_host;
-    fa.result_seq = result_host ? result_seq : 0u;
-    fa.err = ctx->dev_error;
-    fa.cursor = perm ? cursor : nullptr;
-    fa.cursor_delta = B; fa.cursor_mod = n_perm > 0 ? n_perm : 1;
-    rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold_grid), 0, fa, pdl);
-    if (rc) return rc;
     if (xc) {
         // allreduce + optimizer as one kernel over NVLink peer memory (reduce-scatter, all-gather, update)
         const size_t par = xc->seq & 1u;
@@ -977,7 +904,9 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         xa.err = ctx->dev_error;
         xa.stamp = next_stamp();
         w->runs++;
-        return launch_pdl(ctx, wide_xchg_opt_kernel, dim3(grid), 0, xa, pdl);
+        rc = launch_pdl(ctx, wide_xchg_opt_kernel, dim3(grid), 0, xa, pdl);
+        w->kernels_per_step = (int)(ctx->launches - launches0);
+        return rc;
     }
     if (d.data_parallel && ctx->world > 1 && ctx->nccl_comm) {
         // sum of the per-rank mean gradients; the optimizer folds 1 / world (grad_scale)
@@ -988,8 +917,10 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
     }
     unsigned long long* opt_stamp = next_stamp();
     w->runs++;
-    return optimizer_step_split(ctx, d.optimizer, w->P, w->G, w->M, w->V, w->hyper, sgd_lr, grad_scale, (size_t)d.arena_len, w->w_split,
-                                w->w_split + w->arena_plane, pdl, opt_stamp);
+    rc = optimizer_step_split(ctx, d.optimizer, w->P, w->G, w->M, w->V, w->hyper, sgd_lr, grad_scale, (size_t)d.arena_len, w->w_split,
+                              w->w_split + w->arena_plane, pdl, opt_stamp);
+    w->kernels_per_step = (int)(ctx->launches - launches0);
+    return rc;
 }
 
 }  // namespace tp

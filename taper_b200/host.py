@@ -142,6 +142,20 @@ class Model:
     def zero_grad(self):
         check(lib.tp_model_zero_grad(self.h))
 
+    def forward_tensor(self, x: "Tensor") -> "Tensor":
+        """Module::forward on a device tensor (records tape nodes)."""
+        h = C.c_void_p()
+        check(lib.tp_module_forward(self.h, x.h, C.byref(h)))
+        return Tensor(_h=h)
+
+    def parameters(self):
+        out = []
+        for i in range(self.num_params()):
+            h = C.c_void_p()
+            check(lib.tp_model_parameter(self.h, i, C.byref(h)))
+            out.append(Tensor(_h=h))
+        return out
+
     def load_from_oracle(self, oracle_model):
         ps = oracle_model.parameters()
         assert len(ps) == self.num_params()
@@ -333,6 +347,142 @@ class Trainer:
         c = C.c_uint64()
         check(lib.tp_trainer_graph_replays(self.h, C.byref(c)))
         return c.value
+
+
+class Tensor:
+    """A device tensor handle of the host layer (taper::Tensor = the reference's Tensor, src/tensor.rs:236-244): every op
+    records the tape node the reference records.  What a Rust shim binds (rust/taper-b200)."""
+
+    def __init__(self, data=None, shape=None, requires_grad=False, _h=None):
+        if _h is not None:
+            self.h = _h
+            return
+        data = _f32(data)
+        shape = tuple(shape) if shape is not None else data.shape
+        self.h = C.c_void_p()
+        check(lib.tp_tensor_new(_fp(data), _shape(shape), len(shape), int(requires_grad), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_tensor_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        nd = C.c_int()
+        check(lib.tp_tensor_ndim(self.h, C.byref(nd)))
+        dims = (C.c_size_t * nd.value)()
+        check(lib.tp_tensor_shape(self.h, dims, nd.value))
+        return tuple(dims)
+
+    def data(self):
+        out = np.empty(int(np.prod(self.shape)), F32)
+        check(lib.tp_tensor_data(self.h, _fp(out), out.size))
+        return out.reshape(self.shape)
+
+    def grad(self):
+        out = np.empty(int(np.prod(self.shape)), F32)
+        has = C.c_int()
+        check(lib.tp_tensor_grad(self.h, _fp(out), out.size, C.byref(has)))
+        return out.reshape(self.shape) if has.value else None
+
+    def zero_grad(self):
+        check(lib.tp_tensor_zero_grad(self.h))
+
+    def backward(self):
+        check(lib.tp_tensor_backward(self.h))
+
+    def _un(self, op, arg=0.0):
+        h = C.c_void_p()
+        check(lib.tp_tensor_unary(op.encode(), self.h, arg, C.byref(h)))
+        return Tensor(_h=h)
+
+    def _bin(self, op, other):
+        h = C.c_void_p()
+        check(lib.tp_tensor_binary(op.encode(), self.h, other.h, C.byref(h)))
+        return Tensor(_h=h)
+
+    def relu(self): return self._un("relu")
+    def exp(self): return self._un("exp")
+    def log(self): return self._un("log")
+    def sigmoid(self): return self._un("sigmoid")
+    def mean(self): return self._un("mean")
+    def transpose(self): return self._un("transpose")
+    def pow(self, e): return self._un("pow", float(e))
+    def sqrt(self): return self._un("sqrt")
+    def matmul(self, o): return self._bin("matmul", o)
+    def add_broadcast(self, o): return self._bin("add_broadcast", o)
+    def __add__(self, o): return self._bin("add", o)
+    def __sub__(self, o): return self._bin("sub", o)
+    def __mul__(self, o): return self._bin("mul", o)
+    def __truediv__(self, o): return self._bin("div", o)
+
+    def reshape(self, shape):
+        h = C.c_void_p()
+        check(lib.tp_tensor_reshape(self.h, _shape(shape), len(shape), C.byref(h)))
+        return Tensor(_h=h)
+
+    def sum(self, dim=None, keepdim=False):
+        h = C.c_void_p()
+        check(lib.tp_tensor_sum(self.h, -1 if dim is None else int(dim), int(keepdim), C.byref(h)))
+        return Tensor(_h=h)
+
+    def argmax(self, dim=None):
+        h = C.c_void_p()
+        check(lib.tp_tensor_argmax(self.h, -1 if dim is None else int(dim), C.byref(h)))
+        return Tensor(_h=h)
+
+
+def tape_reset():
+    check(lib.tp_tape_reset())
+
+
+def tape_len() -> int:
+    n = C.c_size_t()
+    check(lib.tp_tape_len(C.byref(n)))
+    return n.value
+
+
+def loss(kind, predictions: Tensor, targets: Tensor) -> Tensor:
+    h = C.c_void_p()
+    check(lib.tp_loss(kind.encode(), predictions.h, targets.h, C.byref(h)))
+    return Tensor(_h=h)
+
+
+def accuracy(predictions: Tensor, targets: Tensor) -> float:
+    a = C.c_float()
+    check(lib.tp_accuracy(predictions.h, targets.h, C.byref(a)))
+    return a.value
+
+
+class Optimizer:
+    """optim::{SGD, Adam, AdamW} over tensor handles (src/optim.rs:8-181)."""
+
+    def __init__(self, kind, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = list(params)
+        arr = (C.c_void_p * len(self.params))(*[p.h for p in self.params])
+        self.h = C.c_void_p()
+        check(lib.tp_optimizer_create(kind.encode(), arr, len(self.params), lr, betas[0], betas[1], eps, weight_decay, C.byref(self.h)))
+
+    def step(self): check(lib.tp_optimizer_step(self.h))
+    def zero_grad(self): check(lib.tp_optimizer_zero_grad(self.h))
+    def set_lr(self, lr): check(lib.tp_optimizer_set_lr(self.h, lr))
+
+    def get_lr(self):
+        lr = C.c_float()
+        check(lib.tp_optimizer_get_lr(self.h, C.byref(lr)))
+        return lr.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.tp_optimizer_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 class Dataset:

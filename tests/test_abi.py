@@ -26,7 +26,7 @@ def test_no_torch_or_cxx_types_in_abi():
     from taper_b200 import capi
     allowed = {"int", "float", "size_t", "uint64_t", "uint32_t", "int64_t", "char", "void", "const", "*",
                "tp_ctx", "tp_buf", "tp_graph", "tp_event", "tp_model", "tp_trainer", "tp_conv_desc", "tp_pool_desc", "tp_step", "tp_step_desc", "tp_xchg",
-               "tp_dataset", "tp_loader", "tp_scheduler"}
+               "tp_dataset", "tp_loader", "tp_scheduler", "tp_tensor", "tp_optimizer"}
     for name, (ret, params) in capi.declared_symbols().items():
         for decl in [ret] + params:
             toks = set(decl.replace("*", " * ").split())
