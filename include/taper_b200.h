@@ -226,6 +226,20 @@ int tp_conv2d_fwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp
 int tp_conv2d_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* gy, const tp_buf* relu_mask_y,
                   tp_buf* dx, tp_buf* dw, tp_buf* db, const tp_conv_desc* d,
                   int acc_dx, int acc_dw, int acc_db);
+/* A stack of n_layers (<= 8) 3x3 / stride 1 / pad 1 convolutions, each + bias (+ ReLU when relu[l]) and, when pool[l],
+ * followed by a 2x2 / stride 2 max-pool, evaluated back to back:  x [N, C_in, H, W] fp32 NCHW -> y NCHW fp32 (the last
+ * layer's output, pooled if pool[last]).  Replaces the chain conv2d_relu -> max_pool2d -> conv2d_relu ... that
+ * Sequential::forward runs over examples/train_mnist_cnn.rs:35-100 (Tensor::conv2d src/tensor.rs:1221-1285, conv2d_relu
+ * :1379-1389, max_pool2d :1391-1464) when nothing but the last output is observed — the strict-reference tape, where
+ * im2col drops the autograd link, so no intermediate activation or pooling index is ever read again.
+ * weights[l]: the reference's [C_out, C_in, 3, 3] buffer read as [K = ci*9 + kr*3 + kc, C_out] (Appendix A2); biases[l]
+ * may be NULL.  Intermediate activations stay in the tensor cores' operand format (NHWC bf16 hi/lo pairs); products are
+ * bf16x3 (three bf16 MMAs per fp32 product, ~1e-5 of |y|inf), accumulation fp32.
+ * Shapes: C_in % 32 == 0 or C_in * 9 <= 36 (direct fp32 first layer, needs n_layers >= 2); every C_out in {32, 64, 128};
+ * W < 32.  Anything else: TP_ERR_UNSUPPORTED and nothing has been launched (callers run the layers one by one). */
+int tp_conv_stack_fwd(tp_ctx*, const tp_buf* x, int n, int c_in, int h, int w, int n_layers,
+                      const tp_buf* const* weights, const tp_buf* const* biases, const int* c_out,
+                      const int* pool, const int* relu, tp_buf* y);
 /* y = x + bias[c] per channel; gb[c] (+)= sum_{n,hw} g     add_bias_4d  src/tensor.rs:1972-2031 */
 int tp_add_bias_4d(tp_ctx*, const tp_buf* x, const tp_buf* bias, tp_buf* y, int n, int c, int hw, int relu);
 int tp_bias_grad_4d(tp_ctx*, const tp_buf* g, tp_buf* gb, int n, int c, int hw, int accumulate);

@@ -33,6 +33,10 @@ int tp_host_ctx(tp_ctx** out);
  *   reference_op_sequence  1 = Linear records transpose -> matmul -> add_broadcast exactly as src/nn.rs:54-60
  *   gemm_mode              0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (default), 2 = 1xTF32 tcgen05, 3 = bf16x3 tcgen05 */
 int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op_sequence, int gemm_mode);
+/* 1 (default) = Sequential runs a chain of >= 2 [Conv2d(ReLU) 3x3/s1/p1 (+ MaxPool2d 2x2)] layers as one tp_conv_stack_fwd
+ * (strict-reference conv autograd only: nothing but the chain's last output is read again); 0 = layer by layer,
+ * as Sequential::forward does in the reference (src/nn.rs:149-151) */
+int tp_host_config_conv_stack(int fuse_conv_stack);
 
 /* Sequential from a comma-separated layer list (the constructors of src/nn.rs, src/activation.rs):
  *   linear:IN:OUT[:nobias] | relu | sigmoid | conv:CIN:COUT:K:STRIDE:PAD | conv_relu:CIN:COUT:K:STRIDE:PAD |

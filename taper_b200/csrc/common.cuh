@@ -152,6 +152,11 @@ struct ConvShape {
 int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, const float* bias, int relu, float* y, const ConvShape& g);
 
 
+// ---- stack of 3x3 / s1 / p1 convolutions (+bias, optional ReLU, optional 2x2 max-pool each) on the tcgen05 bf16x3 path over NHWC
+// bf16 hi/lo planes (conv_bx3.cu); NCHW fp32 in and out.  TP_ERR_UNSUPPORTED (nothing launched) when a shape does not fit.
+int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int n_layers, const float* const* w2,
+                   const float* const* bias, const int* cout, const int* pool, const int* relu, float* y);
+
 // ---- bf16x3 tensor-core GEMM on pre-split operands (gemm_bx3.cu) -----------------------------------------------------
 // A "split" tensor holds an fp32 tensor of n elements as two bf16 planes: hi = rn_bf16(x) at [0, n) and
 // lo = rn_bf16(x - hi) `plane` elements further (plane >= n, multiple of 8).

@@ -287,10 +287,13 @@ int tp_col2im(tp_ctx* ctx, const tp_buf* gcol, tp_buf* gx, const tp_conv_desc* d
     return TP_OK;
 }
 
-// which kernel the last tp_conv2d_fwd of this thread ran: 1 direct small-K (CUDA cores), 2 implicit GEMM on tcgen05,
-// 3 materialised im2col + GEMM (tests assert that the BASELINE shapes really take the tensor-core path)
+// which kernel the last tp_conv2d_fwd of this thread ran: 1 direct small-K (CUDA cores), 2 implicit GEMM on tcgen05 (3xTF32,
+// LSU-gathered A tiles), 3 materialised im2col + GEMM, 4 TMA-fed implicit GEMM on bf16 hi/lo planes (conv_bx3.cu) — tests
+// assert that the BASELINE shapes really take the tensor-core paths
 static thread_local int g_last_conv_path = 0;
+static thread_local int g_conv_v2 = 1;
 int tpdbg_last_conv_path(void) { return g_last_conv_path; }
+int tpdbg_conv_v2(int enable) { g_conv_v2 = enable; return 0; }
 
 int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp_buf* y, const tp_conv_desc* d, int relu) {
     TP_CHECK_ARG(ctx, "tp_conv2d_fwd: NULL ctx");
@@ -314,6 +317,15 @@ int tp_conv2d_fwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* b
     // 3xTF32 mode: implicit GEMM — the tensor-core kernel gathers its A tiles from x itself and its epilogue writes NCHW +
     // bias (+ ReLU): neither the [M,K] im2col matrix (231 MB for the 32->32 layer at batch 256) nor the NHWC product ever
     // exists.  Other modes / shapes: materialised im2col + GEMM + transpose.
+    if (g_conv_v2 && (ctx->gemm_mode == 1 || ctx->gemm_mode == 3) && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 &&
+        g.pw == 1 && g.dh == 1 && g.dw == 1) {
+        // 3x3 / s1 / p1: NCHW -> NHWC bf16 hi/lo planes, then the TMA-fed tcgen05 kernel writes NCHW + bias (+ ReLU)
+        const float* wp[1] = {w->ptr};
+        const float* bp[1] = {b ? b->ptr : nullptr};
+        const int co[1] = {g.cout}, po[1] = {0}, re[1] = {relu ? 1 : 0};
+        rc = tp::conv_stack_fwd(ctx, x->ptr, g.n, g.c, g.h, g.w, 1, wp, bp, co, po, re, y->ptr);
+        if (rc != TP_ERR_UNSUPPORTED) { g_last_conv_path = 4; return rc; }
+    }
     if (ctx->gemm_mode == 1) {
         tp::ConvShape cs{g.n, g.c, g.h, g.w, g.cout, g.kh, g.kw, g.sh, g.sw, g.ph, g.pw, g.dh, g.dw, g.ho, g.wo, g.K};
         rc = tp::gemm_tc_conv_fwd(ctx, x->ptr, w->ptr, b ? b->ptr : nullptr, relu, y->ptr, cs);

@@ -1,0 +1,783 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05 (bf16x3, fp32 accumulation in TMEM) over
+// NHWC activations held as bf16 hi/lo pairs — and the chain of such layers (+ 2x2 max-pool) that the reference's CNNs
+// are made of (examples/train_mnist_cnn.rs:35-100; Tensor::conv2d / conv2d_relu src/tensor.rs:1221-1285, 1379-1389;
+// max_pool2d :1391-1464), run back to back without ever leaving that layout.
+//
+// Activation format ("planes"): element (n, y, x, c) of an [N, H, W, C] tensor, C % 32 == 0, lives at bf16 index
+//     (((n*H + y)*W + x) * C/32 + c/32) * 64 + hl*32 + c%32,        hl = 0: hi = rn_bf16(v), hl = 1: lo = rn_bf16(v - hi)
+// i.e. every pixel's 32-channel block is one 128-byte row [hi x32 | lo x32]: exactly one row of a K-major SWIZZLE_128B
+// UMMA operand, same 4 bytes per element as fp32.
+//
+// Implicit GEMM: M = output pixels, N = C_out, K = 9 taps x C_in.  The A operand is never gathered: ONE TMA box
+// {64 bf16, 1 channel block, Wp columns, Hp rows, G images} brings a zero-padded input patch (halo rows via negative /
+// out-of-range coordinates, which TMA zero-fills) into shared memory as Hp*Wp consecutive 128-byte rows, and the A tile
+// of tap (kr, kc) is that SAME patch read from a row offset:  start = patch + (kr*Wp + kc - 1) * 128 bytes.
+// Wp (8 / 16 / 32) is the patch's row pitch in pixels, > W, so column W of every patch row is a zero pixel and serves
+// as the right halo of its row and the left halo of the next one.  Row offsets that are not multiples of 8 rows leave
+// the 1024-byte swizzle atom alignment; measured on B200 (scripts/conv_stack_probe.py): the tensor core applies the 128-byte
+// swizzle to ABSOLUTE shared-memory address bits, exactly as TMA wrote them, so an unaligned start address with the
+// descriptor's base-offset field left 0 reads the shifted rows correctly (shift_mode 2, the default), whereas setting the base
+// offset to (start >> 7) & 7 (shift_mode 1) double-counts the phase and returns garbage.
+// (shift_mode 0, the conservative variant kept for cross-checking: three patches per channel block loaded at x = -1, 0, +1,
+// so every tap offset kr*Wp is atom-aligned — 3x the L2 -> shared-memory traffic, which then bounds the 28x28 layers.)
+// M tile = 128 consecutive patch rows = 128/Wp image rows (or, for images smaller than that, G whole images); rows that
+// fall on pad columns / halo rows compute junk that the epilogue drops (12.5 % of the MMA rows at 28x28, 23 % at 14x14 / 7x7 —
+// the kernel is shared-memory-port bound, not MMA bound).
+// Products: per tap and 32-channel block, A_lo*B_hi + A_hi*B_lo + A_hi*B_hi as 6 MMAs of 128 x C_out x 16 (kind::f16).
+// Weights [K = ci*9 + tap, C_out] (the reference's reinterpretation of the [C_out, C_in, 3, 3] buffer) are
+// re-laid once per step as planes [ci/32][tap][co][hi x32 | lo x32] and either stay resident in shared memory for the
+// whole kernel (<= 80 KB) or stream through a second ring.
+// Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue on a
+// double-buffered TMEM accumulator (tile i+1 multiplies while tile i is read out): bias + ReLU (+ 2x2 max-pool through a
+// shared-memory staging tile) and either the planes of the next layer or NCHW fp32 for the rest of the tape.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kConvThreads = 192;
+constexpr int kMaxRing = 8;
+constexpr int kMaxPrep = 8;
+
+struct ConvP {
+    int N, H, W, CB, Cout;           // input [N, H, W, 32*CB] planes
+    int Wp, R, Hp, G;                // patch pitch, image rows per tile, patch rows per image, images per tile
+    int row_blocks, tiles;
+    int img_rows;                    // Hp * Wp: patch rows per image
+    int patch_bytes;                 // G * Hp * Wp * 128: bytes one TMA box delivers
+    int patch_alloc;                 // bytes reserved per patch (>= patch_bytes and >= what 128 rows + the tap shifts read)
+    int shift_mode;                  // 0: three patches (x = -1, 0, +1), atom-aligned taps; 1 / 2: one patch, row-shifted taps (base offset set / 0)
+    int dbg;                         // development: bit 0 hi*hi products only, bit 1 epilogue reads the accumulator but stores nothing
+    int a_stage_bytes, nA;
+    int w_resident, b_stage_bytes, nB;
+    int out_mode;                    // 0: planes (next conv), 1: NCHW fp32
+    int pool, relu;
+    int Ho, Wo;                      // output spatial size (after the pool)
+    const float* bias;
+    uint16_t* out_planes;
+    float* out_nchw;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// K-major SWIZZLE_128B operand descriptor, split in two 32-bit words so that stepping through a tile is one 32-bit add:
+//   lo = start address >> 4 (bits 0-13) | LBO = 16 B (bit 16, unused by swizzled K-major layouts)
+//   hi = SBO = 1024 B (8 rows of 128 B per swizzle atom) | descriptor version 1 (bit 46) | base offset (bits 49-51) | SWIZZLE_128B (2 << 61)
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return (saddr >> 4) | 0x10000u; }      // saddr < 256 KB
+__device__ __forceinline__ void mma_bf16_w(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+// 8 values -> 16 bytes of hi and 16 bytes of lo
+__device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+    *hi = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvP p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + p.nA * p.a_stage_bytes;
+    const int b_total = p.w_resident ? 9 * p.CB * BN * 128 : p.nB * p.b_stage_bytes;
+    constexpr int kPitch = BN + 4;                                    // floats per staged row (pool)
+    float* stage = (float*)(b_ring + b_total);
+    uint64_t* bars = (uint64_t*)((uint8_t*)stage + (p.pool ? 128 * kPitch * 4 : 0));
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + kMaxRing;
+    uint64_t* b_full = a_empty + kMaxRing;
+    uint64_t* b_empty = b_full + kMaxRing;
+    uint64_t* acc_full = b_empty + kMaxRing;                          // [2]
+    uint64_t* acc_empty = acc_full + 2;                               // [2]
+    uint64_t* w_full = acc_empty + 2;
+    uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < kMaxRing; ++s) {
+            mbar_init(a_full + s, 1);
+            mbar_init(a_empty + s, 1);
+            mbar_init(b_full + s, 1);
+            mbar_init(b_empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 4);
+        }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p.shift_mode) {
+        // the row in front of every patch is the left halo of the patch's first pixel: zero, never written by TMA
+        for (int i = threadIdx.x; i < p.nA * 256; i += kConvThreads)
+            *(uint32_t*)(a_ring + (i >> 8) * p.a_stage_bytes + (i & 255) * 4) = 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the previous kernel; its output (this layer's input planes) is complete after the wait.
+    // The dependents are released only after our own wait, so "complete" is transitive along the chain of launches.
+    pdl_wait();
+    pdl_launch_dependents();
+
+    const int patch_off = p.shift_mode ? 1024 : 0;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            if (p.w_resident) {
+                mbar_expect_tx(w_full, 9 * p.CB * BN * 128);
+                for (int g = 0; g < 3 * p.CB; ++g) tma_load_3d(b_ring + g * 3 * BN * 128, &map_w, w_full, 0, 0, g * 3);
+            }
+            int ai = 0, bi = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int ng = tile / p.row_blocks, rb = tile - ng * p.row_blocks;
+                const int n0 = ng * p.G, y0 = rb * p.R;
+                for (int cb = 0; cb < p.CB; ++cb) {
+                    const int s = ai % p.nA;
+                    mbar_wait(a_empty + s, ((ai / p.nA) & 1) ^ 1);
+                    uint8_t* dst = a_ring + s * p.a_stage_bytes + patch_off;
+                    if (p.shift_mode) {
+                        mbar_expect_tx(a_full + s, p.patch_bytes);
+                        tma_load_5d(dst, &map_x, a_full + s, 0, cb, 0, y0 - 1, n0);
+                    } else {
+                        mbar_expect_tx(a_full + s, 3 * p.patch_bytes);
+                        for (int kc = 0; kc < 3; ++kc) tma_load_5d(dst + kc * p.patch_alloc, &map_x, a_full + s, 0, cb, kc - 1, y0 - 1, n0);
+                    }
+                    ++ai;
+                    if (!p.w_resident) {
+                        for (int kr = 0; kr < 3; ++kr) {
+                            const int sb = bi % p.nB;
+                            mbar_wait(b_empty + sb, ((bi / p.nB) & 1) ^ 1);
+                            mbar_expect_tx(b_full + sb, 3 * BN * 128);
+                            tma_load_3d(b_ring + sb * p.b_stage_bytes, &map_w, b_full + sb, 0, 0, cb * 9 + kr * 3);
+                            ++bi;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D = F32 (1 << 4), A / B = BF16 (1 << 7, 1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            if (p.w_resident) {
+                mbar_wait(w_full, 0);
+                tc_fence_after();
+            }
+            int ai = 0, bi = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int cb = 0; cb < p.CB; ++cb) {
+                    const int s = ai % p.nA;
+                    mbar_wait(a_full + s, (ai / p.nA) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(a_ring + s * p.a_stage_bytes + patch_off);
+                    for (int kr = 0; kr < 3; ++kr) {
+                        uint32_t b0;
+                        int sb = 0;
+                        if (p.w_resident) {
+                            b0 = smem_u32(b_ring + (cb * 9 + kr * 3) * BN * 128);
+                        } else {
+                            sb = bi % p.nB;
+                            mbar_wait(b_full + sb, (bi / p.nB) & 1);
+                            tc_fence_after();
+                            b0 = smem_u32(b_ring + sb * p.b_stage_bytes);
+                        }
+#pragma unroll
+                        for (int kc = 0; kc < 3; ++kc) {
+                            const uint32_t ah = p.shift_mode ? a0 + (uint32_t)((kr * p.Wp + kc - 1) * 128)
+                                                             : a0 + (uint32_t)(kc * p.patch_alloc + kr * p.Wp * 128);
+                            const uint32_t al = desc_lo(ah), bl = desc_lo(b0 + kc * BN * 128);
+                            const uint32_t ahi = kDescHi | (p.shift_mode == 1 ? ((ah >> 7) & 7u) << 17 : 0u);
+                            const uint32_t fresh = (cb == 0 && kr == 0 && kc == 0) ? 1u : 0u;
+                            // [hi x32 | lo x32] rows: hi at byte 0 / 32 (two K = 16 steps = +0 / +2 descriptor units), lo at 64 / 96
+                            // (+4 / +6); small terms first
+                            if (!(p.dbg & 1)) {
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    mma_bf16_w(tmem_d, al + 4 + 2 * kk, ahi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, ahi, bl + 4 + 2 * kk, kDescHi, idesc, 1u);
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, ahi, bl + 2 * kk, kDescHi, idesc, 1u);
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk)
+                                    mma_bf16_w(tmem_d, al + 2 * kk, ahi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
+                            }
+                        }
+                        if (!p.w_resident) {
+                            tc_commit(b_empty + sb);
+                            ++bi;
+                        }
+                    }
+                    tc_commit(a_empty + s);
+                    ++ai;
+                }
+                tc_commit(acc_full + buf);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2-5: TMEM lane quarter q = warp & 3, thread = tile row =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int img = r / p.img_rows, rem = r - img * p.img_rows;
+        const int ri = rem / p.Wp, rj = rem - ri * p.Wp;
+        const int et = threadIdx.x - 64;                                  // 0..127 in warp order 2,3,4,5
+        const int CBo = BN / 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int ng = tile / p.row_blocks, rb = tile - ng * p.row_blocks;
+            const int n0 = ng * p.G, y0 = rb * p.R;
+            const int n = n0 + img, y = y0 + ri, x = rj;
+            const bool valid = img < p.G && n < p.N && ri < p.R && y < p.H && x < p.W;
+            mbar_wait(acc_full + buf, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float t = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.0f);
+                    o[j] = p.relu ? fmaxf(t, 0.0f) : t;
+                }
+                if (p.dbg & 2) {
+                } else if (p.pool) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *(float4*)(stage + r * kPitch + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                } else if (valid) {
+                    if (p.out_mode == 0) {
+                        uint16_t* dst = p.out_planes + ((((size_t)n * p.H + y) * p.W + x) * CBo + (c0 >> 5)) * 64 + (c0 & 31);
+                        uint4 h0, l0, h1, l1;
+                        split8(o, &h0, &l0);
+                        split8(o + 8, &h1, &l1);
+                        *(uint4*)dst = h0;
+                        *(uint4*)(dst + 8) = h1;
+                        *(uint4*)(dst + 32) = l0;
+                        *(uint4*)(dst + 40) = l1;
+                    } else {
+                        float* dst = p.out_nchw + (((size_t)n * BN + c0) * p.H + y) * p.W + x;
+                        const size_t cs = (size_t)p.H * p.W;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dst[j * cs] = o[j];
+                    }
+                }
+            }
+            // the accumulator buffer is free as soon as it has been read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+            if (p.pool && !(p.dbg & 2)) {
+                epi_bar_sync();
+                // 32 pooled slots per tile (slot = lane), BN/4 channels per thread (channel quarter = warp).  The tile's rows
+                // are Wp-wide image rows stacked over the G images (Hp rows each, Hp even whenever G > 1, and R even): stacked rows
+                // (2k, 2k+1) are the two source rows of pooled row k.
+                const int Wh = p.Wp >> 1;
+                const int pr = lane / Wh, pc = lane - pr * Wh;
+                const int trow = 2 * pr;
+                const int timg = trow / p.Hp, tri = trow - timg * p.Hp;
+                const int src = trow * p.Wp + 2 * pc;
+                const int pn = n0 + timg, py = (y0 + tri) >> 1, px = pc;
+                const bool pvalid = timg < p.G && pn < p.N && (y0 + tri + 1) < p.H && (2 * pc + 1) < p.W;
+                constexpr int kCh = BN / 4;
+                const int cq = (et >> 5) * kCh;
+                if (pvalid) {
+                    float m[kCh];
+#pragma unroll
+                    for (int j = 0; j < kCh; j += 4) {
+                        const float4 a = *(const float4*)(stage + src * kPitch + cq + j);
+                        const float4 b = *(const float4*)(stage + (src + 1) * kPitch + cq + j);
+                        const float4 c = *(const float4*)(stage + (src + p.Wp) * kPitch + cq + j);
+                        const float4 d = *(const float4*)(stage + (src + p.Wp + 1) * kPitch + cq + j);
+                        m[j] = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+                        m[j + 1] = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+                        m[j + 2] = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+                        m[j + 3] = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+                    }
+                    if (p.out_mode == 0) {
+                        uint16_t* dst = p.out_planes + ((((size_t)pn * p.Ho + py) * p.Wo + px) * CBo + (cq >> 5)) * 64 + (cq & 31);
+#pragma unroll
+                        for (int j = 0; j < kCh; j += 8) {
+                            uint4 h, l;
+                            split8(m + j, &h, &l);
+                            *(uint4*)(dst + j) = h;
+                            *(uint4*)(dst + 32 + j) = l;
+                        }
+                    } else {
+                        float* dst = p.out_nchw + (((size_t)pn * BN + cq) * p.Ho + py) * p.Wo + px;
+                        const size_t cs = (size_t)p.Ho * p.Wo;
+#pragma unroll
+                        for (int j = 0; j < kCh; ++j) dst[j * cs] = m[j];
+                    }
+                }
+                epi_bar_sync();
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---- weights [K = ci*9 + tap, C_out] fp32 -> planes [ci/32][tap][co][hi x32 | lo x32] ----------------------------
+struct WPrep {
+    const float* w2[kMaxPrep];
+    uint16_t* dst[kMaxPrep];
+    int cin[kMaxPrep], cout[kMaxPrep];
+    int count;
+};
+__global__ void __launch_bounds__(256)
+conv_w_planes_kernel(const __grid_constant__ WPrep wp) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int l = blockIdx.y;
+    if (l >= wp.count) return;
+    const int cin = wp.cin[l], cout = wp.cout[l];
+    const int total = cin * 9 * cout;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const int co = e % cout, k = e / cout;                // k = ci*9 + tap: coalesced reads along co
+        const int ci = k / 9, tap = k - ci * 9;
+        const float v = __ldg(wp.w2[l] + e);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
+        uint16_t* d = wp.dst[l] + ((size_t)((ci >> 5) * 9 + tap) * cout + co) * 64 + (ci & 31);
+        d[0] = __bfloat16_as_ushort(h);
+        d[32] = __bfloat16_as_ushort(lo);
+    }
+}
+
+// ---- NCHW fp32 -> planes (first layer of a stack whose input already has >= 32 channels; the single-layer eager op) --------
+__global__ void __launch_bounds__(256)
+nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int C, int H, int W) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int CG = C / 8;
+    const size_t hw = (size_t)H * W, total = (size_t)N * hw * CG;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        // pixel fastest: a warp reads 32 consecutive x of one channel (coalesced), 8 channels per thread
+        const size_t pix = e % hw;
+        const size_t t = e / hw;
+        const int cg = (int)(t % CG);
+        const size_t n = t / CG;
+        const float* src = x + (n * C + cg * 8) * hw + pix;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j * hw);
+        uint4 h, l;
+        split8(v, &h, &l);
+        uint16_t* dst = out + ((n * hw + pix) * (C / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
+        *(uint4*)dst = h;
+        *(uint4*)(dst + 32) = l;
+    }
+}
+
+// ---- first layer with a tiny contraction (C_in * 9 <= 36: the C_in = 1 image layer): direct fp32 on the CUDA cores,
+// bias + ReLU (+ 2x2 max-pool) fused, output written straight as planes.  Exact fp32, k order (ci, kr, kc) ascending.
+// Replaces im2col + sgemm + transpose_4d + add_bias_4d + relu (+ max_pool2d) of src/tensor.rs:1221-1285, 1379-1464.
+__global__ void __launch_bounds__(256)
+conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ w2, const float* __restrict__ bias,
+                         uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int pool, int relu) {
+    extern __shared__ __align__(16) float sw[];                // [K][Cout] then [Cout]
+    const int K = Cin * 9;
+    float* sb = sw + K * Cout;
+    pdl_wait();
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < K * Cout; i += 256) sw[i] = __ldg(w2 + i);
+    for (int i = threadIdx.x; i < Cout; i += 256) sb[i] = bias ? __ldg(bias + i) : 0.0f;
+    __syncthreads();
+    const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+    const int CG = Cout / 8, nsub = pool ? 4 : 1;
+    const size_t total = (size_t)N * Ho * Wo * CG;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const int cg = (int)(e % CG);
+        const size_t pix = e / CG;
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const size_t n = pix / ((size_t)Wo * Ho);
+        float best[8];
+        for (int s = 0; s < nsub; ++s) {
+            const int yy = pool ? 2 * yo + (s >> 1) : yo, xx = pool ? 2 * xo + (s & 1) : xo;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float* xp = x + (n * Cin + ci) * (size_t)H * W;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+                    const float xv = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + (size_t)iy * W + ix) : 0.0f;
+                    const float4 wa = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8);
+                    const float4 wb = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8 + 4);
+                    acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]); acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
+                    acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]); acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = acc[j] + sb[cg * 8 + j];
+                if (relu) v = fmaxf(v, 0.0f);
+                best[j] = s == 0 ? v : fmaxf(best[j], v);
+            }
+        }
+        uint4 h, l;
+        split8(best, &h, &l);
+        uint16_t* dst = out + (pix * (Cout / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
+        *(uint4*)dst = h;
+        *(uint4*)(dst + 32) = l;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+constexpr int kSmemBudget = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers, TMEM slot*/;
+
+struct TmpBuf {
+    tp_buf* b = nullptr;
+    ~TmpBuf() { if (b) tp_buf_release(b); }
+};
+
+// geometry + shared-memory plan of one layer; false: this shape does not go through the kernel
+bool plan_layer(int N, int H, int W, int Cin, int Cout, bool pool, int out_mode, int shift_mode, ConvP* p, int* smem_bytes) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin % 32 || Cin <= 0) return false;
+    if (Cout != 32 && Cout != 64 && Cout != 128) return false;
+    if (W >= 32) return false;
+    if (pool && (H < 2 || W < 2)) return false;
+    ConvP q{};
+    q.N = N; q.H = H; q.W = W; q.CB = Cin / 32; q.Cout = Cout;
+    q.Wp = W < 8 ? 8 : W < 16 ? 16 : 32;
+    q.R = 128 / q.Wp;
+    if (H <= q.R) {
+        q.Hp = H + 2;
+        q.G = 1 + (q.R - H) / (H + 2);
+        q.row_blocks = 1;
+        if (pool && q.G > 1 && (q.Hp & 1)) {
+            // the pooled read-out pairs tile rows (2k, 2k+1) of the stacked images: every image must start on an even row
+            q.Hp += 1;
+            q.G = 1 + (q.R - H) / q.Hp;
+        }
+    } else {
+        q.Hp = q.R + 2;
+        q.G = 1;
+        q.row_blocks = (H + q.R - 1) / q.R;
+    }
+    if (q.Hp > 256 || q.G > 256) return false;
+    q.img_rows = q.Hp * q.Wp;
+    q.patch_bytes = q.G * q.img_rows * 128;
+    const int need_rows = 128 + 2 * q.Wp + 8;                         // what the nine shifted 128-row reads can touch
+    const int rows = q.G * q.img_rows > need_rows ? q.G * q.img_rows : need_rows;
+    q.patch_alloc = ((rows * 128 + 1023) / 1024) * 1024;
+    q.tiles = ((N + q.G - 1) / q.G) * q.row_blocks;
+    q.shift_mode = shift_mode;
+    q.a_stage_bytes = shift_mode ? 1024 + q.patch_alloc : 3 * q.patch_alloc;
+    const int stage_bytes = pool ? 128 * (Cout + 4) * 4 : 0;
+    const int w_bytes = 9 * q.CB * Cout * 128;
+    int left = kSmemBudget - stage_bytes;
+    if (w_bytes <= 80 * 1024 && left - w_bytes >= 2 * q.a_stage_bytes) {
+        q.w_resident = 1;
+        q.b_stage_bytes = 0; q.nB = 0;
+        int nA = (left - w_bytes) / q.a_stage_bytes;
+        q.nA = nA > 6 ? 6 : nA;
+    } else {
+        q.w_resident = 0;
+        q.b_stage_bytes = 3 * Cout * 128;
+        q.nA = shift_mode ? 3 : 2;
+        if (left - q.nA * q.a_stage_bytes < 2 * q.b_stage_bytes) q.nA = 2;
+        int nB = (left - q.nA * q.a_stage_bytes) / q.b_stage_bytes;
+        if (nB < 2) return false;
+        q.nB = nB > 6 ? 6 : nB;
+    }
+    q.out_mode = out_mode;
+    q.pool = pool ? 1 : 0;
+    q.relu = 1;
+    q.Ho = pool ? H / 2 : H;
+    q.Wo = pool ? W / 2 : W;
+    *p = q;
+    *smem_bytes = q.nA * q.a_stage_bytes + (q.w_resident ? w_bytes : q.nB * q.b_stage_bytes) + stage_bytes + 1024 + 512;
+    return true;
+}
+
+bool make_map_x(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, const ConvP& p) {
+    cuuint64_t gdim[5] = {64, (cuuint64_t)p.CB, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t gstr[4] = {128, (cuuint64_t)p.CB * 128, (cuuint64_t)p.W * p.CB * 128, (cuuint64_t)p.H * p.W * p.CB * 128};
+    cuuint32_t box[5] = {64, 1, (cuuint32_t)p.Wp, (cuuint32_t)p.Hp, (cuuint32_t)p.G};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_map_w(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, int CB, int Cout) {
+    cuuint64_t gdim[3] = {64, (cuuint64_t)Cout, (cuuint64_t)9 * CB};
+    cuuint64_t gstr[2] = {128, (cuuint64_t)Cout * 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)Cout, 3};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename... Args>
+int launch_pdl(tp_ctx* ctx, void (*kern)(Args...), dim3 grid, dim3 block, size_t smem, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    TP_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    TP_LAUNCH_OK(ctx);
+    return TP_OK;
+}
+
+template <int BN>
+int launch_conv(tp_ctx* ctx, const CUtensorMap& mx, const CUtensorMap& mw, const ConvP& p, int smem, bool pdl) {
+    auto kern = conv3x3_bx3_kernel<BN>;
+    // the opt-in is per device and monotone: keep the largest value ever requested
+    static int attr_smem[16] = {};
+    const int dev = ctx->device < 16 ? ctx->device : 15;
+    if (ctx->device >= 16 || attr_smem[dev] < smem) {
+        TP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem[dev] = smem;
+    }
+    const int grid = p.tiles < ctx->sm_count ? p.tiles : ctx->sm_count;
+    return launch_pdl(ctx, kern, dim3(grid), dim3(kConvThreads), (size_t)smem, pdl, mx, mw, p);
+}
+
+int launch_conv_any(tp_ctx* ctx, const CUtensorMap& mx, const CUtensorMap& mw, const ConvP& p, int smem, bool pdl) {
+    if (p.Cout == 32) return launch_conv<32>(ctx, mx, mw, p, smem, pdl);
+    if (p.Cout == 64) return launch_conv<64>(ctx, mx, mw, p, smem, pdl);
+    return launch_conv<128>(ctx, mx, mw, p, smem, pdl);
+}
+
+int default_shift_mode() {
+    static const int m = env_int("TAPER_CONV_SHIFT", 2);
+    return m;
+}
+
+thread_local int g_shift_override = -1;       // tests: force a shift mode for the calls of this thread
+thread_local int g_dbg_flags = 0;
+
+}  // namespace
+
+namespace tp {
+
+size_t conv_planes_floats(size_t n, size_t h, size_t w, size_t c) { return n * h * w * c; }     // 2 bf16 per element = 1 float
+
+// One stack of 3x3 / s1 / p1 Conv(+bias)+ReLU layers, each optionally followed by a 2x2 / s2 max-pool, NCHW fp32 in and out.
+// TP_ERR_UNSUPPORTED: some layer's shape does not go this way (nothing has been launched).
+int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int n_layers, const float* const* w2,
+                   const float* const* bias, const int* cout, const int* pool, const int* relu, float* y) {
+    if (n_layers < 1 || n_layers > kMaxPrep) return TP_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TP_ERR_UNSUPPORTED;
+    const int shift_mode = g_shift_override >= 0 ? g_shift_override : default_shift_mode();
+    cudaSetDevice(ctx->device);
+    // ---- plan every layer first (no launches before the whole stack is known to fit) ----
+    const bool first_direct = C0 * 9 <= 36;
+    if (first_direct && (n_layers < 2 || cout[0] % 32 || cout[0] > 256)) return TP_ERR_UNSUPPORTED;
+    if (!first_direct && C0 % 32) return TP_ERR_UNSUPPORTED;
+    ConvP P[kMaxPrep];
+    int smem[kMaxPrep];
+    int h = H, w = W, c = C0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (!(l == 0 && first_direct)) {
+            if (!plan_layer(N, h, w, c, cout[l], pool[l] != 0, l == n_layers - 1 ? 1 : 0, shift_mode, &P[l], &smem[l])) return TP_ERR_UNSUPPORTED;
+        }
+        if (pool[l]) { h /= 2; w /= 2; }
+        c = cout[l];
+        if (h < 1 || w < 1) return TP_ERR_UNSUPPORTED;
+    }
+    // ---- workspaces: weight planes of the tensor-core layers, two ping-pong activation buffers ----
+    int rc;
+    size_t wtot = 0, woff[kMaxPrep];
+    {
+        int ci = C0;
+        for (int l = 0; l < n_layers; ++l) {
+            woff[l] = wtot;
+            if (!(l == 0 && first_direct)) wtot += (size_t)ci * 9 * cout[l];
+            ci = cout[l];
+        }
+    }
+    TmpBuf wplanes, act[2];
+    if ((rc = tp_buf_alloc(ctx, wtot ? wtot : 1, &wplanes.b))) return rc;
+    size_t amax = first_direct ? 0 : (size_t)N * H * W * C0;
+    {
+        int hh = H, ww = W;
+        for (int l = 0; l + 1 < n_layers; ++l) {
+            if (pool[l]) { hh /= 2; ww /= 2; }
+            const size_t a = (size_t)N * hh * ww * cout[l];
+            if (a > amax) amax = a;
+        }
+    }
+    if ((rc = tp_buf_alloc(ctx, amax ? amax : 1, &act[0].b))) return rc;
+    if ((rc = tp_buf_alloc(ctx, amax ? amax : 1, &act[1].b))) return rc;
+    // ---- weight planes of all layers in one launch ----
+    WPrep wp{};
+    {
+        int ci = C0;
+        for (int l = 0; l < n_layers; ++l) {
+            if (!(l == 0 && first_direct)) {
+                const int i = wp.count++;
+                wp.w2[i] = w2[l];
+                wp.dst[i] = (uint16_t*)(wplanes.b->ptr + woff[l]);
+                wp.cin[i] = ci; wp.cout[i] = cout[l];
+            }
+            ci = cout[l];
+        }
+    }
+    if (wp.count) {
+        if ((rc = launch_pdl(ctx, conv_w_planes_kernel, dim3(32, wp.count), dim3(256), 0, false, wp))) return rc;
+    }
+    // ---- layers ----
+    int cur = 0;
+    h = H; w = W; c = C0;
+    int l0 = 0;
+    if (first_direct) {
+        const int ho = pool[0] ? h / 2 : h, wo = pool[0] ? w / 2 : w;
+        const size_t items = (size_t)N * ho * wo * (cout[0] / 8);
+        const size_t sm = (size_t)(C0 * 9 + 1) * cout[0] * sizeof(float);
+        if ((rc = launch_pdl(ctx, conv_first_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, true, x, w2[0], bias[0],
+                             (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], pool[0] ? 1 : 0, relu[0] ? 1 : 0)))
+            return rc;
+        h = ho; w = wo; c = cout[0];
+        l0 = 1;
+    } else {
+        const size_t items = (size_t)N * h * w * (c / 8);
+        if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, true, x, (uint16_t*)act[cur].b->ptr, N, c, h, w)))
+            return rc;
+    }
+    for (int l = l0; l < n_layers; ++l) {
+        ConvP& p = P[l];
+        p.bias = bias[l];
+        p.relu = relu[l] ? 1 : 0;
+        p.dbg = g_dbg_flags;
+        const bool last = l == n_layers - 1;
+        p.out_planes = last ? nullptr : (uint16_t*)act[cur ^ 1].b->ptr;
+        p.out_nchw = last ? y : nullptr;
+        CUtensorMap mx, mw;
+        if (!make_map_x(enc, &mx, (const uint16_t*)act[cur].b->ptr, p)) { set_error("conv_stack_fwd: cuTensorMapEncodeTiled (activations) failed"); return TP_ERR_CUDA; }
+        if (!make_map_w(enc, &mw, (const uint16_t*)(wplanes.b->ptr + woff[l]), p.CB, p.Cout)) { set_error("conv_stack_fwd: cuTensorMapEncodeTiled (weights) failed"); return TP_ERR_CUDA; }
+        if ((rc = launch_conv_any(ctx, mx, mw, p, smem[l], true))) return rc;
+        cur ^= 1;
+    }
+    return TP_OK;
+}
+
+}  // namespace tp
+
+extern "C" {
+
+int tpdbg_conv_shift_mode(int mode) {
+    g_shift_override = mode;
+    return 0;
+}
+int tpdbg_conv_flags(int flags) {
+    g_dbg_flags = flags;
+    return 0;
+}
+
+int tp_conv_stack_fwd(tp_ctx* ctx, const tp_buf* x, int n, int c_in, int h, int w, int n_layers, const tp_buf* const* weights,
+                      const tp_buf* const* biases, const int* c_out, const int* pool, const int* relu, tp_buf* y) {
+    TP_CHECK_ARG(ctx && x && weights && biases && c_out && pool && relu && y, "tp_conv_stack_fwd: NULL argument");
+    TP_CHECK_ARG(n_layers >= 1 && n_layers <= kMaxPrep, "tp_conv_stack_fwd: 1..%d layers", kMaxPrep);
+    TP_CHECK_ARG(n > 0 && c_in > 0 && h > 0 && w > 0, "tp_conv_stack_fwd: empty input");
+    TP_NEED(x, (size_t)n * c_in * h * w, "x");
+    const float* wp[kMaxPrep];
+    const float* bp[kMaxPrep];
+    int ci = c_in, hh = h, ww = w;
+    for (int l = 0; l < n_layers; ++l) {
+        TP_CHECK_ARG(c_out[l] > 0, "tp_conv_stack_fwd: layer %d has no output channels", l);
+        TP_NEED(weights[l], (size_t)ci * 9 * c_out[l], "weight");
+        if (biases[l]) TP_NEED(biases[l], (size_t)c_out[l], "bias");
+        wp[l] = weights[l]->ptr;
+        bp[l] = biases[l] ? biases[l]->ptr : nullptr;
+        if (pool[l]) { hh /= 2; ww /= 2; }
+        ci = c_out[l];
+    }
+    TP_CHECK_ARG(hh > 0 && ww > 0, "tp_conv_stack_fwd: the pools leave no output");
+    TP_NEED(y, (size_t)n * ci * hh * ww, "y");
+    int rc = tp::conv_stack_fwd(ctx, x->ptr, n, c_in, h, w, n_layers, wp, bp, c_out, pool, relu, y->ptr);
+    if (rc == TP_ERR_UNSUPPORTED) tp::set_error("tp_conv_stack_fwd: a layer's shape is outside the tensor-core stack (3x3/s1/p1, C_in %% 32 == 0 "
+                                                 "(or C_in*9 <= 36 for the first layer), C_out in {32, 64, 128}, W < 32)");
+    return rc;
+}
+
+}  // extern "C"

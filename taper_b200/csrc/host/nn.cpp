@@ -69,7 +69,40 @@ Tensor Dropout::forward(const Tensor& input) const {                            
 Tensor Sequential::forward(const Tensor& input) const {                         // src/nn.rs:149-151
     Tensor x = input;
     const bool fuse = Config::fuse_linear_relu() && !Config::reference_op_sequence();
+    const bool fuse_conv = Config::fuse_conv_stack() && !Config::reference_op_sequence() && !Config::conv_full_adjoint();
     for (size_t i = 0; i < layers.size(); ++i) {
+        if (fuse_conv && x.shape().size() == 4 && !x.needs_grad()) {
+            // peephole: [Conv2d(ReLU) 3x3 s1 p1 (+ MaxPool2d 2x2 s2)]+  ->  one stack on the tensor cores
+            std::vector<ConvStackLayer> run;
+            size_t j = i;
+            while (j < layers.size() && run.size() < 8) {
+                auto* cv = dynamic_cast<const Conv2d*>(layers[j].get());
+                if (!cv || cv->weight.shape()[2] != 3 || cv->weight.shape()[3] != 3 || cv->stride != Pair{1, 1} ||
+                    cv->padding != Pair{1, 1} || cv->dilation != Pair{1, 1} || cv->groups != 1)
+                    break;
+                ConvStackLayer ly;
+                ly.weight = cv->weight;
+                ly.bias = cv->bias;
+                ly.relu = dynamic_cast<const Conv2dReLU*>(cv) != nullptr;
+                ++j;
+                if (j < layers.size()) {
+                    auto* mp = dynamic_cast<const MaxPool2d*>(layers[j].get());
+                    if (mp && mp->kernel_size == Pair{2, 2} && mp->stride.value_or(mp->kernel_size) == Pair{2, 2} && mp->padding == Pair{0, 0}) {
+                        ly.pool = true;
+                        ++j;
+                    }
+                }
+                run.push_back(ly);
+            }
+            if (run.size() >= 2) {
+                Tensor y = x.conv_stack(run);
+                if (y.defined()) {
+                    x = y;
+                    i = j - 1;
+                    continue;
+                }
+            }
+        }
         if (fuse && i + 1 < layers.size()) {
             // peephole: Linear followed by ReLU -> bias + ReLU in the GEMM epilogue, mask folded into backward
             auto* lin = dynamic_cast<const Linear*>(layers[i].get());

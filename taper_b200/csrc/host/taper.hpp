@@ -39,9 +39,16 @@ struct Config {
     // true: nn::Linear records the reference's literal op sequence transpose -> matmul -> add_broadcast
     // (src/nn.rs:54-60, three tape nodes) instead of the single fused node.  Same numbers, more launches.
     static bool& reference_op_sequence();
+    // Sequential peephole: a run of >= 2 [Conv2d / Conv2dReLU (3x3, stride 1, pad 1)] (+ MaxPool2d 2x2) layers whose input
+    // carries no gradient runs as one stack on the tensor cores (tp_conv_stack_fwd: NHWC bf16 hi/lo activations between the
+    // layers, pooling in the conv epilogue).  Only under the strict-reference conv autograd (A1), where nothing but the
+    // stack's last output is ever read again; off under reference_op_sequence.  Same numbers within the bf16x3 bound.
+    static bool& fuse_conv_stack();
 };
 
 struct TensorImpl;
+
+struct ConvStackLayer;
 
 // ---- Tensor  (src/tensor.rs:236-244, 469-541) -----------------------------------------------------
 class Tensor {
@@ -99,12 +106,22 @@ public:
 
     // fused Linear (+ReLU): one node standing for transpose+matmul+add_broadcast(+relu) of src/nn.rs:54-60
     Tensor linear(const Tensor& weight, const Tensor* bias, bool relu) const;
+    // a stack of 3x3 / s1 / p1 convolutions (+bias, +ReLU, + 2x2 max-pool) as one fused forward (Config::fuse_conv_stack);
+    // records the one node the strict-reference tape can ever deliver through: the last layer's bias gradient.
+    // Returns an undefined Tensor when the shapes are outside the fused kernels (the caller runs the layers one by one).
+    Tensor conv_stack(const std::vector<ConvStackLayer>& layers) const;
 
 private:
     Tensor conv2d_impl(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation, bool relu) const;
     std::shared_ptr<TensorImpl> impl_;
     bool requires_grad_ = false;
     friend struct TensorImpl;
+};
+
+struct ConvStackLayer {           // one layer of Tensor::conv_stack: conv 3x3 / s1 / p1 + bias (+ ReLU) (+ 2x2 / s2 max-pool)
+    Tensor weight;
+    std::optional<Tensor> bias;
+    bool relu = true, pool = false;
 };
 
 Tensor operator+(const Tensor& a, const Tensor& b);     // src/ops.rs:8-52

@@ -50,6 +50,7 @@ void synchronize() { check(tp_sync(ctx())); }
 
 bool& Config::conv_full_adjoint() { static thread_local bool v = false; return v; }
 bool& Config::fuse_linear_relu() { static thread_local bool v = true; return v; }
+bool& Config::fuse_conv_stack() { static thread_local bool v = true; return v; }
 bool& Config::reference_op_sequence() { static thread_local bool v = false; return v; }
 
 // ---- TensorImpl -----------------------------------------------------------------------------------
@@ -653,6 +654,67 @@ Tensor Tensor::conv2d_relu(const Tensor& weight, const Tensor* bias, Pair stride
     // mask is folded into the backward.  With no bias in strict mode the reference's output does not
     // require grad, which conv2d_impl reproduces.
     return conv2d_impl(weight, bias, stride, padding, dilation, true);
+}
+
+// ---- a stack of conv2d_relu (+ max_pool2d) layers as one fused forward (tp_conv_stack_fwd) ------------------------------------
+// Strict-reference autograd only: im2col / transpose_4d drop the tape links, so of everything these layers record
+// only the LAST layer's add_bias_4d node (src/tensor.rs:2003-2027) ever sees a gradient — through that layer's ReLU
+// (src/ops.rs:358-370) and, when it is pooled, through max_pool2d's scatter (src/tensor.rs:1476-1516), which hands every
+// pooled gradient to exactly one pre-pool unit whose ReLU gate equals [pooled output > 0].  Hence
+//     bias.grad[c] (+)= sum_{n, p} g[n, c, p] * [out[n, c, p] > 0]          (out = the stack's output, pooled or not)
+// and no intermediate activation or pooling index is needed.
+Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers) const {
+    if (shape().size() != 4 || layers.empty() || layers.size() > 8 || needs_grad() || Config::conv_full_adjoint()) return Tensor();
+    const int L = (int)layers.size();
+    const tp_buf* wb[8];
+    const tp_buf* bb[8];
+    int co[8], po[8], re[8];
+    size_t c = shape()[1], h = shape()[2], w = shape()[3];
+    for (int l = 0; l < L; ++l) {
+        const Tensor& wt = layers[l].weight;
+        if (wt.shape().size() != 4 || wt.shape()[1] != c || wt.shape()[2] != 3 || wt.shape()[3] != 3) return Tensor();
+        if (layers[l].bias && (layers[l].bias->shape().size() != 1 || layers[l].bias->shape()[0] != wt.shape()[0])) return Tensor();
+        wb[l] = wt.buf();
+        bb[l] = layers[l].bias ? layers[l].bias->buf() : nullptr;
+        co[l] = (int)wt.shape()[0];
+        po[l] = layers[l].pool ? 1 : 0;
+        re[l] = layers[l].relu ? 1 : 0;
+        c = wt.shape()[0];
+        if (layers[l].pool) { h /= 2; w /= 2; }
+    }
+    if (!h || !w) return Tensor();
+    const size_t n = shape()[0];
+    Tensor out = Tensor::empty({n, c, h, w});
+    int rc = tp_conv_stack_fwd(ctx(), buf(), (int)n, (int)shape()[1], (int)shape()[2], (int)shape()[3], L, wb, bb, co, po, re, out.buf());
+    if (rc == TP_ERR_UNSUPPORTED) return Tensor();
+    check(rc);
+    const ConvStackLayer& last = layers[L - 1];
+    if (last.bias && last.bias->needs_grad()) {
+        out.set_requires_grad(true);
+        Tensor b = *last.bias;
+        const bool relu = last.relu;
+        const int nn = (int)n, cc = (int)c, hw = (int)(h * w);
+        // the closure keeps every weight alive like the reference's per-layer closures do
+        std::vector<Tensor> keep;
+        for (auto& ly : layers) keep.push_back(ly.weight);
+        tape_push(out, [b, out, relu, nn, cc, hw, keep]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            int ab = 0;
+            tp_buf* gb = b.impl()->grad_for_write(&ab);
+            if (relu) {
+                tp_buf* masked = nullptr;
+                check(tp_buf_alloc(ctx(), (size_t)nn * cc * hw, &masked));
+                int rc2 = tp_relu_bwd(ctx(), out.buf(), g, masked, (size_t)nn * cc * hw, 0);
+                if (!rc2) rc2 = tp_bias_grad_4d(ctx(), masked, gb, nn, cc, hw, ab);
+                tp_buf_release(masked);
+                check(rc2);
+            } else {
+                check(tp_bias_grad_4d(ctx(), g, gb, nn, cc, hw, ab));
+            }
+        });
+    }
+    return out;
 }
 
 // ---- pooling  (src/tensor.rs:1391-1660) ---------------------------------------------------------------------------------------------

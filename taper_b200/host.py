@@ -41,6 +41,10 @@ def config(conv_full_adjoint=-1, fuse_linear_relu=-1, reference_op_sequence=-1, 
     check(lib.tp_host_config(int(conv_full_adjoint), int(fuse_linear_relu), int(reference_op_sequence), int(gemm_mode)))
 
 
+def config_conv_stack(fuse=1):
+    check(lib.tp_host_config_conv_stack(int(fuse)))
+
+
 def host_ctx():
     h = C.c_void_p()
     check(lib.tp_host_ctx(C.byref(h)))

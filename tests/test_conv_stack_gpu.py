@@ -1,0 +1,184 @@
+"""tp_conv_stack_fwd (conv_bx3.cu): chains of 3x3 / s1 / p1 Conv + bias (+ ReLU) (+ 2x2 max-pool) on the TMA-fed tcgen05 bf16x3
+kernel over NHWC bf16 hi/lo planes, against the oracle's layer-by-layer conv2d_relu / max_pool2d (src/tensor.rs:1221-1285,
+1379-1389, 1391-1464).  Covers both tap-addressing variants of the kernel (three atom-aligned patches; one patch read through
+row-shifted descriptors), every tile geometry the MNIST models produce (28x28: 4 rows x 32 columns per tile, 14x14: 8 x 16,
+7x7: two images per tile), ragged batches against the images-per-tile packing, resident and streamed weights, the planes
+-> planes and planes -> NCHW epilogues with and without pooling, and the Sequential peephole that feeds it.
+Tolerance: 1e-4 of ||ref||_inf (north_star); measured ~5e-6 per layer, ~1.5e-5 after five layers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import taper_ref as R
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture()
+def ctx():
+    import taper_b200
+    from taper_b200 import capi
+    c = taper_b200.Ctx(0)
+    yield c
+    capi.lib.tpdbg_conv_shift_mode(-1)
+    c.close()
+
+
+def oracle_stack(x, ws, bs, pools, relus):
+    t = R.Tensor.new(x, x.shape)
+    for w, b, pool, relu in zip(ws, bs, pools, relus):
+        wt = R.Tensor.new(w, w.shape)
+        bt = R.Tensor.new(b, b.shape) if b is not None else None
+        t = t.conv2d_relu(wt, bt, (1, 1), (1, 1), (1, 1)) if relu else t.conv2d(wt, bt, (1, 1), (1, 1), (1, 1))
+        if pool:
+            t = t.max_pool2d((2, 2), (2, 2))
+    return t.data().reshape(t.shape)
+
+
+def run_stack(ctx, x, ws, bs, pools, relus, expect_rc=0):
+    from taper_b200 import capi
+    lib = capi.lib
+    n, c, h, w = x.shape
+    L = len(ws)
+    xb = ctx.upload(x)
+    wb = [ctx.upload(v) for v in ws]
+    bb = [ctx.upload(v) if v is not None else None for v in bs]
+    hh, ww = h, w
+    for p in pools:
+        if p:
+            hh //= 2
+            ww //= 2
+    cout = [v.shape[0] for v in ws]
+    y = ctx.alloc(n * cout[-1] * hh * ww)
+    capi.check(lib.tp_buf_fill(ctx.h, y.h, -7.0, y.n))
+    W = (C.c_void_p * L)(*[b.h for b in wb])
+    B = (C.c_void_p * L)(*[(b.h if b is not None else None) for b in bb])
+    co = (C.c_int * L)(*cout)
+    po = (C.c_int * L)(*[int(p) for p in pools])
+    re = (C.c_int * L)(*[int(r) for r in relus])
+    rc = lib.tp_conv_stack_fwd(ctx.h, xb.h, n, c, h, w, L, W, B, co, po, re, y.h)
+    if expect_rc:
+        assert rc == expect_rc, rc
+        return None
+    capi.check(rc)
+    return y.download().reshape(n, cout[-1], hh, ww)
+
+
+def make(rng, n, c0, hw, couts, bias=True):
+    x = rng.random((n, c0, hw, hw)).astype(F32)
+    ws, bs = [], []
+    ci = c0
+    for co in couts:
+        ws.append((rng.standard_normal((co, ci, 3, 3)) * np.sqrt(2.0 / (ci * 9))).astype(F32))
+        bs.append((rng.standard_normal(co) * 0.05).astype(F32) if bias else None)
+        ci = co
+    return x, ws, bs
+
+
+def close(got, ref, tol, what):
+    scale = max(float(np.abs(ref).max()), 1e-6)
+    err = float(np.abs(got - ref).max())
+    assert not np.isnan(got).any(), what
+    assert err <= tol * scale, f"{what}: max |diff| {err:.3e} > {tol:g} * {scale:.3e}"
+
+
+CASES = [
+    # name, n, c0, hw, couts, pools
+    ("32->32 @28", 3, 32, 28, [32], [0]),
+    ("32->32 @28 pool", 3, 32, 28, [32], [1]),
+    ("32->64 @14", 5, 32, 14, [64], [0]),
+    ("64->64 @14 pool", 5, 64, 14, [64], [1]),
+    ("64->128 @7, odd batch on two images per tile", 5, 64, 7, [128], [0]),
+    ("64->128 @7, one image", 1, 64, 7, [128], [0]),
+    ("64->32 @20 (ragged last row block)", 2, 64, 20, [32], [0]),
+    ("32->64 @5 pool (odd size, floor pooling)", 7, 32, 5, [64], [1]),
+    ("128->128 @7 (streamed weights)", 3, 128, 7, [128], [0]),
+    ("128->64 @14 pool (streamed weights)", 2, 128, 14, [64], [1]),
+    ("96->32 @9 (three channel blocks)", 4, 96, 9, [32], [0]),
+    ("example CNN stack", 5, 1, 28, [32, 32, 64, 64, 128], [0, 1, 0, 1, 0]),
+    ("contract CNN stack", 6, 1, 28, [32, 64], [1, 1]),
+    ("3-channel image stack", 3, 3, 16, [32, 32], [0, 1]),
+    ("32-channel input stack", 3, 32, 12, [64, 64, 32], [1, 0, 0]),
+]
+
+
+@pytest.mark.parametrize("mode", [2, 0])
+@pytest.mark.parametrize("name,n,c0,hw,couts,pools", CASES, ids=[c[0] for c in CASES])
+def test_conv_stack_vs_oracle(ctx, mode, name, n, c0, hw, couts, pools):
+    from taper_b200 import capi
+    capi.lib.tpdbg_conv_shift_mode(mode)
+    rng = np.random.default_rng(abs(hash((n, c0, hw, tuple(couts)))) % (2 ** 31))
+    x, ws, bs = make(rng, n, c0, hw, couts)
+    relus = [1] * len(couts)
+    ref = oracle_stack(x, ws, bs, pools, relus)
+    got = run_stack(ctx, x, ws, bs, pools, relus)
+    assert not (got == -7.0).any(), "output elements left unwritten"
+    close(got, ref, 1e-4, name)
+    flips = int(np.sum((got > 0) != (ref > 0)))
+    assert flips <= 1e-4 * ref.size + 2, f"{flips} of {ref.size} ReLU decisions differ"
+
+
+def test_conv_stack_without_bias_and_relu(ctx):
+    rng = np.random.default_rng(5)
+    x, ws, _ = make(rng, 3, 32, 14, [64, 32])
+    x = (x - 0.5).astype(F32)                                              # signed inputs: cancellation in the sums
+    ref = oracle_stack(x, ws, [None, None], [0, 0], [0, 0])
+    got = run_stack(ctx, x, ws, [None, None], [0, 0], [0, 0])
+    close(got, ref, 1e-4, "no bias, no relu")
+    assert (got < 0).any()
+
+
+TP_ERR_UNSUPPORTED = 5            # include/taper_b200.h
+
+
+def test_conv_stack_rejects_shapes_outside_the_kernel(ctx):
+    """W >= 32, C_in not a multiple of 32, C_out outside {32, 64, 128}, a lone small-K layer: status 5 and nothing launched (the
+    host layer then runs the layers one by one)."""
+    rng = np.random.default_rng(6)
+    for (c0, hw, couts) in [(32, 32, [32]), (16, 14, [32]), (32, 14, [48]), (1, 28, [32])]:
+        x, ws, bs = make(rng, 2, c0, hw, couts)
+        l0 = ctx.launches()
+        run_stack(ctx, x, ws, bs, [0] * len(couts), [1] * len(couts), expect_rc=TP_ERR_UNSUPPORTED)
+        assert ctx.launches() - l0 <= 1            # the fill of y in run_stack
+
+
+def test_example_cnn_stack_at_baseline_batch_vs_oracle(ctx):
+    """The five conv layers of the shipped example model (examples/train_mnist_cnn.rs:35-100) at configs[2]'s batch 256 through
+    one tp_conv_stack_fwd: 1792 + 512 + 512 + 128 tensor-core tiles."""
+    rng = np.random.default_rng(11)
+    x, ws, bs = make(rng, 256, 1, 28, [32, 32, 64, 64, 128])
+    pools = [0, 1, 0, 1, 0]
+    ref = oracle_stack(x, ws, bs, pools, [1] * 5)
+    got = run_stack(ctx, x, ws, bs, pools, [1] * 5)
+    close(got, ref, 1e-4, "example CNN stack, batch 256")
+
+
+def test_conv2_layer_at_config4_batch_vs_oracle(ctx):
+    """The 32 -> 32 layer at 28x28 with its pool at configs[4]'s batch 1024: 7168 tiles over the persistent CTAs."""
+    rng = np.random.default_rng(12)
+    x, ws, bs = make(rng, 1024, 32, 28, [32])
+    ref = oracle_stack(x, ws, bs, [1], [1])
+    got = run_stack(ctx, x, ws, bs, [1], [1])
+    close(got, ref, 1e-4, "32 -> 32 @28 + pool, batch 1024")
+
+
+def test_sequential_peephole_runs_the_stack_and_matches_layer_by_layer():
+    """Sequential::forward with the conv-stack peephole on / off: same output within the bf16x3 bound, far fewer launches; the
+    backward through the stack's one tape node delivers the last conv's bias gradient exactly like the per-layer tape."""
+    from taper_b200 import host
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    rng = np.random.default_rng(3)
+    x = rng.random((6, 1, 28, 28)).astype(F32)
+    outs, launches = [], []
+    for fuse in (1, 0):
+        host.config_conv_stack(fuse)
+        m = host.Model(host.CNN5, 7)
+        m.forward(x)                                                        # sizes the allocator caches
+        l0 = host.launches()
+        outs.append(m.forward(x))
+        launches.append(host.launches() - l0)
+    host.config_conv_stack(1)
+    close(outs[0], outs[1], 1e-4, "fused vs per-layer logits")
+    assert launches[0] + 6 <= launches[1], launches

@@ -192,18 +192,24 @@ def test_cuda_reproduces_golden_conv_pool():
 
 
 @pytest.mark.gpu
-def test_cuda_reproduces_golden_conv_on_the_tcgen05_path():
-    """C_out = 32, K = 288: this fixture goes through the implicit-GEMM tensor-core kernel (asserted), unlike conv_pool.npz whose
-    C_out = 4 layer takes the direct kernel."""
+@pytest.mark.parametrize("path", [4, 2])
+def test_cuda_reproduces_golden_conv_on_the_tcgen05_path(path):
+    """C_out = 32, K = 288: this fixture goes through the implicit-GEMM tensor-core kernels (asserted: 4 = the TMA-fed bf16x3
+    kernel of conv_bx3.cu, 2 = round 1's 3xTF32 kernel with gathered A tiles), unlike conv_pool.npz whose C_out = 4 layer takes
+    the direct kernel."""
     from taper_b200 import host, capi
     host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
-    fx = np.load(os.path.join(HERE, "conv_igemm.npz"))
-    m = host.Model("conv_relu:32:32:3:1:1", 0)
-    m.set_param(0, fx["w"])
-    m.set_param(1, fx["b"])
-    close(m.forward(fx["x"]), fx["conv_relu"], 1e-4, "conv_relu 32 -> 32")
-    assert capi.lib.tpdbg_last_conv_path() == 2
-    m2 = host.Model("conv_relu:32:32:3:1:1,maxpool:2:2", 0)
-    m2.set_param(0, fx["w"])
-    m2.set_param(1, fx["b"])
-    close(m2.forward(fx["x"]), fx["maxpool"], 1e-4, "conv_relu -> maxpool")
+    capi.lib.tpdbg_conv_v2(1 if path == 4 else 0)
+    try:
+        fx = np.load(os.path.join(HERE, "conv_igemm.npz"))
+        m = host.Model("conv_relu:32:32:3:1:1", 0)
+        m.set_param(0, fx["w"])
+        m.set_param(1, fx["b"])
+        close(m.forward(fx["x"]), fx["conv_relu"], 1e-4, "conv_relu 32 -> 32")
+        assert capi.lib.tpdbg_last_conv_path() == path
+        m2 = host.Model("conv_relu:32:32:3:1:1,maxpool:2:2", 0)
+        m2.set_param(0, fx["w"])
+        m2.set_param(1, fx["b"])
+        close(m2.forward(fx["x"]), fx["maxpool"], 1e-4, "conv_relu -> maxpool")
+    finally:
+        capi.lib.tpdbg_conv_v2(1)
