@@ -240,6 +240,14 @@ int tp_conv2d_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* gy, c
 int tp_conv_stack_fwd(tp_ctx*, const tp_buf* x, int n, int c_in, int h, int w, int n_layers,
                       const tp_buf* const* weights, const tp_buf* const* biases, const int* c_out,
                       const int* pool, const int* relu, tp_buf* y);
+/* Global average pool fused with the per-plane count of positive units:  mean[n,c] = sum_p y[n,c,p] / hw
+ * (AdaptiveAvgPool2d::global -> avg_pool2d, src/nn.rs:670-686, src/tensor.rs:1524-1590), cnt[n,c] = #{p : y[n,c,p] > 0}
+ * (NULL to skip).  cnt is all that the backward of [conv bias -> ReLU -> global average pool] needs: */
+int tp_gap_count_fwd(tp_ctx*, const tp_buf* y, tp_buf* mean, tp_buf* cnt, int n, int c, int hw);
+/* gb[c] (+)= sum_n (g[n,c] / hw) * cnt[n,c]  — avg_pool2d backward (g / hw to every unit, src/tensor.rs:1600-1655), ReLU
+ * backward (src/ops.rs:358-370) and add_bias_4d backward (sum over n,h,w, src/tensor.rs:2003-2027) as one reduction over
+ * [N, C]; cnt == NULL: no ReLU between the bias and the pool.  Deterministic (fixed summation order). */
+int tp_gap_relu_bias_grad(tp_ctx*, const tp_buf* g, const tp_buf* cnt, tp_buf* gb, int n, int c, int hw, int accumulate);
 /* y = x + bias[c] per channel; gb[c] (+)= sum_{n,hw} g     add_bias_4d  src/tensor.rs:1972-2031 */
 int tp_add_bias_4d(tp_ctx*, const tp_buf* x, const tp_buf* bias, tp_buf* y, int n, int c, int hw, int relu);
 int tp_bias_grad_4d(tp_ctx*, const tp_buf* g, tp_buf* gb, int n, int c, int hw, int accumulate);

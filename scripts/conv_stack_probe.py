@@ -129,7 +129,7 @@ def main():
         ref = oracle_stack(x, ws, [None], [0], [0])
         got, _ = run_stack(ctx, x, ws, [None], [0], [0])
         report("32->64 @14 no bias no relu", got, ref)
-    capi.lib.tpdbg_conv_shift_mode(0)
+    capi.lib.tpdbg_conv_shift_mode(-1)           # the library's default variant
     if a.big:
         x, ws, bs = make(rng, 256, 1, 28, [32, 32, 64, 64, 128])
         pools = [0, 1, 0, 1, 0]

@@ -480,6 +480,88 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
     }
 }
 
+// ---- global average pool of the stack's output fused with the count of positive units per plane ------------------------------
+// mean[n, c] = sum_p y[n, c, p] / hw  (AdaptiveAvgPool2d::global -> avg_pool2d, src/nn.rs:670-686, src/tensor.rs:1524-1590);
+// cnt[n, c] = #{p : y[n, c, p] > 0} is everything the backward of the pool + ReLU + bias chain needs (see gap_bias_grad below).
+// One warp per (n, c) plane, two planes in flight per warp.
+__global__ void __launch_bounds__(256)
+gap_count_kernel(const float* __restrict__ y, float* __restrict__ mean, float* __restrict__ cnt, int planes, int hw) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * 256) >> 5;
+    const float inv = 1.0f;
+    (void)inv;
+    for (int p0 = warp * 2; p0 < planes; p0 += nwarps * 2) {
+        float s[2] = {0.0f, 0.0f}, c[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int p = p0 + u;
+            if (p < planes)
+                for (int i = lane; i < hw; i += 32) {
+                    const float v = __ldg(y + (size_t)p * hw + i);
+                    s[u] += v;
+                    c[u] += v > 0.0f ? 1.0f : 0.0f;
+                }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+                c[u] += __shfl_xor_sync(0xffffffffu, c[u], o);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (p0 + u < planes) {
+                    mean[p0 + u] = s[u] / (float)hw;
+                    if (cnt) cnt[p0 + u] = c[u];
+                }
+        }
+    }
+}
+
+// gb[c] (+)= sum_n (g[n, c] / hw) * cnt[n, c]: the gradient of the last conv's bias through avg_pool2d backward (every unit
+// of the plane receives g / hw, src/tensor.rs:1600-1655), the ReLU gate (src/ops.rs:358-370) and add_bias_4d's sum over
+// n, h, w (src/tensor.rs:2003-2027), without materialising the [N, C, H, W] gradient.  cnt == NULL: no ReLU (every unit passes).
+// Stage 1: grid (C/32, S) partial sums over an n-slice in a fixed order; stage 2 folds the S partials in order (deterministic).
+__global__ void __launch_bounds__(256)
+gap_bias_grad_stage1(const float* __restrict__ g, const float* __restrict__ cnt, float* __restrict__ part, int N, int C, int hw) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float red[8][33];
+    const int cl = threadIdx.x & 31, nr = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int S = gridDim.y;
+    const int n0 = (int)(((long long)blockIdx.y * N) / S), n1 = (int)(((long long)(blockIdx.y + 1) * N) / S);
+    float acc = 0.0f;
+    if (c < C)
+        for (int n = n0 + nr; n < n1; n += 8) {
+            const float t = __ldg(g + (size_t)n * C + c) / (float)hw;
+            acc += cnt ? t * __ldg(cnt + (size_t)n * C + c) : t * (float)hw;
+        }
+    red[nr][cl] = acc;
+    __syncthreads();
+    if (nr == 0 && c < C) {
+        float s = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][cl];
+        part[(size_t)blockIdx.y * C + c] = s;
+    }
+}
+__global__ void __launch_bounds__(256)
+gap_bias_grad_stage2(const float* __restrict__ part, float* __restrict__ gb, int S, int C, int accumulate) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.0f;
+    for (int i = 0; i < S; ++i) s += part[(size_t)i * C + c];
+    gb[c] = accumulate ? gb[c] + s : s;
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -650,6 +732,9 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
     if (!enc) return TP_ERR_UNSUPPORTED;
     const int shift_mode = g_shift_override >= 0 ? g_shift_override : default_shift_mode();
     cudaSetDevice(ctx->device);
+    // programmatic dependent launch, also while the step is being captured (the graph keeps the programmatic edges)
+    static const bool pdl_in_capture = env_int("TAPER_CONV_PDL_CAPTURE", 1) != 0;
+    const bool pdl = !ctx->capturing || pdl_in_capture;
     // ---- plan every layer first (no launches before the whole stack is known to fit) ----
     const bool first_direct = C0 * 9 <= 36;
     if (first_direct && (n_layers < 2 || cout[0] % 32 || cout[0] > 256)) return TP_ERR_UNSUPPORTED;
@@ -714,14 +799,14 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         const int ho = pool[0] ? h / 2 : h, wo = pool[0] ? w / 2 : w;
         const size_t items = (size_t)N * ho * wo * (cout[0] / 8);
         const size_t sm = (size_t)(C0 * 9 + 1) * cout[0] * sizeof(float);
-        if ((rc = launch_pdl(ctx, conv_first_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, true, x, w2[0], bias[0],
+        if ((rc = launch_pdl(ctx, conv_first_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, pdl, x, w2[0], bias[0],
                              (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], pool[0] ? 1 : 0, relu[0] ? 1 : 0)))
             return rc;
         h = ho; w = wo; c = cout[0];
         l0 = 1;
     } else {
         const size_t items = (size_t)N * h * w * (c / 8);
-        if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, true, x, (uint16_t*)act[cur].b->ptr, N, c, h, w)))
+        if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, pdl, x, (uint16_t*)act[cur].b->ptr, N, c, h, w)))
             return rc;
     }
     for (int l = l0; l < n_layers; ++l) {
@@ -735,7 +820,7 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         CUtensorMap mx, mw;
         if (!make_map_x(enc, &mx, (const uint16_t*)act[cur].b->ptr, p)) { set_error("conv_stack_fwd: cuTensorMapEncodeTiled (activations) failed"); return TP_ERR_CUDA; }
         if (!make_map_w(enc, &mw, (const uint16_t*)(wplanes.b->ptr + woff[l]), p.CB, p.Cout)) { set_error("conv_stack_fwd: cuTensorMapEncodeTiled (weights) failed"); return TP_ERR_CUDA; }
-        if ((rc = launch_conv_any(ctx, mx, mw, p, smem[l], true))) return rc;
+        if ((rc = launch_conv_any(ctx, mx, mw, p, smem[l], pdl))) return rc;
         cur ^= 1;
     }
     return TP_OK;
@@ -778,6 +863,34 @@ int tp_conv_stack_fwd(tp_ctx* ctx, const tp_buf* x, int n, int c_in, int h, int 
     if (rc == TP_ERR_UNSUPPORTED) tp::set_error("tp_conv_stack_fwd: a layer's shape is outside the tensor-core stack (3x3/s1/p1, C_in %% 32 == 0 "
                                                  "(or C_in*9 <= 36 for the first layer), C_out in {32, 64, 128}, W < 32)");
     return rc;
+}
+
+int tp_gap_count_fwd(tp_ctx* ctx, const tp_buf* y, tp_buf* mean, tp_buf* cnt, int n, int c, int hw) {
+    TP_CHECK_ARG(ctx && n >= 0 && c >= 0 && hw > 0, "tp_gap_count_fwd: bad argument");
+    const size_t planes = (size_t)n * c;
+    TP_NEED(y, planes * hw, "y"); TP_NEED(mean, planes, "mean");
+    if (cnt) TP_NEED(cnt, planes, "cnt");
+    if (!planes) return TP_OK;
+    TP_CHECK_ARG(planes <= 0x7fffffff, "tp_gap_count_fwd: N*C = %zu exceeds int range", planes);
+    cudaSetDevice(ctx->device);
+    return launch_pdl(ctx, gap_count_kernel, dim3(tp::grid_for(ctx, planes * 16, 256, 8)), dim3(256), 0, true,
+                      (const float*)y->ptr, mean->ptr, cnt ? cnt->ptr : (float*)nullptr, (int)planes, hw);
+}
+
+int tp_gap_relu_bias_grad(tp_ctx* ctx, const tp_buf* g, const tp_buf* cnt, tp_buf* gb, int n, int c, int hw, int accumulate) {
+    TP_CHECK_ARG(ctx && n >= 0 && c >= 0 && hw > 0, "tp_gap_relu_bias_grad: bad argument");
+    TP_NEED(g, (size_t)n * c, "g"); TP_NEED(gb, (size_t)c, "gb");
+    if (cnt) TP_NEED(cnt, (size_t)n * c, "cnt");
+    if (!c) return TP_OK;
+    cudaSetDevice(ctx->device);
+    const int S = n >= 512 ? 16 : n >= 64 ? 4 : 1;
+    TmpBuf part;
+    int rc = tp_buf_alloc(ctx, (size_t)S * c, &part.b);
+    if (rc) return rc;
+    if ((rc = launch_pdl(ctx, gap_bias_grad_stage1, dim3((c + 31) / 32, S), dim3(256), 0, true, (const float*)g->ptr,
+                         cnt ? (const float*)cnt->ptr : (const float*)nullptr, part.b->ptr, n, c, hw)))
+        return rc;
+    return launch_pdl(ctx, gap_bias_grad_stage2, dim3((c + 255) / 256), dim3(256), 0, true, (const float*)part.b->ptr, gb->ptr, S, c, accumulate);
 }
 
 }  // extern "C"

@@ -95,7 +95,21 @@ Tensor Sequential::forward(const Tensor& input) const {                         
                 run.push_back(ly);
             }
             if (run.size() >= 2) {
-                Tensor y = x.conv_stack(run);
+                // ... + AdaptiveAvgPool2d::global (+ Flatten(1)) ride along: pooled features and the count of positive units
+                // per plane are all that forward and backward need of the last activation
+                int gap = 0;
+                if (j < layers.size()) {
+                    auto* ap = dynamic_cast<const AdaptiveAvgPool2d*>(layers[j].get());
+                    if (ap && ap->output_size == Pair{1, 1}) {
+                        gap = 1;
+                        ++j;
+                        if (j < layers.size()) {
+                            auto* fl = dynamic_cast<const Flatten*>(layers[j].get());
+                            if (fl && fl->start_dim == 1) { gap = 2; ++j; }
+                        }
+                    }
+                }
+                Tensor y = x.conv_stack(run, gap);
                 if (y.defined()) {
                     x = y;
                     i = j - 1;

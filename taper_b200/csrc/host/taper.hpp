@@ -109,7 +109,8 @@ public:
     // a stack of 3x3 / s1 / p1 convolutions (+bias, +ReLU, + 2x2 max-pool) as one fused forward (Config::fuse_conv_stack);
     // records the one node the strict-reference tape can ever deliver through: the last layer's bias gradient.
     // Returns an undefined Tensor when the shapes are outside the fused kernels (the caller runs the layers one by one).
-    Tensor conv_stack(const std::vector<ConvStackLayer>& layers) const;
+    // gap: 0 = the stack's NCHW output; 1 = followed by a global average pool -> [N, C, 1, 1]; 2 = and Flatten(1) -> [N, C]
+    Tensor conv_stack(const std::vector<ConvStackLayer>& layers, int gap = 0) const;
 
 private:
     Tensor conv2d_impl(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation, bool relu) const;

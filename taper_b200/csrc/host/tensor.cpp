@@ -663,7 +663,7 @@ Tensor Tensor::conv2d_relu(const Tensor& weight, const Tensor* bias, Pair stride
 // pooled gradient to exactly one pre-pool unit whose ReLU gate equals [pooled output > 0].  Hence
 //     bias.grad[c] (+)= sum_{n, p} g[n, c, p] * [out[n, c, p] > 0]          (out = the stack's output, pooled or not)
 // and no intermediate activation or pooling index is needed.
-Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers) const {
+Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers, int gap) const {
     if (shape().size() != 4 || layers.empty() || layers.size() > 8 || needs_grad() || Config::conv_full_adjoint()) return Tensor();
     const int L = (int)layers.size();
     const tp_buf* wb[8];
@@ -689,14 +689,37 @@ Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers) const {
     if (rc == TP_ERR_UNSUPPORTED) return Tensor();
     check(rc);
     const ConvStackLayer& last = layers[L - 1];
-    if (last.bias && last.bias->needs_grad()) {
+    const bool bias_rg = last.bias && last.bias->needs_grad();
+    const bool relu = last.relu;
+    const int nn = (int)n, cc = (int)c, hw = (int)(h * w);
+    // the closures keep every weight alive like the reference's per-layer closures do
+    std::vector<Tensor> keep;
+    for (auto& ly : layers) keep.push_back(ly.weight);
+    if (gap) {
+        // AdaptiveAvgPool2d::global (+ Flatten) on top (src/nn.rs:670-686, 743-745): avg_pool2d backward hands g / hw to every unit
+        // of a plane (src/tensor.rs:1600-1655), so with cnt[n, c] = #{units > 0} of the plane
+        //     bias.grad[c] (+)= sum_n (g[n, c] / hw) * cnt[n, c]
+        // and the [N, C, H, W] gradient, its ReLU mask pass and the conv output itself are never needed again.
+        Tensor feat = Tensor::empty(gap == 2 ? Shape{n, c} : Shape{n, c, 1, 1});
+        Tensor cnt;
+        if (bias_rg && relu) cnt = Tensor::empty({n, c});
+        check(tp_gap_count_fwd(ctx(), out.buf(), feat.buf(), cnt.defined() ? cnt.buf() : nullptr, nn, cc, hw));
+        if (bias_rg) {
+            feat.set_requires_grad(true);
+            Tensor b = *last.bias;
+            tape_push(feat, [b, feat, cnt, nn, cc, hw, keep]() {
+                tp_buf* g = feat.grad_buf();
+                if (!g) return;
+                int ab = 0;
+                tp_buf* gb = b.impl()->grad_for_write(&ab);
+                check(tp_gap_relu_bias_grad(ctx(), g, cnt.defined() ? cnt.buf() : nullptr, gb, nn, cc, hw, ab));
+            });
+        }
+        return feat;
+    }
+    if (bias_rg) {
         out.set_requires_grad(true);
         Tensor b = *last.bias;
-        const bool relu = last.relu;
-        const int nn = (int)n, cc = (int)c, hw = (int)(h * w);
-        // the closure keeps every weight alive like the reference's per-layer closures do
-        std::vector<Tensor> keep;
-        for (auto& ly : layers) keep.push_back(ly.weight);
         tape_push(out, [b, out, relu, nn, cc, hw, keep]() {
             tp_buf* g = out.grad_buf();
             if (!g) return;

@@ -182,3 +182,58 @@ def test_sequential_peephole_runs_the_stack_and_matches_layer_by_layer():
     host.config_conv_stack(1)
     close(outs[0], outs[1], 1e-4, "fused vs per-layer logits")
     assert launches[0] + 6 <= launches[1], launches
+
+
+def test_gap_count_and_bias_gradient_vs_oracle(ctx):
+    """tp_gap_count_fwd / tp_gap_relu_bias_grad against the oracle's chain relu -> avg_pool2d (global) and its backward into the
+    conv bias (src/tensor.rs:1524-1660, src/ops.rs:358-370, src/tensor.rs:2003-2027): mean exact to summation order, count exact,
+    bias gradient 1e-5."""
+    rng = np.random.default_rng(21)
+    for (n, c, hw) in [(1024, 128, 49), (37, 64, 196), (5, 32, 9)]:
+        side = int(round(hw ** 0.5))
+        z = (rng.standard_normal((n, c, side, side))).astype(F32)
+        y = np.maximum(z, 0).astype(F32)
+        g = (rng.standard_normal((n, c)) * 1e-3).astype(F32)
+        mean, cnt, gb = ctx.alloc(n * c), ctx.alloc(n * c), ctx.alloc(c)
+        ctx.call("gap_count_fwd", ctx.upload(y), mean, cnt, n, c, hw)
+        np.testing.assert_allclose(mean.download().reshape(n, c), y.reshape(n, c, hw).mean(axis=2), rtol=2e-6, atol=1e-7)
+        np.testing.assert_array_equal(cnt.download().reshape(n, c), (y.reshape(n, c, hw) > 0).sum(axis=2).astype(F32))
+        # oracle: loss = sum(avg_pool2d(relu(z)) * G)  =>  z.grad summed over n, h, w is what add_bias_4d hands to the bias
+        R.Tape.reset()
+        zt = R.Tensor.new(z, z.shape).requires_grad_()
+        pooled = zt.relu().avg_pool2d((side, side), (side, side))
+        (pooled * R.Tensor.new(g.reshape(n, c, 1, 1), (n, c, 1, 1))).sum().backward()
+        ref = np.asarray(zt.grad(), np.float64).reshape(n, c, hw).sum(axis=(0, 2))
+        R.Tape.reset()
+        ctx.call("gap_relu_bias_grad", ctx.upload(g), cnt, gb, n, c, hw, 0)
+        got = gb.download()
+        assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-6)
+        ctx.call("gap_relu_bias_grad", ctx.upload(g), cnt, gb, n, c, hw, 1)          # accumulate
+        assert np.abs(gb.download() - 2 * ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6)
+        ctx.call("gap_relu_bias_grad", ctx.upload(g), None, gb, n, c, hw, 0)         # no ReLU: every unit passes
+        assert np.abs(gb.download() - g.astype(np.float64).sum(axis=0)).max() <= 1e-5 * np.abs(g.sum(axis=0)).max() + 1e-9
+
+
+def test_example_cnn_step_fused_vs_per_layer_tape():
+    """loss_backward of the shipped example model with the conv-stack (+ global average pool) node against the per-layer tape of
+    the same library: same loss, same None pattern, the same bias / Linear gradients to 1e-4 (+ the ReLU-threshold slack is not
+    needed here: both paths share the conv kernel, so the masks agree)."""
+    from taper_b200 import host
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    rng = np.random.default_rng(4)
+    x = rng.random((32, 1, 28, 28)).astype(F32)
+    y = rng.integers(0, 10, 32).astype(F32)
+    res = []
+    for fuse in (1, 0):
+        host.config_conv_stack(fuse)
+        m = host.Model(host.CNN5, 9)
+        m.zero_grad()
+        loss, correct, _ = m.loss_backward(x, y)
+        res.append((loss, correct, [m.get_grad(j) for j in range(m.num_params())]))
+    host.config_conv_stack(1)
+    assert res[0][0] == pytest.approx(res[1][0], rel=1e-5)
+    assert res[0][1] == res[1][1]
+    for j, (ga, gb) in enumerate(zip(res[0][2], res[1][2])):
+        assert (ga is None) == (gb is None), j
+        if ga is not None:
+            close(ga, gb, 1e-4, f"grad {j}")
