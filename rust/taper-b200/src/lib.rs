@@ -9,6 +9,11 @@ use std::ptr;
 
 pub use taper_b200_sys as ffi;
 
+// taper's own API surface (Tensor / Tape / nn / activation / loss / optim / train) over the host ABI: with `[lib] name = "taper"`
+// the reference's examples compile against this crate as they are.
+mod taper_api;
+pub use taper_api::{activation, loss, nn, optim, train, Tape, Tensor};
+
 /// Non-zero status -> panic with the library's thread-local message: the reference panics on the same conditions
 /// (`assert!` / `unwrap`, e.g. src/ops.rs:11-15, 201-208).
 #[inline]

@@ -40,7 +40,9 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kConvThreads = 192;
+constexpr int kMmaWarps = 2;               // MMA-issuing warps: one per accumulator buffer, tiles alternate between them
+constexpr int kEpiWarp0 = 1 + kMmaWarps;    // first of the four epilogue warps
+constexpr int kConvThreads = 32 * (1 + kMmaWarps + 4);
 constexpr int kMaxRing = 8;
 constexpr int kMaxPrep = 8;
 
@@ -134,7 +136,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             mbar_init(a_full + s, 1);
             mbar_init(a_empty + s, 1);
             mbar_init(b_full + s, 1);
-            mbar_init(b_empty + s, 1);
+            mbar_init(b_empty + s, kMmaWarps);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(acc_full + b, 1);
@@ -166,111 +168,143 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
     if (warp == 0) {
         // ===== TMA producer =====
+        // Tiles are handled in PAIRS (it = 2P, 2P + 1): issuer w owns tile 2P + w, its own half of the patch ring (stages
+        // w*nAe .. w*nAe + nAe - 1, filled and drained strictly in that issuer's order) and accumulator w.  Streamed weights go
+        // through ONE ring that both issuers walk in lockstep — every stage (3 taps of one channel block) is multiplied into both
+        // tiles of the pair and released by both (b_empty counts 2) — so each ring has exactly one consumer sequence: a parity
+        // wait can never be more than one phase away from the barrier's state, and the weights are read from L2 once per pair.
         if (lane == 0) {
             if (p.w_resident) {
                 mbar_expect_tx(w_full, 9 * p.CB * BN * 128);
                 for (int g = 0; g < 3 * p.CB; ++g) tma_load_3d(b_ring + g * 3 * BN * 128, &map_w, w_full, 0, 0, g * 3);
             }
-            int ai = 0, bi = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                const int ng = tile / p.row_blocks, rb = tile - ng * p.row_blocks;
-                const int n0 = ng * p.G, y0 = rb * p.R;
+            const int nAe = p.nA / kMmaWarps;
+            const int my_tiles = ((int)p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int npairs = (my_tiles + kMmaWarps - 1) / kMmaWarps;
+            for (int P = 0; P < npairs; ++P) {
                 for (int cb = 0; cb < p.CB; ++cb) {
-                    const int s = ai % p.nA;
-                    mbar_wait(a_empty + s, ((ai / p.nA) & 1) ^ 1);
-                    uint8_t* dst = a_ring + s * p.a_stage_bytes + patch_off;
-                    if (p.shift_mode) {
-                        mbar_expect_tx(a_full + s, p.patch_bytes);
-                        tma_load_5d(dst, &map_x, a_full + s, 0, cb, 0, y0 - 1, n0);
-                    } else {
-                        mbar_expect_tx(a_full + s, 3 * p.patch_bytes);
-                        for (int kc = 0; kc < 3; ++kc) tma_load_5d(dst + kc * p.patch_alloc, &map_x, a_full + s, 0, cb, kc - 1, y0 - 1, n0);
+                    const int k = P * p.CB + cb;
+                    for (int w = 0; w < kMmaWarps; ++w) {
+                        const int tile = blockIdx.x + (P * kMmaWarps + w) * gridDim.x;
+                        if (tile >= p.tiles) continue;
+                        const int ng = tile / p.row_blocks, rb = tile - ng * p.row_blocks;
+                        const int n0 = ng * p.G, y0 = rb * p.R;
+                        const int s = w * nAe + k % nAe;
+                        mbar_wait(a_empty + s, ((k / nAe) & 1) ^ 1);
+                        uint8_t* dst = a_ring + s * p.a_stage_bytes + patch_off;
+                        if (p.shift_mode) {
+                            mbar_expect_tx(a_full + s, p.patch_bytes);
+                            tma_load_5d(dst, &map_x, a_full + s, 0, cb, 0, y0 - 1, n0);
+                        } else {
+                            mbar_expect_tx(a_full + s, 3 * p.patch_bytes);
+                            for (int kc = 0; kc < 3; ++kc) tma_load_5d(dst + kc * p.patch_alloc, &map_x, a_full + s, 0, cb, kc - 1, y0 - 1, n0);
+                        }
                     }
-                    ++ai;
                     if (!p.w_resident) {
                         for (int kr = 0; kr < 3; ++kr) {
+                            const int bi = k * 3 + kr;
                             const int sb = bi % p.nB;
                             mbar_wait(b_empty + sb, ((bi / p.nB) & 1) ^ 1);
                             mbar_expect_tx(b_full + sb, 3 * BN * 128);
                             tma_load_3d(b_ring + sb * p.b_stage_bytes, &map_w, b_full + sb, 0, 0, cb * 9 + kr * 3);
-                            ++bi;
                         }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp <= kMmaWarps) {
+        // ===== MMA issuers: warp 1 + w multiplies tile 2P + w of every pair into accumulator w.  One thread issuing all MMAs is
+        // latency-bound on its own instruction stream (measured ~95 clocks per MMA against the ~48 the shared-memory port allows
+        // for 128 x 32 x 16): two issuers interleave their streams in the tensor pipe. =====
         if (lane == 0) {
+            const int mw = warp - 1;
             // instruction descriptor: D = F32 (1 << 4), A / B = BF16 (1 << 7, 1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // descriptor-unit (16 B) offsets of the nine taps inside a patch stage
+            uint32_t tap_off[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int kr = t / 3, kc = t - 3 * kr;
+                tap_off[t] = p.shift_mode ? (uint32_t)((kr * p.Wp + kc - 1) * 8) : (uint32_t)((kc * p.patch_alloc + kr * p.Wp * 128) >> 4);
+            }
+            const int nAe = p.nA / kMmaWarps;
+            const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
+            const uint32_t a_lo0 = desc_lo(smem_u32(a_ring + patch_off)) + (uint32_t)(mw * nAe) * a_step;
+            const uint32_t b_lo0 = desc_lo(smem_u32(b_ring)), b_step = (uint32_t)p.b_stage_bytes >> 4;
             if (p.w_resident) {
                 mbar_wait(w_full, 0);
                 tc_fence_after();
             }
-            int ai = 0, bi = 0, it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * BN;
-                for (int cb = 0; cb < p.CB; ++cb) {
-                    const int s = ai % p.nA;
-                    mbar_wait(a_full + s, (ai / p.nA) & 1);
+            const uint32_t tmem_d = tmem_base + mw * BN;
+            const int my_tiles = ((int)p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int npairs = (my_tiles + kMmaWarps - 1) / kMmaWarps;
+            for (int P = 0; P < npairs; ++P) {
+                const bool has = (int)(blockIdx.x + (P * kMmaWarps + mw) * gridDim.x) < p.tiles;
+                if (has) {
+                    mbar_wait(acc_empty + mw, (P & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(a_ring + s * p.a_stage_bytes + patch_off);
+                }
+                for (int cb = 0; cb < p.CB; ++cb) {
+                    const int k = P * p.CB + cb;
+                    const int sl = k % nAe;                             // stage inside this issuer's half of the patch ring
+                    if (has) {
+                        mbar_wait(a_full + mw * nAe + sl, (k / nAe) & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t a_lo = a_lo0 + sl * a_step;
+#pragma unroll
                     for (int kr = 0; kr < 3; ++kr) {
-                        uint32_t b0;
+                        uint32_t b_lo;
                         int sb = 0;
                         if (p.w_resident) {
-                            b0 = smem_u32(b_ring + (cb * 9 + kr * 3) * BN * 128);
+                            b_lo = b_lo0 + (uint32_t)((cb * 9 + kr * 3) * BN * 8);
                         } else {
+                            const int bi = k * 3 + kr;
                             sb = bi % p.nB;
                             mbar_wait(b_full + sb, (bi / p.nB) & 1);
                             tc_fence_after();
-                            b0 = smem_u32(b_ring + sb * p.b_stage_bytes);
+                            b_lo = b_lo0 + sb * b_step;
                         }
+                        if (has) {
 #pragma unroll
-                        for (int kc = 0; kc < 3; ++kc) {
-                            const uint32_t ah = p.shift_mode ? a0 + (uint32_t)((kr * p.Wp + kc - 1) * 128)
-                                                             : a0 + (uint32_t)(kc * p.patch_alloc + kr * p.Wp * 128);
-                            const uint32_t al = desc_lo(ah), bl = desc_lo(b0 + kc * BN * 128);
-                            const uint32_t ahi = kDescHi | (p.shift_mode == 1 ? ((ah >> 7) & 7u) << 17 : 0u);
-                            const uint32_t fresh = (cb == 0 && kr == 0 && kc == 0) ? 1u : 0u;
-                            // [hi x32 | lo x32] rows: hi at byte 0 / 32 (two K = 16 steps = +0 / +2 descriptor units), lo at 64 / 96
-                            // (+4 / +6); small terms first
-                            if (!(p.dbg & 1)) {
+                            for (int kc = 0; kc < 3; ++kc) {
+                                const uint32_t al = a_lo + tap_off[kr * 3 + kc], bl = b_lo + kc * BN * 8;
+                                const uint32_t fresh = (cb == 0 && kr == 0 && kc == 0) ? 1u : 0u;
+                                // [hi x32 | lo x32] rows: hi at byte 0 / 32 (two K = 16 steps = +0 / +2 descriptor units), lo at
+                                // 64 / 96 (+4 / +6); small terms first
+                                if (!(p.dbg & 1)) {
 #pragma unroll
-                                for (int kk = 0; kk < 2; ++kk)
-                                    mma_bf16_w(tmem_d, al + 4 + 2 * kk, ahi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
+                                    for (int kk = 0; kk < 2; ++kk)
+                                        mma_bf16_w(tmem_d, al + 4 + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
 #pragma unroll
-                                for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, ahi, bl + 4 + 2 * kk, kDescHi, idesc, 1u);
+                                    for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 4 + 2 * kk, kDescHi, idesc, 1u);
 #pragma unroll
-                                for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, ahi, bl + 2 * kk, kDescHi, idesc, 1u);
-                            } else {
+                                    for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc, 1u);
+                                } else {
 #pragma unroll
-                                for (int kk = 0; kk < 2; ++kk)
-                                    mma_bf16_w(tmem_d, al + 2 * kk, ahi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
+                                    for (int kk = 0; kk < 2; ++kk)
+                                        mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
+                                }
                             }
                         }
                         if (!p.w_resident) {
-                            tc_commit(b_empty + sb);
-                            ++bi;
+                            // release this issuer's share of the weight stage (an issuer without a tile in the last pair just arrives)
+                            if (has) tc_commit(b_empty + sb);
+                            else mbar_arrive(b_empty + sb);
                         }
                     }
-                    tc_commit(a_empty + s);
-                    ++ai;
+                    if (has) tc_commit(a_empty + mw * nAe + sl);
                 }
-                tc_commit(acc_full + buf);
+                if (has) tc_commit(acc_full + mw);
             }
         }
     } else {
-        // ===== epilogue warps 2-5: TMEM lane quarter q = warp & 3, thread = tile row =====
+        // ===== four epilogue warps: TMEM lane quarter q = warp & 3, thread = tile row =====
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int img = r / p.img_rows, rem = r - img * p.img_rows;
         const int ri = rem / p.Wp, rj = rem - ri * p.Wp;
-        const int et = threadIdx.x - 64;                                  // 0..127 in warp order 2,3,4,5
+        const int et = threadIdx.x - 32 * kEpiWarp0;                      // 0..127 in warp order
         const int CBo = BN / 32;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
@@ -404,21 +438,19 @@ __global__ void __launch_bounds__(256)
 nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int C, int H, int W) {
     pdl_wait();
     pdl_launch_dependents();
-    const int CG = C / 8;
-    const size_t hw = (size_t)H * W, total = (size_t)N * hw * CG;
-    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        // pixel fastest: a warp reads 32 consecutive x of one channel (coalesced), 8 channels per thread
-        const size_t pix = e % hw;
-        const size_t t = e / hw;
-        const int cg = (int)(t % CG);
-        const size_t n = t / CG;
-        const float* src = x + (n * C + cg * 8) * hw + pix;
+    const unsigned int CG = C / 8;
+    const unsigned int hw = (unsigned int)(H * W), total = (unsigned int)N * hw * CG;      // < 2^31 (checked on the host)
+    for (unsigned int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        // pixel fastest: a warp reads 32 consecutive x of one channel (coalesced), 8 channels per thread; 32-bit index math
+        const unsigned int t = e / hw, pix = e - t * hw;
+        const unsigned int n = t / CG, cg = t - n * CG;
+        const float* src = x + ((size_t)n * C + cg * 8) * hw + pix;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j * hw);
         uint4 h, l;
         split8(v, &h, &l);
-        uint16_t* dst = out + ((n * hw + pix) * (C / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
+        uint16_t* dst = out + (((size_t)n * hw + pix) * (C / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
         *(uint4*)dst = h;
         *(uint4*)(dst + 32) = l;
     }
@@ -439,14 +471,16 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
     for (int i = threadIdx.x; i < Cout; i += 256) sb[i] = bias ? __ldg(bias + i) : 0.0f;
     __syncthreads();
     const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
-    const int CG = Cout / 8, nsub = pool ? 4 : 1;
-    const size_t total = (size_t)N * Ho * Wo * CG;
-    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        const int cg = (int)(e % CG);
-        const size_t pix = e / CG;
-        const int xo = (int)(pix % Wo);
-        const int yo = (int)((pix / Wo) % Ho);
-        const size_t n = pix / ((size_t)Wo * Ho);
+    const unsigned int CG = Cout / 8;
+    const int nsub = pool ? 4 : 1;
+    const unsigned int total = (unsigned int)N * Ho * Wo * CG;                               // < 2^31 (checked on the host)
+    for (unsigned int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        // 32-bit index arithmetic (64-bit divisions cost more than the nine taps)
+        const unsigned int pix = e / CG, cg = e - pix * CG;
+        const unsigned int rowi = pix / (unsigned int)Wo;
+        const int xo = (int)(pix - rowi * (unsigned int)Wo);
+        const unsigned int n = rowi / (unsigned int)Ho;
+        const int yo = (int)(rowi - n * (unsigned int)Ho);
         float best[8];
         for (int s = 0; s < nsub; ++s) {
             const int yy = pool ? 2 * yo + (s >> 1) : yo, xx = pool ? 2 * xo + (s & 1) : xo;
@@ -454,7 +488,7 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
             for (int ci = 0; ci < Cin; ++ci) {
-                const float* xp = x + (n * Cin + ci) * (size_t)H * W;
+                const float* xp = x + ((size_t)n * Cin + ci) * (size_t)H * W;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
@@ -474,7 +508,7 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
         }
         uint4 h, l;
         split8(best, &h, &l);
-        uint16_t* dst = out + (pix * (Cout / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
+        uint16_t* dst = out + ((size_t)pix * (Cout / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
         *(uint4*)dst = h;
         *(uint4*)(dst + 32) = l;
     }
@@ -630,15 +664,16 @@ bool plan_layer(int N, int H, int W, int Cin, int Cout, bool pool, int out_mode,
     const int stage_bytes = pool ? 128 * (Cout + 4) * 4 : 0;
     const int w_bytes = 9 * q.CB * Cout * 128;
     int left = kSmemBudget - stage_bytes;
+    // patch stages come in pairs (one half of the ring per MMA issuer)
     if (w_bytes <= 80 * 1024 && left - w_bytes >= 2 * q.a_stage_bytes) {
         q.w_resident = 1;
         q.b_stage_bytes = 0; q.nB = 0;
         int nA = (left - w_bytes) / q.a_stage_bytes;
-        q.nA = nA > 6 ? 6 : nA;
+        q.nA = nA >= 6 ? 6 : nA >= 4 ? 4 : 2;
     } else {
         q.w_resident = 0;
         q.b_stage_bytes = 3 * Cout * 128;
-        q.nA = shift_mode ? 3 : 2;
+        q.nA = 4;
         if (left - q.nA * q.a_stage_bytes < 2 * q.b_stage_bytes) q.nA = 2;
         int nB = (left - q.nA * q.a_stage_bytes) / q.b_stage_bytes;
         if (nB < 2) return false;
@@ -737,6 +772,7 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
     const bool pdl = !ctx->capturing || pdl_in_capture;
     // ---- plan every layer first (no launches before the whole stack is known to fit) ----
     const bool first_direct = C0 * 9 <= 36;
+    if ((size_t)N * H * W * (size_t)(C0 > 32 ? C0 : 32) >= ((size_t)1 << 31)) return TP_ERR_UNSUPPORTED;      // 32-bit index math in the layout kernels
     if (first_direct && (n_layers < 2 || cout[0] % 32 || cout[0] > 256)) return TP_ERR_UNSUPPORTED;
     if (!first_direct && C0 % 32) return TP_ERR_UNSUPPORTED;
     ConvP P[kMaxPrep];

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 F32 = np.float32
 
 # (batch, C_in, H = W, C_out, expected path: 1 direct small-K kernel, 2 implicit GEMM on tcgen05 with LSU-gathered A tiles
-# (3xTF32, gemm_tc.cu), 4 TMA-fed implicit GEMM on bf16 hi/lo planes (conv_bx3.cu, the default for 3x3 / s1 / p1 layers))
+# (3xTF32, gemm_tc.cu: tp_set_gemm_mode 1), 4 TMA-fed implicit GEMM on bf16 hi/lo planes (conv_bx3.cu: tp_set_gemm_mode 3 — and,
+# whatever the mode, the fused conv stack of Sequential, tests/test_conv_stack_gpu.py))
 LAYERS = [
     (256, 1, 28, 32, 1),          # conv1: K = 9, direct kernel on the CUDA cores
     (256, 32, 28, 32, 4),         # conv2: M = 200704, K = 288, N = 32  (1792 tiles of 4 x 32 pixels)
@@ -22,7 +23,7 @@ LAYERS = [
     (256, 64, 14, 64, 4),         # conv4: M = 50176,  K = 576, N = 64
     (256, 64, 7, 128, 4),         # conv5: M = 12544,  K = 576, N = 128 (two images per tile, streamed weights)
     (1024, 32, 28, 32, 4),        # conv2 at configs[4]'s batch: 7168 tiles
-    (256, 32, 28, 32, 2),         # the same layers on the round-1 kernel (tpdbg_conv_v2(0)): 128 x 32 tiles, two CTAs per SM
+    (256, 32, 28, 32, 2),         # the same layers on the 3xTF32 kernel: 128 x 32 tiles, two CTAs per SM
     (256, 64, 14, 64, 2),
     (256, 64, 7, 128, 2),         # 128 x 128 tiles
 ]
@@ -46,11 +47,8 @@ def test_conv_relu_layer_at_baseline_batch_vs_oracle(ctx, n, cin, hw, cout, path
     d = ConvDesc(n, cin, hw, hw, cout, 3, 3, 1, 1, 1, 1, 1, 1)
     ref = R.Tensor.new(x, x.shape).conv2d_relu(R.Tensor.new(w, w.shape), R.Tensor.new(b, b.shape), (1, 1), (1, 1), (1, 1)).data()
     y = ctx.alloc(ref.size)
-    capi.lib.tpdbg_conv_v2(0 if path == 2 else 1)
-    try:
-        ctx.call("conv2d_fwd", ctx.upload(x), ctx.upload(w), ctx.upload(b), y, d, 1)
-    finally:
-        capi.lib.tpdbg_conv_v2(1)
+    ctx.call("set_gemm_mode", 3 if path == 4 else 1)          # eager conv: bf16x3 mode -> conv_bx3.cu, 3xTF32 mode -> gemm_tc.cu
+    ctx.call("conv2d_fwd", ctx.upload(x), ctx.upload(w), ctx.upload(b), y, d, 1)
     assert capi.lib.tpdbg_last_conv_path() == path
     got = y.download()
     close(got, ref, 1e-4, f"conv_relu {n}x{cin}x{hw}x{hw} -> {cout}")

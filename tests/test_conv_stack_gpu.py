@@ -101,6 +101,11 @@ CASES = [
     ("contract CNN stack", 6, 1, 28, [32, 64], [1, 1]),
     ("3-channel image stack", 3, 3, 16, [32, 32], [0, 1]),
     ("32-channel input stack", 3, 32, 12, [64, 64, 32], [1, 0, 0]),
+    # several tiles per persistent CTA: both MMA issuers at work, odd tile counts, the weight ring shared by the tile pair
+    ("128->128 @7 batch 700 (350 tiles, streamed weights)", 700, 128, 7, [128], [0]),
+    ("64->64 @14 batch 301 pool (602 tiles, streamed weights)", 301, 64, 14, [64], [1]),
+    ("32->32 @28 batch 75 (525 tiles, resident weights)", 75, 32, 28, [32], [0]),
+    ("96->64 @14 batch 223 (446 tiles, three channel blocks)", 223, 96, 14, [64], [0]),
 ]
 
 
@@ -168,7 +173,7 @@ def test_sequential_peephole_runs_the_stack_and_matches_layer_by_layer():
     """Sequential::forward with the conv-stack peephole on / off: same output within the bf16x3 bound, far fewer launches; the
     backward through the stack's one tape node delivers the last conv's bias gradient exactly like the per-layer tape."""
     from taper_b200 import host
-    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=3)     # per-layer convs on the same kernel
     rng = np.random.default_rng(3)
     x = rng.random((6, 1, 28, 28)).astype(F32)
     outs, launches = [], []
@@ -180,6 +185,7 @@ def test_sequential_peephole_runs_the_stack_and_matches_layer_by_layer():
         outs.append(m.forward(x))
         launches.append(host.launches() - l0)
     host.config_conv_stack(1)
+    host.config(gemm_mode=1)
     close(outs[0], outs[1], 1e-4, "fused vs per-layer logits")
     assert launches[0] + 6 <= launches[1], launches
 
@@ -217,9 +223,9 @@ def test_gap_count_and_bias_gradient_vs_oracle(ctx):
 def test_example_cnn_step_fused_vs_per_layer_tape():
     """loss_backward of the shipped example model with the conv-stack (+ global average pool) node against the per-layer tape of
     the same library: same loss, same None pattern, the same bias / Linear gradients to 1e-4 (+ the ReLU-threshold slack is not
-    needed here: both paths share the conv kernel, so the masks agree)."""
+    needed here: in bf16x3 mode both paths share the conv kernel, so the masks agree)."""
     from taper_b200 import host
-    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=3)
     rng = np.random.default_rng(4)
     x = rng.random((32, 1, 28, 28)).astype(F32)
     y = rng.integers(0, 10, 32).astype(F32)
@@ -231,6 +237,7 @@ def test_example_cnn_step_fused_vs_per_layer_tape():
         loss, correct, _ = m.loss_backward(x, y)
         res.append((loss, correct, [m.get_grad(j) for j in range(m.num_params())]))
     host.config_conv_stack(1)
+    host.config(gemm_mode=1)
     assert res[0][0] == pytest.approx(res[1][0], rel=1e-5)
     assert res[0][1] == res[1][1]
     for j, (ga, gb) in enumerate(zip(res[0][2], res[1][2])):

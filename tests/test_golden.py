@@ -198,8 +198,7 @@ def test_cuda_reproduces_golden_conv_on_the_tcgen05_path(path):
     kernel of conv_bx3.cu, 2 = round 1's 3xTF32 kernel with gathered A tiles), unlike conv_pool.npz whose C_out = 4 layer takes
     the direct kernel."""
     from taper_b200 import host, capi
-    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
-    capi.lib.tpdbg_conv_v2(1 if path == 4 else 0)
+    host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=3 if path == 4 else 1)
     try:
         fx = np.load(os.path.join(HERE, "conv_igemm.npz"))
         m = host.Model("conv_relu:32:32:3:1:1", 0)
@@ -212,4 +211,4 @@ def test_cuda_reproduces_golden_conv_on_the_tcgen05_path(path):
         m2.set_param(1, fx["b"])
         close(m2.forward(fx["x"]), fx["maxpool"], 1e-4, "conv_relu -> maxpool")
     finally:
-        capi.lib.tpdbg_conv_v2(1)
+        host.config(gemm_mode=1)
