@@ -437,9 +437,15 @@ def measure(name, args, dist, rank, world, local, windows, primary):
     ds = host.Dataset(Xu.reshape(DATASET_N, cols) if wide else X.reshape(DATASET_N, cols), Y)
     loader = host.Loader(ds, batch, shuffle=False, sample_shape=sample_shape)      # shuffle off: K steps are a fraction of an epoch
     tr.train_epoch(loader, max_batches=W)
+    per_epoch = max(1, DATASET_N // batch)              # K steps may span several passes over the 60000-sample dataset (train_epoch
+                                                        # resets the loader on entry; only full batches are timed)
     dist.barrier()
     t0 = time.perf_counter()
-    e2e_loss, e2e_acc = tr.train_epoch(loader, max_batches=args.steps)
+    done = 0
+    while done < args.steps:
+        k = min(args.steps - done, per_epoch)
+        e2e_loss, e2e_acc = tr.train_epoch(loader, max_batches=k)
+        done += k
     host.sync()
     t1 = time.perf_counter()
     e2e_s = dist.max(t1 - t0)

@@ -23,12 +23,17 @@
 // M tile = 128 consecutive patch rows = 128/Wp image rows (or, for images smaller than that, G whole images); rows that
 // fall on pad columns / halo rows compute junk that the epilogue drops (12.5 % of the MMA rows at 28x28, 23 % at 14x14 / 7x7 —
 // the kernel is shared-memory-port bound, not MMA bound).
-// Products: per tap and 32-channel block, A_lo*B_hi + A_hi*B_lo + A_hi*B_hi as 6 MMAs of 128 x C_out x 16 (kind::f16).
+// Products (bf16x3: A_hi*W_hi + A_hi*W_lo + A_lo*W_hi, fp32 accumulation): per tap, 32-channel block and K = 16 step TWO MMAs,
+//   A_hi x [W_hi ; W_lo]  (N = 2*C_out: hi*hi lands in accumulator columns [0, C_out), hi*lo in [C_out, 2*C_out))
+//   A_lo x  W_hi          (N = C_out, into columns [0, C_out))
+// and the epilogue adds the two column halves: the A tile — which dominates the shared-memory port for C_out <= 64 — is read
+// twice per product instead of three times, and a third fewer MMAs go through the issuing threads.
 // Weights [K = ci*9 + tap, C_out] (the reference's reinterpretation of the [C_out, C_in, 3, 3] buffer) are
-// re-laid once per step as planes [ci/32][tap][co][hi x32 | lo x32] and either stay resident in shared memory for the
-// whole kernel (<= 80 KB) or stream through a second ring.
-// Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue on a
-// double-buffered TMEM accumulator (tile i+1 multiplies while tile i is read out): bias + ReLU (+ 2x2 max-pool through a
+// re-laid once per step as [ci/32][tap pair][W_hi rows x C_out ; W_lo rows x C_out][tap 2p x32 | tap 2p+1 x32] (128-byte
+// K-major rows again; a tap is the row's first or second half) and either stay resident in shared memory for the whole kernel
+// (<= 96 KB) or stream through a second ring, one tap pair per stage.
+// Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warps 1-2 MMA issuers (one per TMEM accumulator; tiles
+// are handled in pairs), warps 3-6 epilogue (tile i+1 multiplies while tile i is read out): bias + ReLU (+ 2x2 max-pool through a
 // shared-memory staging tile) and either the planes of the next layer or NCHW fp32 for the rest of the tape.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -105,6 +110,12 @@ __device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
     *lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
 }
 
+// development aid: SM-clock stamps of CTA 0's first 64 tiles, read back with tpdbg_conv_times():
+//   [0] issuer saw its accumulator free  [1] issuer committed the tile  [2] epilogue saw the accumulator full
+//   [3] epilogue released the accumulator  [4] producer issued the tile's first patch load  [5] issuer saw the first patch
+__device__ long long g_conv_t[6][64];
+#define CONV_T(kind, it) do { if (blockIdx.x == 0 && (it) < 64) g_conv_t[kind][it] = clock64(); } while (0)
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN>
@@ -114,7 +125,8 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + p.nA * p.a_stage_bytes;
-    const int b_total = p.w_resident ? 9 * p.CB * BN * 128 : p.nB * p.b_stage_bytes;
+    constexpr int kPairBytes = 2 * BN * 128;                          // one weight stage: a pair of taps, rows [W_hi x BN ; W_lo x BN]
+    const int b_total = p.w_resident ? 5 * p.CB * kPairBytes : p.nB * kPairBytes;
     constexpr int kPitch = BN + 4;                                    // floats per staged row (pool)
     float* stage = (float*)(b_ring + b_total);
     uint64_t* bars = (uint64_t*)((uint8_t*)stage + (p.pool ? 128 * kPitch * 4 : 0));
@@ -126,7 +138,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint64_t* acc_empty = acc_full + 2;                               // [2]
     uint64_t* w_full = acc_empty + 2;
     uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
-    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr uint32_t kTmemCols = 4 * BN;                            // two accumulators of [hi*hi + lo*hi | hi*lo] = 2 * BN columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -175,8 +187,8 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // wait can never be more than one phase away from the barrier's state, and the weights are read from L2 once per pair.
         if (lane == 0) {
             if (p.w_resident) {
-                mbar_expect_tx(w_full, 9 * p.CB * BN * 128);
-                for (int g = 0; g < 3 * p.CB; ++g) tma_load_3d(b_ring + g * 3 * BN * 128, &map_w, w_full, 0, 0, g * 3);
+                mbar_expect_tx(w_full, 5 * p.CB * kPairBytes);
+                for (int g = 0; g < 5 * p.CB; ++g) tma_load_3d(b_ring + g * kPairBytes, &map_w, w_full, 0, 0, g);
             }
             const int nAe = p.nA / kMmaWarps;
             const int my_tiles = ((int)p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -192,6 +204,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         const int s = w * nAe + k % nAe;
                         mbar_wait(a_empty + s, ((k / nAe) & 1) ^ 1);
                         uint8_t* dst = a_ring + s * p.a_stage_bytes + patch_off;
+                        if (cb == 0) CONV_T(4, P * kMmaWarps + w);
                         if (p.shift_mode) {
                             mbar_expect_tx(a_full + s, p.patch_bytes);
                             tma_load_5d(dst, &map_x, a_full + s, 0, cb, 0, y0 - 1, n0);
@@ -201,12 +214,12 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         }
                     }
                     if (!p.w_resident) {
-                        for (int kr = 0; kr < 3; ++kr) {
-                            const int bi = k * 3 + kr;
+                        for (int pr = 0; pr < 5; ++pr) {
+                            const int bi = k * 5 + pr;
                             const int sb = bi % p.nB;
                             mbar_wait(b_empty + sb, ((bi / p.nB) & 1) ^ 1);
-                            mbar_expect_tx(b_full + sb, 3 * BN * 128);
-                            tma_load_3d(b_ring + sb * p.b_stage_bytes, &map_w, b_full + sb, 0, 0, cb * 9 + kr * 3);
+                            mbar_expect_tx(b_full + sb, kPairBytes);
+                            tma_load_3d(b_ring + sb * kPairBytes, &map_w, b_full + sb, 0, 0, cb * 5 + pr);
                         }
                     }
                 }
@@ -218,8 +231,12 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // for 128 x 32 x 16): two issuers interleave their streams in the tensor pipe. =====
         if (lane == 0) {
             const int mw = warp - 1;
-            // instruction descriptor: D = F32 (1 << 4), A / B = BF16 (1 << 7, 1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptors: D = F32 (1 << 4), A / B = BF16 (1 << 7, 1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24.
+            // Per tap and K = 16 step two MMAs instead of three:  A_hi x [W_hi ; W_lo] (N = 2 BN: hi*hi into columns [0, BN), hi*lo
+            // into [BN, 2 BN)) and A_lo x W_hi (N = BN, into [0, BN)); the epilogue adds the two column halves.  The A tile — the
+            // operand that dominates the shared-memory port for C_out <= 64 — is read twice per product instead of three times.
+            const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17), idesc1 = idesc_base | ((uint32_t)(BN >> 3) << 17);
             // descriptor-unit (16 B) offsets of the nine taps inside a patch stage
             uint32_t tap_off[9];
 #pragma unroll
@@ -230,12 +247,13 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const int nAe = p.nA / kMmaWarps;
             const uint32_t a_step = (uint32_t)p.a_stage_bytes >> 4;
             const uint32_t a_lo0 = desc_lo(smem_u32(a_ring + patch_off)) + (uint32_t)(mw * nAe) * a_step;
-            const uint32_t b_lo0 = desc_lo(smem_u32(b_ring)), b_step = (uint32_t)p.b_stage_bytes >> 4;
+            constexpr uint32_t kPairUnits = (uint32_t)kPairBytes >> 4;
+            const uint32_t b_lo0 = desc_lo(smem_u32(b_ring));
             if (p.w_resident) {
                 mbar_wait(w_full, 0);
                 tc_fence_after();
             }
-            const uint32_t tmem_d = tmem_base + mw * BN;
+            const uint32_t tmem_d = tmem_base + mw * 2 * BN;
             const int my_tiles = ((int)p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
             const int npairs = (my_tiles + kMmaWarps - 1) / kMmaWarps;
             for (int P = 0; P < npairs; ++P) {
@@ -243,6 +261,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (has) {
                     mbar_wait(acc_empty + mw, (P & 1) ^ 1);
                     tc_fence_after();
+                    CONV_T(0, P * kMmaWarps + mw);
                 }
                 for (int cb = 0; cb < p.CB; ++cb) {
                     const int k = P * p.CB + cb;
@@ -250,40 +269,36 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     if (has) {
                         mbar_wait(a_full + mw * nAe + sl, (k / nAe) & 1);
                         tc_fence_after();
+                        if (cb == 0) CONV_T(5, P * kMmaWarps + mw);
                     }
                     const uint32_t a_lo = a_lo0 + sl * a_step;
 #pragma unroll
-                    for (int kr = 0; kr < 3; ++kr) {
+                    for (int pr = 0; pr < 5; ++pr) {                    // weight stage = taps 2 pr, 2 pr + 1
                         uint32_t b_lo;
                         int sb = 0;
                         if (p.w_resident) {
-                            b_lo = b_lo0 + (uint32_t)((cb * 9 + kr * 3) * BN * 8);
+                            b_lo = b_lo0 + (uint32_t)(cb * 5 + pr) * kPairUnits;
                         } else {
-                            const int bi = k * 3 + kr;
+                            const int bi = k * 5 + pr;
                             sb = bi % p.nB;
                             mbar_wait(b_full + sb, (bi / p.nB) & 1);
                             tc_fence_after();
-                            b_lo = b_lo0 + sb * b_step;
+                            b_lo = b_lo0 + (uint32_t)sb * kPairUnits;
                         }
                         if (has) {
 #pragma unroll
-                            for (int kc = 0; kc < 3; ++kc) {
-                                const uint32_t al = a_lo + tap_off[kr * 3 + kc], bl = b_lo + kc * BN * 8;
-                                const uint32_t fresh = (cb == 0 && kr == 0 && kc == 0) ? 1u : 0u;
-                                // [hi x32 | lo x32] rows: hi at byte 0 / 32 (two K = 16 steps = +0 / +2 descriptor units), lo at
-                                // 64 / 96 (+4 / +6); small terms first
-                                if (!(p.dbg & 1)) {
+                            for (int h = 0; h < 2; ++h) {
+                                const int tap = 2 * pr + h;
+                                if (tap < 9) {
+                                    // patch rows are [hi x32 | lo x32] (hi at +0 / +2 descriptor units for the two K = 16 steps, lo at
+                                    // +4 / +6); weight rows are [tap 2 pr x32 | tap 2 pr + 1 x32]
+                                    const uint32_t al = a_lo + tap_off[tap], bl = b_lo + 4 * h;
+                                    const uint32_t fresh = (cb == 0 && tap == 0) ? 1u : 0u;
 #pragma unroll
-                                    for (int kk = 0; kk < 2; ++kk)
-                                        mma_bf16_w(tmem_d, al + 4 + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
-#pragma unroll
-                                    for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 4 + 2 * kk, kDescHi, idesc, 1u);
-#pragma unroll
-                                    for (int kk = 0; kk < 2; ++kk) mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc, 1u);
-                                } else {
-#pragma unroll
-                                    for (int kk = 0; kk < 2; ++kk)
-                                        mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc, (fresh && kk == 0) ? 0u : 1u);
+                                    for (int kk = 0; kk < 2; ++kk) {
+                                        mma_bf16_w(tmem_d, al + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc2, (fresh && kk == 0) ? 0u : 1u);
+                                        if (!(p.dbg & 1)) mma_bf16_w(tmem_d, al + 4 + 2 * kk, kDescHi, bl + 2 * kk, kDescHi, idesc1, 1u);
+                                    }
                                 }
                             }
                         }
@@ -295,7 +310,10 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                     if (has) tc_commit(a_empty + mw * nAe + sl);
                 }
-                if (has) tc_commit(acc_full + mw);
+                if (has) {
+                    tc_commit(acc_full + mw);
+                    CONV_T(1, P * kMmaWarps + mw);
+                }
             }
         }
     } else {
@@ -315,15 +333,17 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const bool valid = img < p.G && n < p.N && ri < p.R && y < p.H && x < p.W;
             mbar_wait(acc_full + buf, (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+            if (threadIdx.x == 32 * kEpiWarp0) CONV_T(2, it);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
+                uint32_t v[16], v2[16];
                 tmem_ld16(taddr + c0, v);
+                tmem_ld16(taddr + BN + c0, v2);
                 float o[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    float t = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.0f);
+                    float t = (__uint_as_float(v[j]) + __uint_as_float(v2[j])) + (p.bias ? __ldg(p.bias + c0 + j) : 0.0f);
                     o[j] = p.relu ? fmaxf(t, 0.0f) : t;
                 }
                 if (p.dbg & 2) {
@@ -352,6 +372,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
+            if (threadIdx.x == 32 * kEpiWarp0) CONV_T(3, it);
             if (p.pool && !(p.dbg & 2)) {
                 epi_bar_sync();
                 // 32 pooled slots per tile (slot = lane), BN/4 channels per thread (channel quarter = warp).  The tile's rows
@@ -406,7 +427,9 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
 }
 
-// ---- weights [K = ci*9 + tap, C_out] fp32 -> planes [ci/32][tap][co][hi x32 | lo x32] ----------------------------
+// ---- weights [K = ci*9 + tap, C_out] fp32 -> the kernel's B operand:
+//   [ci/32][tap pair p = tap/2 (5 pairs, the tenth tap is zero)][row r < 2*C_out][64 bf16 = tap 2p: 32 channels | tap 2p+1: 32 channels]
+//   rows r < C_out hold hi = rn_bf16(w) of output channel r, rows r >= C_out hold lo = rn_bf16(w - hi) of channel r - C_out
 struct WPrep {
     const float* w2[kMaxPrep];
     uint16_t* dst[kMaxPrep];
@@ -420,16 +443,16 @@ conv_w_planes_kernel(const __grid_constant__ WPrep wp) {
     const int l = blockIdx.y;
     if (l >= wp.count) return;
     const int cin = wp.cin[l], cout = wp.cout[l];
-    const int total = cin * 9 * cout;
+    const int total = cin * 10 * cout;                          // tap 9 of every channel: the zero half of the fifth pair
     for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
-        const int co = e % cout, k = e / cout;                // k = ci*9 + tap: coalesced reads along co
-        const int ci = k / 9, tap = k - ci * 9;
-        const float v = __ldg(wp.w2[l] + e);
+        const int co = e % cout, k = e / cout;                  // k = ci*10 + tap: coalesced reads along co
+        const int ci = k / 10, tap = k - ci * 10;
+        const float v = tap < 9 ? __ldg(wp.w2[l] + (size_t)(ci * 9 + tap) * cout + co) : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
-        uint16_t* d = wp.dst[l] + ((size_t)((ci >> 5) * 9 + tap) * cout + co) * 64 + (ci & 31);
+        uint16_t* d = wp.dst[l] + ((size_t)((ci >> 5) * 5 + (tap >> 1)) * 2 * cout + co) * 64 + (tap & 1) * 32 + (ci & 31);
         d[0] = __bfloat16_as_ushort(h);
-        d[32] = __bfloat16_as_ushort(lo);
+        d[(size_t)cout * 64] = __bfloat16_as_ushort(lo);
     }
 }
 
@@ -459,9 +482,11 @@ nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, i
 // ---- first layer with a tiny contraction (C_in * 9 <= 36: the C_in = 1 image layer): direct fp32 on the CUDA cores,
 // bias + ReLU (+ 2x2 max-pool) fused, output written straight as planes.  Exact fp32, k order (ci, kr, kc) ascending.
 // Replaces im2col + sgemm + transpose_4d + add_bias_4d + relu (+ max_pool2d) of src/tensor.rs:1221-1285, 1379-1464.
+template <bool POOL>
 __global__ void __launch_bounds__(256)
 conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ w2, const float* __restrict__ bias,
-                         uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int pool, int relu) {
+                         uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int relu) {
+    constexpr bool pool = POOL;
     extern __shared__ __align__(16) float sw[];                // [K][Cout] then [Cout]
     const int K = Cin * 9;
     float* sb = sw + K * Cout;
@@ -472,7 +497,7 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
     __syncthreads();
     const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
     const unsigned int CG = Cout / 8;
-    const int nsub = pool ? 4 : 1;
+    constexpr int nsub = POOL ? 4 : 1, win = POOL ? 4 : 3;
     const unsigned int total = (unsigned int)N * Ho * Wo * CG;                               // < 2^31 (checked on the host)
     for (unsigned int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
         // 32-bit index arithmetic (64-bit divisions cost more than the nine taps)
@@ -481,29 +506,54 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
         const int xo = (int)(pix - rowi * (unsigned int)Wo);
         const unsigned int n = rowi / (unsigned int)Ho;
         const int yo = (int)(rowi - n * (unsigned int)Ho);
-        float best[8];
-        for (int s = 0; s < nsub; ++s) {
-            const int yy = pool ? 2 * yo + (s >> 1) : yo, xx = pool ? 2 * xo + (s & 1) : xo;
-            float acc[8];
+        const int y0 = (pool ? 2 * yo : yo) - 1, x0 = (pool ? 2 * xo : xo) - 1;
+        float acc[nsub][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-            for (int ci = 0; ci < Cin; ++ci) {
-                const float* xp = x + ((size_t)n * Cin + ci) * (size_t)H * W;
+        for (int s = 0; s < nsub; ++s)
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
-                    const float xv = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + (size_t)iy * W + ix) : 0.0f;
-                    const float4 wa = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8);
-                    const float4 wb = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8 + 4);
-                    acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]); acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
-                    acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]); acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+            for (int j = 0; j < 8; ++j) acc[s][j] = 0.0f;
+        for (int ci = 0; ci < Cin; ++ci) {
+            // the whole input window first (3x3, or 4x4 shared by the four pooled positions): every load is in flight before the
+            // first multiply, instead of one round trip per tap
+            const float* xp = x + ((size_t)n * Cin + ci) * (size_t)H * W;
+            float in[win * win];
+#pragma unroll
+            for (int r = 0; r < win; ++r)
+#pragma unroll
+                for (int c = 0; c < win; ++c) {
+                    const int iy = y0 + r, ix = x0 + c;
+                    in[r * win + c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + (size_t)iy * W + ix) : 0.0f;
+                }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float4 wa = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8);
+                const float4 wb = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8 + 4);
+#pragma unroll
+                for (int s = 0; s < nsub; ++s) {
+                    {
+                        const float xv = in[((s >> 1) + tap / 3) * win + (s & 1) + tap % 3];
+                        acc[s][0] = fmaf(xv, wa.x, acc[s][0]); acc[s][1] = fmaf(xv, wa.y, acc[s][1]);
+                        acc[s][2] = fmaf(xv, wa.z, acc[s][2]); acc[s][3] = fmaf(xv, wa.w, acc[s][3]);
+                        acc[s][4] = fmaf(xv, wb.x, acc[s][4]); acc[s][5] = fmaf(xv, wb.y, acc[s][5]);
+                        acc[s][6] = fmaf(xv, wb.z, acc[s][6]); acc[s][7] = fmaf(xv, wb.w, acc[s][7]);
+                    }
                 }
             }
+        }
+        float best[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float v = acc[j] + sb[cg * 8 + j];
-                if (relu) v = fmaxf(v, 0.0f);
-                best[j] = s == 0 ? v : fmaxf(best[j], v);
+        for (int j = 0; j < 8; ++j) {
+            const float bj = sb[cg * 8 + j];
+            float v = acc[0][j] + bj;
+            if (relu) v = fmaxf(v, 0.0f);
+            best[j] = v;
+#pragma unroll
+            for (int s = 1; s < nsub; ++s) {
+                {
+                    float u = acc[s][j] + bj;
+                    if (relu) u = fmaxf(u, 0.0f);
+                    best[j] = fmaxf(best[j], u);
+                }
             }
         }
         uint4 h, l;
@@ -662,22 +712,23 @@ bool plan_layer(int N, int H, int W, int Cin, int Cout, bool pool, int out_mode,
     q.shift_mode = shift_mode;
     q.a_stage_bytes = shift_mode ? 1024 + q.patch_alloc : 3 * q.patch_alloc;
     const int stage_bytes = pool ? 128 * (Cout + 4) * 4 : 0;
-    const int w_bytes = 9 * q.CB * Cout * 128;
+    const int pair_bytes = 2 * Cout * 128;                              // one weight stage (two taps, hi and lo rows)
+    const int w_bytes = 5 * q.CB * pair_bytes;
     int left = kSmemBudget - stage_bytes;
     // patch stages come in pairs (one half of the ring per MMA issuer)
-    if (w_bytes <= 80 * 1024 && left - w_bytes >= 2 * q.a_stage_bytes) {
+    if (w_bytes <= 96 * 1024 && left - w_bytes >= 2 * q.a_stage_bytes) {
         q.w_resident = 1;
         q.b_stage_bytes = 0; q.nB = 0;
         int nA = (left - w_bytes) / q.a_stage_bytes;
         q.nA = nA >= 6 ? 6 : nA >= 4 ? 4 : 2;
     } else {
         q.w_resident = 0;
-        q.b_stage_bytes = 3 * Cout * 128;
+        q.b_stage_bytes = pair_bytes;
         q.nA = 4;
         if (left - q.nA * q.a_stage_bytes < 2 * q.b_stage_bytes) q.nA = 2;
         int nB = (left - q.nA * q.a_stage_bytes) / q.b_stage_bytes;
         if (nB < 2) return false;
-        q.nB = nB > 6 ? 6 : nB;
+        q.nB = nB > 8 ? 8 : nB;
     }
     q.out_mode = out_mode;
     q.pool = pool ? 1 : 0;
@@ -699,9 +750,9 @@ bool make_map_x(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, const 
 }
 
 bool make_map_w(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, int CB, int Cout) {
-    cuuint64_t gdim[3] = {64, (cuuint64_t)Cout, (cuuint64_t)9 * CB};
-    cuuint64_t gstr[2] = {128, (cuuint64_t)Cout * 128};
-    cuuint32_t box[3] = {64, (cuuint32_t)Cout, 3};
+    cuuint64_t gdim[3] = {64, (cuuint64_t)2 * Cout, (cuuint64_t)5 * CB};
+    cuuint64_t gstr[2] = {128, (cuuint64_t)2 * Cout * 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)(2 * Cout), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -793,7 +844,7 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         int ci = C0;
         for (int l = 0; l < n_layers; ++l) {
             woff[l] = wtot;
-            if (!(l == 0 && first_direct)) wtot += (size_t)ci * 9 * cout[l];
+            if (!(l == 0 && first_direct)) wtot += (size_t)ci * 10 * cout[l];          // bf16 pairs: 5 tap pairs x (hi + lo rows) x 64 per 32 channels
             ci = cout[l];
         }
     }
@@ -835,9 +886,11 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         const int ho = pool[0] ? h / 2 : h, wo = pool[0] ? w / 2 : w;
         const size_t items = (size_t)N * ho * wo * (cout[0] / 8);
         const size_t sm = (size_t)(C0 * 9 + 1) * cout[0] * sizeof(float);
-        if ((rc = launch_pdl(ctx, conv_first_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, pdl, x, w2[0], bias[0],
-                             (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], pool[0] ? 1 : 0, relu[0] ? 1 : 0)))
-            return rc;
+        rc = pool[0] ? launch_pdl(ctx, conv_first_planes_kernel<true>, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, pdl, x, w2[0], bias[0],
+                                  (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], relu[0] ? 1 : 0)
+                     : launch_pdl(ctx, conv_first_planes_kernel<false>, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, pdl, x, w2[0], bias[0],
+                                  (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], relu[0] ? 1 : 0);
+        if (rc) return rc;
         h = ho; w = wo; c = cout[0];
         l0 = 1;
     } else {
@@ -869,6 +922,9 @@ extern "C" {
 int tpdbg_conv_shift_mode(int mode) {
     g_shift_override = mode;
     return 0;
+}
+int tpdbg_conv_times(long long* out384) {
+    return cudaMemcpyFromSymbol(out384, g_conv_t, sizeof(long long) * 6 * 64) == cudaSuccess ? 0 : 1;
 }
 int tpdbg_conv_flags(int flags) {
     g_dbg_flags = flags;
