@@ -32,9 +32,10 @@
 // re-laid once per step as [ci/32][tap pair][W_hi rows x C_out ; W_lo rows x C_out][tap 2p x32 | tap 2p+1 x32] (128-byte
 // K-major rows again; a tap is the row's first or second half) and either stay resident in shared memory for the whole kernel
 // (<= 96 KB) or stream through a second ring, one tap pair per stage.
-// Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warps 1-2 MMA issuers (one per TMEM accumulator; tiles
-// are handled in pairs), warps 3-6 epilogue (tile i+1 multiplies while tile i is read out): bias + ReLU (+ 2x2 max-pool through a
-// shared-memory staging tile) and either the planes of the next layer or NCHW fp32 for the rest of the tape.
+// Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warps 1-2 MMA issuers (two for C_out <= 64, tiles handled
+// in pairs; one for C_out = 128) with TWO TMEM accumulators each, warps 3-6 epilogue (the next tiles multiply while a tile is
+// read out): bias + ReLU (+ 2x2 max-pool through a shared-memory staging tile) and either the planes of the next layer or NCHW
+// fp32 for the rest of the tape.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -45,9 +46,18 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kMmaWarps = 2;               // MMA-issuing warps: one per accumulator buffer, tiles alternate between them
-constexpr int kEpiWarp0 = 1 + kMmaWarps;    // first of the four epilogue warps
-constexpr int kConvThreads = 32 * (1 + kMmaWarps + 4);
+constexpr int kMaxIssuers = 2;             // warps 1..2 can issue MMAs (C_out = 128 uses one: its accumulators fill TMEM two at a time)
+constexpr int kEpiWarp0 = 1 + kMaxIssuers;  // first of the four epilogue warps
+constexpr int kConvThreads = 32 * (1 + kMaxIssuers + 4);
+// MMA issuers and accumulators per issuer for a tile width.  Measured (scripts/conv_timeline.py): with one accumulator per issuer
+// an issuer idles while the epilogue drains its tile (pipe utilisation ~60 %); with two it starts the next tile at once.  An
+// accumulator is 2 * C_out TMEM columns ([hi*hi + lo*hi | hi*lo]) and TMEM has 512.
+template <int BN> struct ConvCfg {
+    static constexpr int kIssuers = BN <= 64 ? 2 : 1;
+    static constexpr int kAccPer = 2;
+    static constexpr int kAccs = kIssuers * kAccPer;
+    static constexpr uint32_t kTmemCols = kAccs * 2 * BN < 32 ? 32 : kAccs * 2 * BN;
+};
 constexpr int kMaxRing = 8;
 constexpr int kMaxPrep = 8;
 
@@ -134,11 +144,12 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint64_t* a_empty = a_full + kMaxRing;
     uint64_t* b_full = a_empty + kMaxRing;
     uint64_t* b_empty = b_full + kMaxRing;
-    uint64_t* acc_full = b_empty + kMaxRing;                          // [2]
-    uint64_t* acc_empty = acc_full + 2;                               // [2]
-    uint64_t* w_full = acc_empty + 2;
+    uint64_t* acc_full = b_empty + kMaxRing;                          // [4]
+    uint64_t* acc_empty = acc_full + 4;                               // [4]
+    uint64_t* w_full = acc_empty + 4;
     uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
-    constexpr uint32_t kTmemCols = 4 * BN;                            // two accumulators of [hi*hi + lo*hi | hi*lo] = 2 * BN columns
+    constexpr int kMmaWarps = ConvCfg<BN>::kIssuers, kAccPer = ConvCfg<BN>::kAccPer;
+    constexpr uint32_t kTmemCols = ConvCfg<BN>::kTmemCols;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -150,7 +161,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             mbar_init(b_full + s, 1);
             mbar_init(b_empty + s, kMmaWarps);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, 4);
         }
@@ -225,11 +236,11 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 }
             }
         }
-    } else if (warp <= kMmaWarps) {
+    } else if (warp <= kMaxIssuers) {
         // ===== MMA issuers: warp 1 + w multiplies tile 2P + w of every pair into accumulator w.  One thread issuing all MMAs is
         // latency-bound on its own instruction stream (measured ~95 clocks per MMA against the ~48 the shared-memory port allows
         // for 128 x 32 x 16): two issuers interleave their streams in the tensor pipe. =====
-        if (lane == 0) {
+        if (lane == 0 && warp <= kMmaWarps) {
             const int mw = warp - 1;
             // instruction descriptors: D = F32 (1 << 4), A / B = BF16 (1 << 7, 1 << 10), both K-major, N >> 3 at 17, M >> 4 at 24.
             // Per tap and K = 16 step two MMAs instead of three:  A_hi x [W_hi ; W_lo] (N = 2 BN: hi*hi into columns [0, BN), hi*lo
@@ -253,13 +264,14 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 mbar_wait(w_full, 0);
                 tc_fence_after();
             }
-            const uint32_t tmem_d = tmem_base + mw * 2 * BN;
             const int my_tiles = ((int)p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
             const int npairs = (my_tiles + kMmaWarps - 1) / kMmaWarps;
             for (int P = 0; P < npairs; ++P) {
                 const bool has = (int)(blockIdx.x + (P * kMmaWarps + mw) * gridDim.x) < p.tiles;
+                const int acc = mw * kAccPer + P % kAccPer;               // this issuer's P-th tile goes to its accumulator P % kAccPer
+                const uint32_t tmem_d = tmem_base + acc * 2 * BN;
                 if (has) {
-                    mbar_wait(acc_empty + mw, (P & 1) ^ 1);
+                    mbar_wait(acc_empty + acc, ((P / kAccPer) & 1) ^ 1);
                     tc_fence_after();
                     CONV_T(0, P * kMmaWarps + mw);
                 }
@@ -311,7 +323,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     if (has) tc_commit(a_empty + mw * nAe + sl);
                 }
                 if (has) {
-                    tc_commit(acc_full + mw);
+                    tc_commit(acc_full + acc);
                     CONV_T(1, P * kMmaWarps + mw);
                 }
             }
@@ -326,12 +338,13 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int CBo = BN / 32;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
+            const int ew = it % kMmaWarps, ej = it / kMmaWarps;           // issuer and that issuer's tile count
+            const int buf = ew * kAccPer + ej % kAccPer;
             const int ng = tile / p.row_blocks, rb = tile - ng * p.row_blocks;
             const int n0 = ng * p.G, y0 = rb * p.R;
             const int n = n0 + img, y = y0 + ri, x = rj;
             const bool valid = img < p.G && n < p.N && ri < p.R && y < p.H && x < p.W;
-            mbar_wait(acc_full + buf, (it >> 1) & 1);
+            mbar_wait(acc_full + buf, (ej / kAccPer) & 1);
             tc_fence_after();
             if (threadIdx.x == 32 * kEpiWarp0) CONV_T(2, it);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN;
