@@ -240,6 +240,12 @@ int tp_conv2d_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* gy, c
 int tp_conv_stack_fwd(tp_ctx*, const tp_buf* x, int n, int c_in, int h, int w, int n_layers,
                       const tp_buf* const* weights, const tp_buf* const* biases, const int* c_out,
                       const int* pool, const int* relu, tp_buf* y);
+/* The same stack with AdaptiveAvgPool2d::global on top (src/nn.rs:670-686): mean[n,c] over the last layer's plane and, when
+ * cnt != NULL, cnt[n,c] = #{units of the plane > 0}; the last layer's activation itself is not written when its tiles hold whole
+ * images (7x7 and smaller: the pooling happens in the conv epilogue), otherwise it goes through a scratch buffer. */
+int tp_conv_stack_gap_fwd(tp_ctx*, const tp_buf* x, int n, int c_in, int h, int w, int n_layers,
+                          const tp_buf* const* weights, const tp_buf* const* biases, const int* c_out,
+                          const int* pool, const int* relu, tp_buf* mean, tp_buf* cnt);
 /* Global average pool fused with the per-plane count of positive units:  mean[n,c] = sum_p y[n,c,p] / hw
  * (AdaptiveAvgPool2d::global -> avg_pool2d, src/nn.rs:670-686, src/tensor.rs:1524-1590), cnt[n,c] = #{p : y[n,c,p] > 0}
  * (NULL to skip).  cnt is all that the backward of [conv bias -> ReLU -> global average pool] needs: */

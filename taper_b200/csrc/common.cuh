@@ -155,7 +155,13 @@ int gemm_tc_conv_fwd(tp_ctx* ctx, const float* x, const float* w2, const float* 
 // ---- stack of 3x3 / s1 / p1 convolutions (+bias, optional ReLU, optional 2x2 max-pool each) on the tcgen05 bf16x3 path over NHWC
 // bf16 hi/lo planes (conv_bx3.cu); NCHW fp32 in and out.  TP_ERR_UNSUPPORTED (nothing launched) when a shape does not fit.
 int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int n_layers, const float* const* w2,
-                   const float* const* bias, const int* cout, const int* pool, const int* relu, float* y);
+                   const float* const* bias, const int* cout, const int* pool, const int* relu, float* y,
+                   float* gap_mean = nullptr, float* gap_cnt = nullptr);       // gap_mean: global average pool on top (y unused)
+
+// input gradient of a 3x3 / s1 / p1 convolution on the same kernel (dZ = gy * [relu_mask_y > 0] re-laid as planes, weights transposed
+// and mirrored); NCHW fp32 in and out.  TP_ERR_UNSUPPORTED when the shape does not fit (nothing launched).
+int conv_bx3_dx(tp_ctx* ctx, const float* gy, const float* relu_mask_y, const float* w2, float* dx, int N, int Cin, int H, int W,
+                int Cout, int accumulate);
 
 // ---- bf16x3 tensor-core GEMM on pre-split operands (gemm_bx3.cu) -----------------------------------------------------
 // A "split" tensor holds an fp32 tensor of n elements as two bf16 planes: hi = rn_bf16(x) at [0, n) and

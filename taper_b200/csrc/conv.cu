@@ -360,6 +360,15 @@ int tp_conv2d_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* g
     if (!M) return TP_OK;
     TP_CHECK_ARG(M <= 0x7fffffff, "tp_conv2d_bwd: N*Ho*Wo = %zu exceeds int range", M);
 
+    // 3x3 / s1 / p1 with tensor-core-sized channel counts: dX = conv(gy * mask, mirrored W^T) on the implicit-GEMM kernel
+    // (conv_bx3.cu) — no [M, K] gradient matrix, no col2im
+    if (dx && g_conv_v2 && ctx->gemm_mode != 0 && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 && g.pw == 1 &&
+        g.dh == 1 && g.dw == 1) {
+        TP_NEED(w, (size_t)g.K * g.cout, "w"); TP_NEED(dx, (size_t)g.n * g.c * g.h * g.w, "dx");
+        rc = tp::conv_bx3_dx(ctx, gy->ptr, relu_mask_y ? relu_mask_y->ptr : nullptr, w->ptr, dx->ptr, g.n, g.c, g.h, g.w, g.cout, acc_dx);
+        if (rc == TP_OK) dx = nullptr;                         // done
+        else if (rc != TP_ERR_UNSUPPORTED) return rc;
+    }
     const tp_buf* gz = gy;                     // gradient w.r.t. the pre-activation conv output, NCHW
     TmpBuf gmask;
     if (relu_mask_y && db && !(dw || dx)) {
@@ -386,12 +395,29 @@ int tp_conv2d_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* g
     tp::Epilogue ep;
     if (dw) {
         TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(dw, (size_t)g.K * g.cout, "dw");
+        // dW2[K,Cout] (+)= col^T[K,M] * g_nhwc[M,Cout]   (matmul backward wrt B, src/ops.rs:280-291), in image chunks so that the
+        // materialised im2col matrix stays below 256 MB whatever the batch (the whole [M, K] matrix is 925 MB for the 32 -> 32
+        // layer at batch 1024): the chunks accumulate into dW in image order
+        const size_t per_img = (size_t)g.ho * g.wo * g.K;
+        int chunk = (int)(((size_t)64 << 20) / (per_img ? per_img : 1));
+        if (chunk < 1) chunk = 1;
+        if (chunk > g.n) chunk = g.n;
         TmpBuf col;
-        if ((rc = tp_buf_alloc(ctx, M * g.K, &col.b))) return rc;
-        if ((rc = tp_im2col(ctx, x, col.b, d))) return rc;
-        // dW2[K,Cout] (+)= col^T[K,M] * g_nhwc[M,Cout]   (matmul backward wrt B, src/ops.rs:280-291)
-        if ((rc = tp::gemm_rowmajor(ctx, 1, 0, g.K, g.cout, (int)M, 1.0f, col.b->ptr, g_nhwc.b->ptr, acc_dw ? 1.0f : 0.0f, dw->ptr, ep)))
-            return rc;
+        if ((rc = tp_buf_alloc(ctx, (size_t)chunk * per_img, &col.b))) return rc;
+        for (int n0 = 0; n0 < g.n; n0 += chunk) {
+            const int nb = g.n - n0 < chunk ? g.n - n0 : chunk;
+            tp_conv_desc dc = *d;
+            dc.n = nb;
+            tp_buf* xs = nullptr;
+            if ((rc = tp_buf_slice(const_cast<tp_buf*>(x), (size_t)n0 * g.c * g.h * g.w, (size_t)nb * g.c * g.h * g.w, &xs))) return rc;
+            rc = tp_im2col(ctx, xs, col.b, &dc);
+            tp_buf_release(xs);
+            if (rc) return rc;
+            const size_t m0 = (size_t)n0 * g.ho * g.wo;
+            if ((rc = tp::gemm_rowmajor(ctx, 1, 0, g.K, g.cout, nb * g.ho * g.wo, 1.0f, col.b->ptr, g_nhwc.b->ptr + m0 * g.cout,
+                                        (acc_dw || n0 > 0) ? 1.0f : 0.0f, dw->ptr, ep)))
+                return rc;
+        }
     }
     if (dx) {
         TP_NEED(w, (size_t)g.K * g.cout, "w"); TP_NEED(dx, (size_t)g.n * g.c * g.h * g.w, "dx");

@@ -72,8 +72,12 @@ struct ConvP {
     int dbg;                         // development: bit 0 hi*hi products only, bit 1 epilogue reads the accumulator but stores nothing
     int a_stage_bytes, nA;
     int w_resident, b_stage_bytes, nB;
-    int out_mode;                    // 0: planes (next conv), 1: NCHW fp32
+    int out_mode;                    // 0: planes (next conv), 1: NCHW fp32, 2: global average pool -> mean[N, C] + cnt[N, C]
+    int warp_img[4];                 // out_mode 2: the image (within the tile) whose rows epilogue warp q holds, -1: none
+    float* out_mean;
+    float* out_cnt;                  // may be NULL
     int pool, relu;
+    int accumulate;                  // NCHW output: out += result (gradient accumulation into a live grad, src/ops.rs:250-253)
     int Ho, Wo;                      // output spatial size (after the pool)
     const float* bias;
     uint16_t* out_planes;
@@ -120,6 +124,24 @@ __device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
     *lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
 }
 
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving: after the exchange with lane ^ 16 a
+// lane keeps 8 of the 16 sums, then 4, 2, 1; a last exchange with lane ^ 1 completes them).  Returns, in every lane, the total
+// of value index warp_sum16_index(lane).  Fixed association order: deterministic.
+__device__ __forceinline__ int warp_sum16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int n = 8, off = 16; n >= 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float send = upper ? v[j] : v[j + n];
+            const float keep = upper ? v[j + n] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // development aid: SM-clock stamps of CTA 0's first 64 tiles, read back with tpdbg_conv_times():
 //   [0] issuer saw its accumulator free  [1] issuer committed the tile  [2] epilogue saw the accumulator full
 //   [3] epilogue released the accumulator  [4] producer issued the tile's first patch load  [5] issuer saw the first patch
@@ -139,7 +161,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int b_total = p.w_resident ? 5 * p.CB * kPairBytes : p.nB * kPairBytes;
     constexpr int kPitch = BN + 4;                                    // floats per staged row (pool)
     float* stage = (float*)(b_ring + b_total);
-    uint64_t* bars = (uint64_t*)((uint8_t*)stage + (p.pool ? 128 * kPitch * 4 : 0));
+    uint64_t* bars = (uint64_t*)((uint8_t*)stage + (p.pool ? 128 * kPitch * 4 : p.out_mode == 2 ? 8 * BN * 4 : 0));
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + kMaxRing;
     uint64_t* b_full = a_empty + kMaxRing;
@@ -360,6 +382,20 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     o[j] = p.relu ? fmaxf(t, 0.0f) : t;
                 }
                 if (p.dbg & 2) {
+                } else if (p.out_mode == 2) {
+                    // global average pool in the epilogue: per-warp sums (and counts of positive units) of the 16 channels over the
+                    // warp's 32 tile rows -> shared memory; folded per image below
+                    float sv[16], cv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        sv[j] = valid ? o[j] : 0.0f;
+                        cv[j] = (valid && o[j] > 0.0f) ? 1.0f : 0.0f;
+                    }
+                    const float ts = warp_sum16(sv, lane), tc = warp_sum16(cv, lane);
+                    if (!(lane & 1)) {
+                        stage[(q * 2 + 0) * BN + c0 + warp_sum16_index(lane)] = ts;
+                        stage[(q * 2 + 1) * BN + c0 + warp_sum16_index(lane)] = tc;
+                    }
                 } else if (p.pool) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) *(float4*)(stage + r * kPitch + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -377,7 +413,7 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         float* dst = p.out_nchw + (((size_t)n * BN + c0) * p.H + y) * p.W + x;
                         const size_t cs = (size_t)p.H * p.W;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) dst[j * cs] = o[j];
+                        for (int j = 0; j < 16; ++j) dst[j * cs] = p.accumulate ? dst[j * cs] + o[j] : o[j];
                     }
                 }
             }
@@ -386,6 +422,24 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
             if (threadIdx.x == 32 * kEpiWarp0) CONV_T(3, it);
+            if (p.out_mode == 2 && !(p.dbg & 2)) {
+                epi_bar_sync();
+                // fold the warps of each image in warp order (fixed: deterministic), one channel per thread
+                for (int c = et; c < BN; c += 128) {
+                    for (int g = 0; g < p.G; ++g) {
+                        float ssum = 0.0f, scnt = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            if (p.warp_img[w] == g) { ssum += stage[(w * 2 + 0) * BN + c]; scnt += stage[(w * 2 + 1) * BN + c]; }
+                        const int gn = n0 + g;
+                        if (gn < p.N) {
+                            p.out_mean[(size_t)gn * BN + c] = ssum / (float)(p.H * p.W);
+                            if (p.out_cnt) p.out_cnt[(size_t)gn * BN + c] = scnt;
+                        }
+                    }
+                }
+                epi_bar_sync();
+            }
             if (p.pool && !(p.dbg & 2)) {
                 epi_bar_sync();
                 // 32 pooled slots per tile (slot = lane), BN/4 channels per thread (channel quarter = warp).  The tile's rows
@@ -447,6 +501,7 @@ struct WPrep {
     const float* w2[kMaxPrep];
     uint16_t* dst[kMaxPrep];
     int cin[kMaxPrep], cout[kMaxPrep];
+    int adjoint[kMaxPrep];           // 1: the weights of the input-gradient convolution, W'[co*9 + (8 - tap), ci] = W[ci*9 + tap, co]
     int count;
 };
 __global__ void __launch_bounds__(256)
@@ -460,7 +515,10 @@ conv_w_planes_kernel(const __grid_constant__ WPrep wp) {
     for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
         const int co = e % cout, k = e / cout;                  // k = ci*10 + tap: coalesced reads along co
         const int ci = k / 10, tap = k - ci * 10;
-        const float v = tap < 9 ? __ldg(wp.w2[l] + (size_t)(ci * 9 + tap) * cout + co) : 0.0f;
+        // adjoint: this layer's (ci, co) are the forward layer's (co, ci) and the taps are mirrored (dX = conv(dY, flipped W^T))
+        const float v = tap >= 9 ? 0.0f
+                        : wp.adjoint[l] ? __ldg(wp.w2[l] + (size_t)(co * 9 + (8 - tap)) * cin + ci)
+                                        : __ldg(wp.w2[l] + (size_t)(ci * 9 + tap) * cout + co);
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(h));
         uint16_t* d = wp.dst[l] + ((size_t)((ci >> 5) * 5 + (tap >> 1)) * 2 * cout + co) * 64 + (tap & 1) * 32 + (ci & 31);
@@ -471,7 +529,7 @@ conv_w_planes_kernel(const __grid_constant__ WPrep wp) {
 
 // ---- NCHW fp32 -> planes (first layer of a stack whose input already has >= 32 channels; the single-layer eager op) --------
 __global__ void __launch_bounds__(256)
-nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int C, int H, int W) {
+nchw_to_planes_kernel(const float* __restrict__ x, const float* __restrict__ mask, uint16_t* __restrict__ out, int N, int C, int H, int W) {
     pdl_wait();
     pdl_launch_dependents();
     const unsigned int CG = C / 8;
@@ -484,6 +542,11 @@ nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, i
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j * hw);
+        if (mask) {                                          // ReLU backward on the way in: g * [y > 0]  (src/ops.rs:358-370)
+            const float* ms = mask + (src - x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(ms + j * hw) > 0.0f ? v[j] : 0.0f;
+        }
         uint4 h, l;
         split8(v, &h, &l);
         uint16_t* dst = out + (((size_t)n * hw + pix) * (C / 32) + (cg >> 2)) * 64 + (cg & 3) * 8;
@@ -724,7 +787,7 @@ bool plan_layer(int N, int H, int W, int Cin, int Cout, bool pool, int out_mode,
     q.tiles = ((N + q.G - 1) / q.G) * q.row_blocks;
     q.shift_mode = shift_mode;
     q.a_stage_bytes = shift_mode ? 1024 + q.patch_alloc : 3 * q.patch_alloc;
-    const int stage_bytes = pool ? 128 * (Cout + 4) * 4 : 0;
+    const int stage_bytes = pool ? 128 * (Cout + 4) * 4 : out_mode == 2 ? 8 * Cout * 4 : 0;
     const int pair_bytes = 2 * Cout * 128;                              // one weight stage (two taps, hi and lo rows)
     const int w_bytes = 5 * q.CB * pair_bytes;
     int left = kSmemBudget - stage_bytes;
@@ -744,6 +807,20 @@ bool plan_layer(int N, int H, int W, int Cin, int Cout, bool pool, int out_mode,
         q.nB = nB > 8 ? 8 : nB;
     }
     q.out_mode = out_mode;
+    if (out_mode == 2) {
+        // the pooled epilogue folds whole images inside a tile: every image in one tile, every epilogue warp's rows in one image
+        if (pool || q.row_blocks != 1) return false;
+        for (int w = 0; w < 4; ++w) {
+            q.warp_img[w] = -1;
+            for (int r = 32 * w; r < 32 * w + 32; ++r) {
+                const int img = r / q.img_rows, rem = r - img * q.img_rows;
+                const int ri = rem / q.Wp, rj = rem - ri * q.Wp;
+                if (img >= q.G || ri >= H || rj >= W) continue;
+                if (q.warp_img[w] >= 0 && q.warp_img[w] != img) return false;
+                q.warp_img[w] = img;
+            }
+        }
+    }
     q.pool = pool ? 1 : 0;
     q.relu = 1;
     q.Ho = pool ? H / 2 : H;
@@ -825,7 +902,7 @@ size_t conv_planes_floats(size_t n, size_t h, size_t w, size_t c) { return n * h
 // One stack of 3x3 / s1 / p1 Conv(+bias)+ReLU layers, each optionally followed by a 2x2 / s2 max-pool, NCHW fp32 in and out.
 // TP_ERR_UNSUPPORTED: some layer's shape does not go this way (nothing has been launched).
 int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int n_layers, const float* const* w2,
-                   const float* const* bias, const int* cout, const int* pool, const int* relu, float* y) {
+                   const float* const* bias, const int* cout, const int* pool, const int* relu, float* y, float* gap_mean, float* gap_cnt) {
     if (n_layers < 1 || n_layers > kMaxPrep) return TP_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) return TP_ERR_UNSUPPORTED;
@@ -841,10 +918,17 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
     if (!first_direct && C0 % 32) return TP_ERR_UNSUPPORTED;
     ConvP P[kMaxPrep];
     int smem[kMaxPrep];
+    bool gap_in_epilogue = false;
     int h = H, w = W, c = C0;
     for (int l = 0; l < n_layers; ++l) {
         if (!(l == 0 && first_direct)) {
-            if (!plan_layer(N, h, w, c, cout[l], pool[l] != 0, l == n_layers - 1 ? 1 : 0, shift_mode, &P[l], &smem[l])) return TP_ERR_UNSUPPORTED;
+            const bool last = l == n_layers - 1;
+            // a trailing global average pool is folded into the last layer's epilogue when its tiles hold whole images
+            if (last && gap_mean && plan_layer(N, h, w, c, cout[l], pool[l] != 0, 2, shift_mode, &P[l], &smem[l])) {
+                gap_in_epilogue = true;
+            } else if (!plan_layer(N, h, w, c, cout[l], pool[l] != 0, last ? 1 : 0, shift_mode, &P[l], &smem[l])) {
+                return TP_ERR_UNSUPPORTED;
+            }
         }
         if (pool[l]) { h /= 2; w /= 2; }
         c = cout[l];
@@ -892,6 +976,15 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         if ((rc = launch_pdl(ctx, conv_w_planes_kernel, dim3(32, wp.count), dim3(256), 0, false, wp))) return rc;
     }
     // ---- layers ----
+    // a trailing global average pool that the last epilogue cannot absorb reads the NCHW output from a scratch buffer
+    int hl = H, wl = W;
+    for (int l = 0; l < n_layers; ++l) if (pool[l]) { hl /= 2; wl /= 2; }
+    TmpBuf ytmp;
+    float* y_last = y;
+    if (gap_mean && !gap_in_epilogue) {
+        if ((rc = tp_buf_alloc(ctx, (size_t)N * cout[n_layers - 1] * hl * wl, &ytmp.b))) return rc;
+        y_last = ytmp.b->ptr;
+    }
     int cur = 0;
     h = H; w = W; c = C0;
     int l0 = 0;
@@ -908,24 +1001,75 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         l0 = 1;
     } else {
         const size_t items = (size_t)N * h * w * (c / 8);
-        if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, pdl, x, (uint16_t*)act[cur].b->ptr, N, c, h, w)))
+        if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, pdl, x, (const float*)nullptr, (uint16_t*)act[cur].b->ptr, N, c, h, w)))
             return rc;
     }
     for (int l = l0; l < n_layers; ++l) {
         ConvP& p = P[l];
         p.bias = bias[l];
         p.relu = relu[l] ? 1 : 0;
+        p.accumulate = 0;
         p.dbg = g_dbg_flags;
         const bool last = l == n_layers - 1;
         p.out_planes = last ? nullptr : (uint16_t*)act[cur ^ 1].b->ptr;
-        p.out_nchw = last ? y : nullptr;
+        p.out_nchw = last ? y_last : nullptr;
+        p.out_mean = gap_mean;
+        p.out_cnt = gap_cnt;
         CUtensorMap mx, mw;
         if (!make_map_x(enc, &mx, (const uint16_t*)act[cur].b->ptr, p)) { set_error("conv_stack_fwd: cuTensorMapEncodeTiled (activations) failed"); return TP_ERR_CUDA; }
         if (!make_map_w(enc, &mw, (const uint16_t*)(wplanes.b->ptr + woff[l]), p.CB, p.Cout)) { set_error("conv_stack_fwd: cuTensorMapEncodeTiled (weights) failed"); return TP_ERR_CUDA; }
         if ((rc = launch_conv_any(ctx, mx, mw, p, smem[l], pdl))) return rc;
         cur ^= 1;
     }
+    if (gap_mean && !gap_in_epilogue) {
+        const size_t planes = (size_t)N * cout[n_layers - 1];
+        if ((rc = launch_pdl(ctx, gap_count_kernel, dim3(grid_for(ctx, planes * 16, 256, 8)), dim3(256), 0, pdl, (const float*)y_last, gap_mean,
+                             gap_cnt, (int)planes, hl * wl)))
+            return rc;
+    }
     return TP_OK;
+}
+
+// Input gradient of a 3x3 / s1 / p1 convolution as the SAME implicit GEMM (north_star's dY . W^T on the conv path; the reference
+// drops this link, SURVEY A1 — full-adjoint mode only):  dX = conv(dZ, W') with dZ = gy * [y > 0] (ReLU backward, src/ops.rs:358-370,
+// applied while gy is re-laid as planes) and W'[co*9 + (8 - tap), ci] = W[ci*9 + tap, co] (channels swapped, taps mirrored).
+// Replaces gcol = gy_nhwc . W^T  [M, K]  +  col2im  (src/ops.rs:254-265 on the im2col matrix): no [M, 9*C_in] buffer.
+// gy, relu_mask_y: NCHW [N, Cout, H, W]; dx: NCHW [N, Cin, H, W], overwritten or accumulated into.
+int conv_bx3_dx(tp_ctx* ctx, const float* gy, const float* relu_mask_y, const float* w2, float* dx, int N, int Cin, int H, int W,
+                int Cout, int accumulate) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TP_ERR_UNSUPPORTED;
+    if (Cout % 32 || (size_t)N * H * W * (size_t)Cout >= ((size_t)1 << 31)) return TP_ERR_UNSUPPORTED;
+    const int shift_mode = g_shift_override >= 0 ? g_shift_override : default_shift_mode();
+    cudaSetDevice(ctx->device);
+    ConvP p;
+    int smem;
+    if (!plan_layer(N, H, W, /*Cin of this conv*/ Cout, /*Cout of this conv*/ Cin, false, 1, shift_mode, &p, &smem)) return TP_ERR_UNSUPPORTED;
+    int rc;
+    TmpBuf wplanes, planes;
+    if ((rc = tp_buf_alloc(ctx, (size_t)Cout * 10 * Cin, &wplanes.b))) return rc;
+    if ((rc = tp_buf_alloc(ctx, (size_t)N * H * W * Cout, &planes.b))) return rc;
+    WPrep wp{};
+    wp.count = 1;
+    wp.w2[0] = w2;
+    wp.dst[0] = (uint16_t*)wplanes.b->ptr;
+    wp.cin[0] = Cout; wp.cout[0] = Cin;
+    wp.adjoint[0] = 1;
+    if ((rc = launch_pdl(ctx, conv_w_planes_kernel, dim3(32, 1), dim3(256), 0, false, wp))) return rc;
+    const size_t items = (size_t)N * H * W * (Cout / 8);
+    if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, true, gy, relu_mask_y,
+                         (uint16_t*)planes.b->ptr, N, Cout, H, W)))
+        return rc;
+    p.bias = nullptr;
+    p.relu = 0;
+    p.accumulate = accumulate ? 1 : 0;
+    p.dbg = 0;
+    p.out_planes = nullptr;
+    p.out_nchw = dx;
+    CUtensorMap mx, mw;
+    if (!make_map_x(enc, &mx, (const uint16_t*)planes.b->ptr, p)) { set_error("conv_bx3_dx: cuTensorMapEncodeTiled (gradient planes) failed"); return TP_ERR_CUDA; }
+    if (!make_map_w(enc, &mw, (const uint16_t*)wplanes.b->ptr, p.CB, p.Cout)) { set_error("conv_bx3_dx: cuTensorMapEncodeTiled (weights) failed"); return TP_ERR_CUDA; }
+    return launch_conv_any(ctx, mx, mw, p, smem, true);
 }
 
 }  // namespace tp
@@ -964,9 +1108,33 @@ int tp_conv_stack_fwd(tp_ctx* ctx, const tp_buf* x, int n, int c_in, int h, int 
     }
     TP_CHECK_ARG(hh > 0 && ww > 0, "tp_conv_stack_fwd: the pools leave no output");
     TP_NEED(y, (size_t)n * ci * hh * ww, "y");
-    int rc = tp::conv_stack_fwd(ctx, x->ptr, n, c_in, h, w, n_layers, wp, bp, c_out, pool, relu, y->ptr);
+    int rc = tp::conv_stack_fwd(ctx, x->ptr, n, c_in, h, w, n_layers, wp, bp, c_out, pool, relu, y->ptr, nullptr, nullptr);
     if (rc == TP_ERR_UNSUPPORTED) tp::set_error("tp_conv_stack_fwd: a layer's shape is outside the tensor-core stack (3x3/s1/p1, C_in %% 32 == 0 "
                                                  "(or C_in*9 <= 36 for the first layer), C_out in {32, 64, 128}, W < 32)");
+    return rc;
+}
+
+int tp_conv_stack_gap_fwd(tp_ctx* ctx, const tp_buf* x, int n, int c_in, int h, int w, int n_layers, const tp_buf* const* weights,
+                          const tp_buf* const* biases, const int* c_out, const int* pool, const int* relu, tp_buf* mean, tp_buf* cnt) {
+    TP_CHECK_ARG(ctx && x && weights && biases && c_out && pool && relu && mean, "tp_conv_stack_gap_fwd: NULL argument");
+    TP_CHECK_ARG(n_layers >= 1 && n_layers <= kMaxPrep, "tp_conv_stack_gap_fwd: 1..%d layers", kMaxPrep);
+    TP_CHECK_ARG(n > 0 && c_in > 0 && h > 0 && w > 0, "tp_conv_stack_gap_fwd: empty input");
+    TP_NEED(x, (size_t)n * c_in * h * w, "x");
+    const float* wp[kMaxPrep];
+    const float* bp[kMaxPrep];
+    int ci = c_in;
+    for (int l = 0; l < n_layers; ++l) {
+        TP_CHECK_ARG(c_out[l] > 0, "tp_conv_stack_gap_fwd: layer %d has no output channels", l);
+        TP_NEED(weights[l], (size_t)ci * 9 * c_out[l], "weight");
+        if (biases[l]) TP_NEED(biases[l], (size_t)c_out[l], "bias");
+        wp[l] = weights[l]->ptr;
+        bp[l] = biases[l] ? biases[l]->ptr : nullptr;
+        ci = c_out[l];
+    }
+    TP_NEED(mean, (size_t)n * ci, "mean");
+    if (cnt) TP_NEED(cnt, (size_t)n * ci, "cnt");
+    int rc = tp::conv_stack_fwd(ctx, x->ptr, n, c_in, h, w, n_layers, wp, bp, c_out, pool, relu, nullptr, mean->ptr, cnt ? cnt->ptr : nullptr);
+    if (rc == TP_ERR_UNSUPPORTED) tp::set_error("tp_conv_stack_gap_fwd: a layer's shape is outside the tensor-core stack (see tp_conv_stack_fwd)");
     return rc;
 }
 

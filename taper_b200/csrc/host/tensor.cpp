@@ -684,10 +684,6 @@ Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers, int gap) co
     }
     if (!h || !w) return Tensor();
     const size_t n = shape()[0];
-    Tensor out = Tensor::empty({n, c, h, w});
-    int rc = tp_conv_stack_fwd(ctx(), buf(), (int)n, (int)shape()[1], (int)shape()[2], (int)shape()[3], L, wb, bb, co, po, re, out.buf());
-    if (rc == TP_ERR_UNSUPPORTED) return Tensor();
-    check(rc);
     const ConvStackLayer& last = layers[L - 1];
     const bool bias_rg = last.bias && last.bias->needs_grad();
     const bool relu = last.relu;
@@ -703,7 +699,10 @@ Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers, int gap) co
         Tensor feat = Tensor::empty(gap == 2 ? Shape{n, c} : Shape{n, c, 1, 1});
         Tensor cnt;
         if (bias_rg && relu) cnt = Tensor::empty({n, c});
-        check(tp_gap_count_fwd(ctx(), out.buf(), feat.buf(), cnt.defined() ? cnt.buf() : nullptr, nn, cc, hw));
+        int rc = tp_conv_stack_gap_fwd(ctx(), buf(), nn, (int)shape()[1], (int)shape()[2], (int)shape()[3], L, wb, bb, co, po, re, feat.buf(),
+                                       cnt.defined() ? cnt.buf() : nullptr);
+        if (rc == TP_ERR_UNSUPPORTED) return Tensor();
+        check(rc);
         if (bias_rg) {
             feat.set_requires_grad(true);
             Tensor b = *last.bias;
@@ -717,6 +716,10 @@ Tensor Tensor::conv_stack(const std::vector<ConvStackLayer>& layers, int gap) co
         }
         return feat;
     }
+    Tensor out = Tensor::empty({n, c, h, w});
+    int rc = tp_conv_stack_fwd(ctx(), buf(), nn, (int)shape()[1], (int)shape()[2], (int)shape()[3], L, wb, bb, co, po, re, out.buf());
+    if (rc == TP_ERR_UNSUPPORTED) return Tensor();
+    check(rc);
     if (bias_rg) {
         out.set_requires_grad(true);
         Tensor b = *last.bias;

@@ -244,3 +244,84 @@ def test_example_cnn_step_fused_vs_per_layer_tape():
         assert (ga is None) == (gb is None), j
         if ga is not None:
             close(ga, gb, 1e-4, f"grad {j}")
+
+
+@pytest.mark.parametrize("n,cin,hw,cout,relu", [
+    (5, 32, 28, 32, 1),          # conv2 of the example model
+    (6, 32, 14, 64, 1),          # conv3: gradient planes of 64 channels, 32 output channels
+    (7, 64, 14, 64, 0),          # conv4, no ReLU
+    (9, 64, 7, 128, 1),          # conv5: two images per tile, 128-channel gradient (four channel blocks)
+    (300, 64, 14, 64, 1),        # several tiles per persistent CTA; dW accumulates over image chunks
+])
+def test_full_adjoint_input_gradient_on_the_conv_kernel_vs_oracle(ctx, n, cin, hw, cout, relu):
+    """tp_conv2d_bwd with dx / dw requested (full adjoint, the two tape links the reference drops): dX comes from the
+    implicit-GEMM kernel run on the masked gradient with mirrored, transposed weights (no [M, 9*C_in] matrix, no col2im); dW
+    from im2col chunks that accumulate.  Against the oracle's matmul backward through im2col (src/ops.rs:254-291)."""
+    from taper_b200 import ConvDesc
+    rng = np.random.default_rng(n * 131 + cin + cout + hw)
+    x = (rng.random((n, cin, hw, hw)) - 0.3).astype(F32)
+    wt = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(F32)
+    b = (rng.standard_normal(cout) * 0.05).astype(F32)
+    R.Config.strict_reference_conv = False
+    try:
+        R.Tape.reset()
+        X = R.Tensor.new(x, x.shape).requires_grad_()
+        _ = X.reshape(x.shape)
+        W = R.Tensor.new(wt, wt.shape).requires_grad_()
+        B = R.Tensor.new(b, b.shape).requires_grad_()
+        out = (X.conv2d_relu if relu else X.conv2d)(W, B, (1, 1), (1, 1), (1, 1))
+        gy = np.random.default_rng(7).standard_normal(out.data().size).astype(F32)
+        out._grad[0] = gy.copy()
+        R.tape_backward(len(R.Tape.nodes) - 1)
+        y_ref, dx_ref, dw_ref, db_ref = out.data().copy(), X.grad().copy(), W.grad().copy(), B.grad().copy()
+    finally:
+        R.Config.strict_reference_conv = True
+        R.Tape.reset()
+    d = ConvDesc(n, cin, hw, hw, cout, 3, 3, 1, 1, 1, 1, 1, 1)
+    xb, wb, Y, G = ctx.upload(x), ctx.upload(wt), ctx.upload(y_ref), ctx.upload(gy)
+    gx, gw, gb = ctx.alloc(x.size), ctx.alloc(wt.size), ctx.alloc(cout)
+    mem0 = ctx.launches()
+    ctx.call("conv2d_bwd", xb, wb, G, Y if relu else None, gx, gw, gb, d, 0, 0, 0)
+    close(gx.download(), dx_ref.reshape(-1), 1e-4, "dX")
+    close(gw.download(), dw_ref.reshape(-1), 1e-4, "dW")
+    close(gb.download(), db_ref.reshape(-1), 1e-4, "db")
+    ctx.call("conv2d_bwd", xb, wb, G, Y if relu else None, gx, gw, gb, d, 1, 1, 1)          # accumulate into live gradients
+    close(gx.download(), 2 * dx_ref.reshape(-1), 1e-4, "dX accumulated")
+    close(gw.download(), 2 * dw_ref.reshape(-1), 1e-4, "dW accumulated")
+    assert ctx.launches() > mem0
+
+
+@pytest.mark.parametrize("n,c0,hw,couts,pools", [
+    (5, 1, 28, [32, 32, 64, 64, 128], [0, 1, 0, 1, 0]),       # the example model: 7x7 last layer, pooled in the conv epilogue
+    (301, 64, 7, [128], [0]),                                   # several tiles per CTA, odd batch on two images per tile
+    (3, 32, 5, [64, 32], [0, 0]),                               # three 5x5 images per tile
+    (4, 32, 14, [64], [0]),                                     # 14x14: images span two tiles -> scratch NCHW + gap kernel
+    (6, 1, 28, [32, 64], [1, 1]),                               # pooled last layer -> scratch NCHW + gap kernel
+])
+def test_conv_stack_with_global_average_pool_vs_oracle(ctx, n, c0, hw, couts, pools):
+    """tp_conv_stack_gap_fwd: mean and positive-unit count of the last layer's planes against the oracle's conv chain followed by
+    avg_pool2d over the whole plane (src/nn.rs:670-686)."""
+    from taper_b200 import capi
+    lib = capi.lib
+    rng = np.random.default_rng(n + c0 + hw + len(couts))
+    x, ws, bs = make(rng, n, c0, hw, couts)
+    relus = [1] * len(couts)
+    ref = oracle_stack(x, ws, bs, pools, relus)                               # [n, C, h, w]
+    L = len(ws)
+    xb = ctx.upload(x)
+    wb = [ctx.upload(v) for v in ws]
+    bb = [ctx.upload(v) for v in bs]
+    mean, cnt = ctx.alloc(n * couts[-1]), ctx.alloc(n * couts[-1])
+    W = (C.c_void_p * L)(*[b.h for b in wb])
+    B = (C.c_void_p * L)(*[b.h for b in bb])
+    co = (C.c_int * L)(*couts)
+    po = (C.c_int * L)(*pools)
+    re = (C.c_int * L)(*relus)
+    capi.check(lib.tp_conv_stack_gap_fwd(ctx.h, xb.h, n, c0, hw, hw, L, W, B, co, po, re, mean.h, cnt.h))
+    flat = ref.reshape(n, couts[-1], -1)
+    close(mean.download().reshape(n, -1), flat.mean(axis=2), 1e-4, "pooled features")
+    got_cnt = cnt.download().reshape(n, -1)
+    ref_cnt = (flat > 0).sum(axis=2)
+    # a unit within the conv error of zero may land on either side of the ReLU
+    near = (np.abs(flat) <= 4e-5 * np.abs(flat).max()).sum(axis=2)
+    assert (np.abs(got_cnt - ref_cnt) <= near).all()
