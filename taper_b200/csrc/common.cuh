@@ -163,6 +163,10 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
 int conv_bx3_dx(tp_ctx* ctx, const float* gy, const float* relu_mask_y, const float* w2, float* dx, int N, int Cin, int H, int W,
                 int Cout, int accumulate);
 
+// weight gradient of a 3x3 / s1 / p1 convolution as an implicit GEMM over pixels (both operands MN-major planes, two taps per MMA)
+int conv_bx3_dw(tp_ctx* ctx, const float* x, const float* gy, const float* relu_mask_y, float* dw, int N, int Cin, int H, int W, int Cout,
+                int accumulate);
+
 // ---- bf16x3 tensor-core GEMM on pre-split operands (gemm_bx3.cu) -----------------------------------------------------
 // A "split" tensor holds an fp32 tensor of n elements as two bf16 planes: hi = rn_bf16(x) at [0, n) and
 // lo = rn_bf16(x - hi) `plane` elements further (plane >= n, multiple of 8).

@@ -376,6 +376,28 @@ int tp_conv2d_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* g
         if ((rc = tp_relu_bwd(ctx, relu_mask_y, gy, gmask.b, M * g.cout, 0))) return rc;
         gz = gmask.b;
     }
+    // ... and dW = im2col(x)^T . (gy * mask) as an implicit GEMM over pixels (conv_bx3.cu: conv_dw_kernel), bf16x3 mode
+    if (dw && g_conv_v2 && ctx->gemm_mode == 3 && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 && g.pw == 1 &&
+        g.dh == 1 && g.dw == 1) {
+        TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(dw, (size_t)g.K * g.cout, "dw");
+        rc = tp::conv_bx3_dw(ctx, x->ptr, gy->ptr, relu_mask_y ? relu_mask_y->ptr : nullptr, dw->ptr, g.n, g.c, g.h, g.w, g.cout, acc_dw);
+        if (rc == TP_OK) {
+            if (db) {                                           // the bias gradient no longer rides on the NHWC gradient matrix
+                TP_NEED(db, g.cout, "db");
+                const tp_buf* gzb = gy;
+                TmpBuf gm;
+                if (relu_mask_y) {
+                    if ((rc = tp_buf_alloc(ctx, M * g.cout, &gm.b))) return rc;
+                    if ((rc = tp_relu_bwd(ctx, relu_mask_y, gy, gm.b, M * g.cout, 0))) return rc;
+                    gzb = gm.b;
+                }
+                if ((rc = tp_bias_grad_4d(ctx, gzb, db, g.n, g.cout, hw, acc_db))) return rc;
+                db = nullptr;
+            }
+            dw = nullptr;
+        } else if (rc != TP_ERR_UNSUPPORTED) return rc;
+    }
+    if (!dw && !dx && !db) return TP_OK;
     TmpBuf g_nhwc;
     if (dw || dx) {
         if ((rc = tp_buf_alloc(ctx, M * g.cout, &g_nhwc.b))) return rc;

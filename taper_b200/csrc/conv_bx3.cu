@@ -494,6 +494,181 @@ conv3x3_bx3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
 }
 
+// ---- weight gradient of a 3x3 / s1 / p1 convolution as an implicit GEMM (full adjoint; north_star's X^T . dY on the conv path) ----
+//   dW[ci*9 + tap, co] = sum over output pixels r of  X[r shifted by tap, ci] * dZ[r, co]        (src/ops.rs:280-291 on the im2col matrix)
+// The contraction runs over PIXELS, and both operands already sit in shared memory pixel-major: a row of an activation patch is
+// [hi x32 | lo x32] of a 32-channel block — as an MN-major UMMA operand that is 64 "M" values per K index, and the same for the
+// gradient tile as the N operand.  One MMA of M = 128 (two taps side by side: the second 64-value chunk is another tap's
+// patch, LBO = the distance between the two starts), N = 64, K = 16 pixels therefore produces, for two taps at once, all four
+// hi / lo blocks of the bf16x3 product: [X_hi ; X_lo]^T . [dZ_hi | dZ_lo]; the epilogue adds hi*hi + hi*lo + lo*hi.
+// Patches come in the three x-shifted copies (x = -1, 0, +1) so that every tap offset is a whole number of swizzle atoms
+// (MN-major operands with atom-aligned starts are the layout gemm_bx3.cu's T,N GEMMs already use).  A CTA owns one (ci block,
+// co block) pair and a slice of the tiles, accumulates all of them in TMEM (5 tap pairs x 64 columns) and writes one partial
+// [9][32][32]; conv_dw_fold_kernel sums the partials in CTA order (deterministic) into dW.
+struct DwP {
+    int N, H, W, CBx, CBz;            // X: [N, H, W, 32*CBx] planes, dZ: [N, H, W, 32*CBz] planes
+    int Wp, R, Hp, G, row_blocks, tiles;
+    int patch_bytes, patch_alloc;     // one X patch: delivered / reserved bytes
+    int z_bytes;                      // dZ tile box bytes
+    int stage_bytes;                  // 3 X patches + 1 dZ tile
+    int slices;                       // CTAs per (ci block, co block) pair
+    float* partial;                   // [pair][slice][9][32][32]
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z, const __grid_constant__ DwP p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kStages = 2;
+    uint64_t* full = (uint64_t*)(smem + kStages * p.stage_bytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* done = empty + kStages;
+    uint32_t* tmem_slot = (uint32_t*)(done + 1);
+    constexpr uint32_t kTmemCols = 512;                       // 5 tap pairs x 64 columns
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.y, cbx = pair / p.CBz, cbz = pair - cbx * p.CBz;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_z);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // rows of a stage that no TMA box covers are still read by the 128-row MMAs (they meet zero gradient rows or belong to pad
+    // positions): they must hold finite values
+    for (int i = threadIdx.x; i < kStages * p.stage_bytes / 16; i += 192) ((uint4*)smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_launch_dependents();
+    const int my_tiles = ((int)p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (warp == 0) {
+        if (lane == 0) {
+            int i = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++i) {
+                const int ng = tile / p.row_blocks, rb = tile - ng * p.row_blocks;
+                const int n0 = ng * p.G, y0 = rb * p.R;
+                const int s = i % kStages;
+                mbar_wait(empty + s, ((i / kStages) & 1) ^ 1);
+                uint8_t* st = smem + s * p.stage_bytes;
+                mbar_expect_tx(full + s, 3 * p.patch_bytes + p.z_bytes);
+                for (int kc = 0; kc < 3; ++kc) tma_load_5d(st + kc * p.patch_alloc, &map_x, full + s, 0, cbx, kc - 1, y0 - 1, n0);
+                tma_load_5d(st + 3 * p.patch_alloc, &map_z, full + s, 0, cbz, 0, y0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A / B = BF16, both MN-major (bits 15, 16), N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // tap pairs (first chunk, second chunk) as (kc, kr): horizontal neighbours share a row offset, the x = +1 column pairs up
+            // vertically; the ninth tap is paired with itself (its second half is ignored)
+            const int pa_kc[5] = {0, 0, 0, 2, 2}, pa_kr[5] = {0, 1, 2, 0, 2};
+            const int pb_kc[5] = {1, 1, 1, 2, 2}, pb_kr[5] = {0, 1, 2, 1, 2};
+            uint32_t a_off[5], a_lbo[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int oa = pa_kc[q] * p.patch_alloc + pa_kr[q] * p.Wp * 128, ob = pb_kc[q] * p.patch_alloc + pb_kr[q] * p.Wp * 128;
+                a_off[q] = (uint32_t)oa >> 4;
+                a_lbo[q] = (uint32_t)((ob > oa ? ob - oa : 1024) >> 4) << 16;
+            }
+            int i = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++i) {
+                const int s = i % kStages;
+                mbar_wait(full + s, (i / kStages) & 1);
+                tc_fence_after();
+                const uint32_t x_lo = smem_u32(smem + s * p.stage_bytes) >> 4;
+                const uint32_t z_lo = ((smem_u32(smem + s * p.stage_bytes + 3 * p.patch_alloc)) >> 4) | 0x10000u;
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ++ks) {               // 16 pixels (tile rows) per step: 2048 bytes further in both operands
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        mma_bf16_w(tmem_base + q * 64, (x_lo + a_off[q] + ks * 128) | a_lbo[q], kDescHi, z_lo + ks * 128, kDescHi, idesc,
+                                   (i == 0 && ks == 0) ? 0u : 1u);
+                }
+                tc_commit(empty + s);
+            }
+            tc_commit(done);
+        }
+    }
+    // ===== epilogue (warps 2-5, once): fold hi / lo blocks of the five accumulators into the partial [9][32][32] =====
+    if (warp >= 2) {
+        const int q4 = warp & 3, row = q4 * 32 + lane;        // TMEM lane = M index: [tap A: hi 0-31, lo 32-63 | tap B: hi 64-95, lo 96-127]
+        float* stg = (float*)smem;                              // the pipeline stages are idle by now: [128 rows][33] floats
+        if (my_tiles > 0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+        }
+        float* out = p.partial + ((size_t)pair * gridDim.x + blockIdx.x) * (9 * 32 * 32);
+        const int tap_of[5][2] = {{0, 1}, {3, 4}, {6, 7}, {2, 5}, {8, -1}};    // tap = kr*3 + kc of (chunk A, chunk B) per pair
+        for (int q = 0; q < 5; ++q) {
+            float v[32];
+            if (my_tiles > 0) {
+                uint32_t u[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + q * 64;
+                float a[64];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    tmem_ld16(taddr + c0, u);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a[c0 + j] = __uint_as_float(u[j]);
+                }
+                // hi rows (q4 even) contribute hi*hi + hi*lo, lo rows (q4 odd) lo*hi
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (q4 & 1) ? a[j] : a[j] + a[32 + j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stg[row * 33 + j] = v[j];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // thread t: channel ci = t % 32 of chunk t / 64 ... two passes over (chunk, ci) x 32 co
+            const int t = threadIdx.x - 64;
+            for (int e = t; e < 2 * 32 * 32; e += 128) {
+                const int chunk = e >> 10, ci = (e >> 5) & 31, co = e & 31;
+                const int tap = tap_of[q][chunk];
+                if (tap < 0) continue;
+                out[(tap * 32 + ci) * 32 + co] = stg[(chunk * 64 + ci) * 33 + co] + stg[(chunk * 64 + 32 + ci) * 33 + co];
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// dW[(cbx*32 + ci)*9 + tap][cbz*32 + co] (+)= sum over slices of partial[pair][slice][tap][ci][co], slices in order
+__global__ void __launch_bounds__(256)
+conv_dw_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw, int CBx, int CBz, int slices, int Cout, int accumulate) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int total = CBx * CBz * 9 * 32 * 32;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const int co = e & 31, ci = (e >> 5) & 31;
+        const int t = e >> 10, tap = t % 9, pair = t / 9;
+        const int cbx = pair / CBz, cbz = pair - cbx * CBz;
+        const float* src = partial + (size_t)pair * slices * 9216 + (tap * 32 + ci) * 32 + co;
+        float s = 0.0f;
+        for (int k = 0; k < slices; ++k) s += src[(size_t)k * 9216];
+        float* d = dw + (size_t)((cbx * 32 + ci) * 9 + tap) * Cout + cbz * 32 + co;
+        *d = accumulate ? *d + s : s;
+    }
+}
+
 // ---- weights [K = ci*9 + tap, C_out] fp32 -> the kernel's B operand:
 //   [ci/32][tap pair p = tap/2 (5 pairs, the tenth tap is zero)][row r < 2*C_out][64 bf16 = tap 2p: 32 channels | tap 2p+1: 32 channels]
 //   rows r < C_out hold hi = rn_bf16(w) of output channel r, rows r >= C_out hold lo = rn_bf16(w - hi) of channel r - C_out
@@ -1070,6 +1245,64 @@ int conv_bx3_dx(tp_ctx* ctx, const float* gy, const float* relu_mask_y, const fl
     if (!make_map_x(enc, &mx, (const uint16_t*)planes.b->ptr, p)) { set_error("conv_bx3_dx: cuTensorMapEncodeTiled (gradient planes) failed"); return TP_ERR_CUDA; }
     if (!make_map_w(enc, &mw, (const uint16_t*)wplanes.b->ptr, p.CB, p.Cout)) { set_error("conv_bx3_dx: cuTensorMapEncodeTiled (weights) failed"); return TP_ERR_CUDA; }
     return launch_conv_any(ctx, mx, mw, p, smem, true);
+}
+
+// Weight gradient of a 3x3 / s1 / p1 convolution as an implicit GEMM over pixels (conv_dw_kernel above): x NCHW [N, Cin, H, W],
+// gy / relu_mask_y NCHW [N, Cout, H, W], dw [Cin*9, Cout] (the reference's [K, C_out] view), overwritten or accumulated.
+int conv_bx3_dw(tp_ctx* ctx, const float* x, const float* gy, const float* relu_mask_y, float* dw, int N, int Cin, int H, int W, int Cout,
+                int accumulate) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TP_ERR_UNSUPPORTED;
+    if (Cin % 32 || Cout % 32 || Cin <= 0 || Cout <= 0 || W >= 32) return TP_ERR_UNSUPPORTED;
+    if ((size_t)N * H * W * (size_t)(Cin > Cout ? Cin : Cout) >= ((size_t)1 << 31)) return TP_ERR_UNSUPPORTED;
+    cudaSetDevice(ctx->device);
+    ConvP g;
+    int unused;
+    if (!plan_layer(N, H, W, Cin, 32, false, 0, /*three aligned patches*/ 0, &g, &unused)) return TP_ERR_UNSUPPORTED;
+    DwP p{};
+    p.N = N; p.H = H; p.W = W; p.CBx = Cin / 32; p.CBz = Cout / 32;
+    p.Wp = g.Wp; p.R = g.R; p.Hp = g.Hp; p.G = g.G; p.row_blocks = g.row_blocks; p.tiles = g.tiles;
+    p.patch_bytes = g.patch_bytes; p.patch_alloc = g.patch_alloc;
+    const int hz = g.G > 1 ? g.Hp : g.R;                        // gradient tile rows per image: the patch's image pitch, no halo
+    p.z_bytes = g.G * hz * g.Wp * 128;
+    const int z_alloc = ((p.z_bytes > 128 * 128 ? p.z_bytes : 128 * 128) + 1023) / 1024 * 1024;
+    p.stage_bytes = 3 * p.patch_alloc + z_alloc;
+    const int smem = 2 * p.stage_bytes + 1024 + 256;
+    if (smem > 227 * 1024) return TP_ERR_UNSUPPORTED;
+    const int pairs = p.CBx * p.CBz;
+    int slices = ctx->sm_count / pairs;
+    if (slices < 1) slices = 1;
+    if (slices > p.tiles) slices = p.tiles;
+    p.slices = slices;
+    int rc;
+    TmpBuf xpl, zpl, part;
+    if ((rc = tp_buf_alloc(ctx, (size_t)N * H * W * Cin, &xpl.b))) return rc;
+    if ((rc = tp_buf_alloc(ctx, (size_t)N * H * W * Cout, &zpl.b))) return rc;
+    if ((rc = tp_buf_alloc(ctx, (size_t)pairs * slices * 9216, &part.b))) return rc;
+    p.partial = part.b->ptr;
+    size_t items = (size_t)N * H * W * (Cin / 8);
+    if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, false, x, (const float*)nullptr,
+                         (uint16_t*)xpl.b->ptr, N, Cin, H, W)))
+        return rc;
+    items = (size_t)N * H * W * (Cout / 8);
+    if ((rc = launch_pdl(ctx, nchw_to_planes_kernel, dim3(grid_for(ctx, items, 256, 8)), dim3(256), 0, true, gy, relu_mask_y,
+                         (uint16_t*)zpl.b->ptr, N, Cout, H, W)))
+        return rc;
+    CUtensorMap mx, mz;
+    if (!make_map_x(enc, &mx, (const uint16_t*)xpl.b->ptr, g)) { set_error("conv_bx3_dw: cuTensorMapEncodeTiled (activation planes) failed"); return TP_ERR_CUDA; }
+    ConvP gz = g;
+    gz.CB = p.CBz;
+    gz.Hp = hz;
+    if (!make_map_x(enc, &mz, (const uint16_t*)zpl.b->ptr, gz)) { set_error("conv_bx3_dw: cuTensorMapEncodeTiled (gradient planes) failed"); return TP_ERR_CUDA; }
+    static int attr_smem[16] = {};
+    const int dev = ctx->device < 16 ? ctx->device : 15;
+    if (ctx->device >= 16 || attr_smem[dev] < smem) {
+        TP_CUDA(cudaFuncSetAttribute(conv_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem[dev] = smem;
+    }
+    if ((rc = launch_pdl(ctx, conv_dw_kernel, dim3(slices, pairs), dim3(192), (size_t)smem, true, mx, mz, p))) return rc;
+    return launch_pdl(ctx, conv_dw_fold_kernel, dim3(grid_for(ctx, (size_t)pairs * 9216, 256, 4)), dim3(256), 0, true, (const float*)part.b->ptr, dw,
+                      p.CBx, p.CBz, slices, Cout, accumulate ? 1 : 0);
 }
 
 }  // namespace tp

@@ -253,10 +253,12 @@ def test_example_cnn_step_fused_vs_per_layer_tape():
     (9, 64, 7, 128, 1),          # conv5: two images per tile, 128-channel gradient (four channel blocks)
     (300, 64, 14, 64, 1),        # several tiles per persistent CTA; dW accumulates over image chunks
 ])
-def test_full_adjoint_input_gradient_on_the_conv_kernel_vs_oracle(ctx, n, cin, hw, cout, relu):
+@pytest.mark.parametrize("mode", [1, 3])
+def test_full_adjoint_input_gradient_on_the_conv_kernel_vs_oracle(ctx, mode, n, cin, hw, cout, relu):
     """tp_conv2d_bwd with dx / dw requested (full adjoint, the two tape links the reference drops): dX comes from the
     implicit-GEMM kernel run on the masked gradient with mirrored, transposed weights (no [M, 9*C_in] matrix, no col2im); dW
-    from im2col chunks that accumulate.  Against the oracle's matmul backward through im2col (src/ops.rs:254-291)."""
+    from im2col chunks that accumulate (gemm_mode 1) or, in bf16x3 mode (3), from the implicit GEMM over pixels (conv_dw_kernel:
+    MN-major planes, two taps per MMA).  Against the oracle's matmul backward through im2col (src/ops.rs:254-291)."""
     from taper_b200 import ConvDesc
     rng = np.random.default_rng(n * 131 + cin + cout + hw)
     x = (rng.random((n, cin, hw, hw)) - 0.3).astype(F32)
@@ -281,6 +283,7 @@ def test_full_adjoint_input_gradient_on_the_conv_kernel_vs_oracle(ctx, n, cin, h
     xb, wb, Y, G = ctx.upload(x), ctx.upload(wt), ctx.upload(y_ref), ctx.upload(gy)
     gx, gw, gb = ctx.alloc(x.size), ctx.alloc(wt.size), ctx.alloc(cout)
     mem0 = ctx.launches()
+    ctx.call("set_gemm_mode", mode)
     ctx.call("conv2d_bwd", xb, wb, G, Y if relu else None, gx, gw, gb, d, 0, 0, 0)
     close(gx.download(), dx_ref.reshape(-1), 1e-4, "dX")
     close(gw.download(), dw_ref.reshape(-1), 1e-4, "dW")
