@@ -222,7 +222,9 @@ int tp_conv2d_fwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp
 /* gy is the gradient w.r.t. the conv output (after undoing ReLU if fused: pass relu_mask_y).
  *   db[co]   (+)= sum_{n,oh,ow} gy                       add_bias_4d backward  src/tensor.rs:2003-2027
  *   dw[K,Co] (+)= col^T * gy_nhwc ;  dx (+)= col2im(gy_nhwc * w^T)   (full adjoint; NULL to skip —
- *   the reference computes neither, Appendix A1) */
+ *   the reference computes neither, Appendix A1).  For 3x3 / s1 / p1 layers with channel counts that are multiples of 32 both
+ *   run as implicit GEMMs on the tensor cores (dx: the forward kernel on the masked gradient with mirrored, transposed
+ *   weights; dw: a contraction over pixels on MN-major bf16 hi/lo planes) — neither the im2col matrix nor its gradient exists */
 int tp_conv2d_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* gy, const tp_buf* relu_mask_y,
                   tp_buf* dx, tp_buf* dw, tp_buf* db, const tp_conv_desc* d,
                   int acc_dx, int acc_dw, int acc_db);

@@ -376,8 +376,8 @@ int tp_conv2d_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* g
         if ((rc = tp_relu_bwd(ctx, relu_mask_y, gy, gmask.b, M * g.cout, 0))) return rc;
         gz = gmask.b;
     }
-    // ... and dW = im2col(x)^T . (gy * mask) as an implicit GEMM over pixels (conv_bx3.cu: conv_dw_kernel), bf16x3 mode
-    if (dw && g_conv_v2 && ctx->gemm_mode == 3 && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 && g.pw == 1 &&
+    // ... and dW = im2col(x)^T . (gy * mask) as an implicit GEMM over pixels (conv_bx3.cu: conv_dw_kernel)
+    if (dw && g_conv_v2 && ctx->gemm_mode != 0 && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 && g.pw == 1 &&
         g.dh == 1 && g.dw == 1) {
         TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(dw, (size_t)g.K * g.cout, "dw");
         rc = tp::conv_bx3_dw(ctx, x->ptr, gy->ptr, relu_mask_y ? relu_mask_y->ptr : nullptr, dw->ptr, g.n, g.c, g.h, g.w, g.cout, acc_dw);

@@ -257,8 +257,8 @@ def test_example_cnn_step_fused_vs_per_layer_tape():
 def test_full_adjoint_input_gradient_on_the_conv_kernel_vs_oracle(ctx, mode, n, cin, hw, cout, relu):
     """tp_conv2d_bwd with dx / dw requested (full adjoint, the two tape links the reference drops): dX comes from the
     implicit-GEMM kernel run on the masked gradient with mirrored, transposed weights (no [M, 9*C_in] matrix, no col2im); dW
-    from im2col chunks that accumulate (gemm_mode 1) or, in bf16x3 mode (3), from the implicit GEMM over pixels (conv_dw_kernel:
-    MN-major planes, two taps per MMA).  Against the oracle's matmul backward through im2col (src/ops.rs:254-291)."""
+    from the implicit GEMM over pixels (conv_dw_kernel: MN-major planes, two taps per MMA) in both tensor-core modes.  Against the
+    oracle's matmul backward through im2col (src/ops.rs:254-291)."""
     from taper_b200 import ConvDesc
     rng = np.random.default_rng(n * 131 + cin + cout + hw)
     x = (rng.random((n, cin, hw, hw)) - 0.3).astype(F32)
