@@ -228,6 +228,19 @@ int tp_conv2d_fwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* b, tp
 int tp_conv2d_bwd(tp_ctx*, const tp_buf* x, const tp_buf* w, const tp_buf* gy, const tp_buf* relu_mask_y,
                   tp_buf* dx, tp_buf* dw, tp_buf* db, const tp_conv_desc* d,
                   int acc_dx, int acc_dw, int acc_db);
+/* A chain of n_layers (<= 4) small Linear(+ReLU) layers — every width dims[l] <= 128, dims has n_layers + 1 entries — as one
+ * forward and one backward launch (+ a deterministic fold of per-CTA partials): exact fp32 FFMA with all weights in shared
+ * memory.  Replaces, per layer, Linear::forward (src/nn.rs:54-60: transpose src/tensor.rs:544-591, matmul src/ops.rs:200-228,
+ * add_broadcast src/tensor.rs:636-704), ReLU (src/ops.rs:312-374) and their backward closures (src/ops.rs:254-291, 358-370,
+ * src/tensor.rs:680-691) for classifier heads like the example CNN's 128-128-64-10 (examples/train_mnist_cnn.rs:80-100).
+ *   fwd: acts[l] [batch, dims[l+1]] = relu?(in_l . W_l^T + b_l), in_0 = x, in_l = acts[l-1]; weights[l] is [dims[l+1], dims[l]].
+ *   bwd: gout = gradient of acts[n_layers-1]; dw[l] / db[l] / dx (each may be NULL) are stored (acc 0) or added to (acc 1). */
+int tp_mlp_small_supported(int n_layers, const int* dims, int batch);
+int tp_mlp_small_fwd(tp_ctx*, const tp_buf* x, int n_layers, const int* dims, const tp_buf* const* weights,
+                     const tp_buf* const* biases, const int* relu, tp_buf* const* acts, int batch);
+int tp_mlp_small_bwd(tp_ctx*, const tp_buf* x, int n_layers, const int* dims, const tp_buf* const* weights, const int* relu,
+                     const tp_buf* const* acts, const tp_buf* gout, tp_buf* dx, tp_buf* const* dw, tp_buf* const* db,
+                     int acc_dx, const int* acc_dw, const int* acc_db, int batch);
 /* A stack of n_layers (<= 8) 3x3 / stride 1 / pad 1 convolutions, each + bias (+ ReLU when relu[l]) and, when pool[l],
  * followed by a 2x2 / stride 2 max-pool, evaluated back to back:  x [N, C_in, H, W] fp32 NCHW -> y NCHW fp32 (the last
  * layer's output, pooled if pool[last]).  Replaces the chain conv2d_relu -> max_pool2d -> conv2d_relu ... that

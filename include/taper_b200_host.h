@@ -37,6 +37,9 @@ int tp_host_config(int conv_full_adjoint, int fuse_linear_relu, int reference_op
  * (strict-reference conv autograd only: nothing but the chain's last output is read again); 0 = layer by layer,
  * as Sequential::forward does in the reference (src/nn.rs:149-151) */
 int tp_host_config_conv_stack(int fuse_conv_stack);
+/* 1 (default) = Sequential runs a chain of >= 2 Linear(+ReLU) layers of width <= 128 as one forward / one backward launch
+ * (tp_mlp_small_*); 0 = one fused Linear launch per layer */
+int tp_host_config_small_mlp(int fuse_small_mlp);
 
 /* Sequential from a comma-separated layer list (the constructors of src/nn.rs, src/activation.rs):
  *   linear:IN:OUT[:nobias] | relu | sigmoid | conv:CIN:COUT:K:STRIDE:PAD | conv_relu:CIN:COUT:K:STRIDE:PAD |

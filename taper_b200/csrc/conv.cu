@@ -221,6 +221,70 @@ nchw_to_nhwc_mask_kernel(const float* __restrict__ gy, const float* __restrict__
     }
 }
 
+
+// ---- weight gradient of a 3x3 / s1 / p1 convolution with a tiny contraction per output (C_in * 9 <= 36: the image layer) --------
+//   dW[ci*9 + tap, co] = sum_{n,y,x} X[n, ci, y + kr - 1, x + kc - 1] * gy[n, co, y, x] * [mask > 0]      (src/ops.rs:280-291 on im2col)
+// A 9 x 32 output over 200 000+ pixels is a reduction, not a GEMM: warp w owns four output channels, lanes walk the pixels of the
+// CTA's images (coalesced along x for gy, the mask and the input window), 36 accumulators per lane, one shuffle tree per CTA;
+// partials [split][K][Cout] are folded in split order (deterministic).
+__global__ void __launch_bounds__(kThreads)
+conv_dw_smallk_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ mask, float* __restrict__ partial,
+                      int N, int Cin, int H, int W, int Cout, int n_per_split) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * n_per_split, n1 = min(N, n0 + n_per_split);
+    const int hw = H * W;
+    const int K = Cin * 9;
+    for (int cg = warp; cg * 4 < Cout; cg += kThreads / 32) {
+        for (int ci = 0; ci < Cin; ++ci) {
+            float acc[4][9];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc[j][t] = 0.0f;
+            for (int n = n0; n < n1; ++n) {
+                const float* xp = x + ((size_t)n * Cin + ci) * hw;
+                for (int p = lane; p < hw; p += 32) {
+                    const int y = p / W, xx = p - y * W;
+                    float in[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+                        in[t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + iy * W + ix) : 0.0f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int co = cg * 4 + j;
+                        if (co < Cout) {
+                            const size_t gi = ((size_t)n * Cout + co) * hw + p;
+                            float g = __ldg(gy + gi);
+                            if (mask) g = __ldg(mask + gi) > 0.0f ? g : 0.0f;
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) acc[j][t] = fmaf(in[t], g, acc[j][t]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    float v = acc[j][t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && cg * 4 + j < Cout) partial[((size_t)blockIdx.x * K + ci * 9 + t) * Cout + cg * 4 + j] = v;
+                }
+        }
+    }
+}
+__global__ void __launch_bounds__(kThreads)
+conv_dw_smallk_fold(const float* __restrict__ partial, float* __restrict__ dw, int count, int splits, int accumulate) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.0f;
+    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * count + i];
+    dw[i] = accumulate ? dw[i] + s : s;
+}
+
 int make_geom(const tp_conv_desc* d, ConvGeom* g, const char* fn) {
     TP_CHECK_ARG(d, "%s: NULL descriptor", fn);
     TP_CHECK_ARG(d->n >= 0 && d->c_in > 0 && d->h > 0 && d->w > 0 && d->c_out > 0 && d->kh > 0 && d->kw > 0 &&
@@ -375,6 +439,34 @@ int tp_conv2d_bwd(tp_ctx* ctx, const tp_buf* x, const tp_buf* w, const tp_buf* g
         if ((rc = tp_buf_alloc(ctx, M * g.cout, &gmask.b))) return rc;
         if ((rc = tp_relu_bwd(ctx, relu_mask_y, gy, gmask.b, M * g.cout, 0))) return rc;
         gz = gmask.b;
+    }
+    // the image layer (C_in * 9 <= 36): dW is a [K, Cout] reduction over the pixels, done directly (no im2col, no GEMM)
+    if (dw && g.K <= 36 && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 && g.pw == 1 && g.dh == 1 && g.dw == 1) {
+        TP_NEED(x, (size_t)g.n * g.c * g.h * g.w, "x"); TP_NEED(dw, (size_t)g.K * g.cout, "dw");
+        int splits = ctx->sm_count * 2 < g.n ? ctx->sm_count * 2 : g.n;
+        const int nps = (g.n + splits - 1) / splits;
+        splits = (g.n + nps - 1) / nps;
+        TmpBuf part;
+        if ((rc = tp_buf_alloc(ctx, (size_t)splits * g.K * g.cout, &part.b))) return rc;
+        conv_dw_smallk_kernel<<<splits, kThreads, 0, ctx->stream>>>(x->ptr, gy->ptr, relu_mask_y ? relu_mask_y->ptr : nullptr, part.b->ptr,
+                                                                   g.n, g.c, g.h, g.w, g.cout, nps);
+        TP_LAUNCH_OK(ctx);
+        conv_dw_smallk_fold<<<(g.K * g.cout + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(part.b->ptr, dw->ptr, g.K * g.cout, splits,
+                                                                                               acc_dw);
+        TP_LAUNCH_OK(ctx);
+        if (db) {
+            TP_NEED(db, g.cout, "db");
+            const tp_buf* gzb = gy;
+            TmpBuf gm;
+            if (relu_mask_y) {
+                if ((rc = tp_buf_alloc(ctx, M * g.cout, &gm.b))) return rc;
+                if ((rc = tp_relu_bwd(ctx, relu_mask_y, gy, gm.b, M * g.cout, 0))) return rc;
+                gzb = gm.b;
+            }
+            if ((rc = tp_bias_grad_4d(ctx, gzb, db, g.n, g.cout, hw, acc_db))) return rc;
+            db = nullptr;
+        }
+        dw = nullptr;
     }
     // ... and dW = im2col(x)^T . (gy * mask) as an implicit GEMM over pixels (conv_bx3.cu: conv_dw_kernel)
     if (dw && g_conv_v2 && ctx->gemm_mode != 0 && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.ph == 1 && g.pw == 1 &&

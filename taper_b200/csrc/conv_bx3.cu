@@ -112,16 +112,22 @@ __device__ __forceinline__ void mma_bf16_w(uint32_t tmem_d, uint32_t alo, uint32
         : "memory");
 }
 
+// two floats -> packed bf16x2 (one cvt.rn.bf16x2.f32), low half = a
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
 }
-// 8 values -> 16 bytes of hi and 16 bytes of lo
+// 8 values -> 16 bytes of hi = rn_bf16(v) and 16 bytes of lo = rn_bf16(v - hi); bf16 -> fp32 is a 16-bit shift
 __device__ __forceinline__ void split8(const float* v, uint4* hi, uint4* lo) {
-    float r[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-    *hi = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    *lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+    for (int j = 0; j < 4; ++j) {
+        h[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+        const float r0 = v[2 * j] - __uint_as_float(h[j] << 16), r1 = v[2 * j + 1] - __uint_as_float(h[j] & 0xffff0000u);
+        l[j] = pack_bf16(r0, r1);
+    }
+    *hi = make_uint4(h[0], h[1], h[2], h[3]);
+    *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving: after the exchange with lane ^ 16 a
@@ -768,13 +774,21 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
             // first multiply, instead of one round trip per tap
             const float* xp = x + ((size_t)n * Cin + ci) * (size_t)H * W;
             float in[win * win];
+            if (y0 >= 0 && x0 >= 0 && y0 + win <= H && x0 + win <= W) {            // interior window: no bounds checks
+                const float* wp0 = xp + y0 * W + x0;
 #pragma unroll
-            for (int r = 0; r < win; ++r)
+                for (int r = 0; r < win; ++r)
 #pragma unroll
-                for (int c = 0; c < win; ++c) {
-                    const int iy = y0 + r, ix = x0 + c;
-                    in[r * win + c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + (size_t)iy * W + ix) : 0.0f;
-                }
+                    for (int c = 0; c < win; ++c) in[r * win + c] = __ldg(wp0 + r * W + c);
+            } else {
+#pragma unroll
+                for (int r = 0; r < win; ++r)
+#pragma unroll
+                    for (int c = 0; c < win; ++c) {
+                        const int iy = y0 + r, ix = x0 + c;
+                        in[r * win + c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + iy * W + ix) : 0.0f;
+                    }
+            }
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const float4 wa = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8);

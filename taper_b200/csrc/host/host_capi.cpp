@@ -92,6 +92,10 @@ int tp_host_config_conv_stack(int fuse_conv_stack) {
     return guarded([&] { Config::fuse_conv_stack() = fuse_conv_stack != 0; });
 }
 
+int tp_host_config_small_mlp(int fuse_small_mlp) {
+    return guarded([&] { Config::fuse_small_mlp() = fuse_small_mlp != 0; });
+}
+
 int tp_model_create(const char* spec, uint64_t seed, tp_model** out) {
     return guarded([&] {
         if (!spec || !out) panic("tp_model_create: NULL argument");

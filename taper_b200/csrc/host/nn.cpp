@@ -117,6 +117,34 @@ Tensor Sequential::forward(const Tensor& input) const {                         
                 }
             }
         }
+        if (fuse && Config::fuse_small_mlp() && x.shape().size() == 2) {
+            // peephole: [Linear (+ ReLU)]{2,4} with every width <= 128 -> one forward / one backward launch (tp_mlp_small_*)
+            std::vector<MlpLayer> run;
+            size_t j = i;
+            size_t width = x.shape()[1];
+            while (j < layers.size() && run.size() < 4) {
+                auto* lin = dynamic_cast<const Linear*>(layers[j].get());
+                if (!lin || width > 128 || lin->weight.shape()[0] > 128 || lin->weight.shape()[1] != width) break;
+                MlpLayer ly;
+                ly.weight = lin->weight;
+                ly.bias = lin->bias;
+                ++j;
+                if (j < layers.size() && dynamic_cast<const ReLU*>(layers[j].get())) {
+                    ly.relu = true;
+                    ++j;
+                }
+                width = lin->weight.shape()[0];
+                run.push_back(ly);
+            }
+            if (run.size() >= 2) {
+                Tensor y = x.mlp_chain(run);
+                if (y.defined()) {
+                    x = y;
+                    i = j - 1;
+                    continue;
+                }
+            }
+        }
         if (fuse && i + 1 < layers.size()) {
             // peephole: Linear followed by ReLU -> bias + ReLU in the GEMM epilogue, mask folded into backward
             auto* lin = dynamic_cast<const Linear*>(layers[i].get());

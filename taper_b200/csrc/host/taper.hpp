@@ -44,11 +44,15 @@ struct Config {
     // layers, pooling in the conv epilogue).  Only under the strict-reference conv autograd (A1), where nothing but the
     // stack's last output is ever read again; off under reference_op_sequence.  Same numbers within the bf16x3 bound.
     static bool& fuse_conv_stack();
+    // Sequential peephole: a run of >= 2 Linear(+ReLU) layers whose widths are all <= 128 (a classifier head) runs as one
+    // forward and one backward launch of exact fp32 FFMA kernels (tp_mlp_small_*) instead of one tensor-core launch per product.
+    static bool& fuse_small_mlp();
 };
 
 struct TensorImpl;
 
 struct ConvStackLayer;
+struct MlpLayer;
 
 // ---- Tensor  (src/tensor.rs:236-244, 469-541) -----------------------------------------------------
 class Tensor {
@@ -111,6 +115,8 @@ public:
     // Returns an undefined Tensor when the shapes are outside the fused kernels (the caller runs the layers one by one).
     // gap: 0 = the stack's NCHW output; 1 = followed by a global average pool -> [N, C, 1, 1]; 2 = and Flatten(1) -> [N, C]
     Tensor conv_stack(const std::vector<ConvStackLayer>& layers, int gap = 0) const;
+    // a chain of small Linear(+ReLU) layers as one node (Config::fuse_small_mlp); undefined Tensor when the widths do not qualify
+    Tensor mlp_chain(const std::vector<MlpLayer>& layers) const;
 
 private:
     Tensor conv2d_impl(const Tensor& weight, const Tensor* bias, Pair stride, Pair padding, Pair dilation, bool relu) const;
@@ -123,6 +129,12 @@ struct ConvStackLayer {           // one layer of Tensor::conv_stack: conv 3x3 /
     Tensor weight;
     std::optional<Tensor> bias;
     bool relu = true, pool = false;
+};
+
+struct MlpLayer {                 // one layer of Tensor::mlp_chain: x . W^T + b (+ ReLU)
+    Tensor weight;
+    std::optional<Tensor> bias;
+    bool relu = false;
 };
 
 Tensor operator+(const Tensor& a, const Tensor& b);     // src/ops.rs:8-52

@@ -51,6 +51,7 @@ void synchronize() { check(tp_sync(ctx())); }
 bool& Config::conv_full_adjoint() { static thread_local bool v = false; return v; }
 bool& Config::fuse_linear_relu() { static thread_local bool v = true; return v; }
 bool& Config::fuse_conv_stack() { static thread_local bool v = true; return v; }
+bool& Config::fuse_small_mlp() { static thread_local bool v = true; return v; }
 bool& Config::reference_op_sequence() { static thread_local bool v = false; return v; }
 
 // ---- TensorImpl -----------------------------------------------------------------------------------
@@ -602,6 +603,64 @@ Tensor Tensor::linear(const Tensor& weight, const Tensor* bias, bool relu) const
             tp_buf* gw = w.needs_grad() ? w.impl()->grad_for_write(&aw) : nullptr;
             tp_buf* gb = (b && b->needs_grad()) ? b->impl()->grad_for_write(&ab) : nullptr;
             check(tp_linear_bwd(ctx(), x.buf(), w.buf(), g, relu ? out.buf() : nullptr, gx, gw, gb, batch, fin, fout, ax, aw, ab));
+        });
+    }
+    return out;
+}
+
+// ---- a chain of small Linear(+ReLU) layers as one node (tp_mlp_small_fwd / bwd) ---------------------------------------------
+Tensor Tensor::mlp_chain(const std::vector<MlpLayer>& layers) const {
+    const int L = (int)layers.size();
+    if (shape().size() != 2 || L < 1 || L > 4) return Tensor();
+    const int batch = (int)shape()[0];
+    int dims[5];
+    dims[0] = (int)shape()[1];
+    for (int l = 0; l < L; ++l) {
+        const Tensor& w = layers[l].weight;
+        if (w.shape().size() != 2 || (int)w.shape()[1] != dims[l]) return Tensor();
+        if (layers[l].bias && (layers[l].bias->shape().size() != 1 || layers[l].bias->shape()[0] != w.shape()[0])) return Tensor();
+        dims[l + 1] = (int)w.shape()[0];
+    }
+    if (!tp_mlp_small_supported(L, dims, batch)) return Tensor();
+    const tp_buf* wb[4];
+    const tp_buf* bb[4];
+    tp_buf* ab[4];
+    int re[4];
+    std::vector<Tensor> acts;
+    bool any = needs_grad();
+    for (int l = 0; l < L; ++l) {
+        acts.push_back(Tensor::empty({(size_t)batch, (size_t)dims[l + 1]}));
+        wb[l] = layers[l].weight.buf();
+        bb[l] = layers[l].bias ? layers[l].bias->buf() : nullptr;
+        ab[l] = acts[l].buf();
+        re[l] = layers[l].relu ? 1 : 0;
+        any = any || layers[l].weight.needs_grad() || (layers[l].bias && layers[l].bias->needs_grad());
+    }
+    check(tp_mlp_small_fwd(ctx(), buf(), L, dims, wb, bb, re, ab, batch));
+    Tensor out = acts[L - 1];
+    if (any) {
+        out.set_requires_grad(true);
+        Tensor x = *this;
+        std::vector<MlpLayer> ls = layers;
+        std::vector<int> dv(dims, dims + L + 1);
+        tape_push(out, [x, ls, acts, out, dv, batch]() {
+            tp_buf* g = out.grad_buf();
+            if (!g) return;
+            const int L = (int)ls.size();
+            const tp_buf* wb[4];
+            const tp_buf* ab[4];
+            tp_buf* dw[4];
+            tp_buf* db[4];
+            int re[4], aw[4] = {0, 0, 0, 0}, abi[4] = {0, 0, 0, 0}, ax = 0;
+            for (int l = 0; l < L; ++l) {
+                wb[l] = ls[l].weight.buf();
+                ab[l] = acts[l].buf();
+                re[l] = ls[l].relu ? 1 : 0;
+                dw[l] = ls[l].weight.needs_grad() ? ls[l].weight.impl()->grad_for_write(&aw[l]) : nullptr;
+                db[l] = (ls[l].bias && ls[l].bias->needs_grad()) ? ls[l].bias->impl()->grad_for_write(&abi[l]) : nullptr;
+            }
+            tp_buf* gx = x.needs_grad() ? x.impl()->grad_for_write(&ax) : nullptr;
+            check(tp_mlp_small_bwd(ctx(), x.buf(), L, dv.data(), wb, re, ab, g, gx, dw, db, ax, aw, abi, batch));
         });
     }
     return out;

@@ -45,6 +45,10 @@ def config_conv_stack(fuse=1):
     check(lib.tp_host_config_conv_stack(int(fuse)))
 
 
+def config_small_mlp(fuse=1):
+    check(lib.tp_host_config_small_mlp(int(fuse)))
+
+
 def host_ctx():
     h = C.c_void_p()
     check(lib.tp_host_ctx(C.byref(h)))
