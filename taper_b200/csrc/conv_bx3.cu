@@ -739,7 +739,7 @@ nchw_to_planes_kernel(const float* __restrict__ x, const float* __restrict__ mas
 // ---- first layer with a tiny contraction (C_in * 9 <= 36: the C_in = 1 image layer): direct fp32 on the CUDA cores,
 // bias + ReLU (+ 2x2 max-pool) fused, output written straight as planes.  Exact fp32, k order (ci, kr, kc) ascending.
 // Replaces im2col + sgemm + transpose_4d + add_bias_4d + relu (+ max_pool2d) of src/tensor.rs:1221-1285, 1379-1464.
-template <bool POOL>
+template <bool POOL, bool C1>
 __global__ void __launch_bounds__(256)
 conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ w2, const float* __restrict__ bias,
                          uint16_t* __restrict__ out, int N, int Cin, int H, int W, int Cout, int relu) {
@@ -756,6 +756,18 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
     const unsigned int CG = Cout / 8;
     constexpr int nsub = POOL ? 4 : 1, win = POOL ? 4 : 3;
     const unsigned int total = (unsigned int)N * Ho * Wo * CG;                               // < 2^31 (checked on the host)
+    // C1 (one input channel, the image layer): the grid stride is a multiple of the channel-group count, so a thread keeps its
+    // channel group for all its pixels and holds its 9 x 8 weights in registers — the per-tap shared-memory loads (4 LSU
+    // wavefronts per 128-bit load, 18 loads per pixel) were what bound this kernel
+    float4 wreg[C1 ? 9 : 1][2];
+    if (C1) {
+        const unsigned int cg0 = (blockIdx.x * 256 + threadIdx.x) % CG;
+#pragma unroll
+        for (int tap = 0; tap < (C1 ? 9 : 1); ++tap) {
+            wreg[tap][0] = *(const float4*)(sw + tap * Cout + cg0 * 8);
+            wreg[tap][1] = *(const float4*)(sw + tap * Cout + cg0 * 8 + 4);
+        }
+    }
     for (unsigned int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
         // 32-bit index arithmetic (64-bit divisions cost more than the nine taps)
         const unsigned int pix = e / CG, cg = e - pix * CG;
@@ -791,8 +803,8 @@ conv_first_planes_kernel(const float* __restrict__ x, const float* __restrict__ 
             }
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const float4 wa = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8);
-                const float4 wb = *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8 + 4);
+                const float4 wa = C1 ? wreg[C1 ? tap : 0][0] : *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8);
+                const float4 wb = C1 ? wreg[C1 ? tap : 0][1] : *(const float4*)(sw + (ci * 9 + tap) * Cout + cg * 8 + 4);
 #pragma unroll
                 for (int s = 0; s < nsub; ++s) {
                     {
@@ -1181,10 +1193,19 @@ int conv_stack_fwd(tp_ctx* ctx, const float* x, int N, int C0, int H, int W, int
         const int ho = pool[0] ? h / 2 : h, wo = pool[0] ? w / 2 : w;
         const size_t items = (size_t)N * ho * wo * (cout[0] / 8);
         const size_t sm = (size_t)(C0 * 9 + 1) * cout[0] * sizeof(float);
-        rc = pool[0] ? launch_pdl(ctx, conv_first_planes_kernel<true>, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, pdl, x, w2[0], bias[0],
-                                  (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], relu[0] ? 1 : 0)
-                     : launch_pdl(ctx, conv_first_planes_kernel<false>, dim3(grid_for(ctx, items, 256, 8)), dim3(256), sm, pdl, x, w2[0], bias[0],
-                                  (uint16_t*)act[cur].b->ptr, N, C0, h, w, cout[0], relu[0] ? 1 : 0);
+        {
+            // grid: a multiple of the channel-group count in threads (the C1 kernels keep a thread on one channel group)
+            const dim3 grid(grid_for(ctx, items, 256, 8)), block(256);
+            const bool c1 = C0 == 1 && (256 % (cout[0] / 8)) == 0;
+            uint16_t* dst = (uint16_t*)act[cur].b->ptr;
+            const int rl = relu[0] ? 1 : 0;
+            if (pool[0])
+                rc = c1 ? launch_pdl(ctx, conv_first_planes_kernel<true, true>, grid, block, sm, pdl, x, w2[0], bias[0], dst, N, C0, h, w, cout[0], rl)
+                        : launch_pdl(ctx, conv_first_planes_kernel<true, false>, grid, block, sm, pdl, x, w2[0], bias[0], dst, N, C0, h, w, cout[0], rl);
+            else
+                rc = c1 ? launch_pdl(ctx, conv_first_planes_kernel<false, true>, grid, block, sm, pdl, x, w2[0], bias[0], dst, N, C0, h, w, cout[0], rl)
+                        : launch_pdl(ctx, conv_first_planes_kernel<false, false>, grid, block, sm, pdl, x, w2[0], bias[0], dst, N, C0, h, w, cout[0], rl);
+        }
         if (rc) return rc;
         h = ho; w = wo; c = cout[0];
         l0 = 1;

@@ -116,10 +116,18 @@ def test_sequential_peephole_on_the_cnn_head_matches_per_layer_and_oracle():
     from taper_b200 import host
     host.config(conv_full_adjoint=0, fuse_linear_relu=1, reference_op_sequence=0, gemm_mode=1)
     spec = "linear:128:128,relu,linear:128:64,relu,linear:64:10"
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(10)
     ref = R.build_mlp([128, 128, 64, 10], np.random.default_rng(9))
     x = rng.random((96, 128)).astype(F32)
     y = rng.integers(0, 10, 96).astype(F32)
+    # no pre-activation within rounding distance of the ReLU threshold: a unit at |z| ~ 1e-7 is on for one summation order and
+    # off for another (seed 5 has z = +9.1e-8 in fp64 that the oracle's fp32 sum rounds to -1.0e-7), and one flipped unit moves
+    # its bias gradient by 1/sqrt(batch).  The seed is chosen so the comparison below is about the kernels.
+    h = x.astype(np.float64)
+    for lin in [l for l in ref.layers if hasattr(l, "weight")][:2]:
+        z = h @ np.asarray(lin.weight.data(), np.float64).reshape(lin.weight.shape).T + np.asarray(lin.bias.data(), np.float64)
+        assert np.abs(z).min() > 5e-5
+        h = np.maximum(z, 0.0)
     R.Tape.reset()
     l_ref = R.cross_entropy_loss(ref.forward(R.Tensor.new(x, x.shape)), R.Tensor.new(y, y.shape))
     l_ref.backward()
