@@ -144,6 +144,14 @@ def main():
         tl = list(prev[:n]) + [last[0]]
         for i, nm in enumerate(names):
             print(f"  {nm:10s} {(tl[i + 1] - tl[i]) / 1e3:7.2f}")
+        if world > 1:
+            x = prev[n - 1:n + 6]
+            lab = ["A: push my parts of the other slices", "A: release + raise flags", "A: wait for the peers' flags", "B: reduce my slice + push the result",
+                   "B: release + raise + wait", "C: optimizer"]
+            print("  exchange kernel, CTA 0 (us): " + " | ".join(f"{l} {(x[i + 1] - x[i]) / 1e3:.2f}" for i, l in enumerate(lab)))
+            y = prev[n - 1:n + 9]
+            print(f"  exchange kernel, last CTA to pass (us after the kernel's start): peers' A flags seen {(y[7] - y[0]) / 1e3:.2f} | peers' B flags seen "
+                  f"{(y[8] - y[0]) / 1e3:.2f} | optimizer done {(y[9] - y[0]) / 1e3:.2f}  (CTA 0: {(y[3] - y[0]) / 1e3:.2f} | {(y[5] - y[0]) / 1e3:.2f} | {(y[6] - y[0]) / 1e3:.2f})")
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()

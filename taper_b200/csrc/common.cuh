@@ -201,7 +201,16 @@ int bx3_best_splits(tp_ctx* ctx, int bn, long tiles, int k);           // K-spli
 int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl);
 // compatible problems share a launch; `tail` (a tpfold::FoldStep, wide_fold.cuh) rides along on extra CTAs of the LAST launch
 // when that launch leaves SMs free (*tail_done says whether it did)
-int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const void* tail = nullptr, bool* tail_done = nullptr);
+// data parallel: the epilogue also stores every output vector that lies in another rank's slice of the gradient arena into
+// that rank's exchange window over NVLink (the reduce-scatter push of step_wide.cu's exchange rides on the GEMM's stores)
+struct Bx3Push {
+    const float* base = nullptr;     // the local gradient arena; outputs outside [base, base + world * slice) are not pushed
+    float* peer[8] = {};             // peer[q]: where rank q receives MY contribution to its slice (NULL for q == rank)
+    unsigned int slice = 0;          // floats per slice (a multiple of 4)
+    int world = 0, rank = 0;         // world <= 1: off
+};
+int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const void* tail = nullptr, bool* tail_done = nullptr,
+                     const Bx3Push* push = nullptr);
 int split_bf16(tp_ctx* ctx, const float* src, uint16_t* dst, size_t n, long long plane, bool pdl);
 // fp32 operands: splits both into temporaries first.  TP_ERR_UNSUPPORTED when the shape cannot go through TMA.
 int gemm_bx3(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* a, const float* b, float beta,

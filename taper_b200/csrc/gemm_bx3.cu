@@ -64,6 +64,7 @@ struct Bx3Group {
     // the GEMM tiles leave free, the others leave at once
     int tail_y0, tail_workers;
     tpfold::FoldStep tail;
+    tp::Bx3Push push;                // data parallel: outputs in another rank's slice of the arena also go to that rank's window
 };
 
 // K-major operand : rows of 128 B (64 bf16 of K), 8 rows = one 1024 B swizzle atom -> SBO 1024; LBO unused.
@@ -411,6 +412,13 @@ gemm_bx3_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                             o[j] = v;
                         }
                         if (p.c) *(float4*)(p.c + g) = make_float4(o[0], o[1], o[2], o[3]);
+                        if (grp.push.world > 1 && p.c) {
+                            // reduce-scatter push: the owner of this vector's slice sums the ranks' contributions (step_wide.cu)
+                            const unsigned int e = (unsigned int)((p.c + g) - grp.push.base);
+                            const unsigned int q = e / grp.push.slice;
+                            if ((int)q != grp.push.rank && q < (unsigned int)grp.push.world)
+                                *(float4*)(grp.push.peer[q] + (e - q * grp.push.slice)) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
                         if (p.c_split) split_store4(p.c_split + g, p.c_split + p.c_plane + g, o);
                     } else {
                         o[0] = o[1] = o[2] = o[3] = 0.0f;
@@ -500,7 +508,8 @@ bool make_map(EncodeTiledFn enc, CUtensorMap* map, const uint16_t* ptr, int rows
 }
 
 template <int BN, bool A_MN, bool B_MN, bool DRAIN>
-int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail, int tail_workers) {
+int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail, int tail_workers,
+             const tp::Bx3Push* push) {
     auto kern = gemm_bx3_kernel<BN, A_MN, B_MN, DRAIN>;
     constexpr int smem = Smem<BN>::kTotal;
     static bool attr_set[16] = {};                    // per device
@@ -512,6 +521,7 @@ int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, c
     }
     Bx3Group g{};
     g.count = count;
+    if (push) g.push = *push;
     int rows = 0, max_tn = 0;
     for (int i = 0; i < count; ++i) {
         const tp::Bx3Launch& L = *Ls[i];
@@ -566,12 +576,12 @@ int launch_t(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, c
 }
 
 template <int BN, bool DRAIN>
-int launch_major(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail, int tw) {
+int launch_major(tp_ctx* ctx, const tp::Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail, int tw, const tp::Bx3Push* push) {
     const tp::Bx3Launch& L = *Ls[0];
-    if (!L.a_mn && !L.b_mn) return launch_t<BN, false, false, DRAIN>(ctx, Ls, count, pdl, tail, tw);
-    if (!L.a_mn && L.b_mn) return launch_t<BN, false, true, DRAIN>(ctx, Ls, count, pdl, tail, tw);
-    if (L.a_mn && !L.b_mn) return launch_t<BN, true, false, DRAIN>(ctx, Ls, count, pdl, tail, tw);
-    return launch_t<BN, true, true, DRAIN>(ctx, Ls, count, pdl, tail, tw);
+    if (!L.a_mn && !L.b_mn) return launch_t<BN, false, false, DRAIN>(ctx, Ls, count, pdl, tail, tw, push);
+    if (!L.a_mn && L.b_mn) return launch_t<BN, false, true, DRAIN>(ctx, Ls, count, pdl, tail, tw, push);
+    if (L.a_mn && !L.b_mn) return launch_t<BN, true, false, DRAIN>(ctx, Ls, count, pdl, tail, tw, push);
+    return launch_t<BN, true, true, DRAIN>(ctx, Ls, count, pdl, tail, tw, push);
 }
 
 template <int BN>
@@ -732,12 +742,13 @@ int bx3_prepare(tp_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, c
     return TP_OK;
 }
 
-static int launch_any(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail = nullptr, int tw = 0) {
+static int launch_any(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const tpfold::FoldStep* tail = nullptr, int tw = 0,
+                      const Bx3Push* push = nullptr) {
     cudaSetDevice(ctx->device);
     const Bx3Launch& L = *Ls[0];
-    if (L.bn == 256) return launch_major<256, false>(ctx, Ls, count, pdl, tail, tw);
-    if (L.bn == 128) return L.drain ? launch_major<128, true>(ctx, Ls, count, pdl, tail, tw) : launch_major<128, false>(ctx, Ls, count, pdl, tail, tw);
-    return L.drain ? launch_major<64, true>(ctx, Ls, count, pdl, tail, tw) : launch_major<64, false>(ctx, Ls, count, pdl, tail, tw);
+    if (L.bn == 256) return launch_major<256, false>(ctx, Ls, count, pdl, tail, tw, push);
+    if (L.bn == 128) return L.drain ? launch_major<128, true>(ctx, Ls, count, pdl, tail, tw, push) : launch_major<128, false>(ctx, Ls, count, pdl, tail, tw, push);
+    return L.drain ? launch_major<64, true>(ctx, Ls, count, pdl, tail, tw, push) : launch_major<64, false>(ctx, Ls, count, pdl, tail, tw, push);
 }
 
 int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl) {
@@ -748,7 +759,7 @@ int bx3_launch(tp_ctx* ctx, const Bx3Launch& L, bool pdl) {
 // problems that share tile width, operand majors, K-split and drain mode go out as ONE launch (up to three); the rest follow
 // one by one.  The tail (fold + bookkeeping of the wide plan) joins the last launch when that launch's tiles leave at least
 // four SMs free in its first wave and it is not a K-split (cluster) launch; otherwise the caller launches it by itself.
-int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const void* tail, bool* tail_done) {
+int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pdl, const void* tail, bool* tail_done, const Bx3Push* push) {
     if (tail_done) *tail_done = false;
     int i = 0;
     while (i < count) {
@@ -763,7 +774,7 @@ int bx3_launch_group(tp_ctx* ctx, const Bx3Launch* const* Ls, int count, bool pd
             const long free_sms = (long)ctx->sm_count - ctas % ctx->sm_count;
             if (ctas % ctx->sm_count != 0 && free_sms >= 4) tw = (int)(free_sms < 16 ? free_sms : 16);
         }
-        int rc = launch_any(ctx, Ls + i, j - i, pdl, tw ? static_cast<const tpfold::FoldStep*>(tail) : nullptr, tw);
+        int rc = launch_any(ctx, Ls + i, j - i, pdl, tw ? static_cast<const tpfold::FoldStep*>(tail) : nullptr, tw, push);
         if (rc) return rc;
         if (tw && tail_done) *tail_done = true;
         i = j;

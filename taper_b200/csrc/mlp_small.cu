@@ -8,19 +8,26 @@
 // add_broadcast src/tensor.rs:636-704), ReLU (src/ops.rs:312-374) and their backward closures (matmul backward
 // src/ops.rs:254-291, bias column sums src/tensor.rs:680-691, ReLU mask src/ops.rs:358-370).
 //
-// A CTA owns kRows consecutive batch rows.  Forward: all weights transposed into shared memory ([in][out + 1]: the inner
-// loop reads consecutive outputs conflict-free), activations of the CTA's rows staged per layer, every layer's output written
-// to global (the backward needs them).  Backward: per layer dW / db partials of the CTA's rows and the gradient of the
-// layer's input (masked by the previous ReLU); a fold kernel sums the per-CTA partials in CTA order (deterministic).
-// Products are accumulated in ascending k with fmaf, bias added last — the order of the reference's matmul + add_broadcast.
+//
+// A CTA owns kRows = 16 consecutive batch rows (64 CTAs at batch 1024).  Every layer's weights are brought into shared memory
+// once per CTA with 16-byte cp.async copies in their own [out][in] layout (row pitch in + 4 floats: a quarter-warp's 128-bit
+// reads of eight consecutive rows fall into eight different bank groups), all in flight at once — the first version staged
+// them through registers with a transpose and spent most of its 30 us waiting on those loads with 8 warps per SM.
+// Forward: register tiles of 2 rows x 4 outputs walk k four at a time (128-bit shared loads of the activations, broadcast
+// within a warp, and of four weight rows); every layer's output is written to global (the backward needs it).  Backward: per
+// layer the dW / db partials of the CTA's rows (4 x 4 tiles over (o, k), contraction over the 16 rows) and the gradient of
+// the layer's input (2 rows x 4 inputs, masked by the previous ReLU); a fold kernel sums the per-CTA partials in CTA order
+// (deterministic).  Products are accumulated in ascending k with fmaf, bias added last — the order of the reference's
+// matmul + add_broadcast.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRows = 32;            // batch rows per CTA
+constexpr int kRows = 16;            // batch rows per CTA
 constexpr int kMaxL = 4;
 constexpr int kMaxW = 128;
+constexpr int kXP = kMaxW + 4;       // row pitch of the staged activations / gradients (floats)
 
 struct MlpArgs {
     int L, batch;
@@ -33,83 +40,127 @@ struct MlpArgs {
 };
 
 __device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
-__device__ __forceinline__ int wpitch(int out) { return pad4(out) + 4; }       // transposed-weight row pitch: 16-byte aligned, not a multiple of 32 banks
+__device__ __forceinline__ int wpitch(int in) { return pad4(in) + 4; }         // weight row pitch in shared memory (floats)
+__device__ __forceinline__ int wrows(int out) { return pad4(out); }            // rows held per layer (rows >= out are zero)
 
-// Register tiles of 4 rows x 4 outputs (16 independent FMA chains per thread: the loops are latency-bound otherwise — one
-// accumulator per thread measured 122 us for this kernel at batch 1024, against ~6 us of issue time).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// weights of layer (in, out) at `w` -> dst[pad4(out)][wpitch(in)]; pad columns and pad rows zero
+__device__ __forceinline__ void stage_weights(float* dst, const float* __restrict__ w, int in, int out) {
+    const int wp = wpitch(in), in4 = pad4(in);
+    if ((in & 3) == 0 && (((uintptr_t)w) & 15) == 0) {
+        const int vec = in >> 2;
+        for (int i = threadIdx.x; i < out * vec; i += kThreads) {
+            const int o = i / vec, v = i - o * vec;
+            cp_async16(dst + o * wp + 4 * v, w + (size_t)o * in + 4 * v);
+        }
+    } else {
+#pragma unroll 4
+        for (int i = threadIdx.x; i < out * in4; i += kThreads) {
+            const int o = i / in4, k = i - o * in4;
+            dst[o * wp + k] = k < in ? __ldg(w + (size_t)o * in + k) : 0.0f;
+        }
+    }
+    for (int i = threadIdx.x; i < (wrows(out) - out) * in4; i += kThreads) {
+        const int o = out + i / in4, k = i % in4;
+        dst[o * wp + k] = 0.0f;
+    }
+}
+
+// `rows` rows of a [batch, width] matrix -> dst[kRows][kXP]; pad columns (up to pad4(width)) and rows >= rows zero
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int rows, int width) {
+    const int w4 = pad4(width);
+    if ((width & 3) == 0 && (((uintptr_t)src) & 15) == 0) {
+        const int vec = width >> 2;
+        for (int i = threadIdx.x; i < kRows * vec; i += kThreads) {
+            const int r = i / vec, v = i - r * vec;
+            if (r < rows) cp_async16(dst + r * kXP + 4 * v, src + (size_t)r * width + 4 * v);
+            else *(float4*)(dst + r * kXP + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int i = threadIdx.x; i < kRows * w4; i += kThreads) {
+            const int r = i / w4, k = i - r * w4;
+            dst[r * kXP + k] = (r < rows && k < width) ? __ldg(src + (size_t)r * width + k) : 0.0f;
+        }
+    }
+}
+
+#define TP_FMA4(acc, xv, wv)                 \
+    do {                                     \
+        acc = fmaf((xv).x, (wv).x, acc);     \
+        acc = fmaf((xv).y, (wv).y, acc);     \
+        acc = fmaf((xv).z, (wv).z, acc);     \
+        acc = fmaf((xv).w, (wv).w, acc);     \
+    } while (0)
+
 __global__ void __launch_bounds__(kThreads)
 mlp_small_fwd_kernel(const __grid_constant__ MlpArgs a) {
     extern __shared__ __align__(16) float sm[];
-    // layout: transposed weights of every layer ([in][wpitch(out)], columns >= out zero), then two activation buffers [kRows][kMaxW]
-    float* wt[kMaxL];
+    // layout: the weights of every layer ([pad4(out)][wpitch(in)]), then two activation buffers [kRows][kXP]
+    float* ws[kMaxL];
     float* p = sm;
     for (int l = 0; l < a.L; ++l) {
-        wt[l] = p;
-        p += a.dims[l] * wpitch(a.dims[l + 1]);
+        ws[l] = p;
+        p += wrows(a.dims[l + 1]) * wpitch(a.dims[l]);
     }
     float* cur = p;
-    float* nxt = p + kRows * kMaxW;
+    float* nxt = p + kRows * kXP;
     const int r0 = blockIdx.x * kRows;
     const int rows = min(kRows, a.batch - r0);
-    for (int l = 0; l < a.L; ++l) {
-        const int in = a.dims[l], out = a.dims[l + 1], wp = wpitch(out);
-        for (int i = threadIdx.x; i < in * wp; i += kThreads) wt[l][i] = 0.0f;
-    }
-    for (int i = threadIdx.x; i < 2 * kRows * kMaxW; i += kThreads) cur[i] = 0.0f;
+    for (int l = 0; l < a.L; ++l) stage_weights(ws[l], a.W[l], a.dims[l], a.dims[l + 1]);
+    stage_rows(cur, a.x + (size_t)r0 * a.dims[0], rows, a.dims[0]);
+    cp_async_wait_all();
     __syncthreads();
     for (int l = 0; l < a.L; ++l) {
-        const int in = a.dims[l], out = a.dims[l + 1], wp = wpitch(out);
-        // eight independent loads in flight per thread (one load per iteration leaves the kernel waiting on L2 latency)
-#pragma unroll 8
-        for (int i = threadIdx.x; i < in * out; i += kThreads) {
-            const int o = i / in, k = i - o * in;
-            wt[l][k * wp + o] = __ldg(a.W[l] + i);
-        }
-    }
-    {
-        const int in = a.dims[0];
-#pragma unroll 8
-        for (int i = threadIdx.x; i < rows * in; i += kThreads) {
-            const int r = i / in, k = i - r * in;
-            cur[r * kMaxW + k] = __ldg(a.x + (size_t)r0 * in + i);
-        }
-    }
-    __syncthreads();
-    for (int l = 0; l < a.L; ++l) {
-        const int in = a.dims[l], out = a.dims[l + 1], wp = wpitch(out);
-        const int og_n = pad4(out) / 4;
-        for (int t = threadIdx.x; t < (kRows / 4) * og_n; t += kThreads) {
+        const int in4 = pad4(a.dims[l]), out = a.dims[l + 1], wp = wpitch(a.dims[l]);
+        const int og_n = pad4(out) >> 2;                                         // a thread's four outputs: og + og_n * j
+        const float* bias = a.b[l];
+        for (int t = threadIdx.x; t < (kRows / 2) * og_n; t += kThreads) {
             const int rg = t / og_n, og = t - rg * og_n;
-            const float* xr = cur + rg * 4 * kMaxW;
-            const float* w = wt[l] + og * 4;
-            float acc[4][4];
+            const float* x0 = cur + (2 * rg) * kXP;
+            const float* x1 = x0 + kXP;
+            const float* w0 = ws[l] + (og) * wp;                                 // rows >= out exist (zero) up to pad4(out)
+            const float* w1 = ws[l] + (og + og_n) * wp;
+            const float* w2 = ws[l] + (og + 2 * og_n) * wp;
+            const float* w3 = ws[l] + (og + 3 * og_n) * wp;
+            float acc[2][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-            for (int k = 0; k < in; ++k) {
-                const float4 wv = *(const float4*)(w + k * wp);
-                const float x0 = xr[k], x1 = xr[kMaxW + k], x2 = xr[2 * kMaxW + k], x3 = xr[3 * kMaxW + k];
-                acc[0][0] = fmaf(x0, wv.x, acc[0][0]); acc[0][1] = fmaf(x0, wv.y, acc[0][1]); acc[0][2] = fmaf(x0, wv.z, acc[0][2]); acc[0][3] = fmaf(x0, wv.w, acc[0][3]);
-                acc[1][0] = fmaf(x1, wv.x, acc[1][0]); acc[1][1] = fmaf(x1, wv.y, acc[1][1]); acc[1][2] = fmaf(x1, wv.z, acc[1][2]); acc[1][3] = fmaf(x1, wv.w, acc[1][3]);
-                acc[2][0] = fmaf(x2, wv.x, acc[2][0]); acc[2][1] = fmaf(x2, wv.y, acc[2][1]); acc[2][2] = fmaf(x2, wv.z, acc[2][2]); acc[2][3] = fmaf(x2, wv.w, acc[2][3]);
-                acc[3][0] = fmaf(x3, wv.x, acc[3][0]); acc[3][1] = fmaf(x3, wv.y, acc[3][1]); acc[3][2] = fmaf(x3, wv.z, acc[3][2]); acc[3][3] = fmaf(x3, wv.w, acc[3][3]);
+#pragma unroll 2
+            for (int k = 0; k < in4; k += 4) {
+                const float4 a0 = *(const float4*)(x0 + k), a1 = *(const float4*)(x1 + k);
+                const float4 v0 = *(const float4*)(w0 + k), v1 = *(const float4*)(w1 + k);
+                const float4 v2 = *(const float4*)(w2 + k), v3 = *(const float4*)(w3 + k);
+                TP_FMA4(acc[0][0], a0, v0); TP_FMA4(acc[0][1], a0, v1); TP_FMA4(acc[0][2], a0, v2); TP_FMA4(acc[0][3], a0, v3);
+                TP_FMA4(acc[1][0], a1, v0); TP_FMA4(acc[1][1], a1, v1); TP_FMA4(acc[1][2], a1, v2); TP_FMA4(acc[1][3], a1, v3);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = rg * 4 + i;
+            for (int j = 0; j < 4; ++j) {
+                const int o = og + og_n * j;
+                if (o >= out) continue;
+                const float bj = bias ? __ldg(bias + o) : 0.0f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int o = og * 4 + j;
-                    if (o < out) {
-                        float v = acc[i][j];
-                        if (a.b[l]) v += __ldg(a.b[l] + o);
-                        if (a.relu[l]) v = fmaxf(v, 0.0f);
-                        nxt[r * kMaxW + o] = v;
-                        if (r < rows) a.act[l][(size_t)(r0 + r) * out + o] = v;
-                    }
+                for (int i = 0; i < 2; ++i) {
+                    const int r = 2 * rg + i;
+                    float v = acc[i][j];
+                    if (bias) v += bj;
+                    if (a.relu[l]) v = fmaxf(v, 0.0f);
+                    nxt[r * kXP + o] = v;
+                    if (r < rows) a.act[l][(size_t)(r0 + r) * out + o] = v;
                 }
             }
+        }
+        // pad columns of the next layer's input must be zero
+        for (int i = threadIdx.x; i < kRows * (pad4(out) - out); i += kThreads) {
+            const int r = i / (pad4(out) - out), k = out + i % (pad4(out) - out);
+            nxt[r * kXP + k] = 0.0f;
         }
         __syncthreads();
         float* t2 = cur; cur = nxt; nxt = t2;
@@ -134,46 +185,44 @@ struct MlpBwdArgs {
 __global__ void __launch_bounds__(kThreads)
 mlp_small_bwd_kernel(const __grid_constant__ MlpBwdArgs a) {
     extern __shared__ __align__(16) float sm[];
-    // gz [kRows][kMaxW] (gradient of the current layer's pre-activation), gin [kRows][kMaxW], xin [kRows][kMaxW] (rows >= the CTA's
-    // row count and columns beyond the widths stay zero), W [out][kMaxW]
-    float* gz = sm;
-    float* gin = gz + kRows * kMaxW;
-    float* xin = gin + kRows * kMaxW;
-    float* w = xin + kRows * kMaxW;
+    // the weights of every layer ([pad4(out)][wpitch(in)]), then gz (gradient of the current layer's pre-activation), gin, xin:
+    // [kRows][kXP] each; rows >= the CTA's row count and pad columns are zero
+    float* ws[kMaxL];
+    float* p = sm;
+    for (int l = 0; l < a.L; ++l) {
+        ws[l] = p;
+        p += wrows(a.dims[l + 1]) * wpitch(a.dims[l]);
+    }
+    float* gz = p;
+    float* gin = gz + kRows * kXP;
+    float* xin = gin + kRows * kXP;
     const int r0 = blockIdx.x * kRows;
     const int rows = min(kRows, a.batch - r0);
     float* part = a.partial + (size_t)blockIdx.x * a.n_params;
-    for (int i = threadIdx.x; i < 3 * kRows * kMaxW; i += kThreads) sm[i] = 0.0f;
-    __syncthreads();
+    for (int l = 0; l < a.L; ++l) stage_weights(ws[l], a.W[l], a.dims[l], a.dims[l + 1]);
     {
-        const int out = a.dims[a.L];
-#pragma unroll 4
-        for (int i = threadIdx.x; i < rows * out; i += kThreads) {
-            const int r = i / out, o = i - r * out;
-            float g = __ldg(a.gout + (size_t)r0 * out + i);
-            if (a.relu[a.L - 1]) g = __ldg(a.act[a.L - 1] + (size_t)r0 * out + i) > 0.0f ? g : 0.0f;
-            gz[r * kMaxW + o] = g;
+        const int out = a.dims[a.L], o4 = pad4(out);
+        const bool relu = a.relu[a.L - 1] != 0;
+        for (int i = threadIdx.x; i < kRows * o4; i += kThreads) {
+            const int r = i / o4, o = i - r * o4;
+            float g = 0.0f;
+            if (r < rows && o < out) {
+                g = __ldg(a.gout + (size_t)(r0 + r) * out + o);
+                if (relu) g = __ldg(a.act[a.L - 1] + (size_t)(r0 + r) * out + o) > 0.0f ? g : 0.0f;
+            }
+            gz[r * kXP + o] = g;
         }
     }
     for (int l = a.L - 1; l >= 0; --l) {
-        const int in = a.dims[l], out = a.dims[l + 1];
+        const int in = a.dims[l], out = a.dims[l + 1], in4 = pad4(in), out4 = pad4(out), wp = wpitch(in);
         const float* xin_g = l == 0 ? a.x : a.act[l - 1];
-        for (int i = threadIdx.x; i < kRows * kMaxW; i += kThreads) xin[i] = 0.0f;
-        __syncthreads();
-#pragma unroll 8
-        for (int i = threadIdx.x; i < rows * in; i += kThreads) {
-            const int r = i / in, k = i - r * in;
-            xin[r * kMaxW + k] = __ldg(xin_g + (size_t)r0 * in + i);
-        }
-#pragma unroll 8
-        for (int i = threadIdx.x; i < out * kMaxW; i += kThreads) {
-            const int o = i / kMaxW, k = i - o * kMaxW;
-            w[i] = k < in ? __ldg(a.W[l] + (size_t)o * in + k) : 0.0f;
-        }
+        stage_rows(xin, xin_g + (size_t)r0 * in, rows, in);
+        cp_async_wait_all();
         __syncthreads();
         // dW[o][k] partial = sum_r gz[r][o] * xin[r][k]   (src/ops.rs:280-291): 4 x 4 register tiles over (o, k)
         {
-            const int kg_n = pad4(in) / 4, og_n = pad4(out) / 4;
+            const int kg_n = in4 >> 2, og_n = out4 >> 2;
+            float* dst = part + a.p_off[l];
             for (int t = threadIdx.x; t < og_n * kg_n; t += kThreads) {
                 const int og = t / kg_n, kg = t - og * kg_n;
                 float acc[4][4];
@@ -181,81 +230,88 @@ mlp_small_bwd_kernel(const __grid_constant__ MlpBwdArgs a) {
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
                 for (int r = 0; r < kRows; ++r) {
-                    const float4 g4 = *(const float4*)(gz + r * kMaxW + og * 4);
-                    const float4 x4 = *(const float4*)(xin + r * kMaxW + kg * 4);
+                    const float4 g4 = *(const float4*)(gz + r * kXP + og * 4);
+                    const float4 x4 = *(const float4*)(xin + r * kXP + kg * 4);
                     acc[0][0] = fmaf(g4.x, x4.x, acc[0][0]); acc[0][1] = fmaf(g4.x, x4.y, acc[0][1]); acc[0][2] = fmaf(g4.x, x4.z, acc[0][2]); acc[0][3] = fmaf(g4.x, x4.w, acc[0][3]);
                     acc[1][0] = fmaf(g4.y, x4.x, acc[1][0]); acc[1][1] = fmaf(g4.y, x4.y, acc[1][1]); acc[1][2] = fmaf(g4.y, x4.z, acc[1][2]); acc[1][3] = fmaf(g4.y, x4.w, acc[1][3]);
                     acc[2][0] = fmaf(g4.z, x4.x, acc[2][0]); acc[2][1] = fmaf(g4.z, x4.y, acc[2][1]); acc[2][2] = fmaf(g4.z, x4.z, acc[2][2]); acc[2][3] = fmaf(g4.z, x4.w, acc[2][3]);
                     acc[3][0] = fmaf(g4.w, x4.x, acc[3][0]); acc[3][1] = fmaf(g4.w, x4.y, acc[3][1]); acc[3][2] = fmaf(g4.w, x4.z, acc[3][2]); acc[3][3] = fmaf(g4.w, x4.w, acc[3][3]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+                    const int o = og * 4 + i;
+                    if (o >= out) continue;
+                    if ((in & 3) == 0) {
+                        *(float4*)(dst + (long long)o * in + kg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int o = og * 4 + i, k = kg * 4 + j;
-                        if (o < out && k < in) part[a.p_off[l] + (long long)o * in + k] = acc[i][j];
+                        for (int j = 0; j < 4; ++j)
+                            if (kg * 4 + j < in) dst[(long long)o * in + kg * 4 + j] = acc[i][j];
                     }
+                }
             }
         }
         // db[o] = sum_r gz[r][o]  (src/tensor.rs:680-691)
         for (int o = threadIdx.x; o < out; o += kThreads) {
             float acc = 0.0f;
-            for (int r = 0; r < kRows; ++r) acc += gz[r * kMaxW + o];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) acc += gz[r * kXP + o];
             part[a.p_off[l] + (long long)out * in + o] = acc;
         }
-        // gradient of the layer's input: gin[r][k] = sum_o gz[r][o] * W[o][k]  (src/ops.rs:254-265), then the previous ReLU's mask
+        // gradient of the layer's input: gin[r][k] = sum_o gz[r][o] * W[o][k]  (src/ops.rs:254-265), then the previous ReLU's
+        // mask: 2 rows x 4 inputs per thread, o four at a time (rows >= out of the staged weights are zero)
         if (l > 0 || a.dx) {
-            const int kg_n = pad4(in) / 4;
-            for (int t = threadIdx.x; t < (kRows / 4) * kg_n; t += kThreads) {
+            const int kg_n = in4 >> 2;
+            const bool mask = l > 0 && a.relu[l - 1] != 0;
+            for (int t = threadIdx.x; t < (kRows / 2) * kg_n; t += kThreads) {
                 const int rg = t / kg_n, kg = t - rg * kg_n;
-                float acc[4][4];
+                const float* g0 = gz + (2 * rg) * kXP;
+                const float* g1 = g0 + kXP;
+                const float* w = ws[l] + kg * 4;
+                float acc[2][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 2; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-                const float* g = gz + rg * 4 * kMaxW;
-                for (int o = 0; o < out; ++o) {
-                    const float4 w4 = *(const float4*)(w + o * kMaxW + kg * 4);
-                    const float g0 = g[o], g1 = g[kMaxW + o], g2 = g[2 * kMaxW + o], g3 = g[3 * kMaxW + o];
-                    acc[0][0] = fmaf(g0, w4.x, acc[0][0]); acc[0][1] = fmaf(g0, w4.y, acc[0][1]); acc[0][2] = fmaf(g0, w4.z, acc[0][2]); acc[0][3] = fmaf(g0, w4.w, acc[0][3]);
-                    acc[1][0] = fmaf(g1, w4.x, acc[1][0]); acc[1][1] = fmaf(g1, w4.y, acc[1][1]); acc[1][2] = fmaf(g1, w4.z, acc[1][2]); acc[1][3] = fmaf(g1, w4.w, acc[1][3]);
-                    acc[2][0] = fmaf(g2, w4.x, acc[2][0]); acc[2][1] = fmaf(g2, w4.y, acc[2][1]); acc[2][2] = fmaf(g2, w4.z, acc[2][2]); acc[2][3] = fmaf(g2, w4.w, acc[2][3]);
-                    acc[3][0] = fmaf(g3, w4.x, acc[3][0]); acc[3][1] = fmaf(g3, w4.y, acc[3][1]); acc[3][2] = fmaf(g3, w4.z, acc[3][2]); acc[3][3] = fmaf(g3, w4.w, acc[3][3]);
+#pragma unroll 2
+                for (int o = 0; o < out4; o += 4) {
+                    const float4 ga = *(const float4*)(g0 + o), gb = *(const float4*)(g1 + o);
+                    const float4 wa = *(const float4*)(w + (o) * wp), wb = *(const float4*)(w + (o + 1) * wp);
+                    const float4 wc = *(const float4*)(w + (o + 2) * wp), wd = *(const float4*)(w + (o + 3) * wp);
+                    acc[0][0] = fmaf(ga.x, wa.x, acc[0][0]); acc[0][1] = fmaf(ga.x, wa.y, acc[0][1]); acc[0][2] = fmaf(ga.x, wa.z, acc[0][2]); acc[0][3] = fmaf(ga.x, wa.w, acc[0][3]);
+                    acc[1][0] = fmaf(gb.x, wa.x, acc[1][0]); acc[1][1] = fmaf(gb.x, wa.y, acc[1][1]); acc[1][2] = fmaf(gb.x, wa.z, acc[1][2]); acc[1][3] = fmaf(gb.x, wa.w, acc[1][3]);
+                    acc[0][0] = fmaf(ga.y, wb.x, acc[0][0]); acc[0][1] = fmaf(ga.y, wb.y, acc[0][1]); acc[0][2] = fmaf(ga.y, wb.z, acc[0][2]); acc[0][3] = fmaf(ga.y, wb.w, acc[0][3]);
+                    acc[1][0] = fmaf(gb.y, wb.x, acc[1][0]); acc[1][1] = fmaf(gb.y, wb.y, acc[1][1]); acc[1][2] = fmaf(gb.y, wb.z, acc[1][2]); acc[1][3] = fmaf(gb.y, wb.w, acc[1][3]);
+                    acc[0][0] = fmaf(ga.z, wc.x, acc[0][0]); acc[0][1] = fmaf(ga.z, wc.y, acc[0][1]); acc[0][2] = fmaf(ga.z, wc.z, acc[0][2]); acc[0][3] = fmaf(ga.z, wc.w, acc[0][3]);
+                    acc[1][0] = fmaf(gb.z, wc.x, acc[1][0]); acc[1][1] = fmaf(gb.z, wc.y, acc[1][1]); acc[1][2] = fmaf(gb.z, wc.z, acc[1][2]); acc[1][3] = fmaf(gb.z, wc.w, acc[1][3]);
+                    acc[0][0] = fmaf(ga.w, wd.x, acc[0][0]); acc[0][1] = fmaf(ga.w, wd.y, acc[0][1]); acc[0][2] = fmaf(ga.w, wd.z, acc[0][2]); acc[0][3] = fmaf(ga.w, wd.w, acc[0][3]);
+                    acc[1][0] = fmaf(gb.w, wd.x, acc[1][0]); acc[1][1] = fmaf(gb.w, wd.y, acc[1][1]); acc[1][2] = fmaf(gb.w, wd.z, acc[1][2]); acc[1][3] = fmaf(gb.w, wd.w, acc[1][3]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 2; ++i) {
+                    const int r = 2 * rg + i;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int r = rg * 4 + i, k = kg * 4 + j;
-                        if (k < in) {
-                            float v = acc[i][j];
-                            if (l > 0 && a.relu[l - 1]) v = xin[r * kMaxW + k] > 0.0f ? v : 0.0f;
-                            gin[r * kMaxW + k] = v;
-                            if (l == 0 && r < rows) {
-                                float* d = a.dx + (size_t)(r0 + r) * in + k;
-                                *d = a.acc_dx ? *d + v : v;
-                            }
+                        const int k = kg * 4 + j;
+                        float v = acc[i][j];
+                        if (mask) v = xin[r * kXP + k] > 0.0f ? v : 0.0f;
+                        if (k >= in) v = 0.0f;
+                        gin[r * kXP + k] = v;
+                        if (l == 0 && r < rows && k < in) {
+                            float* d = a.dx + (size_t)(r0 + r) * in + k;
+                            *d = a.acc_dx ? *d + v : v;
                         }
                     }
+                }
             }
         }
         __syncthreads();
         float* t2 = gz; gz = gin; gin = t2;
-        // the next layer's gz columns beyond its width must be zero (they feed 4-wide tiles): the buffer that becomes gin is
-        // rewritten per element below, the one that became gz was written for k < in only over zeros of the same or a wider layer
-        if (l > 0) {
-            const int nin = a.dims[l];                           // width of the new gz
-            for (int i = threadIdx.x; i < kRows * kMaxW; i += kThreads) {
-                const int k = i & (kMaxW - 1);
-                if (k >= nin) gz[i] = 0.0f;
-            }
-            __syncthreads();
-        }
     }
 }
 
-// dst[i] (+)= sum over ctas of partial[cta][off + i], ctas in order; one launch for all tensors
 struct FoldArgs {
     const float* partial;
     long long n_params;
@@ -286,16 +342,12 @@ mlp_small_fold_kernel(const __grid_constant__ FoldArgs f) {
 
 bool shapes_ok(int L, const int* dims, int batch, size_t* fwd_smem, size_t* bwd_smem) {
     if (L < 1 || L > kMaxL || batch < 1) return false;
-    size_t wsum = 0, wmax = 0;
+    size_t wsum = 0;
     for (int l = 0; l <= L; ++l)
         if (dims[l] < 1 || dims[l] > kMaxW) return false;
-    for (int l = 0; l < L; ++l) {
-        wsum += (size_t)dims[l] * (((dims[l + 1] + 3) & ~3) + 4);
-        const size_t w = (size_t)dims[l + 1] * kMaxW;
-        if (w > wmax) wmax = w;
-    }
-    *fwd_smem = (wsum + 2 * kRows * kMaxW) * sizeof(float);
-    *bwd_smem = (3 * kRows * kMaxW + wmax) * sizeof(float);
+    for (int l = 0; l < L; ++l) wsum += (size_t)((dims[l + 1] + 3) & ~3) * (((dims[l] + 3) & ~3) + 4);
+    *fwd_smem = (wsum + 2 * kRows * kXP) * sizeof(float);
+    *bwd_smem = (wsum + 3 * kRows * kXP) * sizeof(float);
     return *fwd_smem <= 200 * 1024 && *bwd_smem <= 200 * 1024;
 }
 
@@ -365,8 +417,9 @@ int tp_mlp_small_bwd(tp_ctx* ctx, const tp_buf* x, int n_layers, const int* dims
         a.W[l] = weights[l]->ptr;
         a.act[l] = acts[l]->ptr;
         a.relu[l] = relu[l] ? 1 : 0;
-        a.p_off[l] = np;
+        a.p_off[l] = np;                          // a multiple of 4: the kernel stores dW partial rows as float4 when in % 4 == 0
         np += (long long)dims[l] * dims[l + 1] + dims[l + 1];
+        np = (np + 3) & ~3LL;
     }
     a.n_params = np;
     a.x = x->ptr;

@@ -58,6 +58,15 @@ __device__ __forceinline__ void split_store4(uint16_t* hi, uint16_t* lo, float a
     *(uint2*)lo = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
+// profiling: the latest time any CTA of the grid passes this point (the slot is zeroed by the host before the run)
+__device__ __forceinline__ void stamp_max(unsigned long long* stamp) {
+    if (stamp && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(stamp, gt);
+    }
+}
+
 __device__ __forceinline__ void stamp_now(unsigned long long* stamp) {
     if (stamp && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long gt;
@@ -348,6 +357,9 @@ struct XchgArgs {
     float* peer_slots[kMaxWorld];
     int* err;
     unsigned long long* stamp;
+    // float4 ranges of the arena the weight-gradient GEMMs' epilogues have already pushed (Bx3Push): phase A skips them
+    int n_pushed;
+    long long pushed_lo[4], pushed_hi[4];
 };
 
 struct AdamArgsW {
@@ -405,17 +417,32 @@ wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
         const long long n = chunk_len(j);
         const float4* src = G4 + (long long)j * a.slice4 + c0;
         float4* dst = reinterpret_cast<float4*>(a.peer_slots[j] + (long long)a.rank * a.row) + c0;
+        const long long e0 = (long long)j * a.slice4 + c0;         // arena position (float4) of the chunk's first vector
+        bool covered = false;                                      // the whole chunk inside one pushed range: the common case
+        for (int r = 0; r < a.n_pushed; ++r) covered = covered || (e0 >= a.pushed_lo[r] && e0 + n <= a.pushed_hi[r]);
+        if (covered) continue;
         for (long long i0 = t; i0 < n; i0 += kThreads * 4) {
             float4 v[4];
+            bool live[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (i0 + u * kThreads < n) v[u] = __ldcg(src + i0 + u * kThreads);
+            for (int u = 0; u < 4; ++u) {
+                const long long i = i0 + u * kThreads;
+                live[u] = i < n;
+                for (int r = 0; r < a.n_pushed; ++r)
+                    if (e0 + i >= a.pushed_lo[r] && e0 + i < a.pushed_hi[r]) live[u] = false;
+                if (live[u]) v[u] = __ldcg(src + i);
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (i0 + u * kThreads < n) dst[i0 + u * kThreads] = v[u];
+            for (int u = 0; u < 4; ++u) if (live[u]) dst[i0 + u * kThreads] = v[u];
         }
     }
+    stamp_now(a.stamp ? a.stamp + 1 : nullptr);          // CTA 0's phase stamps (profiling only): pushed | flag raised | peers seen | ...
     raise_flags(a, c);
+    stamp_now(a.stamp ? a.stamp + 2 : nullptr);
     // ---- B: reduce my slice in rank order, hand the result to everybody ----
     if (!wait_flags(a, c)) return;       // a peer never arrived: its slot is stale, apply nothing
+    stamp_now(a.stamp ? a.stamp + 3 : nullptr);
+    stamp_max(a.stamp ? a.stamp + 7 : nullptr);
     {
         const long long n = chunk_len(a.rank);
         const long long res_off = a.slice4;                    // result area of a row starts after its recv area
@@ -447,9 +474,12 @@ wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
             }
         }
     }
+    stamp_now(a.stamp ? a.stamp + 4 : nullptr);
     raise_flags(a, C_ + c);
     // ---- C: optimizer on chunk c of every slice ----
     if (!wait_flags(a, C_ + c)) return;
+    stamp_now(a.stamp ? a.stamp + 5 : nullptr);
+    stamp_max(a.stamp ? a.stamp + 8 : nullptr);
     AdamArgsW aa{};
     if (a.opt_kind != 0) {
         const float* h = a.hyper;
@@ -498,6 +528,8 @@ wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
             }
         }
     }
+    stamp_now(a.stamp ? a.stamp + 6 : nullptr);
+    stamp_max(a.stamp ? a.stamp + 9 : nullptr);
 }
 
 template <typename Kern, typename Arg>
@@ -553,6 +585,7 @@ struct WidePlan {
     FoldTable fold{};                // host copy; the device copy lives in the plan's block
     FoldTable* fold_dev = nullptr;
     bool fold_in_group = true;       // the grouped dW launch runs the fold on extra CTAs
+    bool push_in_gemm = true;        // data parallel: the dW epilogues push other ranks' slices into their exchange windows
     bool pdl = true;
     bool weights_fresh = false;
     unsigned long long* stamps = nullptr;    // [2][16] %globaltimer per kernel of the last two steps (tp_step_set_profile)
@@ -717,6 +750,7 @@ static int wide_build(WidePlan* w, Carver& c) {
         return TP_ERR_CUDA;
     }
     { const char* v = getenv("TAPER_WIDE_FOLD_IN_GROUP"); w->fold_in_group = !(v && v[0] == '0'); }
+    { const char* v = getenv("TAPER_WIDE_PUSH_IN_GEMM"); w->push_in_gemm = !(v && v[0] == '0'); }
     return TP_OK;
 }
 
@@ -870,7 +904,20 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         all[n++] = &w->dw_last;
         for (int l = L - 2; l >= 0; --l) { w->dw[l].stamp = nullptr; all[n++] = &w->dw[l]; }
         bool folded = false;
-        rc = bx3_launch_group(ctx, all, n, pdl, w->fold_in_group ? &fs : nullptr, &folded);
+        Bx3Push push{};
+        if (xc && w->push_in_gemm) {
+            // data parallel: the epilogues store every vector that belongs to another rank's slice straight into that rank's
+            // exchange window, so the reduce-scatter's NVLink traffic overlaps the remaining tiles instead of following them
+            const size_t par = xc->seq & 1u;
+            const long long slice4 = (d.arena_len / 4 + xc->world - 1) / xc->world;
+            push.base = w->G;
+            push.slice = (unsigned int)(slice4 * 4);
+            push.world = xc->world; push.rank = xc->rank;
+            for (int r = 0; r < xc->world; ++r)
+                push.peer[r] = r == xc->rank ? nullptr
+                                             : reinterpret_cast<float*>(xc->peers[r] + xc->slots_off) + par * xc->world * xc->row + (size_t)xc->rank * xc->row;
+        }
+        rc = bx3_launch_group(ctx, all, n, pdl, w->fold_in_group ? &fs : nullptr, &folded, push.world > 1 ? &push : nullptr);
         if (rc) return rc;
         if (!folded) {
             fs.stamp = next_stamp();
@@ -903,6 +950,18 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         }
         xa.err = ctx->dev_error;
         xa.stamp = next_stamp();
+        xa.n_pushed = 0;
+        if (w->push_in_gemm) {
+            auto pushed = [&](const Bx3Launch& g) {
+                if (!g.c || xa.n_pushed >= 4) return;
+                const long long lo = (g.c - w->G) / 4;
+                xa.pushed_lo[xa.n_pushed] = lo;
+                xa.pushed_hi[xa.n_pushed] = lo + (long long)g.m * g.n / 4;
+                xa.n_pushed++;
+            };
+            pushed(w->dw_last);
+            for (int l = L - 2; l >= 0; --l) pushed(w->dw[l]);
+        }
         w->runs++;
         rc = launch_pdl(ctx, wide_xchg_opt_kernel, dim3(grid), 0, xa, pdl);
         w->kernels_per_step = (int)(ctx->launches - launches0);
