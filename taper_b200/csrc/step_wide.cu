@@ -585,7 +585,8 @@ struct WidePlan {
     FoldTable fold{};                // host copy; the device copy lives in the plan's block
     FoldTable* fold_dev = nullptr;
     bool fold_in_group = true;       // the grouped dW launch runs the fold on extra CTAs
-    bool push_in_gemm = true;        // data parallel: the dW epilogues push other ranks' slices into their exchange windows
+    bool push_in_gemm = false;       // data parallel: the dW epilogues push other ranks' slices into their exchange windows
+                                     // (TAPER_WIDE_PUSH_IN_GEMM=1; measured neutral at 2 GPUs: the NVLink stores then lengthen the GEMM)
     bool pdl = true;
     bool weights_fresh = false;
     unsigned long long* stamps = nullptr;    // [2][16] %globaltimer per kernel of the last two steps (tp_step_set_profile)
@@ -750,7 +751,7 @@ static int wide_build(WidePlan* w, Carver& c) {
         return TP_ERR_CUDA;
     }
     { const char* v = getenv("TAPER_WIDE_FOLD_IN_GROUP"); w->fold_in_group = !(v && v[0] == '0'); }
-    { const char* v = getenv("TAPER_WIDE_PUSH_IN_GEMM"); w->push_in_gemm = !(v && v[0] == '0'); }
+    { const char* v = getenv("TAPER_WIDE_PUSH_IN_GEMM"); w->push_in_gemm = v && v[0] == '1'; }
     return TP_OK;
 }
 
