@@ -82,7 +82,8 @@ int tp_trainer_step(tp_trainer* t, const float* images, const float* labels, siz
  * tp_trainer_fetch in FIFO order (at most 8 outstanding) */
 int tp_trainer_step_async(tp_trainer* t, const float* images, const float* labels, size_t batch,
                           const size_t* sample_shape, int ndim, int pinned);
-/* device-resident dataset + on-device batch gather (MNISTDataset::get_batch, src/data/mnist.rs:276-309) */
+/* device-resident dataset + on-device batch gather (MNISTDataset::get_batch, src/data/mnist.rs:276-309); perm: the sample
+ * order, EXACTLY n entries (DataLoader's shuffled indices, src/data/mnist.rs:326-358), or NULL for 0..n-1 */
 int tp_trainer_load_dataset(tp_trainer* t, const float* images, const float* labels, size_t n,
                             const size_t* sample_shape, int ndim, const uint32_t* perm);
 int tp_trainer_step_resident(tp_trainer* t, size_t batch);

@@ -10,7 +10,8 @@ The reference is a Rust crate and no Rust toolchain exists in the build image, s
 itself could not be executed.  The oracle is pinned against every known-answer test the reference's
 own tests hold for this path (``tests/test_oracle_kats.py`` cites each
 ``tests/smoke.rs`` / ``src/loss.rs`` / ``src/optim.rs`` line) and, for everything that is standard
-math, against PyTorch autograd (``tests/golden/gen_golden.py``).  Conv2d / pooling / optimizer
+math, against PyTorch autograd (the ``torch`` cross-checks in ``tests/test_oracle_kats.py``; the ``tests/golden/*.npz``
+vectors are written by ``tests/golden/make_golden.py`` from this oracle: drift guards, not pins).  Conv2d / pooling / optimizer
 *values* are not pinned by any reference test ("parity unpinned" there): the
 restatement following the cited lines is the only pin.
 

@@ -37,7 +37,7 @@ if PEER:
     tr.peer_exchange_init(dist)
 elif not WIDE:
     tr.set_use_fused(False)
-tr.load_dataset(X, Y, shard_permutation(perm, rank, world, b))
+tr.load_dataset(X, Y, np.resize(shard_permutation(perm, rank, world, b), n))    # one entry per sample (the shard's order, repeated)
 local_losses = []
 for s in range(steps):                            # eager, capture (with the allreduce inside the graph), replays
     tr.step_resident(b)
@@ -75,7 +75,9 @@ if not torch.equal(flat, ref0):
     ok = False; print(f"rank {rank}: replica diverged from rank 0")
 flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("DP_CHECK", "OK" if flag.item() == 1 else "FAILED", f"world={world} graph_replays={tr.graph_replays()} fused_kind={tr.fused_kind()}")
+    print("DP_CHECK", "OK" if flag.item() == 1 else "FAILED", f"world={world} graph_replays={tr.graph_replays()} fused_kind={tr.fused_kind()}", flush=True)
+code = 0 if flag.item() == 1 else 1
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if flag.item() == 1 else 1)
+sys.stdout.flush(); sys.stderr.flush()
+os._exit(code)          # no interpreter finalisation: two NCCL instances + CUDA IPC mappings tearing down under it have ended a rank with SIGSEGV

@@ -135,21 +135,27 @@ def main():
         if nph.value == len(names) - 1:               # the fold rode along on extra CTAs of the dW launch
             names.remove("fold")
             names[names.index("dW (all)")] = "dW (all) + fold"
-        buf = np.zeros(32, np.int64)
+        if world > 1 and os.environ.get("TAPER_WIDE_PUSH_IN_GEMM", "0") == "1" and L >= 3:
+            # data parallel: weight gradients interleaved with the dX chain, their epilogues push over NVLink
+            names = ["input"] + [f"fwd{l}" for l in range(L - 1)] + ["head", f"dW{L - 1}+dW{L - 2} (push)"]
+            for l in range(L - 2, 0, -1):
+                names += [f"dX{l}", f"dW{l - 1} (push)" + (" + fold" if l == 1 else "")]
+            names += ["exchange+optimizer"]
+        buf = np.zeros(64, np.int64)
         slots = C.c_int()
         check(lib.tp_step_read_profile(step, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(slots)))
-        prev, last = buf[:16].astype(np.float64), buf[16:].astype(np.float64)
+        prev, last, xprev = buf[:16].astype(np.float64), buf[16:32].astype(np.float64), buf[32:48].astype(np.float64)
         n = len(names)
         print(f"per-kernel time in situ (us, %globaltimer at the end of each kernel's dependency wait; step-to-step {(last[0] - prev[0]) / 1e3:.2f} us)")
         tl = list(prev[:n]) + [last[0]]
         for i, nm in enumerate(names):
             print(f"  {nm:10s} {(tl[i + 1] - tl[i]) / 1e3:7.2f}")
         if world > 1:
-            x = prev[n - 1:n + 6]
+            x = np.concatenate([prev[n - 1:n], xprev[1:7]])
             lab = ["A: push my parts of the other slices", "A: release + raise flags", "A: wait for the peers' flags", "B: reduce my slice + push the result",
                    "B: release + raise + wait", "C: optimizer"]
             print("  exchange kernel, CTA 0 (us): " + " | ".join(f"{l} {(x[i + 1] - x[i]) / 1e3:.2f}" for i, l in enumerate(lab)))
-            y = prev[n - 1:n + 9]
+            y = np.concatenate([prev[n - 1:n], xprev[1:10]])
             print(f"  exchange kernel, last CTA to pass (us after the kernel's start): peers' A flags seen {(y[7] - y[0]) / 1e3:.2f} | peers' B flags seen "
                   f"{(y[8] - y[0]) / 1e3:.2f} | optimizer done {(y[9] - y[0]) / 1e3:.2f}  (CTA 0: {(y[3] - y[0]) / 1e3:.2f} | {(y[5] - y[0]) / 1e3:.2f} | {(y[6] - y[0]) / 1e3:.2f})")
         if dist is not None:

@@ -357,6 +357,7 @@ struct XchgArgs {
     float* peer_slots[kMaxWorld];
     int* err;
     unsigned long long* stamp;
+    unsigned long long* stamp_x;     // profiling: 16 more slots for the kernel's own phases (CTA 0's stamps, latest-CTA stamps)
     // float4 ranges of the arena the weight-gradient GEMMs' epilogues have already pushed (Bx3Push): phase A skips them
     int n_pushed;
     long long pushed_lo[4], pushed_hi[4];
@@ -412,37 +413,54 @@ wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
         return n > 0 ? n : 0;
     };
     // ---- A: my contributions to the other ranks' slices ----
-    for (int j = 0; j < a.world; ++j) {
-        if (j == a.rank) continue;
-        const long long n = chunk_len(j);
-        const float4* src = G4 + (long long)j * a.slice4 + c0;
-        float4* dst = reinterpret_cast<float4*>(a.peer_slots[j] + (long long)a.rank * a.row) + c0;
-        const long long e0 = (long long)j * a.slice4 + c0;         // arena position (float4) of the chunk's first vector
-        bool covered = false;                                      // the whole chunk inside one pushed range: the common case
-        for (int r = 0; r < a.n_pushed; ++r) covered = covered || (e0 >= a.pushed_lo[r] && e0 + n <= a.pushed_hi[r]);
-        if (covered) continue;
-        for (long long i0 = t; i0 < n; i0 += kThreads * 4) {
-            float4 v[4];
-            bool live[4];
+    // One flat index space over (slice j, vector i of chunk c): a thread keeps four independent load -> remote store pairs in
+    // flight whatever the world size (one loop per peer was a chain of world - 1 dependent L2 round trips per CTA: 5.4 us at 8 GPUs)
+    const int ch = (int)a.chunk4;
+    const int flat = a.world * ch;
+    __shared__ int s_len[kMaxWorld];                               // vectors of chunk c that exist in slice q
+    if (t < kMaxWorld) s_len[t] = t < a.world ? (int)chunk_len(t) : 0;
+    __syncthreads();
+    {
+        bool all_pushed = a.n_pushed > 0;                          // every vector of this CTA's chunks already pushed by the GEMMs?
+        for (int j = 0; j < a.world && all_pushed; ++j) {
+            if (j == a.rank) continue;
+            const long long n = chunk_len(j), e0 = (long long)j * a.slice4 + c0;
+            bool covered = n == 0;
+            for (int r = 0; r < a.n_pushed; ++r) covered = covered || (e0 >= a.pushed_lo[r] && e0 + n <= a.pushed_hi[r]);
+            all_pushed = covered;
+        }
+        if (!all_pushed) {
+            const int flat_a = flat - ch;                          // the peers' slices only
+            for (int x0 = t; x0 < flat_a; x0 += kThreads * 4) {
+                float4 v[4];
+                float4* dst[4];
+                bool live[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long i = i0 + u * kThreads;
-                live[u] = i < n;
-                for (int r = 0; r < a.n_pushed; ++r)
-                    if (e0 + i >= a.pushed_lo[r] && e0 + i < a.pushed_hi[r]) live[u] = false;
-                if (live[u]) v[u] = __ldcg(src + i);
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + u * kThreads;
+                    const int jp = x / ch, i = x - jp * ch;
+                    const int j = min(jp + (jp >= a.rank ? 1 : 0), a.world - 1);
+                    live[u] = x < flat_a && i < s_len[j];
+                    const long long e = (long long)j * a.slice4 + c0 + i;         // arena position (float4)
+                    for (int r = 0; r < a.n_pushed; ++r)
+                        if (e >= a.pushed_lo[r] && e < a.pushed_hi[r]) live[u] = false;
+                    if (live[u]) {
+                        v[u] = __ldcg(G4 + e);
+                        dst[u] = reinterpret_cast<float4*>(a.peer_slots[j] + (long long)a.rank * a.row) + c0 + i;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (live[u]) *dst[u] = v[u];
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (live[u]) dst[i0 + u * kThreads] = v[u];
         }
     }
-    stamp_now(a.stamp ? a.stamp + 1 : nullptr);          // CTA 0's phase stamps (profiling only): pushed | flag raised | peers seen | ...
+    stamp_now(a.stamp_x ? a.stamp_x + 1 : nullptr);          // CTA 0's phase stamps (profiling only): pushed | flag raised | peers seen | ...
     raise_flags(a, c);
-    stamp_now(a.stamp ? a.stamp + 2 : nullptr);
+    stamp_now(a.stamp_x ? a.stamp_x + 2 : nullptr);
     // ---- B: reduce my slice in rank order, hand the result to everybody ----
     if (!wait_flags(a, c)) return;       // a peer never arrived: its slot is stale, apply nothing
-    stamp_now(a.stamp ? a.stamp + 3 : nullptr);
-    stamp_max(a.stamp ? a.stamp + 7 : nullptr);
+    stamp_now(a.stamp_x ? a.stamp_x + 3 : nullptr);
+    stamp_max(a.stamp_x ? a.stamp_x + 7 : nullptr);
     {
         const long long n = chunk_len(a.rank);
         const long long res_off = a.slice4;                    // result area of a row starts after its recv area
@@ -474,12 +492,12 @@ wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
             }
         }
     }
-    stamp_now(a.stamp ? a.stamp + 4 : nullptr);
+    stamp_now(a.stamp_x ? a.stamp_x + 4 : nullptr);
     raise_flags(a, C_ + c);
     // ---- C: optimizer on chunk c of every slice ----
     if (!wait_flags(a, C_ + c)) return;
-    stamp_now(a.stamp ? a.stamp + 5 : nullptr);
-    stamp_max(a.stamp ? a.stamp + 8 : nullptr);
+    stamp_now(a.stamp_x ? a.stamp_x + 5 : nullptr);
+    stamp_max(a.stamp_x ? a.stamp_x + 8 : nullptr);
     AdamArgsW aa{};
     if (a.opt_kind != 0) {
         const float* h = a.hyper;
@@ -493,43 +511,43 @@ wide_xchg_opt_kernel(const __grid_constant__ XchgArgs a) {
     float4* P4 = reinterpret_cast<float4*>(a.P);
     float4* M4 = reinterpret_cast<float4*>(a.M);
     float4* V4 = reinterpret_cast<float4*>(a.V);
-    for (int q = 0; q < a.world; ++q) {
-        const long long n = chunk_len(q);
-        const float4* res = reinterpret_cast<const float4*>(a.my_slots + (long long)q * a.row) + a.slice4 + c0;
-        const long long e0 = (long long)q * a.slice4 + c0;
-        for (long long i0 = t; i0 < n; i0 += kThreads * 4) {                 // four vectors (gradient, p, m, v) in flight per thread
-            float4 gg[4], pp[4], mm[4], vv[4];
+    // flat index space over (slice q, vector i of chunk c) again: four (gradient, p, m, v) quadruples in flight per thread
+    for (int x0 = t; x0 < flat; x0 += kThreads * 4) {
+        float4 gg[4], pp[4], mm[4], vv[4];
+        long long ee[4];
+        bool live[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long i = i0 + u * kThreads;
-                if (i < n) {
-                    gg[u] = __ldcg(res + i);
-                    pp[u] = P4[e0 + i];
-                    if (a.opt_kind != 0) { mm[u] = M4[e0 + i]; vv[u] = V4[e0 + i]; }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long i = i0 + u * kThreads;
-                if (i >= n) continue;
-                if (a.opt_kind == 0) {
-                    if (a.grad_scale != 1.0f) { gg[u].x *= a.grad_scale; gg[u].y *= a.grad_scale; gg[u].z *= a.grad_scale; gg[u].w *= a.grad_scale; }
-                    pp[u].x -= a.sgd_lr * gg[u].x; pp[u].y -= a.sgd_lr * gg[u].y;                                      // src/optim.rs:29
-                    pp[u].z -= a.sgd_lr * gg[u].z; pp[u].w -= a.sgd_lr * gg[u].w;
-                } else {
-                    adam_elem_w(pp[u].x, gg[u].x, mm[u].x, vv[u].x, aa);
-                    adam_elem_w(pp[u].y, gg[u].y, mm[u].y, vv[u].y, aa);
-                    adam_elem_w(pp[u].z, gg[u].z, mm[u].z, vv[u].z, aa);
-                    adam_elem_w(pp[u].w, gg[u].w, mm[u].w, vv[u].w, aa);
-                    M4[e0 + i] = mm[u]; V4[e0 + i] = vv[u];
-                }
-                P4[e0 + i] = pp[u];
-                split_store4(a.hi + 4 * (e0 + i), a.lo + 4 * (e0 + i), pp[u].x, pp[u].y, pp[u].z, pp[u].w);
+        for (int u = 0; u < 4; ++u) {
+            const int x = x0 + u * kThreads;
+            const int q = x / ch, i = x - q * ch;
+            live[u] = x < flat && i < s_len[q];
+            ee[u] = (long long)q * a.slice4 + c0 + i;
+            if (live[u]) {
+                gg[u] = __ldcg(reinterpret_cast<const float4*>(a.my_slots + (long long)q * a.row) + a.slice4 + c0 + i);
+                pp[u] = P4[ee[u]];
+                if (a.opt_kind != 0) { mm[u] = M4[ee[u]]; vv[u] = V4[ee[u]]; }
             }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!live[u]) continue;
+            if (a.opt_kind == 0) {
+                if (a.grad_scale != 1.0f) { gg[u].x *= a.grad_scale; gg[u].y *= a.grad_scale; gg[u].z *= a.grad_scale; gg[u].w *= a.grad_scale; }
+                pp[u].x -= a.sgd_lr * gg[u].x; pp[u].y -= a.sgd_lr * gg[u].y;                                      // src/optim.rs:29
+                pp[u].z -= a.sgd_lr * gg[u].z; pp[u].w -= a.sgd_lr * gg[u].w;
+            } else {
+                adam_elem_w(pp[u].x, gg[u].x, mm[u].x, vv[u].x, aa);
+                adam_elem_w(pp[u].y, gg[u].y, mm[u].y, vv[u].y, aa);
+                adam_elem_w(pp[u].z, gg[u].z, mm[u].z, vv[u].z, aa);
+                adam_elem_w(pp[u].w, gg[u].w, mm[u].w, vv[u].w, aa);
+                M4[ee[u]] = mm[u]; V4[ee[u]] = vv[u];
+            }
+            P4[ee[u]] = pp[u];
+            split_store4(a.hi + 4 * ee[u], a.lo + 4 * ee[u], pp[u].x, pp[u].y, pp[u].z, pp[u].w);
+        }
     }
-    stamp_now(a.stamp ? a.stamp + 6 : nullptr);
-    stamp_max(a.stamp ? a.stamp + 9 : nullptr);
+    stamp_now(a.stamp_x ? a.stamp_x + 6 : nullptr);
+    stamp_max(a.stamp_x ? a.stamp_x + 9 : nullptr);
 }
 
 template <typename Kern, typename Arg>
@@ -802,8 +820,8 @@ int wide_create(tp_ctx* ctx, const tp_step_desc* desc, float* P, float* G, float
 int wide_set_profile(WidePlan* w, int on) {
     cudaSetDevice(w->ctx->device);
     if (on && !w->stamps) {
-        TP_CUDA(cudaMalloc(&w->stamps, 32 * sizeof(unsigned long long)));
-        TP_CUDA(cudaMemsetAsync(w->stamps, 0, 32 * sizeof(unsigned long long), w->ctx->stream));
+        TP_CUDA(cudaMalloc(&w->stamps, 64 * sizeof(unsigned long long)));
+        TP_CUDA(cudaMemsetAsync(w->stamps, 0, 64 * sizeof(unsigned long long), w->ctx->stream));
     }
     w->profile = on != 0;
     return TP_OK;
@@ -814,10 +832,12 @@ int wide_read_profile(WidePlan* w, long long* out, size_t cap, int* slots) {
     if (!w->stamps || cap < 32) { set_error("tp_step_read_profile: profiling is off or the buffer is too small"); return TP_ERR_INVALID; }
     cudaSetDevice(w->ctx->device);
     TP_CUDA(cudaStreamSynchronize(w->ctx->stream));
-    unsigned long long h[32];
+    unsigned long long h[64];                          // per parity: 16 kernel slots, then 16 slots of the exchange kernel's phases
     TP_CUDA(cudaMemcpy(h, w->stamps, sizeof h, cudaMemcpyDeviceToHost));
     const int last = (w->runs + 1) & 1;                // parity of the last run
-    for (int i = 0; i < 16; ++i) { out[i] = (long long)h[(last ^ 1) * 16 + i]; out[16 + i] = (long long)h[last * 16 + i]; }
+    for (int i = 0; i < 16; ++i) { out[i] = (long long)h[(last ^ 1) * 32 + i]; out[16 + i] = (long long)h[last * 32 + i]; }
+    if (cap >= 64)                                     // out[32..47] / out[48..63]: the exchange kernel's phase stamps of the same two runs
+        for (int i = 0; i < 16; ++i) { out[32 + i] = (long long)h[(last ^ 1) * 32 + 16 + i]; out[48 + i] = (long long)h[last * 32 + 16 + i]; }
     if (slots) *slots = 16;
     return TP_OK;
 }
@@ -858,7 +878,7 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         w->weights_fresh = true;
     }
     const uint64_t launches0 = ctx->launches;
-    unsigned long long* st = w->profile ? w->stamps + (w->runs & 1) * 16 : nullptr;
+    unsigned long long* st = w->profile ? w->stamps + (w->runs & 1) * 32 : nullptr;
     int slot = 0;
     auto next_stamp = [&]() { return st ? st + (slot < 15 ? slot++ : 15) : nullptr; };
     InputArgs ia{};
@@ -885,18 +905,56 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
     rc = d.dims[L] == 10 ? launch_pdl(ctx, wide_head_kernel<10>, dim3(w->head_grid), w->head_smem, ha, pdl)
                          : launch_pdl(ctx, wide_head_kernel<kMaxOut>, dim3(w->head_grid), w->head_smem, ha, pdl);
     if (rc) return rc;
-    for (int l = L - 2; l > 0; --l) {                  // the dX chain: dZ_{L-2} -> ... -> dZ_0
-        w->dx[l].stamp = next_stamp();
-        rc = bx3_launch(ctx, w->dx[l], pdl);
-        if (rc) return rc;
-    }
     FoldStep fs{};
     fs.table = w->fold_dev;
     fs.result_host = result_host;
     fs.result_seq = result_host ? result_seq : 0u;
     fs.cursor = perm ? cursor : nullptr;
     fs.cursor_delta = B; fs.cursor_mod = n_perm > 0 ? n_perm : 1;
-    {
+    Bx3Push push{};
+    if (xc && w->push_in_gemm) {
+        // data parallel: the weight-gradient epilogues store every vector that belongs to another rank's slice straight into that
+        // rank's exchange window — the reduce-scatter's NVLink traffic rides on the GEMMs' stores
+        const size_t par = xc->seq & 1u;
+        const long long slice4 = (d.arena_len / 4 + xc->world - 1) / xc->world;
+        push.base = w->G;
+        push.slice = (unsigned int)(slice4 * 4);
+        push.world = xc->world; push.rank = xc->rank;
+        for (int r = 0; r < xc->world; ++r)
+            push.peer[r] = r == xc->rank ? nullptr
+                                         : reinterpret_cast<float*>(xc->peers[r] + xc->slots_off) + par * xc->world * xc->row + (size_t)xc->rank * xc->row;
+    }
+    const Bx3Push* pp = push.world > 1 ? &push : nullptr;
+    bool folded = false;
+    if (pp && L >= 3) {
+        // ... and the weight gradients are INTERLEAVED with the dX chain instead of following it: dW_l only needs dZ_l, so it is
+        // launched as soon as dZ_l exists, and its pushes cross NVLink while the next dX / dW kernels compute (at 8 GPUs the
+        // pushes of all gradients at the end of the backward pass cost 25-35 us of exposed NVLink time).  One more launch than the
+        // grouped form.  A dW kernel now directly follows the producer of its dZ operand: no early request of that operand.
+        Bx3Launch first_last = w->dw_last, first_dw = w->dw[L - 2];
+        first_last.a_early = false; first_dw.a_early = false;
+        first_last.stamp = next_stamp(); first_dw.stamp = nullptr;
+        const Bx3Launch* g1[2] = {&first_last, &first_dw};
+        rc = bx3_launch_group(ctx, g1, 2, pdl, nullptr, nullptr, pp);
+        if (rc) return rc;
+        for (int l = L - 2; l > 0; --l) {
+            w->dx[l].stamp = next_stamp();
+            rc = bx3_launch(ctx, w->dx[l], pdl);                   // dZ_{l-1}
+            if (rc) return rc;
+            Bx3Launch g = w->dw[l - 1];
+            g.a_early = false;
+            g.stamp = next_stamp();
+            const Bx3Launch* one[1] = {&g};
+            const bool last = l == 1;
+            rc = bx3_launch_group(ctx, one, 1, pdl, last && w->fold_in_group ? &fs : nullptr, last ? &folded : nullptr, pp);
+            if (rc) return rc;
+        }
+    } else {
+        for (int l = L - 2; l > 0; --l) {                  // the dX chain: dZ_{L-2} -> ... -> dZ_0
+            w->dx[l].stamp = next_stamp();
+            rc = bx3_launch(ctx, w->dx[l], pdl);
+            if (rc) return rc;
+        }
         // every weight gradient: independent of each other, so compatible ones share a launch — and a few extra CTAs of that
         // launch fold the bias-gradient partials and publish the step's results (everything they read is complete by then)
         const Bx3Launch* all[TP_STEP_MAX_LAYERS + 1];
@@ -904,27 +962,13 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         w->dw_last.stamp = next_stamp();
         all[n++] = &w->dw_last;
         for (int l = L - 2; l >= 0; --l) { w->dw[l].stamp = nullptr; all[n++] = &w->dw[l]; }
-        bool folded = false;
-        Bx3Push push{};
-        if (xc && w->push_in_gemm) {
-            // data parallel: the epilogues store every vector that belongs to another rank's slice straight into that rank's
-            // exchange window, so the reduce-scatter's NVLink traffic overlaps the remaining tiles instead of following them
-            const size_t par = xc->seq & 1u;
-            const long long slice4 = (d.arena_len / 4 + xc->world - 1) / xc->world;
-            push.base = w->G;
-            push.slice = (unsigned int)(slice4 * 4);
-            push.world = xc->world; push.rank = xc->rank;
-            for (int r = 0; r < xc->world; ++r)
-                push.peer[r] = r == xc->rank ? nullptr
-                                             : reinterpret_cast<float*>(xc->peers[r] + xc->slots_off) + par * xc->world * xc->row + (size_t)xc->rank * xc->row;
-        }
-        rc = bx3_launch_group(ctx, all, n, pdl, w->fold_in_group ? &fs : nullptr, &folded, push.world > 1 ? &push : nullptr);
+        rc = bx3_launch_group(ctx, all, n, pdl, w->fold_in_group ? &fs : nullptr, &folded, pp);
         if (rc) return rc;
-        if (!folded) {
-            fs.stamp = next_stamp();
-            rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold.n_blocks < 2 * ctx->sm_count ? w->fold.n_blocks : 2 * ctx->sm_count), 0, fs, pdl);
-            if (rc) return rc;
-        }
+    }
+    if (!folded) {
+        fs.stamp = next_stamp();
+        rc = launch_pdl(ctx, wide_fold_kernel, dim3(w->fold.n_blocks < 2 * ctx->sm_count ? w->fold.n_blocks : 2 * ctx->sm_count), 0, fs, pdl);
+        if (rc) return rc;
     }
     if (xc) {
         // allreduce + optimizer as one kernel over NVLink peer memory (reduce-scatter, all-gather, update)
@@ -951,6 +995,7 @@ int wide_run(WidePlan* w, const void* x, int x_is_u8, const float* labels, const
         }
         xa.err = ctx->dev_error;
         xa.stamp = next_stamp();
+        xa.stamp_x = st ? st + 16 : nullptr;
         xa.n_pushed = 0;
         if (w->push_in_gemm) {
             auto pushed = [&](const Bx3Launch& g) {
