@@ -128,7 +128,10 @@ mlp_small_fwd_kernel(const __grid_constant__ MlpArgs a) {
             const float* w1 = ws[l] + (og + og_n) * wp;
             const float* w2 = ws[l] + (og + 2 * og_n) * wp;
             const float* w3 = ws[l] + (og + 3 * og_n) * wp;
-            float acc[2][4];
+            float acc[2][4], bj[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)                               // requested before the k loop: the round trip hides behind it
+                bj[j] = (bias && og + og_n * j < out) ? __ldg(bias + og + og_n * j) : 0.0f;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -145,12 +148,11 @@ mlp_small_fwd_kernel(const __grid_constant__ MlpArgs a) {
             for (int j = 0; j < 4; ++j) {
                 const int o = og + og_n * j;
                 if (o >= out) continue;
-                const float bj = bias ? __ldg(bias + o) : 0.0f;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int r = 2 * rg + i;
                     float v = acc[i][j];
-                    if (bias) v += bj;
+                    if (bias) v += bj[j];
                     if (a.relu[l]) v = fmaxf(v, 0.0f);
                     nxt[r * kXP + o] = v;
                     if (r < rows) a.act[l][(size_t)(r0 + r) * out + o] = v;

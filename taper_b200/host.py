@@ -250,8 +250,8 @@ class Trainer:
         p = None
         if perm is not None:
             perm = np.ascontiguousarray(perm, dtype=np.uint32)
-            if perm.size != images.shape[0]:          # the C ABI reads one entry per sample
-                raise ValueError(f"load_dataset: perm has {perm.size} entries for {images.shape[0]} samples")
+            if perm.size != images_u8.shape[0]:       # the C ABI reads one entry per sample
+                raise ValueError(f"load_dataset_u8: perm has {perm.size} entries for {images_u8.shape[0]} samples")
             p = perm.ctypes.data_as(C.POINTER(C.c_uint32))
         check(lib.tp_trainer_load_dataset_u8(self.h, images_u8.ctypes.data_as(C.c_void_p), _fp(labels), images_u8.shape[0],
                                              _shape(images_u8.shape[1:]), images_u8.ndim - 1, p))
