@@ -233,3 +233,33 @@ def ctx():
     c = taper_b200.Ctx(0)
     yield c
     c.close()
+
+
+def test_load_dataset_rejects_a_permutation_that_does_not_cover_the_dataset():
+    """tp_trainer_load_dataset[_u8] reads one permutation entry per sample (include/taper_b200_host.h): a shorter array — e.g. a
+    data-parallel shard's order handed over as it is — would be read out of bounds, so the Python layer refuses it, and a
+    permutation padded to n entries by repeating the shard's order walks the shard's rows."""
+    from taper_b200 import host
+    from taper_b200.dp import shard_permutation
+    dims, spec = SMALL
+    rng = np.random.default_rng(3)
+    n, b = 512, 64
+    X = rng.random((n, 784)).astype(F32)
+    Xu = rng.integers(0, 256, (n, 784)).astype(np.uint8)
+    Y = rng.integers(0, 10, n).astype(F32)
+    perm = rng.permutation(n)
+    shard = shard_permutation(perm, 1, 2, b)
+    assert shard.size == n // 2
+    ms = [host.Model(spec, 0), host.Model(spec, 0)]
+    ts = [host.Trainer(m, "sgd", lr=0.05) for m in ms]
+    with pytest.raises(ValueError):
+        ts[0].load_dataset(X, Y, shard)
+    with pytest.raises(ValueError):
+        ts[0].load_dataset_u8(Xu, Y, shard)
+    ts[0].load_dataset(X, Y, np.resize(shard, n))
+    for s in range(3):
+        idx = shard[s * b:(s + 1) * b]
+        ts[0].step_resident(b)
+        r0 = ts[0].fetch()
+        r1 = ts[1].step(X[idx], Y[idx])
+        assert r0[0] == pytest.approx(r1[0], rel=1e-6) and r0[1] == r1[1], (s, r0, r1)
